@@ -1,0 +1,140 @@
+/* physecs_b200 -- C ABI of the B200 (sm_100a) implementation of Physecs' per-step pipeline.
+ *
+ * This is the drop-in boundary: the host-side physecs::Scene mirror (physecs_b200/host/) binds to
+ * exactly these entry points, and they are what a maintainer of the reference would call from
+ * physecs::Scene::simulate (reference src/Physecs.cpp:112-561) instead of the CPU stages.
+ * Plain pointers and sizes only; caller-owned host buffers (pinned recommended, see pb_host_alloc);
+ * device memory is owned by the context.  Every function returns 0 on success or a PB_E* code and
+ * never falls back to a CPU path: without a CUDA device pb_ctx_create fails.
+ *
+ * Index spaces
+ *   body row   : rows [0, n_dynamic) are the packed RigidBodyDynamicComponent storage order
+ *                (the reference's b0/b1 index space, src/Physecs.cpp:116-117, :271-272);
+ *                rows [n_dynamic, n_dynamic+n_static) are entities with colliders but no dynamic component.
+ *   collider   : one row per (entity, colliderIndex) -- the reference's BroadPhaseEntry (Physecs.h:80-88).
+ *   quaternions: x,y,z,w in memory (glm::quat layout, reference src/Transform.h:6-10).
+ *   mat3       : column-major 9 floats (glm::mat3).
+ */
+#ifndef PHYSECS_B200_H
+#define PHYSECS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+enum {
+    PB_OK = 0,
+    PB_ECUDA = 1,        /* CUDA runtime error (message in pb_last_error) */
+    PB_ECAPACITY = 2,    /* a per-step arena overflowed (pairs / manifolds / triangle contacts); results of the step are invalid */
+    PB_EINVAL = 3,       /* bad argument */
+    PB_EUNSUPPORTED = 4  /* feature of the reference not available on the device path (message says which) */
+};
+
+/* geometry types == physecs::GeometryType (reference include/Physecs/Colliders.h:9) */
+enum { PB_SPHERE = 0, PB_CAPSULE = 1, PB_BOX = 2, PB_CONVEX_MESH = 3, PB_TRIANGLE_MESH = 4 };
+/* joint types (reference include/Physecs/Joints/*.h) */
+enum { PB_JOINT_FIXED = 0, PB_JOINT_REVOLUTE = 1, PB_JOINT_SPHERICAL = 2, PB_JOINT_UNIVERSAL = 3,
+       PB_JOINT_PRISMATIC = 4, PB_JOINT_GEAR = 5, PB_JOINT_SERVO = 6 };
+/* collider flag bits */
+enum { PB_COL_TRIGGER = 1, PB_COL_ENABLE_SIM = 2 };
+
+typedef struct pb_caps {
+    int max_bodies;      /* dynamic + static rows */
+    int max_colliders;
+    int max_pairs;       /* candidate pairs per step (potentialContacts) */
+    int max_manifolds;   /* contact manifolds per step */
+    int max_joints;
+    int reserved[3];
+} pb_caps;
+
+/* per-step counters (pb_get_counts) */
+typedef struct pb_counts {
+    int n_pairs;         /* broadphase candidate pairs (== reference potentialContacts.size()) */
+    int n_manifolds;     /* contact manifolds with >=1 point (== contactConstraints.size()) */
+    int n_points;        /* contact points */
+    int n_colors;        /* contact colours used this step */
+    int n_overflow;      /* manifolds in the sequential overflow bucket (colour 63) */
+    int status;          /* PB_OK or PB_ECAPACITY */
+    int n_mesh_pairs;
+    int n_triggers;
+} pb_counts;
+
+/* device times of the last pb_step in milliseconds (CUDA events on the context's stream) */
+typedef struct pb_timings {
+    float broadphase, narrowphase, contact_build, solve, total;
+    float reserved[3];
+} pb_timings;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int  pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out);
+void pb_ctx_destroy(pb_ctx* ctx);
+const char* pb_last_error(pb_ctx* ctx);
+int  pb_host_alloc(void** ptr, unsigned long long bytes);   /* pinned host staging */
+void pb_host_free(void* ptr);
+void* pb_stream(pb_ctx* ctx);                                /* cudaStream_t the context launches on */
+
+/* ---- scene description (replaces the reference's registry walks: Physecs.cpp:25-98 signal hooks) - */
+/* entity[n_dynamic+n_static]: entt::entity integer of each row (pair ordering + same-entity test,
+ * Physecs.cpp:145,:158).  kinematic/vel/angvel/inv_mass/com/inv_inertia: n_dynamic rows
+ * (RigidBodyDynamicComponent, reference include/Physecs/Components.h:10-17). */
+int pb_upload_bodies(pb_ctx* ctx, int n_dynamic, int n_static, const int* entity, const float* pos3,
+                     const float* quat4, const int* kinematic, const float* vel3, const float* angvel3,
+                     const float* inv_mass, const float* com3, const float* inv_inertia9);
+/* One row per collider (reference Collider, include/Physecs/Colliders.h:50-58). params4: sphere {r},
+ * capsule {halfHeight, r}, box {hx,hy,hz}, convex {sx,sy,sz}; mesh: handle from pb_register_*.
+ * material3 = {friction, restitution, damping}. Creation-time bounds carry no margin (Physecs.cpp:32). */
+int pb_upload_colliders(pb_ctx* ctx, int n, const int* body_row, const int* collider_index,
+                        const float* local_pos3, const float* local_quat4, const int* type,
+                        const float* params4, const int* mesh, const float* material3, const int* flags,
+                        const int* data);
+/* Convex mesh (reference ConvexMesh, include/Physecs/ConvexMesh.h:29-34): faces as index loops. */
+int pb_register_convex(pb_ctx* ctx, const float* verts3, int n_verts, const int* face_offsets,
+                       const int* face_indices, int n_faces, const float* face_normals3,
+                       const float* face_centroids3, int* handle);
+/* Static triangle mesh.  Builds, on the host at registration time, the same binned-SAH BVH the reference
+ * TriangleMesh constructor builds (src/TriangleMesh.cpp:99-164) so post-build triangle indices (part of the
+ * contact-cache key) agree; tri_order_out (optional, n_tris ints) receives original index of each built triangle. */
+int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int n_verts, const unsigned* indices, int n_indices,
+                        int* handle, int* tri_order_out);
+/* joints: params per type -- revolute {driveEnabled, driveVelocity, driveMaxTorque}; prismatic {upper, lower,
+ * driveEnabled, targetPosition, stiffness, damping}; gear {ratio}; servo {targetAngle, stiffness, damping}.
+ * color[n]: colour assigned by the host-side greedy colouring (reference Physecs.cpp:690-710), 8 = overflow. */
+int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* body_row0, const int* body_row1,
+                     const float* anchor0_pos3, const float* anchor0_quat4, const float* anchor1_pos3,
+                     const float* anchor1_quat4, const float* params8, const int* color);
+/* entity pairs that must not collide (reference nonCollidingPairs, Physecs.cpp:209,:694,:788): rows (e0<e1) */
+int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* entity_pairs2);
+
+/* ---- per-step state exchange ---------------------------------------------------------------------- */
+/* push registry state of the dynamic rows (what the reference reads through registry.get each step) */
+int pb_set_state(pb_ctx* ctx, int n_dynamic, const float* pos3, const float* quat4, const float* vel3,
+                 const float* angvel3);
+/* a static/kinematic row was moved through registry.patch<TransformComponent> (Physecs.cpp:51-54,:79-90):
+ * new transform + bounds refresh with the 0.01 margin */
+int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4);
+/* recompute bounds (+0.01 margin) of every collider of a non-kinematic dynamic body, as the end of
+ * simulate does (Physecs.cpp:556-559); used after pb_set_state when the caller wants bounds to follow */
+int pb_refresh_bounds(pb_ctx* ctx);
+/* == physecs::Scene::simulate(timeStep) with the scene's knobs (Physecs.cpp:100-110, :112-561) */
+int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
+int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3);
+int pb_sync(pb_ctx* ctx);
+
+/* ---- parity / debug taps ----------------------------------------------------------------------------- */
+int pb_get_counts(pb_ctx* ctx, pb_counts* out);
+int pb_get_timings(pb_ctx* ctx, pb_timings* out);
+/* candidate pairs of the last step as rows (entity0, colIdx0, entity1, colIdx1), entity0 < entity1 */
+int pb_get_pairs(pb_ctx* ctx, int* out4, int cap, int* n);
+/* collider bounds rows (min xyz, max xyz) in collider order */
+int pb_get_bounds(pb_ctx* ctx, float* out6);
+/* manifolds of the last step in SOLVE ORDER (colour-major): keys rows (entity0, colIdx0, entity1, colIdx1, tri),
+ * num_points, normal3, points rows [4][2][3] world space at narrowphase time, color */
+int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* num_points, float* normal3, float* points24,
+                     int* color, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

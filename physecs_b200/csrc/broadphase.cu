@@ -1,0 +1,332 @@
+// Broadphase: per-collider world AABBs, 30-bit Morton keys, radix sort, Karras LBVH build, bottom-up
+// refit and a stack traversal that emits overlapping collider pairs through warp-aggregated appends.
+//
+// Replaces (reference, /root/reference):
+//   Scene::updateBounds            src/Physecs.cpp:79-90   + getBounds*  src/BoundsUtil.cpp:23-85
+//   SAP insertion sort + sweep      src/Physecs.cpp:119-173 (pair predicates :138-154, ordering :158-168)
+// The pair SET is identical to the sweep's: two closed AABBs overlap on all three axes, both colliders
+// have enableSimulation, they belong to different entities and at least one owner is a non-kinematic
+// dynamic body.  Built with -fmad=false so bounds equal the reference's fp32 values bit for bit.
+#include "pb_ctx.h"
+#include "pb_math.cuh"
+#include "np_bounds.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define COLF_TRIGGER 1
+#define COLF_ENABLE 2
+#define COLF_DYNAMIC 4
+
+// ---- ordered-int float encoding for atomic min/max -------------------------------------------------------
+__device__ __forceinline__ int floatToOrdered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float orderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// mode 0: all colliders; mode 1: colliders of non-kinematic dynamic bodies; mode 2: colliders whose row is flagged in rowMark
+__global__ void k_update_bounds(int n, int mode, const int* __restrict__ rowMark, float margin,
+                                const int* __restrict__ colRow, const int* __restrict__ colType, const int* __restrict__ colFlags,
+                                const int* __restrict__ colMesh, const float4* __restrict__ colLPos, const float4* __restrict__ colLQuat,
+                                const float4* __restrict__ colParams, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                                const PbConvexDev* __restrict__ convexes, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int type = colType[i];
+    if (type == PB_TRIANGLE_MESH) return;  // separate reduction kernel
+    int flags = colFlags[i];
+    int row = colRow[i];
+    if (mode == 1 && !(flags & COLF_DYNAMIC)) return;
+    if (mode == 2 && !rowMark[row]) return;
+    V3 bp = mk3(pos[row]); Q4 bq = mkq(quat[row]);
+    V3 wp = bp + rotate(bq, mk3(colLPos[i]));
+    Q4 wq = qmul(bq, mkq(colLQuat[i]));
+    Aabb b = shapeBounds(wp, wq, type, colParams[i], convexes, colMesh[i]);
+    b.mx = b.mx + mk3(margin);
+    b.mn = b.mn - mk3(margin);
+    aabbMin[i] = f4(b.mn); aabbMax[i] = f4(b.mx);
+}
+
+// getBoundsTriangleMesh (BoundsUtil.cpp:77-85): min/max over every transformed vertex
+__global__ void k_trimesh_bounds(int col, const int* __restrict__ colRow, const float4* __restrict__ colLPos,
+                                 const float4* __restrict__ colLQuat, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                                 const float4* __restrict__ verts, int nVerts, int* __restrict__ acc) {
+    int row = colRow[col];
+    V3 bp = mk3(pos[row]); Q4 bq = mkq(quat[row]);
+    V3 wp = bp + rotate(bq, mk3(colLPos[col]));
+    Q4 wq = qmul(bq, mkq(colLQuat[col]));
+    V3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nVerts; i += gridDim.x * blockDim.x) {
+        V3 p = wp + rotate(wq, mk3(verts[i]));
+        mn = vmin(mn, p); mx = vmax(mx, p);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, d)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, d));
+        mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, d));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, d));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&acc[0], floatToOrdered(mn.x)); atomicMin(&acc[1], floatToOrdered(mn.y)); atomicMin(&acc[2], floatToOrdered(mn.z));
+        atomicMax(&acc[3], floatToOrdered(mx.x)); atomicMax(&acc[4], floatToOrdered(mx.y)); atomicMax(&acc[5], floatToOrdered(mx.z));
+    }
+}
+__global__ void k_trimesh_bounds_init(int* acc) {
+    if (threadIdx.x < 3) acc[threadIdx.x] = floatToOrdered(FLT_MAX);
+    else if (threadIdx.x < 6) acc[threadIdx.x] = floatToOrdered(-FLT_MAX);
+}
+__global__ void k_trimesh_bounds_store(int col, float margin, const int* __restrict__ acc, float4* aabbMin, float4* aabbMax) {
+    V3 mn = mk3(orderedToFloat(acc[0]), orderedToFloat(acc[1]), orderedToFloat(acc[2]));
+    V3 mx = mk3(orderedToFloat(acc[3]), orderedToFloat(acc[4]), orderedToFloat(acc[5]));
+    mx = mx + mk3(margin); mn = mn - mk3(margin);
+    aabbMin[col] = f4(mn); aabbMax[col] = f4(mx);
+}
+
+static int launchTrimeshBounds(pb_ctx* ctx, int col, float margin) {
+    int mesh = ctx->hColMesh[col];
+    const PbTriMesh& tm = ctx->triMeshes[mesh];
+    int* acc = (int*)ctx->sceneBounds + 8;
+    k_trimesh_bounds_init<<<1, 32, 0, ctx->stream>>>(acc);
+    int blocks = pb_grid(tm.nVerts, 256); if (blocks > 1024) blocks = 1024;
+    k_trimesh_bounds<<<blocks, 256, 0, ctx->stream>>>(col, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, tm.verts, tm.nVerts, acc);
+    k_trimesh_bounds_store<<<1, 1, 0, ctx->stream>>>(col, margin, acc, ctx->aabbMin, ctx->aabbMax);
+    return PB_OK;
+}
+
+int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic) {
+    if (ctx->nCol == 0) return PB_OK;
+    k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, onlyDynamic ? 1 : 0, nullptr, margin, ctx->colRow, ctx->colType,
+        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
+    if (!onlyDynamic) {
+        auto& types = ctx->hColType;
+        for (int c = 0; c < ctx->nCol; ++c) if (types[c] == PB_TRIANGLE_MESH) launchTrimeshBounds(ctx, c, margin);
+    }
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+// rows moved through registry.patch: dRowMark[row] != 0 marks them (device array of nRows ints)
+int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin) {
+    if (ctx->nCol == 0) return PB_OK;
+    k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, 2, dRowMark, margin, ctx->colRow, ctx->colType,
+        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin) { return launchTrimeshBounds(ctx, col, margin); }
+
+// world pose of every collider (Physecs.cpp:194-198), refreshed once per step for the narrowphase
+__global__ void k_world_pose(int n, const int* __restrict__ colRow, const float4* __restrict__ colLPos, const float4* __restrict__ colLQuat,
+                             const float4* __restrict__ pos, const float4* __restrict__ quat, float4* __restrict__ wpos, float4* __restrict__ wquat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int row = colRow[i];
+    V3 bp = mk3(pos[row]); Q4 bq = mkq(quat[row]);
+    wpos[i] = f4(bp + rotate(bq, mk3(colLPos[i])));
+    wquat[i] = f4(qmul(bq, mkq(colLQuat[i])));
+}
+int pb_world_poses(pb_ctx* ctx) {
+    if (ctx->nCol == 0) return PB_OK;
+    k_world_pose<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, ctx->colWPos, ctx->colWQuat);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+// ---- Morton keys --------------------------------------------------------------------------------------------------
+__global__ void k_scene_bounds_init(int* sb) {
+    if (threadIdx.x < 3) sb[threadIdx.x] = floatToOrdered(FLT_MAX);
+    else if (threadIdx.x < 6) sb[threadIdx.x] = floatToOrdered(-FLT_MAX);
+}
+__global__ void k_scene_bounds(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, int* __restrict__ sb) {
+    V3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 c = (mk3(aabbMin[i]) + mk3(aabbMax[i])) * 0.5f;
+        // clamp so a single huge static (terrain, ground) does not flatten the key space
+        mn = vmin(mn, c); mx = vmax(mx, c);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, d)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, d));
+        mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, d));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, d));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&sb[0], floatToOrdered(mn.x)); atomicMin(&sb[1], floatToOrdered(mn.y)); atomicMin(&sb[2], floatToOrdered(mn.z));
+        atomicMax(&sb[3], floatToOrdered(mx.x)); atomicMax(&sb[4], floatToOrdered(mx.y)); atomicMax(&sb[5], floatToOrdered(mx.z));
+    }
+}
+__device__ __forceinline__ unsigned int expandBits(unsigned int v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const int* __restrict__ sb,
+                         unsigned int* __restrict__ keys, int* __restrict__ ids) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 lo = mk3(orderedToFloat(sb[0]), orderedToFloat(sb[1]), orderedToFloat(sb[2]));
+    V3 hi = mk3(orderedToFloat(sb[3]), orderedToFloat(sb[4]), orderedToFloat(sb[5]));
+    V3 c = (mk3(aabbMin[i]) + mk3(aabbMax[i])) * 0.5f;
+    V3 ext = hi - lo;
+    float sx = ext.x > 0.f ? 1024.f / ext.x : 0.f, sy = ext.y > 0.f ? 1024.f / ext.y : 0.f, sz = ext.z > 0.f ? 1024.f / ext.z : 0.f;
+    unsigned int x = (unsigned int)fminf(fmaxf((c.x - lo.x) * sx, 0.f), 1023.f);
+    unsigned int y = (unsigned int)fminf(fmaxf((c.y - lo.y) * sy, 0.f), 1023.f);
+    unsigned int z = (unsigned int)fminf(fmaxf((c.z - lo.z) * sz, 0.f), 1023.f);
+    keys[i] = (expandBits(x) << 2) | (expandBits(y) << 1) | expandBits(z);
+    ids[i] = i;
+}
+
+// ---- Karras LBVH ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int deltaKey(const unsigned int* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned int a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((unsigned int)i ^ (unsigned int)j);
+    return __clz(a ^ b);
+}
+
+// child encoding: >= 0 internal node index, < 0 leaf: ~(sorted leaf position)
+__global__ void k_lbvh_build(int n, const unsigned int* __restrict__ keys, int* __restrict__ left, int* __restrict__ right,
+                             int* __restrict__ parent, int* __restrict__ leafParent, int* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    flag[i] = 0;
+    int d = (deltaKey(keys, n, i, i + 1) - deltaKey(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = deltaKey(keys, n, i, i - d);
+    int lmax = 2;
+    while (deltaKey(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (deltaKey(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = deltaKey(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (deltaKey(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int lc = (lo == gamma) ? ~gamma : gamma;
+    int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = lc; right[i] = rc;
+    if (lc >= 0) parent[lc] = i; else leafParent[~lc] = i;
+    if (rc >= 0) parent[rc] = i; else leafParent[~rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// node layout for traversal: nodeMin[2*i] = left child box min (w = left child), nodeMax[2*i] = left box max (w = right child)
+//                            nodeMin[2*i+1] = right child box min,                nodeMax[2*i+1] = right box max
+// leaf children are re-encoded as ~colliderIndex so the traversal needs no indirection.
+__global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* __restrict__ left, const int* __restrict__ right,
+                             const int* __restrict__ parent, const int* __restrict__ leafParent, int* __restrict__ flag,
+                             const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                             float4* __restrict__ nodeMin, float4* __restrict__ nodeMax) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = leafParent[i];
+    while (p >= 0) {
+        __threadfence();
+        if (atomicAdd(&flag[p], 1) == 0) return;  // first arrival waits for the sibling subtree
+        int lc = left[p], rc = right[p];
+        float4 lmn, lmx, rmn, rmx;
+        int lenc, renc;
+        if (lc < 0) { int c = leafId[~lc]; lmn = aabbMin[c]; lmx = aabbMax[c]; lenc = ~c; }
+        else {
+            float4 a0 = __ldcg(&nodeMin[2 * lc]), a1 = __ldcg(&nodeMax[2 * lc]), b0 = __ldcg(&nodeMin[2 * lc + 1]), b1 = __ldcg(&nodeMax[2 * lc + 1]);
+            lmn = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.f);
+            lmx = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
+            lenc = lc;
+        }
+        if (rc < 0) { int c = leafId[~rc]; rmn = aabbMin[c]; rmx = aabbMax[c]; renc = ~c; }
+        else {
+            float4 a0 = __ldcg(&nodeMin[2 * rc]), a1 = __ldcg(&nodeMax[2 * rc]), b0 = __ldcg(&nodeMin[2 * rc + 1]), b1 = __ldcg(&nodeMax[2 * rc + 1]);
+            rmn = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.f);
+            rmx = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
+            renc = rc;
+        }
+        lmn.w = __int_as_float(lenc); lmx.w = __int_as_float(renc);
+        nodeMin[2 * p] = lmn; nodeMax[2 * p] = lmx; nodeMin[2 * p + 1] = rmn; nodeMax[2 * p + 1] = rmx;
+        p = parent[p];
+    }
+}
+
+// closed-interval overlap == !(a.max < b.min || a.min > b.max) per axis (Physecs.cpp:152-154)
+__device__ __forceinline__ bool overlaps(V3 amn, V3 amx, float4 bmn, float4 bmx) {
+    return !(amx.x < bmn.x || amn.x > bmx.x) && !(amx.y < bmn.y || amn.y > bmx.y) && !(amx.z < bmn.z || amn.z > bmx.z);
+}
+
+__device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ colRow, const int* __restrict__ rowEntity,
+                                         int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
+    auto g = cg::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&counters[CNT_PAIRS], (int)g.size());
+    base = g.shfl(base, 0);
+    int slot = base + (int)g.thread_rank();
+    if (slot < maxPairs) {
+        unsigned int ea = (unsigned int)rowEntity[colRow[a]], eb = (unsigned int)rowEntity[colRow[b]];
+        pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
+    } else {
+        atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+    }
+}
+
+// One thread per sorted leaf; only colliders of non-kinematic dynamic bodies issue queries (a pair needs one,
+// Physecs.cpp:147), which keeps huge static boxes / terrain from walking the whole tree.
+__global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* __restrict__ colFlags, const int* __restrict__ colRow,
+                             const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                             const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax,
+                             int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a = leafId[i];
+    int fa = colFlags[a];
+    if ((fa & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC)) return;
+    V3 amn = mk3(aabbMin[a]), amx = mk3(aabbMax[a]);
+    int rowA = colRow[a];
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        int node = stack[--sp];
+        float4 lmn = nodeMin[2 * node], lmx = nodeMax[2 * node], rmn = nodeMin[2 * node + 1], rmx = nodeMax[2 * node + 1];
+        int lc = __float_as_int(lmn.w), rc = __float_as_int(lmx.w);
+        bool ol = overlaps(amn, amx, lmn, lmx), orr = overlaps(amn, amx, rmn, rmx);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            bool o = side ? orr : ol;
+            int c = side ? rc : lc;
+            if (!o) continue;
+            if (c >= 0) { if (sp < 64) stack[sp++] = c; continue; }
+            int b = ~c;
+            if (b == a) continue;
+            int fb = colFlags[b];
+            if (!(fb & COLF_ENABLE)) continue;
+            if ((fb & COLF_DYNAMIC) && b < a) continue;     // dynamic-dynamic pairs are found from both sides: keep one
+            if (colRow[b] == rowA) continue;                // same entity (Physecs.cpp:145)
+            emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
+        }
+    }
+}
+
+// n == 2..: general path.  n < 2: no pairs.
+int pb_broadphase(pb_ctx* ctx) {
+    int n = ctx->nCol;
+    if (n < 2) return PB_OK;
+    int* sb = (int*)ctx->sceneBounds;
+    k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb);
+    int blocks = pb_grid(n, 256); if (blocks > ctx->numSMs * 8) blocks = ctx->numSMs * 8;
+    k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
+    k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA);
+    bool inA = true;
+    int rc = pb_radix_sort_pairs(ctx, ctx->mortonA, ctx->leafIdA, ctx->mortonB, ctx->leafIdB, n, 30, ctx->radixHist, ctx->radixTiles, &inA);
+    if (rc) return rc;
+    unsigned int* keys = inA ? ctx->mortonA : ctx->mortonB;
+    int* ids = inA ? ctx->leafIdA : ctx->leafIdB;
+    k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag);
+    k_lbvh_refit<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ids, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag,
+                                                            ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
+    k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
+                                                            ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}

@@ -1,0 +1,544 @@
+// C ABI (include/physecs_b200.h): context, scene upload, per-step orchestration and parity taps.
+// Step orchestration == physecs::Scene::simulate (reference src/Physecs.cpp:112-561), device side.
+#include "pb_ctx.h"
+#include "pb_math.cuh"
+#include "trimesh_build.h"
+#include <algorithm>
+#include <cstring>
+
+int pb_fail(pb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const int* row1, const float* a0p, const float* a0q,
+                     const float* a1p, const float* a1q, const float* params8, const int* color);
+void pb_joints_free(pb_ctx* ctx);
+
+// ---- packed host layout <-> float4 SoA ----------------------------------------------------------------------------
+__global__ void k_unpack3(int n, const float* __restrict__ src, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+__global__ void k_unpack4(int n, const float* __restrict__ src, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+}
+__global__ void k_pack3(int n, const float4* __restrict__ src, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = src[i]; dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; }
+}
+__global__ void k_pack4(int n, const float4* __restrict__ src, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = src[i]; dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
+}
+__global__ void k_com_invmass(int n, const float* __restrict__ com, const float* __restrict__ invMass, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(com[3 * i], com[3 * i + 1], com[3 * i + 2], invMass[i]);
+}
+__global__ void k_unpack_m3(int n, const float* __restrict__ src, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) for (int c = 0; c < 3; ++c) dst[3 * i + c] = make_float4(src[9 * i + 3 * c], src[9 * i + 3 * c + 1], src[9 * i + 3 * c + 2], 0.f);
+}
+__global__ void k_scatter_rows(int n, const int* __restrict__ rows, const float* __restrict__ p3, const float* __restrict__ q4,
+                               float4* __restrict__ pos, float4* __restrict__ quat, int* __restrict__ mark) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = rows[i];
+    pos[r] = make_float4(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], 0.f);
+    quat[r] = make_float4(q4[4 * i], q4[4 * i + 1], q4[4 * i + 2], q4[4 * i + 3]);
+    mark[r] = 1;
+}
+
+static int ensureStage(pb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stageBytes) return PB_OK;
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr; ctx->stageBytes = 0;
+    cudaError_t e = cudaMalloc((void**)&ctx->stage, bytes);
+    if (e != cudaSuccess) return pb_fail(ctx, PB_ECUDA, std::string("cudaMalloc stage: ") + cudaGetErrorString(e));
+    ctx->stageBytes = bytes;
+    return PB_OK;
+}
+
+// upload a packed host array (n*width floats) and expand to float4 rows at dst
+static int uploadVec(pb_ctx* ctx, const float* host, int n, int width, float4* dst) {
+    if (n <= 0) return PB_OK;
+    size_t bytes = sizeof(float) * (size_t)n * width;
+    int rc = ensureStage(ctx, bytes); if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (width == 3) k_unpack3<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
+    else k_unpack4<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
+    // the staging buffer is reused by the next upload on the same stream: stream order keeps this safe
+    return PB_OK;
+}
+template <class T> static int uploadRaw(pb_ctx* ctx, const T* host, size_t n, T* dst) {
+    if (n == 0) return PB_OK;
+    PB_CUDA(ctx, cudaMemcpyAsync(dst, host, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return PB_OK;
+}
+
+extern "C" {
+
+int pb_host_alloc(void** ptr, unsigned long long bytes) { return cudaMallocHost(ptr, bytes) == cudaSuccess ? PB_OK : PB_ECUDA; }
+void pb_host_free(void* ptr) { cudaFreeHost(ptr); }
+const char* pb_last_error(pb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* pb_stream(pb_ctx* ctx) { return (void*)ctx->stream; }
+
+int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
+    if (!caps || !out) return PB_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return PB_ECUDA;   // no CPU fallback
+    pb_ctx* ctx = new pb_ctx();
+    ctx->device = device;
+    ctx->caps = *caps;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->numSMs = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
+    int rc = 0;
+#define A(p, n) if (!rc) rc = pb_alloc(ctx, &ctx->p, (n))
+    A(rowEntity, R); A(pos, R); A(quat, R); A(vel, R); A(angvel, R); A(velPre, R); A(angvelPre, R); A(velLive, R); A(angvelLive, R);
+    A(comInvMass, R); A(invIL, 3 * R); A(invIW, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
+    A(colRow, C); A(colIndex, C); A(colType, C); A(colFlags, C); A(colData, C); A(colMesh, C);
+    A(colLPos, C); A(colLQuat, C); A(colParams, C); A(colMat, C); A(colWPos, C); A(colWQuat, C); A(aabbMin, C); A(aabbMax, C);
+    A(mortonA, C); A(mortonB, C); A(leafIdA, C); A(leafIdB, C);
+    size_t sortMax = std::max(C, M);
+    ctx->radixTiles = (int)((sortMax + 511) / 512);
+    A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
+    A(sceneBounds, 32);
+    A(nodeLeft, C); A(nodeRight, C); A(nodeParent, C); A(leafParent, C); A(nodeFlag, C); A(nodeMin, 2 * C); A(nodeMax, 2 * C);
+    A(pairs, P); A(pairOrder, 2 * P);
+    A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
+    A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
+    const size_t PT = 4 * M;
+    for (int b = 0; b < 2; ++b) { A(pR0T[b], PT); A(cPointOfsBuf[b], M + 1); A(cNpBuf[b], M + 1); }
+    A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
+    size_t cs = 1; while (cs < 2 * M) cs <<= 1;
+    ctx->cacheSize = (int)cs;
+    for (int b = 0; b < 2; ++b) { A(cacheTag[b], cs); A(cacheVal[b], cs); }
+    A(counters, CNT_TOTAL);
+    A(triMeshDev, 64); A(convexDev, 256);
+#undef A
+    if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * CNT_TOTAL) != cudaSuccess) rc = PB_ECUDA;
+    if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
+    cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);
+    *out = ctx;
+    return PB_OK;
+}
+
+void pb_ctx_destroy(pb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pb_joints_free(ctx);
+#define F(p) if (ctx->p) cudaFree(ctx->p)
+    F(rowEntity); F(pos); F(quat); F(vel); F(angvel); F(velPre); F(angvelPre); F(velLive); F(angvelLive); F(comInvMass); F(invIL); F(invIW);
+    F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
+    F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
+    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds);
+    F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
+    F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
+    F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
+    F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
+    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding);
+#undef F
+    for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
+    for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
+    if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pb_sync(pb_ctx* ctx) {
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, const float* pos3, const float* quat4, const int* kinematic,
+                     const float* vel3, const float* angvel3, const float* invMass, const float* com3, const float* invI9) {
+    cudaSetDevice(ctx->device);
+    int rows = nDyn + nStatic;
+    if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
+    ctx->nDyn = nDyn; ctx->nStatic = nStatic; ctx->nRows = rows;
+    int rc;
+    if ((rc = uploadRaw(ctx, entity, rows, ctx->rowEntity))) return rc;
+    if ((rc = uploadVec(ctx, pos3, rows, 3, ctx->pos))) return rc;
+    if ((rc = uploadVec(ctx, quat4, rows, 4, ctx->quat))) return rc;
+    if (nDyn) {
+        if ((rc = uploadRaw(ctx, kinematic, nDyn, ctx->kinematic))) return rc;
+        if ((rc = uploadVec(ctx, vel3, nDyn, 3, ctx->vel))) return rc;
+        if ((rc = uploadVec(ctx, angvel3, nDyn, 3, ctx->angvel))) return rc;
+        size_t bytes = sizeof(float) * (size_t)nDyn * 13;
+        if ((rc = ensureStage(ctx, bytes))) return rc;
+        float* s = ctx->stage;
+        PB_CUDA(ctx, cudaMemcpyAsync(s, com3, sizeof(float) * 3 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * (size_t)nDyn, invMass, sizeof(float) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)nDyn, invI9, sizeof(float) * 9 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+        k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
+        k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
+    }
+    ctx->cacheValid = false;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIndex, const float* lpos3, const float* lquat4, const int* type,
+                        const float* params4, const int* mesh, const float* material3, const int* flags, const int* data) {
+    cudaSetDevice(ctx->device);
+    if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
+    ctx->nCol = n;
+    ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
+    // device flags: bit0 trigger, bit1 enableSimulation, bit2 owner is a non-kinematic dynamic body (BroadPhaseEntry::isDynamic)
+    std::vector<int> kin(ctx->nDyn);
+    if (ctx->nDyn) PB_CUDA(ctx, cudaMemcpy(kin.data(), ctx->kinematic, sizeof(int) * ctx->nDyn, cudaMemcpyDeviceToHost));
+    std::vector<int> f(n);
+    std::vector<float> mat4((size_t)4 * n);
+    bool trig = false;
+    for (int i = 0; i < n; ++i) {
+        int row = bodyRow[i];
+        if (row < 0 || row >= ctx->nRows) return pb_fail(ctx, PB_EINVAL, "collider body_row out of range");
+        bool dyn = row < ctx->nDyn && !kin[row];
+        f[i] = (flags[i] & 3) | (dyn ? 4 : 0);
+        trig |= (flags[i] & PB_COL_TRIGGER) != 0;
+        if (type[i] == PB_TRIANGLE_MESH && (mesh[i] < 0 || mesh[i] >= (int)ctx->triMeshes.size())) return pb_fail(ctx, PB_EINVAL, "bad trimesh handle");
+        if (type[i] == PB_CONVEX_MESH && (mesh[i] < 0 || mesh[i] >= (int)ctx->convexes.size())) return pb_fail(ctx, PB_EINVAL, "bad convex handle");
+        mat4[4 * i] = material3[3 * i]; mat4[4 * i + 1] = material3[3 * i + 1]; mat4[4 * i + 2] = material3[3 * i + 2]; mat4[4 * i + 3] = 0.f;
+    }
+    ctx->triggersPresent = trig;
+    int rc;
+    if ((rc = uploadRaw(ctx, bodyRow, n, ctx->colRow))) return rc;
+    if ((rc = uploadRaw(ctx, colIndex, n, ctx->colIndex))) return rc;
+    if ((rc = uploadRaw(ctx, type, n, ctx->colType))) return rc;
+    if ((rc = uploadRaw(ctx, f.data(), n, ctx->colFlags))) return rc;
+    if ((rc = uploadRaw(ctx, data, n, ctx->colData))) return rc;
+    if ((rc = uploadRaw(ctx, mesh, n, ctx->colMesh))) return rc;
+    if ((rc = uploadVec(ctx, lpos3, n, 3, ctx->colLPos))) return rc;
+    if ((rc = uploadVec(ctx, lquat4, n, 4, ctx->colLQuat))) return rc;
+    if ((rc = uploadVec(ctx, params4, n, 4, ctx->colParams))) return rc;
+    if ((rc = uploadVec(ctx, mat4.data(), n, 4, ctx->colMat))) return rc;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    // creation-time bounds: no margin (Physecs.cpp:32)
+    if ((rc = pb_update_bounds_all(ctx, 0.f, 0))) return rc;
+    ctx->cacheValid = false;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+static int syncMeshTables(pb_ctx* ctx) {
+    std::vector<PbTriMeshDev> t(ctx->triMeshes.size());
+    for (size_t i = 0; i < t.size(); ++i) {
+        auto& m = ctx->triMeshes[i];
+        t[i] = { m.verts, m.tris, m.triNormal, m.triCentroid, m.nodeMin, m.nodeMax, m.nTris, m.nNodes,
+                 { m.bmin[0], m.bmin[1], m.bmin[2] }, { m.bmax[0], m.bmax[1], m.bmax[2] } };
+    }
+    std::vector<PbConvexDev> c(ctx->convexes.size());
+    for (size_t i = 0; i < c.size(); ++i) {
+        auto& m = ctx->convexes[i];
+        c[i] = { m.verts, m.faceOffsets, m.faceIndices, m.faceNormal, m.faceCentroid, m.nVerts, m.nVertsPadded, m.nFaces, 0 };
+    }
+    if (t.size() > 64 || c.size() > 256) return pb_fail(ctx, PB_ECAPACITY, "too many meshes");
+    if (!t.empty()) PB_CUDA(ctx, cudaMemcpy(ctx->triMeshDev, t.data(), sizeof(PbTriMeshDev) * t.size(), cudaMemcpyHostToDevice));
+    if (!c.empty()) PB_CUDA(ctx, cudaMemcpy(ctx->convexDev, c.data(), sizeof(PbConvexDev) * c.size(), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+int pb_register_convex(pb_ctx* ctx, const float* verts3, int nVerts, const int* faceOffsets, const int* faceIndices, int nFaces,
+                       const float* faceNormals3, const float* faceCentroids3, int* handle) {
+    cudaSetDevice(ctx->device);
+    PbConvex m;
+    m.nVerts = nVerts; m.nVertsPadded = (nVerts + 3) / 4 * 4; m.nFaces = nFaces;
+    std::vector<float4> v(m.nVertsPadded);
+    for (int i = 0; i < m.nVertsPadded; ++i) {
+        int s = i < nVerts ? i : nVerts - 1;   // padded by repeating the last vertex (ConvexMesh.cpp:8-10)
+        v[i] = make_float4(verts3[3 * s], verts3[3 * s + 1], verts3[3 * s + 2], 0.f);
+    }
+    std::vector<float4> fn(nFaces), fc(nFaces);
+    for (int i = 0; i < nFaces; ++i) {
+        fn[i] = make_float4(faceNormals3[3 * i], faceNormals3[3 * i + 1], faceNormals3[3 * i + 2], 0.f);
+        fc[i] = make_float4(faceCentroids3[3 * i], faceCentroids3[3 * i + 1], faceCentroids3[3 * i + 2], 0.f);
+    }
+    int nIdx = faceOffsets[nFaces];
+    int rc = 0;
+    if (!rc) rc = pb_alloc(ctx, &m.verts, v.size());
+    if (!rc) rc = pb_alloc(ctx, &m.faceOffsets, (size_t)nFaces + 1);
+    if (!rc) rc = pb_alloc(ctx, &m.faceIndices, (size_t)nIdx);
+    if (!rc) rc = pb_alloc(ctx, &m.faceNormal, (size_t)nFaces);
+    if (!rc) rc = pb_alloc(ctx, &m.faceCentroid, (size_t)nFaces);
+    if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpy(m.verts, v.data(), sizeof(float4) * v.size(), cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.faceOffsets, faceOffsets, sizeof(int) * (nFaces + 1), cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.faceIndices, faceIndices, sizeof(int) * nIdx, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.faceNormal, fn.data(), sizeof(float4) * nFaces, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.faceCentroid, fc.data(), sizeof(float4) * nFaces, cudaMemcpyHostToDevice));
+    ctx->convexes.push_back(m);
+    *handle = (int)ctx->convexes.size() - 1;
+    return syncMeshTables(ctx);
+}
+
+int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsigned* indices, int nIndices, int* handle, int* triOrderOut) {
+    cudaSetDevice(ctx->device);
+    PbHostTriMesh h;
+    pb_build_trimesh_host(verts3, nVerts, indices, nIndices, h);
+    PbTriMesh m;
+    m.nVerts = nVerts; m.nTris = h.nTris; m.nNodes = h.nNodes;
+    std::vector<float4> v(nVerts), tn(h.nTris), tc(h.nTris), nmn(h.nNodes), nmx(h.nNodes);
+    std::vector<int4> ti(h.nTris);
+    for (int k = 0; k < 3; ++k) { m.bmin[k] = 3.4e38f; m.bmax[k] = -3.4e38f; }
+    for (int i = 0; i < nVerts; ++i) {
+        v[i] = make_float4(verts3[3 * i], verts3[3 * i + 1], verts3[3 * i + 2], 0.f);
+        for (int k = 0; k < 3; ++k) { m.bmin[k] = std::min(m.bmin[k], verts3[3 * i + k]); m.bmax[k] = std::max(m.bmax[k], verts3[3 * i + k]); }
+    }
+    for (int i = 0; i < h.nTris; ++i) {
+        ti[i] = make_int4((int)h.triIdx[3 * i], (int)h.triIdx[3 * i + 1], (int)h.triIdx[3 * i + 2], 0);
+        tn[i] = make_float4(h.triNormal[3 * i], h.triNormal[3 * i + 1], h.triNormal[3 * i + 2], 0.f);
+        tc[i] = make_float4(h.triCentroid[3 * i], h.triCentroid[3 * i + 1], h.triCentroid[3 * i + 2], 0.f);
+    }
+    for (int i = 0; i < h.nNodes; ++i) {
+        int cnt = h.nodeCountIndex[2 * i], idx = h.nodeCountIndex[2 * i + 1];
+        float fc, fi; memcpy(&fc, &cnt, 4); memcpy(&fi, &idx, 4);
+        nmn[i] = make_float4(h.nodeBounds[6 * i], h.nodeBounds[6 * i + 1], h.nodeBounds[6 * i + 2], fc);
+        nmx[i] = make_float4(h.nodeBounds[6 * i + 3], h.nodeBounds[6 * i + 4], h.nodeBounds[6 * i + 5], fi);
+    }
+    int rc = 0;
+    if (!rc) rc = pb_alloc(ctx, &m.verts, (size_t)nVerts);
+    if (!rc) rc = pb_alloc(ctx, &m.tris, (size_t)h.nTris);
+    if (!rc) rc = pb_alloc(ctx, &m.triNormal, (size_t)h.nTris);
+    if (!rc) rc = pb_alloc(ctx, &m.triCentroid, (size_t)h.nTris);
+    if (!rc) rc = pb_alloc(ctx, &m.nodeMin, (size_t)h.nNodes);
+    if (!rc) rc = pb_alloc(ctx, &m.nodeMax, (size_t)h.nNodes);
+    if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpy(m.verts, v.data(), sizeof(float4) * nVerts, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.tris, ti.data(), sizeof(int4) * h.nTris, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.triNormal, tn.data(), sizeof(float4) * h.nTris, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.triCentroid, tc.data(), sizeof(float4) * h.nTris, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.nodeMin, nmn.data(), sizeof(float4) * h.nNodes, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.nodeMax, nmx.data(), sizeof(float4) * h.nNodes, cudaMemcpyHostToDevice));
+    ctx->triMeshes.push_back(m);
+    *handle = (int)ctx->triMeshes.size() - 1;
+    if (triOrderOut) memcpy(triOrderOut, h.triOrig.data(), sizeof(int) * h.nTris);
+    return syncMeshTables(ctx);
+}
+
+int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* row0, const int* row1, const float* a0p, const float* a0q,
+                     const float* a1p, const float* a1q, const float* params8, const int* color) {
+    cudaSetDevice(ctx->device);
+    return pb_joints_upload(ctx, n, type, row0, row1, a0p, a0q, a1p, a1q, params8, color);
+}
+
+int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* pairs2) {
+    cudaSetDevice(ctx->device);
+    std::vector<unsigned long long> keys(n);
+    for (int i = 0; i < n; ++i) {
+        unsigned int a = (unsigned int)pairs2[2 * i], b = (unsigned int)pairs2[2 * i + 1];
+        if (a > b) std::swap(a, b);
+        keys[i] = ((unsigned long long)a << 32) | b;
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    int rc = pb_alloc(ctx, &ctx->nonColliding, keys.size());
+    if (rc) return rc;
+    ctx->nNonColliding = (int)keys.size();
+    if (!keys.empty()) PB_CUDA(ctx, cudaMemcpy(ctx->nonColliding, keys.data(), sizeof(unsigned long long) * keys.size(), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
+    cudaSetDevice(ctx->device);
+    if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state: n_dynamic mismatch");
+    if (!nDyn) return PB_OK;
+    // one staged H2D burst (13 floats / body), then unpack into the float4 SoA
+    size_t n = (size_t)nDyn;
+    int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
+    float* s = ctx->stage;
+    if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int g = pb_grid(nDyn, 256);
+    if (pos3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
+    if (quat4) k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
+    if (vel3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 7 * n, ctx->vel);
+    if (angvel3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 10 * n, ctx->angvel);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return PB_OK;
+    size_t bytes = sizeof(float) * 8 * (size_t)n;
+    int rc = ensureStage(ctx, bytes); if (rc) return rc;
+    float* s = ctx->stage;
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->rowMark, 0, sizeof(int) * ctx->nRows, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s, rows, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + n, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter_rows<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const int*)s, s + n, s + 4 * (size_t)n, ctx->pos, ctx->quat, ctx->rowMark);
+    if ((rc = pb_update_bounds_rows(ctx, ctx->rowMark, n, 0.01f))) return rc;
+    std::vector<char> moved(ctx->nRows, 0);
+    for (int i = 0; i < n; ++i) if (rows[i] >= 0 && rows[i] < ctx->nRows) moved[rows[i]] = 1;
+    for (int c = 0; c < ctx->nCol; ++c)
+        if (ctx->hColType[c] == PB_TRIANGLE_MESH && moved[ctx->hColRow[c]]) pb_update_bounds_trimesh_col(ctx, c, 0.01f);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_refresh_bounds(pb_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    return pb_update_bounds_all(ctx, 0.01f, 1);
+}
+
+static int readCounters(pb_ctx* ctx) {
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
+    cudaSetDevice(ctx->device);
+    if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
+    if (ctx->triggersPresent) return pb_fail(ctx, PB_EUNSUPPORTED, "trigger colliders are not implemented on the device path yet");
+    int rc;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream));
+    if ((rc = pb_broadphase(ctx))) return rc;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if ((rc = pb_world_poses(ctx))) return rc;
+    if ((rc = pb_narrowphase(ctx))) return rc;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if ((rc = readCounters(ctx))) return rc;
+    int nPairs = ctx->hCounters[CNT_PAIRS], nRaw = ctx->hCounters[CNT_RAWM], status = ctx->hCounters[CNT_STATUS];
+    ctx->lastCounts = pb_counts{};
+    ctx->lastCounts.n_pairs = nPairs;
+    ctx->lastCounts.n_mesh_pairs = ctx->hCounters[CNT_MESH_PAIRS];
+    ctx->lastCounts.n_triggers = ctx->hCounters[CNT_TRIGGERS];
+    if (nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY)) {
+        ctx->lastCounts.status = PB_ECAPACITY;
+        return pb_fail(ctx, PB_ECAPACITY, "per-step arena overflow: pairs=" + std::to_string(nPairs) + "/" + std::to_string(ctx->caps.max_pairs) +
+                       " manifolds=" + std::to_string(nRaw) + "/" + std::to_string(ctx->caps.max_manifolds) + " (or triangle contacts per pair)");
+    }
+    if (status & 0x100) return pb_fail(ctx, PB_EUNSUPPORTED, "a candidate pair involves a shape combination not implemented on the device path");
+    ctx->curBuf ^= 1;
+    if ((rc = pb_contact_build(ctx, nRaw))) return rc;
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    if (nRaw > 0) { if ((rc = readCounters(ctx))) return rc; }
+    ctx->lastCounts.n_manifolds = nRaw > 0 ? ctx->hCounters[CNT_MANIFOLDS] : 0;
+    ctx->lastCounts.n_colors = nRaw > 0 ? ctx->hCounters[CNT_NCOLORS] : 0;
+    ctx->lastCounts.n_overflow = nRaw > 0 ? ctx->hCounters[CNT_OVERFLOW] : 0;
+    ctx->lastCounts.n_points = nRaw > 0 ? ctx->hCounters[CNT_POINTS] : 0;
+    if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
+    ctx->cacheValid = true;
+    // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
+    if ((rc = pb_update_bounds_all(ctx, 0.01f, 1))) return rc;
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3) {
+    cudaSetDevice(ctx->device);
+    int nDyn = ctx->nDyn;
+    if (!nDyn) return PB_OK;
+    size_t n = (size_t)nDyn;
+    int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
+    float* s = ctx->stage;
+    int g = pb_grid(nDyn, 256);
+    if (pos3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
+    if (quat4) k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
+    if (vel3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, s + 7 * n);
+    if (angvel3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->angvel, s + 10 * n);
+    if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3, s, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4, s + 3 * n, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3, s + 7 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(angvel3, s + 10 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_get_counts(pb_ctx* ctx, pb_counts* out) { *out = ctx->lastCounts; return PB_OK; }
+
+int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pb_timings t{};
+    cudaEventElapsedTime(&t.broadphase, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t.narrowphase, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t.contact_build, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&t.solve, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&t.total, ctx->ev[0], ctx->ev[4]);
+    *out = t;
+    return PB_OK;
+}
+
+int pb_get_pairs(pb_ctx* ctx, int* out4, int cap, int* n) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int np = std::min(ctx->lastCounts.n_pairs, ctx->caps.max_pairs);
+    *n = np;
+    if (!out4 || np == 0) return PB_OK;
+    std::vector<int2> p(np);
+    PB_CUDA(ctx, cudaMemcpy(p.data(), ctx->pairs, sizeof(int2) * np, cudaMemcpyDeviceToHost));
+    std::vector<int> rowEnt(ctx->nRows), colIdx(ctx->nCol);
+    PB_CUDA(ctx, cudaMemcpy(rowEnt.data(), ctx->rowEntity, sizeof(int) * ctx->nRows, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(colIdx.data(), ctx->colIndex, sizeof(int) * ctx->nCol, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < np && i < cap; ++i) {
+        out4[4 * i] = rowEnt[ctx->hColRow[p[i].x]]; out4[4 * i + 1] = colIdx[p[i].x];
+        out4[4 * i + 2] = rowEnt[ctx->hColRow[p[i].y]]; out4[4 * i + 3] = colIdx[p[i].y];
+    }
+    return PB_OK;
+}
+
+int pb_get_bounds(pb_ctx* ctx, float* out6) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float4> mn(ctx->nCol), mx(ctx->nCol);
+    if (!ctx->nCol) return PB_OK;
+    PB_CUDA(ctx, cudaMemcpy(mn.data(), ctx->aabbMin, sizeof(float4) * ctx->nCol, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(mx.data(), ctx->aabbMax, sizeof(float4) * ctx->nCol, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ctx->nCol; ++i) {
+        out6[6 * i] = mn[i].x; out6[6 * i + 1] = mn[i].y; out6[6 * i + 2] = mn[i].z;
+        out6[6 * i + 3] = mx[i].x; out6[6 * i + 4] = mx[i].y; out6[6 * i + 5] = mx[i].z;
+    }
+    return PB_OK;
+}
+
+int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* normal3, float* points24, int* color, int* n) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int nm = ctx->lastCounts.n_manifolds;
+    *n = nm;
+    if (nm == 0 || cap == 0) return PB_OK;
+    std::vector<int> sorted(nm);
+    PB_CUDA(ctx, cudaMemcpy(sorted.data(), ctx->mSorted, sizeof(int) * nm, cudaMemcpyDeviceToHost));
+    int nRaw = ctx->hCounters[CNT_RAWM];
+    std::vector<int4> key(nRaw); std::vector<float4> nrm(nRaw), pts((size_t)8 * nRaw);
+    PB_CUDA(ctx, cudaMemcpy(key.data(), ctx->mKey, sizeof(int4) * nRaw, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(nrm.data(), ctx->mNormal, sizeof(float4) * nRaw, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(pts.data(), ctx->mPts, sizeof(float4) * 8 * (size_t)nRaw, cudaMemcpyDeviceToHost));
+    std::vector<int> rowEnt(ctx->nRows), colIdx(ctx->nCol);
+    PB_CUDA(ctx, cudaMemcpy(rowEnt.data(), ctx->rowEntity, sizeof(int) * ctx->nRows, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(colIdx.data(), ctx->colIndex, sizeof(int) * ctx->nCol, cudaMemcpyDeviceToHost));
+    const int* cs = ctx->hCounters + CNT_COLORSTART;
+    int c = 0;
+    for (int s = 0; s < nm && s < cap; ++s) {
+        int raw = sorted[s];
+        int4 k = key[raw];
+        keys5[5 * s] = rowEnt[ctx->hColRow[k.x]]; keys5[5 * s + 1] = colIdx[k.x];
+        keys5[5 * s + 2] = rowEnt[ctx->hColRow[k.y]]; keys5[5 * s + 3] = colIdx[k.y]; keys5[5 * s + 4] = k.z;
+        numPoints[s] = k.w;
+        normal3[3 * s] = nrm[raw].x; normal3[3 * s + 1] = nrm[raw].y; normal3[3 * s + 2] = nrm[raw].z;
+        for (int p = 0; p < 4; ++p) for (int side = 0; side < 2; ++side) {
+            float4 v = p < k.w ? pts[8 * (size_t)raw + 2 * p + side] : make_float4(0, 0, 0, 0);
+            points24[24 * s + 6 * p + 3 * side] = v.x; points24[24 * s + 6 * p + 3 * side + 1] = v.y; points24[24 * s + 6 * p + 3 * side + 2] = v.z;
+        }
+        while (c < PB_MAX_COLORS - 1 && s >= cs[c + 1]) ++c;
+        if (color) color[s] = c;
+    }
+    return PB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,208 @@
+// Contact constraint build: raw manifolds -> colour-batched, solve-ordered constraint SoA.
+//
+//   k_color          lock-free greedy colouring of the body/manifold graph (64-bit colour set per dynamic body).
+//                    The reference solves contacts strictly sequentially (src/Physecs.cpp:484-486); within one
+//                    colour no two manifolds share a dynamic body, so a parallel colour == a sequential sub-sweep
+//                    and the whole step equals the reference fed the (colour, slot) order (north_star gate 3).
+//   radix pass       manifolds grouped by colour (stable), exclusive scan of point counts -> point offsets
+//   k_contact_build  material mix, body indices, body-local arms, restitution target with the previous step's
+//                    contact cache (src/Physecs.cpp:215-315; cache semantics :237, :291-300, :313)
+#include "pb_ctx.h"
+#include "pb_math.cuh"
+
+#define DISCARD_COLOR 255u
+
+__device__ __forceinline__ int solverIndex(int row, int nDyn, const int* __restrict__ kinematic) {
+    return (row < nDyn && !kinematic[row]) ? row : -1;
+}
+
+__global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counters, int maxManifolds, const int* __restrict__ colRow,
+                        int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMask,
+                        unsigned int* __restrict__ sortKey, int* __restrict__ sortVal) {
+    __shared__ int hist[PB_MAX_COLORS];
+    if (threadIdx.x < PB_MAX_COLORS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 key = mKey[i];
+        unsigned int color = DISCARD_COLOR;
+        if (key.w > 0) {
+            int b0 = solverIndex(colRow[key.x], nDyn, kinematic), b1 = solverIndex(colRow[key.y], nDyn, kinematic);
+            int lo = b0, hi = b1;
+            if (lo < 0 || (hi >= 0 && hi < lo)) { int t = lo; lo = hi; hi = t; }   // lo = smallest valid index first (or -1 if none)
+            if (lo < 0) { lo = hi; hi = -1; }
+            if (lo < 0) color = 0;
+            else {
+                while (true) {
+                    unsigned long long m0 = *((volatile unsigned long long*)&colorMask[lo]);
+                    unsigned long long m1 = hi >= 0 ? *((volatile unsigned long long*)&colorMask[hi]) : 0ull;
+                    unsigned long long freeSet = ~(m0 | m1) & ~(1ull << PB_OVERFLOW_COLOR);
+                    if (!freeSet) { color = PB_OVERFLOW_COLOR; break; }
+                    int c = __ffsll((long long)freeSet) - 1;
+                    unsigned long long bit = 1ull << c;
+                    unsigned long long old = atomicOr(&colorMask[lo], bit);
+                    if (old & bit) continue;
+                    if (hi >= 0 && hi != lo) {
+                        old = atomicOr(&colorMask[hi], bit);
+                        if (old & bit) { atomicAnd(&colorMask[lo], ~bit); continue; }
+                    }
+                    color = (unsigned int)c;
+                    break;
+                }
+            }
+            atomicAdd(&hist[color], 1);
+        }
+        sortKey[i] = color;
+        sortVal[i] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x < PB_MAX_COLORS && hist[threadIdx.x]) atomicAdd(&counters[CNT_COLORSTART + threadIdx.x], hist[threadIdx.x]);
+}
+
+__global__ void k_color_starts(int* counters) {
+    if (threadIdx.x == 0) {
+        int run = 0, ncol = 0;
+        for (int c = 0; c < PB_MAX_COLORS; ++c) {
+            int cnt = counters[CNT_COLORSTART + c];
+            counters[CNT_COLORSTART + c] = run;
+            run += cnt;
+            if (cnt) ncol = c + 1;
+            if (c == PB_OVERFLOW_COLOR) counters[CNT_OVERFLOW] = cnt;
+        }
+        counters[CNT_COLORSTART + PB_MAX_COLORS] = run;
+        counters[CNT_MANIFOLDS] = run;
+        counters[CNT_NCOLORS] = ncol;
+    }
+}
+
+__global__ void k_gather_np(const int* __restrict__ counters, const int* __restrict__ mSorted, const int4* __restrict__ mKey, int* __restrict__ np, int maxManifolds) {
+    int n = counters[CNT_MANIFOLDS];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < maxManifolds; i += gridDim.x * blockDim.x)
+        np[i] = i < n ? mKey[mSorted[i]].w : 0;
+}
+
+__global__ void k_count_points(int* counters, const int* __restrict__ pointOfs, const int* __restrict__ np) {
+    int n = counters[CNT_MANIFOLDS];
+    counters[CNT_POINTS] = n > 0 ? pointOfs[n - 1] + np[n - 1] : 0;
+}
+
+__device__ __forceinline__ unsigned long long hashKey(int a, int b, int tri) {
+    unsigned long long h = ((unsigned long long)(unsigned int)a << 32) | (unsigned int)b;
+    h ^= (unsigned long long)(unsigned int)tri * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h | 1ull;   // 0 = empty slot
+}
+
+__global__ void __launch_bounds__(128) k_contact_build(
+    int* __restrict__ counters, const int* __restrict__ mSorted, const int4* __restrict__ mKey, const float4* __restrict__ mNormal,
+    const float4* __restrict__ mPts, const int* __restrict__ pointOfs, const int* __restrict__ colRow, const float4* __restrict__ colMat,
+    int nDyn, const int* __restrict__ kinematic, const float4* __restrict__ pos, const float4* __restrict__ quat,
+    const float4* __restrict__ vel, const float4* __restrict__ angvel, const float4* __restrict__ comInvMass,
+    int2* __restrict__ cBodies, int2* __restrict__ cRowsT, float4* __restrict__ cNormal, float4* __restrict__ cSoft, int* __restrict__ cNp,
+    float4* __restrict__ pR0T, float4* __restrict__ pR1,
+    // previous step (contact cache)
+    const unsigned long long* __restrict__ prevTag, const int4* __restrict__ prevVal, const int* __restrict__ prevPointOfs,
+    const int* __restrict__ prevNp, const float4* __restrict__ prevR0T,
+    unsigned long long* __restrict__ curTag, int4* __restrict__ curVal, int cacheMask) {
+    int n = counters[CNT_MANIFOLDS];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        int raw = mSorted[s];
+        int4 key = mKey[raw];
+        int np = key.w;
+        V3 nrm = mk3(mNormal[raw]);
+        int row0 = colRow[key.x], row1 = colRow[key.y];
+        float4 mat0 = colMat[key.x], mat1 = colMat[key.y];
+        float friction = (mat0.x + mat1.x) * 0.5f;
+        float isSoft = 0.f, frequency = 0.f, damping = 0.f, restitution;
+        if (mat0.z != 0.f || mat1.z != 0.f) {
+            isSoft = 1.f;
+            if (mat0.z != 0.f && mat1.z != 0.f) { frequency = gmin(mat0.y, mat1.y); damping = gmin(mat0.z, mat1.z); }
+            else if (mat0.z != 0.f) { frequency = mat0.y; damping = mat0.z; }
+            else { frequency = mat1.y; damping = mat1.z; }
+            restitution = 0.f;
+        } else restitution = (mat0.y + mat1.y) * 0.5f;
+        int b0 = solverIndex(row0, nDyn, kinematic), b1 = solverIndex(row1, nDyn, kinematic);
+        Q4 q0 = mkq(quat[row0]), q1 = mkq(quat[row1]);
+        V3 com0 = mk3(0.f), v0 = mk3(0.f), w0 = mk3(0.f), com1 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
+        if (b0 >= 0) { com0 = mk3(pos[row0]) + rotate(q0, mk3(comInvMass[b0])); v0 = mk3(vel[b0]); w0 = mk3(angvel[b0]); }
+        if (b1 >= 0) { com1 = mk3(pos[row1]) + rotate(q1, mk3(comInvMass[b1])); v1 = mk3(vel[b1]); w1 = mk3(angvel[b1]); }
+        Q4 iq0 = qinverse(q0), iq1 = qinverse(q1);
+        // previous manifold of the same (pair, triangle) key
+        int prevSlot = -1;
+        unsigned long long tag = hashKey(key.x, key.y, key.z);
+        bool useCache = restitution != 0.f;
+        if (useCache && prevTag) {
+            unsigned int h = (unsigned int)(tag >> 1) & cacheMask;
+            while (true) {
+                unsigned long long t = prevTag[h];
+                if (t == 0ull) break;
+                if (t == tag) { int4 v = prevVal[h]; if (v.x == key.x && v.y == key.y && v.z == key.z) { prevSlot = v.w; break; } }
+                h = (h + 1) & cacheMask;
+            }
+        }
+        int pofs = pointOfs[s];
+        for (int k = 0; k < np; ++k) {
+            V3 r0 = mk3(mPts[8 * (size_t)raw + 2 * k]) - com0;
+            V3 r1 = mk3(mPts[8 * (size_t)raw + 2 * k + 1]) - com1;
+            V3 rel = v1 + cross(w1, r1) - v0 - cross(w0, r0);
+            float relN = dot(rel, nrm);
+            r0 = rotate(iq0, r0);
+            r1 = rotate(iq1, r1);
+            float target = 0.f;
+            bool found = false;
+            if (prevSlot >= 0) {
+                int pn = prevNp[prevSlot], po = prevPointOfs[prevSlot];
+                for (int i = 0; i < pn; ++i) {
+                    float4 pr = prevR0T[po + i];
+                    if ((double)distance(r0, mk3(pr)) < 0.1) { found = true; target = pr.w; break; }
+                }
+            }
+            if (!found) target = -restitution * relN;
+            pR0T[pofs + k] = f4(r0, target);
+            pR1[pofs + k] = f4(r1, 0.f);
+        }
+        cBodies[s] = make_int2(b0, b1);
+        cRowsT[s] = make_int2(row0, row1);
+        cNormal[s] = f4(nrm, friction);
+        cSoft[s] = make_float4(isSoft, frequency, damping, 0.f);
+        cNp[s] = np;
+        if (useCache) {
+            unsigned int h = (unsigned int)(tag >> 1) & cacheMask;
+            while (true) {
+                unsigned long long old = atomicCAS(&curTag[h], 0ull, tag);
+                if (old == 0ull) { curVal[h] = make_int4(key.x, key.y, key.z, s); break; }
+                h = (h + 1) & cacheMask;
+            }
+        }
+    }
+}
+
+int pb_contact_build(pb_ctx* ctx, int nRaw) {
+    int blocks = ctx->numSMs * 8;
+    int maxM = ctx->caps.max_manifolds;
+    cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
+    k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
+                                             ctx->mSortKeyA, ctx->mSortTmp);
+    k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
+    // group by colour: one stable 8-bit radix pass over the raw arena (nRaw was read back after the narrowphase)
+    int n = nRaw;
+    if (n <= 0) return PB_OK;
+    bool inA = true;
+    int rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 8, ctx->radixHist, ctx->radixTiles, &inA);
+    if (rc) return rc;
+    ctx->mSorted = inA ? ctx->mSortTmp : ctx->mSortValB;
+    int cur = ctx->curBuf, prev = cur ^ 1;
+    int* pointOfs = ctx->cPointOfsBuf[cur];
+    k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);
+    rc = pb_exclusive_scan(ctx, ctx->cNpBuf[cur], pointOfs, n, (int*)ctx->radixHist);
+    if (rc) return rc;
+    k_count_points<<<1, 1, 0, ctx->stream>>>(ctx->counters, pointOfs, ctx->cNpBuf[cur]);
+    cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
+    k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
+        ctx->nDyn, ctx->kinematic, ctx->pos, ctx->quat, ctx->vel, ctx->angvel, ctx->comInvMass,
+        ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
+        ctx->cacheValid ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],
+        ctx->cacheTag[cur], ctx->cacheVal[cur], ctx->cacheSize - 1);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}

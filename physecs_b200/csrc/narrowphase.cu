@@ -1,0 +1,281 @@
+// Narrowphase: candidate pairs -> contact manifolds.
+//
+// Stage layout (one grid-stride launch each, counts stay on the device):
+//   k_pair_classify   filter (trigger / nonCollidingPairs) + shape-pair bin histogram   Physecs.cpp:200-209
+//   k_bin_starts      exclusive scan of the bin histogram
+//   k_pair_scatter    pair indices grouped by bin
+//   k_np_prim<BIN>    thread-per-pair analytic routines                                  Collision.cpp:895-1016 dispatch
+//   k_np_mesh         thread-per-(shape, mesh) pair: BVH cull + filter + manifolds        CollisionTriangleMesh.cpp:882-956
+// Each warp appends its manifolds with ONE atomic (ballot + prefix), so the manifold arena stays dense.
+// Built with -fmad=false: feature / face decisions then follow the reference's fp32 arithmetic.
+#include "pb_ctx.h"
+#include "pb_math.cuh"
+#include "np_prims.cuh"
+#include "np_mesh.cuh"
+#include "np_gjk.cuh"
+
+#define COLF_TRIGGER 1
+#define COLF_ENABLE 2
+#define COLF_DYNAMIC 4
+
+enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_COUNT };
+
+__device__ __forceinline__ int binOf(int t0, int t1) {
+    if (t0 == PB_TRIANGLE_MESH || t1 == PB_TRIANGLE_MESH) return (t0 == t1) ? -1 : BIN_MESH;
+    if (t0 == PB_CONVEX_MESH || t1 == PB_CONVEX_MESH) return BIN_GJK;
+    int lo = min(t0, t1), hi = max(t0, t1);
+    if (lo == PB_SPHERE) return hi == PB_SPHERE ? BIN_SS : (hi == PB_CAPSULE ? BIN_SC : BIN_SB);
+    if (lo == PB_CAPSULE) return hi == PB_CAPSULE ? BIN_CC : BIN_CB;
+    return BIN_BB;
+}
+
+__device__ __forceinline__ bool isNonColliding(const unsigned long long* __restrict__ keys, int n, unsigned long long k) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        unsigned long long v = keys[mid];
+        if (v == k) return true;
+        if (v < k) lo = mid + 1; else hi = mid - 1;
+    }
+    return false;
+}
+
+__global__ void k_pair_classify(const int2* __restrict__ pairs, int* __restrict__ pairBin, int* __restrict__ counters, int maxPairs,
+                                const int* __restrict__ colType, const int* __restrict__ colFlags, const int* __restrict__ colRow,
+                                const int* __restrict__ rowEntity, const unsigned long long* __restrict__ nonColl, int nNonColl) {
+    __shared__ int sh[BIN_COUNT + 1];
+    if (threadIdx.x <= BIN_COUNT) sh[threadIdx.x] = 0;
+    __syncthreads();
+    int n = min(counters[CNT_PAIRS], maxPairs);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int2 p = pairs[i];
+        int bin;
+        int f0 = colFlags[p.x], f1 = colFlags[p.y];
+        if ((f0 | f1) & COLF_TRIGGER) { bin = -2; atomicAdd(&sh[BIN_COUNT], 1); }   // defaultContactFilter (Physecs.cpp:20-23)
+        else {
+            bin = binOf(colType[p.x], colType[p.y]);
+            if (bin >= 0 && nNonColl) {
+                unsigned long long k = ((unsigned long long)(unsigned int)rowEntity[colRow[p.x]] << 32) | (unsigned int)rowEntity[colRow[p.y]];
+                if (isNonColliding(nonColl, nNonColl, k)) bin = -1;
+            }
+            if (bin >= 0) atomicAdd(&sh[bin], 1);
+        }
+        pairBin[i] = bin;
+    }
+    __syncthreads();
+    if (threadIdx.x < BIN_COUNT && sh[threadIdx.x]) atomicAdd(&counters[CNT_BIN0 + threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x == BIN_COUNT && sh[BIN_COUNT]) atomicAdd(&counters[CNT_TRIGGERS], sh[BIN_COUNT]);
+}
+
+__global__ void k_bin_starts(int* counters) {
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < BIN_COUNT; ++b) { counters[CNT_BINSTART + b] = run; run += counters[CNT_BIN0 + b]; counters[CNT_BIN0 + b] = 0; }
+        counters[CNT_BINSTART + BIN_COUNT] = run;
+        counters[CNT_MESH_PAIRS] = run - counters[CNT_BINSTART + BIN_MESH];
+    }
+}
+
+__global__ void k_pair_scatter(const int* __restrict__ pairBin, int* __restrict__ pairOrder, int* __restrict__ counters, int maxPairs) {
+    int n = min(counters[CNT_PAIRS], maxPairs);
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+        int i = base + (threadIdx.x & 31);
+        int bin = i < n ? pairBin[i] : -1;
+        unsigned int act = __ballot_sync(0xffffffffu, bin >= 0);
+        if (bin >= 0) {
+            unsigned int peers = __match_any_sync(act, bin);
+            int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+            int leader = __ffs(peers) - 1;
+            int b = 0;
+            if (rank == 0) b = atomicAdd(&counters[CNT_BIN0 + bin], __popc(peers));
+            b = __shfl_sync(peers, b, leader);
+            pairOrder[counters[CNT_BINSTART + bin] + b + rank] = i;
+        }
+    }
+}
+
+// ---- manifold arena append ------------------------------------------------------------------------------------
+__device__ __forceinline__ int warpReserve(int want, int* counter) {
+    // every lane of the warp must call; returns this lane's base slot for `want` entries
+    int lane = threadIdx.x & 31;
+    int inc = want;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    int total = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (lane == 31 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - want;
+}
+
+__device__ __forceinline__ void storeManifold(int slot, int maxManifolds, int colA, int colB, const Manifold& m, bool flip,
+                                              int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int* counters) {
+    if (slot >= maxManifolds) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); return; }
+    mKey[slot] = make_int4(colA, colB, m.tri, m.np);
+    V3 n = flip ? -m.n : m.n;
+    mNormal[slot] = f4(n);
+    for (int k = 0; k < m.np; ++k) {
+        mPts[8 * (size_t)slot + 2 * k] = f4(flip ? m.p1[k] : m.p0[k]);
+        mPts[8 * (size_t)slot + 2 * k + 1] = f4(flip ? m.p0[k] : m.p1[k]);
+    }
+}
+
+// ---- analytic bins ------------------------------------------------------------------------------------------------
+template <int BIN>
+__global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                 const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                 const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                 const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
+    int lane = threadIdx.x & 31;
+    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+        int idx = base + lane;
+        bool hit = false, flip = false;
+        Manifold m; m.np = 0; m.tri = -1;
+        int a = 0, b = 0;
+        if (idx < end) {
+            int2 p = pairs[pairOrder[idx]];
+            a = p.x; b = p.y;
+            int t0 = colType[a], t1 = colType[b];
+            float4 q0 = colParams[a], q1 = colParams[b];
+            V3 pos0 = mk3(wpos[a]), pos1 = mk3(wpos[b]);
+            Q4 or0 = mkq(wquat[a]), or1 = mkq(wquat[b]);
+            if (BIN == BIN_SS) hit = collideSphereSphere(pos0, q0.x, pos1, q1.x, m);
+            else if (BIN == BIN_CC) hit = collideCapsuleCapsule(pos0, or0, q0.x, q0.y, pos1, or1, q1.x, q1.y, m);
+            else if (BIN == BIN_BB) hit = collideBoxBox(pos0, or0, mk3(q0.x, q0.y, q0.z), pos1, or1, mk3(q1.x, q1.y, q1.z), m);
+            else if (BIN == BIN_SC) {
+                if (t0 == PB_SPHERE) hit = collideSphereCapsule(pos0, q0.x, pos1, or1, q1.x, q1.y, m);
+                else { hit = collideSphereCapsule(pos1, q1.x, pos0, or0, q0.x, q0.y, m); flip = true; }
+            } else if (BIN == BIN_SB) {
+                if (t0 == PB_SPHERE) hit = collideSphereBox(pos0, q0.x, pos1, or1, mk3(q1.x, q1.y, q1.z), m);
+                else { hit = collideSphereBox(pos1, q1.x, pos0, or0, mk3(q0.x, q0.y, q0.z), m); flip = true; }
+            } else if (BIN == BIN_CB) {
+                if (t0 == PB_CAPSULE) hit = collideCapsuleBox(pos0, or0, q0.x, q0.y, pos1, or1, mk3(q1.x, q1.y, q1.z), m);
+                else { hit = collideCapsuleBox(pos1, or1, q1.x, q1.y, pos0, or0, mk3(q0.x, q0.y, q0.z), m); flip = true; }
+            } else if (BIN == BIN_GJK) {
+                hit = collideGjkPair(t0, q0, pos0, or0, colMesh[a], t1, q1, pos1, or1, colMesh[b], convexes, m, flip, counters);
+            }
+            hit = hit && m.np > 0;
+        }
+        int slot = warpReserve(hit ? 1 : 0, &counters[CNT_RAWM]);
+        if (hit) storeManifold(slot, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+    }
+}
+
+// ---- mesh bin --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                 const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
+                                                 const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                 const PbTriMeshDev* __restrict__ meshes, const PbConvexDev* __restrict__ convexes,
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    int start = counters[CNT_BINSTART + BIN_MESH], end = counters[CNT_BINSTART + BIN_MESH + 1];
+    int lane = threadIdx.x & 31;
+    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+        int idx = base + lane;
+        TriContact contacts[PB_MAX_TRI_CONTACTS];
+        unsigned char order[PB_MAX_TRI_CONTACTS];   // generation order: >=0 index into contacts
+        int nGen = 0;
+        int a = 0, b = 0, shape = 0, type = 0;
+        bool flip = false;
+        V3 pos1 = mk3(0.f), localPos = mk3(0.f); Q4 or1 = mkq(make_float4(0, 0, 0, 1)), localOr = or1;
+        float4 prm = make_float4(0, 0, 0, 0);
+        int meshId = 0;
+        if (idx < end) {
+            int2 p = pairs[pairOrder[idx]];
+            a = p.x; b = p.y;
+            // Collision.cpp:897-907: mesh on side 0 -> collide (shape1, mesh0) and flip
+            flip = colType[a] == PB_TRIANGLE_MESH;
+            shape = flip ? b : a;
+            int meshCol = flip ? a : b;
+            type = colType[shape];
+            prm = colParams[shape];
+            meshId = colMesh[meshCol];
+            V3 pos0 = mk3(wpos[shape]); Q4 or0 = mkq(wquat[shape]);
+            pos1 = mk3(wpos[meshCol]); or1 = mkq(wquat[meshCol]);
+            Q4 invOr1 = qinverse(or1);
+            localPos = rotate(invOr1, pos0 - pos1);
+            localOr = qmul(invOr1, or0);
+            if (type == PB_SPHERE || type == PB_CAPSULE) {
+                bool overflow = false;
+                int cnt = meshCollect(type, prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow);
+                if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+                // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
+                unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
+                int nVoid = 0;
+                unsigned char live[PB_MAX_TRI_CONTACTS];
+                int nLive = cnt;
+                for (int i = 0; i < cnt; ++i) live[i] = (unsigned char)i;
+                const PbTriMeshDev& mesh = meshes[meshId];
+                for (int i = nLive - 1; i >= 0; --i) {
+                    int ci = live[i];
+                    if (contacts[ci].feature == TF_FACE) {
+                        int4 ti = mesh.tris[contacts[ci].tri];
+                        voidInsert(voidSet, nVoid, (unsigned)ti.x); voidInsert(voidSet, nVoid, (unsigned)ti.y); voidInsert(voidSet, nVoid, (unsigned)ti.z);
+                        order[nGen++] = (unsigned char)ci;
+                        live[i] = live[nLive - 1];
+                        --nLive;
+                    }
+                }
+                // stable insertion sort by distance (std::sort on <=16 elements is an insertion sort, CTM.cpp:932)
+                for (int i = 1; i < nLive; ++i) {
+                    unsigned char v = live[i];
+                    float d = contacts[v].dist;
+                    int j = i;
+                    while (j > 0 && d < contacts[live[j - 1]].dist) { live[j] = live[j - 1]; --j; }
+                    live[j] = v;
+                }
+                // pass 2 (CTM.cpp:934-953)
+                for (int i = 0; i < nLive; ++i) {
+                    int ci = live[i];
+                    const TriContact& tc = contacts[ci];
+                    int4 ti = mesh.tris[tc.tri];
+                    unsigned int vi[3] = { (unsigned)ti.x, (unsigned)ti.y, (unsigned)ti.z };
+                    if (tc.feature == TF_EDGE) {
+                        if (voided(voidSet, nVoid, vi[(tc.fidx + 1) % 3]) && voided(voidSet, nVoid, vi[(tc.fidx + 2) % 3])) continue;
+                    } else {
+                        if (voided(voidSet, nVoid, vi[tc.fidx])) continue;
+                    }
+                    order[nGen++] = (unsigned char)ci;
+                    voidInsert(voidSet, nVoid, vi[0]); voidInsert(voidSet, nVoid, vi[1]); voidInsert(voidSet, nVoid, vi[2]);
+                }
+            } else {
+                atomicOr(&counters[CNT_STATUS], PB_STATUS_UNSUPPORTED_SHAPE);
+            }
+        }
+        int slot = warpReserve(nGen, &counters[CNT_RAWM]);
+        for (int g = 0; g < nGen; ++g) {
+            const TriContact& tc = contacts[order[g]];
+            Manifold m; m.np = 0; m.tri = tc.tri;
+            if (type == PB_CAPSULE && tc.feature == TF_FACE) {
+                if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
+            } else {
+                manifoldFromClosest(pos1, or1, tc, m);
+            }
+            m.tri = tc.tri;
+            // a == side 0 of the pair; manifolds are computed shape->mesh, flip when the mesh is side 0
+            storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+        }
+    }
+}
+
+int pb_narrowphase(pb_ctx* ctx) {
+    if (ctx->nCol < 2) return PB_OK;
+    int blocks = ctx->numSMs * 8;
+    int* pairBin = ctx->pairOrder + ctx->caps.max_pairs;   // second half of the pairOrder allocation
+    k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
+                                                      ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding);
+    k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
+    k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
+    const int2* pairs = (const int2*)ctx->pairs;
+#define LAUNCH_PRIM(BIN) k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
+        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
+    LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
+    if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
+#undef LAUNCH_PRIM
+    if (!ctx->triMeshes.empty())
+        k_np_mesh<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+                                                   ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}

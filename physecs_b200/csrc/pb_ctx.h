@@ -1,0 +1,192 @@
+// Internal context: every device-resident SoA array of a scene, per-step arenas and scratch.
+// All arrays are float4 / int aligned SoA so each kernel's loads coalesce (DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/physecs_b200.h"
+
+#define PB_MAX_COLORS 64          // contact colours: 0..62 parallel, 63 = sequential overflow bucket
+#define PB_OVERFLOW_COLOR 63
+#define PB_JOINT_COLORS 9         // reference JointGraph: 8 colours + overflow (Physecs.h:137-152)
+#define PB_MAX_TRI_CONTACTS 24    // triangle contacts kept per (shape, mesh) pair
+#define PB_NUM_BINS 16            // narrowphase shape-pair bins
+#define PB_MAX_JOINT_ROWS 8
+
+struct PbTriMesh {
+    int nVerts = 0, nTris = 0, nNodes = 0;
+    float4* verts = nullptr;       // xyz
+    int4* tris = nullptr;          // i0,i1,i2 (post-build order), w unused
+    float4* triNormal = nullptr;   // xyz
+    float4* triCentroid = nullptr; // xyz
+    float4* nodeMin = nullptr;     // xyz, w = triCount (int bits)
+    float4* nodeMax = nullptr;     // xyz, w = index    (int bits)
+    float bmin[3], bmax[3];        // local-space bounds of all vertices (BoundsUtil.cpp:77-85 needs every vertex)
+};
+
+struct PbConvex {
+    int nVerts = 0, nVertsPadded = 0, nFaces = 0;
+    float4* verts = nullptr;        // padded to x4 by repeating the last vertex (ConvexMesh.cpp:8-10)
+    int* faceOffsets = nullptr;     // nFaces+1
+    int* faceIndices = nullptr;
+    float4* faceNormal = nullptr;
+    float4* faceCentroid = nullptr;
+};
+
+// device-side view of registered meshes (array of these lives in device memory)
+struct PbTriMeshDev {
+    const float4* verts; const int4* tris; const float4* triNormal; const float4* triCentroid;
+    const float4* nodeMin; const float4* nodeMax; int nTris; int nNodes;
+    float bmin[3]; float bmax[3];
+};
+struct PbConvexDev {
+    const float4* verts; const int* faceOffsets; const int* faceIndices; const float4* faceNormal;
+    const float4* faceCentroid; int nVerts; int nVertsPadded; int nFaces; int pad;
+};
+
+// header of the per-step device counters block (one int each, zeroed at step start)
+enum {
+    CNT_PAIRS = 0, CNT_MANIFOLDS, CNT_POINTS, CNT_STATUS, CNT_MESH_PAIRS, CNT_TRIGGERS, CNT_OVERFLOW, CNT_NCOLORS,
+    CNT_RAWM,                           // raw manifold arena entries (incl. 0-point holes); CNT_MANIFOLDS = solve count
+    CNT_BIN0 = 16,                      // PB_NUM_BINS bin counters
+    CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
+    CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
+    CNT_TOTAL = 192
+};
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    pb_caps caps{};
+    std::string err;
+    int numSMs = 148;
+
+    // ---- bodies -------------------------------------------------------------------------------
+    int nDyn = 0, nStatic = 0, nRows = 0;
+    int* rowEntity = nullptr;        // [rows] entt::entity integer
+    float4* pos = nullptr;           // [rows] xyz
+    float4* quat = nullptr;          // [rows] xyzw
+    float4* vel = nullptr;           // [dyn] component velocity (substep-start value)
+    float4* angvel = nullptr;
+    float4* velPre = nullptr;        // [dyn] post-gravity/gyro value friction rows read (quirk Q3)
+    float4* angvelPre = nullptr;
+    float4* velLive = nullptr;       // [dyn] velocityTemp the solver iterates on
+    float4* angvelLive = nullptr;
+    float4* comInvMass = nullptr;    // [dyn] com xyz, invMass w
+    float4* invIL = nullptr;         // [3*dyn] local inverse inertia columns
+    float4* invIW = nullptr;         // [3*dyn] world inverse inertia columns (massTemp)
+    int* kinematic = nullptr;        // [dyn]
+    float4* pseudoLin = nullptr;     // [dyn] xyz, w = constraintCount (int bits)
+    float4* pseudoAng = nullptr;     // [dyn]
+    unsigned long long* colorMask = nullptr; // [dyn] contact colours in use per body
+    float* stage = nullptr;          // device staging for packed host uploads/downloads
+    size_t stageBytes = 0;
+
+    // ---- colliders ------------------------------------------------------------------------------
+    int nCol = 0;
+    int* colRow = nullptr; int* colIndex = nullptr; int* colType = nullptr; int* colFlags = nullptr; int* colData = nullptr;
+    int* colMesh = nullptr;
+    float4* colLPos = nullptr; float4* colLQuat = nullptr; float4* colParams = nullptr; float4* colMat = nullptr;
+    float4* colWPos = nullptr; float4* colWQuat = nullptr;   // world pose, refreshed each step
+    float4* aabbMin = nullptr; float4* aabbMax = nullptr;     // persistent bounds (BroadPhaseEntry::bounds)
+    std::vector<int> hColType, hColMesh, hColRow;   // host mirrors (trimesh colliders are found on the host)
+    int* rowMark = nullptr;          // [rows] scratch marks for pb_move_rows
+
+    // ---- meshes ------------------------------------------------------------------------------------
+    std::vector<PbTriMesh> triMeshes; std::vector<PbConvex> convexes;
+    PbTriMeshDev* triMeshDev = nullptr; PbConvexDev* convexDev = nullptr;
+
+    // ---- non-colliding entity pairs (sorted u64 keys) ----------------------------------------------
+    unsigned long long* nonColliding = nullptr; int nNonColliding = 0;
+
+    // ---- broadphase scratch ---------------------------------------------------------------------------
+    unsigned int* mortonA = nullptr; unsigned int* mortonB = nullptr; int* leafIdA = nullptr; int* leafIdB = nullptr;
+    unsigned int* radixHist = nullptr; int radixTiles = 0;
+    float* sceneBounds = nullptr;    // 6 floats (ordered-int encoded) min/max of AABB centres
+    int* nodeLeft = nullptr; int* nodeRight = nullptr; int* nodeParent = nullptr; int* leafParent = nullptr;
+    int* nodeRangeLast = nullptr; int* nodeFlag = nullptr;
+    float4* nodeMin = nullptr; float4* nodeMax = nullptr;
+    int2* pairs = nullptr;           // [maxPairs] (colA, colB); A is the lower-entity side
+    int* pairOrder = nullptr;        // [2*maxPairs] pair indices grouped by bin | bin of each pair
+
+    // ---- manifolds (raw narrowphase output) -----------------------------------------------------------
+    int4* mKey = nullptr;            // (colA, colB, tri, numPoints)
+    float4* mNormal = nullptr;       // xyz
+    float4* mPts = nullptr;          // [8*maxManifolds]: slot 2k = position0, 2k+1 = position1
+    int* mColor = nullptr;           // colour per raw manifold
+    int* mSorted = nullptr;          // [maxManifolds] raw index per solve slot
+    int* mSortTmp = nullptr; unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
+
+    // ---- contact constraints (solve order) ---------------------------------------------------------------
+    int2* cBodies = nullptr;         // solver body index or -1 (b0, b1)
+    int2* cRowsT = nullptr;          // transform rows (row0, row1)
+    float4* cNormal = nullptr;       // n xyz, friction w
+    float4* cSoft = nullptr;         // isSoft, frequency, dampingRatio, unused
+    // per point, double-buffered (prev step kept for the contact cache)
+    float4* pR0T[2] = {nullptr, nullptr};   // local r0 xyz, targetVelocity w
+    float4* pR1 = nullptr;                  // local r1 xyz
+    int curBuf = 0;
+    // per-substep rows per point
+    float4* rowA = nullptr;          // r0xn xyz, c
+    float4* rowB = nullptr;          // r1xn xyz, effMassN (1/k or 0)
+    float4* rowC = nullptr;          // I0^-1 (r0xn) xyz, targetVelocity
+    float4* rowD = nullptr;          // I1^-1 (r1xn) xyz, lambdaT0 (friction increment, constant within a substep)
+    float4* rowE = nullptr;          // t xyz, kT!=0 flag
+    float4* rowF = nullptr;          // I0^-1 (r0xt) xyz
+    float4* rowG = nullptr;          // I1^-1 (r1xt) xyz
+    float2* rowL = nullptr;          // totalLambdaN, totalLambdaT
+    // contact cache (hash table over previous step's manifolds)
+    unsigned long long* cacheTag[2] = {nullptr, nullptr}; int4* cacheVal[2] = {nullptr, nullptr}; int cacheSize = 0;
+    bool cacheValid = false;
+    int* cPointOfsBuf[2] = {nullptr, nullptr}; int* cNpBuf[2] = {nullptr, nullptr};
+
+    // ---- joints ---------------------------------------------------------------------------------------------
+    int nJoints = 0;
+    int jointColorStart[PB_JOINT_COLORS + 1] = {0};
+    int* jType = nullptr; int2* jRows = nullptr; int2* jBodies = nullptr;
+    float4* jA0P = nullptr; float4* jA0Q = nullptr; float4* jA1P = nullptr; float4* jA1Q = nullptr;
+    float4* jParams = nullptr;       // [2*J]
+    float4* jState = nullptr;        // [2*J] persistent per-joint state (gear angles, prismatic limit flags)
+    int* jRowOfs = nullptr; int* jNumRows = nullptr; int nJointRows = 0;
+    float4* jr[8] = {nullptr};       // joint row arrays (see joints.cu)
+    float* jrLambda = nullptr;
+
+    // ---- counters / host mirrors ---------------------------------------------------------------------------
+    int* counters = nullptr;         // CNT_TOTAL ints on device
+    int* hCounters = nullptr;        // pinned mirror
+    pb_counts lastCounts{};
+    pb_timings lastTimings{};
+    cudaEvent_t ev[6] = {nullptr};
+    bool triggersPresent = false;
+};
+
+// ---- helpers --------------------------------------------------------------------------------------------------
+int pb_fail(pb_ctx* ctx, int code, const std::string& msg);
+#define PB_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return pb_fail((ctx), PB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T> static inline int pb_alloc(pb_ctx* ctx, T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return pb_fail(ctx, PB_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return PB_OK;
+}
+
+static inline int pb_grid(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
+
+// stage launches (implemented in the .cu files)
+int pb_broadphase(pb_ctx* ctx);
+int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);
+int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin);
+int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);
+int pb_world_poses(pb_ctx* ctx);
+int pb_narrowphase(pb_ctx* ctx);
+int pb_contact_build(pb_ctx* ctx, int nRaw);
+int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
+int pb_joints_alloc(pb_ctx* ctx);
+
+// generic device primitives (primitives.cu)
+int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,
+                        unsigned int* hist, int histCapTiles, bool* resultInA);
+int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch);

@@ -1,0 +1,180 @@
+// Device-wide primitives used by several stages: exclusive scan and a stable LSD radix sort of
+// (32-bit key, 32-bit payload) pairs.  They replace the reference's persistent insertion sort
+// (src/Physecs.cpp:121-133) as the ordering machinery of the broadphase and also order manifolds by colour.
+//
+// Radix pass = 3 launches: per-warp-tile digit histogram -> scan of the (digit-major) histogram ->
+// stable scatter where each warp ranks its keys round by round with __match_any_sync.
+#include "pb_ctx.h"
+
+#define SCAN_THREADS 1024
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int warpInclusiveScan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// inclusive scan over a block of SCAN_THREADS; returns inclusive value, total via *total
+__device__ __forceinline__ int blockInclusiveScan(int v, int* total) {
+    __shared__ int warpSums[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warpInclusiveScan(v, lane);
+    if (lane == 31) warpSums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = (lane < (blockDim.x >> 5)) ? warpSums[lane] : 0;
+        s = warpInclusiveScan(s, lane);
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    int offset = w ? warpSums[w - 1] : 0;
+    if (total) *total = warpSums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return inc + offset;
+}
+
+__global__ void k_scan_reduce(const int* __restrict__ in, int* __restrict__ blockSums, int n) {
+    int base = blockIdx.x * SCAN_TILE;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n) s += in[idx];
+    }
+    int total;
+    blockInclusiveScan(s, &total);
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_blocksums(int* __restrict__ blockSums, int nb) {
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        int idx = base + threadIdx.x;
+        int v = idx < nb ? blockSums[idx] : 0;
+        int total;
+        int inc = blockInclusiveScan(v, &total);
+        int c = carry;
+        if (idx < nb) blockSums[idx] = c + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ blockSums, int n) {
+    int base = blockIdx.x * SCAN_TILE;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        v[i] = idx < n ? in[idx] : 0;
+        s += v[i];
+    }
+    int inc = blockInclusiveScan(s, nullptr);
+    int run = blockSums[blockIdx.x] + inc - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n) out[idx] = run;
+        run += v[i];
+    }
+}
+
+// out[i] = sum(in[0..i-1]); in and out may alias.  scratch: at least ceil(n/4096)+1 ints.
+int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch) {
+    if (n <= 0) return PB_OK;
+    int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, scratch, n);
+    k_scan_blocksums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scratch, nb);
+    k_scan_final<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, scratch, n);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+#define RS_WARPS 8
+#define RS_ITEMS 16
+#define RS_WARP_TILE (32 * RS_ITEMS)        // keys per warp tile
+
+__global__ void k_radix_hist(const unsigned int* __restrict__ keys, unsigned int* __restrict__ hist, int n, int shift, int numTiles) {
+    __shared__ unsigned int sh[RS_WARPS][256];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < 256; i += 32) sh[w][i] = 0;
+    __syncwarp();
+    int tile = blockIdx.x * RS_WARPS + w;
+    if (tile < numTiles) {
+        int base = tile * RS_WARP_TILE;
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            int idx = base + r * 32 + lane;
+            if (idx < n) atomicAdd(&sh[w][(keys[idx] >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) hist[(size_t)i * numTiles + tile] = sh[w][i];
+    }
+}
+
+__global__ void k_radix_scatter(const unsigned int* __restrict__ keys, const int* __restrict__ vals,
+                                unsigned int* __restrict__ keysOut, int* __restrict__ valsOut,
+                                const unsigned int* __restrict__ hist, int n, int shift, int numTiles) {
+    __shared__ unsigned int sh[RS_WARPS][256];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x * RS_WARPS + w;
+    if (tile >= numTiles) return;
+    for (int i = lane; i < 256; i += 32) sh[w][i] = hist[(size_t)i * numTiles + tile];
+    __syncwarp();
+    int base = tile * RS_WARP_TILE;
+    unsigned int ltMask = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        unsigned int active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            unsigned int k = keys[idx];
+            int v = vals[idx];
+            unsigned int d = (k >> shift) & 255u;
+            unsigned int peers = __match_any_sync(active, d);
+            unsigned int rank = __popc(peers & ltMask);
+            unsigned int b = sh[w][d];
+            __syncwarp(active);
+            if (rank == 0) sh[w][d] = b + __popc(peers);
+            __syncwarp(active);
+            keysOut[b + rank] = k;
+            valsOut[b + rank] = v;
+        }
+    }
+}
+
+// Sort (keysA, valsA) by the low `bits` bits of the key, 8 bits per pass, ping-ponging with (keysB, valsB).
+// hist must hold 256 * ceil(n/512) (+ scan scratch of ceil(that/4096)+1) uints.
+int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,
+                        unsigned int* hist, int histCapTiles, bool* resultInA) {
+    *resultInA = true;
+    if (n <= 1) return PB_OK;
+    int numTiles = (n + RS_WARP_TILE - 1) / RS_WARP_TILE;
+    if (numTiles > histCapTiles) return pb_fail(ctx, PB_ECAPACITY, "radix sort histogram capacity");
+    int blocks = (numTiles + RS_WARPS - 1) / RS_WARPS;
+    int histN = 256 * numTiles;
+    int* scanScratch = (int*)(hist + (size_t)256 * histCapTiles);
+    unsigned int* src = keysA; int* srcV = valsA; unsigned int* dst = keysB; int* dstV = valsB;
+    for (int shift = 0; shift < bits; shift += 8) {
+        k_radix_hist<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
+        int rc = pb_exclusive_scan(ctx, (const int*)hist, (int*)hist, histN, scanScratch);
+        if (rc) return rc;
+        k_radix_scatter<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
+        unsigned int* t = src; src = dst; dst = t;
+        int* tv = srcV; srcV = dstV; dstV = tv;
+        *resultInA = !*resultInA;
+    }
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}

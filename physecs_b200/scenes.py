@@ -1,0 +1,464 @@
+"""Flat scene descriptions + the synthetic scene generators of BASELINE.json's configs.
+
+A SceneDesc is the array form of what an application would put in its entt::registry
+(TransformComponent / RigidBodyCollisionComponent / RigidBodyDynamicComponent, reference
+include/Physecs/Components.h:6-17, src/Transform.h:6-10).  The same description feeds the oracle harness
+(oracle/ref.py) and the device context (physecs_b200/capi.py), so both sides see identical inputs.
+
+Mass properties follow the reference's setup-time helper (src/MassUtil.cpp:6-28, :73-192) including its
+box quirk (half extents used in the full-extent formula); they are inputs to both sides.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import List, Optional
+
+import numpy as np
+
+SPHERE, CAPSULE, BOX, CONVEX_MESH, TRIANGLE_MESH = 0, 1, 2, 3, 4
+J_FIXED, J_REVOLUTE, J_SPHERICAL, J_UNIVERSAL, J_PRISMATIC, J_GEAR, J_SERVO = range(7)
+F_COLLISION, F_DYNAMIC, F_KINEMATIC = 1, 2, 4
+COL_TRIGGER, COL_ENABLE_SIM = 1, 2
+
+f32 = np.float32
+
+
+@dataclasses.dataclass
+class ConvexMeshDesc:
+    verts: np.ndarray          # [nv,3]
+    face_offsets: np.ndarray   # [nf+1]
+    face_indices: np.ndarray
+    face_normals: np.ndarray   # [nf,3]
+    face_centroids: np.ndarray # [nf,3]
+
+
+@dataclasses.dataclass
+class TriMeshDesc:
+    verts: np.ndarray    # [nv,3] float32
+    indices: np.ndarray  # [3*nt] uint32
+
+
+@dataclasses.dataclass
+class SceneDesc:
+    """Entities in creation order (entity id == index)."""
+    pos: np.ndarray        # [n,3]
+    quat: np.ndarray       # [n,4] xyzw
+    flags: np.ndarray      # [n] F_* bits
+    vel: np.ndarray        # [n,3]
+    angvel: np.ndarray     # [n,3]
+    inv_mass: np.ndarray   # [n]
+    com: np.ndarray        # [n,3]
+    inv_inertia: np.ndarray  # [n,9] column-major
+    col_offsets: np.ndarray  # [n+1]
+    col_lpos: np.ndarray     # [nc,3]
+    col_lquat: np.ndarray    # [nc,4]
+    col_type: np.ndarray     # [nc]
+    col_params: np.ndarray   # [nc,4]
+    col_mesh: np.ndarray     # [nc]
+    col_material: np.ndarray # [nc,3] friction, restitution, damping
+    col_flags: np.ndarray    # [nc]
+    col_data: np.ndarray     # [nc]
+    convex: List[ConvexMeshDesc] = dataclasses.field(default_factory=list)
+    trimesh: List[TriMeshDesc] = dataclasses.field(default_factory=list)
+    joints: list = dataclasses.field(default_factory=list)       # (type, e0, a0p, a0q, e1, a1p, a1q, params)
+    no_collide: list = dataclasses.field(default_factory=list)   # (e0, e1)
+    substeps: int = 8
+    iterations: int = 2
+    gravity: float = 9.81
+    dt: float = 1.0 / 60.0
+    name: str = ""
+
+    @property
+    def n(self):
+        return len(self.pos)
+
+    @property
+    def n_dynamic(self):
+        return int(np.count_nonzero(self.flags & F_DYNAMIC))
+
+    def dynamic_entities(self):
+        return np.nonzero(self.flags & F_DYNAMIC)[0].astype(np.int32)
+
+    def static_entities(self):
+        return np.nonzero((self.flags & F_DYNAMIC) == 0)[0].astype(np.int32)
+
+
+class SceneBuilder:
+    def __init__(self, name=""):
+        self.name = name
+        self.ent = []
+        self.cols = []
+        self.convex = []
+        self.trimesh = []
+        self.joints = []
+        self.no_collide = []
+
+    def add_convex(self, m: ConvexMeshDesc):
+        self.convex.append(m)
+        return len(self.convex) - 1
+
+    def add_trimesh(self, m: TriMeshDesc):
+        self.trimesh.append(m)
+        return len(self.trimesh) - 1
+
+    def add_body(self, pos, quat=(0, 0, 0, 1), colliders=(), dynamic=True, kinematic=False, mass=1.0, vel=(0, 0, 0), angvel=(0, 0, 0)):
+        """colliders: list of dicts(type, params, lpos, lquat, mesh, material, flags, data)"""
+        e = len(self.ent)
+        cols = []
+        for c in colliders:
+            d = dict(lpos=(0, 0, 0), lquat=(0, 0, 0, 1), mesh=-1, material=(0.4, 0.2, 0.0), flags=COL_ENABLE_SIM, data=0)
+            d.update(c)
+            p = list(d["params"]) + [0.0] * (4 - len(d["params"]))
+            d["params"] = p
+            cols.append(d)
+        flags = (F_COLLISION if cols else 0) | (F_DYNAMIC if dynamic else 0) | (F_KINEMATIC if (dynamic and kinematic) else 0)
+        com = np.zeros(3, f32)
+        inv_i = np.zeros(9, f32)
+        inv_m = f32(0)
+        if dynamic:
+            com, inv_inertia = compute_mass_props(cols, mass, self.convex)
+            inv_i = inv_inertia.T.reshape(9)  # column-major
+            inv_m = f32(1.0) / f32(mass)
+        self.ent.append(dict(pos=pos, quat=quat, flags=flags, vel=vel, angvel=angvel, inv_mass=inv_m, com=com, inv_i=inv_i, cols=cols))
+        return e
+
+    def add_joint(self, jtype, e0, a0p, a0q, e1, a1p, a1q, params=()):
+        p = list(params) + [0.0] * (8 - len(params))
+        self.joints.append((jtype, e0, np.asarray(a0p, f32), np.asarray(a0q, f32), e1, np.asarray(a1p, f32), np.asarray(a1q, f32), np.asarray(p, f32)))
+
+    def build(self, **kw) -> SceneDesc:
+        n = len(self.ent)
+        A = lambda key, w: np.ascontiguousarray(np.array([e[key] for e in self.ent], dtype=f32).reshape(n, w) if w > 1 else np.array([e[key] for e in self.ent], dtype=f32))
+        cols = [c for e in self.ent for c in e["cols"]]
+        nc = len(cols)
+        offs = np.zeros(n + 1, np.int32)
+        offs[1:] = np.cumsum([len(e["cols"]) for e in self.ent])
+        C = lambda key, w, dt=f32: np.ascontiguousarray(np.array([c[key] for c in cols], dtype=dt).reshape(nc, w) if w > 1 else np.array([c[key] for c in cols], dtype=dt))
+        d = SceneDesc(
+            pos=A("pos", 3), quat=A("quat", 4), flags=np.array([e["flags"] for e in self.ent], np.int32), vel=A("vel", 3), angvel=A("angvel", 3),
+            inv_mass=A("inv_mass", 1), com=A("com", 3), inv_inertia=A("inv_i", 9), col_offsets=offs,
+            col_lpos=C("lpos", 3), col_lquat=C("lquat", 4), col_type=C("type", 1, np.int32), col_params=C("params", 4), col_mesh=C("mesh", 1, np.int32),
+            col_material=C("material", 3), col_flags=C("flags", 1, np.int32), col_data=C("data", 1, np.int32),
+            convex=self.convex, trimesh=self.trimesh, joints=self.joints, no_collide=self.no_collide, name=self.name)
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+
+def bulk_scene(name, pos, quat, flags, col_type, col_params, mass, material=(0.4, 0.2, 0.0), vel=None, angvel=None,
+               col_mesh=None, trimesh=(), convex=(), **kw) -> SceneDesc:
+    """Vectorised builder for the big configs: exactly one collider per entity at the body origin."""
+    n = len(pos)
+    pos = np.ascontiguousarray(pos, f32); quat = np.ascontiguousarray(quat, f32)
+    flags = np.ascontiguousarray(flags, np.int32)
+    col_type = np.ascontiguousarray(col_type, np.int32)
+    col_params = np.ascontiguousarray(col_params, f32)
+    dyn = (flags & F_DYNAMIC) != 0
+    inv_mass = np.where(dyn, f32(1.0) / np.asarray(mass, f32), f32(0)).astype(f32)
+    inv_i = np.zeros((n, 9), f32)
+    m = np.broadcast_to(np.asarray(mass, f32), (n,))
+    diag = single_shape_inertia_diag(col_type, col_params, m)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv_diag = np.where(dyn[:, None] & (diag != 0), f32(1.0) / diag, f32(0)).astype(f32)
+    inv_i[:, 0] = inv_diag[:, 0]; inv_i[:, 4] = inv_diag[:, 1]; inv_i[:, 8] = inv_diag[:, 2]
+    mat = np.broadcast_to(np.asarray(material, f32), (n, 3)).copy()
+    d = SceneDesc(
+        pos=pos, quat=quat, flags=flags | F_COLLISION,
+        vel=np.zeros((n, 3), f32) if vel is None else np.ascontiguousarray(vel, f32),
+        angvel=np.zeros((n, 3), f32) if angvel is None else np.ascontiguousarray(angvel, f32),
+        inv_mass=inv_mass, com=np.zeros((n, 3), f32), inv_inertia=inv_i,
+        col_offsets=np.arange(n + 1, dtype=np.int32), col_lpos=np.zeros((n, 3), f32),
+        col_lquat=np.tile(np.array([0, 0, 0, 1], f32), (n, 1)), col_type=col_type, col_params=col_params,
+        col_mesh=np.full(n, -1, np.int32) if col_mesh is None else np.ascontiguousarray(col_mesh, np.int32),
+        col_material=mat, col_flags=np.full(n, COL_ENABLE_SIM, np.int32), col_data=np.zeros(n, np.int32),
+        convex=list(convex), trimesh=list(trimesh), name=name)
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+# ---- mass properties (reference src/MassUtil.cpp) ---------------------------------------------------------------
+def single_shape_inertia_diag(col_type, prm, mass):
+    """Diagonal inertia of a single collider at the origin with identity local orientation (fp32 like the reference)."""
+    n = len(col_type)
+    out = np.ones((n, 3), f32)
+    m = mass.astype(f32)
+    s = col_type == SPHERE
+    r = prm[:, 0]
+    v = f32(2.0) * m * r * r / f32(5.0)
+    out[s] = np.stack([v, v, v], 1)[s]
+    c = col_type == CAPSULE
+    hh, rr = prm[:, 0], prm[:, 1]
+    pi = f32(math.pi)
+    vc = f32(2) * rr * rr * pi * hh
+    vs = f32(4) * rr ** 3 * pi / f32(3)
+    vt = vc + vs
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mc = vc * m / vt
+        ms = vs * m / vt
+    ixx = mc * (hh * hh / f32(3) + rr * rr / f32(4)) + ms * (hh * hh + f32(3) * hh * rr / f32(4) + f32(2) * rr * rr / f32(5))
+    iyy = mc * rr * rr / f32(2) + ms * f32(2) * rr * rr / f32(5)
+    out[c] = np.stack([ixx, iyy, ixx], 1)[c].astype(f32)
+    b = col_type == BOX
+    mm = m / f32(12)
+    x, y, z = prm[:, 0] ** 2, prm[:, 1] ** 2, prm[:, 2] ** 2
+    out[b] = np.stack([mm * (y + z), mm * (x + z), mm * (x + y)], 1)[b].astype(f32)
+    return out
+
+
+def quat_to_mat(q):
+    x, y, z, w = [float(v) for v in q]
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]], dtype=np.float64)
+
+
+def compute_mass_props(cols, mass, convex_meshes):
+    """computeCOMAndInvInertiaTensor (reference src/MassUtil.cpp:73-185) for sphere/capsule/box/convex colliders."""
+    pi = math.pi
+    com = np.zeros(3)
+    total = 0.0
+    vols = []
+    for c in cols:
+        if c["flags"] & COL_TRIGGER:
+            vols.append(0.0)
+            continue
+        t, p = c["type"], c["params"]
+        if t == SPHERE:
+            v = 4 * pi * p[0] ** 3 / 3
+        elif t == CAPSULE:
+            v = 4 * pi * p[1] ** 3 / 3 + p[1] * p[1] * pi * p[0] * 2
+        elif t == BOX:
+            v = p[0] * p[1] * p[2]
+        elif t == CONVEX_MESH:
+            v = 0.0
+            for (vol, cen) in _convex_tets(convex_meshes[c["mesh"]], p):
+                v += vol
+            vols.append(v)
+            cen_sum = np.zeros(3)
+            for (vol, cen) in _convex_tets(convex_meshes[c["mesh"]], p):
+                cen_sum += (np.asarray(c["lpos"], float) + cen) * vol
+            com += cen_sum
+            total += v
+            continue
+        else:
+            vols.append(0.0)
+            continue
+        vols.append(v)
+        com += np.asarray(c["lpos"], float) * v
+        total += v
+    if total == 0:
+        return np.zeros(3, f32), np.eye(3, dtype=f32)
+    com /= total
+    I = np.zeros((3, 3))
+    for c, v in zip(cols, vols):
+        if c["flags"] & COL_TRIGGER or v == 0.0:
+            continue
+        t, p = c["type"], c["params"]
+        m = mass * v / total
+        r = com - np.asarray(c["lpos"], float)
+        pa = m * (np.eye(3) * r.dot(r) - np.outer(r, r))
+        if t == SPHERE:
+            I += np.eye(3) * (2 * m * p[0] ** 2 / 5) + pa
+        elif t == CAPSULE:
+            hh, rr = p[0], p[1]
+            vc = 2 * rr * rr * pi * hh
+            vs = 4 * rr ** 3 * pi / 3
+            mc, ms = vc * m / (vc + vs), vs * m / (vc + vs)
+            ixx = mc * (hh * hh / 3 + rr * rr / 4) + ms * (hh * hh + 3 * hh * rr / 4 + 2 * rr * rr / 5)
+            iyy = mc * rr * rr / 2 + ms * 2 * rr * rr / 5
+            R = quat_to_mat(c["lquat"])
+            I += R @ np.diag([ixx, iyy, ixx]) @ R.T + pa
+        elif t == BOX:
+            mm = m / 12
+            x, y, z = p[0] ** 2, p[1] ** 2, p[2] ** 2
+            R = quat_to_mat(c["lquat"])
+            I += R @ np.diag([mm * (y + z), mm * (x + z), mm * (x + y)]) @ R.T + pa
+        elif t == CONVEX_MESH:
+            mesh = convex_meshes[c["mesh"]]
+            d = np.asarray(c["lpos"], float) - com
+            center = (np.asarray(p[:3]) * mesh.verts.astype(float)).sum(0)
+            nv_padded = (len(mesh.verts) + 3) // 4 * 4
+            center = center + (nv_padded - len(mesh.verts)) * np.asarray(p[:3]) * mesh.verts[-1].astype(float)
+            center /= len(mesh.verts)
+            for f in range(len(mesh.face_offsets) - 1):
+                idx = mesh.face_indices[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+                v0 = np.asarray(p[:3]) * mesh.verts[idx[0]]
+                for i in range(1, len(idx) - 1):
+                    v1 = np.asarray(p[:3]) * mesh.verts[idx[i]]
+                    v2 = np.asarray(p[:3]) * mesh.verts[idx[i + 1]]
+                    vol = abs(np.dot(np.cross(v0 - center, v1 - center), v2 - center)) / 6
+                    mt = mass * vol / total
+                    I += _inertia_tet(mt, [center + d, v0 + d, v1 + d, v2 + d])
+    return com.astype(f32), np.linalg.inv(I).astype(f32)
+
+
+def _convex_tets(mesh, p):
+    s = np.asarray(p[:3], float)
+    nv_padded = (len(mesh.verts) + 3) // 4 * 4
+    center = (s * mesh.verts.astype(float)).sum(0) + (nv_padded - len(mesh.verts)) * s * mesh.verts[-1].astype(float)
+    center /= len(mesh.verts)   # reference iterates the padded buffer but divides by size() (MassUtil.cpp:99-103)
+    for f in range(len(mesh.face_offsets) - 1):
+        idx = mesh.face_indices[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+        v0 = s * mesh.verts[idx[0]]
+        for i in range(1, len(idx) - 1):
+            v1 = s * mesh.verts[idx[i]]
+            v2 = s * mesh.verts[idx[i + 1]]
+            vol = abs(np.dot(np.cross(v0 - center, v1 - center), v2 - center)) / 6
+            yield vol, (center + v0 + v1 + v2) / 4
+
+
+def _inertia_tet(mass, v):
+    v = [np.asarray(x, float) for x in v]
+    d = np.zeros(3)
+    for i in range(4):
+        for j in range(i + 1):
+            d += v[j] * v[i]
+    a, b, c = (d[1] + d[2]) / 10, (d[0] + d[2]) / 10, (d[0] + d[1]) / 10
+    ap = bp = cp = 0.0
+    for i in range(4):
+        for j in range(4):
+            mult = 2 if i == j else 1
+            ap += mult * v[i][1] * v[j][2]
+            bp += mult * v[i][0] * v[j][2]
+            cp += mult * v[i][0] * v[j][1]
+    ap /= 20; bp /= 20; cp /= 20
+    I = np.zeros((3, 3))
+    I[0, 0], I[1, 1], I[2, 2] = a, b, c
+    I[0, 1] = I[1, 0] = -bp
+    I[2, 0] = I[0, 2] = -cp
+    I[1, 2] = I[2, 1] = -ap
+    return mass * I
+
+
+# ---- deterministic RNG (splitmix64, top 24 bits -> uniform float) --------------------------------
+class SplitMix:
+    def __init__(self, seed):
+        self.state = np.uint64(seed)
+
+    def u64(self, n):
+        with np.errstate(over="ignore"):
+            idx = np.arange(1, n + 1, dtype=np.uint64)
+            z = self.state + idx * np.uint64(0x9E3779B97F4A7C15)
+            self.state = self.state + np.uint64(n) * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def uniform(self, n, lo=0.0, hi=1.0):
+        u = (self.u64(n) >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+        return (lo + (hi - lo) * u).astype(f32)
+
+    def unit_quat(self, n):
+        q = np.stack([self.uniform(n, -1, 1) for _ in range(4)], 1).astype(np.float64)
+        # a few rejection rounds toward uniform-in-ball, then normalise
+        nrm = np.linalg.norm(q, axis=1)
+        bad = (nrm > 1) | (nrm < 1e-3)
+        for _ in range(8):
+            k = int(bad.sum())
+            if not k:
+                break
+            q[bad] = np.stack([self.uniform(k, -1, 1) for _ in range(4)], 1)
+            nrm = np.linalg.norm(q, axis=1)
+            bad = (nrm > 1) | (nrm < 1e-3)
+        q /= np.linalg.norm(q, axis=1)[:, None]
+        return q.astype(f32)
+
+
+IDQ = np.array([0, 0, 0, 1], f32)
+
+
+# ---- config 1: box pyramid -----------------------------------------------------------------------------------------
+def pyramid(n_boxes=1000, substeps=8, iterations=2) -> SceneDesc:
+    """C1: rows r=0.., row r has (R-r) boxes, half extent 0.5, on a static ground box."""
+    rows = 1
+    while rows * (rows + 1) // 2 < n_boxes:
+        rows += 1
+    pos = [(0.0, -1.0, 0.0)]
+    for r in range(rows):
+        cnt = rows - r
+        for c in range(cnt):
+            if len(pos) - 1 >= n_boxes:
+                break
+            pos.append(((c - cnt / 2.0) * 1.05, 0.5 + r, 0.0))
+    n = len(pos)
+    flags = np.full(n, F_DYNAMIC, np.int32); flags[0] = 0
+    prm = np.zeros((n, 4), f32); prm[:, :3] = 0.5; prm[0, :3] = (100, 1, 100)
+    return bulk_scene("pyramid_%d" % n_boxes, np.array(pos, f32), np.tile(IDQ, (n, 1)), flags, np.full(n, BOX), prm, 1.0,
+                      material=(0.4, 0.2, 0.0), substeps=substeps, iterations=iterations)
+
+
+# ---- config 2: mixed primitives falling into a bin -------------------------------------------------------------------
+def mixed_bin(n_bodies=100_000, seed=0xC2, substeps=4, iterations=2, spacing=1.0) -> SceneDesc:
+    rng = SplitMix(seed)
+    nx, nz = 50, 50
+    ny = (n_bodies + nx * nz - 1) // (nx * nz)
+    i = np.arange(n_bodies)
+    gx, gz, gy = i % nx, (i // nx) % nz, i // (nx * nz)
+    jit = np.stack([rng.uniform(n_bodies, -0.1, 0.1) for _ in range(3)], 1)
+    p = np.stack([(gx - nx / 2 + 0.5) * spacing, 1.0 + gy * spacing, (gz - nz / 2 + 0.5) * spacing], 1).astype(f32) + jit
+    t = (i % 3).astype(np.int32)
+    prm = np.zeros((n_bodies, 4), f32)
+    a, b, c = rng.uniform(n_bodies, 0.2, 0.4), rng.uniform(n_bodies, 0.15, 0.3), rng.uniform(n_bodies, 0.2, 0.4)
+    prm[t == SPHERE, 0] = a[t == SPHERE]
+    prm[t == CAPSULE, 0] = a[t == CAPSULE]; prm[t == CAPSULE, 1] = b[t == CAPSULE]
+    prm[t == BOX, 0] = a[t == BOX]; prm[t == BOX, 1] = c[t == BOX]; prm[t == BOX, 2] = rng.uniform(n_bodies, 0.2, 0.4)[t == BOX]
+    q = rng.unit_quat(n_bodies)
+    half = nx * spacing / 2 + 2.0
+    height = ny * spacing + 4.0
+    spos = np.array([(0, -1, 0), (half + 1, height / 2, 0), (-half - 1, height / 2, 0), (0, height / 2, half + 1), (0, height / 2, -half - 1)], f32)
+    sprm = np.array([(half + 2, 1, half + 2, 0), (1, height / 2 + 1, half + 2, 0), (1, height / 2 + 1, half + 2, 0),
+                     (half + 2, height / 2 + 1, 1, 0), (half + 2, height / 2 + 1, 1, 0)], f32)
+    pos = np.concatenate([spos, p]); quat = np.concatenate([np.tile(IDQ, (5, 1)), q])
+    flags = np.concatenate([np.zeros(5, np.int32), np.full(n_bodies, F_DYNAMIC, np.int32)])
+    types = np.concatenate([np.full(5, BOX, np.int32), t]); params = np.concatenate([sprm, prm])
+    return bulk_scene("mixed_bin_%d" % n_bodies, pos, quat, flags, types, params, 1.0, material=(0.4, 0.0, 0.0),
+                      substeps=substeps, iterations=iterations)
+
+
+# ---- config 4: spheres + capsules over a triangle-mesh terrain ----------------------------------------------------------
+def terrain_mesh(cells=1024, spacing=1.0, seed=0xC4) -> TriMeshDesc:
+    rng = SplitMix(seed ^ 0x7E44A1)
+    nv = cells + 1
+    ix, iz = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
+    x = (ix - cells / 2) * spacing
+    z = (iz - cells / 2) * spacing
+    u = rng.uniform(nv * nv, -1, 1).reshape(nv, nv)
+    y = 2.0 * np.sin(0.05 * x) * np.cos(0.05 * z) + 0.25 * u
+    verts = np.stack([x, y, z], -1).reshape(-1, 3).astype(f32)
+    cx, cz = np.meshgrid(np.arange(cells), np.arange(cells), indexing="ij")
+    v00 = (cx * nv + cz).ravel(); v10 = ((cx + 1) * nv + cz).ravel(); v01 = (cx * nv + cz + 1).ravel(); v11 = ((cx + 1) * nv + cz + 1).ravel()
+    # CCW seen from +Y so normals point up
+    tris = np.stack([np.stack([v00, v01, v11], 1), np.stack([v00, v11, v10], 1)], 1).reshape(-1, 3)
+    return TriMeshDesc(verts=np.ascontiguousarray(verts), indices=np.ascontiguousarray(tris.reshape(-1).astype(np.uint32)))
+
+
+def terrain_height(x, z):
+    return 2.0 * np.sin(0.05 * x) * np.cos(0.05 * z)
+
+
+def terrain(n_bodies=1_000_000, cells=1024, seed=0xC4, substeps=4, iterations=2, spacing=1.0, drop=1.0) -> SceneDesc:
+    """C4: spheres (even i) and capsules (odd i) on a sqrt(n) x sqrt(n) grid over a static triangle-mesh terrain."""
+    rng = SplitMix(seed)
+    mesh = terrain_mesh(cells, 1.0, seed)
+    side = int(math.ceil(math.sqrt(n_bodies)))
+    i = np.arange(n_bodies)
+    gx, gz = i % side, i // side
+    x = (gx - side / 2 + 0.5) * spacing + rng.uniform(n_bodies, -0.2, 0.2)
+    z = (gz - side / 2 + 0.5) * spacing + rng.uniform(n_bodies, -0.2, 0.2)
+    y = terrain_height(x, z) + 0.25 + drop
+    p = np.stack([x, y, z], 1).astype(f32)
+    t = np.where(i % 2 == 0, SPHERE, CAPSULE).astype(np.int32)
+    prm = np.zeros((n_bodies, 4), f32)
+    rs, hh, rc = rng.uniform(n_bodies, 0.2, 0.35), rng.uniform(n_bodies, 0.15, 0.3), rng.uniform(n_bodies, 0.15, 0.25)
+    prm[t == SPHERE, 0] = rs[t == SPHERE]
+    prm[t == CAPSULE, 0] = hh[t == CAPSULE]; prm[t == CAPSULE, 1] = rc[t == CAPSULE]
+    q = rng.unit_quat(n_bodies)
+    pos = np.concatenate([np.zeros((1, 3), f32), p]); quat = np.concatenate([IDQ[None], q])
+    flags = np.concatenate([np.zeros(1, np.int32), np.full(n_bodies, F_DYNAMIC, np.int32)])
+    types = np.concatenate([np.array([TRIANGLE_MESH], np.int32), t]); params = np.concatenate([np.zeros((1, 4), f32), prm])
+    col_mesh = np.full(n_bodies + 1, -1, np.int32); col_mesh[0] = 0
+    return bulk_scene("terrain_%d" % n_bodies, pos, quat, flags, types, params, 1.0, material=(0.4, 0.0, 0.0), col_mesh=col_mesh,
+                      trimesh=[mesh], substeps=substeps, iterations=iterations)
