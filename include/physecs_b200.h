@@ -98,6 +98,10 @@ int pb_register_convex(pb_ctx* ctx, const float* verts3, int n_verts, const int*
  * contact-cache key) agree; tri_order_out (optional, n_tris ints) receives original index of each built triangle. */
 int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int n_verts, const unsigned* indices, int n_indices,
                         int* handle, int* tri_order_out);
+/* The host-side BVH build alone (no device needed): outputs sized n_tris*3 (tri_idx), n_tris (tri_orig),
+ * 2*n_tris*6 (node_bounds), 2*n_tris*2 (node_count_index); *n_nodes receives the node count. */
+int pb_build_trimesh(const float* verts3, int n_verts, const unsigned* indices, int n_indices, unsigned* tri_idx,
+                     int* tri_orig, float* node_bounds6, int* node_count_index2, int* n_nodes);
 /* joints: params per type -- revolute {driveEnabled, driveVelocity, driveMaxTorque}; prismatic {upper, lower,
  * driveEnabled, targetPosition, stiffness, damping}; gear {ratio}; servo {targetAngle, stiffness, damping}.
  * color[n]: colour assigned by the host-side greedy colouring (reference Physecs.cpp:690-710), 8 = overflow. */

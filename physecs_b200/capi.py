@@ -22,7 +22,7 @@ EXPORTS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_host_alloc", "pb_host_free", "pb_stream",
     "pb_upload_bodies", "pb_upload_colliders", "pb_register_convex", "pb_register_trimesh", "pb_upload_joints",
     "pb_set_noncolliding_pairs", "pb_set_state", "pb_move_rows", "pb_refresh_bounds", "pb_step", "pb_get_state", "pb_sync",
-    "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds",
+    "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds", "pb_build_trimesh",
 ]
 
 
@@ -72,6 +72,20 @@ def _f(a):
 
 def _i(a):
     return np.ascontiguousarray(a, np.int32)
+
+
+def build_trimesh(verts, indices):
+    """Host-side registration-time BVH build (same construction as the reference TriangleMesh ctor)."""
+    lib = load_library()
+    v = _f(verts); idx = np.ascontiguousarray(indices, np.uint32)
+    nt = len(idx) // 3
+    tri = np.zeros((nt, 3), np.uint32); orig = np.zeros(nt, np.int32)
+    nb = np.zeros((2 * nt, 6), np.float32); ci = np.zeros((2 * nt, 2), np.int32)
+    nn = C.c_int()
+    rc = lib.pb_build_trimesh(_p(v), len(v), _p(idx, C.c_uint), len(idx), _p(tri, C.c_uint), _p(orig, C.c_int), _p(nb), _p(ci, C.c_int), C.byref(nn))
+    if rc != PB_OK:
+        raise RuntimeError("pb_build_trimesh failed")
+    return tri, orig, nb[:nn.value], ci[:nn.value]
 
 
 class PbError(RuntimeError):

@@ -323,6 +323,18 @@ int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsi
     return syncMeshTables(ctx);
 }
 
+int pb_build_trimesh(const float* verts3, int nVerts, const unsigned* indices, int nIndices, unsigned* triIdx, int* triOrig,
+                     float* nodeBounds6, int* nodeCountIndex2, int* nNodes) {
+    PbHostTriMesh h;
+    pb_build_trimesh_host(verts3, nVerts, indices, nIndices, h);
+    if (triIdx) memcpy(triIdx, h.triIdx.data(), sizeof(unsigned) * h.triIdx.size());
+    if (triOrig) memcpy(triOrig, h.triOrig.data(), sizeof(int) * h.triOrig.size());
+    if (nodeBounds6) memcpy(nodeBounds6, h.nodeBounds.data(), sizeof(float) * h.nodeBounds.size());
+    if (nodeCountIndex2) memcpy(nodeCountIndex2, h.nodeCountIndex.data(), sizeof(int) * h.nodeCountIndex.size());
+    if (nNodes) *nNodes = h.nNodes;
+    return PB_OK;
+}
+
 int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* row0, const int* row1, const float* a0p, const float* a0q,
                      const float* a1p, const float* a1q, const float* params8, const int* color) {
     cudaSetDevice(ctx->device);

@@ -186,7 +186,11 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
     // group by colour: one stable 8-bit radix pass over the raw arena (nRaw was read back after the narrowphase)
     int n = nRaw;
-    if (n <= 0) return PB_OK;
+    if (n <= 0) {
+        // no manifolds this step: the contact cache of this step must still read as empty for the next one
+        cudaMemsetAsync(ctx->cacheTag[ctx->curBuf], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
+        return PB_OK;
+    }
     bool inA = true;
     int rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 8, ctx->radixHist, ctx->radixTiles, &inA);
     if (rc) return rc;

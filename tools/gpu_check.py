@@ -1,0 +1,29 @@
+"""Development helper (run under gpurun): verbose gate runs on several scenes, one failure does not stop the rest."""
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from physecs_b200 import scenes as S  # noqa: E402
+from tests import parity  # noqa: E402
+
+CASES = {
+    "pyramid": lambda: (S.pyramid(120), 30),
+    "bin": lambda: (S.mixed_bin(1200, spacing=0.8), 50),
+    "terrain": lambda: (S.terrain(1500, cells=48, drop=0.3), 50),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for name in names:
+        desc, steps = CASES[name]()
+        t0 = time.time()
+        try:
+            s = parity.run_gates(desc, steps=steps, verbose=True)
+            print(f"[{name}] OK {s} in {time.time() - t0:.1f}s", flush=True)
+        except Exception:
+            print(f"[{name}] FAILED after {time.time() - t0:.1f}s", flush=True)
+            traceback.print_exc()
