@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the Physecs per-step pipeline on B200.
+
+Workload (BASELINE.json configs[3], the 1M-body configuration the metric is quoted on): 1,000,000 spheres and
+capsules over a static 2,097,152-triangle terrain mesh, 60 Hz, 4 TGS substeps x 2 iterations (+ relaxation),
+settled for --settle steps before measuring so the contact graph is populated.  A "step" is one
+physecs::Scene::simulate(1/60): broadphase -> narrowphase -> contact build -> substep solve.
+
+Lines printed (one JSON object, rank 0):
+  value   body-steps/s with the scene resident in HBM (pb_step only), CUDA events on the context's stream
+  e2e     the same metric through the C ABI with HOST buffers: pb_set_state (H2D) + pb_step + pb_get_state (D2H) per step
+  roofline  dominant kernel = k_contact_solve (one colour batch per launch): algorithmic bytes (SURVEY.md §8d:
+            180 + 140*points per manifold per pass) / measured launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, "reference + hash fix" build) on a bounded sample
+
+`--impl reference` times the reference CPU implementation itself on the host cores (bounded sample of the same workload).
+N > 1 (torchrun): independent replicas of the workload, one per GPU, no collective on the data path ("weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "body-steps/sec at 1M bodies (spheres+capsules on triangle-mesh terrain, 4 substeps)"
+UNIT = "body-steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_sample(n_sample, cells, settle, warmup, steps, threads):
+    """Time the reference CPU implementation (oracle/_ref) on a bounded sample of the workload."""
+    from oracle.ref import RefScene
+    from physecs_b200 import scenes as S
+    d = S.terrain(n_sample, cells=cells, drop=0.3)
+    ref = RefScene(d, threads, hashfix=True)
+    for _ in range(settle + warmup):
+        ref.simulate()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.simulate()
+    dt = time.perf_counter() - t0
+    nm = len(ref.manifold_keys())
+    ref.close()
+    return n_sample * steps / dt, dt / steps * 1e3, nm
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(cores - 1, 0)
+    n_sample, cells = args.ref_bodies, args.ref_cells
+    try:
+        value, ms, nm = reference_sample(n_sample, cells, args.ref_settle, args.warmup, args.steps, threads)
+    except Exception as e:  # oracle not built
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not usable: {e}"}))
+        return
+    sample = f"terrain scene, {n_sample} bodies on a {cells}x{cells}-cell mesh, settled {args.ref_settle} steps, reference+hash-fix build, Scene(registry, {threads})"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 terrain: spheres+capsules over static triangle mesh, 60 Hz, 4 substeps x 2 iterations", "sample_bodies": n_sample,
+                   "manifolds": nm},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads + 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bodies", type=int, default=1_000_000)
+    ap.add_argument("--cells", type=int, default=1024)
+    ap.add_argument("--settle", type=int, default=150)
+    ap.add_argument("--ref-bodies", type=int, default=4000)
+    ap.add_argument("--ref-cells", type=int, default=80)
+    ap.add_argument("--ref-settle", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from physecs_b200 import scenes as S
+    from physecs_b200.capi import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the device path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.bodies
+    desc = S.terrain(n, cells=args.cells, drop=0.3)
+    ctx = Context(desc, device=local_rank, max_pairs=8 * n + 4096, max_manifolds=6 * n + 4096)
+    n_dyn = ctx.n_dyn
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    for _ in range(args.settle):
+        ctx.step()
+    ctx.sync()
+    for _ in range(args.warmup):
+        ctx.step()
+    ctx.sync()
+
+    # ---- timed region A: device-resident ---------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launches()
+    ctx.set_profile(True)
+    barrier(); torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sumM = sumP = sumC = sumPairs = 0
+    phase = np.zeros(5)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.step()
+        c = ctx.counts()
+        sumM += c.n_manifolds; sumP += c.n_points; sumC += c.n_colors; sumPairs += c.n_pairs
+    e1.record(stream)
+    barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launches() - launches0
+    prof = ctx.profile()
+    ctx.set_profile(False)
+    t = ctx.timings()
+    ms_per_step = ms_total / args.steps
+    value = world * n_dyn * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_contact_solve) ----------------------------------------------------------
+    peak, peak_src = peaks()
+    pass_ms, n_pass = prof["solve_pass"]
+    avgM, avgP, avgC = sumM / args.steps, sumP / args.steps, max(sumC / args.steps, 1.0)
+    bytes_per_pass = 180.0 * avgM + 140.0 * avgP
+    pass_avg_ms = pass_ms / max(n_pass, 1)
+    achieved = bytes_per_pass / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_contact_solve_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_contact_solve", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_per_pass / avgC, "launch_ms": pass_avg_ms / avgC,
+                "launches_timed": int(n_pass * avgC), "share_of_step": pass_ms / ms_total,
+                "note": "algorithmic bytes = (180 + 140*points) per manifold per pass (SURVEY.md 8d); one launch = one colour batch"}
+
+    # ---- timed region B: end to end through the C ABI with pinned host buffers --------------------------------------
+    pos_t = torch.empty((n_dyn, 3), dtype=torch.float32).pin_memory(); quat_t = torch.empty((n_dyn, 4), dtype=torch.float32).pin_memory()
+    vel_t = torch.empty((n_dyn, 3), dtype=torch.float32).pin_memory(); ang_t = torch.empty((n_dyn, 3), dtype=torch.float32).pin_memory()
+    pos, quat, vel, ang = pos_t.numpy(), quat_t.numpy(), vel_t.numpy(), ang_t.numpy()
+    import ctypes as C
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    lib = ctx.lib
+    lib.pb_get_state(ctx.ctx, fp(pos), fp(quat), fp(vel), fp(ang))
+    e2e_steps = args.steps
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = lib.pb_set_state(ctx.ctx, n_dyn, fp(pos), fp(quat), fp(vel), fp(ang))
+        rc |= lib.pb_step(ctx.ctx, C.c_float(desc.dt), desc.substeps, desc.iterations, C.c_float(desc.gravity))
+        rc |= lib.pb_get_state(ctx.ctx, fp(pos), fp(quat), fp(vel), fp(ang))
+        if rc:
+            raise RuntimeError(lib.pb_last_error(ctx.ctx).decode())
+    torch.cuda.synchronize(); barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n_dyn * e2e_steps / e2e_s
+    bytes_io = 13 * 4 * n_dyn
+    checksum = float(np.abs(pos).sum())
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 terrain: %d spheres+capsules over a static %d-triangle mesh, 60 Hz, 4 substeps x 2 iterations + relaxation" % (n_dyn, 2 * args.cells * args.cells),
+                   "bodies_per_gpu": n_dyn, "settle_steps": args.settle, "replicas": world, "l2_policy": "working set >> L2 (per-step traffic ~GBs; no flush needed)",
+                   "avg_pairs": sumPairs / args.steps, "avg_manifolds": avgM, "avg_points": avgP, "avg_colors": avgC},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "checksum": checksum},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "phase_ms_last_step": {"broadphase": t.broadphase, "narrowphase": t.narrowphase, "contact_build": t.contact_build, "solve": t.solve, "total": t.total},
+        "stage_ms_per_step": {"solve_passes": pass_ms / args.steps, "contact_prep": prof["contact_prep"][0] / args.steps},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            v, ms, nm = reference_sample(args.ref_bodies, args.ref_cells, 100, 3, 15, max(cores - 1, 0))
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": ms,
+                                   "sample": f"reference+hash-fix build, terrain scene with {args.ref_bodies} bodies, settled 100 steps, 15 timed steps, Scene(registry, {max(cores - 1, 0)})"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    else:
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "rank 0 at N=1 only"}
+
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,13 @@ int pb_get_bounds(pb_ctx* ctx, float* out6);
 int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* num_points, float* normal3, float* points24,
                      int* color, int* n);
 
+/* optional per-stage CUDA-event profiling (bench.py roofline): stage ids 0 = one contact-solve pass over all
+ * colours, 1 = contact prep, 2 = body integration, 3 = joints.  pb_set_profile(ctx,1) resets the accumulators. */
+int pb_set_profile(pb_ctx* ctx, int on);
+int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8);
+/* kernels launched by this context since creation */
+unsigned long long pb_get_launches(pb_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ EXPORTS = [
     "pb_upload_bodies", "pb_upload_colliders", "pb_register_convex", "pb_register_trimesh", "pb_upload_joints",
     "pb_set_noncolliding_pairs", "pb_set_state", "pb_move_rows", "pb_refresh_bounds", "pb_step", "pb_get_state", "pb_sync",
     "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds", "pb_build_trimesh",
+    "pb_set_profile", "pb_get_profile", "pb_get_launches",
 ]
 
 
@@ -56,6 +57,7 @@ def load_library():
     lib.pb_stream.restype = C.c_void_p
     lib.pb_ctx_destroy.restype = None
     lib.pb_host_free.restype = None
+    lib.pb_get_launches.restype = C.c_ulonglong
     _lib = lib
     return lib
 
@@ -244,6 +246,21 @@ class Context:
         t = Timings()
         self._check(self.lib.pb_get_timings(self.ctx, C.byref(t)))
         return t
+
+    def set_profile(self, on=True):
+        self._check(self.lib.pb_set_profile(self.ctx, int(on)))
+
+    def profile(self):
+        ms = (C.c_double * 8)(); cnt = (C.c_longlong * 8)()
+        self._check(self.lib.pb_get_profile(self.ctx, ms, cnt))
+        names = ["solve_pass", "contact_prep", "integrate", "joints"]
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
+    def launches(self):
+        return int(self.lib.pb_get_launches(self.ctx))
+
+    def stream_ptr(self):
+        return int(self.lib.pb_stream(self.ctx))
 
     def pairs(self):
         n = C.c_int()

@@ -83,16 +83,16 @@ static int launchTrimeshBounds(pb_ctx* ctx, int col, float margin) {
     int mesh = ctx->hColMesh[col];
     const PbTriMesh& tm = ctx->triMeshes[mesh];
     int* acc = (int*)ctx->sceneBounds + 8;
-    k_trimesh_bounds_init<<<1, 32, 0, ctx->stream>>>(acc);
+    ++ctx->launches, k_trimesh_bounds_init<<<1, 32, 0, ctx->stream>>>(acc);
     int blocks = pb_grid(tm.nVerts, 256); if (blocks > 1024) blocks = 1024;
-    k_trimesh_bounds<<<blocks, 256, 0, ctx->stream>>>(col, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, tm.verts, tm.nVerts, acc);
-    k_trimesh_bounds_store<<<1, 1, 0, ctx->stream>>>(col, margin, acc, ctx->aabbMin, ctx->aabbMax);
+    ++ctx->launches, k_trimesh_bounds<<<blocks, 256, 0, ctx->stream>>>(col, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, tm.verts, tm.nVerts, acc);
+    ++ctx->launches, k_trimesh_bounds_store<<<1, 1, 0, ctx->stream>>>(col, margin, acc, ctx->aabbMin, ctx->aabbMax);
     return PB_OK;
 }
 
 int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic) {
     if (ctx->nCol == 0) return PB_OK;
-    k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, onlyDynamic ? 1 : 0, nullptr, margin, ctx->colRow, ctx->colType,
+    ++ctx->launches, k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, onlyDynamic ? 1 : 0, nullptr, margin, ctx->colRow, ctx->colType,
         ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
     if (!onlyDynamic) {
         auto& types = ctx->hColType;
@@ -105,7 +105,7 @@ int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic) {
 // rows moved through registry.patch: dRowMark[row] != 0 marks them (device array of nRows ints)
 int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin) {
     if (ctx->nCol == 0) return PB_OK;
-    k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, 2, dRowMark, margin, ctx->colRow, ctx->colType,
+    ++ctx->launches, k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, 2, dRowMark, margin, ctx->colRow, ctx->colType,
         ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
@@ -124,7 +124,7 @@ __global__ void k_world_pose(int n, const int* __restrict__ colRow, const float4
 }
 int pb_world_poses(pb_ctx* ctx) {
     if (ctx->nCol == 0) return PB_OK;
-    k_world_pose<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, ctx->colWPos, ctx->colWQuat);
+    ++ctx->launches, k_world_pose<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, ctx->colWPos, ctx->colWQuat);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -313,19 +313,19 @@ int pb_broadphase(pb_ctx* ctx) {
     int n = ctx->nCol;
     if (n < 2) return PB_OK;
     int* sb = (int*)ctx->sceneBounds;
-    k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb);
+    ++ctx->launches, k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb);
     int blocks = pb_grid(n, 256); if (blocks > ctx->numSMs * 8) blocks = ctx->numSMs * 8;
-    k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
-    k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA);
+    ++ctx->launches, k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
+    ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA);
     bool inA = true;
     int rc = pb_radix_sort_pairs(ctx, ctx->mortonA, ctx->leafIdA, ctx->mortonB, ctx->leafIdB, n, 30, ctx->radixHist, ctx->radixTiles, &inA);
     if (rc) return rc;
     unsigned int* keys = inA ? ctx->mortonA : ctx->mortonB;
     int* ids = inA ? ctx->leafIdA : ctx->leafIdB;
-    k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag);
-    k_lbvh_refit<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ids, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag,
+    ++ctx->launches, k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag);
+    ++ctx->launches, k_lbvh_refit<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ids, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag,
                                                             ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
-    k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
+    ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

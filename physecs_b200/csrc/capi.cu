@@ -66,8 +66,8 @@ static int uploadVec(pb_ctx* ctx, const float* host, int n, int width, float4* d
     size_t bytes = sizeof(float) * (size_t)n * width;
     int rc = ensureStage(ctx, bytes); if (rc) return rc;
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (width == 3) k_unpack3<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
-    else k_unpack4<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
+    if (width == 3) ++ctx->launches, k_unpack3<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
+    else ++ctx->launches, k_unpack4<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->stage, dst);
     // the staging buffer is reused by the next upload on the same stream: stream order keeps this safe
     return PB_OK;
 }
@@ -77,7 +77,52 @@ template <class T> static int uploadRaw(pb_ctx* ctx, const T* host, size_t n, T*
     return PB_OK;
 }
 
+void pb_prof_begin(pb_ctx* ctx, int kind) {
+    if (!ctx->profile) return;
+    if (ctx->profUsed + 2 > ctx->profEv.size()) {
+        size_t old = ctx->profEv.size();
+        ctx->profEv.resize(old + 512);
+        for (size_t i = old; i < ctx->profEv.size(); ++i) cudaEventCreate(&ctx->profEv[i]);
+    }
+    ctx->profKind.push_back(kind);
+    cudaEventRecord(ctx->profEv[ctx->profUsed], ctx->stream);
+}
+void pb_prof_end(pb_ctx* ctx) {
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->profEv[ctx->profUsed + 1], ctx->stream);
+    ctx->profUsed += 2;
+}
+static void profCollect(pb_ctx* ctx) {
+    for (size_t i = 0; i + 1 < ctx->profUsed + 1 && i / 2 < ctx->profKind.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->profEv[i], ctx->profEv[i + 1]);
+        int k = ctx->profKind[i / 2];
+        ctx->profMs[k] += ms; ctx->profCount[k] += 1;
+    }
+    ctx->profUsed = 0; ctx->profKind.clear();
+}
+
 extern "C" {
+
+// enable/disable per-stage event profiling; enabling resets the accumulators
+int pb_set_profile(pb_ctx* ctx, int on) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->profile = on != 0;
+    ctx->profUsed = 0; ctx->profKind.clear();
+    for (int k = 0; k < PROF_COUNT; ++k) { ctx->profMs[k] = 0; ctx->profCount[k] = 0; }
+    return PB_OK;
+}
+// accumulated stage times since pb_set_profile(1): ms[8], count[8] indexed by stage id
+// (0 = contact solve pass over all colours, 1 = contact prep, 2 = body integration, 3 = joints)
+int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    profCollect(ctx);
+    for (int k = 0; k < PROF_COUNT; ++k) { ms8[k] = ctx->profMs[k]; count8[k] = ctx->profCount[k]; }
+    return PB_OK;
+}
+unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
 
 int pb_host_alloc(void** ptr, unsigned long long bytes) { return cudaMallocHost(ptr, bytes) == cudaSuccess ? PB_OK : PB_ECUDA; }
 void pb_host_free(void* ptr) { cudaFreeHost(ptr); }
@@ -178,8 +223,8 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
         PB_CUDA(ctx, cudaMemcpyAsync(s, com3, sizeof(float) * 3 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * (size_t)nDyn, invMass, sizeof(float) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)nDyn, invI9, sizeof(float) * 9 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
-        k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
-        k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
+        ++ctx->launches, k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
+        ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
     }
     ctx->cacheValid = false;
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -371,10 +416,10 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
     if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     int g = pb_grid(nDyn, 256);
-    if (pos3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
-    if (quat4) k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
-    if (vel3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 7 * n, ctx->vel);
-    if (angvel3) k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 10 * n, ctx->angvel);
+    if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
+    if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
+    if (vel3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 7 * n, ctx->vel);
+    if (angvel3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 10 * n, ctx->angvel);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -389,7 +434,7 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
     PB_CUDA(ctx, cudaMemcpyAsync(s, rows, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
     PB_CUDA(ctx, cudaMemcpyAsync(s + n, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-    k_scatter_rows<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const int*)s, s + n, s + 4 * (size_t)n, ctx->pos, ctx->quat, ctx->rowMark);
+    ++ctx->launches, k_scatter_rows<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const int*)s, s + n, s + 4 * (size_t)n, ctx->pos, ctx->quat, ctx->rowMark);
     if ((rc = pb_update_bounds_rows(ctx, ctx->rowMark, n, 0.01f))) return rc;
     std::vector<char> moved(ctx->nRows, 0);
     for (int i = 0; i < n; ++i) if (rows[i] >= 0 && rows[i] < ctx->nRows) moved[rows[i]] = 1;
@@ -442,6 +487,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     ctx->lastCounts.n_colors = nRaw > 0 ? ctx->hCounters[CNT_NCOLORS] : 0;
     ctx->lastCounts.n_overflow = nRaw > 0 ? ctx->hCounters[CNT_OVERFLOW] : 0;
     ctx->lastCounts.n_points = nRaw > 0 ? ctx->hCounters[CNT_POINTS] : 0;
+    if (ctx->profile && ctx->profUsed > 4096) { cudaStreamSynchronize(ctx->stream); profCollect(ctx); }
     if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
     ctx->cacheValid = true;
     // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
@@ -459,10 +505,10 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
     int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
     float* s = ctx->stage;
     int g = pb_grid(nDyn, 256);
-    if (pos3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
-    if (quat4) k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
-    if (vel3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, s + 7 * n);
-    if (angvel3) k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->angvel, s + 10 * n);
+    if (pos3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
+    if (quat4) ++ctx->launches, k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
+    if (vel3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, s + 7 * n);
+    if (angvel3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->angvel, s + 10 * n);
     if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3, s, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4, s + 3 * n, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3, s + 7 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -181,9 +181,9 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     int blocks = ctx->numSMs * 8;
     int maxM = ctx->caps.max_manifolds;
     cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
-    k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
+    ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
                                              ctx->mSortKeyA, ctx->mSortTmp);
-    k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
+    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
     // group by colour: one stable 8-bit radix pass over the raw arena (nRaw was read back after the narrowphase)
     int n = nRaw;
     if (n <= 0) {
@@ -197,12 +197,12 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     ctx->mSorted = inA ? ctx->mSortTmp : ctx->mSortValB;
     int cur = ctx->curBuf, prev = cur ^ 1;
     int* pointOfs = ctx->cPointOfsBuf[cur];
-    k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);
+    ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);
     rc = pb_exclusive_scan(ctx, ctx->cNpBuf[cur], pointOfs, n, (int*)ctx->radixHist);
     if (rc) return rc;
-    k_count_points<<<1, 1, 0, ctx->stream>>>(ctx->counters, pointOfs, ctx->cNpBuf[cur]);
+    ++ctx->launches, k_count_points<<<1, 1, 0, ctx->stream>>>(ctx->counters, pointOfs, ctx->cNpBuf[cur]);
     cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
-    k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
+    ++ctx->launches, k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
         ctx->nDyn, ctx->kinematic, ctx->pos, ctx->quat, ctx->vel, ctx->angvel, ctx->comInvMass,
         ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
         ctx->cacheValid ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],

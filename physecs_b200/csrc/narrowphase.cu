@@ -263,18 +263,18 @@ int pb_narrowphase(pb_ctx* ctx) {
     if (ctx->nCol < 2) return PB_OK;
     int blocks = ctx->numSMs * 8;
     int* pairBin = ctx->pairOrder + ctx->caps.max_pairs;   // second half of the pairOrder allocation
-    k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
+    ++ctx->launches, k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
                                                       ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding);
-    k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
-    k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
+    ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
+    ++ctx->launches, k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
-#define LAUNCH_PRIM(BIN) k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
+#define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
     if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
 #undef LAUNCH_PRIM
     if (!ctx->triMeshes.empty())
-        k_np_mesh<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+        ++ctx->launches, k_np_mesh<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                    ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

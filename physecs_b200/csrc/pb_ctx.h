@@ -159,7 +159,20 @@ struct pb_ctx {
     pb_timings lastTimings{};
     cudaEvent_t ev[6] = {nullptr};
     bool triggersPresent = false;
+    unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
+    // optional per-stage event profiling (pb_set_profile): events recorded around stage groups, summed lazily
+    bool profile = false;
+    std::vector<cudaEvent_t> profEv;  // pairs (begin, end)
+    std::vector<int> profKind;        // stage id per pair
+    size_t profUsed = 0;
+    double profMs[8] = {0};
+    long long profCount[8] = {0};
 };
+
+// profiling stage ids
+enum { PROF_SOLVE_PASS = 0, PROF_CONTACT_PREP = 1, PROF_INTEGRATE = 2, PROF_JOINTS = 3, PROF_COUNT = 8 };
+void pb_prof_begin(pb_ctx* ctx, int kind);
+void pb_prof_end(pb_ctx* ctx);
 
 // ---- helpers --------------------------------------------------------------------------------------------------
 int pb_fail(pb_ctx* ctx, int code, const std::string& msg);

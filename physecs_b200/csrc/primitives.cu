@@ -92,9 +92,9 @@ __global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, 
 int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch) {
     if (n <= 0) return PB_OK;
     int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, scratch, n);
-    k_scan_blocksums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scratch, nb);
-    k_scan_final<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, scratch, n);
+    ++ctx->launches, k_scan_reduce<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, scratch, n);
+    ++ctx->launches, k_scan_blocksums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scratch, nb);
+    ++ctx->launches, k_scan_final<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, scratch, n);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -167,10 +167,10 @@ int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned i
     int* scanScratch = (int*)(hist + (size_t)256 * histCapTiles);
     unsigned int* src = keysA; int* srcV = valsA; unsigned int* dst = keysB; int* dstV = valsB;
     for (int shift = 0; shift < bits; shift += 8) {
-        k_radix_hist<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
+        ++ctx->launches, k_radix_hist<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
         int rc = pb_exclusive_scan(ctx, (const int*)hist, (int*)hist, histN, scanScratch);
         if (rc) return rc;
-        k_radix_scatter<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
+        ++ctx->launches, k_radix_scatter<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
         unsigned int* t = src; src = dst; dst = t;
         int* tv = srcV; srcV = dstV; dstV = tv;
         *resultInA = !*resultInA;

@@ -231,30 +231,34 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     float h = dt / (float)substeps;
     int ncol = ctx->lastCounts.n_colors;
     for (int sub = 0; sub < substeps; ++sub) {
-        k_integrate_v<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, gravity, ctx->kinematic, ctx->quat, ctx->vel, ctx->angvel, ctx->invIL,
+        ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, gravity, ctx->kinematic, ctx->quat, ctx->vel, ctx->angvel, ctx->invIL,
             ctx->velPre, ctx->angvelPre, ctx->velLive, ctx->angvelLive, ctx->invIW, ctx->pseudoLin, ctx->pseudoAng);
+        if (nM > 0) pb_prof_begin(ctx, PROF_CONTACT_PREP);
         if (nM > 0)
-            k_contact_prep<<<pb_grid(nM, 128), 128, 0, ctx->stream>>>(nM, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur],
+            ++ctx->launches, k_contact_prep<<<pb_grid(nM, 128), 128, 0, ctx->stream>>>(nM, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur],
                 ctx->pR0T[cur], ctx->pR1, ctx->pos, ctx->quat, ctx->comInvMass, ctx->vel, ctx->angvel, ctx->velPre, ctx->angvelPre, ctx->invIW,
                 ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
+        if (nM > 0) pb_prof_end(ctx);
         if (ctx->nJoints) { int rc = pb_joint_prep(ctx, h); if (rc) return rc; }
         for (int it = 0; it <= iterations; ++it) {
             const bool relax = it == iterations;
             if (relax)
-                k_integrate_x<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
+                ++ctx->launches, k_integrate_x<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
                     ctx->velLive, ctx->angvelLive, ctx->pseudoLin, ctx->pseudoAng);
+            if (nM > 0) pb_prof_begin(ctx, PROF_SOLVE_PASS);
             for (int c = 0; c < ncol; ++c) {
                 int start = colorStart[c], count = colorStart[c + 1] - start;
                 if (count <= 0) continue;
                 if (c == PB_OVERFLOW_COLOR)
-                    k_contact_solve_seq<<<1, 1, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
+                    ++ctx->launches, k_contact_solve_seq<<<1, 1, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
                         ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur], ctx->comInvMass, ctx->velLive, ctx->angvelLive,
                         ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
                 else
-                    k_contact_solve<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
+                    ++ctx->launches, k_contact_solve<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
                         ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur], ctx->comInvMass, ctx->velLive, ctx->angvelLive,
                         ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
             }
+            if (nM > 0) pb_prof_end(ctx);
             if (!relax && ctx->nJoints) { int rc = pb_joint_solve(ctx, h, it == 0); if (rc) return rc; }
         }
         // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity
