@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=80)
     ap.add_argument("--ref-settle", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (never a bench value)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -198,6 +199,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sumM = sumP = sumC = sumPairs = 0
     phase = np.zeros(5)
+    if args.ncu:
+        ctx.lib.pb_profiler_range(1)
     e0.record(stream)
     for _ in range(args.steps):
         ctx.step()
@@ -205,6 +208,8 @@ def main():
         sumM += c.n_manifolds; sumP += c.n_points; sumC += c.n_colors; sumPairs += c.n_pairs
     e1.record(stream)
     barrier(); torch.cuda.synchronize()
+    if args.ncu:
+        ctx.lib.pb_profiler_range(0)
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launches() - launches0

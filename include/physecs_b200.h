@@ -144,6 +144,8 @@ int pb_set_profile(pb_ctx* ctx, int on);
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8);
 /* kernels launched by this context since creation */
 unsigned long long pb_get_launches(pb_ctx* ctx);
+/* cudaProfilerStart/Stop, so `ncu --profile-from-start off` captures only the timed region of bench.py */
+void pb_profiler_range(int start);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 #include "trimesh_build.h"
 #include <algorithm>
 #include <cstring>
+#include <cuda_profiler_api.h>
 
 int pb_fail(pb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -123,6 +124,7 @@ int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
     return PB_OK;
 }
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
+void pb_profiler_range(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
 
 int pb_host_alloc(void** ptr, unsigned long long bytes) { return cudaMallocHost(ptr, bytes) == cudaSuccess ? PB_OK : PB_ECUDA; }
 void pb_host_free(void* ptr) { cudaFreeHost(ptr); }
