@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=80)
     ap.add_argument("--ref-settle", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batched-scenes", type=int, default=4096, help="ragdoll scenes for the sharded-batch section (0 = skip)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (never a bench value)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -276,6 +277,32 @@ def main():
         "stage_ms_per_step": {"solve_passes": pass_ms / args.steps, "contact_prep": prof["contact_prep"][0] / args.steps},
     }
 
+    ctx.close()
+
+    # ---- batched independent scenes (BASELINE.json configs[4]): 4096 ragdoll scenes sharded by scene across ranks ----
+    if args.batched_scenes > 0:
+        per_rank = args.batched_scenes // world
+        rd = S.ragdolls(per_rank, seed=0xC5 + rank)
+        rctx = Context(rd, device=local_rank, max_pairs=64 * rd.n, max_manifolds=16 * rd.n)
+        for _ in range(120):
+            rctx.step()
+        rctx.sync()
+        rstream = torch.cuda.ExternalStream(rctx.stream_ptr(), device=torch.device("cuda", local_rank))
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        r0.record(rstream)
+        for _ in range(args.steps):
+            rctx.step()
+        r1.record(rstream)
+        barrier(); torch.cuda.synchronize()
+        rms = max_over_ranks(r0.elapsed_time(r1))
+        rc_ = rctx.counts()
+        out["batched_scenes"] = {"metric": "batched-scene steps/s (4096 independent ragdoll scenes, 11 bodies + 10 joints + ground each, 4 substeps)",
+                                 "value": per_rank * world * args.steps / (rms * 1e-3), "unit": "scene-steps/s", "scenes": per_rank * world,
+                                 "scenes_per_gpu": per_rank, "ms_per_step": rms / args.steps, "scaling": "strong", "bodies": int(rctx.n_dyn) * world,
+                                 "manifolds_last_step": int(rc_.n_manifolds), "joints": len(rd.joints) * world}
+        rctx.close()
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
@@ -287,7 +314,6 @@ def main():
     else:
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "rank 0 at N=1 only"}
 
-    ctx.close()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

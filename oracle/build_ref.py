@@ -179,7 +179,7 @@ def build(verbose=True):
         flags = [
             "-std=gnu++23", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
             "-march=x86-64-v3", "-w",
-            "-DGLM_FORCE_INLINE", "-DPHYSECS_EXPORTS", "-DENTT_PACKED_PAGE=1048576",
+            "-DGLM_FORCE_INLINE", "-DPHYSECS_EXPORTS", "-DENTT_PACKED_PAGE=1048576", "-DNDEBUG",
             "-include", os.path.join(BUILD, "shim.h"),
             "-I", os.path.join(root, "src"), "-I", os.path.join(root, "src", "Joints"),
             "-I", os.path.join(root, "include", "Physecs"),

@@ -382,6 +382,9 @@ int ph_narrowphase(void* hp, const int* pairs, int npairs, int cap, int* keys, f
         auto or0 = t0.orientation * col0.orientation;
         auto pos1 = t1.position + t1.orientation * col1.position;
         auto or1 = t1.orientation * col1.orientation;
+        // same filters as the step: trigger pairs and nonCollidingPairs never reach collision() (Physecs.cpp:200-209)
+        if (h->scene->contactFilter(col0.isTrigger, col0.data, col1.isTrigger, col1.data) == physecs::TRIGGER) continue;
+        if (h->scene->nonCollidingPairs.count({ e0, e1 })) continue;
         buf.clear();
         if (!physecs::collision(pos0, or0, col0.geometry, pos1, or1, col1.geometry, buf)) continue;
         for (auto& r : buf) {

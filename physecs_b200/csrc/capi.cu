@@ -489,6 +489,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     ctx->lastCounts.n_colors = nRaw > 0 ? ctx->hCounters[CNT_NCOLORS] : 0;
     ctx->lastCounts.n_overflow = nRaw > 0 ? ctx->hCounters[CNT_OVERFLOW] : 0;
     ctx->lastCounts.n_points = nRaw > 0 ? ctx->hCounters[CNT_POINTS] : 0;
+    if ((rc = pb_joint_begin_step(ctx))) return rc;
     if (ctx->profile && ctx->profUsed > 4096) { cudaStreamSynchronize(ctx->stream); profCollect(ctx); }
     if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
     ctx->cacheValid = true;

@@ -141,16 +141,10 @@ struct pb_ctx {
     bool cacheValid = false;
     int* cPointOfsBuf[2] = {nullptr, nullptr}; int* cNpBuf[2] = {nullptr, nullptr};
 
-    // ---- joints ---------------------------------------------------------------------------------------------
+    // ---- joints (arrays owned by joints.cu) ----------------------------------------------------------------------
     int nJoints = 0;
     int jointColorStart[PB_JOINT_COLORS + 1] = {0};
-    int* jType = nullptr; int2* jRows = nullptr; int2* jBodies = nullptr;
-    float4* jA0P = nullptr; float4* jA0Q = nullptr; float4* jA1P = nullptr; float4* jA1Q = nullptr;
-    float4* jParams = nullptr;       // [2*J]
-    float4* jState = nullptr;        // [2*J] persistent per-joint state (gear angles, prismatic limit flags)
-    int* jRowOfs = nullptr; int* jNumRows = nullptr; int nJointRows = 0;
-    float4* jr[8] = {nullptr};       // joint row arrays (see joints.cu)
-    float* jrLambda = nullptr;
+    void* jointStore = nullptr;
 
     // ---- counters / host mirrors ---------------------------------------------------------------------------
     int* counters = nullptr;         // CNT_TOTAL ints on device
@@ -197,7 +191,7 @@ int pb_world_poses(pb_ctx* ctx);
 int pb_narrowphase(pb_ctx* ctx);
 int pb_contact_build(pb_ctx* ctx, int nRaw);
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
-int pb_joints_alloc(pb_ctx* ctx);
+int pb_joint_begin_step(pb_ctx* ctx);
 
 // generic device primitives (primitives.cu)
 int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,

@@ -462,3 +462,142 @@ def terrain(n_bodies=1_000_000, cells=1024, seed=0xC4, substeps=4, iterations=2,
     col_mesh = np.full(n_bodies + 1, -1, np.int32); col_mesh[0] = 0
     return bulk_scene("terrain_%d" % n_bodies, pos, quat, flags, types, params, 1.0, material=(0.4, 0.0, 0.0), col_mesh=col_mesh,
                       trimesh=[mesh], substeps=substeps, iterations=iterations)
+
+
+# ---- config 5: batched ragdoll scenes -------------------------------------------------------------------------------------
+def qmul(a, b):
+    """Hamilton product of xyzw quaternions (broadcasting)."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx,
+                     aw * bw - ax * bx - ay * by - az * bz], -1)
+
+
+def qconj(q):
+    q = np.asarray(q, np.float64).copy()
+    q[..., :3] *= -1
+    return q
+
+
+def qrot(q, v):
+    q = np.asarray(q, np.float64); v = np.asarray(v, np.float64)
+    qv = q[..., :3]
+    uv = np.cross(qv, v)
+    uuv = np.cross(qv, uv)
+    return v + 2.0 * (q[..., 3:4] * uv + uuv)
+
+
+def axis_angle(axis, ang):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    return np.concatenate([axis * math.sin(ang / 2), [math.cos(ang / 2)]])
+
+
+def ragdoll_template():
+    """One ragdoll (11 bodies, 10 joints) in T-pose + its ground box; entity 0 = ground."""
+    b = SceneBuilder("ragdoll")
+    mat = (0.6, 0.0, 0.0)
+    b.add_body((0, -0.5, 0), colliders=[dict(type=BOX, params=(3.95, 0.5, 3.95), material=mat)], dynamic=False)
+    qz = axis_angle((0, 0, 1), math.pi / 2)   # capsule Y axis -> world -X .. arms along X
+    parts = [
+        ("pelvis", BOX, (0.15, 0.10, 0.10), (0, 1.00, 0), IDQ, 8.0),
+        ("torso", BOX, (0.18, 0.22, 0.11), (0, 1.35, 0), IDQ, 20.0),
+        ("head", SPHERE, (0.11,), (0, 1.72, 0), IDQ, 5.0),
+        ("uarm_l", CAPSULE, (0.13, 0.045), (0.36, 1.5, 0), qz, 2.0),
+        ("larm_l", CAPSULE, (0.12, 0.04), (0.70, 1.5, 0), qz, 1.5),
+        ("uarm_r", CAPSULE, (0.13, 0.045), (-0.36, 1.5, 0), qz, 2.0),
+        ("larm_r", CAPSULE, (0.12, 0.04), (-0.70, 1.5, 0), qz, 1.5),
+        ("uleg_l", CAPSULE, (0.18, 0.06), (0.09, 0.68, 0), IDQ, 7.0),
+        ("lleg_l", CAPSULE, (0.18, 0.05), (0.09, 0.24, 0), IDQ, 4.0),
+        ("uleg_r", CAPSULE, (0.18, 0.06), (-0.09, 0.68, 0), IDQ, 7.0),
+        ("lleg_r", CAPSULE, (0.18, 0.05), (-0.09, 0.24, 0), IDQ, 4.0),
+    ]
+    ids = {}
+    for name, t, prm, pos, q, mass in parts:
+        ids[name] = b.add_body(pos, quat=tuple(q), colliders=[dict(type=t, params=prm, material=mat)], mass=mass)
+    qhingeZ = axis_angle((0, 1, 0), -math.pi / 2)   # local X -> world Z
+
+    def joint(jt, a, c, world_point, world_frame=IDQ, params=(), world_frame1=None):
+        ea, ec = ids[a], ids[c]
+        pa, qa = np.asarray(b.ent[ea]["pos"], float), np.asarray(b.ent[ea]["quat"], float)
+        pc, qc = np.asarray(b.ent[ec]["pos"], float), np.asarray(b.ent[ec]["quat"], float)
+        wp = np.asarray(world_point, float)
+        wf1 = world_frame if world_frame1 is None else world_frame1
+        b.add_joint(jt, ea, qrot(qconj(qa), wp - pa), qmul(qconj(qa), world_frame), ec, qrot(qconj(qc), wp - pc), qmul(qconj(qc), wf1), params)
+
+    # universal joint: the two anchor frames' z axes must be perpendicular at rest (UniversalJoint.cpp:8-20 drives u0[2].u1[2] to 0)
+    joint(J_UNIVERSAL, "pelvis", "torso", (0, 1.115, 0), IDQ, (), axis_angle((1, 0, 0), math.pi / 2))
+    joint(J_SPHERICAL, "torso", "head", (0, 1.59, 0))
+    joint(J_SPHERICAL, "torso", "uarm_l", (0.20, 1.5, 0))
+    joint(J_REVOLUTE, "uarm_l", "larm_l", (0.53, 1.5, 0), qhingeZ)
+    joint(J_SPHERICAL, "torso", "uarm_r", (-0.20, 1.5, 0))
+    joint(J_REVOLUTE, "uarm_r", "larm_r", (-0.53, 1.5, 0), qhingeZ)
+    joint(J_SPHERICAL, "pelvis", "uleg_l", (0.09, 0.89, 0))
+    joint(J_REVOLUTE, "uleg_l", "lleg_l", (0.09, 0.46, 0))
+    joint(J_SPHERICAL, "pelvis", "uleg_r", (-0.09, 0.89, 0))
+    joint(J_REVOLUTE, "uleg_r", "lleg_r", (-0.09, 0.46, 0))
+    for i in range(1, 12):
+        for j in range(i + 1, 12):
+            b.no_collide.append((i, j))
+    return b.build()
+
+
+def ragdolls(n_scenes=4096, seed=0xC5, substeps=4, iterations=2, spacing=8.0, drop=0.6) -> SceneDesc:
+    """C5: n independent ragdoll scenes (ground box + 11 bodies + 10 joints each) laid out on a grid in one registry."""
+    t = ragdoll_template()
+    m = t.n  # 12 entities per scene
+    rng = SplitMix(seed)
+    side = int(math.ceil(math.sqrt(n_scenes)))
+    s = np.arange(n_scenes)
+    off = np.stack([(s % side - side / 2.0) * spacing, np.zeros(n_scenes), (s // side - side / 2.0) * spacing], 1)
+    rootq = rng.unit_quat(n_scenes).astype(np.float64)
+    pos = np.tile(t.pos.astype(np.float64), (n_scenes, 1)).reshape(n_scenes, m, 3)
+    quat = np.tile(t.quat.astype(np.float64), (n_scenes, 1)).reshape(n_scenes, m, 4)
+    centre = np.array([0, 1.0, 0])
+    body = np.arange(1, m)
+    rel = pos[:, body] - centre
+    pos[:, body] = centre + qrot(rootq[:, None, :], rel) + np.array([0, drop + 0.9, 0])
+    quat[:, body] = qmul(rootq[:, None, :], quat[:, body])
+    pos += off[:, None, :]
+    rep = lambda a: np.tile(a, (n_scenes,) + (1,) * (a.ndim - 1))
+    d = SceneDesc(
+        pos=np.ascontiguousarray(pos.reshape(-1, 3), f32), quat=np.ascontiguousarray(quat.reshape(-1, 4), f32), flags=rep(t.flags),
+        vel=rep(t.vel), angvel=rep(t.angvel), inv_mass=rep(t.inv_mass), com=rep(t.com), inv_inertia=rep(t.inv_inertia),
+        col_offsets=np.arange(n_scenes * m + 1, dtype=np.int32), col_lpos=rep(t.col_lpos), col_lquat=rep(t.col_lquat), col_type=rep(t.col_type),
+        col_params=rep(t.col_params), col_mesh=rep(t.col_mesh), col_material=rep(t.col_material), col_flags=rep(t.col_flags), col_data=rep(t.col_data),
+        name="ragdolls_%d" % n_scenes, substeps=substeps, iterations=iterations)
+    joints = []
+    nocol = []
+    for k in range(n_scenes):
+        base = k * m
+        for (jt, e0, a0p, a0q, e1, a1p, a1q, prm) in t.joints:
+            joints.append((jt, e0 + base, a0p, a0q, e1 + base, a1p, a1q, prm))
+        nocol.extend((a + base, c + base) for a, c in t.no_collide)
+    d.joints = joints
+    d.no_collide = nocol
+    return d
+
+
+def joint_zoo(seed=5) -> SceneDesc:
+    """Small scene exercising every joint type (chains hanging from static anchors, one resting on the ground)."""
+    b = SceneBuilder("joint_zoo")
+    b.add_body((0, -0.5, 0), colliders=[dict(type=BOX, params=(20.0, 0.5, 20.0))], dynamic=False)
+    x = -6.0
+    specs = [(J_SPHERICAL, ()), (J_REVOLUTE, ()), (J_UNIVERSAL, ()), (J_FIXED, ()), (J_REVOLUTE, (1.0, 2.0, 5.0)),
+             (J_PRISMATIC, (0.5, -0.5, 0.0, 0.0, 5.0, 1.0)), (J_PRISMATIC, (0.2, -0.2, 1.0, 0.1, 5.0, 1.0)), (J_SERVO, (0.5, 30.0, 1.0))]
+    for jt, prm in specs:
+        anchor = b.add_body((x, 3.0, 0), colliders=[dict(type=BOX, params=(0.1, 0.1, 0.1))], dynamic=False)
+        prev = anchor
+        prev_pos = np.array([x, 3.0, 0.0])
+        for link in range(3):
+            p = prev_pos + np.array([0.35, -0.05, 0.02 * link])
+            cur = b.add_body(tuple(p), colliders=[dict(type=CAPSULE if link % 2 == 0 else BOX, params=(0.12, 0.05) if link % 2 == 0 else (0.1, 0.06, 0.08))], mass=1.0 + link)
+            mid = (prev_pos + p) / 2
+            q1 = axis_angle((1, 0, 0), math.pi / 2) if jt == J_UNIVERSAL else IDQ   # universal: z axes perpendicular at rest
+            b.add_joint(jt, prev, mid - prev_pos, IDQ, cur, mid - p, q1, prm)
+            prev, prev_pos = cur, p
+        x += 1.6
+    return b.build(substeps=4, iterations=2)

@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
     (lambda: S.pyramid(120), 40),
     (lambda: S.mixed_bin(1200, spacing=0.8), 60),
     (lambda: S.terrain(1500, cells=48, drop=0.3), 60),
+    (lambda: S.joint_zoo(), 50),          # every joint type except gear; servo uses acos -> 1e-4 gate, the rest are bit-exact
+    (lambda: S.ragdolls(8), 90),          # config 5 in miniature: joints + contacts
 ])
 def test_three_gates(maker, steps):
     desc = maker()
