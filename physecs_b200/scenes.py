@@ -601,3 +601,90 @@ def joint_zoo(seed=5) -> SceneDesc:
             prev, prev_pos = cur, p
         x += 1.6
     return b.build(substeps=4, iterations=2)
+
+
+# ---- config 3: convex meshes ---------------------------------------------------------------------------------------------------
+def convex_from_points(points) -> ConvexMeshDesc:
+    """ConvexMesh (reference include/Physecs/ConvexMesh.h:7-34) from a point set: faces as CCW index loops (seen from outside),
+    unit outward normals and face centroids."""
+    from scipy.spatial import ConvexHull
+    pts = np.asarray(points, np.float64)
+    hull = ConvexHull(pts)
+    used = np.unique(hull.simplices)
+    remap = -np.ones(len(pts), int); remap[used] = np.arange(len(used))
+    verts = pts[used]
+    centre = verts.mean(0)
+    groups = {}
+    for simplex, eq in zip(hull.simplices, hull.equations):
+        key = tuple(np.round(eq, 6))
+        groups.setdefault(key, set()).update(remap[simplex].tolist())
+    offsets, indices, normals, cents = [0], [], [], []
+    for key, vs in sorted(groups.items()):
+        n = np.array(key[:3]); n /= np.linalg.norm(n)
+        vs = sorted(vs)
+        c = verts[vs].mean(0)
+        # order CCW around the outward normal
+        ref = verts[vs[0]] - c
+        ref -= n * ref.dot(n)
+        ref /= np.linalg.norm(ref)
+        tang = np.cross(n, ref)
+        ang = [math.atan2((verts[v] - c).dot(tang), (verts[v] - c).dot(ref)) for v in vs]
+        order = [v for _, v in sorted(zip(ang, vs))]
+        indices.extend(order); offsets.append(len(indices)); normals.append(n); cents.append(c)
+    return ConvexMeshDesc(verts=verts.astype(f32), face_offsets=np.array(offsets, np.int32), face_indices=np.array(indices, np.int32),
+                          face_normals=np.array(normals, f32), face_centroids=np.array(cents, f32))
+
+
+def convex_templates():
+    """Six hull templates: tetrahedron, cube, octahedron, hexagonal prism, icosahedron, dodecahedron."""
+    phi = (1 + math.sqrt(5)) / 2
+    tet = [(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)]
+    cube = [(x, y, z) for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)]
+    octa = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    hexp = [(math.cos(k * math.pi / 3), y, math.sin(k * math.pi / 3)) for k in range(6) for y in (-0.8, 0.8)]
+    ico = [(0, s1, s2 * phi) for s1 in (-1, 1) for s2 in (-1, 1)] + [(s1, s2 * phi, 0) for s1 in (-1, 1) for s2 in (-1, 1)] + \
+          [(s2 * phi, 0, s1) for s1 in (-1, 1) for s2 in (-1, 1)]
+    dod = [(x, y, z) for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)] + [(0, s1 / phi, s2 * phi) for s1 in (-1, 1) for s2 in (-1, 1)] + \
+          [(s1 / phi, s2 * phi, 0) for s1 in (-1, 1) for s2 in (-1, 1)] + [(s2 * phi, 0, s1 / phi) for s1 in (-1, 1) for s2 in (-1, 1)]
+    out = []
+    for pts in (tet, cube, octa, hexp, ico, dod):
+        p = np.array(pts, np.float64)
+        p /= np.abs(p).max()
+        out.append(convex_from_points(p))
+    return out
+
+
+def convex_pile(n_bodies=250_000, seed=0xC3, substeps=4, iterations=2, spacing=1.2, mix_prims=False) -> SceneDesc:
+    """C3: convex-mesh bodies (6 templates, per-body scale in [0.3,0.5]^3) on a lattice over a static box floor.
+    mix_prims=True replaces every 4th body by a sphere / capsule / box so all X-convex pair routines are exercised."""
+    rng = SplitMix(seed)
+    meshes = convex_templates()
+    nx = nz = max(2, int(math.ceil((n_bodies / 2.0) ** (1 / 3.0))))
+    i = np.arange(n_bodies)
+    gx, gz, gy = i % nx, (i // nx) % nz, i // (nx * nz)
+    jit = np.stack([rng.uniform(n_bodies, -0.1, 0.1) for _ in range(3)], 1)
+    p = np.stack([(gx - nx / 2 + 0.5) * spacing, 0.8 + gy * spacing, (gz - nz / 2 + 0.5) * spacing], 1).astype(f32) + jit
+    prm = np.zeros((n_bodies, 4), f32)
+    prm[:, 0], prm[:, 1], prm[:, 2] = rng.uniform(n_bodies, 0.3, 0.5), rng.uniform(n_bodies, 0.3, 0.5), rng.uniform(n_bodies, 0.3, 0.5)
+    t = np.full(n_bodies, CONVEX_MESH, np.int32)
+    mesh = (i % len(meshes)).astype(np.int32)
+    if mix_prims:
+        sel = i % 4 == 3
+        t[sel] = (i[sel] // 4) % 3
+        mesh[sel] = -1
+        prm[t == CAPSULE, 1] = prm[t == CAPSULE, 1] * 0.6
+    q = rng.unit_quat(n_bodies)
+    half = nx * spacing / 2 + 3.0
+    pos = np.concatenate([np.array([[0, -1, 0]], f32), p]); quat = np.concatenate([IDQ[None], q])
+    flags = np.concatenate([np.zeros(1, np.int32), np.full(n_bodies, F_DYNAMIC, np.int32)])
+    types = np.concatenate([np.array([BOX], np.int32), t]); params = np.concatenate([np.array([[half, 1, half, 0]], f32), prm])
+    col_mesh = np.concatenate([np.array([-1], np.int32), mesh])
+    d = bulk_scene("convex_pile_%d" % n_bodies, pos, quat, flags, types, params, 1.0, material=(0.4, 0.0, 0.0), col_mesh=col_mesh,
+                   convex=meshes, substeps=substeps, iterations=iterations)
+    # convex inertia: use the solid-box approximation of the scaled bounding box (inputs to both sides; MassUtil is setup-time)
+    cm = types == CONVEX_MESH
+    hx, hy, hz = params[cm, 0], params[cm, 1], params[cm, 2]
+    mm = f32(1.0 / 12.0)
+    d.inv_inertia[cm, 0] = f32(1) / (mm * (hy * hy + hz * hz) * f32(4)); d.inv_inertia[cm, 4] = f32(1) / (mm * (hx * hx + hz * hz) * f32(4))
+    d.inv_inertia[cm, 8] = f32(1) / (mm * (hx * hx + hy * hy) * f32(4))
+    return d

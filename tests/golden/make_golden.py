@@ -36,6 +36,21 @@ def soup(n=90, seed=11, extent=2.2):
     return S.bulk_scene("soup", p, q, flags, t, prm, 1.0, substeps=4)
 
 
+def convex_soup(n=80, seed=13, extent=1.8):
+    """Dense soup of convex meshes mixed with spheres / capsules / boxes (GJK/EPA routines)."""
+    rng = S.SplitMix(seed)
+    meshes = S.convex_templates()
+    p = np.stack([rng.uniform(n, -extent, extent) for _ in range(3)], 1)
+    q = rng.unit_quat(n)
+    i = np.arange(n)
+    t = np.where(i % 3 == 2, (i // 3) % 3, S.CONVEX_MESH).astype(np.int32)
+    prm = np.zeros((n, 4), np.float32)
+    prm[:, 0], prm[:, 1], prm[:, 2] = rng.uniform(n, 0.3, 0.55), rng.uniform(n, 0.25, 0.5), rng.uniform(n, 0.3, 0.55)
+    mesh = np.where(t == S.CONVEX_MESH, i % len(meshes), -1).astype(np.int32)
+    flags = np.full(n, S.F_DYNAMIC, np.int32)
+    return S.bulk_scene("convex_soup", p, q, flags, t, prm, 1.0, col_mesh=mesh, convex=meshes, substeps=4)
+
+
 def all_pairs(n):
     i, j = np.triu_indices(n, 1)
     z = np.zeros_like(i)
@@ -56,6 +71,13 @@ def main():
     m = r.narrowphase(pr)
     np.savez_compressed(os.path.join(HERE, "narrowphase_mesh.npz"), **m)
     print("mesh manifolds", len(m["keys"]), "points hist", np.bincount(m["num_points"]))
+    r.close()
+
+    d = convex_soup()
+    r = RefScene(d, 0, hashfix=True)
+    m = r.narrowphase(all_pairs(d.n))
+    np.savez_compressed(os.path.join(HERE, "narrowphase_convex.npz"), **m)
+    print("convex manifolds", len(m["keys"]), "points hist", np.bincount(m["num_points"]))
     r.close()
 
     d = S.pyramid(60)

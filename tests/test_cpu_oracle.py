@@ -38,6 +38,18 @@ def test_oracle_reproduces_golden_narrowphase():
 
 
 @needs_oracle
+def test_oracle_reproduces_golden_convex():
+    mg = _golden_module()
+    d = mg.convex_soup()
+    r = R.RefScene(d, 0, hashfix=True)
+    m = r.narrowphase(mg.all_pairs(d.n))
+    g = np.load(os.path.join(GOLD, "narrowphase_convex.npz"))
+    for k in ("keys", "num_points", "normal", "points"):
+        assert np.array_equal(m[k], g[k]), k
+    r.close()
+
+
+@needs_oracle
 def test_oracle_reproduces_golden_mesh():
     d = S.terrain(400, cells=24, drop=-0.15)
     r = R.RefScene(d, 0, hashfix=True)

@@ -47,3 +47,14 @@ def test_mesh_manifolds_match_golden():
     n, worst = parity.compare_manifolds(gm, _gold("narrowphase_mesh.npz"), tol=0.0)
     assert n > 300 and worst == 0.0
     ctx.close()
+
+
+def test_convex_manifolds_match_golden():
+    """GJK / EPA bin (sphere / capsule / box / convex vs convex) against the reference's physecs::collision."""
+    d = _golden_module().convex_soup()
+    ctx = Context(d)
+    ctx.step()
+    gm = ctx.manifolds()
+    n, worst = parity.compare_manifolds(gm, _gold("narrowphase_convex.npz"), tol=0.0)
+    assert n > 100 and worst == 0.0
+    ctx.close()

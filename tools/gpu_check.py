@@ -25,6 +25,7 @@ CASES = {
     "terrain": lambda: (S.terrain(1500, cells=48, drop=0.3), 50),
     "zoo": lambda: (S.joint_zoo(), 60),
     "ragdolls": lambda: (S.ragdolls(8), 90),
+    "convex": lambda: (S.convex_pile(300, mix_prims=True), 90),
     **{"zoo%d" % i: (lambda i=i: (zoo_part(i), 40)) for i in range(8)},
 }
 
