@@ -13,15 +13,20 @@
 #include "np_prims.cuh"
 #include "np_mesh.cuh"
 #include "np_gjk.cuh"
+#include "np_mesh_heavy.cuh"
 
 #define COLF_TRIGGER 1
 #define COLF_ENABLE 2
 #define COLF_DYNAMIC 4
 
-enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_COUNT };
+enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_MESHH, BIN_COUNT };
 
 __device__ __forceinline__ int binOf(int t0, int t1) {
-    if (t0 == PB_TRIANGLE_MESH || t1 == PB_TRIANGLE_MESH) return (t0 == t1) ? -1 : BIN_MESH;
+    if (t0 == PB_TRIANGLE_MESH || t1 == PB_TRIANGLE_MESH) {
+        if (t0 == t1) return -1;
+        int other = t0 == PB_TRIANGLE_MESH ? t1 : t0;
+        return (other == PB_SPHERE || other == PB_CAPSULE) ? BIN_MESH : BIN_MESHH;   // box / convex vs mesh: GJK-sized scratch
+    }
     if (t0 == PB_CONVEX_MESH || t1 == PB_CONVEX_MESH) return BIN_GJK;
     int lo = min(t0, t1), hi = max(t0, t1);
     if (lo == PB_SPHERE) return hi == PB_SPHERE ? BIN_SS : (hi == PB_CAPSULE ? BIN_SC : BIN_SB);
@@ -163,13 +168,65 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
     }
 }
 
-// ---- mesh bin --------------------------------------------------------------------------------------------------------
+// ---- mesh bins -------------------------------------------------------------------------------------------------------
+// Collect triangle contacts of one (shape, mesh) pair in the reference's traversal order (TriangleMesh.cpp:166-192:
+// explicit stack, left child popped first; CollisionTriangleMesh.cpp:895-907).
+template <bool HEAVY>
+__device__ inline int meshCollect(int type, float4 prm, V3 localPos, Q4 localOr, const PbTriMeshDev& mesh,
+                                  const PbConvexDev* convexes, int convexId, TriContact* contacts, bool* overflow, Epa* scratch, int* counters) {
+    Aabb lb = shapeBounds(localPos, localOr, type, prm, convexes, convexId);
+    Shape convexShape;
+    if (HEAVY && type == PB_CONVEX_MESH) convexShape = makeShape(type, prm, localPos, localOr, convexes, convexId);
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    int cnt = 0;
+    while (sp > 0) {
+        int node = stack[--sp];
+        float4 nmn = mesh.nodeMin[node], nmx = mesh.nodeMax[node];
+        if (lb.mx.x < nmn.x || lb.mn.x > nmx.x) continue;      // physecs::intersects (BoundsUtil.cpp:87-92)
+        if (lb.mx.y < nmn.y || lb.mn.y > nmx.y) continue;
+        if (lb.mx.z < nmn.z || lb.mn.z > nmx.z) continue;
+        int triCount = __float_as_int(nmn.w), index = __float_as_int(nmx.w);
+        if (triCount) {
+            for (int k = 0; k < triCount; ++k) {
+                int tri = index + k;
+                int4 ti = mesh.tris[tri];
+                V3 a = mk3(mesh.verts[ti.x]), b = mk3(mesh.verts[ti.y]), c = mk3(mesh.verts[ti.z]);
+                V3 n = mk3(mesh.triNormal[tri]);
+                TriContact tc;
+                tc.boxFeature = 0; tc.boxAxis = 0; tc.fidx = 0; tc.feature = TF_FACE; tc.dist = 0.f;
+                tc.normal = tc.cpBody = tc.cpTri = mk3(0.f);
+                bool hit = false;
+                if (!HEAVY) {
+                    if (type == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, a, b, c, n, tc);
+                    else hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, a, b, c, n, tc);
+                } else {
+                    if (type == PB_BOX) hit = boxTriangle(localPos, localOr, mk3(prm.x, prm.y, prm.z), a, b, c, n, tc);
+                    else hit = convexTriangle(convexShape, a, b, c, mk3(mesh.triCentroid[tri]), tc, *scratch, counters);
+                }
+                if (hit) {
+                    tc.tri = tri;
+                    if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
+                    else *overflow = true;
+                }
+            }
+        } else {
+            if (sp + 2 <= 64) { stack[sp++] = index + 1; stack[sp++] = index; }
+            else *overflow = true;
+        }
+    }
+    return cnt;
+}
+
+template <bool HEAVY>
 __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
                                                  const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                  const PbTriMeshDev* __restrict__ meshes, const PbConvexDev* __restrict__ convexes,
                                                  int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
-    int start = counters[CNT_BINSTART + BIN_MESH], end = counters[CNT_BINSTART + BIN_MESH + 1];
+    const int BIN = HEAVY ? BIN_MESHH : BIN_MESH;
+    int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
     int lane = threadIdx.x & 31;
     for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
         int idx = base + lane;
@@ -196,9 +253,10 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             Q4 invOr1 = qinverse(or1);
             localPos = rotate(invOr1, pos0 - pos1);
             localOr = qmul(invOr1, or0);
-            if (type == PB_SPHERE || type == PB_CAPSULE) {
+            {
                 bool overflow = false;
-                int cnt = meshCollect(type, prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow);
+                Epa scratch;
+                int cnt = meshCollect<HEAVY>(type, prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow, HEAVY ? &scratch : nullptr, counters);
                 if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
                 // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
                 unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
@@ -239,18 +297,29 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
                     order[nGen++] = (unsigned char)ci;
                     voidInsert(voidSet, nVoid, vi[0]); voidInsert(voidSet, nVoid, vi[1]); voidInsert(voidSet, nVoid, vi[2]);
                 }
-            } else {
-                atomicOr(&counters[CNT_STATUS], PB_STATUS_UNSUPPORTED_SHAPE);
             }
         }
         int slot = warpReserve(nGen, &counters[CNT_RAWM]);
         for (int g = 0; g < nGen; ++g) {
             const TriContact& tc = contacts[order[g]];
             Manifold m; m.np = 0; m.tri = tc.tri;
-            if (type == PB_CAPSULE && tc.feature == TF_FACE) {
-                if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
+            if (!HEAVY) {
+                if (type == PB_CAPSULE && tc.feature == TF_FACE) {
+                    if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
+                } else {
+                    manifoldFromClosest(pos1, or1, tc, m);
+                }
+            } else if (type == PB_BOX) {
+                // CTM.cpp:843-880: FACE -> box vs triangle face; EDGE -> by box feature; VERTEX -> box face vs triangle
+                V3 he = mk3(prm.x, prm.y, prm.z);
+                if (tc.feature == TF_FACE) boxTriangleFaceManifold(localPos, localOr, he, pos1, or1, meshes[meshId], tc, m);
+                else if (tc.feature == TF_EDGE && tc.boxFeature != BOXF_FACE) boxEdgeTriangleEdgeManifold(localPos, localOr, he, pos1, or1, meshes[meshId], tc, m);
+                else boxFaceTriangleManifold(localPos, localOr, he, pos1, or1, meshes[meshId], tc, m);
             } else {
-                manifoldFromClosest(pos1, or1, tc, m);
+                const PbConvexDev& cm = convexes[colMesh[shape]];
+                V3 sc = mk3(prm.x, prm.y, prm.z);
+                if (tc.feature == TF_FACE) convexTriangleFaceManifold(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, counters);
+                else convexFaceTriangleManifold(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, counters);
             }
             m.tri = tc.tri;
             // a == side 0 of the pair; manifolds are computed shape->mesh, flip when the mesh is side 0
@@ -274,7 +343,10 @@ int pb_narrowphase(pb_ctx* ctx) {
     if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
 #undef LAUNCH_PRIM
     if (!ctx->triMeshes.empty())
-        ++ctx->launches, k_np_mesh<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+        ++ctx->launches, k_np_mesh<true><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+                                                   ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
+    if (!ctx->triMeshes.empty())
+        ++ctx->launches, k_np_mesh<false><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                    ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

@@ -131,44 +131,3 @@ __device__ __forceinline__ void voidInsert(unsigned int* set, int& n, unsigned i
     if (!voided(set, n, v) && n < 3 * PB_MAX_TRI_CONTACTS) set[n++] = v;
 }
 
-// Collect triangle contacts of one (shape, mesh) pair in the reference's traversal order.
-// Returns the number of contacts (capped at PB_MAX_TRI_CONTACTS, *overflow set when the cap is hit).
-__device__ inline int meshCollect(int type, float4 prm, V3 localPos, Q4 localOr, const PbTriMeshDev& mesh,
-                                  const PbConvexDev* convexes, int convexId, TriContact* contacts, bool* overflow) {
-    Aabb lb = shapeBounds(localPos, localOr, type, prm, convexes, convexId);
-    int stack[64];
-    int sp = 0;
-    stack[sp++] = 0;
-    int cnt = 0;
-    while (sp > 0) {
-        int node = stack[--sp];
-        float4 nmn = mesh.nodeMin[node], nmx = mesh.nodeMax[node];
-        // physecs::intersects (BoundsUtil.cpp:87-92)
-        if (lb.mx.x < nmn.x || lb.mn.x > nmx.x) continue;
-        if (lb.mx.y < nmn.y || lb.mn.y > nmx.y) continue;
-        if (lb.mx.z < nmn.z || lb.mn.z > nmx.z) continue;
-        int triCount = __float_as_int(nmn.w), index = __float_as_int(nmx.w);
-        if (triCount) {
-            for (int k = 0; k < triCount; ++k) {
-                int tri = index + k;
-                int4 ti = mesh.tris[tri];
-                V3 a = mk3(mesh.verts[ti.x]), b = mk3(mesh.verts[ti.y]), c = mk3(mesh.verts[ti.z]);
-                V3 n = mk3(mesh.triNormal[tri]);
-                TriContact tc;
-                tc.boxFeature = 0; tc.boxAxis = 0;
-                bool hit = false;
-                if (type == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, a, b, c, n, tc);
-                else if (type == PB_CAPSULE) hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, a, b, c, n, tc);
-                if (hit) {
-                    tc.tri = tri;
-                    if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
-                    else *overflow = true;
-                }
-            }
-        } else {
-            if (sp + 2 <= 64) { stack[sp++] = index + 1; stack[sp++] = index; }
-            else *overflow = true;
-        }
-    }
-    return cnt;
-}

@@ -604,6 +604,36 @@ def joint_zoo(seed=5) -> SceneDesc:
 
 
 # ---- config 3: convex meshes ---------------------------------------------------------------------------------------------------
+def terrain_mixed(n_bodies=2000, cells=48, seed=0xC6, substeps=4, iterations=2, spacing=1.0, drop=0.3) -> SceneDesc:
+    """All four dynamic shape kinds (sphere, capsule, box, convex mesh) over a triangle-mesh terrain: exercises every
+    X-vs-triangle routine of CollisionTriangleMesh.cpp."""
+    rng = SplitMix(seed)
+    mesh = terrain_mesh(cells, 1.0, seed)
+    meshes = convex_templates()
+    side = int(math.ceil(math.sqrt(n_bodies)))
+    i = np.arange(n_bodies)
+    gx, gz = i % side, i // side
+    x = (gx - side / 2 + 0.5) * spacing + rng.uniform(n_bodies, -0.2, 0.2)
+    z = (gz - side / 2 + 0.5) * spacing + rng.uniform(n_bodies, -0.2, 0.2)
+    y = terrain_height(x, z) + 0.25 + drop
+    p = np.stack([x, y, z], 1).astype(f32)
+    t = (i % 4).astype(np.int32)
+    prm = np.zeros((n_bodies, 4), f32)
+    a, b, c = rng.uniform(n_bodies, 0.2, 0.35), rng.uniform(n_bodies, 0.15, 0.3), rng.uniform(n_bodies, 0.2, 0.35)
+    prm[:, 0] = a
+    prm[t == CAPSULE, 1] = b[t == CAPSULE]
+    prm[t >= BOX, 1] = b[t >= BOX] + 0.05
+    prm[t >= BOX, 2] = c[t >= BOX]
+    cmesh = np.where(t == CONVEX_MESH, (i // 4) % len(meshes), -1).astype(np.int32)
+    q = rng.unit_quat(n_bodies)
+    pos = np.concatenate([np.zeros((1, 3), f32), p]); quat = np.concatenate([IDQ[None], q])
+    flags = np.concatenate([np.zeros(1, np.int32), np.full(n_bodies, F_DYNAMIC, np.int32)])
+    types = np.concatenate([np.array([TRIANGLE_MESH], np.int32), t]); params = np.concatenate([np.zeros((1, 4), f32), prm])
+    col_mesh = np.concatenate([np.array([0], np.int32), cmesh])
+    return bulk_scene("terrain_mixed_%d" % n_bodies, pos, quat, flags, types, params, 1.0, material=(0.4, 0.1, 0.0), col_mesh=col_mesh,
+                      trimesh=[mesh], convex=meshes, substeps=substeps, iterations=iterations)
+
+
 def convex_from_points(points) -> ConvexMeshDesc:
     """ConvexMesh (reference include/Physecs/ConvexMesh.h:7-34) from a point set: faces as CCW index loops (seen from outside),
     unit outward normals and face centroids."""

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
     (lambda: S.terrain(1500, cells=48, drop=0.3), 60, True),
     (lambda: S.joint_zoo(), 50, False),        # every joint type except gear; servo uses acos -> 1e-4 gate, the rest are bit-exact
     (lambda: S.ragdolls(8), 90, True),
-    (lambda: S.convex_pile(300, mix_prims=True), 90, True),   # config 3 in miniature: GJK/EPA, all X-convex routines        # config 5 in miniature: joints + contacts
+    (lambda: S.convex_pile(300, mix_prims=True), 90, True),   # config 3 in miniature: GJK/EPA, all X-convex routines
+    (lambda: S.terrain_mixed(800, cells=40), 90, True),        # sphere / capsule / box / convex vs triangle mesh        # config 5 in miniature: joints + contacts
 ])
 def test_three_gates(maker, steps, need_contacts):
     desc = maker()

@@ -26,6 +26,7 @@ CASES = {
     "zoo": lambda: (S.joint_zoo(), 60),
     "ragdolls": lambda: (S.ragdolls(8), 90),
     "convex": lambda: (S.convex_pile(300, mix_prims=True), 90),
+    "tmix": lambda: (S.terrain_mixed(800, cells=40), 90),
     **{"zoo%d" % i: (lambda i=i: (zoo_part(i), 40)) for i in range(8)},
 }
 
