@@ -29,7 +29,7 @@ enum {
     PB_ECUDA = 1,        /* CUDA runtime error (message in pb_last_error) */
     PB_ECAPACITY = 2,    /* a per-step arena overflowed (pairs / manifolds / triangle contacts); results of the step are invalid */
     PB_EINVAL = 3,       /* bad argument */
-    PB_EUNSUPPORTED = 4  /* feature of the reference not available on the device path (message says which) */
+    PB_EUNSUPPORTED = 4  /* a shape pair the reference itself has no routine for (mesh vs mesh) reached the narrowphase */
 };
 
 /* geometry types == physecs::GeometryType (reference include/Physecs/Colliders.h:9) */
@@ -58,7 +58,7 @@ typedef struct pb_counts {
     int n_overflow;      /* manifolds in the sequential overflow bucket (colour 63) */
     int status;          /* PB_OK or PB_ECAPACITY */
     int n_mesh_pairs;
-    int n_triggers;
+    int n_triggers;      /* overlapping trigger pairs (== triggerCacheTemp.size()) */
 } pb_counts;
 
 /* device times of the last pb_step in milliseconds (CUDA events on the context's stream) */
@@ -104,17 +104,39 @@ int pb_build_trimesh(const float* verts3, int n_verts, const unsigned* indices, 
                      int* tri_orig, float* node_bounds6, int* node_count_index2, int* n_nodes);
 /* joints: params per type -- revolute {driveEnabled, driveVelocity, driveMaxTorque}; prismatic {upper, lower,
  * driveEnabled, targetPosition, stiffness, damping}; gear {ratio}; servo {targetAngle, stiffness, damping}.
- * color[n]: colour assigned by the host-side greedy colouring (reference Physecs.cpp:690-710), 8 = overflow. */
+ * color[n]: colour assigned by the host-side greedy colouring (reference Physecs.cpp:690-710); 0..7 are solved one
+ * thread per joint with the SIMD-path semantics (Constraint1DW.cpp), 8 = the overflow bucket, solved sequentially
+ * with the scalar-path semantics (Constraint1D.cpp, quirk Q9). */
 int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* body_row0, const int* body_row1,
                      const float* anchor0_pos3, const float* anchor0_quat4, const float* anchor1_pos3,
                      const float* anchor1_quat4, const float* params8, const int* color);
+/* new parameters of the uploaded joints after a setter call on a live joint (reference Joints/*.cpp setters); same
+ * layout and joint order as pb_upload_joints; accumulated impulses and gear angle state are kept */
+int pb_update_joint_params(pb_ctx* ctx, int n, const float* params8);
 /* entity pairs that must not collide (reference nonCollidingPairs, Physecs.cpp:209,:694,:788): rows (e0<e1) */
 int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* entity_pairs2);
+/* Contact filter (reference Scene::setContactFilter, Physecs.cpp:200, :795): the user's function
+ * ContactType f(bool isTrigger0, int data0, bool isTrigger1, int data1) depends only on the (isTrigger, data) class of
+ * each collider, so the host tabulates it: collider_class[n_colliders] in [0, n_classes), lut[c0 * n_classes + c1] = 1
+ * when f answers TRIGGER for (class c0 = side 0 = lower entity, class c1).  n_classes = 0 restores defaultContactFilter
+ * (Physecs.cpp:20-23).  Must be called again after pb_upload_colliders. */
+int pb_set_contact_filter(pb_ctx* ctx, int n_colliders, const int* collider_class, int n_classes, const unsigned char* lut);
+/* isKinematic of every dynamic row changed (Scene::setIsKinematic, Physecs.cpp:753-770): solver flags and the
+ * BroadPhaseEntry::isDynamic bit of the owning colliders follow */
+int pb_set_kinematic(pb_ctx* ctx, int n_dynamic, const int* kinematic);
+/* mass properties of the dynamic rows changed in the registry (the reference reads them live every step) */
+int pb_set_mass(pb_ctx* ctx, int n_dynamic, const float* inv_mass, const float* com3, const float* inv_inertia9);
+/* overwrite persistent collider bounds (BroadPhaseEntry::bounds): lets the host carry bounds across a re-upload so the
+ * creation-without-margin / margin-after-update history of surviving colliders is kept (quirk Q6) */
+int pb_set_bounds(pb_ctx* ctx, int n, const int* colliders, const float* bounds6);
 
 /* ---- per-step state exchange ---------------------------------------------------------------------- */
 /* push registry state of the dynamic rows (what the reference reads through registry.get each step) */
 int pb_set_state(pb_ctx* ctx, int n_dynamic, const float* pos3, const float* quat4, const float* vel3,
                  const float* angvel3);
+/* transforms of the static rows [n_dynamic, n_dynamic + n_static): the reference reads every Transform live in the
+ * narrowphase (Physecs.cpp:191-198) while bounds only follow registry.patch (pb_move_rows) */
+int pb_set_static_poses(pb_ctx* ctx, int n_static, const float* pos3, const float* quat4);
 /* a static/kinematic row was moved through registry.patch<TransformComponent> (Physecs.cpp:51-54,:79-90):
  * new transform + bounds refresh with the 0.01 margin */
 int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4);
@@ -131,6 +153,10 @@ int pb_get_counts(pb_ctx* ctx, pb_counts* out);
 int pb_get_timings(pb_ctx* ctx, pb_timings* out);
 /* candidate pairs of the last step as rows (entity0, colIdx0, entity1, colIdx1), entity0 < entity1 */
 int pb_get_pairs(pb_ctx* ctx, int* out4, int cap, int* n);
+/* overlapping TRIGGER pairs of the last step (reference triggerCacheTemp, Physecs.cpp:200-207) as rows
+ * (entity0, colIdx0, entity1, colIdx1), entity0 < entity1; the enter / exit diff and listener calls
+ * (Physecs.cpp:538-552) are host work */
+int pb_get_triggers(pb_ctx* ctx, int* out4, int cap, int* n);
 /* collider bounds rows (min xyz, max xyz) in collider order */
 int pb_get_bounds(pb_ctx* ctx, float* out6);
 /* manifolds of the last step in SOLVE ORDER (colour-major): keys rows (entity0, colIdx0, entity1, colIdx1, tri),

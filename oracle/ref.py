@@ -147,6 +147,26 @@ class RefScene:
         full = np.concatenate([pr[keys[:, 0]], keys[:, 1:2]], 1) if m else np.zeros((0, 5), np.int32)
         return dict(keys=full, num_points=keys[:, 2].copy(), normal=nrm[:m], points=pts[:m])
 
+    def triggers(self):
+        """Overlapping trigger pairs of the last simulate, rows (e0, c0, e1, c1)."""
+        n = self.lib.ph_num_triggers(self.h)
+        out = np.zeros((max(n, 1), 4), np.int32)
+        self.lib.ph_get_triggers(self.h, _p(out, C.c_int))
+        return out[:n]
+
+    def record_trigger_events(self):
+        self.lib.ph_record_trigger_events(self.h)
+
+    def take_trigger_events(self):
+        """Listener calls since the last take, rows (0 enter | 1 exit, e0, c0, e1, c1)."""
+        cap = 1 << 16
+        out = np.zeros((cap, 5), np.int32)
+        n = self.lib.ph_take_trigger_events(self.h, _p(out, C.c_int), cap)
+        return out[:min(n, cap)]
+
+    def set_contact_filter(self, mode):
+        self.lib.ph_set_contact_filter(self.h, int(mode))
+
     def trimesh(self, mesh_id=0):
         nt, nn = C.c_int(), C.c_int()
         self.lib.ph_trimesh_sizes(self.h, mesh_id, C.byref(nt), C.byref(nn))

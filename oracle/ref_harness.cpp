@@ -46,7 +46,26 @@ struct Key5 {
     }
 };
 
+struct TriggerRecorder : physecs::OnTriggerEnterListener, physecs::OnTriggerExitListener {
+    std::vector<std::array<int, 5>> events;   // (0 = enter | 1 = exit, e0, c0, e1, c1)
+    void onTriggerEnter(entt::entity e0, int c0, entt::entity e1, int c1) override { events.push_back({ 0, (int)e0, c0, (int)e1, c1 }); }
+    void onTriggerExit(entt::entity e0, int c0, entt::entity e1, int c1) override { events.push_back({ 1, (int)e0, c0, (int)e1, c1 }); }
+};
+
+// custom contact filters for the setContactFilter tests (Physecs.h:224); the same predicates are tabulated in
+// tests/parity.py for the device path
+physecs::ContactType filterParity(bool t0, int d0, bool t1, int d1) {
+    if ((t0 || t1) && ((d0 + d1) % 2 == 0)) return physecs::TRIGGER;
+    return physecs::COLLISION;
+}
+physecs::ContactType filterAsymmetric(bool t0, int d0, bool t1, int d1) {
+    if (t0 && !t1) return physecs::TRIGGER;
+    if (t1 && d0 == 1) return physecs::TRIGGER;
+    return physecs::COLLISION;
+}
+
 struct Harness {
+    TriggerRecorder recorder;
     entt::registry registry;
     std::unique_ptr<physecs::Scene> scene;
     std::vector<entt::entity> entities;
@@ -401,6 +420,37 @@ int ph_narrowphase(void* hp, const int* pairs, int npairs, int cap, int* keys, f
         }
     }
     return m;
+}
+
+// overlapping trigger pairs after the last simulate (triggerCache after the swap at Physecs.cpp:553)
+int ph_num_triggers(void* hp) { return (int)((Harness*)hp)->scene->triggerCache.size(); }
+void ph_get_triggers(void* hp, int* out) {
+    auto* h = (Harness*)hp;
+    size_t i = 0;
+    for (auto& p : h->scene->triggerCache) {
+        out[4 * i + 0] = (int)p.entity0; out[4 * i + 1] = p.colliderIndex0;
+        out[4 * i + 2] = (int)p.entity1; out[4 * i + 3] = p.colliderIndex1;
+        ++i;
+    }
+}
+// register the recording listeners (Scene::addOnTriggerEnterCallback / addOnTriggerExitCallback)
+void ph_record_trigger_events(void* hp) {
+    auto* h = (Harness*)hp;
+    h->scene->addOnTriggerEnterCallback(&h->recorder);
+    h->scene->addOnTriggerExitCallback(&h->recorder);
+}
+// events since the last call, rows (kind, e0, c0, e1, c1); returns the count and clears the log
+int ph_take_trigger_events(void* hp, int* out, int cap) {
+    auto* h = (Harness*)hp;
+    int n = (int)h->recorder.events.size();
+    for (int i = 0; i < n && i < cap; ++i) for (int k = 0; k < 5; ++k) out[5 * i + k] = h->recorder.events[i][k];
+    h->recorder.events.clear();
+    return n;
+}
+// 0 = defaultContactFilter, 1 = filterParity, 2 = filterAsymmetric
+void ph_set_contact_filter(void* hp, int mode) {
+    auto* h = (Harness*)hp;
+    h->scene->setContactFilter(mode == 1 ? filterParity : mode == 2 ? filterAsymmetric : physecs::defaultContactFilter);
 }
 
 int ph_num_dynamic(void* hp) {

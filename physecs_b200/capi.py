@@ -23,7 +23,9 @@ EXPORTS = [
     "pb_upload_bodies", "pb_upload_colliders", "pb_register_convex", "pb_register_trimesh", "pb_upload_joints",
     "pb_set_noncolliding_pairs", "pb_set_state", "pb_move_rows", "pb_refresh_bounds", "pb_step", "pb_get_state", "pb_sync",
     "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds", "pb_build_trimesh",
-    "pb_set_profile", "pb_get_profile", "pb_get_launches",
+    "pb_set_profile", "pb_get_profile", "pb_get_launches", "pb_profiler_range",
+    "pb_update_joint_params", "pb_set_contact_filter", "pb_set_kinematic", "pb_set_mass", "pb_set_bounds",
+    "pb_set_static_poses", "pb_get_triggers",
 ]
 
 
@@ -273,6 +275,32 @@ class Context:
         out = np.zeros((len(self.desc.col_type), 6), np.float32)
         self._check(self.lib.pb_get_bounds(self.ctx, _p(out)))
         return out
+
+    def triggers(self):
+        """Overlapping trigger pairs of the last step, rows (entity0, colIdx0, entity1, colIdx1)."""
+        cap = max(self.counts().n_triggers, 1)
+        out = np.zeros((cap, 4), np.int32)
+        n = C.c_int()
+        self._check(self.lib.pb_get_triggers(self.ctx, _p(out, C.c_int), cap, C.byref(n)))
+        return out[:n.value]
+
+    def set_contact_filter(self, fn=None):
+        """Tabulate a contact filter fn(isTrigger0, data0, isTrigger1, data1) -> bool (True = TRIGGER) over the (isTrigger, data)
+        classes present in the scene and hand the table to the device (reference Scene::setContactFilter).  None = default."""
+        d = self.desc
+        if fn is None:
+            self._check(self.lib.pb_set_contact_filter(self.ctx, 0, None, 0, None))
+            return
+        keys = list(zip((d.col_flags & S.COL_TRIGGER).astype(bool).tolist(), d.col_data.tolist()))
+        classes = sorted(set(keys))
+        index = {k: i for i, k in enumerate(classes)}
+        cls = _i([index[k] for k in keys])
+        K = len(classes)
+        lut = np.zeros((K, K), np.uint8)
+        for i, (t0, d0) in enumerate(classes):
+            for j, (t1, d1) in enumerate(classes):
+                lut[i, j] = 1 if fn(t0, d0, t1, d1) else 0
+        self._check(self.lib.pb_set_contact_filter(self.ctx, len(cls), _p(cls, C.c_int), K, lut.ctypes.data_as(C.POINTER(C.c_ubyte))))
 
     def manifolds(self):
         cap = max(self.counts().n_manifolds, 1)

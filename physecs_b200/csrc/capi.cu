@@ -15,6 +15,7 @@ int pb_fail(pb_ctx* ctx, int code, const std::string& msg) {
 int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const int* row1, const float* a0p, const float* a0q,
                      const float* a1p, const float* a1q, const float* params8, const int* color);
 void pb_joints_free(pb_ctx* ctx);
+int pb_joints_update_params(pb_ctx* ctx, int n, const float* params8);
 
 // ---- packed host layout <-> float4 SoA ----------------------------------------------------------------------------
 __global__ void k_unpack3(int n, const float* __restrict__ src, float4* __restrict__ dst) {
@@ -49,6 +50,22 @@ __global__ void k_scatter_rows(int n, const int* __restrict__ rows, const float*
     pos[r] = make_float4(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], 0.f);
     quat[r] = make_float4(q4[4 * i], q4[4 * i + 1], q4[4 * i + 2], q4[4 * i + 3]);
     mark[r] = 1;
+}
+
+__global__ void k_scatter_bounds(int n, const int* __restrict__ cols, const float* __restrict__ b6, float4* __restrict__ mn, float4* __restrict__ mx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cols[i];
+    mn[c] = make_float4(b6[6 * i], b6[6 * i + 1], b6[6 * i + 2], 0.f);
+    mx[c] = make_float4(b6[6 * i + 3], b6[6 * i + 4], b6[6 * i + 5], 0.f);
+}
+// BroadPhaseEntry::isDynamic (Physecs.cpp:56-77, :753-770): bit2 of the device collider flags
+__global__ void k_col_dynamic_flag(int n, const int* __restrict__ colRow, int nDyn, const int* __restrict__ kinematic, int* __restrict__ colFlags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int row = colRow[i];
+    bool dyn = row < nDyn && !kinematic[row];
+    colFlags[i] = (colFlags[i] & 3) | (dyn ? 4 : 0);
 }
 
 static int ensureStage(pb_ctx* ctx, size_t bytes) {
@@ -157,7 +174,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
     A(sceneBounds, 32);
     A(nodeLeft, C); A(nodeRight, C); A(nodeParent, C); A(leafParent, C); A(nodeFlag, C); A(nodeMin, 2 * C); A(nodeMax, 2 * C);
-    A(pairs, P); A(pairOrder, 2 * P);
+    A(pairs, P); A(pairOrder, 2 * P); A(trigPairs, P); A(colClass, C);
     A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
     A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
     const size_t PT = 4 * M;
@@ -190,7 +207,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
-    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding);
+    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
@@ -211,6 +228,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
     int rows = nDyn + nStatic;
     if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
     ctx->nDyn = nDyn; ctx->nStatic = nStatic; ctx->nRows = rows;
+    ctx->hRowEntity.assign(entity, entity + rows);
     int rc;
     if ((rc = uploadRaw(ctx, entity, rows, ctx->rowEntity))) return rc;
     if ((rc = uploadVec(ctx, pos3, rows, 3, ctx->pos))) return rc;
@@ -239,6 +257,9 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
     if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
     ctx->nCol = n;
     ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
+    ctx->hColIndex.assign(colIndex, colIndex + n);
+    // a custom filter table is indexed by collider: it has to be set again after every collider upload
+    if (ctx->filterLut) { cudaFree(ctx->filterLut); ctx->filterLut = nullptr; ctx->nFilterClasses = 0; }
     // device flags: bit0 trigger, bit1 enableSimulation, bit2 owner is a non-kinematic dynamic body (BroadPhaseEntry::isDynamic)
     std::vector<int> kin(ctx->nDyn);
     if (ctx->nDyn) PB_CUDA(ctx, cudaMemcpy(kin.data(), ctx->kinematic, sizeof(int) * ctx->nDyn, cudaMemcpyDeviceToHost));
@@ -255,7 +276,8 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
         if (type[i] == PB_CONVEX_MESH && (mesh[i] < 0 || mesh[i] >= (int)ctx->convexes.size())) return pb_fail(ctx, PB_EINVAL, "bad convex handle");
         mat4[4 * i] = material3[3 * i]; mat4[4 * i + 1] = material3[3 * i + 1]; mat4[4 * i + 2] = material3[3 * i + 2]; mat4[4 * i + 3] = 0.f;
     }
-    ctx->triggersPresent = trig;
+    ctx->anyTriggerFlag = trig;
+    if (!ctx->filterLut) ctx->triggersPossible = trig;
     int rc;
     if ((rc = uploadRaw(ctx, bodyRow, n, ctx->colRow))) return rc;
     if ((rc = uploadRaw(ctx, colIndex, n, ctx->colIndex))) return rc;
@@ -388,6 +410,11 @@ int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* row0, const
     return pb_joints_upload(ctx, n, type, row0, row1, a0p, a0q, a1p, a1q, params8, color);
 }
 
+int pb_update_joint_params(pb_ctx* ctx, int n, const float* params8) {
+    cudaSetDevice(ctx->device);
+    return pb_joints_update_params(ctx, n, params8);
+}
+
 int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* pairs2) {
     cudaSetDevice(ctx->device);
     std::vector<unsigned long long> keys(n);
@@ -460,7 +487,6 @@ static int readCounters(pb_ctx* ctx) {
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
     cudaSetDevice(ctx->device);
     if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
-    if (ctx->triggersPresent) return pb_fail(ctx, PB_EUNSUPPORTED, "trigger colliders are not implemented on the device path yet");
     int rc;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream));
@@ -517,6 +543,93 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
     if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3, s + 7 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(angvel3, s + 10 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float* quat4) {
+    cudaSetDevice(ctx->device);
+    if (nStatic != ctx->nStatic) return pb_fail(ctx, PB_EINVAL, "pb_set_static_poses: n_static mismatch");
+    if (!nStatic) return PB_OK;
+    size_t n = (size_t)nStatic;
+    int rc = ensureStage(ctx, sizeof(float) * 13 * (size_t)std::max(ctx->nDyn, nStatic)); if (rc) return rc;
+    float* s = ctx->stage;
+    PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int g = pb_grid(nStatic, 256);
+    ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nStatic, s, ctx->pos + ctx->nDyn);
+    ++ctx->launches, k_unpack4<<<g, 256, 0, ctx->stream>>>(nStatic, s + 3 * n, ctx->quat + ctx->nDyn);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return PB_OK;
+    for (int i = 0; i < n; ++i) if (cols[i] < 0 || cols[i] >= ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_bounds: collider out of range");
+    int rc = ensureStage(ctx, sizeof(float) * 7 * (size_t)n); if (rc) return rc;
+    float* s = ctx->stage;
+    PB_CUDA(ctx, cudaMemcpyAsync(s, cols, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + n, bounds6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ++ctx->launches, k_scatter_bounds<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const int*)s, s + n, ctx->aabbMin, ctx->aabbMax);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
+    cudaSetDevice(ctx->device);
+    if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
+    if (!nDyn) return PB_OK;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->kinematic, kinematic, sizeof(int) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->nCol) ++ctx->launches, k_col_dynamic_flag<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colFlags);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_set_mass(pb_ctx* ctx, int nDyn, const float* invMass, const float* com3, const float* invI9) {
+    cudaSetDevice(ctx->device);
+    if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_mass: n_dynamic mismatch");
+    if (!nDyn) return PB_OK;
+    int rc = ensureStage(ctx, sizeof(float) * 13 * (size_t)nDyn); if (rc) return rc;
+    float* s = ctx->stage;
+    PB_CUDA(ctx, cudaMemcpyAsync(s, com3, sizeof(float) * 3 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * (size_t)nDyn, invMass, sizeof(float) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)nDyn, invI9, sizeof(float) * 9 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
+    ++ctx->launches, k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
+    ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_set_contact_filter(pb_ctx* ctx, int nColliders, const int* colliderClass, int nClasses, const unsigned char* lut) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->filterLut) { cudaFree(ctx->filterLut); ctx->filterLut = nullptr; }
+    ctx->nFilterClasses = 0;
+    if (nClasses <= 0 || !lut) { ctx->triggersPossible = ctx->anyTriggerFlag; return PB_OK; }   // defaultContactFilter
+    if (nColliders != ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_contact_filter: collider count mismatch (upload colliders first)");
+    for (int i = 0; i < nColliders; ++i) if (colliderClass[i] < 0 || colliderClass[i] >= nClasses) return pb_fail(ctx, PB_EINVAL, "collider class out of range");
+    int rc = pb_alloc(ctx, &ctx->filterLut, (size_t)nClasses * nClasses); if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpy(ctx->filterLut, lut, (size_t)nClasses * nClasses, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(ctx->colClass, colliderClass, sizeof(int) * nColliders, cudaMemcpyHostToDevice));
+    ctx->nFilterClasses = nClasses;
+    bool any = false;
+    for (size_t i = 0; i < (size_t)nClasses * nClasses; ++i) any |= lut[i] != 0;
+    ctx->triggersPossible = any;
+    return PB_OK;
+}
+
+int pb_get_triggers(pb_ctx* ctx, int* out4, int cap, int* n) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int nt = std::min(ctx->lastCounts.n_triggers, ctx->caps.max_pairs);
+    *n = nt;
+    if (!out4 || nt == 0 || cap == 0) return PB_OK;
+    std::vector<int2> p(nt);
+    PB_CUDA(ctx, cudaMemcpy(p.data(), ctx->trigPairs, sizeof(int2) * nt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nt && i < cap; ++i) {
+        out4[4 * i] = ctx->hRowEntity[ctx->hColRow[p[i].x]]; out4[4 * i + 1] = ctx->hColIndex[p[i].x];
+        out4[4 * i + 2] = ctx->hRowEntity[ctx->hColRow[p[i].y]]; out4[4 * i + 3] = ctx->hColIndex[p[i].y];
+    }
     return PB_OK;
 }
 

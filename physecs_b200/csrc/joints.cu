@@ -196,7 +196,7 @@ __global__ void k_joint_begin(JointDev J, const float4* __restrict__ pos, const 
 }
 
 // per substep and colour: fill rows (makeConstraints), effective masses, NGS pseudo-velocity pass (Constraint1DW.cpp:6-115)
-__global__ void k_joint_prep(JointDev J, int start, int count, const int* __restrict__ kinematic,
+__global__ void k_joint_prep(JointDev J, int start, int count, int doNgs, const int* __restrict__ kinematic,
                              const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ comInvMass,
                              const float4* __restrict__ invIW, float4* __restrict__ pseudoLin, float4* __restrict__ pseudoAng) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,7 +247,7 @@ __global__ void k_joint_prep(JointDev J, int start, int count, const int* __rest
         J.a0tMin[idx] = f4(a0t, R.mn);
         J.a1tMax[idx] = f4(a1t, R.mx);
         J.soft[idx] = make_float2(R.freq, R.damp);
-        if (flags & JF_SOFT) continue;
+        if ((flags & JF_SOFT) || !doNgs) continue;
         if (R.c != 0.f && k != 0.f) {            // NGS correction, masked per lane (quirk Q10)
             float lambda = R.c / k;
             if (flags & JF_LIMITED) lambda = fminf(fmaxf(lambda, R.mn), R.mx);
@@ -257,8 +257,127 @@ __global__ void k_joint_prep(JointDev J, int start, int count, const int* __rest
             if (b1 >= 0) ++cnt1;
         }
     }
+    if (!doNgs) return;
     if (b0 >= 0) { pseudoLin[b0] = make_float4(pv0.x, pv0.y, pv0.z, __int_as_float(cnt0)); pseudoAng[b0] = f4(pw0); }
     if (b1 >= 0) { pseudoLin[b1] = make_float4(pv1.x, pv1.y, pv1.z, __int_as_float(cnt1)); pseudoAng[b1] = f4(pw1); }
+}
+
+// ---- overflow bucket (joint colour index 8): the reference's scalar, strictly sequential path ----------------------------
+// Joints of the bucket may share bodies, so rows are visited exactly in the reference's order: flag list by flag list
+// (NONE, ANGULAR, SOFT, LIMITED, ANGULAR|SOFT, ANGULAR|LIMITED -- Constraint1DContainer.h:117), joints in creation
+// order inside a list, rows in creation order inside a joint.  Arithmetic is Constraint1D.cpp's, which differs from the
+// SIMD path (quirk Q9): the warm start only perturbs the local velocity copy, LIMITED clamps to [min, max] without the
+// time step, a row with invEffMass == 0 is skipped before the warm start, and the soft / bias terms divide by invEffMass.
+__device__ __forceinline__ int flagList(int flags) {
+    switch (flags) { case 0: return 0; case JF_ANGULAR: return 1; case JF_SOFT: return 2; case JF_LIMITED: return 3;
+                     case JF_ANGULAR | JF_SOFT: return 4; default: return 5; }
+}
+
+// preSolve NGS pass of the bucket (Constraint1D.cpp:31-51); rows were filled by k_joint_prep(doNgs = 0)
+__global__ void k_joint_ngs_seq(JointDev J, int start, int count, const int* __restrict__ kinematic, const float4* __restrict__ comInvMass,
+                                float4* __restrict__ pseudoLin, float4* __restrict__ pseudoAng) {
+    if (blockIdx.x || threadIdx.x) return;
+    for (int list = 0; list < 6; ++list) {
+        if (list == 2 || list == 4) continue;   // SOFT lists return before the correction
+        for (int j = start; j < start + count; ++j) {
+            int type = J.type[j];
+            float4 prm0 = J.prm[2 * j], st0 = J.state[2 * j];
+            int n = jointRowCount(type, prm0, st0);
+            int2 rr = J.rows[j];
+            int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+            float im0 = b0 >= 0 ? comInvMass[b0].w : 0.f, im1 = b1 >= 0 ? comInvMass[b1].w : 0.f;
+            for (int r = 0; r < n; ++r) {
+                int flags = jointRowFlags(type, r, prm0, st0);
+                if (flagList(flags) != list) continue;
+                int idx = r * J.n + j;
+                float4 LC = J.linC[idx], A1 = J.a1K[idx], A0t = J.a0tMin[idx], A1t = J.a1tMax[idx];
+                float c = LC.w, k = A1.w;
+                if (c == 0.f || k == 0.f) continue;
+                float lambda = c / k;
+                if (flags & JF_LIMITED) lambda = gclamp(lambda, A0t.w, A1t.w);
+                V3 lin = mk3(LC);
+                if (b0 >= 0) {
+                    float4 l = pseudoLin[b0]; V3 pv = mk3(l); int cnt = __float_as_int(l.w);
+                    if (!(flags & JF_ANGULAR)) pv += lambda * (im0 * lin);
+                    pseudoLin[b0] = make_float4(pv.x, pv.y, pv.z, __int_as_float(cnt + 1));
+                    pseudoAng[b0] = f4(mk3(pseudoAng[b0]) + lambda * mk3(A0t));
+                }
+                if (b1 >= 0) {
+                    float4 l = pseudoLin[b1]; V3 pv = mk3(l); int cnt = __float_as_int(l.w);
+                    if (!(flags & JF_ANGULAR)) pv -= lambda * (im1 * lin);
+                    pseudoLin[b1] = make_float4(pv.x, pv.y, pv.z, __int_as_float(cnt + 1));
+                    pseudoAng[b1] = f4(mk3(pseudoAng[b1]) - lambda * mk3(A1t));
+                }
+            }
+        }
+    }
+}
+
+// solve pass of the bucket (Constraint1D.cpp:55-127)
+__global__ void k_joint_solve_seq(JointDev J, int start, int count, float h, int warmStart, const int* __restrict__ kinematic,
+                                  const float4* __restrict__ comInvMass, float4* __restrict__ velLive, float4* __restrict__ angvelLive) {
+    if (blockIdx.x || threadIdx.x) return;
+    for (int list = 0; list < 6; ++list) {
+        for (int j = start; j < start + count; ++j) {
+            int type = J.type[j];
+            float4 prm0 = J.prm[2 * j], st0 = J.state[2 * j];
+            int n = jointRowCount(type, prm0, st0);
+            int2 rr = J.rows[j];
+            int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+            float im0 = b0 >= 0 ? comInvMass[b0].w : 0.f, im1 = b1 >= 0 ? comInvMass[b1].w : 0.f;
+            for (int r = 0; r < n; ++r) {
+                int flags = jointRowFlags(type, r, prm0, st0);
+                if (flagList(flags) != list) continue;
+                int idx = r * J.n + j;
+                float4 LC = J.linC[idx], A0 = J.a0T[idx], A1 = J.a1K[idx], A0t = J.a0tMin[idx], A1t = J.a1tMax[idx];
+                float c = LC.w, k = A1.w;
+                if (k == 0.f) continue;
+                V3 lin = mk3(LC), a0 = mk3(A0), a1 = mk3(A1), a0t = mk3(A0t), a1t = mk3(A1t);
+                V3 l0t = im0 * lin, l1t = im1 * lin;
+                const bool ang = (flags & JF_ANGULAR) != 0;
+                V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
+                if (b0 >= 0) { if (!ang) v0 = mk3(velLive[b0]); w0 = mk3(angvelLive[b0]); }
+                if (b1 >= 0) { if (!ang) v1 = mk3(velLive[b1]); w1 = mk3(angvelLive[b1]); }
+                float total = J.lambda[idx];
+                if (!(flags & JF_SOFT)) {
+                    if (warmStart && !((double)fabsf(c) > 1e-4 || fabsf(total) > 10000.f)) {
+                        total = total * 0.5f;
+                        if (b0 >= 0) { if (!ang) v0 += total * l0t; w0 += total * a0t; }
+                        if (b1 >= 0) { if (!ang) v1 -= total * l1t; w1 -= total * a1t; }
+                    }
+                }
+                float rel = dot(a1, w1) - dot(a0, w0);
+                if (!ang) rel += dot(lin, v1) - dot(lin, v0);
+                float lambda;
+                if (flags & JF_SOFT) {
+                    float2 sf = J.soft[idx];
+                    float af = 2.f * 3.14159265358979323846f * sf.x;
+                    float stiffness = af * af / k;
+                    float damping = 2.f * af * sf.y / k;
+                    float gamma = 1.f / (damping + h * stiffness);
+                    float beta = h * stiffness / (damping + h * stiffness);
+                    lambda = (rel + beta * c / h) / (k + gamma / h);
+                } else {
+                    lambda = (rel - A0.w + 0.2f * c / h) / k;
+                }
+                if (flags & JF_LIMITED) {
+                    float prev = total;
+                    total += lambda;
+                    total = gclamp(total, A0t.w, A1t.w);
+                    lambda = total - prev;
+                } else total += lambda;
+                J.lambda[idx] = total;
+                if (b0 >= 0) {
+                    if (!ang) velLive[b0] = f4(mk3(velLive[b0]) + lambda * l0t);
+                    angvelLive[b0] = f4(mk3(angvelLive[b0]) + lambda * a0t);
+                }
+                if (b1 >= 0) {
+                    if (!ang) velLive[b1] = f4(mk3(velLive[b1]) - lambda * l1t);
+                    angvelLive[b1] = f4(mk3(angvelLive[b1]) - lambda * a1t);
+                }
+            }
+        }
+    }
 }
 
 // per iteration and colour (Constraint1DW.cpp:118-233)
@@ -364,7 +483,6 @@ int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const
     if (n == 0) return PB_OK;
     for (int j = 0; j < n; ++j) {
         if (color[j] < 0 || color[j] > 8) return pb_fail(ctx, PB_EINVAL, "joint colour out of range");
-        if (color[j] == 8) return pb_fail(ctx, PB_EUNSUPPORTED, "joint graph needs more than 8 colours (the reference's sequential overflow bucket is not on the device path)");
         if (type[j] < 0 || type[j] > PB_JOINT_SERVO) return pb_fail(ctx, PB_EINVAL, "joint type");
     }
     JointStore* s = new JointStore();
@@ -409,6 +527,22 @@ int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const
     return PB_OK;
 }
 
+// setters called on live joints (RevoluteJoint::setDriveVelocity, ServoJoint::setTargetAngle, ...): new params in the
+// caller's joint order; persistent joint state (gear angles, accumulated impulses) is kept
+int pb_joints_update_params(pb_ctx* ctx, int n, const float* params8) {
+    JointStore* s = store(ctx);
+    if (!s || n != s->n) return pb_fail(ctx, PB_EINVAL, "pb_update_joint_params: joint count mismatch");
+    std::vector<float4> prm(2 * (size_t)n);
+    for (int k = 0; k < n; ++k) {
+        const float* P = params8 + 8 * (size_t)s->order[k];
+        prm[2 * k] = make_float4(P[0], P[1], P[2], P[3]);
+        prm[2 * k + 1] = make_float4(P[4], P[5], P[6], P[7]);
+    }
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaMemcpy(s->prm, prm.data(), sizeof(float4) * 2 * n, cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
 int pb_joint_begin_step(pb_ctx* ctx) {
     if (!ctx->nJoints) return PB_OK;
     JointDev J = devView(ctx);
@@ -423,8 +557,16 @@ int pb_joint_prep(pb_ctx* ctx, float h) {
     for (int c = 0; c < 8; ++c) {
         int start = ctx->jointColorStart[c], count = ctx->jointColorStart[c + 1] - start;
         if (count <= 0) continue;
-        ++ctx->launches, k_joint_prep<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(J, start, count, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
+        ++ctx->launches, k_joint_prep<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(J, start, count, 1, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
                                                                                      ctx->invIW, ctx->pseudoLin, ctx->pseudoAng);
+    }
+    {   // overflow bucket: parallel row fill, sequential NGS pass
+        int start = ctx->jointColorStart[8], count = ctx->jointColorStart[9] - start;
+        if (count > 0) {
+            ++ctx->launches, k_joint_prep<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(J, start, count, 0, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
+                                                                                         ctx->invIW, ctx->pseudoLin, ctx->pseudoAng);
+            ++ctx->launches, k_joint_ngs_seq<<<1, 32, 0, ctx->stream>>>(J, start, count, ctx->kinematic, ctx->comInvMass, ctx->pseudoLin, ctx->pseudoAng);
+        }
     }
     pb_prof_end(ctx);
     PB_CUDA(ctx, cudaGetLastError());
@@ -439,6 +581,11 @@ int pb_joint_solve(pb_ctx* ctx, float h, int warmStart) {
         if (count <= 0) continue;
         ++ctx->launches, k_joint_solve<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(J, start, count, h, warmStart, ctx->kinematic, ctx->comInvMass,
                                                                                       ctx->velLive, ctx->angvelLive);
+    }
+    {
+        int start = ctx->jointColorStart[8], count = ctx->jointColorStart[9] - start;
+        if (count > 0)
+            ++ctx->launches, k_joint_solve_seq<<<1, 32, 0, ctx->stream>>>(J, start, count, h, warmStart, ctx->kinematic, ctx->comInvMass, ctx->velLive, ctx->angvelLive);
     }
     pb_prof_end(ctx);
     PB_CUDA(ctx, cudaGetLastError());

@@ -14,12 +14,13 @@
 #include "np_mesh.cuh"
 #include "np_gjk.cuh"
 #include "np_mesh_heavy.cuh"
+#include "np_overlap.cuh"
 
 #define COLF_TRIGGER 1
 #define COLF_ENABLE 2
 #define COLF_DYNAMIC 4
 
-enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_MESHH, BIN_COUNT };
+enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_MESHH, BIN_TRIGGER, BIN_COUNT };
 
 __device__ __forceinline__ int binOf(int t0, int t1) {
     if (t0 == PB_TRIANGLE_MESH || t1 == PB_TRIANGLE_MESH) {
@@ -47,29 +48,33 @@ __device__ __forceinline__ bool isNonColliding(const unsigned long long* __restr
 
 __global__ void k_pair_classify(const int2* __restrict__ pairs, int* __restrict__ pairBin, int* __restrict__ counters, int maxPairs,
                                 const int* __restrict__ colType, const int* __restrict__ colFlags, const int* __restrict__ colRow,
-                                const int* __restrict__ rowEntity, const unsigned long long* __restrict__ nonColl, int nNonColl) {
-    __shared__ int sh[BIN_COUNT + 1];
-    if (threadIdx.x <= BIN_COUNT) sh[threadIdx.x] = 0;
+                                const int* __restrict__ rowEntity, const unsigned long long* __restrict__ nonColl, int nNonColl,
+                                const int* __restrict__ colClass, const unsigned char* __restrict__ filterLut, int nClasses) {
+    __shared__ int sh[BIN_COUNT];
+    if (threadIdx.x < BIN_COUNT) sh[threadIdx.x] = 0;
     __syncthreads();
     int n = min(counters[CNT_PAIRS], maxPairs);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int2 p = pairs[i];
         int bin;
-        int f0 = colFlags[p.x], f1 = colFlags[p.y];
-        if ((f0 | f1) & COLF_TRIGGER) { bin = -2; atomicAdd(&sh[BIN_COUNT], 1); }   // defaultContactFilter (Physecs.cpp:20-23)
+        // contactFilter(col0.isTrigger, col0.data, col1.isTrigger, col1.data) (Physecs.cpp:200): the default filter
+        // (Physecs.cpp:20-23) reads the trigger flags; a custom one is tabulated per (isTrigger, data) class on the host
+        bool trigger;
+        if (filterLut) trigger = filterLut[colClass[p.x] * nClasses + colClass[p.y]] != 0;
+        else trigger = ((colFlags[p.x] | colFlags[p.y]) & COLF_TRIGGER) != 0;
+        if (trigger) bin = BIN_TRIGGER;
         else {
             bin = binOf(colType[p.x], colType[p.y]);
             if (bin >= 0 && nNonColl) {
                 unsigned long long k = ((unsigned long long)(unsigned int)rowEntity[colRow[p.x]] << 32) | (unsigned int)rowEntity[colRow[p.y]];
                 if (isNonColliding(nonColl, nNonColl, k)) bin = -1;
             }
-            if (bin >= 0) atomicAdd(&sh[bin], 1);
         }
+        if (bin >= 0) atomicAdd(&sh[bin], 1);
         pairBin[i] = bin;
     }
     __syncthreads();
     if (threadIdx.x < BIN_COUNT && sh[threadIdx.x]) atomicAdd(&counters[CNT_BIN0 + threadIdx.x], sh[threadIdx.x]);
-    if (threadIdx.x == BIN_COUNT && sh[BIN_COUNT]) atomicAdd(&counters[CNT_TRIGGERS], sh[BIN_COUNT]);
 }
 
 __global__ void k_bin_starts(int* counters) {
@@ -77,7 +82,7 @@ __global__ void k_bin_starts(int* counters) {
         int run = 0;
         for (int b = 0; b < BIN_COUNT; ++b) { counters[CNT_BINSTART + b] = run; run += counters[CNT_BIN0 + b]; counters[CNT_BIN0 + b] = 0; }
         counters[CNT_BINSTART + BIN_COUNT] = run;
-        counters[CNT_MESH_PAIRS] = run - counters[CNT_BINSTART + BIN_MESH];
+        counters[CNT_MESH_PAIRS] = counters[CNT_BINSTART + BIN_TRIGGER] - counters[CNT_BINSTART + BIN_MESH];
     }
 }
 
@@ -328,12 +333,39 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
     }
 }
 
+// ---- trigger pairs (Physecs.cpp:200-207) --------------------------------------------------------------------------------
+// One thread per TRIGGER-classified pair: physecs::overlap on the world collider poses; overlapping pairs are appended
+// (collider indices, side 0 = lower entity) for the enter / exit diff the host runs after the step (Physecs.cpp:538-552).
+__global__ void __launch_bounds__(128) k_np_trigger(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                    const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
+                                                    const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                    const PbConvexDev* __restrict__ convexes, int2* __restrict__ trigPairs, int maxTrig) {
+    int start = counters[CNT_BINSTART + BIN_TRIGGER], end = counters[CNT_BINSTART + BIN_TRIGGER + 1];
+    int lane = threadIdx.x & 31;
+    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+        int idx = base + lane;
+        bool hit = false;
+        int2 p = make_int2(0, 0);
+        if (idx < end) {
+            p = pairs[pairOrder[idx]];
+            hit = overlapShapes(colType[p.x], colParams[p.x], mk3(wpos[p.x]), mkq(wquat[p.x]), colMesh[p.x],
+                                colType[p.y], colParams[p.y], mk3(wpos[p.y]), mkq(wquat[p.y]), colMesh[p.y], convexes);
+        }
+        int slot = warpReserve(hit ? 1 : 0, &counters[CNT_TRIGGERS]);
+        if (hit) {
+            if (slot < maxTrig) trigPairs[slot] = p;
+            else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+        }
+    }
+}
+
 int pb_narrowphase(pb_ctx* ctx) {
     if (ctx->nCol < 2) return PB_OK;
     int blocks = ctx->numSMs * 8;
     int* pairBin = ctx->pairOrder + ctx->caps.max_pairs;   // second half of the pairOrder allocation
     ++ctx->launches, k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
-                                                      ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding);
+                                                      ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding,
+                                                      ctx->colClass, ctx->filterLut, ctx->nFilterClasses);
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
     ++ctx->launches, k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
@@ -348,6 +380,9 @@ int pb_narrowphase(pb_ctx* ctx) {
     if (!ctx->triMeshes.empty())
         ++ctx->launches, k_np_mesh<false><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                    ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
+    if (ctx->triggersPossible)
+        ++ctx->launches, k_np_trigger<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+                                                    ctx->colWQuat, ctx->convexDev, ctx->trigPairs, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

@@ -90,7 +90,7 @@ struct pb_ctx {
     float4* colLPos = nullptr; float4* colLQuat = nullptr; float4* colParams = nullptr; float4* colMat = nullptr;
     float4* colWPos = nullptr; float4* colWQuat = nullptr;   // world pose, refreshed each step
     float4* aabbMin = nullptr; float4* aabbMax = nullptr;     // persistent bounds (BroadPhaseEntry::bounds)
-    std::vector<int> hColType, hColMesh, hColRow;   // host mirrors (trimesh colliders are found on the host)
+    std::vector<int> hColType, hColMesh, hColRow, hColIndex, hRowEntity;   // host mirrors (trimesh colliders are found on the host)
     int* rowMark = nullptr;          // [rows] scratch marks for pb_move_rows
 
     // ---- meshes ------------------------------------------------------------------------------------
@@ -152,7 +152,10 @@ struct pb_ctx {
     pb_counts lastCounts{};
     pb_timings lastTimings{};
     cudaEvent_t ev[6] = {nullptr};
-    bool triggersPresent = false;
+    // contact filter (Physecs.cpp:200): optional K x K table over (isTrigger, data) classes; nullptr = defaultContactFilter
+    int* colClass = nullptr; unsigned char* filterLut = nullptr; int nFilterClasses = 0;
+    bool anyTriggerFlag = false, triggersPossible = false;
+    int2* trigPairs = nullptr;       // [maxPairs] overlapping TRIGGER pairs of the last step (collider indices)
     unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
     // optional per-stage event profiling (pb_set_profile): events recorded around stage groups, summed lazily
     bool profile = false;

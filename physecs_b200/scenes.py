@@ -718,3 +718,90 @@ def convex_pile(n_bodies=250_000, seed=0xC3, substeps=4, iterations=2, spacing=1
     d.inv_inertia[cm, 0] = f32(1) / (mm * (hy * hy + hz * hz) * f32(4)); d.inv_inertia[cm, 4] = f32(1) / (mm * (hx * hx + hz * hz) * f32(4))
     d.inv_inertia[cm, 8] = f32(1) / (mm * (hx * hx + hy * hy) * f32(4))
     return d
+
+
+# ---- joint overflow bucket, gears, triggers -------------------------------------------------------------------------------------
+def joint_star(arms=12, seed=7) -> SceneDesc:
+    """A hub with `arms` two-link arms jointed to it: the hub's 8 colour bits run out, so arms 9.. land in the reference's
+    sequential overflow bucket (Physecs.cpp:701-704, quirk Q21) and are solved with the scalar Constraint1D semantics.
+    Arm types cycle through spherical / revolute / prismatic(limit) / servo / fixed so every flag list appears in the bucket."""
+    b = SceneBuilder("joint_star")
+    b.add_body((0, -0.5, 0), colliders=[dict(type=BOX, params=(20.0, 0.5, 20.0))], dynamic=False)
+    hub_pos = np.array([0.0, 2.0, 0.0])
+    post = b.add_body((0, 3.0, 0), colliders=[dict(type=BOX, params=(0.1, 0.1, 0.1))], dynamic=False)
+    hub = b.add_body(tuple(hub_pos), colliders=[dict(type=SPHERE, params=(0.3,))], mass=5.0)
+    b.add_joint(J_SPHERICAL, post, (0, -0.5, 0), IDQ, hub, (0, 0.5, 0), IDQ)
+    kinds = [(J_SPHERICAL, ()), (J_REVOLUTE, ()), (J_PRISMATIC, (0.1, -0.1, 0.0, 0.0, 5.0, 1.0)), (J_SERVO, (0.3, 30.0, 1.0)), (J_FIXED, ()),
+             (J_REVOLUTE, (1.0, 1.5, 4.0)), (J_PRISMATIC, (0.3, -0.3, 1.0, 0.05, 5.0, 1.0)), (J_UNIVERSAL, ())]
+    for a in range(arms):
+        ang = 2 * math.pi * a / arms
+        dirv = np.array([math.cos(ang), -0.1 * (a % 3), math.sin(ang)])
+        p1 = hub_pos + 0.7 * dirv
+        p2 = hub_pos + 1.3 * dirv
+        e1 = b.add_body(tuple(p1), colliders=[dict(type=CAPSULE, params=(0.12, 0.05))], mass=1.0)
+        e2 = b.add_body(tuple(p2), colliders=[dict(type=BOX, params=(0.08, 0.06, 0.1))], mass=0.5 + 0.1 * a)
+        jt, prm = kinds[a % len(kinds)]
+        q1 = axis_angle((1, 0, 0), math.pi / 2) if jt == J_UNIVERSAL else IDQ
+        mid = hub_pos + 0.35 * dirv
+        b.add_joint(jt, hub, mid - hub_pos, IDQ, e1, mid - p1, q1, prm)
+        mid2 = (p1 + p2) / 2
+        b.add_joint(J_SPHERICAL if a % 2 else J_REVOLUTE, e1, mid2 - p1, IDQ, e2, mid2 - p2, IDQ)
+    return b.build(substeps=4, iterations=2)
+
+
+def gear_train(pairs=3) -> SceneDesc:
+    """Pairs of wheels on revolute axles (axis = anchor-frame x) coupled by a GearJoint (GearJoint.cpp:10-50); one wheel of each
+    pair is driven by its revolute motor, the other has to follow with the gear ratio."""
+    b = SceneBuilder("gear_train")
+    b.add_body((0, -0.5, 0), colliders=[dict(type=BOX, params=(20.0, 0.5, 20.0))], dynamic=False)
+    for k in range(pairs):
+        z = 2.0 * k
+        frame = b.add_body((0, 2.0, z), colliders=[dict(type=BOX, params=(0.05, 0.05, 0.05))], dynamic=False)
+        r0, r1 = 0.4, 0.2 + 0.1 * k
+        w0 = b.add_body((0.0, 2.0, z), colliders=[dict(type=BOX, params=(0.05, r0, r0))], mass=2.0, angvel=(0.5, 0, 0))
+        w1 = b.add_body((0.0, 2.0 + r0 + r1, z), colliders=[dict(type=BOX, params=(0.05, r1, r1))], mass=1.0)
+        b.add_joint(J_REVOLUTE, frame, (0, 0, 0), IDQ, w0, (0, 0, 0), IDQ, (1.0, 1.0 + k, 10.0))
+        b.add_joint(J_REVOLUTE, frame, (0, r0 + r1, 0), IDQ, w1, (0, 0, 0), IDQ)
+        b.add_joint(J_GEAR, w0, (0, 0, 0), IDQ, w1, (0, 0, 0), IDQ, (r0 / r1,))
+        b.no_collide.append((w0, w1))
+    return b.build(substeps=4, iterations=2)
+
+
+def trigger_zoo(n=160, seed=0x7216) -> SceneDesc:
+    """Trigger volumes of every geometry kind (static and carried by dynamic bodies) swept by falling bodies of every kind:
+    exercises physecs::overlap (Overlap.cpp) for all shape pairs, incl. the GJK boolean path for convex meshes."""
+    rng = SplitMix(seed)
+    b = SceneBuilder("trigger_zoo")
+    meshes = convex_templates()
+    for m in meshes:
+        b.add_convex(m)
+    b.add_body((0, -0.5, 0), colliders=[dict(type=BOX, params=(30.0, 0.5, 30.0))], dynamic=False)
+    u = rng.uniform(16 * n, 0.0, 1.0)
+    qs = rng.unit_quat(2 * n)
+    k = 0
+
+    def shape(t, s):
+        if t == SPHERE: return dict(type=SPHERE, params=(0.25 * s,))
+        if t == CAPSULE: return dict(type=CAPSULE, params=(0.25 * s, 0.15 * s))
+        if t == BOX: return dict(type=BOX, params=(0.2 * s, 0.25 * s, 0.15 * s))
+        return dict(type=CONVEX_MESH, params=(0.35 * s, 0.3 * s, 0.4 * s), mesh=int(s * 97) % len(meshes))
+
+    side = int(math.ceil(math.sqrt(n)))
+    for i in range(n):
+        x, z = (i % side - side / 2) * 1.1, (i // side - side / 2) * 1.1
+        # a static trigger volume near the ground, type cycles through all four kinds
+        zone = shape(i % 4, 1.6 + 0.8 * u[k]); k += 1
+        zone["flags"] = COL_ENABLE_SIM | COL_TRIGGER
+        zone["data"] = i % 3
+        b.add_body((x + 0.2 * (u[k] - 0.5), 0.6, z + 0.2 * (u[k + 1] - 0.5)), quat=tuple(qs[2 * i]), colliders=[zone], dynamic=False); k += 2
+        # a dynamic body falling through it; every 5th carries its own trigger collider next to the solid one
+        solid = shape((i // 4) % 4, 0.8 + 0.6 * u[k]); k += 1
+        solid["data"] = i % 2
+        cols = [solid]
+        if i % 5 == 0:
+            halo = shape((i // 5) % 4, 2.0)
+            halo["flags"] = COL_ENABLE_SIM | COL_TRIGGER
+            halo["lpos"] = (0.1, 0.0, 0.0)
+            cols.append(halo)
+        b.add_body((x, 1.6 + 1.2 * u[k], z), quat=tuple(qs[2 * i + 1]), colliders=cols, mass=1.0, vel=(0.5 * (u[k + 1] - 0.5), 0, 0.5 * (u[k + 2] - 0.5))); k += 3
+    return b.build(substeps=4, iterations=2)

@@ -103,14 +103,33 @@ def one_step_solve(ctx, ref, tol=TOL):
     return matched, errs
 
 
-def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=False):
+# custom contact filters: the same predicates as filterParity / filterAsymmetric in oracle/ref_harness.cpp
+FILTERS = {
+    0: None,
+    1: lambda t0, d0, t1, d1: (t0 or t1) and (d0 + d1) % 2 == 0,
+    2: lambda t0, d0, t1, d1: (t0 and not t1) or (t1 and d0 == 1),
+}
+
+
+def compare_triggers(gpu_trig, ref_trig):
+    g, r = pair_set(gpu_trig), pair_set(ref_trig)
+    assert len(g) == len(gpu_trig), "device emitted duplicate trigger pairs"
+    assert g == r, f"trigger pair sets differ: missing={sorted(r - g)[:5]} extra={sorted(g - r)[:5]} ({len(r - g)}/{len(g - r)} of {len(r)})"
+    return len(g)
+
+
+def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=False, contact_filter=0):
     """All three gates on `steps` consecutive steps, teacher-forced from the oracle's trajectory.
     Returns a summary dict.  Needs a CUDA device (device path) and oracle/_ref (checker)."""
     from oracle.ref import RefScene
     from physecs_b200.capi import Context
     ref = RefScene(desc, ref_threads, hashfix=True)
     ctx = Context(desc)
-    summary = dict(steps=0, pairs=0, manifolds=0, worst_manifold=0.0, worst_solve={})
+    summary = dict(steps=0, pairs=0, manifolds=0, worst_manifold=0.0, worst_solve={}, triggers=0, trigger_changes=0)
+    prev_trig = set()
+    if contact_filter:
+        ref.set_contact_filter(contact_filter)
+        ctx.set_contact_filter(FILTERS[contact_filter])
     try:
         compare_bounds(ctx, ref)
         for k in range(steps):
@@ -130,6 +149,11 @@ def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=Fal
             matched, missing, extra = ref.order_stats()
             assert missing == 0 and extra == 0, f"step {k}: manifold sets differ: matched={matched} missing={missing} extra={extra}"
             npairs = compare_pairs(gp, ref.pairs())
+            gt = ctx.triggers()
+            summary["triggers"] = max(summary["triggers"], compare_triggers(gt, ref.triggers()))
+            cur_trig = pair_set(gt)
+            summary["trigger_changes"] += len(cur_trig ^ prev_trig)
+            prev_trig = cur_trig
             P, Q, V, W = ctx.get_state_entities()
             p, q, v, w = ref.get_state()
             s = np.sign(np.sum(Q * q, axis=1, keepdims=True)); s[s == 0] = 1

@@ -23,3 +23,30 @@ def test_three_gates(maker, steps, need_contacts):
     assert s["steps"] == steps
     assert s["manifolds"] > 0 or not need_contacts, "scene produced no contacts: the test checks nothing"
     assert s["worst_manifold"] <= parity.TOL
+
+
+def test_joint_overflow_bucket():
+    """More than 8 joints on one body: the 9th.. land in the reference's sequential overflow bucket (scalar Constraint1D
+    semantics, quirk Q9); the device solves that bucket sequentially with the same arithmetic."""
+    from physecs_b200.joint_colors import color_joints
+    d = S.joint_star(12)
+    colors = color_joints([(j[1], j[4]) for j in d.joints])
+    assert (colors == 8).sum() >= 4
+    s = parity.run_gates(d, steps=60)
+    assert s["steps"] == 60
+
+
+def test_gear_joint():
+    """GearJoint (persistent angle state across steps; atan2f / fmodf -> 1e-4 gate)."""
+    s = parity.run_gates(S.gear_train(3), steps=60)
+    assert s["steps"] == 60
+
+
+@pytest.mark.parametrize("contact_filter", [0, 1, 2])
+def test_trigger_pairs(contact_filter):
+    """physecs::overlap on TRIGGER pairs (every shape combination) + the three gates on the colliding rest; custom contact
+    filters (Scene::setContactFilter) go through the tabulated (isTrigger, data) class table."""
+    s = parity.run_gates(S.trigger_zoo(160), steps=70, contact_filter=contact_filter)
+    assert s["steps"] == 70
+    assert s["triggers"] > 20, "no overlapping trigger pairs: the test checks nothing"
+    assert s["trigger_changes"] > 40, "trigger sets never changed: enter / exit not exercised"
