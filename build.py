@@ -73,5 +73,48 @@ def build(verbose=False, force=False):
     return lib
 
 
+HOST_SRC = ["Scene.cpp", "Meshes.cpp", "MassUtil.cpp", "scene_harness.cpp"]
+
+
+def find_ecs_includes():
+    """EnTT / GLM are the APPLICATION's dependencies (header-only); they are not vendored in this repo.  Looked up in
+    PHYSECS_ENTT_INCLUDE / PHYSECS_GLM_INCLUDE, else in the reference tree's vendor/ directory when it is present."""
+    entt = os.environ.get("PHYSECS_ENTT_INCLUDE")
+    glm = os.environ.get("PHYSECS_GLM_INCLUDE")
+    ref = os.environ.get("PHYSECS_REFERENCE", "/root/reference")
+    if not entt:
+        cand = os.path.join(ref, "vendor", "entt-3.12.2", "single_include", "entt")
+        entt = cand if os.path.exists(os.path.join(cand, "entt.hpp")) else None
+    if not glm:
+        cand = os.path.join(ref, "vendor", "glm 0.9.9.8")
+        glm = cand if os.path.exists(os.path.join(cand, "glm", "glm.hpp")) else None
+    return entt, glm
+
+
+def build_host(verbose=False, force=False):
+    """libphysecs_b200_scene.so: the host C++ layer (physecs::Scene over entt::registry) + the flat test harness.
+    Returns the path, or None when EnTT / GLM headers are not available (the prebuilt library, if any, is kept)."""
+    lib = os.path.join(OUT, "libphysecs_b200_scene.so")
+    entt, glm = find_ecs_includes()
+    if not entt or not glm:
+        return lib if os.path.exists(lib) else None
+    host = os.path.join(ROOT, "physecs_b200", "host")
+    inc = os.path.join(ROOT, "include")
+    srcs = [os.path.join(host, f) for f in HOST_SRC]
+    deps = srcs + [os.path.join(dp, f) for dp, _, fns in os.walk(os.path.join(inc, "Physecs")) for f in fns] + [os.path.join(inc, "physecs_b200.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DGLM_FORCE_INLINE", "-I", os.path.join(inc, "Physecs"),
+           "-I", os.path.join(inc, "Physecs", "Joints"), "-I", inc, "-I", glm, "-I", entt] + srcs + \
+          ["-o", lib, "-L", OUT, "-lphysecs_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if verbose and r.stdout:
+        print(r.stdout.decode())
+    if r.returncode:
+        raise RuntimeError("host layer build failed:\n" + r.stdout.decode()[-8000:])
+    return lib
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_host(verbose="-v" in sys.argv, force="-f" in sys.argv))

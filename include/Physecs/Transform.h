@@ -1,0 +1,3 @@
+// Drop-in header name of the reference (include/Physecs/Transform.h); the declarations live in detail/b200_types.hpp.
+#pragma once
+#include "detail/b200_types.hpp"

@@ -70,6 +70,9 @@ typedef struct pb_timings {
 /* ---- context ------------------------------------------------------------------------------------ */
 int  pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out);
 void pb_ctx_destroy(pb_ctx* ctx);
+/* enlarge the per-step arenas of a live context (after pb_step returned PB_ECAPACITY): scene, bounds and the contact
+ * cache of the previous step are kept, so the failed step can be run again */
+int  pb_grow_arenas(pb_ctx* ctx, int max_pairs, int max_manifolds);
 const char* pb_last_error(pb_ctx* ctx);
 int  pb_host_alloc(void** ptr, unsigned long long bytes);   /* pinned host staging */
 void pb_host_free(void* ptr);
@@ -113,8 +116,15 @@ int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* body_row0, 
 /* new parameters of the uploaded joints after a setter call on a live joint (reference Joints/*.cpp setters); same
  * layout and joint order as pb_upload_joints; accumulated impulses and gear angle state are kept */
 int pb_update_joint_params(pb_ctx* ctx, int n, const float* params8);
+/* after a re-upload: old_index[j] = position joint j had in the previous pb_upload_joints call (-1 = new joint);
+ * surviving joints keep their persistent state (GearJoint angle tracking, GearJoint.cpp:32-44) */
+int pb_keep_joint_state(pb_ctx* ctx, int n, const int* old_index);
 /* entity pairs that must not collide (reference nonCollidingPairs, Physecs.cpp:209,:694,:788): rows (e0<e1) */
 int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* entity_pairs2);
+/* after pb_upload_colliders: old_to_new[i] = new index of the collider that was row i before the upload (-1 = removed).
+ * Re-keys the contact cache of the last step (reference contactCache, Physecs.cpp:237, :291-300, :553) so restitution
+ * targets of persisting contacts survive adding / removing bodies, as they do in the reference */
+int pb_keep_contact_cache(pb_ctx* ctx, int n_old, const int* old_to_new);
 /* Contact filter (reference Scene::setContactFilter, Physecs.cpp:200, :795): the user's function
  * ContactType f(bool isTrigger0, int data0, bool isTrigger1, int data1) depends only on the (isTrigger, data) class of
  * each collider, so the host tabulates it: collider_class[n_colliders] in [0, n_classes), lut[c0 * n_classes + c1] = 1

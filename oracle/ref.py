@@ -94,7 +94,7 @@ class RefScene:
         return float(self.lib.ph_simulate(self.h, C.c_float(self.desc.dt if dt is None else dt)))
 
     def get_state(self):
-        n = self.desc.n
+        n = self.lib.ph_num_entities(self.h)
         pos = np.zeros((n, 3), np.float32); quat = np.zeros((n, 4), np.float32)
         vel = np.zeros((n, 3), np.float32); ang = np.zeros((n, 3), np.float32)
         self.lib.ph_get_state(self.h, _p(pos), _p(quat), _p(vel), _p(ang))
@@ -146,6 +146,33 @@ class RefScene:
         keys = keys[:m]
         full = np.concatenate([pr[keys[:, 0]], keys[:, 1:2]], 1) if m else np.zeros((0, 5), np.int32)
         return dict(keys=full, num_points=keys[:, 2].copy(), normal=nrm[:m], points=pts[:m])
+
+    def add_entities(self, d):
+        """Append the entities of another SceneDesc to the live registry (same meshes); returns the first new entity id."""
+        first = self.lib.ph_add_entities(self.h, d.n, _p(_f(d.pos)), _p(_f(d.quat)), _p(_i(d.flags), C.c_int), _p(_f(d.vel)), _p(_f(d.angvel)),
+                                         _p(_f(d.inv_mass)), _p(_f(d.com)), _p(_f(d.inv_inertia)), _p(_i(d.col_offsets), C.c_int), _p(_f(d.col_lpos)),
+                                         _p(_f(d.col_lquat)), _p(_i(d.col_type), C.c_int), _p(_f(d.col_params)), _p(_i(d.col_mesh), C.c_int),
+                                         _p(_f(d.col_material)), _p(_i(d.col_flags), C.c_int), _p(_i(d.col_data), C.c_int))
+        self._extra = getattr(self, "_extra", 0) + d.n
+        return first
+
+    def destroy_entity(self, e):
+        self.lib.ph_destroy_entity(self.h, int(e))
+
+    def add_joint(self, t, e0, a0p, a0q, e1, a1p, a1q, prm):
+        return self.lib.ph_add_joint(self.h, int(t), int(e0), _p(_f(a0p)), _p(_f(a0q)), int(e1), _p(_f(a1p)), _p(_f(a1q)), _p(_f(prm)))
+
+    def destroy_joint(self, j):
+        self.lib.ph_destroy_joint(self.h, int(j))
+
+    def set_revolute_drive(self, j, enabled, velocity, max_torque):
+        self.lib.ph_set_revolute_drive(self.h, int(j), int(enabled), C.c_float(velocity), C.c_float(max_torque))
+
+    def set_kinematic(self, e, kin):
+        self.lib.ph_set_kinematic(self.h, int(e), int(kin))
+
+    def set_can_collide(self, e0, e1, can):
+        self.lib.ph_set_can_collide(self.h, int(e0), int(e1), int(can))
 
     def triggers(self):
         """Overlapping trigger pairs of the last simulate, rows (e0, c0, e1, c1)."""

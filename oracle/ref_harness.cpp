@@ -328,6 +328,7 @@ void ph_get_state(void* hp, float* pos, float* quat, float* vel, float* angvel) 
     auto* h = (Harness*)hp;
     for (size_t i = 0; i < h->entities.size(); ++i) {
         auto e = h->entities[i];
+        if (!h->registry.valid(e)) continue;
         auto& t = h->registry.get<TransformComponent>(e);
         for (int k = 0; k < 3; ++k) pos[3 * i + k] = t.position[k];
         quat[4 * i + 0] = t.orientation.x; quat[4 * i + 1] = t.orientation.y;
@@ -452,6 +453,30 @@ void ph_set_contact_filter(void* hp, int mode) {
     auto* h = (Harness*)hp;
     h->scene->setContactFilter(mode == 1 ? filterParity : mode == 2 ? filterAsymmetric : physecs::defaultContactFilter);
 }
+
+// structural edits through the reference's public API (registry.destroy fires Scene::onRigidBodyDelete / onDynamicDelete)
+void ph_destroy_entity(void* hp, int e) { auto* h = (Harness*)hp; h->registry.destroy(h->entities[e]); }
+void ph_destroy_joint(void* hp, int j) { auto* h = (Harness*)hp; h->scene->destroyJoint(h->joints[j]); h->joints[j] = nullptr; }
+int ph_set_revolute_drive(void* hp, int j, int enabled, float velocity, float maxTorque) {
+    auto* h = (Harness*)hp;
+    auto* r = dynamic_cast<physecs::RevoluteJoint*>(h->joints[j]);
+    if (!r) return -1;
+    r->setDriveEnabled(enabled != 0); r->setDriveVelocity(velocity); r->setDriveMaxTorque(maxTorque);
+    return 0;
+}
+void ph_add_collider(void* hp, int e, const float* lpos, const float* lquat, int type, const float* params, int mesh, const float* material, int flags, int data) {
+    auto* h = (Harness*)hp;
+    physecs::Collider col{};
+    col.position = v3(lpos);
+    col.orientation = q4(lquat);
+    col.geometry = makeGeometry(h, type, params, mesh);
+    col.material = { material[0], material[1], material[2] };
+    col.isTrigger = flags & 1;
+    col.enableSimulation = (flags >> 1) & 1;
+    col.data = data;
+    h->scene->addCollider(h->entities[e], col);
+}
+void ph_clear_colliders(void* hp, int e) { auto* h = (Harness*)hp; h->scene->clearColliders(h->entities[e]); }
 
 int ph_num_dynamic(void* hp) {
     auto* h = (Harness*)hp;

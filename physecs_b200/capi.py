@@ -25,7 +25,7 @@ EXPORTS = [
     "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds", "pb_build_trimesh",
     "pb_set_profile", "pb_get_profile", "pb_get_launches", "pb_profiler_range",
     "pb_update_joint_params", "pb_set_contact_filter", "pb_set_kinematic", "pb_set_mass", "pb_set_bounds",
-    "pb_set_static_poses", "pb_get_triggers",
+    "pb_set_static_poses", "pb_get_triggers", "pb_keep_contact_cache", "pb_keep_joint_state", "pb_grow_arenas",
 ]
 
 
@@ -120,10 +120,20 @@ class Context:
         if desc is not None:
             self.upload(desc)
 
+    @classmethod
+    def from_handle(cls, ptr, desc):
+        """Non-owning view of an existing pb_ctx* (the host Scene's context): parity taps only."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.ctx = C.c_void_p(ptr)
+        self.desc = desc
+        self._borrowed = True
+        return self
+
     def close(self):
-        if self.ctx:
+        if self.ctx and not getattr(self, "_borrowed", False):
             self.lib.pb_ctx_destroy(self.ctx)
-            self.ctx = C.c_void_p()
+        self.ctx = C.c_void_p()
 
     def __del__(self):
         try:

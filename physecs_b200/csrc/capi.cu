@@ -16,6 +16,7 @@ int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const
                      const float* a1p, const float* a1q, const float* params8, const int* color);
 void pb_joints_free(pb_ctx* ctx);
 int pb_joints_update_params(pb_ctx* ctx, int n, const float* params8);
+int pb_joints_keep_state(pb_ctx* ctx, int n, const int* oldIndex);
 
 // ---- packed host layout <-> float4 SoA ----------------------------------------------------------------------------
 __global__ void k_unpack3(int n, const float* __restrict__ src, float4* __restrict__ dst) {
@@ -190,6 +191,54 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
     cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);
     *out = ctx;
+    return PB_OK;
+}
+
+// Grow the per-step arenas of a live context.  Everything sized by max_pairs / max_manifolds is scratch that a step
+// rewrites from the start, EXCEPT the previous step's contact-cache payload (point arrays + hash table of buffer curBuf),
+// which is copied / re-hashed so a step that overflowed can simply be run again.
+int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
+    cudaSetDevice(ctx->device);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t oldM = ctx->caps.max_manifolds;
+    const size_t P = std::max(maxPairs, ctx->caps.max_pairs), M = std::max((size_t)maxManifolds, oldM), C = ctx->caps.max_colliders;
+    int rc = 0;
+#define A(p, n) if (!rc) rc = pb_alloc(ctx, &ctx->p, (n))
+    if ((int)P > ctx->caps.max_pairs) { A(pairs, P); A(pairOrder, 2 * P); A(trigPairs, P); }
+    if (M > oldM) {
+        size_t sortMax = std::max(C, M);
+        ctx->radixTiles = (int)((sortMax + 511) / 512);
+        A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
+        A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
+        A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
+        const size_t PT = 4 * M, oldPT = 4 * oldM;
+        A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
+        const int keep = ctx->curBuf, other = keep ^ 1;
+        A(pR0T[other], PT); A(cPointOfsBuf[other], M + 1); A(cNpBuf[other], M + 1);
+        // previous-step payload: allocate, copy, swap in
+        float4* nR = nullptr; int* nOfs = nullptr; int* nNp = nullptr;
+        if (!rc) rc = pb_alloc(ctx, &nR, PT);
+        if (!rc) rc = pb_alloc(ctx, &nOfs, M + 1);
+        if (!rc) rc = pb_alloc(ctx, &nNp, M + 1);
+        size_t cs = 1; while (cs < 2 * M) cs <<= 1;
+        unsigned long long* nTag[2] = { nullptr, nullptr }; int4* nVal[2] = { nullptr, nullptr };
+        for (int b = 0; b < 2 && !rc; ++b) { rc = pb_alloc(ctx, &nTag[b], cs); if (!rc) rc = pb_alloc(ctx, &nVal[b], cs); }
+        if (rc) return rc;
+        PB_CUDA(ctx, cudaMemcpyAsync(nR, ctx->pR0T[keep], sizeof(float4) * oldPT, cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(nOfs, ctx->cPointOfsBuf[keep], sizeof(int) * (oldM + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(nNp, ctx->cNpBuf[keep], sizeof(int) * (oldM + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+        pb_contact_cache_rehash(ctx, ctx->cacheSize, ctx->cacheTag[keep], ctx->cacheVal[keep], (int)cs, nTag[keep], nVal[keep]);
+        PB_CUDA(ctx, cudaMemsetAsync(nTag[other], 0, sizeof(unsigned long long) * cs, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->pR0T[keep]); cudaFree(ctx->cPointOfsBuf[keep]); cudaFree(ctx->cNpBuf[keep]);
+        ctx->pR0T[keep] = nR; ctx->cPointOfsBuf[keep] = nOfs; ctx->cNpBuf[keep] = nNp;
+        for (int b = 0; b < 2; ++b) { cudaFree(ctx->cacheTag[b]); cudaFree(ctx->cacheVal[b]); ctx->cacheTag[b] = nTag[b]; ctx->cacheVal[b] = nVal[b]; }
+        ctx->cacheSize = (int)cs;
+    }
+#undef A
+    if (rc) return rc;
+    ctx->caps.max_pairs = (int)P;
+    ctx->caps.max_manifolds = (int)M;
     return PB_OK;
 }
 
@@ -503,6 +552,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     ctx->lastCounts.n_triggers = ctx->hCounters[CNT_TRIGGERS];
     if (nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY)) {
         ctx->lastCounts.status = PB_ECAPACITY;
+        ctx->lastCounts.n_manifolds = nRaw;   // what the arenas would have needed (counters keep counting past the capacity)
         return pb_fail(ctx, PB_ECAPACITY, "per-step arena overflow: pairs=" + std::to_string(nPairs) + "/" + std::to_string(ctx->caps.max_pairs) +
                        " manifolds=" + std::to_string(nRaw) + "/" + std::to_string(ctx->caps.max_manifolds) + " (or triangle contacts per pair)");
     }
@@ -519,6 +569,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     if (ctx->profile && ctx->profUsed > 4096) { cudaStreamSynchronize(ctx->stream); profCollect(ctx); }
     if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
     ctx->cacheValid = true;
+    ctx->cacheBuilt = true;
     // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
     if ((rc = pb_update_bounds_all(ctx, 0.01f, 1))) return rc;
     cudaEventRecord(ctx->ev[4], ctx->stream);
@@ -598,6 +649,21 @@ int pb_set_mass(pb_ctx* ctx, int nDyn, const float* invMass, const float* com3, 
     ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
+}
+
+int pb_keep_contact_cache(pb_ctx* ctx, int nOld, const int* oldToNew) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->cacheBuilt || nOld <= 0) return PB_OK;   // nothing to keep (fresh context)
+    int rc = ensureStage(ctx, sizeof(int) * (size_t)nOld); if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, oldToNew, sizeof(int) * (size_t)nOld, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = pb_contact_cache_remap(ctx, nOld, (const int*)ctx->stage))) return rc;
+    ctx->cacheValid = true;
+    return PB_OK;
+}
+
+int pb_keep_joint_state(pb_ctx* ctx, int n, const int* oldIndex) {
+    cudaSetDevice(ctx->device);
+    return pb_joints_keep_state(ctx, n, oldIndex);
 }
 
 int pb_set_contact_filter(pb_ctx* ctx, int nColliders, const int* colliderClass, int nClasses, const unsigned char* lut) {

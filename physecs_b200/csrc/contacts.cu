@@ -9,6 +9,7 @@
 //                    contact cache (src/Physecs.cpp:215-315; cache semantics :237, :291-300, :313)
 #include "pb_ctx.h"
 #include "pb_math.cuh"
+#include <utility>
 
 #define DISCARD_COLOR 255u
 
@@ -175,6 +176,57 @@ __global__ void __launch_bounds__(128) k_contact_build(
             }
         }
     }
+}
+
+// Re-key the last step's contact cache after a collider re-upload (collider indices are part of the key): entries whose
+// colliders survive are re-inserted under their new indices, the rest are dropped.  Payload slots stay valid because the
+// per-point arrays of the previous step are untouched by an upload.
+__global__ void k_cache_remap(int size, const unsigned long long* __restrict__ oldTag, const int4* __restrict__ oldVal, const int* __restrict__ oldToNew,
+                              int nOld, unsigned long long* __restrict__ newTag, int4* __restrict__ newVal) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    if (oldTag[i] == 0ull) return;
+    int4 v = oldVal[i];
+    if (v.x < 0 || v.x >= nOld || v.y < 0 || v.y >= nOld) return;
+    int a = oldToNew[v.x], b = oldToNew[v.y];
+    if (a < 0 || b < 0) return;
+    unsigned long long tag = hashKey(a, b, v.z);
+    unsigned int h = (unsigned int)(tag >> 1) & (unsigned int)(size - 1);
+    while (true) {
+        unsigned long long old = atomicCAS(&newTag[h], 0ull, tag);
+        if (old == 0ull) { newVal[h] = make_int4(a, b, v.z, v.w); break; }
+        h = (h + 1) & (unsigned int)(size - 1);
+    }
+}
+
+// same entries, larger table (arena growth)
+__global__ void k_cache_rehash(int oldSize, const unsigned long long* __restrict__ oldTag, const int4* __restrict__ oldVal,
+                               int newSize, unsigned long long* __restrict__ newTag, int4* __restrict__ newVal) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= oldSize) return;
+    unsigned long long tag = oldTag[i];
+    if (tag == 0ull) return;
+    unsigned int h = (unsigned int)(tag >> 1) & (unsigned int)(newSize - 1);
+    while (true) {
+        unsigned long long old = atomicCAS(&newTag[h], 0ull, tag);
+        if (old == 0ull) { newVal[h] = oldVal[i]; break; }
+        h = (h + 1) & (unsigned int)(newSize - 1);
+    }
+}
+void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long* oldTag, const int4* oldVal, int newSize, unsigned long long* newTag, int4* newVal) {
+    cudaMemsetAsync(newTag, 0, sizeof(unsigned long long) * (size_t)newSize, ctx->stream);
+    ++ctx->launches, k_cache_rehash<<<pb_grid(oldSize, 256), 256, 0, ctx->stream>>>(oldSize, oldTag, oldVal, newSize, newTag, newVal);
+}
+
+int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
+    int cur = ctx->curBuf, other = cur ^ 1;
+    cudaMemsetAsync(ctx->cacheTag[other], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
+    ++ctx->launches, k_cache_remap<<<pb_grid(ctx->cacheSize, 256), 256, 0, ctx->stream>>>(ctx->cacheSize, ctx->cacheTag[cur], ctx->cacheVal[cur], dOldToNew, nOld,
+                                                                                         ctx->cacheTag[other], ctx->cacheVal[other]);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->cacheTag[0], ctx->cacheTag[1]);
+    std::swap(ctx->cacheVal[0], ctx->cacheVal[1]);
+    return PB_OK;
 }
 
 int pb_contact_build(pb_ctx* ctx, int nRaw) {

@@ -455,6 +455,8 @@ struct JointStore {
     float4* linC = nullptr; float4* a0T = nullptr; float4* a1K = nullptr; float4* a0tMin = nullptr; float4* a1tMax = nullptr;
     float2* soft = nullptr; float* lambda = nullptr;
     std::vector<int> order;   // device slot -> caller's joint index
+    // persistent state of the previous upload (gear angles), kept so surviving joints can carry it over
+    std::vector<float4> prevState; std::vector<int> prevOrder;
 };
 static JointStore* store(pb_ctx* ctx) { return (JointStore*)ctx->jointStore; }
 
@@ -479,6 +481,13 @@ static JointDev devView(pb_ctx* ctx) {
 
 int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const int* row1, const float* a0p, const float* a0q,
                      const float* a1p, const float* a1q, const float* params8, const int* color) {
+    std::vector<float4> prevState; std::vector<int> prevOrder;
+    if (JointStore* old = store(ctx)) {
+        cudaStreamSynchronize(ctx->stream);
+        prevState.resize(2 * (size_t)old->n);
+        cudaMemcpy(prevState.data(), old->state, sizeof(float4) * 2 * old->n, cudaMemcpyDeviceToHost);
+        prevOrder = old->order;
+    }
     pb_joints_free(ctx);
     if (n == 0) return PB_OK;
     for (int j = 0; j < n; ++j) {
@@ -488,6 +497,7 @@ int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const
     JointStore* s = new JointStore();
     ctx->jointStore = s;
     s->n = n;
+    s->prevState.swap(prevState); s->prevOrder.swap(prevOrder);
     // colour-major order, stable inside a colour (== the reference's per-colour joint vectors)
     s->order.resize(n);
     for (int j = 0; j < n; ++j) s->order[j] = j;
@@ -540,6 +550,26 @@ int pb_joints_update_params(pb_ctx* ctx, int n, const float* params8) {
     }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     PB_CUDA(ctx, cudaMemcpy(s->prm, prm.data(), sizeof(float4) * 2 * n, cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+// oldIndex[j] = index the caller's joint j had in the PREVIOUS pb_upload_joints call, or -1 for a new joint
+int pb_joints_keep_state(pb_ctx* ctx, int n, const int* oldIndex) {
+    JointStore* s = store(ctx);
+    if (!s || n != s->n) return n == 0 ? PB_OK : pb_fail(ctx, PB_EINVAL, "pb_keep_joint_state: joint count mismatch");
+    if (s->prevOrder.empty()) return PB_OK;
+    std::vector<int> oldSlot(s->prevOrder.size(), -1);
+    for (size_t k = 0; k < s->prevOrder.size(); ++k) oldSlot[s->prevOrder[k]] = (int)k;
+    std::vector<float4> st(2 * (size_t)n);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaMemcpy(st.data(), s->state, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) {
+        int oj = oldIndex[s->order[k]];
+        if (oj < 0 || oj >= (int)oldSlot.size() || oldSlot[oj] < 0) continue;
+        st[2 * k] = s->prevState[2 * (size_t)oldSlot[oj]];
+        st[2 * k + 1] = s->prevState[2 * (size_t)oldSlot[oj] + 1];
+    }
+    PB_CUDA(ctx, cudaMemcpy(s->state, st.data(), sizeof(float4) * 2 * n, cudaMemcpyHostToDevice));
     return PB_OK;
 }
 

@@ -139,6 +139,7 @@ struct pb_ctx {
     // contact cache (hash table over previous step's manifolds)
     unsigned long long* cacheTag[2] = {nullptr, nullptr}; int4* cacheVal[2] = {nullptr, nullptr}; int cacheSize = 0;
     bool cacheValid = false;
+    bool cacheBuilt = false;         // a step has run on this context: the previous-step tables hold real data
     int* cPointOfsBuf[2] = {nullptr, nullptr}; int* cNpBuf[2] = {nullptr, nullptr};
 
     // ---- joints (arrays owned by joints.cu) ----------------------------------------------------------------------
@@ -195,6 +196,8 @@ int pb_narrowphase(pb_ctx* ctx);
 int pb_contact_build(pb_ctx* ctx, int nRaw);
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
 int pb_joint_begin_step(pb_ctx* ctx);
+int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew);
+void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long* oldTag, const int4* oldVal, int newSize, unsigned long long* newTag, int4* newVal);
 
 // generic device primitives (primitives.cu)
 int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,

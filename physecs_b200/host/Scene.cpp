@@ -1,0 +1,731 @@
+// physecs::Scene -- host side of the B200 path (declared in include/Physecs/detail/b200_scene.hpp).
+//
+// Mirrors the reference's Scene (src/Physecs.cpp): same EnTT signal hooks (:92-98), same per-step contract (:112-561),
+// same joint-graph colouring (:690-710), nonCollidingPairs (:788-793), trigger enter / exit diff (:538-552).  The
+// arithmetic of the step is not here: this file walks the registry, keeps the device scene description in sync and calls
+// the C ABI of include/physecs_b200.h.  Registry walks are the only O(bodies) host work per step; they run on the
+// Scene's worker threads and go through pinned staging buffers.
+#include <Physecs.h>
+#include <MassUtil.h>
+#include "../../include/physecs_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+
+namespace physecs {
+
+ContactType defaultContactFilter(bool isTrigger0, int, bool isTrigger1, int) {
+    return (isTrigger0 || isTrigger1) ? TRIGGER : COLLISION;
+}
+
+namespace {
+
+// ---- fork-join helper for the gather / scatter loops ---------------------------------------------------------------------
+class Workers {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cvStart, cvDone;
+    std::function<void(size_t, size_t)> job;
+    size_t total = 0, chunk = 0;
+    std::atomic<size_t> next{0};
+    int generation = 0, running = 0;
+    bool quit = false;
+
+    void drain() {
+        for (;;) {
+            size_t b = next.fetch_add(chunk);
+            if (b >= total) return;
+            job(b, std::min(total, b + chunk));
+        }
+    }
+    void loop() {
+        int seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cvStart.wait(lk, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+            lk.unlock();
+            drain();
+            lk.lock();
+            if (--running == 0) cvDone.notify_one();
+        }
+    }
+
+public:
+    explicit Workers(int n) { for (int i = 0; i < n; ++i) threads.emplace_back([this] { loop(); }); }
+    ~Workers() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cvStart.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    // fn(begin, end) over [0, n); the caller participates
+    void parallelFor(size_t n, const std::function<void(size_t, size_t)>& fn) {
+        if (n == 0) return;
+        if (threads.empty() || n < 4096) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = fn; total = n; next = 0;
+            chunk = std::max<size_t>(1024, n / ((threads.size() + 1) * 8));
+            running = (int)threads.size();
+            ++generation;
+        }
+        cvStart.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(m);
+        cvDone.wait(lk, [&] { return running == 0; });
+    }
+};
+
+template <class T> struct Pinned {
+    T* p = nullptr; size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) pb_host_free(p);
+        p = nullptr; cap = 0;
+        void* q = nullptr;
+        size_t want = std::max<size_t>(n + n / 4, 256);
+        if (pb_host_alloc(&q, sizeof(T) * want) != PB_OK) throw std::runtime_error("physecs_b200: pinned host allocation failed");
+        p = (T*)q; cap = want;
+    }
+    ~Pinned() { if (p) pb_host_free(p); }
+};
+
+inline unsigned long long colKey(entt::entity e, int idx) { return ((unsigned long long)entt::to_integral(e) << 20) ^ (unsigned long long)(unsigned)idx; }
+
+using Clock = std::chrono::steady_clock;
+inline double msSince(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+} // namespace
+
+struct Scene::Impl {
+    explicit Impl(int threads) : workers(std::max(threads, 0)) {}
+
+    Workers workers;
+    int device = 0;
+    pb_ctx* ctx = nullptr;
+    pb_caps caps{};
+    SyncMode syncMode = SYNC_FULL;
+    int wantPairs = 0, wantManifolds = 0;       // user-chosen initial arena sizes (0 = scale with the collider count)
+
+    // rows: [0, nDyn) = packed order of the RigidBodyDynamicComponent storage (the reference's b0 / b1 index space,
+    // Physecs.cpp:116-117), then the static rows (collision component, no dynamic component)
+    std::vector<entt::entity> rowEntity;
+    std::vector<int> entityRow;                 // entt::to_entity(e) -> row, -1 = none
+    std::vector<unsigned> rowTransformIdx;      // cached packed index into the TransformComponent storage, validated on use
+    int nDyn = 0, nStatic = 0;
+    struct ColRef { entt::entity e; int idx; };
+    std::vector<ColRef> cols;                   // device collider order
+
+    bool topologyDirty = true, jointsDirty = true, pairsDirty = true, filterDirty = true, ctxFresh = true;
+    bool stagingValid = false;                  // pinned buffers hold the current state of every dynamic row
+    std::unordered_set<unsigned long long> freshCols;   // colliders created since the last upload: creation-time bounds (no margin)
+    struct Move { entt::entity e; glm::vec3 p; glm::quat q; };
+    std::vector<Move> moved;                    // registry.patch<TransformComponent> since the last step
+    std::unordered_set<unsigned> touched;       // device-authoritative mode: dynamic rows to re-read
+
+    std::unordered_map<const ConvexMesh*, int> convexHandle;
+    std::unordered_map<const TriangleMesh*, int> trimeshHandle;
+
+    // pinned staging
+    Pinned<float> hPos, hQuat, hVel, hAng, hSPos, hSQuat;
+    // host mirrors for change detection of fields the reference reads live every step
+    std::vector<int> kin;
+    std::vector<float> invMass, com, invI;
+
+    // joints
+    std::vector<Joint*> joints;                 // creation order
+    std::vector<Joint*> uploadedJoints;         // joint list of the last pb_upload_joints (state carry-over)
+    std::unordered_map<entt::entity, unsigned char> jointBits;   // JointGraph::bitsets (Physecs.h:150)
+    std::set<std::pair<unsigned, unsigned>> nonColliding;         // (lower, higher) entity integers
+
+    // triggers
+    std::vector<std::array<int, 4>> triggerCache;
+    std::vector<OnTriggerEnterListener*> enterListeners;
+    std::vector<OnTriggerExitListener*> exitListeners;
+    ContactType (*filter)(bool, int, bool, int) = defaultContactFilter;
+
+    std::vector<glm::vec3> contactPoints;
+    StepStats stats{};
+
+    [[noreturn]] void fail(const char* what, int rc) {
+        std::string msg = std::string("physecs_b200: ") + what + " failed (" + std::to_string(rc) + ")";
+        if (ctx) { msg += ": "; msg += pb_last_error(ctx); }
+        throw std::runtime_error(msg);
+    }
+    void check(int rc, const char* what) { if (rc != PB_OK) fail(what, rc); }
+    int rowOf(entt::entity e) const {
+        auto i = (size_t)entt::to_entity(e);
+        if (i >= entityRow.size()) return -1;
+        int r = entityRow[i];
+        return (r >= 0 && rowEntity[r] == e) ? r : -1;
+    }
+};
+
+// ---- construction / signals (reference Physecs.cpp:25-98, :815-821) ------------------------------------------------------------
+Scene::Scene(entt::registry& registry, int numThreads) : registry(registry), impl(new Impl(numThreads)) {
+    registry.on_construct<RigidBodyCollisionComponent>().connect<&Scene::onRigidBodyCreate>(this);
+    registry.on_destroy<RigidBodyCollisionComponent>().connect<&Scene::onRigidBodyDelete>(this);
+    registry.on_update<RigidBodyCollisionComponent>().connect<&Scene::onRigidBodyUpdate>(this);
+    registry.on_update<TransformComponent>().connect<&Scene::onRigidBodyMove>(this);
+    registry.on_construct<RigidBodyDynamicComponent>().connect<&Scene::onDynamicCreate>(this);
+    registry.on_destroy<RigidBodyDynamicComponent>().connect<&Scene::onDynamicDelete>(this);
+    // bodies that already exist are picked up by the first rebuild (the reference would miss them; harmless superset)
+}
+
+Scene::~Scene() {
+    registry.on_construct<RigidBodyCollisionComponent>().disconnect<&Scene::onRigidBodyCreate>(this);
+    registry.on_destroy<RigidBodyCollisionComponent>().disconnect<&Scene::onRigidBodyDelete>(this);
+    registry.on_update<RigidBodyCollisionComponent>().disconnect<&Scene::onRigidBodyUpdate>(this);
+    registry.on_update<TransformComponent>().disconnect<&Scene::onRigidBodyMove>(this);
+    registry.on_construct<RigidBodyDynamicComponent>().disconnect<&Scene::onDynamicCreate>(this);
+    registry.on_destroy<RigidBodyDynamicComponent>().disconnect<&Scene::onDynamicDelete>(this);
+    if (impl->ctx) pb_ctx_destroy(impl->ctx);
+    // joints still alive are leaked exactly like the reference leaks them (Physecs.cpp:815-821 never deletes them)
+}
+
+void Scene::onRigidBodyCreate(entt::registry& reg, entt::entity e) {
+    impl->topologyDirty = true;
+    auto& c = reg.get<RigidBodyCollisionComponent>(e);
+    for (int i = 0; i < (int)c.colliders.size(); ++i) impl->freshCols.insert(colKey(e, i));
+}
+void Scene::onRigidBodyDelete(entt::registry&, entt::entity) { impl->topologyDirty = true; }
+// colliders edited in place and announced with registry.patch / replace<RigidBodyCollisionComponent>: the reference reads
+// collider geometry live in its narrowphase; the device copy is refreshed instead (bounds keep their history)
+void Scene::onRigidBodyUpdate(entt::registry&, entt::entity) { impl->topologyDirty = true; }
+void Scene::onDynamicCreate(entt::registry&, entt::entity) { impl->topologyDirty = true; }
+void Scene::onDynamicDelete(entt::registry&, entt::entity) { impl->topologyDirty = true; }
+
+// registry.patch / replace<TransformComponent> (reference onRigidBodyMove -> updateBounds, Physecs.cpp:51-54, :79-90):
+// the bounds of the entity's colliders are recomputed from the transform AT PATCH TIME with the 0.01 margin
+void Scene::onRigidBodyMove(entt::registry& reg, entt::entity e) {
+    if (!reg.any_of<RigidBodyCollisionComponent>(e)) return;
+    auto& t = reg.get<TransformComponent>(e);
+    impl->moved.push_back({ e, t.position, t.orientation });
+    int r = impl->rowOf(e);
+    if (r >= 0 && r < impl->nDyn) impl->touched.insert((unsigned)r);
+}
+
+void Scene::setDevice(int cudaDevice) {
+    if (impl->ctx) throw std::runtime_error("physecs_b200: setDevice after the first simulate()");
+    impl->device = cudaDevice;
+}
+void Scene::setSyncMode(SyncMode mode) { impl->syncMode = mode; }
+void Scene::notifyBodyChanged(entt::entity e) {
+    int r = impl->rowOf(e);
+    if (r >= 0 && r < impl->nDyn) impl->touched.insert((unsigned)r);
+}
+void Scene::setArenaCapacity(int maxPairs, int maxManifolds) { impl->wantPairs = maxPairs; impl->wantManifolds = maxManifolds; }
+pb_ctx* Scene::nativeContext() { return impl->ctx; }
+Scene::StepStats Scene::getLastStepStats() const { return impl->stats; }
+
+// ---- joints (reference addJoint / destroyJoint, Physecs.cpp:690-723) -----------------------------------------------------------
+void Scene::addJoint(Joint* joint) {
+    auto e0 = joint->getEntity0(), e1 = joint->getEntity1();
+    unsigned a = entt::to_integral(e0), b = entt::to_integral(e1);
+    impl->nonColliding.insert(a < b ? std::make_pair(a, b) : std::make_pair(b, a));
+    impl->pairsDirty = true;
+    unsigned char& c0 = impl->jointBits[e0];
+    unsigned char& c1 = impl->jointBits[e1];
+    // lowest colour free on both entities; the union promotes to int so index 8 (the overflow bucket) is always
+    // available and consumes no bit (quirk Q21)
+    unsigned un = ~(unsigned)(c0 | c1);
+    int i = __builtin_ctz(un);
+    c0 = (unsigned char)(c0 | (1u << i));
+    c1 = (unsigned char)(c1 | (1u << i));
+    joint->setColor(i);
+    impl->joints.push_back(joint);
+    impl->jointsDirty = true;
+}
+
+void Scene::destroyJoint(Joint* joint) {
+    auto it = std::find(impl->joints.begin(), impl->joints.end(), joint);
+    if (it == impl->joints.end()) return;
+    impl->joints.erase(it);
+    std::replace(impl->uploadedJoints.begin(), impl->uploadedJoints.end(), joint, (Joint*)nullptr);   // the address may be reused
+    auto e0 = joint->getEntity0(), e1 = joint->getEntity1();
+    unsigned a = entt::to_integral(e0), b = entt::to_integral(e1);
+    impl->nonColliding.erase(a < b ? std::make_pair(a, b) : std::make_pair(b, a));
+    impl->jointBits[e0] &= (unsigned char)~(1u << joint->getColor());
+    impl->jointBits[e1] &= (unsigned char)~(1u << joint->getColor());
+    impl->pairsDirty = impl->jointsDirty = true;
+    delete joint;
+}
+
+// ---- collider / body edits (reference Physecs.cpp:725-770, :788-797) -----------------------------------------------------------
+void Scene::clearColliders(entt::entity entity) {
+    auto& col = registry.get<RigidBodyCollisionComponent>(entity);
+    col.colliders.clear();
+    impl->topologyDirty = true;
+}
+
+void Scene::addCollider(entt::entity entity, const Collider& collider) {
+    auto& col = registry.get<RigidBodyCollisionComponent>(entity);
+    impl->freshCols.insert(colKey(entity, (int)col.colliders.size()));
+    col.colliders.push_back(collider);
+    impl->topologyDirty = true;
+}
+
+void Scene::setIsKinematic(entt::entity entity, bool isKinematic) {
+    auto& d = registry.get<RigidBodyDynamicComponent>(entity);
+    d.isKinematic = isKinematic;
+    if (isKinematic) { d.velocity = glm::vec3(0); d.angularVelocity = glm::vec3(0); }
+    notifyBodyChanged(entity);   // the kinematic flag itself is picked up by the per-step mirror comparison
+}
+
+void Scene::addOnTriggerEnterCallback(OnTriggerEnterListener* cb) { impl->enterListeners.push_back(cb); }
+void Scene::addOnTriggerExitCallback(OnTriggerExitListener* cb) { impl->exitListeners.push_back(cb); }
+void Scene::removeOnTriggerEnterCallback(OnTriggerEnterListener* cb) {
+    auto it = std::find(impl->enterListeners.begin(), impl->enterListeners.end(), cb);
+    if (it != impl->enterListeners.end()) impl->enterListeners.erase(it);
+}
+void Scene::removeOnTriggerExitCallback(OnTriggerExitListener* cb) {
+    auto it = std::find(impl->exitListeners.begin(), impl->exitListeners.end(), cb);
+    if (it != impl->exitListeners.end()) impl->exitListeners.erase(it);
+}
+
+void Scene::setCanCollide(entt::entity entity0, entt::entity entity1, bool canCollide) {
+    unsigned a = entt::to_integral(entity0), b = entt::to_integral(entity1);
+    auto key = a < b ? std::make_pair(a, b) : std::make_pair(b, a);
+    if (canCollide) impl->nonColliding.erase(key); else impl->nonColliding.insert(key);
+    impl->pairsDirty = true;
+}
+
+void Scene::setContactFilter(ContactType (*filter)(bool, int, bool, int)) {
+    impl->filter = filter ? filter : defaultContactFilter;
+    impl->filterDirty = true;
+}
+
+const std::vector<glm::vec3>& Scene::getContactPoints() {
+    auto& out = impl->contactPoints;
+    out.clear();
+    if (!impl->ctx) return out;
+    pb_counts c{};
+    pb_get_counts(impl->ctx, &c);
+    int n = c.n_manifolds;
+    if (n <= 0) return out;
+    std::vector<int> keys((size_t)5 * n), np(n), color(n);
+    std::vector<float> nrm((size_t)3 * n), pts((size_t)24 * n);
+    int got = 0;
+    impl->check(pb_get_manifolds(impl->ctx, n, keys.data(), np.data(), nrm.data(), pts.data(), color.data(), &got), "pb_get_manifolds");
+    for (int m = 0; m < got; ++m)
+        for (int k = 0; k < np[m]; ++k) {
+            const float* p = &pts[(size_t)24 * m + 6 * k];
+            out.emplace_back(p[0], p[1], p[2]);
+            out.emplace_back(p[3], p[4], p[5]);
+        }
+    return out;
+}
+
+// ---- the step ----------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <class T>
+inline T& packedAt(entt::storage_for_t<T>& st, size_t pos) {
+    constexpr size_t page = entt::component_traits<T>::page_size;
+    return st.raw()[pos / page][pos % page];
+}
+
+} // namespace
+
+void Scene::simulate(float timeStep) {
+    Impl& S = *impl;
+    auto tStart = Clock::now();
+    auto& dynStore = registry.storage<RigidBodyDynamicComponent>();
+    auto& colStore = registry.storage<RigidBodyCollisionComponent>();
+    auto& trStore = registry.storage<TransformComponent>();
+
+    // ---- (re)build the device scene description after structural changes -----------------------------------------------------
+    auto rebuild = [&](bool growCaps) {
+        // bounds history of colliders that survive the re-upload (creation bounds have no margin, refreshed ones do: quirk Q6)
+        std::unordered_map<unsigned long long, std::array<float, 6>> keep;
+        if (S.ctx && !S.ctxFresh && !S.cols.empty()) {
+            std::vector<float> b((size_t)6 * S.cols.size());
+            S.check(pb_get_bounds(S.ctx, b.data()), "pb_get_bounds");
+            keep.reserve(S.cols.size() * 2);
+            for (size_t i = 0; i < S.cols.size(); ++i) {
+                unsigned long long k = colKey(S.cols[i].e, S.cols[i].idx);
+                if (S.freshCols.count(k)) continue;
+                std::array<float, 6> a;
+                std::memcpy(a.data(), &b[6 * i], sizeof(float) * 6);
+                keep.emplace(k, a);
+            }
+        }
+        std::vector<Impl::ColRef> oldCols;
+        if (S.ctx && !S.ctxFresh) oldCols = S.cols;
+        const size_t nDyn = dynStore.size();
+        S.rowEntity.clear();
+        S.rowEntity.reserve(nDyn + colStore.size());
+        const entt::entity* dynEnts = dynStore.data();
+        for (size_t i = 0; i < nDyn; ++i) S.rowEntity.push_back(dynEnts[i]);
+        const entt::entity* colEnts = colStore.data();
+        for (size_t i = 0; i < colStore.size(); ++i)
+            if (!dynStore.contains(colEnts[i])) S.rowEntity.push_back(colEnts[i]);
+        S.nDyn = (int)nDyn;
+        S.nStatic = (int)S.rowEntity.size() - S.nDyn;
+        const int rows = (int)S.rowEntity.size();
+        size_t maxIdx = 0;
+        for (auto e : S.rowEntity) maxIdx = std::max(maxIdx, (size_t)entt::to_entity(e));
+        S.entityRow.assign(rows ? maxIdx + 1 : 0, -1);
+        S.rowTransformIdx.assign(rows, 0u);
+        for (int r = 0; r < rows; ++r) {
+            S.entityRow[(size_t)entt::to_entity(S.rowEntity[r])] = r;
+            S.rowTransformIdx[r] = (unsigned)trStore.index(S.rowEntity[r]);
+        }
+        // colliders, row-major
+        S.cols.clear();
+        for (int r = 0; r < rows; ++r) {
+            auto e = S.rowEntity[r];
+            if (!colStore.contains(e)) continue;
+            auto& cc = colStore.get(e);
+            for (int i = 0; i < (int)cc.colliders.size(); ++i) S.cols.push_back({ e, i });
+        }
+        const int nCol = (int)S.cols.size();
+
+        // capacities: context is sized with headroom and re-created when the scene outgrows it
+        auto roomy = [](int n) { return std::max(1024, n + n / 2); };
+        bool need = !S.ctx || rows > S.caps.max_bodies || nCol > S.caps.max_colliders || (int)S.joints.size() > S.caps.max_joints || growCaps;
+        if (need) {
+            pb_caps c{};
+            c.max_bodies = roomy(rows);
+            c.max_colliders = roomy(nCol);
+            c.max_pairs = S.wantPairs > 0 ? S.wantPairs : 8 * c.max_colliders + 4096;
+            c.max_manifolds = S.wantManifolds > 0 ? S.wantManifolds : 6 * c.max_colliders + 4096;
+            c.max_joints = roomy((int)S.joints.size());
+            if (S.ctx) { pb_ctx_destroy(S.ctx); S.ctx = nullptr; }
+            S.convexHandle.clear(); S.trimeshHandle.clear();
+            int rc = pb_ctx_create(S.device, &c, &S.ctx);
+            if (rc != PB_OK) { S.ctx = nullptr; S.fail("pb_ctx_create (a CUDA device is required: there is no CPU fallback)", rc); }
+            S.caps = c;
+            S.jointsDirty = S.pairsDirty = S.filterDirty = true;
+            S.uploadedJoints.clear();
+            oldCols.clear();         // a new context starts with an empty contact cache
+        }
+
+        // meshes referenced by colliders
+        for (auto& cr : S.cols) {
+            const Collider& c = colStore.get(cr.e).colliders[cr.idx];
+            if (c.geometry.type == CONVEX_MESH && !S.convexHandle.count(c.geometry.convex.mesh)) {
+                const ConvexMesh* m = c.geometry.convex.mesh;
+                std::vector<float> v((size_t)3 * m->vertices.size()), fn((size_t)3 * m->faces.size()), fc((size_t)3 * m->faces.size());
+                for (int i = 0; i < m->vertices.size(); ++i) std::memcpy(&v[3 * i], &m->vertices[i], sizeof(float) * 3);
+                std::vector<int> off(m->faces.size() + 1, 0), idx;
+                for (size_t f = 0; f < m->faces.size(); ++f) {
+                    idx.insert(idx.end(), m->faces[f].indices.begin(), m->faces[f].indices.end());
+                    off[f + 1] = (int)idx.size();
+                    std::memcpy(&fn[3 * f], &m->faces[f].normal, sizeof(float) * 3);
+                    std::memcpy(&fc[3 * f], &m->faces[f].centroid, sizeof(float) * 3);
+                }
+                int h = -1;
+                S.check(pb_register_convex(S.ctx, v.data(), m->vertices.size(), off.data(), idx.data(), (int)m->faces.size(), fn.data(), fc.data(), &h), "pb_register_convex");
+                S.convexHandle[m] = h;
+            }
+            if (c.geometry.type == TRIANGLE_MESH && !S.trimeshHandle.count(c.geometry.triangleMesh.mesh)) {
+                const TriangleMesh* m = c.geometry.triangleMesh.mesh;
+                int h = -1;
+                S.check(pb_register_trimesh(S.ctx, (const float*)m->vertices.data(), (int)m->vertices.size(), m->getSourceIndices().data(),
+                                            (int)m->getSourceIndices().size(), &h, nullptr), "pb_register_trimesh");
+                S.trimeshHandle[m] = h;
+            }
+        }
+
+        // bodies
+        std::vector<int> ent(rows);
+        std::vector<float> pos((size_t)3 * rows), quat((size_t)4 * rows), vel((size_t)3 * nDyn), ang((size_t)3 * nDyn);
+        S.kin.assign(nDyn, 0); S.invMass.assign(nDyn, 0.f); S.com.assign(3 * nDyn, 0.f); S.invI.assign(9 * nDyn, 0.f);
+        for (int r = 0; r < rows; ++r) {
+            auto e = S.rowEntity[r];
+            ent[r] = (int)entt::to_integral(e);
+            const TransformComponent& t = packedAt<TransformComponent>(trStore, S.rowTransformIdx[r]);
+            std::memcpy(&pos[3 * (size_t)r], &t.position, sizeof(float) * 3);
+            quat[4 * (size_t)r] = t.orientation.x; quat[4 * (size_t)r + 1] = t.orientation.y; quat[4 * (size_t)r + 2] = t.orientation.z; quat[4 * (size_t)r + 3] = t.orientation.w;
+            if (r < (int)nDyn) {
+                const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, (size_t)r);
+                S.kin[r] = d.isKinematic ? 1 : 0;
+                std::memcpy(&vel[3 * (size_t)r], &d.velocity, sizeof(float) * 3);
+                std::memcpy(&ang[3 * (size_t)r], &d.angularVelocity, sizeof(float) * 3);
+                S.invMass[r] = d.invMass;
+                std::memcpy(&S.com[3 * (size_t)r], &d.com, sizeof(float) * 3);
+                std::memcpy(&S.invI[9 * (size_t)r], &d.invInertiaTensor, sizeof(float) * 9);
+            }
+        }
+        S.check(pb_upload_bodies(S.ctx, (int)nDyn, S.nStatic, ent.data(), pos.data(), quat.data(), S.kin.data(), vel.data(), ang.data(),
+                                 S.invMass.data(), S.com.data(), S.invI.data()), "pb_upload_bodies");
+
+        // colliders
+        std::vector<int> cRow(nCol), cIdx(nCol), cType(nCol), cMesh(nCol), cFlags(nCol), cData(nCol);
+        std::vector<float> lp((size_t)3 * nCol), lq((size_t)4 * nCol), prm((size_t)4 * nCol, 0.f), mat((size_t)3 * nCol);
+        for (int i = 0; i < nCol; ++i) {
+            const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
+            cRow[i] = S.entityRow[(size_t)entt::to_entity(S.cols[i].e)];
+            cIdx[i] = S.cols[i].idx;
+            cType[i] = (int)c.geometry.type;
+            cMesh[i] = -1;
+            std::memcpy(&lp[3 * (size_t)i], &c.position, sizeof(float) * 3);
+            lq[4 * (size_t)i] = c.orientation.x; lq[4 * (size_t)i + 1] = c.orientation.y; lq[4 * (size_t)i + 2] = c.orientation.z; lq[4 * (size_t)i + 3] = c.orientation.w;
+            float* p = &prm[4 * (size_t)i];
+            switch (c.geometry.type) {
+                case SPHERE: p[0] = c.geometry.sphere.radius; break;
+                case CAPSULE: p[0] = c.geometry.capsule.halfHeight; p[1] = c.geometry.capsule.radius; break;
+                case BOX: std::memcpy(p, &c.geometry.box.halfExtents, sizeof(float) * 3); break;
+                case CONVEX_MESH: std::memcpy(p, &c.geometry.convex.scale, sizeof(float) * 3); cMesh[i] = S.convexHandle[c.geometry.convex.mesh]; break;
+                case TRIANGLE_MESH: cMesh[i] = S.trimeshHandle[c.geometry.triangleMesh.mesh]; break;
+            }
+            mat[3 * (size_t)i] = c.material.friction; mat[3 * (size_t)i + 1] = c.material.restitution; mat[3 * (size_t)i + 2] = c.material.damping;
+            cFlags[i] = (c.isTrigger ? PB_COL_TRIGGER : 0) | (c.enableSimulation ? PB_COL_ENABLE_SIM : 0);
+            cData[i] = c.data;
+        }
+        S.check(pb_upload_colliders(S.ctx, nCol, cRow.data(), cIdx.data(), lp.data(), lq.data(), cType.data(), prm.data(), cMesh.data(), mat.data(),
+                                    cFlags.data(), cData.data()), "pb_upload_colliders");
+        if (!keep.empty()) {
+            std::vector<int> which; std::vector<float> b;
+            for (int i = 0; i < nCol; ++i) {
+                auto it = keep.find(colKey(S.cols[i].e, S.cols[i].idx));
+                if (it == keep.end()) continue;
+                which.push_back(i);
+                b.insert(b.end(), it->second.begin(), it->second.end());
+            }
+            if (!which.empty()) S.check(pb_set_bounds(S.ctx, (int)which.size(), which.data(), b.data()), "pb_set_bounds");
+        }
+        if (!oldCols.empty()) {
+            // persisting contacts keep their cached restitution targets across the re-upload (reference contactCache is keyed
+            // by (entity, collider) pairs, Physecs.cpp:237; the device table is keyed by collider rows, so re-key it)
+            std::unordered_map<unsigned long long, int> now;
+            now.reserve((size_t)nCol * 2);
+            for (int i = 0; i < nCol; ++i) now.emplace(colKey(S.cols[i].e, S.cols[i].idx), i);
+            std::vector<int> oldToNew(oldCols.size(), -1);
+            for (size_t i = 0; i < oldCols.size(); ++i) {
+                unsigned long long k = colKey(oldCols[i].e, oldCols[i].idx);
+                if (S.freshCols.count(k)) continue;
+                auto it = now.find(k);
+                if (it != now.end()) oldToNew[i] = it->second;
+            }
+            S.check(pb_keep_contact_cache(S.ctx, (int)oldToNew.size(), oldToNew.data()), "pb_keep_contact_cache");
+        }
+        S.freshCols.clear();
+        S.touched.clear();
+        S.stagingValid = false;
+        S.topologyDirty = false;
+        S.ctxFresh = false;
+        S.jointsDirty = true;        // body rows may have moved
+        S.filterDirty = true;        // the filter table is per collider
+    };
+
+    auto uploadJoints = [&] {
+        const int n = (int)S.joints.size();
+        std::vector<int> type(n), r0(n), r1(n), color(n);
+        std::vector<float> a0p((size_t)3 * n), a0q((size_t)4 * n), a1p((size_t)3 * n), a1q((size_t)4 * n), prm((size_t)8 * n);
+        for (int j = 0; j < n; ++j) {
+            Joint* J = S.joints[j];
+            type[j] = J->kind; color[j] = J->getColor();
+            r0[j] = S.rowOf(J->getEntity0()); r1[j] = S.rowOf(J->getEntity1());
+            if (r0[j] < 0 || r1[j] < 0) throw std::runtime_error("physecs_b200: a joint references an entity that is not a rigid body");
+            glm::vec3 p0 = J->getAnchor0Pos(), p1 = J->getAnchor1Pos();
+            glm::quat q0 = J->getAnchor0Or(), q1 = J->getAnchor1Or();
+            std::memcpy(&a0p[3 * (size_t)j], &p0, sizeof(float) * 3); std::memcpy(&a1p[3 * (size_t)j], &p1, sizeof(float) * 3);
+            a0q[4 * (size_t)j] = q0.x; a0q[4 * (size_t)j + 1] = q0.y; a0q[4 * (size_t)j + 2] = q0.z; a0q[4 * (size_t)j + 3] = q0.w;
+            a1q[4 * (size_t)j] = q1.x; a1q[4 * (size_t)j + 1] = q1.y; a1q[4 * (size_t)j + 2] = q1.z; a1q[4 * (size_t)j + 3] = q1.w;
+            std::memcpy(&prm[8 * (size_t)j], J->params, sizeof(float) * 8);
+            J->paramsDirty = false;
+        }
+        S.check(pb_upload_joints(S.ctx, n, type.data(), r0.data(), r1.data(), a0p.data(), a0q.data(), a1p.data(), a1q.data(), prm.data(), color.data()), "pb_upload_joints");
+        if (!S.uploadedJoints.empty() && n) {
+            // joints that were already on the device keep their persistent state (gear angle tracking)
+            std::unordered_map<const Joint*, int> was;
+            for (size_t j = 0; j < S.uploadedJoints.size(); ++j) was.emplace(S.uploadedJoints[j], (int)j);
+            std::vector<int> oldIndex(n, -1);
+            for (int j = 0; j < n; ++j) { auto it = was.find(S.joints[j]); if (it != was.end()) oldIndex[j] = it->second; }
+            S.check(pb_keep_joint_state(S.ctx, n, oldIndex.data()), "pb_keep_joint_state");
+        }
+        S.uploadedJoints = S.joints;
+        S.jointsDirty = false;
+    };
+
+    auto uploadFilter = [&] {
+        if (S.filter == defaultContactFilter) { S.check(pb_set_contact_filter(S.ctx, 0, nullptr, 0, nullptr), "pb_set_contact_filter"); S.filterDirty = false; return; }
+        // tabulate the user's function over the (isTrigger, data) classes present in the scene
+        std::vector<std::pair<bool, int>> classes;
+        std::vector<int> cls(S.cols.size());
+        std::unordered_map<long long, int> index;
+        for (size_t i = 0; i < S.cols.size(); ++i) {
+            const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
+            long long key = ((long long)c.data << 1) | (c.isTrigger ? 1 : 0);
+            auto it = index.find(key);
+            if (it == index.end()) { it = index.emplace(key, (int)classes.size()).first; classes.emplace_back(c.isTrigger, c.data); }
+            cls[i] = it->second;
+        }
+        const int K = (int)classes.size();
+        if ((long long)K * K > (1ll << 26)) throw std::runtime_error("physecs_b200: custom contact filter over too many distinct collider data values");
+        std::vector<unsigned char> lut((size_t)K * K);
+        for (int a = 0; a < K; ++a)
+            for (int b = 0; b < K; ++b)
+                lut[(size_t)a * K + b] = S.filter(classes[a].first, classes[a].second, classes[b].first, classes[b].second) == TRIGGER ? 1 : 0;
+        S.check(pb_set_contact_filter(S.ctx, (int)cls.size(), cls.data(), K, lut.data()), "pb_set_contact_filter");
+        S.filterDirty = false;
+    };
+
+    if (S.topologyDirty) rebuild(false);
+    const int nDyn = S.nDyn, nStatic = S.nStatic;
+    if (S.jointsDirty) uploadJoints();
+    else {
+        bool dirty = false;
+        for (Joint* J : S.joints) dirty |= J->paramsDirty;
+        if (dirty) {
+            std::vector<float> prm((size_t)8 * S.joints.size());
+            for (size_t j = 0; j < S.joints.size(); ++j) { std::memcpy(&prm[8 * j], S.joints[j]->params, sizeof(float) * 8); S.joints[j]->paramsDirty = false; }
+            S.check(pb_update_joint_params(S.ctx, (int)S.joints.size(), prm.data()), "pb_update_joint_params");
+        }
+    }
+    if (S.pairsDirty) {
+        std::vector<int> p; p.reserve(2 * S.nonColliding.size());
+        for (auto& pr : S.nonColliding) { p.push_back((int)pr.first); p.push_back((int)pr.second); }
+        S.check(pb_set_noncolliding_pairs(S.ctx, (int)S.nonColliding.size(), p.data()), "pb_set_noncolliding_pairs");
+        S.pairsDirty = false;
+    }
+    if (S.filterDirty) uploadFilter();
+
+    // ---- bodies announced through registry.patch<TransformComponent>: pose + bounds (+0.01) from the patch-time transform -----
+    if (!S.moved.empty()) {
+        std::vector<int> rows; std::vector<float> p, q;
+        for (auto& mv : S.moved) {
+            int r = S.rowOf(mv.e);
+            if (r < 0) continue;
+            rows.push_back(r);
+            p.insert(p.end(), { mv.p.x, mv.p.y, mv.p.z });
+            q.insert(q.end(), { mv.q.x, mv.q.y, mv.q.z, mv.q.w });
+        }
+        if (!rows.empty()) S.check(pb_move_rows(S.ctx, (int)rows.size(), rows.data(), p.data(), q.data()), "pb_move_rows");
+        S.moved.clear();
+    }
+
+    // ---- gather: registry -> pinned SoA ------------------------------------------------------------------------------------------
+    auto tGather = Clock::now();
+    S.hPos.reserve((size_t)3 * nDyn); S.hQuat.reserve((size_t)4 * nDyn); S.hVel.reserve((size_t)3 * nDyn); S.hAng.reserve((size_t)3 * nDyn);
+    S.hSPos.reserve((size_t)3 * nStatic); S.hSQuat.reserve((size_t)4 * nStatic);
+    std::atomic<int> kinChanged{0}, massChanged{0};
+    const entt::entity* trEnts = trStore.data();
+    const size_t trSize = trStore.size();
+    auto transformOf = [&](int r) -> TransformComponent& {
+        unsigned idx = S.rowTransformIdx[r];
+        if (idx >= trSize || trEnts[idx] != S.rowEntity[r]) {      // storage was reordered behind our back: re-resolve
+            idx = (unsigned)trStore.index(S.rowEntity[r]);
+            S.rowTransformIdx[r] = idx;
+        }
+        return packedAt<TransformComponent>(trStore, idx);
+    };
+    const bool full = S.syncMode == SYNC_FULL;
+    auto gatherDyn = [&](size_t b, size_t e) {
+        for (size_t r = b; r < e; ++r) {
+            const TransformComponent& t = transformOf((int)r);
+            const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
+            float* p = S.hPos.p + 3 * r; float* q = S.hQuat.p + 4 * r; float* v = S.hVel.p + 3 * r; float* w = S.hAng.p + 3 * r;
+            p[0] = t.position.x; p[1] = t.position.y; p[2] = t.position.z;
+            q[0] = t.orientation.x; q[1] = t.orientation.y; q[2] = t.orientation.z; q[3] = t.orientation.w;
+            v[0] = d.velocity.x; v[1] = d.velocity.y; v[2] = d.velocity.z;
+            w[0] = d.angularVelocity.x; w[1] = d.angularVelocity.y; w[2] = d.angularVelocity.z;
+            // fields the reference reads live every step (Physecs.cpp:219-226, :446-467): detect direct writes
+            int k = d.isKinematic ? 1 : 0;
+            if (k != S.kin[r]) { S.kin[r] = k; kinChanged.store(1, std::memory_order_relaxed); }
+            if (d.invMass != S.invMass[r] || std::memcmp(&d.com, &S.com[3 * r], sizeof(float) * 3) || std::memcmp(&d.invInertiaTensor, &S.invI[9 * r], sizeof(float) * 9)) {
+                S.invMass[r] = d.invMass;
+                std::memcpy(&S.com[3 * r], &d.com, sizeof(float) * 3);
+                std::memcpy(&S.invI[9 * r], &d.invInertiaTensor, sizeof(float) * 9);
+                massChanged.store(1, std::memory_order_relaxed);
+            }
+        }
+    };
+    if (full) {
+        S.workers.parallelFor((size_t)nDyn, gatherDyn);
+        S.workers.parallelFor((size_t)nStatic, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+                const TransformComponent& t = transformOf(nDyn + (int)i);
+                float* p = S.hSPos.p + 3 * i; float* q = S.hSQuat.p + 4 * i;
+                p[0] = t.position.x; p[1] = t.position.y; p[2] = t.position.z;
+                q[0] = t.orientation.x; q[1] = t.orientation.y; q[2] = t.orientation.z; q[3] = t.orientation.w;
+            }
+        });
+    } else if (!S.touched.empty()) {
+        // device-authoritative: the staging buffers still hold the previous step's result; refresh only announced rows
+        if (!S.stagingValid) S.workers.parallelFor((size_t)nDyn, gatherDyn);
+        else for (unsigned r : S.touched) if ((int)r < nDyn) gatherDyn(r, r + 1);
+    }
+    if (kinChanged.load()) S.check(pb_set_kinematic(S.ctx, nDyn, S.kin.data()), "pb_set_kinematic");
+    if (massChanged.load()) S.check(pb_set_mass(S.ctx, nDyn, S.invMass.data(), S.com.data(), S.invI.data()), "pb_set_mass");
+    const double gatherMs = msSince(tGather);
+
+    // ---- device step ---------------------------------------------------------------------------------------------------------------
+    if (full || !S.touched.empty()) {
+        S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
+        if (full) S.check(pb_set_static_poses(S.ctx, nStatic, S.hSPos.p, S.hSQuat.p), "pb_set_static_poses");
+    }
+    S.touched.clear();
+    int rc = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
+    for (int attempt = 0; rc == PB_ECAPACITY && attempt < 4; ++attempt) {
+        // a per-step arena overflowed.  Nothing persistent was touched (poses, bounds and the contact cache change only
+        // after the narrowphase has fitted), so enlarge the arenas in place and run the step again.  The device counters
+        // keep counting past the capacity, so they tell how much room the step needs.
+        pb_counts need{};
+        pb_get_counts(S.ctx, &need);
+        int wantP = std::max(S.caps.max_pairs, need.n_pairs + need.n_pairs / 2 + 1024);
+        int wantM = std::max(S.caps.max_manifolds, need.n_manifolds + need.n_manifolds / 2 + 1024);
+        if (need.n_pairs <= S.caps.max_pairs && need.n_manifolds <= S.caps.max_manifolds) break;   // not an arena problem (triangle contacts per pair)
+        S.check(pb_grow_arenas(S.ctx, wantP, wantM), "pb_grow_arenas");
+        S.caps.max_pairs = S.wantPairs = wantP; S.caps.max_manifolds = S.wantManifolds = wantM;
+        rc = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
+    }
+    S.check(rc, "pb_step");
+    S.check(pb_get_state(S.ctx, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_get_state");
+    S.stagingValid = true;
+
+    // ---- scatter: pinned SoA -> registry (kinematic bodies are not integrated, Physecs.cpp:446, :497) ---------------------------
+    auto tScatter = Clock::now();
+    S.workers.parallelFor((size_t)nDyn, [&](size_t b, size_t e) {
+        for (size_t r = b; r < e; ++r) {
+            if (S.kin[r]) continue;
+            TransformComponent& t = transformOf((int)r);
+            RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
+            const float* p = S.hPos.p + 3 * r; const float* q = S.hQuat.p + 4 * r; const float* v = S.hVel.p + 3 * r; const float* w = S.hAng.p + 3 * r;
+            t.position = glm::vec3(p[0], p[1], p[2]);
+            t.orientation = glm::quat(q[3], q[0], q[1], q[2]);
+            d.velocity = glm::vec3(v[0], v[1], v[2]);
+            d.angularVelocity = glm::vec3(w[0], w[1], w[2]);
+        }
+    });
+    const double scatterMs = msSince(tScatter);
+
+    // ---- triggers: enter / exit diff against the previous step (Physecs.cpp:538-553) ---------------------------------------------
+    pb_counts counts{};
+    pb_get_counts(S.ctx, &counts);
+    if (counts.n_triggers > 0 || !S.triggerCache.empty()) {
+        std::vector<std::array<int, 4>> cur((size_t)std::max(counts.n_triggers, 0));
+        int got = 0;
+        if (counts.n_triggers > 0) S.check(pb_get_triggers(S.ctx, &cur[0][0], counts.n_triggers, &got), "pb_get_triggers");
+        cur.resize((size_t)got);
+        std::sort(cur.begin(), cur.end());
+        std::vector<std::array<int, 4>> entered, exited;
+        std::set_difference(cur.begin(), cur.end(), S.triggerCache.begin(), S.triggerCache.end(), std::back_inserter(entered));
+        std::set_difference(S.triggerCache.begin(), S.triggerCache.end(), cur.begin(), cur.end(), std::back_inserter(exited));
+        S.triggerCache.swap(cur);
+        auto listenersIn = S.enterListeners;     // listeners may unregister themselves from inside a callback
+        auto listenersOut = S.exitListeners;
+        for (auto& t : entered) for (auto* l : listenersIn) l->onTriggerEnter((entt::entity)(unsigned)t[0], t[1], (entt::entity)(unsigned)t[2], t[3]);
+        for (auto& t : exited) for (auto* l : listenersOut) l->onTriggerExit((entt::entity)(unsigned)t[0], t[1], (entt::entity)(unsigned)t[2], t[3]);
+    }
+
+    pb_timings tm{};
+    pb_get_timings(S.ctx, &tm);
+    S.stats = { counts.n_pairs, counts.n_manifolds, counts.n_points, counts.n_colors, counts.n_triggers, tm.total, gatherMs, scatterMs, msSince(tStart) };
+}
+
+} // namespace physecs

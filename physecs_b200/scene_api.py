@@ -1,0 +1,191 @@
+"""ctypes face of the host C++ layer: physecs::Scene over an entt::registry (include/Physecs/Physecs.h of this repo,
+physecs_b200/host/*.cpp), reached through the flat entry points of physecs_b200/host/scene_harness.cpp.
+
+This is the public API an application uses -- registry components in, Scene::simulate, registry components out -- so
+the parity tests and bench.py's scene-level end-to-end number go through it.  The library is built by build.py when
+EnTT / GLM headers are available (they are the application's own dependency, not vendored here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphysecs_b200_scene.so")
+
+EXPORTS = [
+    "psh_create", "psh_destroy", "psh_last_error", "psh_add_convex", "psh_add_trimesh", "psh_add_entities", "psh_destroy_entity",
+    "psh_add_collider", "psh_clear_colliders", "psh_add_joint", "psh_set_revolute_drive", "psh_destroy_joint", "psh_set_params",
+    "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter", "psh_record_trigger_events",
+    "psh_take_trigger_events", "psh_set_state", "psh_simulate", "psh_num_entities", "psh_get_state", "psh_native_context",
+    "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity",
+]
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python build.py` where EnTT and GLM headers are available")
+    capi.load_library()   # libphysecs_b200.so first (the scene library links against it)
+    lib = C.CDLL(LIB_PATH)
+    lib.psh_create.restype = C.c_void_p
+    lib.psh_destroy.restype = None
+    lib.psh_last_error.restype = C.c_char_p
+    lib.psh_simulate.restype = C.c_double
+    lib.psh_native_context.restype = C.c_void_p
+    for f in ("psh_set_params", "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter",
+              "psh_record_trigger_events", "psh_set_state", "psh_get_state", "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity"):
+        getattr(lib, f).restype = None
+    _lib = lib
+    return lib
+
+
+def _p(a, ct=C.c_float):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def _f(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+class SceneError(RuntimeError):
+    pass
+
+
+class HostScene:
+    """physecs::Scene (this repo's) over a registry filled from a SceneDesc, entity id == description index."""
+
+    def __init__(self, desc, num_threads=0, device=0):
+        self.lib = load_library()
+        self.desc = desc
+        self.h = C.c_void_p(self.lib.psh_create(int(num_threads), int(device)))
+        d = desc
+        for m in d.convex:
+            self.lib.psh_add_convex(self.h, _p(_f(m.verts)), len(m.verts), _p(_i(m.face_offsets), C.c_int), _p(_i(m.face_indices), C.c_int),
+                                    len(m.face_offsets) - 1, _p(_f(m.face_normals)), _p(_f(m.face_centroids)))
+        for m in d.trimesh:
+            idx = np.ascontiguousarray(m.indices, np.uint32)
+            self.lib.psh_add_trimesh(self.h, _p(_f(m.verts)), len(m.verts), _p(idx, C.c_uint), len(idx))
+        self.lib.psh_add_entities(self.h, d.n, _p(_f(d.pos)), _p(_f(d.quat)), _p(_i(d.flags), C.c_int), _p(_f(d.vel)), _p(_f(d.angvel)),
+                                  _p(_f(d.inv_mass)), _p(_f(d.com)), _p(_f(d.inv_inertia)), _p(_i(d.col_offsets), C.c_int), _p(_f(d.col_lpos)),
+                                  _p(_f(d.col_lquat)), _p(_i(d.col_type), C.c_int), _p(_f(d.col_params)), _p(_i(d.col_mesh), C.c_int),
+                                  _p(_f(d.col_material)), _p(_i(d.col_flags), C.c_int), _p(_i(d.col_data), C.c_int))
+        self.joint_colors = []
+        for (t, e0, a0p, a0q, e1, a1p, a1q, prm) in d.joints:
+            self.joint_colors.append(self.lib.psh_add_joint(self.h, int(t), int(e0), _p(_f(a0p)), _p(_f(a0q)), int(e1), _p(_f(a1p)), _p(_f(a1q)), _p(_f(prm))))
+        for (e0, e1) in d.no_collide:
+            self.lib.psh_set_can_collide(self.h, int(e0), int(e1), 0)
+        self.lib.psh_set_params(self.h, int(d.substeps), int(d.iterations), C.c_float(d.gravity))
+        self.n = d.n
+
+    def close(self):
+        if self.h:
+            self.lib.psh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return self.lib.psh_last_error(self.h).decode()
+
+    def simulate(self, dt=None):
+        ms = float(self.lib.psh_simulate(self.h, C.c_float(self.desc.dt if dt is None else dt)))
+        if ms < 0:
+            raise SceneError(self._err())
+        return ms
+
+    def get_state(self):
+        n = self.lib.psh_num_entities(self.h)
+        pos = np.zeros((n, 3), np.float32); quat = np.zeros((n, 4), np.float32)
+        vel = np.zeros((n, 3), np.float32); ang = np.zeros((n, 3), np.float32)
+        self.lib.psh_get_state(self.h, _p(pos), _p(quat), _p(vel), _p(ang))
+        return pos, quat, vel, ang
+
+    def set_state(self, ents, pos, quat, vel=None, angvel=None, patch=False):
+        e = _i(ents)
+        self.lib.psh_set_state(self.h, len(e), _p(e, C.c_int), _p(_f(pos)), _p(_f(quat)), _p(_f(vel)) if vel is not None else None,
+                               _p(_f(angvel)) if angvel is not None else None, int(patch))
+
+    def set_kinematic(self, e, kin):
+        self.lib.psh_set_kinematic(self.h, int(e), int(kin))
+
+    def set_can_collide(self, e0, e1, can):
+        self.lib.psh_set_can_collide(self.h, int(e0), int(e1), int(can))
+
+    def set_sync_mode(self, device_authoritative):
+        self.lib.psh_set_sync_mode(self.h, int(device_authoritative))
+
+    def set_arena_capacity(self, max_pairs, max_manifolds):
+        self.lib.psh_set_arena_capacity(self.h, int(max_pairs), int(max_manifolds))
+
+    def set_contact_filter(self, mode):
+        self.lib.psh_set_contact_filter(self.h, int(mode))
+
+    def record_trigger_events(self):
+        self.lib.psh_record_trigger_events(self.h)
+
+    def take_trigger_events(self):
+        cap = 1 << 16
+        out = np.zeros((cap, 5), np.int32)
+        n = self.lib.psh_take_trigger_events(self.h, _p(out, C.c_int), cap)
+        return out[:min(n, cap)]
+
+    def add_entities(self, d):
+        """Append the entities of another SceneDesc to the live registry; returns the first new entity id."""
+        first = self.lib.psh_add_entities(self.h, d.n, _p(_f(d.pos)), _p(_f(d.quat)), _p(_i(d.flags), C.c_int), _p(_f(d.vel)), _p(_f(d.angvel)),
+                                          _p(_f(d.inv_mass)), _p(_f(d.com)), _p(_f(d.inv_inertia)), _p(_i(d.col_offsets), C.c_int), _p(_f(d.col_lpos)),
+                                          _p(_f(d.col_lquat)), _p(_i(d.col_type), C.c_int), _p(_f(d.col_params)), _p(_i(d.col_mesh), C.c_int),
+                                          _p(_f(d.col_material)), _p(_i(d.col_flags), C.c_int), _p(_i(d.col_data), C.c_int))
+        self.n += d.n
+        return first
+
+    def destroy_entity(self, e):
+        self.lib.psh_destroy_entity(self.h, int(e))
+
+    def add_joint(self, t, e0, a0p, a0q, e1, a1p, a1q, prm):
+        return self.lib.psh_add_joint(self.h, int(t), int(e0), _p(_f(a0p)), _p(_f(a0q)), int(e1), _p(_f(a1p)), _p(_f(a1q)), _p(_f(prm)))
+
+    def destroy_joint(self, j):
+        self.lib.psh_destroy_joint(self.h, int(j))
+
+    def set_revolute_drive(self, j, enabled, velocity, max_torque):
+        if self.lib.psh_set_revolute_drive(self.h, int(j), int(enabled), C.c_float(velocity), C.c_float(max_torque)) != 0:
+            raise SceneError("joint is not a RevoluteJoint")
+
+    def stats(self):
+        out = (C.c_double * 9)()
+        self.lib.psh_get_stats(self.h, out)
+        names = ["pairs", "manifolds", "points", "colors", "triggers", "device_ms", "gather_ms", "scatter_ms", "total_ms"]
+        return {k: out[i] for i, k in enumerate(names)}
+
+    def mass_props(self, e, mass):
+        com = np.zeros(3, np.float32); inv = np.zeros(9, np.float32)
+        self.lib.psh_mass_props(self.h, int(e), C.c_float(mass), _p(com), _p(inv))
+        return com, inv
+
+    def taps(self):
+        """Parity taps on the Scene's device context (pairs / manifolds / triggers of the last step)."""
+        ptr = self.lib.psh_native_context(self.h)
+        if not ptr:
+            raise SceneError("the Scene has no device context yet (call simulate first)")
+        return capi.Context.from_handle(ptr, self.desc)
