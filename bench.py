@@ -9,8 +9,8 @@ physecs::Scene::simulate(1/60): broadphase -> narrowphase -> contact build -> su
 Lines printed (one JSON object, rank 0):
   value   body-steps/s with the scene resident in HBM (pb_step only), CUDA events on the context's stream
   e2e     the same metric through the C ABI with HOST buffers: pb_set_state (H2D) + pb_step + pb_get_state (D2H) per step
-  roofline  dominant kernel = k_contact_solve (one colour batch per launch): algorithmic bytes (SURVEY.md §8d:
-            180 + 140*points per manifold per pass) / measured launch time, against MEASURED_PEAKS.json hbm_gbs
+  roofline  dominant kernel = k_substeps (the persistent substep solver, one launch per step): algorithmic bytes
+            (SURVEY.md §8d per-unit figures x units, summed over its phases) / CUDA-event launch time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, "reference + hash fix" build) on a bounded sample
 
 `--impl reference` times the reference CPU implementation itself on the host cores (bounded sample of the same workload).
@@ -204,9 +204,7 @@ def main():
         ctx.lib.pb_profiler_range(1)
     e0.record(stream)
     for _ in range(args.steps):
-        ctx.step()
-        c = ctx.counts()
-        sumM += c.n_manifolds; sumP += c.n_points; sumC += c.n_colors; sumPairs += c.n_pairs
+        ctx.step()       # no read-back inside the timed loop: the counters stay on the device
     e1.record(stream)
     barrier(); torch.cuda.synchronize()
     if args.ncu:
@@ -214,30 +212,53 @@ def main():
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launches() - launches0
+    c = ctx.counts()     # the scene is settled: the last step's counts stand for the timed region
+    sumM, sumP, sumC, sumPairs = c.n_manifolds * args.steps, c.n_points * args.steps, c.n_colors * args.steps, c.n_pairs * args.steps
     prof = ctx.profile()
     ctx.set_profile(False)
     t = ctx.timings()
+    # duration of the dominant kernel by CUDA events on its stream: a few extra steps, each read back (outside the timed region)
+    kernel_ms = []
+    for _ in range(min(args.steps, 20)):
+        ctx.step()
+        kernel_ms.append(ctx.timings().solve_kernel)
+    kernel_ms = float(np.mean(kernel_ms))
     ms_per_step = ms_total / args.steps
     value = world * n_dyn * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_contact_solve) ----------------------------------------------------------
+    # ---- roofline of the dominant kernel: k_substeps, the persistent substep solver (one launch per step) ------------------
+    # algorithmic bytes per launch (per substep): bodies 140 (integrate v) + 120 (integrate x) B/body;
+    # contact prep 244 + 156 p B/manifold; contact solve pass 180 + 140 p B/manifold, (iterations + 1) passes.
     peak, peak_src = peaks()
-    pass_ms, n_pass = prof["solve_pass"]
+    S_, I_ = desc.substeps, desc.iterations
     avgM, avgP, avgC = sumM / args.steps, sumP / args.steps, max(sumC / args.steps, 1.0)
-    bytes_per_pass = 180.0 * avgM + 140.0 * avgP
-    pass_avg_ms = pass_ms / max(n_pass, 1)
-    achieved = bytes_per_pass / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+    bytes_bodies = 260.0 * n_dyn * S_
+    bytes_prep = (244.0 * avgM + 156.0 * avgP) * S_
+    bytes_pass = (180.0 * avgM + 140.0 * avgP)
+    bytes_solve = bytes_pass * (I_ + 1) * S_
+    bytes_launch = bytes_bodies + bytes_prep + bytes_solve
+    phase_ms = {k: v[0] / args.steps for k, v in prof.items()}
+    launch_ms = kernel_ms                  # CUDA events around the k_substeps launch, on the context's stream
+    stamp_ms = sum(phase_ms.values())      # the same from CTA 0's %globaltimer stamps at every grid barrier (splits the launch into phases)
+    achieved = bytes_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    pass_ms = phase_ms.get("contact_pass", 0.0)
+    pass_gbs = bytes_solve / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    prep_ms = phase_ms.get("prep", 0.0)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_contact_solve_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_substeps_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_contact_solve", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_per_pass / avgC, "launch_ms": pass_avg_ms / avgC,
-                "launches_timed": int(n_pass * avgC), "share_of_step": pass_ms / ms_total,
-                "note": "algorithmic bytes = (180 + 140*points) per manifold per pass (SURVEY.md 8d); one launch = one colour batch"}
+    roofline = {"bound": "hbm", "kernel": "k_substeps", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_launch, "launch_ms": launch_ms,
+                "launches_timed": min(args.steps, 20), "share_of_step": launch_ms / ms_per_step, "launch_ms_from_phase_stamps": stamp_ms,
+                "phases": {"contact_solve_passes": {"ms": pass_ms, "GB/s": pass_gbs, "frac": pass_gbs / peak, "bytes": bytes_solve},
+                           "contact_prep": {"ms": prep_ms, "GB/s": bytes_prep / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0, "bytes": bytes_prep},
+                           "integrate": {"ms": phase_ms.get("integrate_v", 0.0) + phase_ms.get("integrate_x", 0.0), "bytes": bytes_bodies}},
+                "note": "one launch = the whole TGS substep loop of a step (persistent cooperative kernel, grid barriers between phases); "
+                        "algorithmic bytes = sum over phases of SURVEY.md 8d's per-unit figures x units; duration = in-kernel phase stamps"}
 
     # ---- timed region B: end to end through the C ABI with pinned host buffers --------------------------------------
     pos_t = torch.empty((n_dyn, 3), dtype=torch.float32).pin_memory(); quat_t = torch.empty((n_dyn, 4), dtype=torch.float32).pin_memory()
@@ -274,7 +295,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "phase_ms_last_step": {"broadphase": t.broadphase, "narrowphase": t.narrowphase, "contact_build": t.contact_build, "solve": t.solve, "total": t.total},
-        "stage_ms_per_step": {"solve_passes": pass_ms / args.steps, "contact_prep": prof["contact_prep"][0] / args.steps},
+        "stage_ms_per_step": phase_ms,
     }
 
     ctx.close()

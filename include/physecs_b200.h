@@ -64,7 +64,8 @@ typedef struct pb_counts {
 /* device times of the last pb_step in milliseconds (CUDA events on the context's stream) */
 typedef struct pb_timings {
     float broadphase, narrowphase, contact_build, solve, total;
-    float reserved[3];
+    float solve_kernel;  /* the persistent substep kernel alone (k_substeps), CUDA events around its launch */
+    float reserved[2];
 } pb_timings;
 
 /* ---- context ------------------------------------------------------------------------------------ */

@@ -14,7 +14,7 @@ import numpy as np
 from . import scenes as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libphysecs_b200.so")
+LIB_PATH = os.environ.get("PHYSECS_B200_LIB") or os.path.join(_HERE, "lib", "libphysecs_b200.so")
 
 PB_OK, PB_ECUDA, PB_ECAPACITY, PB_EINVAL, PB_EUNSUPPORTED = 0, 1, 2, 3, 4
 
@@ -41,7 +41,7 @@ class Counts(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("broadphase", C.c_float), ("narrowphase", C.c_float), ("contact_build", C.c_float), ("solve", C.c_float),
-                ("total", C.c_float), ("reserved", C.c_float * 3)]
+                ("total", C.c_float), ("solve_kernel", C.c_float), ("reserved", C.c_float * 2)]
 
 
 _lib = None
@@ -265,7 +265,8 @@ class Context:
     def profile(self):
         ms = (C.c_double * 8)(); cnt = (C.c_longlong * 8)()
         self._check(self.lib.pb_get_profile(self.ctx, ms, cnt))
-        names = ["solve_pass", "contact_prep", "integrate", "joints"]
+        # (milliseconds, number of phases) per phase kind of the persistent substep kernel
+        names = ["integrate_v", "prep", "contact_pass", "joint_solve", "integrate_x"]
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
     def launches(self):

@@ -96,49 +96,26 @@ template <class T> static int uploadRaw(pb_ctx* ctx, const T* host, size_t n, T*
     return PB_OK;
 }
 
-void pb_prof_begin(pb_ctx* ctx, int kind) {
-    if (!ctx->profile) return;
-    if (ctx->profUsed + 2 > ctx->profEv.size()) {
-        size_t old = ctx->profEv.size();
-        ctx->profEv.resize(old + 512);
-        for (size_t i = old; i < ctx->profEv.size(); ++i) cudaEventCreate(&ctx->profEv[i]);
-    }
-    ctx->profKind.push_back(kind);
-    cudaEventRecord(ctx->profEv[ctx->profUsed], ctx->stream);
-}
-void pb_prof_end(pb_ctx* ctx) {
-    if (!ctx->profile) return;
-    cudaEventRecord(ctx->profEv[ctx->profUsed + 1], ctx->stream);
-    ctx->profUsed += 2;
-}
-static void profCollect(pb_ctx* ctx) {
-    for (size_t i = 0; i + 1 < ctx->profUsed + 1 && i / 2 < ctx->profKind.size(); i += 2) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->profEv[i], ctx->profEv[i + 1]);
-        int k = ctx->profKind[i / 2];
-        ctx->profMs[k] += ms; ctx->profCount[k] += 1;
-    }
-    ctx->profUsed = 0; ctx->profKind.clear();
-}
-
 extern "C" {
 
-// enable/disable per-stage event profiling; enabling resets the accumulators
+// enable/disable per-phase timing inside the persistent substep kernel (CTA 0 stamps %globaltimer at every grid barrier);
+// enabling resets the accumulators
 int pb_set_profile(pb_ctx* ctx, int on) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->profile = on != 0;
-    ctx->profUsed = 0; ctx->profKind.clear();
-    for (int k = 0; k < PROF_COUNT; ++k) { ctx->profMs[k] = 0; ctx->profCount[k] = 0; }
-    return PB_OK;
+    unsigned long long tmp[16];
+    return pb_solve_profile(ctx, tmp, true);
 }
-// accumulated stage times since pb_set_profile(1): ms[8], count[8] indexed by stage id
-// (0 = contact solve pass over all colours, 1 = contact prep, 2 = body integration, 3 = joints)
+// accumulated phase times since pb_set_profile(1): ms8 / count8 indexed by phase kind
+// (0 = integrate velocities, 1 = contact + joint prep, 2 = contact solve colour phases, 3 = joint solve, 4 = integrate positions);
+// count = number of phases (grid barriers) of that kind
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
     cudaSetDevice(ctx->device);
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    profCollect(ctx);
-    for (int k = 0; k < PROF_COUNT; ++k) { ms8[k] = ctx->profMs[k]; count8[k] = ctx->profCount[k]; }
+    unsigned long long raw[16] = {0};
+    int rc = pb_solve_profile(ctx, raw, false);
+    if (rc) return rc;
+    for (int k = 0; k < 8; ++k) { ms8[k] = k < 5 ? raw[k] * 1e-6 : 0.0; count8[k] = k < 5 ? (long long)raw[5 + k] : 0; }
     return PB_OK;
 }
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
@@ -177,7 +154,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     A(nodeLeft, C); A(nodeRight, C); A(nodeParent, C); A(leafParent, C); A(nodeFlag, C); A(nodeMin, 2 * C); A(nodeMax, 2 * C);
     A(pairs, P); A(pairOrder, 2 * P); A(trigPairs, P); A(colClass, C);
     A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
-    A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
+    A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
     const size_t PT = 4 * M;
     for (int b = 0; b < 2; ++b) { A(pR0T[b], PT); A(cPointOfsBuf[b], M + 1); A(cNpBuf[b], M + 1); }
     A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
@@ -210,7 +187,7 @@ int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
         ctx->radixTiles = (int)((sortMax + 511) / 512);
         A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
         A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
-        A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
+        A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
         const size_t PT = 4 * M, oldPT = 4 * oldM;
         A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
         const int keep = ctx->curBuf, other = keep ^ 1;
@@ -253,10 +230,10 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
-    F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
+    F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
-    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut);
+    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
@@ -560,14 +537,9 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     ctx->curBuf ^= 1;
     if ((rc = pb_contact_build(ctx, nRaw))) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
-    if (nRaw > 0) { if ((rc = readCounters(ctx))) return rc; }
-    ctx->lastCounts.n_manifolds = nRaw > 0 ? ctx->hCounters[CNT_MANIFOLDS] : 0;
-    ctx->lastCounts.n_colors = nRaw > 0 ? ctx->hCounters[CNT_NCOLORS] : 0;
-    ctx->lastCounts.n_overflow = nRaw > 0 ? ctx->hCounters[CNT_OVERFLOW] : 0;
-    ctx->lastCounts.n_points = nRaw > 0 ? ctx->hCounters[CNT_POINTS] : 0;
+    ctx->countsStale = nRaw > 0;     // manifold / colour / point counts stay on the device until someone asks (pb_get_counts)
     if ((rc = pb_joint_begin_step(ctx))) return rc;
-    if (ctx->profile && ctx->profUsed > 4096) { cudaStreamSynchronize(ctx->stream); profCollect(ctx); }
-    if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
+    if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity, nRaw))) return rc;
     ctx->cacheValid = true;
     ctx->cacheBuilt = true;
     // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
@@ -699,7 +671,25 @@ int pb_get_triggers(pb_ctx* ctx, int* out4, int cap, int* n) {
     return PB_OK;
 }
 
-int pb_get_counts(pb_ctx* ctx, pb_counts* out) { *out = ctx->lastCounts; return PB_OK; }
+// post-build counters (manifolds with points, colours, points) are produced on the device after the last host sync of the
+// step; they are fetched on demand so a plain simulate loop never waits for them
+static int refreshCounts(pb_ctx* ctx) {
+    if (!ctx->countsStale) return PB_OK;
+    int rc = readCounters(ctx); if (rc) return rc;
+    ctx->lastCounts.n_manifolds = ctx->hCounters[CNT_MANIFOLDS];
+    ctx->lastCounts.n_colors = ctx->hCounters[CNT_NCOLORS];
+    ctx->lastCounts.n_overflow = ctx->hCounters[CNT_OVERFLOW];
+    ctx->lastCounts.n_points = ctx->hCounters[CNT_POINTS];
+    ctx->countsStale = false;
+    return PB_OK;
+}
+
+int pb_get_counts(pb_ctx* ctx, pb_counts* out) {
+    cudaSetDevice(ctx->device);
+    int rc = refreshCounts(ctx);
+    *out = ctx->lastCounts;
+    return rc;
+}
 
 int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
     cudaSetDevice(ctx->device);
@@ -710,6 +700,7 @@ int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
     cudaEventElapsedTime(&t.contact_build, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&t.solve, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&t.total, ctx->ev[0], ctx->ev[4]);
+    if (ctx->nDyn > 0) cudaEventElapsedTime(&t.solve_kernel, ctx->ev[5], ctx->ev[6]);
     *out = t;
     return PB_OK;
 }
@@ -749,6 +740,7 @@ int pb_get_bounds(pb_ctx* ctx, float* out6) {
 int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* normal3, float* points24, int* color, int* n) {
     cudaSetDevice(ctx->device);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { int rc = refreshCounts(ctx); if (rc) return rc; }
     int nm = ctx->lastCounts.n_manifolds;
     *n = nm;
     if (nm == 0 || cap == 0) return PB_OK;

@@ -20,13 +20,15 @@
 #define COLF_ENABLE 2
 #define COLF_DYNAMIC 4
 
-enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH, BIN_MESHH, BIN_TRIGGER, BIN_COUNT };
+// mesh bins are split by the dynamic shape's type so every warp of a mesh launch runs one triangle routine
+enum { BIN_SS = 0, BIN_SC, BIN_CC, BIN_SB, BIN_CB, BIN_BB, BIN_GJK, BIN_MESH_S, BIN_MESH_C, BIN_MESH_B, BIN_MESH_X, BIN_TRIGGER, BIN_COUNT };
+#define PB_MAX_TRI_CAND 128   // BVH leaf triangles visited per (shape, mesh) pair before the per-triangle tests
 
 __device__ __forceinline__ int binOf(int t0, int t1) {
     if (t0 == PB_TRIANGLE_MESH || t1 == PB_TRIANGLE_MESH) {
         if (t0 == t1) return -1;
         int other = t0 == PB_TRIANGLE_MESH ? t1 : t0;
-        return (other == PB_SPHERE || other == PB_CAPSULE) ? BIN_MESH : BIN_MESHH;   // box / convex vs mesh: GJK-sized scratch
+        return BIN_MESH_S + other;   // sphere, capsule, box, convex (box / convex need GJK-sized scratch)
     }
     if (t0 == PB_CONVEX_MESH || t1 == PB_CONVEX_MESH) return BIN_GJK;
     int lo = min(t0, t1), hi = max(t0, t1);
@@ -82,7 +84,7 @@ __global__ void k_bin_starts(int* counters) {
         int run = 0;
         for (int b = 0; b < BIN_COUNT; ++b) { counters[CNT_BINSTART + b] = run; run += counters[CNT_BIN0 + b]; counters[CNT_BIN0 + b] = 0; }
         counters[CNT_BINSTART + BIN_COUNT] = run;
-        counters[CNT_MESH_PAIRS] = counters[CNT_BINSTART + BIN_TRIGGER] - counters[CNT_BINSTART + BIN_MESH];
+        counters[CNT_MESH_PAIRS] = counters[CNT_BINSTART + BIN_TRIGGER] - counters[CNT_BINSTART + BIN_MESH_S];
     }
 }
 
@@ -176,61 +178,72 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
 // ---- mesh bins -------------------------------------------------------------------------------------------------------
 // Collect triangle contacts of one (shape, mesh) pair in the reference's traversal order (TriangleMesh.cpp:166-192:
 // explicit stack, left child popped first; CollisionTriangleMesh.cpp:895-907).
-template <bool HEAVY>
-__device__ inline int meshCollect(int type, float4 prm, V3 localPos, Q4 localOr, const PbTriMeshDev& mesh,
+template <int TYPE>
+__device__ inline int meshCollect(float4 prm, V3 localPos, Q4 localOr, const PbTriMeshDev& mesh,
                                   const PbConvexDev* convexes, int convexId, TriContact* contacts, bool* overflow, Epa* scratch, int* counters) {
-    Aabb lb = shapeBounds(localPos, localOr, type, prm, convexes, convexId);
+    constexpr bool HEAVY = TYPE >= PB_BOX;
+    Aabb lb = shapeBounds(localPos, localOr, TYPE, prm, convexes, convexId);
     Shape convexShape;
-    if (HEAVY && type == PB_CONVEX_MESH) convexShape = makeShape(type, prm, localPos, localOr, convexes, convexId);
-    int stack[64];
-    int sp = 0;
-    stack[sp++] = 0;
-    int cnt = 0;
-    while (sp > 0) {
-        int node = stack[--sp];
-        float4 nmn = mesh.nodeMin[node], nmx = mesh.nodeMax[node];
-        if (lb.mx.x < nmn.x || lb.mn.x > nmx.x) continue;      // physecs::intersects (BoundsUtil.cpp:87-92)
-        if (lb.mx.y < nmn.y || lb.mn.y > nmx.y) continue;
-        if (lb.mx.z < nmn.z || lb.mn.z > nmx.z) continue;
-        int triCount = __float_as_int(nmn.w), index = __float_as_int(nmx.w);
-        if (triCount) {
-            for (int k = 0; k < triCount; ++k) {
-                int tri = index + k;
-                int4 ti = mesh.tris[tri];
-                V3 a = mk3(mesh.verts[ti.x]), b = mk3(mesh.verts[ti.y]), c = mk3(mesh.verts[ti.z]);
-                V3 n = mk3(mesh.triNormal[tri]);
-                TriContact tc;
-                tc.boxFeature = 0; tc.boxAxis = 0; tc.fidx = 0; tc.feature = TF_FACE; tc.dist = 0.f;
-                tc.normal = tc.cpBody = tc.cpTri = mk3(0.f);
-                bool hit = false;
-                if (!HEAVY) {
-                    if (type == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, a, b, c, n, tc);
-                    else hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, a, b, c, n, tc);
-                } else {
-                    if (type == PB_BOX) hit = boxTriangle(localPos, localOr, mk3(prm.x, prm.y, prm.z), a, b, c, n, tc);
-                    else hit = convexTriangle(convexShape, a, b, c, mk3(mesh.triCentroid[tri]), tc, *scratch, counters);
-                }
-                if (hit) {
-                    tc.tri = tri;
-                    if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
+    if (TYPE == PB_CONVEX_MESH) convexShape = makeShape(TYPE, prm, localPos, localOr, convexes, convexId);
+    // pass A: BVH cull only.  Leaf triangles are recorded in visiting order; keeping the tests out of this loop lets the
+    // lanes of a warp walk their (different-depth) trees without dragging the long triangle routines through every branch.
+    int cand[PB_MAX_TRI_CAND];
+    int nc = 0;
+    {
+        int stack[64];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp > 0) {
+            int node = stack[--sp];
+            float4 nmn = mesh.nodeMin[node], nmx = mesh.nodeMax[node];
+            if (lb.mx.x < nmn.x || lb.mn.x > nmx.x) continue;      // physecs::intersects (BoundsUtil.cpp:87-92)
+            if (lb.mx.y < nmn.y || lb.mn.y > nmx.y) continue;
+            if (lb.mx.z < nmn.z || lb.mn.z > nmx.z) continue;
+            int triCount = __float_as_int(nmn.w), index = __float_as_int(nmx.w);
+            if (triCount) {
+                for (int k = 0; k < triCount; ++k) {
+                    if (nc < PB_MAX_TRI_CAND) cand[nc++] = index + k;
                     else *overflow = true;
                 }
+            } else {
+                if (sp + 2 <= 64) { stack[sp++] = index + 1; stack[sp++] = index; }
+                else *overflow = true;
             }
-        } else {
-            if (sp + 2 <= 64) { stack[sp++] = index + 1; stack[sp++] = index; }
+        }
+    }
+    // pass B: per-triangle tests, in the visiting order (== the reference's overlapBvh order, which fixes contact order)
+    int cnt = 0;
+    for (int i = 0; i < nc; ++i) {
+        int tri = cand[i];
+        int4 ti = mesh.tris[tri];
+        V3 a = mk3(mesh.verts[ti.x]), b = mk3(mesh.verts[ti.y]), c = mk3(mesh.verts[ti.z]);
+        V3 n = mk3(mesh.triNormal[tri]);
+        TriContact tc;
+        tc.boxFeature = 0; tc.boxAxis = 0; tc.fidx = 0; tc.feature = TF_FACE; tc.dist = 0.f;
+        tc.normal = tc.cpBody = tc.cpTri = mk3(0.f);
+        bool hit;
+        if (TYPE == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, a, b, c, n, tc);
+        else if (TYPE == PB_CAPSULE) hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, a, b, c, n, tc);
+        else if (TYPE == PB_BOX) hit = boxTriangle(localPos, localOr, mk3(prm.x, prm.y, prm.z), a, b, c, n, tc);
+        else hit = convexTriangle(convexShape, a, b, c, mk3(mesh.triCentroid[tri]), tc, *scratch, counters);
+        if (hit) {
+            tc.tri = tri;
+            if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
             else *overflow = true;
         }
     }
+    (void)HEAVY;
     return cnt;
 }
 
-template <bool HEAVY>
+template <int TYPE>
 __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
                                                  const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                  const PbTriMeshDev* __restrict__ meshes, const PbConvexDev* __restrict__ convexes,
                                                  int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
-    const int BIN = HEAVY ? BIN_MESHH : BIN_MESH;
+    constexpr bool HEAVY = TYPE >= PB_BOX;
+    const int BIN = BIN_MESH_S + TYPE;
     int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
     int lane = threadIdx.x & 31;
     for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
@@ -238,7 +251,8 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
         TriContact contacts[PB_MAX_TRI_CONTACTS];
         unsigned char order[PB_MAX_TRI_CONTACTS];   // generation order: >=0 index into contacts
         int nGen = 0;
-        int a = 0, b = 0, shape = 0, type = 0;
+        int a = 0, b = 0, shape = 0;
+        const int type = TYPE;
         bool flip = false;
         V3 pos1 = mk3(0.f), localPos = mk3(0.f); Q4 or1 = mkq(make_float4(0, 0, 0, 1)), localOr = or1;
         float4 prm = make_float4(0, 0, 0, 0);
@@ -250,7 +264,6 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             flip = colType[a] == PB_TRIANGLE_MESH;
             shape = flip ? b : a;
             int meshCol = flip ? a : b;
-            type = colType[shape];
             prm = colParams[shape];
             meshId = colMesh[meshCol];
             V3 pos0 = mk3(wpos[shape]); Q4 or0 = mkq(wquat[shape]);
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             {
                 bool overflow = false;
                 Epa scratch;
-                int cnt = meshCollect<HEAVY>(type, prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow, HEAVY ? &scratch : nullptr, counters);
+                int cnt = meshCollect<TYPE>(prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow, HEAVY ? &scratch : nullptr, counters);
                 if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
                 // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
                 unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
@@ -374,12 +387,14 @@ int pb_narrowphase(pb_ctx* ctx) {
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
     if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
 #undef LAUNCH_PRIM
-    if (!ctx->triMeshes.empty())
-        ++ctx->launches, k_np_mesh<true><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
-                                                   ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
-    if (!ctx->triMeshes.empty())
-        ++ctx->launches, k_np_mesh<false><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
-                                                   ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
+#define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
+        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
+    if (!ctx->triMeshes.empty()) {
+        // heavy shapes first: their long threads overlap with the tail of nothing else, the light bins fill in after
+        if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
+        LAUNCH_MESH(PB_BOX); LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE);
+    }
+#undef LAUNCH_MESH
     if (ctx->triggersPossible)
         ++ctx->launches, k_np_trigger<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                     ctx->colWQuat, ctx->convexDev, ctx->trigPairs, ctx->caps.max_pairs);

@@ -119,6 +119,7 @@ struct pb_ctx {
     int* mSortTmp = nullptr; unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
 
     // ---- contact constraints (solve order) ---------------------------------------------------------------
+    int4* cHead = nullptr;           // packed solve header: b0, b1, first point, numPoints | isSoft << 8 (one 16-byte load)
     int2* cBodies = nullptr;         // solver body index or -1 (b0, b1)
     int2* cRowsT = nullptr;          // transform rows (row0, row1)
     float4* cNormal = nullptr;       // n xyz, friction w
@@ -152,25 +153,18 @@ struct pb_ctx {
     int* hCounters = nullptr;        // pinned mirror
     pb_counts lastCounts{};
     pb_timings lastTimings{};
-    cudaEvent_t ev[6] = {nullptr};
+    cudaEvent_t ev[8] = {nullptr};
     // contact filter (Physecs.cpp:200): optional K x K table over (isTrigger, data) classes; nullptr = defaultContactFilter
     int* colClass = nullptr; unsigned char* filterLut = nullptr; int nFilterClasses = 0;
     bool anyTriggerFlag = false, triggersPossible = false;
     int2* trigPairs = nullptr;       // [maxPairs] overlapping TRIGGER pairs of the last step (collider indices)
+    // persistent substep kernel (solver.cu)
+    int solveGrid = 0; unsigned int* solveBarrier = nullptr; unsigned long long* solveProfNs = nullptr;
+    bool countsStale = false;        // lastCounts lacks the post-build numbers until the counters are read back
     unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
-    // optional per-stage event profiling (pb_set_profile): events recorded around stage groups, summed lazily
-    bool profile = false;
-    std::vector<cudaEvent_t> profEv;  // pairs (begin, end)
-    std::vector<int> profKind;        // stage id per pair
-    size_t profUsed = 0;
-    double profMs[8] = {0};
-    long long profCount[8] = {0};
+    bool profile = false;            // per-phase device timing inside the persistent substep kernel (pb_set_profile)
 };
 
-// profiling stage ids
-enum { PROF_SOLVE_PASS = 0, PROF_CONTACT_PREP = 1, PROF_INTEGRATE = 2, PROF_JOINTS = 3, PROF_COUNT = 8 };
-void pb_prof_begin(pb_ctx* ctx, int kind);
-void pb_prof_end(pb_ctx* ctx);
 
 // ---- helpers --------------------------------------------------------------------------------------------------
 int pb_fail(pb_ctx* ctx, int code, const std::string& msg);
@@ -194,7 +188,8 @@ int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);
 int pb_world_poses(pb_ctx* ctx);
 int pb_narrowphase(pb_ctx* ctx);
 int pb_contact_build(pb_ctx* ctx, int nRaw);
-int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
+int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound);
+int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset);
 int pb_joint_begin_step(pb_ctx* ctx);
 int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew);
 void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long* oldTag, const int4* oldVal, int newSize, unsigned long long* newTag, int4* newVal);

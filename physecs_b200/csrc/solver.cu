@@ -1,24 +1,69 @@
-// TGS "soft step" substep loop on the device.
+// TGS "soft step" substep loop on the device -- per substep: two streaming kernels + ONE persistent cooperative kernel for
+// everything that is ordered by constraint colour.
 //
-// Per substep (reference src/Physecs.cpp:364-531):
-//   k_integrate_v     gravity + implicit gyroscopic update, massTemp (world inverse inertia), reset pseudo velocities  :443-468
-//   k_contact_prep    world arms, separation, r x n, friction direction, effective masses                            :368-426 + ContactConstraints.cpp:4-31
-//   [joint kernels]   joints.cu
-//   k_contact_solve   one launch per colour and iteration (normal rows then friction rows of each manifold)           ContactConstraints.cpp:33-124
-//   k_integrate_x     positions / orientations (+ pseudo velocities, COM re-anchoring)                                :494-511
-//   k_contact_solve   relaxation pass: hard contacts only, no bias                                                    :516-519
+// Reference (src/Physecs.cpp:364-531), per substep:
+//   integrate velocities   gravity + implicit gyroscopic update, massTemp (world inverse inertia), reset pseudo velocities  :443-468
+//   contact prep           world arms, separation, r x n, friction direction, effective masses        :368-426 + ContactConstraints.cpp:4-31
+//   joint prep             row fill + preSolve / NGS pass per joint colour                              joints.cuh
+//   iterations             contact colours (normal rows then friction rows of each manifold), then joint colours   ContactConstraints.cpp:33-124
+//   integrate positions    positions / orientations (+ pseudo velocities, COM re-anchoring)            :494-511
+//   relaxation             one more contact pass: hard contacts only, no bias                           :516-519
+//
+// Why a persistent kernel for the coloured part: a 1 M-body step has ~9 contact colours whose sizes fall off geometrically (700 k, 600 k, 400 k, 150 k,
+// 30 k, 4 k, 500, 100 manifolds).  Launched separately, every colour pays ~9 us of launch + dependent-load latency however
+// small it is, 3 passes x 4 substeps per step; small scenes (ragdoll batches) are launch-bound outright.  In k_substep_solve
+// the grid is sized to be co-resident (cudaLaunchCooperativeKernel), each colour is a grid-stride loop and colours are
+// separated by a device-wide barrier (one atomic per CTA, ~1-2 us).  The arithmetic is unchanged, so parity is unchanged:
+// inside a colour no two manifolds share a dynamic body and colours still run in order.
+// The two big streaming phases (integrate velocities, contact prep) stay ordinary launches: contact prep needs ~125
+// registers, and folding it into the persistent kernel would cap the solve colours at 16 warps/SM (measured: 2.8 TB/s
+// instead of 4.1 TB/s on the large colours).  The persistent kernel is held to 64 registers (32 warps/SM).
+//
 // Velocity triple buffering replaces the reference's component <-> velocityTemp copies:
 //   vel      = component velocity at substep start (what contact prep reads for the friction direction, :406-412)
 //   velPre   = post-gravity/gyro component velocity (what friction rows read all substep long, quirk Q3, ContactConstraints.cpp:92-102)
 //   velLive  = velocityTemp, iterated by the solver; becomes `vel` of the next substep by pointer swap (:523-530).
-// The friction increment relVel_t / kT is therefore constant within a substep and is precomputed in k_contact_prep.
+// The friction increment relVel_t / kT is therefore constant within a substep and is precomputed in the prep phase.
+//
+// Memory: every array a step mutates is read with __ldcg (L2) -- other SMs write it between barriers and L1 is not
+// coherent; arrays that are constant for the whole launch keep the read-only path.
 #include "pb_ctx.h"
 #include "pb_math.cuh"
+#include "joints.cuh"
 
-__device__ __forceinline__ M3 loadM3(const float4* __restrict__ p, int i) {
+bool pb_joint_view(pb_ctx* ctx, JointDev* out);
+
+struct SubstepParams {
+    int nDyn, substeps, iterations;
+    float h, g;
+    const int* counters;             // device counters block: CNT_MANIFOLDS, CNT_COLORSTART..
+    // bodies
+    const int* kinematic; const float4* comInvMass; const float4* invIL;
+    float4* pos; float4* quat;
+    float4* velA; float4* angvelA;   // substep-start velocity on entry (buffers A / B swap every substep)
+    float4* velB; float4* angvelB;
+    float4* velPre; float4* angvelPre;
+    float4* invIW; float4* pseudoLin; float4* pseudoAng;
+    // contact constraints
+    const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const int* cPointOfs; const int* cNp;
+    const float4* pR0T; const float4* pR1;
+    float4* rowA; float4* rowB; float4* rowC; float4* rowD; float4* rowE; float4* rowF; float4* rowG; float2* rowL;
+    // joints
+    int hasJoints; JointDev J; int jointColorStart[PB_JOINT_COLORS + 1];
+    // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
+    unsigned int* barrier;
+    unsigned long long* profNs;
+};
+
+enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_KINDS };
+
+__device__ __forceinline__ M3 loadM3(const float4* p, int i) {
+    M3 r; r.c[0] = mk3(__ldcg(&p[3 * i])); r.c[1] = mk3(__ldcg(&p[3 * i + 1])); r.c[2] = mk3(__ldcg(&p[3 * i + 2])); return r;
+}
+__device__ __forceinline__ M3 loadM3ro(const float4* __restrict__ p, int i) {
     M3 r; r.c[0] = mk3(p[3 * i]); r.c[1] = mk3(p[3 * i + 1]); r.c[2] = mk3(p[3 * i + 2]); return r;
 }
-__device__ __forceinline__ void storeM3(float4* __restrict__ p, int i, const M3& a) {
+__device__ __forceinline__ void storeM3(float4* p, int i, const M3& a) {
     p[3 * i] = f4(a.c[0]); p[3 * i + 1] = f4(a.c[1]); p[3 * i + 2] = f4(a.c[2]);
 }
 // MathUtil.h:10-21
@@ -30,67 +75,55 @@ __device__ __forceinline__ V3 solve33(const M3& A, V3 b) {
     return mk3(inv * dot(b, c12), inv * dot(A.c[0], cross(b, A.c[2])), inv * dot(A.c[0], cross(A.c[1], b)));
 }
 
-__global__ void __launch_bounds__(128) k_integrate_v(int nDyn, float h, float g, const int* __restrict__ kinematic,
-    const float4* __restrict__ quat, const float4* __restrict__ vel, const float4* __restrict__ angvel, const float4* __restrict__ invIL,
-    float4* __restrict__ velPre, float4* __restrict__ angvelPre, float4* __restrict__ velLive, float4* __restrict__ angvelLive,
-    float4* __restrict__ invIW, float4* __restrict__ pseudoLin, float4* __restrict__ pseudoAng) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nDyn) return;
-    if (kinematic[i]) return;
-    M3 rot = mat3_cast(mkq(quat[i]));
+// ---- phases (one unit of work each) -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const float4* vel, const float4* angvel, float4* velLive, float4* angvelLive) {
+    if (P.kinematic[i]) return;
+    M3 rot = mat3_cast(mkq(__ldcg(&P.quat[i])));
     M3 invRot = transpose(rot);
-    V3 v = mk3(vel[i]) + h * mk3(0.f, -g, 0.f);
-    V3 wl = mul(invRot, mk3(angvel[i]));
-    M3 invI = loadM3(invIL, i);
+    V3 v = mk3(__ldcg(&vel[i])) + P.h * mk3(0.f, -P.g, 0.f);
+    V3 wl = mul(invRot, mk3(__ldcg(&angvel[i])));
+    M3 invI = loadM3ro(P.invIL, i);
     M3 I = inverse(invI);
     V3 Iw = mul(I, wl);
-    V3 f = h * cross(wl, Iw);
-    M3 J = I + h * (mul(matrixCross3(wl), I) - matrixCross3(Iw));
+    V3 f = P.h * cross(wl, Iw);
+    M3 J = I + P.h * (mul(matrixCross3(wl), I) - matrixCross3(Iw));
     wl = wl - solve33(J, f);
     V3 w = mul(rot, wl);
-    velPre[i] = f4(v); angvelPre[i] = f4(w);
+    P.velPre[i] = f4(v); P.angvelPre[i] = f4(w);
     velLive[i] = f4(v); angvelLive[i] = f4(w);
-    pseudoLin[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-    pseudoAng[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    storeM3(invIW, i, mul(mul(rot, invI), invRot));
+    P.pseudoLin[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    P.pseudoAng[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    storeM3(P.invIW, i, mul(mul(rot, invI), invRot));
 }
 
-__global__ void __launch_bounds__(128) k_contact_prep(int nM, const int2* __restrict__ cBodies, const int2* __restrict__ cRowsT,
-    const float4* __restrict__ cNormal, const int* __restrict__ cPointOfs, const int* __restrict__ cNp,
-    const float4* __restrict__ pR0T, const float4* __restrict__ pR1,
-    const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ comInvMass,
-    const float4* __restrict__ vel, const float4* __restrict__ angvel, const float4* __restrict__ velPre, const float4* __restrict__ angvelPre,
-    const float4* __restrict__ invIW,
-    float4* __restrict__ rowA, float4* __restrict__ rowB, float4* __restrict__ rowC, float4* __restrict__ rowD,
-    float4* __restrict__ rowE, float4* __restrict__ rowF, float4* __restrict__ rowG, float2* __restrict__ rowL) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nM) return;
-    int2 bb = cBodies[s];
-    int2 rr = cRowsT[s];
-    V3 n = mk3(cNormal[s]);
-    Q4 q0 = mkq(quat[rr.x]), q1 = mkq(quat[rr.y]);
+__device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const float4* vel, const float4* angvel) {
+    int4 hd = P.cHead[s];
+    int2 bb = make_int2(hd.x, hd.y);
+    int2 rr = P.cRowsT[s];
+    V3 n = mk3(P.cNormal[s]);
+    Q4 q0 = mkq(__ldcg(&P.quat[rr.x])), q1 = mkq(__ldcg(&P.quat[rr.y]));
     V3 com0 = mk3(0.f), v0 = mk3(0.f), w0 = mk3(0.f), vp0 = mk3(0.f), wp0 = mk3(0.f);
     V3 com1 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f), vp1 = mk3(0.f), wp1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
     M3 I0, I1;
     I0.c[0] = I0.c[1] = I0.c[2] = mk3(0.f); I1 = I0;
     if (bb.x >= 0) {
-        float4 c = comInvMass[bb.x];
-        com0 = mk3(pos[rr.x]) + rotate(q0, mk3(c)); im0 = c.w;
-        v0 = mk3(vel[bb.x]); w0 = mk3(angvel[bb.x]); vp0 = mk3(velPre[bb.x]); wp0 = mk3(angvelPre[bb.x]);
-        I0 = loadM3(invIW, bb.x);
+        float4 c = P.comInvMass[bb.x];
+        com0 = mk3(__ldcg(&P.pos[rr.x])) + rotate(q0, mk3(c)); im0 = c.w;
+        v0 = mk3(__ldcg(&vel[bb.x])); w0 = mk3(__ldcg(&angvel[bb.x])); vp0 = mk3(__ldcg(&P.velPre[bb.x])); wp0 = mk3(__ldcg(&P.angvelPre[bb.x]));
+        I0 = loadM3(P.invIW, bb.x);
     }
     if (bb.y >= 0) {
-        float4 c = comInvMass[bb.y];
-        com1 = mk3(pos[rr.y]) + rotate(q1, mk3(c)); im1 = c.w;
-        v1 = mk3(vel[bb.y]); w1 = mk3(angvel[bb.y]); vp1 = mk3(velPre[bb.y]); wp1 = mk3(angvelPre[bb.y]);
-        I1 = loadM3(invIW, bb.y);
+        float4 c = P.comInvMass[bb.y];
+        com1 = mk3(__ldcg(&P.pos[rr.y])) + rotate(q1, mk3(c)); im1 = c.w;
+        v1 = mk3(__ldcg(&vel[bb.y])); w1 = mk3(__ldcg(&angvel[bb.y])); vp1 = mk3(__ldcg(&P.velPre[bb.y])); wp1 = mk3(__ldcg(&P.angvelPre[bb.y]));
+        I1 = loadM3(P.invIW, bb.y);
     }
-    int po = cPointOfs[s], np = cNp[s];
+    int po = hd.z, np = hd.w & 0xff;
     for (int k = 0; k < np; ++k) {
-        float4 a = pR0T[po + k];
+        float4 a = P.pR0T[po + k];
         V3 r0 = rotate(q0, mk3(a));
-        V3 r1 = rotate(q1, mk3(pR1[po + k]));
+        V3 r1 = rotate(q1, mk3(P.pR1[po + k]));
         V3 cp0 = com0 + r0, cp1 = com1 + r1;
         float cn = dot(cp1 - cp0, n);
         V3 r0xn = cross(r0, n), r1xn = cross(r1, n);
@@ -109,221 +142,347 @@ __global__ void __launch_bounds__(128) k_contact_prep(int nM, const int2* __rest
             float relT = dot(-t, vp0) + dot(-r0xt, wp0) + dot(t, vp1) + dot(r1xt, wp1);
             lamT0 = relT / kT;
         }
-        rowA[po + k] = f4(r0xn, cn);
-        rowB[po + k] = f4(r1xn, kN);
-        rowC[po + k] = f4(r0xnt, a.w);
-        rowD[po + k] = f4(r1xnt, lamT0);
-        rowE[po + k] = f4(t, kT != 0.f ? 1.f : 0.f);
-        rowF[po + k] = f4(r0xtt, 0.f);
-        rowG[po + k] = f4(r1xtt, 0.f);
-        rowL[po + k] = make_float2(0.f, 0.f);
+        __stcg(&P.rowA[po + k], f4(r0xn, cn));
+        __stcg(&P.rowB[po + k], f4(r1xn, kN));
+        __stcg(&P.rowC[po + k], f4(r0xnt, a.w));
+        __stcg(&P.rowD[po + k], f4(r1xnt, lamT0));
+        __stcg(&P.rowE[po + k], f4(t, kT != 0.f ? 1.f : 0.f));
+        __stcg(&P.rowF[po + k], f4(r0xtt, 0.f));
+        __stcg(&P.rowG[po + k], f4(r1xtt, 0.f));
+        __stcg(&P.rowL[po + k], make_float2(0.f, 0.f));
     }
 }
 
-// One colour: manifolds [start, start+count).  useBias=0 && skipSoft=1 is the relaxation pass.
-__global__ void __launch_bounds__(128) k_contact_solve(int start, int count, int useBias, int skipSoft, float h,
-    const int2* __restrict__ cBodies, const float4* __restrict__ cNormal, const float4* __restrict__ cSoft,
-    const int* __restrict__ cPointOfs, const int* __restrict__ cNp, const float4* __restrict__ comInvMass,
-    float4* __restrict__ velLive, float4* __restrict__ angvelLive,
-    const float4* __restrict__ rowA, const float4* __restrict__ rowB, const float4* __restrict__ rowC, const float4* __restrict__ rowD,
-    const float4* __restrict__ rowE, const float4* __restrict__ rowF, const float4* __restrict__ rowG, float2* __restrict__ rowL) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    int s = start + i;
-    float4 soft = cSoft[s];
-    if (skipSoft && soft.x != 0.f) return;
-    int2 bb = cBodies[s];
-    float4 nf = cNormal[s];
+// one manifold of the current colour.  useBias=0 && skipSoft=1 is the relaxation pass.
+// Normal row then friction row of one point (ContactConstraints.cpp:33-124); shared by the single-point fast path and the loop.
+__device__ __forceinline__ void normalRow(float4 A, float4 B, float4 C, float4 D, float4 soft, int useBias, float h, V3 n, float im0, float im1,
+                                          V3& v0, V3& w0, V3& v1, V3& w1, float& lamN) {
+    float kN = B.w;
+    if (kN == 0.f) return;
+    V3 r0xn = mk3(A), r1xn = mk3(B);
+    float rv = dot(-n, v0) + dot(-r0xn, w0) + dot(n, v1) + dot(r1xn, w1);
+    float effMass = 1.f / kN;
+    float lambda;
+    if (soft.x != 0.f) {
+        float af = 2.f * 3.14159265358979323846f * soft.y;
+        float stiffness = af * af * effMass;
+        float damping = 2.f * af * soft.z * effMass;
+        float gamma = 1.f / (damping + h * stiffness);
+        float beta = h * stiffness / (damping + h * stiffness);
+        lambda = (rv + beta * A.w / h) / (kN + gamma / h);
+    } else {
+        lambda = (rv - C.w + (useBias ? 0.1f * A.w / h : 0.f)) * effMass;
+    }
+    float prev = lamN;
+    float tot = fminf(prev + lambda, 0.f);
+    lamN = tot;
+    lambda = tot - prev;
+    v0 += lambda * im0 * n; w0 += lambda * mk3(C);
+    v1 -= lambda * im1 * n; w1 -= lambda * mk3(D);
+}
+__device__ __forceinline__ void frictionRow(float4 D, float4 E, float4 F, float4 G, float friction, float lamN, float im0, float im1,
+                                            V3& v0, V3& w0, V3& v1, V3& w1, float& lamT) {
+    V3 t = mk3(E);
+    float limit = friction * lamN;
+    float prev = lamT;
+    float tot = gclamp(prev + D.w, limit, -limit);
+    lamT = tot;
+    float lambda = tot - prev;
+    v0 += lambda * im0 * t; w0 += lambda * mk3(F);
+    v1 -= lambda * im1 * t; w1 -= lambda * mk3(G);
+}
+
+__device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
+    int4 hd = P.cHead[s];
+    const bool isSoft = (hd.w & 0x100) != 0;
+    if (skipSoft && isSoft) return;
+    float4 nf = P.cNormal[s];
+    float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     V3 n = mk3(nf);
     float friction = nf.w;
+    const float h = P.h;
+    const int b0 = hd.x, b1 = hd.y, po = hd.z, np = hd.w & 0xff;
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (bb.x >= 0) { v0 = mk3(velLive[bb.x]); w0 = mk3(angvelLive[bb.x]); im0 = comInvMass[bb.x].w; }
-    if (bb.y >= 0) { v1 = mk3(velLive[bb.y]); w1 = mk3(angvelLive[bb.y]); im1 = comInvMass[bb.y].w; }
-    int po = cPointOfs[s], np = cNp[s];
-    float lamN[4], lamT[4];
-    for (int k = 0; k < np; ++k) {
-        float4 A = rowA[po + k], B = rowB[po + k], C = rowC[po + k], D = rowD[po + k];
-        float2 L = rowL[po + k];
-        lamN[k] = L.x; lamT[k] = L.y;
-        float kN = B.w;
-        if (kN == 0.f) continue;
-        V3 r0xn = mk3(A), r1xn = mk3(B);
-        float rv = dot(-n, v0) + dot(-r0xn, w0) + dot(n, v1) + dot(r1xn, w1);
-        float effMass = 1.f / kN;
-        float lambda;
-        if (soft.x != 0.f) {
-            float af = 2.f * 3.14159265358979323846f * soft.y;
-            float stiffness = af * af * effMass;
-            float damping = 2.f * af * soft.z * effMass;
-            float gamma = 1.f / (damping + h * stiffness);
-            float beta = h * stiffness / (damping + h * stiffness);
-            lambda = (rv + beta * A.w / h) / (kN + gamma / h);
-        } else {
-            lambda = (rv - C.w + (useBias ? 0.1f * A.w / h : 0.f)) * effMass;
+    if (np == 1) {
+        // the common case (a body resting on a mesh triangle, a sphere pair): every load of the manifold is issued in one
+        // wave -- the row loads do not depend on the velocity gathers -- so a thread has ~220 bytes in flight at once
+        float4 A = __ldcg(&P.rowA[po]), B = __ldcg(&P.rowB[po]), C = __ldcg(&P.rowC[po]), D = __ldcg(&P.rowD[po]);
+        float4 E = __ldcg(&P.rowE[po]), F = __ldcg(&P.rowF[po]), G = __ldcg(&P.rowG[po]);
+        float2 L = __ldcg(&P.rowL[po]);
+        if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
+        if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+        float lamN = L.x, lamT = L.y;
+        normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
+        if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
+        __stcg(&P.rowL[po], make_float2(lamN, lamT));
+    } else {
+        if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
+        if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+        float lamN[4], lamT[4];
+        for (int k = 0; k < np; ++k) {
+            float4 A = __ldcg(&P.rowA[po + k]), B = __ldcg(&P.rowB[po + k]), C = __ldcg(&P.rowC[po + k]), D = __ldcg(&P.rowD[po + k]);
+            float2 L = __ldcg(&P.rowL[po + k]);
+            lamN[k] = L.x; lamT[k] = L.y;
+            normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[k]);
         }
-        float prev = lamN[k];
-        float tot = fminf(prev + lambda, 0.f);
-        lamN[k] = tot;
-        lambda = tot - prev;
-        v0 += lambda * im0 * n; w0 += lambda * mk3(C);
-        v1 -= lambda * im1 * n; w1 -= lambda * mk3(D);
-    }
-    for (int k = 0; k < np; ++k) {
-        float4 E = rowE[po + k];
-        if (E.w != 0.f) {
-            float4 D = rowD[po + k];
-            V3 t = mk3(E);
-            float limit = friction * lamN[k];
-            float prev = lamT[k];
-            float tot = gclamp(prev + D.w, limit, -limit);
-            lamT[k] = tot;
-            float lambda = tot - prev;
-            v0 += lambda * im0 * t; w0 += lambda * mk3(rowF[po + k]);
-            v1 -= lambda * im1 * t; w1 -= lambda * mk3(rowG[po + k]);
+        for (int k = 0; k < np; ++k) {
+            float4 E = __ldcg(&P.rowE[po + k]);
+            if (E.w != 0.f)
+                frictionRow(__ldcg(&P.rowD[po + k]), E, __ldcg(&P.rowF[po + k]), __ldcg(&P.rowG[po + k]), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
+            __stcg(&P.rowL[po + k], make_float2(lamN[k], lamT[k]));
         }
-        rowL[po + k] = make_float2(lamN[k], lamT[k]);
     }
-    if (bb.x >= 0) { velLive[bb.x] = f4(v0); angvelLive[bb.x] = f4(w0); }
-    if (bb.y >= 0) { velLive[bb.y] = f4(v1); angvelLive[bb.y] = f4(w1); }
+    if (b0 >= 0) { __stcg(&velLive[b0], f4(v0)); __stcg(&angvelLive[b0], f4(w0)); }
+    if (b1 >= 0) { __stcg(&velLive[b1], f4(v1)); __stcg(&angvelLive[b1], f4(w1)); }
 }
 
-// Sequential overflow bucket (colour 63): one thread walks the manifolds in order.
-__global__ void k_contact_solve_seq(int start, int count, int useBias, int skipSoft, float h,
-    const int2* __restrict__ cBodies, const float4* __restrict__ cNormal, const float4* __restrict__ cSoft,
-    const int* __restrict__ cPointOfs, const int* __restrict__ cNp, const float4* __restrict__ comInvMass,
-    float4* __restrict__ velLive, float4* __restrict__ angvelLive,
-    const float4* __restrict__ rowA, const float4* __restrict__ rowB, const float4* __restrict__ rowC, const float4* __restrict__ rowD,
-    const float4* __restrict__ rowE, const float4* __restrict__ rowF, const float4* __restrict__ rowG, float2* __restrict__ rowL);
+// FOUR lanes per manifold: lane k holds point k, so all rows of the manifold are loaded in one wave; the points are then
+// applied in order (normal rows, then friction rows) by handing the running body velocities from lane to lane with shuffles.
+// Same arithmetic as contactSolve; used when manifolds have several points on average (box stacks, ragdolls), where the
+// one-thread version serialises ~3 memory round trips per point.
+__device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, int lane4, unsigned gmask, int useBias, int skipSoft,
+                                                 float4* velLive, float4* angvelLive) {
+    int4 hd = P.cHead[s];
+    const bool isSoft = (hd.w & 0x100) != 0;
+    if (skipSoft && isSoft) return;          // uniform across the four lanes
+    float4 nf = P.cNormal[s];
+    float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+    V3 n = mk3(nf);
+    float friction = nf.w;
+    const float h = P.h;
+    const int b0 = hd.x, b1 = hd.y, po = hd.z, np = hd.w & 0xff;
+    const bool mine = lane4 < np;
+    float4 A = make_float4(0, 0, 0, 0), B = A, C = A, D = A, E = A, F = A, G = A;
+    float2 L = make_float2(0.f, 0.f);
+    if (mine) {
+        A = __ldcg(&P.rowA[po + lane4]); B = __ldcg(&P.rowB[po + lane4]); C = __ldcg(&P.rowC[po + lane4]); D = __ldcg(&P.rowD[po + lane4]);
+        E = __ldcg(&P.rowE[po + lane4]); F = __ldcg(&P.rowF[po + lane4]); G = __ldcg(&P.rowG[po + lane4]);
+        L = __ldcg(&P.rowL[po + lane4]);
+    }
+    V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
+    float im0 = 0.f, im1 = 0.f;
+    if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
+    if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+    float lamN = L.x, lamT = L.y;
+#define PB_PASS_ON(r) \
+    v0.x = __shfl_sync(gmask, v0.x, r, 4); v0.y = __shfl_sync(gmask, v0.y, r, 4); v0.z = __shfl_sync(gmask, v0.z, r, 4); \
+    w0.x = __shfl_sync(gmask, w0.x, r, 4); w0.y = __shfl_sync(gmask, w0.y, r, 4); w0.z = __shfl_sync(gmask, w0.z, r, 4); \
+    v1.x = __shfl_sync(gmask, v1.x, r, 4); v1.y = __shfl_sync(gmask, v1.y, r, 4); v1.z = __shfl_sync(gmask, v1.z, r, 4); \
+    w1.x = __shfl_sync(gmask, w1.x, r, 4); w1.y = __shfl_sync(gmask, w1.y, r, 4); w1.z = __shfl_sync(gmask, w1.z, r, 4);
+    for (int k = 0; k < np; ++k) {
+        if (lane4 == k) normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
+        PB_PASS_ON(k)
+    }
+    for (int k = 0; k < np; ++k) {
+        if (lane4 == k && E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
+        PB_PASS_ON(k)
+    }
+#undef PB_PASS_ON
+    if (mine) __stcg(&P.rowL[po + lane4], make_float2(lamN, lamT));
+    if (lane4 == 0) {
+        if (b0 >= 0) { __stcg(&velLive[b0], f4(v0)); __stcg(&angvelLive[b0], f4(w0)); }
+        if (b1 >= 0) { __stcg(&velLive[b1], f4(v1)); __stcg(&angvelLive[b1], f4(w1)); }
+    }
+}
 
-__global__ void __launch_bounds__(128) k_integrate_x(int nDyn, float h, const int* __restrict__ kinematic, float4* __restrict__ pos, float4* __restrict__ quat,
-    const float4* __restrict__ comInvMass, const float4* __restrict__ velLive, const float4* __restrict__ angvelLive,
-    const float4* __restrict__ pseudoLin, const float4* __restrict__ pseudoAng) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nDyn) return;
-    if (kinematic[i]) return;
-    float4 pl = pseudoLin[i];
+__device__ __forceinline__ void integrateX(const SubstepParams& P, int i, const float4* velLive, const float4* angvelLive) {
+    if (P.kinematic[i]) return;
+    float4 pl = __ldcg(&P.pseudoLin[i]);
     int cnt = __float_as_int(pl.w);
     float scale = cnt ? 1.f / (float)cnt : 1.f;
-    V3 p = mk3(pos[i]);
-    Q4 q = mkq(quat[i]);
-    V3 com = mk3(comInvMass[i]);
-    p = p + (h * mk3(velLive[i]) + scale * mk3(pl));
+    V3 p = mk3(__ldcg(&P.pos[i]));
+    Q4 q = mkq(__ldcg(&P.quat[i]));
+    V3 com = mk3(P.comInvMass[i]);
+    p = p + (P.h * mk3(__ldcg(&velLive[i])) + scale * mk3(pl));
     V3 prevCom = rotate(q, com);
-    V3 hw = 0.5f * (h * mk3(angvelLive[i]) + scale * mk3(pseudoAng[i]));
+    V3 hw = 0.5f * (P.h * mk3(__ldcg(&angvelLive[i])) + scale * mk3(__ldcg(&P.pseudoAng[i])));
     Q4 dq; dq.w = 0.f; dq.x = hw.x; dq.y = hw.y; dq.z = hw.z;
     Q4 add = qmul(dq, q);
     q.x += add.x; q.y += add.y; q.z += add.z; q.w += add.w;
     q = qnormalize(q);
     p = p + (prevCom - rotate(q, com));
-    pos[i] = f4(p); quat[i] = f4(q);
+    P.pos[i] = f4(p); P.quat[i] = f4(q);
 }
 
-int pb_joint_prep(pb_ctx* ctx, float h);
-int pb_joint_solve(pb_ctx* ctx, float h, int warmStart);
+// ---- device-wide barrier ------------------------------------------------------------------------------------------------------------
+// Monotonic arrival counter (zeroed before the launch): barrier k completes when it reaches k * gridDim.x.  The release /
+// acquire pair on the counter plus the CTA barriers around it order all earlier global writes of every CTA before all later
+// reads of every CTA (the same construction cooperative_groups::grid_group::sync uses).
+struct GridBarrier {
+    unsigned int* counter;
+    unsigned int target;
+    unsigned long long* profNs;
+    unsigned long long tPrev;
+    __device__ __forceinline__ void sync(int kind) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*((volatile unsigned int*)counter) < target) { }
+            __threadfence();
+            if (profNs && blockIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                atomicAdd(&profNs[kind], t - tPrev);
+                atomicAdd(&profNs[PH_KINDS + kind], 1ull);
+                tPrev = t;
+            }
+        }
+        __syncthreads();
+    }
+};
 
-int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
+__global__ void __launch_bounds__(256) k_integrate_v(const __grid_constant__ SubstepParams P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.nDyn) integrateV(P, i, P.velA, P.angvelA, P.velB, P.angvelB);
+}
+
+__global__ void __launch_bounds__(128) k_contact_prep(const __grid_constant__ SubstepParams P) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.counters[CNT_MANIFOLDS]) contactPrep(P, s, P.velA, P.angvelA);
+}
+
+// Joint routines are called, not inlined: their register appetite (row builders, 3x3 products) then spills inside the
+// callee only, and the contact colour loops -- the bandwidth-critical part -- keep a spill-free 64-register budget.
+__device__ __noinline__ void jointPrepCall(const SubstepParams& P, int j, int doNgs) {
+    jointPrepOne(P.J, j, doNgs, P.kinematic, P.pos, P.quat, P.comInvMass, P.invIW, P.pseudoLin, P.pseudoAng);
+}
+__device__ __noinline__ void jointSolveCall(const SubstepParams& P, int j, int lane8, unsigned gmask, int warmStart, float4* velLive, float4* angvelLive) {
+    jointSolveOct(P.J, j, lane8, gmask, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
+}
+__device__ __noinline__ void jointNgsSeqCall(const SubstepParams& P, int start, int count) {
+    jointNgsSeq(P.J, start, count, P.kinematic, P.comInvMass, P.pseudoLin, P.pseudoAng);
+}
+__device__ __noinline__ void jointSolveSeqCall(const SubstepParams& P, int start, int count, int warmStart, float4* velLive, float4* angvelLive) {
+    jointSolveSeq(P.J, start, count, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
+}
+__device__ __noinline__ void contactSolveSeqCall(const SubstepParams& P, int start, int count, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
+    for (int i = 0; i < count; ++i) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive);
+}
+
+// Everything of one substep that is ordered by colour: joint prep (colours share bodies through the pseudo velocities),
+// the solver iterations (contact colours, then joint colours), position integration and the relaxation pass.
+__global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    GridBarrier bar;
+    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
+    if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
+    const int* colorStart = P.counters + CNT_COLORSTART;
+    const int ncol = P.counters[CNT_NCOLORS];
+    float4* velLive = P.velB; float4* angvelLive = P.angvelB;
+    const int lane = threadIdx.x & 31;
+    // several points per manifold on average -> four lanes per manifold (one memory wave per manifold instead of one per point)
+    const bool quad = 2 * (long long)P.counters[CNT_POINTS] > 3 * (long long)P.counters[CNT_MANIFOLDS];
+    // one contact pass over all colours, a barrier after each non-empty colour
+    auto contactPass = [&](int useBias, int skipSoft) {
+        for (int c = 0; c < ncol; ++c) {
+            int start = colorStart[c], count = colorStart[c + 1] - start;
+            if (count <= 0) continue;
+            if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
+                if (tid == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
+            } else if (quad) {
+                for (int i = tid >> 2; i < count; i += nth >> 2) contactSolveQuad(P, start + i, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive);
+            } else {
+                for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive);
+            }
+            bar.sync(PH_CONTACT_PASS);
+        }
+    };
+
+    if (P.hasJoints) {
+        for (int c = 0; c < 8; ++c) {
+            int start = P.jointColorStart[c], count = P.jointColorStart[c + 1] - start;
+            if (count <= 0) continue;
+            for (int i = tid; i < count; i += nth) jointPrepCall(P, start + i, 1);
+            bar.sync(PH_PREP);
+        }
+        int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
+        if (count > 0) {                    // overflow bucket: parallel row fill, then the sequential NGS pass
+            for (int i = tid; i < count; i += nth) jointPrepCall(P, start + i, 0);
+            bar.sync(PH_PREP);
+            if (tid == 0) jointNgsSeqCall(P, start, count);
+            bar.sync(PH_PREP);
+        }
+    }
+
+    for (int it = 0; it < P.iterations; ++it) {
+        contactPass(1, 0);
+        if (P.hasJoints) {
+            for (int c = 0; c < 8; ++c) {
+                int start = P.jointColorStart[c], count = P.jointColorStart[c + 1] - start;
+                if (count <= 0) continue;
+                for (int i = tid >> 3; i < count; i += nth >> 3) jointSolveCall(P, start + i, lane & 7, 0xFFu << (lane & 24), it == 0, velLive, angvelLive);
+                bar.sync(PH_JOINT_SOLVE);
+            }
+            int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
+            if (count > 0) {
+                if (tid == 0) jointSolveSeqCall(P, start, count, it == 0, velLive, angvelLive);
+                bar.sync(PH_JOINT_SOLVE);
+            }
+        }
+    }
+
+    for (int i = tid; i < P.nDyn; i += nth) integrateX(P, i, velLive, angvelLive);
+    bar.sync(PH_INTEGRATE_X);
+    contactPass(0, 1);      // relaxation
+}
+
+int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound) {
     const int nDyn = ctx->nDyn;
     if (nDyn == 0) return PB_OK;
-    const int nM = ctx->lastCounts.n_manifolds;
-    const int* colorStart = ctx->hCounters + CNT_COLORSTART;
+    if (!ctx->solveGrid) {
+        int perSM = 0;
+        PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_substep_solve, 256, 0));
+        if (perSM < 1) return pb_fail(ctx, PB_ECUDA, "k_substep_solve does not fit on an SM");
+        ctx->solveGrid = perSM * ctx->numSMs;
+        int rc = pb_alloc(ctx, &ctx->solveBarrier, 64); if (rc) return rc;
+        rc = pb_alloc(ctx, &ctx->solveProfNs, 2 * PH_KINDS); if (rc) return rc;
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->solveProfNs, 0, sizeof(unsigned long long) * 2 * PH_KINDS, ctx->stream));
+    }
     const int cur = ctx->curBuf;
-    float h = dt / (float)substeps;
-    int ncol = ctx->lastCounts.n_colors;
+    SubstepParams P{};
+    P.nDyn = nDyn; P.substeps = substeps; P.iterations = iterations; P.h = dt / (float)substeps; P.g = gravity;
+    P.counters = ctx->counters;
+    P.kinematic = ctx->kinematic; P.comInvMass = ctx->comInvMass; P.invIL = ctx->invIL;
+    P.pos = ctx->pos; P.quat = ctx->quat;
+    P.velPre = ctx->velPre; P.angvelPre = ctx->angvelPre; P.invIW = ctx->invIW; P.pseudoLin = ctx->pseudoLin; P.pseudoAng = ctx->pseudoAng;
+    P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft;
+    P.cPointOfs = ctx->cPointOfsBuf[cur]; P.cNp = ctx->cNpBuf[cur]; P.pR0T = ctx->pR0T[cur]; P.pR1 = ctx->pR1;
+    P.rowA = ctx->rowA; P.rowB = ctx->rowB; P.rowC = ctx->rowC; P.rowD = ctx->rowD; P.rowE = ctx->rowE; P.rowF = ctx->rowF; P.rowG = ctx->rowG; P.rowL = ctx->rowL;
+    P.hasJoints = pb_joint_view(ctx, &P.J) ? 1 : 0;
+    for (int c = 0; c <= PB_JOINT_COLORS; ++c) P.jointColorStart[c] = ctx->jointColorStart[c];
+    P.barrier = ctx->solveBarrier;
+    P.profNs = ctx->profile ? ctx->solveProfNs : nullptr;
+    // persistent grid: co-resident by construction; small scenes use fewer CTAs so the barrier stays cheap
+    long long work = std::max<long long>(std::max<long long>(nDyn, 4ll * workBound), 8ll * ctx->nJoints);
+    int grid = (int)std::min<long long>(ctx->solveGrid, (work + 255) / 256);
+    if (grid < 1) grid = 1;
+    cudaEventRecord(ctx->ev[5], ctx->stream);
     for (int sub = 0; sub < substeps; ++sub) {
-        ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, gravity, ctx->kinematic, ctx->quat, ctx->vel, ctx->angvel, ctx->invIL,
-            ctx->velPre, ctx->angvelPre, ctx->velLive, ctx->angvelLive, ctx->invIW, ctx->pseudoLin, ctx->pseudoAng);
-        if (nM > 0) pb_prof_begin(ctx, PROF_CONTACT_PREP);
-        if (nM > 0)
-            ++ctx->launches, k_contact_prep<<<pb_grid(nM, 128), 128, 0, ctx->stream>>>(nM, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur],
-                ctx->pR0T[cur], ctx->pR1, ctx->pos, ctx->quat, ctx->comInvMass, ctx->vel, ctx->angvel, ctx->velPre, ctx->angvelPre, ctx->invIW,
-                ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
-        if (nM > 0) pb_prof_end(ctx);
-        if (ctx->nJoints) { int rc = pb_joint_prep(ctx, h); if (rc) return rc; }
-        for (int it = 0; it <= iterations; ++it) {
-            const bool relax = it == iterations;
-            if (relax)
-                ++ctx->launches, k_integrate_x<<<pb_grid(nDyn, 128), 128, 0, ctx->stream>>>(nDyn, h, ctx->kinematic, ctx->pos, ctx->quat, ctx->comInvMass,
-                    ctx->velLive, ctx->angvelLive, ctx->pseudoLin, ctx->pseudoAng);
-            if (nM > 0) pb_prof_begin(ctx, PROF_SOLVE_PASS);
-            for (int c = 0; c < ncol; ++c) {
-                int start = colorStart[c], count = colorStart[c + 1] - start;
-                if (count <= 0) continue;
-                if (c == PB_OVERFLOW_COLOR)
-                    ++ctx->launches, k_contact_solve_seq<<<1, 1, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
-                        ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur], ctx->comInvMass, ctx->velLive, ctx->angvelLive,
-                        ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
-                else
-                    ++ctx->launches, k_contact_solve<<<pb_grid(count, 128), 128, 0, ctx->stream>>>(start, count, relax ? 0 : 1, relax ? 1 : 0, h, ctx->cBodies, ctx->cNormal, ctx->cSoft,
-                        ctx->cPointOfsBuf[cur], ctx->cNpBuf[cur], ctx->comInvMass, ctx->velLive, ctx->angvelLive,
-                        ctx->rowA, ctx->rowB, ctx->rowC, ctx->rowD, ctx->rowE, ctx->rowF, ctx->rowG, ctx->rowL);
-            }
-            if (nM > 0) pb_prof_end(ctx);
-            if (!relax && ctx->nJoints) { int rc = pb_joint_solve(ctx, h, it == 0); if (rc) return rc; }
-        }
-        // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity
+        P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
+        ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(P);
+        if (workBound > 0) ++ctx->launches, k_contact_prep<<<pb_grid(workBound, 128), 128, 0, ctx->stream>>>(P);
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
+        void* args[] = { &P };
+        ++ctx->launches;
+        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_substep_solve, dim3(grid), dim3(256), args, 0, ctx->stream));
+        // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity of the next substep
         std::swap(ctx->vel, ctx->velLive);
         std::swap(ctx->angvel, ctx->angvelLive);
     }
+    cudaEventRecord(ctx->ev[6], ctx->stream);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
 
-__global__ void k_contact_solve_seq(int start, int count, int useBias, int skipSoft, float h,
-    const int2* __restrict__ cBodies, const float4* __restrict__ cNormal, const float4* __restrict__ cSoft,
-    const int* __restrict__ cPointOfs, const int* __restrict__ cNp, const float4* __restrict__ comInvMass,
-    float4* __restrict__ velLive, float4* __restrict__ angvelLive,
-    const float4* __restrict__ rowA, const float4* __restrict__ rowB, const float4* __restrict__ rowC, const float4* __restrict__ rowD,
-    const float4* __restrict__ rowE, const float4* __restrict__ rowF, const float4* __restrict__ rowG, float2* __restrict__ rowL) {
-    for (int i = 0; i < count; ++i) {
-        int s = start + i;
-        float4 soft = cSoft[s];
-        if (skipSoft && soft.x != 0.f) continue;
-        int2 bb = cBodies[s];
-        float4 nf = cNormal[s];
-        V3 n = mk3(nf);
-        float friction = nf.w;
-        V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
-        float im0 = 0.f, im1 = 0.f;
-        if (bb.x >= 0) { v0 = mk3(velLive[bb.x]); w0 = mk3(angvelLive[bb.x]); im0 = comInvMass[bb.x].w; }
-        if (bb.y >= 0) { v1 = mk3(velLive[bb.y]); w1 = mk3(angvelLive[bb.y]); im1 = comInvMass[bb.y].w; }
-        int po = cPointOfs[s], np = cNp[s];
-        for (int k = 0; k < np; ++k) {
-            float4 A = rowA[po + k], B = rowB[po + k], C = rowC[po + k], D = rowD[po + k];
-            float2 L = rowL[po + k];
-            float kN = B.w;
-            if (kN == 0.f) continue;
-            float rv = dot(-n, v0) + dot(-mk3(A), w0) + dot(n, v1) + dot(mk3(B), w1);
-            float effMass = 1.f / kN;
-            float lambda;
-            if (soft.x != 0.f) {
-                float af = 2.f * 3.14159265358979323846f * soft.y;
-                float stiffness = af * af * effMass;
-                float damping = 2.f * af * soft.z * effMass;
-                float gamma = 1.f / (damping + h * stiffness);
-                float beta = h * stiffness / (damping + h * stiffness);
-                lambda = (rv + beta * A.w / h) / (kN + gamma / h);
-            } else lambda = (rv - C.w + (useBias ? 0.1f * A.w / h : 0.f)) * effMass;
-            float tot = fminf(L.x + lambda, 0.f);
-            lambda = tot - L.x;
-            rowL[po + k] = make_float2(tot, L.y);
-            v0 += lambda * im0 * n; w0 += lambda * mk3(C);
-            v1 -= lambda * im1 * n; w1 -= lambda * mk3(D);
-        }
-        for (int k = 0; k < np; ++k) {
-            float4 E = rowE[po + k];
-            if (E.w == 0.f) continue;
-            float4 D = rowD[po + k];
-            float2 L = rowL[po + k];
-            float limit = friction * L.x;
-            float tot = gclamp(L.y + D.w, limit, -limit);
-            float lambda = tot - L.y;
-            rowL[po + k] = make_float2(L.x, tot);
-            V3 t = mk3(E);
-            v0 += lambda * im0 * t; w0 += lambda * mk3(rowF[po + k]);
-            v1 -= lambda * im1 * t; w1 -= lambda * mk3(rowG[po + k]);
-        }
-        if (bb.x >= 0) { velLive[bb.x] = f4(v0); angvelLive[bb.x] = f4(w0); }
-        if (bb.y >= 0) { velLive[bb.y] = f4(v1); angvelLive[bb.y] = f4(w1); }
-    }
+// accumulated per-phase device time of the persistent kernel since profiling was switched on: ns[PH_KINDS], count[PH_KINDS]
+int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset) {
+    if (!ctx->solveProfNs) { for (int i = 0; i < 2 * PH_KINDS; ++i) out[i] = 0; return PB_OK; }
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaMemcpy(out, ctx->solveProfNs, sizeof(unsigned long long) * 2 * PH_KINDS, cudaMemcpyDeviceToHost));
+    if (reset) PB_CUDA(ctx, cudaMemset(ctx->solveProfNs, 0, sizeof(unsigned long long) * 2 * PH_KINDS));
+    return PB_OK;
 }
