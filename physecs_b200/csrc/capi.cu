@@ -35,6 +35,23 @@ __global__ void k_pack4(int n, const float4* __restrict__ src, float* __restrict
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float4 v = src[i]; dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
 }
+// interleaved velocity buffer: dst[2*i] = {v, invMass}, dst[2*i + 1] = {w, 0}; either source may be null (left untouched)
+__global__ void k_unpack_vel(int n, const float* __restrict__ v3, const float* __restrict__ w3, const float4* __restrict__ comInvMass, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (v3) dst[2 * i] = make_float4(v3[3 * i], v3[3 * i + 1], v3[3 * i + 2], comInvMass[i].w);
+    if (w3) dst[2 * i + 1] = make_float4(w3[3 * i], w3[3 * i + 1], w3[3 * i + 2], 0.f);
+}
+__global__ void k_pack_vel(int n, const float4* __restrict__ src, float* __restrict__ v3, float* __restrict__ w3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (v3) { float4 v = src[2 * i]; v3[3 * i] = v.x; v3[3 * i + 1] = v.y; v3[3 * i + 2] = v.z; }
+    if (w3) { float4 w = src[2 * i + 1]; w3[3 * i] = w.x; w3[3 * i + 1] = w.y; w3[3 * i + 2] = w.z; }
+}
+__global__ void k_refresh_invmass(int n, const float4* __restrict__ comInvMass, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[2 * i].w = comInvMass[i].w;
+}
 __global__ void k_com_invmass(int n, const float* __restrict__ com, const float* __restrict__ invMass, float4* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = make_float4(com[3 * i], com[3 * i + 1], com[3 * i + 2], invMass[i]);
@@ -142,7 +159,11 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
     int rc = 0;
 #define A(p, n) if (!rc) rc = pb_alloc(ctx, &ctx->p, (n))
-    A(rowEntity, R); A(pos, R); A(quat, R); A(vel, R); A(angvel, R); A(velPre, R); A(angvelPre, R); A(velLive, R); A(angvelLive, R);
+    A(rowEntity, R); A(pos, R); A(quat, R); A(velBuf[0], 2 * R); A(velBuf[1], 2 * R); A(velBuf[2], 2 * R);
+    if (!rc) {
+        ctx->vel = ctx->velBuf[0]; ctx->angvel = ctx->velBuf[0] + 1; ctx->velPre = ctx->velBuf[1]; ctx->angvelPre = ctx->velBuf[1] + 1;
+        ctx->velLive = ctx->velBuf[2]; ctx->angvelLive = ctx->velBuf[2] + 1;
+    }
     A(comInvMass, R); A(invIL, 3 * R); A(invIW, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
     A(colRow, C); A(colIndex, C); A(colType, C); A(colFlags, C); A(colData, C); A(colMesh, C);
     A(colLPos, C); A(colLQuat, C); A(colParams, C); A(colMat, C); A(colWPos, C); A(colWQuat, C); A(aabbMin, C); A(aabbMax, C);
@@ -225,7 +246,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pb_joints_free(ctx);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
-    F(rowEntity); F(pos); F(quat); F(vel); F(angvel); F(velPre); F(angvelPre); F(velLive); F(angvelLive); F(comInvMass); F(invIL); F(invIW);
+    F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(velBuf[2]); F(comInvMass); F(invIL); F(invIW);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds);
@@ -261,16 +282,18 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
     if ((rc = uploadVec(ctx, quat4, rows, 4, ctx->quat))) return rc;
     if (nDyn) {
         if ((rc = uploadRaw(ctx, kinematic, nDyn, ctx->kinematic))) return rc;
-        if ((rc = uploadVec(ctx, vel3, nDyn, 3, ctx->vel))) return rc;
-        if ((rc = uploadVec(ctx, angvel3, nDyn, 3, ctx->angvel))) return rc;
-        size_t bytes = sizeof(float) * (size_t)nDyn * 13;
+        size_t bytes = sizeof(float) * (size_t)nDyn * 19;
         if ((rc = ensureStage(ctx, bytes))) return rc;
         float* s = ctx->stage;
-        PB_CUDA(ctx, cudaMemcpyAsync(s, com3, sizeof(float) * 3 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * (size_t)nDyn, invMass, sizeof(float) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)nDyn, invI9, sizeof(float) * 9 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
-        ++ctx->launches, k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
-        ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
+        const size_t n = (size_t)nDyn;
+        PB_CUDA(ctx, cudaMemcpyAsync(s, com3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, invMass, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * n, invI9, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 13 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(s + 16 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+        ++ctx->launches, k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * n, ctx->comInvMass);
+        ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * n, ctx->invIL);
+        ++ctx->launches, k_unpack_vel<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 13 * n, s + 16 * n, ctx->comInvMass, ctx->vel);
     }
     ctx->cacheValid = false;
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -473,8 +496,8 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
     int g = pb_grid(nDyn, 256);
     if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
     if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
-    if (vel3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 7 * n, ctx->vel);
-    if (angvel3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s + 10 * n, ctx->angvel);
+    if (vel3 || angvel3)
+        ++ctx->launches, k_unpack_vel<<<g, 256, 0, ctx->stream>>>(nDyn, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr, ctx->comInvMass, ctx->vel);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -559,8 +582,8 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
     int g = pb_grid(nDyn, 256);
     if (pos3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
     if (quat4) ++ctx->launches, k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
-    if (vel3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, s + 7 * n);
-    if (angvel3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->angvel, s + 10 * n);
+    if (vel3 || angvel3)
+        ++ctx->launches, k_pack_vel<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr);
     if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3, s, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4, s + 3 * n, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3, s + 7 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -619,6 +642,7 @@ int pb_set_mass(pb_ctx* ctx, int nDyn, const float* invMass, const float* com3, 
     PB_CUDA(ctx, cudaMemcpyAsync(s + 4 * (size_t)nDyn, invI9, sizeof(float) * 9 * nDyn, cudaMemcpyHostToDevice, ctx->stream));
     ++ctx->launches, k_com_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s, s + 3 * (size_t)nDyn, ctx->comInvMass);
     ++ctx->launches, k_unpack_m3<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, s + 4 * (size_t)nDyn, ctx->invIL);
+    ++ctx->launches, k_refresh_invmass<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(nDyn, ctx->comInvMass, ctx->vel);   // invMass rides in v.w
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }

@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(128) k_contact_build(
         int b0 = solverIndex(row0, nDyn, kinematic), b1 = solverIndex(row1, nDyn, kinematic);
         Q4 q0 = mkq(quat[row0]), q1 = mkq(quat[row1]);
         V3 com0 = mk3(0.f), v0 = mk3(0.f), w0 = mk3(0.f), com1 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
-        if (b0 >= 0) { com0 = mk3(pos[row0]) + rotate(q0, mk3(comInvMass[b0])); v0 = mk3(vel[b0]); w0 = mk3(angvel[b0]); }
-        if (b1 >= 0) { com1 = mk3(pos[row1]) + rotate(q1, mk3(comInvMass[b1])); v1 = mk3(vel[b1]); w1 = mk3(angvel[b1]); }
+        if (b0 >= 0) { com0 = mk3(pos[row0]) + rotate(q0, mk3(comInvMass[b0])); v0 = mk3(vel[2 * b0]); w0 = mk3(angvel[2 * b0]); }
+        if (b1 >= 0) { com1 = mk3(pos[row1]) + rotate(q1, mk3(comInvMass[b1])); v1 = mk3(vel[2 * b1]); w1 = mk3(angvel[2 * b1]); }
         Q4 iq0 = qinverse(q0), iq1 = qinverse(q1);
         // previous manifold of the same (pair, triangle) key
         int prevSlot = -1;

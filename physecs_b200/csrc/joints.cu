@@ -4,9 +4,13 @@
 #include <vector>
 
 // once per step (Physecs.cpp:322-354): reset accumulated impulses, prismatic limit selection (PrismaticJoint.cpp:116-155)
-__global__ void k_joint_begin(JointDev J, const float4* __restrict__ pos, const float4* __restrict__ quat) {
+__global__ void k_joint_begin(JointDev J, int2* __restrict__ bodies, const int* __restrict__ kinematic, const float4* __restrict__ pos, const float4* __restrict__ quat) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J.n) return;
+    {   // b0 / b1 of the step (Physecs.cpp:335-336): kinematic bodies and statics are index -1
+        int2 rr = J.rows[j];
+        bodies[j] = make_int2(jSolverIndex(rr.x, J.nDyn, kinematic), jSolverIndex(rr.y, J.nDyn, kinematic));
+    }
     for (int r = 0; r < MAXR; ++r) J.lambda[r * J.n + j] = 0.f;
     if (J.type[j] == PB_JOINT_PRISMATIC) {
         int2 rr = J.rows[j];
@@ -27,7 +31,7 @@ __global__ void k_joint_begin(JointDev J, const float4* __restrict__ pos, const 
 // ---- host side ---------------------------------------------------------------------------------------------------
 struct JointStore {
     int n = 0;
-    int* type = nullptr; int2* rows = nullptr; float4* a0p = nullptr; float4* a0q = nullptr; float4* a1p = nullptr; float4* a1q = nullptr;
+    int* type = nullptr; int2* rows = nullptr; int2* bodies = nullptr; float4* a0p = nullptr; float4* a0q = nullptr; float4* a1p = nullptr; float4* a1q = nullptr;
     float4* prm = nullptr; float4* state = nullptr;
     float4* linC = nullptr; float4* a0T = nullptr; float4* a1K = nullptr; float4* a0tMin = nullptr; float4* a1tMax = nullptr;
     float2* soft = nullptr; float* lambda = nullptr;
@@ -40,7 +44,7 @@ static JointStore* store(pb_ctx* ctx) { return (JointStore*)ctx->jointStore; }
 void pb_joints_free(pb_ctx* ctx) {
     JointStore* s = store(ctx);
     if (!s) return;
-    cudaFree(s->type); cudaFree(s->rows); cudaFree(s->a0p); cudaFree(s->a0q); cudaFree(s->a1p); cudaFree(s->a1q); cudaFree(s->prm); cudaFree(s->state);
+    cudaFree(s->type); cudaFree(s->rows); cudaFree(s->bodies); cudaFree(s->a0p); cudaFree(s->a0q); cudaFree(s->a1p); cudaFree(s->a1q); cudaFree(s->prm); cudaFree(s->state);
     cudaFree(s->linC); cudaFree(s->a0T); cudaFree(s->a1K); cudaFree(s->a0tMin); cudaFree(s->a1tMax); cudaFree(s->soft); cudaFree(s->lambda);
     delete s;
     ctx->jointStore = nullptr;
@@ -50,7 +54,7 @@ void pb_joints_free(pb_ctx* ctx) {
 static JointDev devView(pb_ctx* ctx) {
     JointStore* s = store(ctx);
     JointDev J;
-    J.n = s->n; J.nDyn = ctx->nDyn; J.type = s->type; J.rows = s->rows; J.a0p = s->a0p; J.a0q = s->a0q; J.a1p = s->a1p; J.a1q = s->a1q;
+    J.n = s->n; J.nDyn = ctx->nDyn; J.type = s->type; J.rows = s->rows; J.bodies = s->bodies; J.a0p = s->a0p; J.a0q = s->a0q; J.a1p = s->a1p; J.a1q = s->a1q;
     J.prm = s->prm; J.state = s->state; J.linC = s->linC; J.a0T = s->a0T; J.a1K = s->a1K; J.a0tMin = s->a0tMin; J.a1tMax = s->a1tMax;
     J.soft = s->soft; J.lambda = s->lambda;
     return J;
@@ -97,7 +101,7 @@ int pb_joints_upload(pb_ctx* ctx, int n, const int* type, const int* row0, const
     int rc = 0;
     size_t R = (size_t)MAXR * n;
 #define A(p, cnt) if (!rc) rc = pb_alloc(ctx, &s->p, (cnt))
-    A(type, n); A(rows, n); A(a0p, n); A(a0q, n); A(a1p, n); A(a1q, n); A(prm, 2 * (size_t)n); A(state, 2 * (size_t)n);
+    A(type, n); A(rows, n); A(bodies, n); A(a0p, n); A(a0q, n); A(a1p, n); A(a1q, n); A(prm, 2 * (size_t)n); A(state, 2 * (size_t)n);
     A(linC, R); A(a0T, R); A(a1K, R); A(a0tMin, R); A(a1tMax, R); A(soft, R); A(lambda, R);
 #undef A
     if (rc) return rc;
@@ -153,7 +157,7 @@ int pb_joints_keep_state(pb_ctx* ctx, int n, const int* oldIndex) {
 int pb_joint_begin_step(pb_ctx* ctx) {
     if (!ctx->nJoints) return PB_OK;
     JointDev J = devView(ctx);
-    ++ctx->launches, k_joint_begin<<<pb_grid(J.n, 128), 128, 0, ctx->stream>>>(J, ctx->pos, ctx->quat);
+    ++ctx->launches, k_joint_begin<<<pb_grid(J.n, 128), 128, 0, ctx->stream>>>(J, store(ctx)->bodies, ctx->kinematic, ctx->pos, ctx->quat);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

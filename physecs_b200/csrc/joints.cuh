@@ -23,7 +23,8 @@
 
 struct JointDev {
     int n; int nDyn;
-    const int* type; const int2* rows; const float4* a0p; const float4* a0q; const float4* a1p; const float4* a1q;
+    const int* type; const int2* rows; const int2* bodies;   // bodies: solver index of each side or -1, resolved once per step
+    const float4* a0p; const float4* a0q; const float4* a1p; const float4* a1q;
     const float4* prm;     // [2*J]
     float4* state;         // [2*J] persistent: prismatic {makeUpper, makeLower}, gear {pa0, pa1, va0, va1 | init}
     // rows, index r*J + j
@@ -181,7 +182,7 @@ __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const i
                                     const float4* invIW, float4* pseudoLin, float4* pseudoAng) {
     int type = J.type[j];
     int2 rr = J.rows[j];
-    int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+    int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
     Q4 q0 = mkq(__ldcg(&quat[rr.x])), q1 = mkq(__ldcg(&quat[rr.y]));
     V3 a0p = mk3(J.a0p[j]), a1p = mk3(J.a1p[j]);
     // JointSolverData r0/r1 (Physecs.cpp:344-345) and calculateWorldSpaceData (Joint.cpp:5-14)
@@ -239,6 +240,41 @@ __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const i
     if (b1 >= 0) { pseudoLin[b1] = make_float4(pv1.x, pv1.y, pv1.z, __int_as_float(cnt1)); pseudoAng[b1] = f4(pw1); }
 }
 
+// NGS pseudo-velocity pass of one joint from the rows jointPrepOne(doNgs = 0) stored (Constraint1DW.cpp:57-115): the same
+// lambda = c / k accumulation, row by row, as the fused version above.  Splitting it off lets the expensive row fill run once
+// for all joints in a plain kernel while only this light pass is ordered by joint colour.
+__device__ inline void jointNgsOne(const JointDev& J, int j, const int* __restrict__ kinematic, const float4* __restrict__ comInvMass,
+                                   float4* pseudoLin, float4* pseudoAng) {
+    int type = J.type[j];
+    int2 rr = J.rows[j];
+    int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
+    float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
+    int n = jointRowCount(type, prm0, st0);
+    float im0 = 0.f, im1 = 0.f;
+    V3 pv0 = mk3(0.f), pw0 = mk3(0.f), pv1 = mk3(0.f), pw1 = mk3(0.f);
+    int cnt0 = 0, cnt1 = 0;
+    if (b0 >= 0) { im0 = comInvMass[b0].w; float4 l = __ldcg(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(__ldcg(&pseudoAng[b0])); }
+    if (b1 >= 0) { im1 = comInvMass[b1].w; float4 l = __ldcg(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(__ldcg(&pseudoAng[b1])); }
+    for (int r = 0; r < n; ++r) {
+        int flags = jointRowFlags(type, r, prm0, st0);
+        if (flags & JF_SOFT) continue;
+        int idx = r * J.n + j;
+        float4 LC = __ldcg(&J.linC[idx]), A1 = __ldcg(&J.a1K[idx]), A0t = __ldcg(&J.a0tMin[idx]), A1t = __ldcg(&J.a1tMax[idx]);
+        float c = LC.w, k = A1.w;
+        if (c != 0.f && k != 0.f) {            // masked per lane in the reference (quirk Q10)
+            float lambda = c / k;
+            if (flags & JF_LIMITED) lambda = fminf(fmaxf(lambda, A0t.w), A1t.w);
+            V3 lin = mk3(LC);
+            if (!(flags & JF_ANGULAR)) { pv0 += lambda * (im0 * lin); pv1 -= lambda * (im1 * lin); }
+            pw0 += lambda * mk3(A0t); pw1 -= lambda * mk3(A1t);
+            if (b0 >= 0) ++cnt0;
+            if (b1 >= 0) ++cnt1;
+        }
+    }
+    if (b0 >= 0) { pseudoLin[b0] = make_float4(pv0.x, pv0.y, pv0.z, __int_as_float(cnt0)); pseudoAng[b0] = f4(pw0); }
+    if (b1 >= 0) { pseudoLin[b1] = make_float4(pv1.x, pv1.y, pv1.z, __int_as_float(cnt1)); pseudoAng[b1] = f4(pw1); }
+}
+
 // ---- overflow bucket (joint colour index 8): the reference's scalar, strictly sequential path ----------------------------
 // Joints of the bucket may share bodies, so rows are visited exactly in the reference's order: flag list by flag list
 // (NONE, ANGULAR, SOFT, LIMITED, ANGULAR|SOFT, ANGULAR|LIMITED -- Constraint1DContainer.h:117), joints in creation
@@ -260,7 +296,7 @@ __device__ inline void jointNgsSeq(const JointDev& J, int start, int count, cons
             float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
             int n = jointRowCount(type, prm0, st0);
             int2 rr = J.rows[j];
-            int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+            int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
             float im0 = b0 >= 0 ? comInvMass[b0].w : 0.f, im1 = b1 >= 0 ? comInvMass[b1].w : 0.f;
             for (int r = 0; r < n; ++r) {
                 int flags = jointRowFlags(type, r, prm0, st0);
@@ -298,7 +334,7 @@ __device__ inline void jointSolveSeq(const JointDev& J, int start, int count, fl
             float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
             int n = jointRowCount(type, prm0, st0);
             int2 rr = J.rows[j];
-            int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+            int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
             float im0 = b0 >= 0 ? comInvMass[b0].w : 0.f, im1 = b1 >= 0 ? comInvMass[b1].w : 0.f;
             for (int r = 0; r < n; ++r) {
                 int flags = jointRowFlags(type, r, prm0, st0);
@@ -311,8 +347,8 @@ __device__ inline void jointSolveSeq(const JointDev& J, int start, int count, fl
                 V3 l0t = im0 * lin, l1t = im1 * lin;
                 const bool ang = (flags & JF_ANGULAR) != 0;
                 V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
-                if (b0 >= 0) { if (!ang) v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); }
-                if (b1 >= 0) { if (!ang) v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); }
+                if (b0 >= 0) { if (!ang) v0 = mk3(__ldcg(&velLive[2 * b0])); w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+                if (b1 >= 0) { if (!ang) v1 = mk3(__ldcg(&velLive[2 * b1])); w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
                 float total = __ldcg(&J.lambda[idx]);
                 if (!(flags & JF_SOFT)) {
                     if (warmStart && !((double)fabsf(c) > 1e-4 || fabsf(total) > 10000.f)) {
@@ -343,12 +379,12 @@ __device__ inline void jointSolveSeq(const JointDev& J, int start, int count, fl
                 } else total += lambda;
                 J.lambda[idx] = total;
                 if (b0 >= 0) {
-                    if (!ang) velLive[b0] = f4(mk3(__ldcg(&velLive[b0])) + lambda * l0t);
-                    angvelLive[b0] = f4(mk3(__ldcg(&angvelLive[b0])) + lambda * a0t);
+                    if (!ang) velLive[2 * b0] = f4(mk3(__ldcg(&velLive[2 * b0])) + lambda * l0t, im0);
+                    angvelLive[2 * b0] = f4(mk3(__ldcg(&angvelLive[2 * b0])) + lambda * a0t);
                 }
                 if (b1 >= 0) {
-                    if (!ang) velLive[b1] = f4(mk3(__ldcg(&velLive[b1])) - lambda * l1t);
-                    angvelLive[b1] = f4(mk3(__ldcg(&angvelLive[b1])) - lambda * a1t);
+                    if (!ang) velLive[2 * b1] = f4(mk3(__ldcg(&velLive[2 * b1])) - lambda * l1t, im1);
+                    angvelLive[2 * b1] = f4(mk3(__ldcg(&angvelLive[2 * b1])) - lambda * a1t);
                 }
             }
         }
@@ -407,13 +443,13 @@ __device__ inline void jointSolveOct(const JointDev& J, int j, int lane8, unsign
                                      const float4* __restrict__ comInvMass, float4* velLive, float4* angvelLive) {
     int type = J.type[j];
     int2 rr = J.rows[j];
-    int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+    int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
     float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
     int n = jointRowCount(type, prm0, st0);
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = comInvMass[b0].w; }
-    if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = comInvMass[b1].w; }
+    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
     const float biasFactor = (float)(0.2 / (double)h);
     const bool mine = lane8 < n;
     int flags = 0; float total = 0.f;
@@ -434,8 +470,8 @@ __device__ inline void jointSolveOct(const JointDev& J, int j, int lane8, unsign
     }
     if (mine) J.lambda[idx] = total;
     if (lane8 == 0) {
-        if (b0 >= 0) { velLive[b0] = f4(v0); angvelLive[b0] = f4(w0); }
-        if (b1 >= 0) { velLive[b1] = f4(v1); angvelLive[b1] = f4(w1); }
+        if (b0 >= 0) { velLive[2 * b0] = f4(v0, im0); angvelLive[2 * b0] = f4(w0); }
+        if (b1 >= 0) { velLive[2 * b1] = f4(v1, im1); angvelLive[2 * b1] = f4(w1); }
     }
 }
 
@@ -444,13 +480,13 @@ __device__ inline void jointSolveOne(const JointDev& J, int j, float h, int warm
                                      const float4* __restrict__ comInvMass, float4* velLive, float4* angvelLive) {
     int type = J.type[j];
     int2 rr = J.rows[j];
-    int b0 = jSolverIndex(rr.x, J.nDyn, kinematic), b1 = jSolverIndex(rr.y, J.nDyn, kinematic);
+    int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
     float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
     int n = jointRowCount(type, prm0, st0);
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = comInvMass[b0].w; }
-    if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = comInvMass[b1].w; }
+    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
     const float biasFactor = (float)(0.2 / (double)h);
     for (int r = 0; r < n; ++r) {
         int flags = jointRowFlags(type, r, prm0, st0);
@@ -461,7 +497,7 @@ __device__ inline void jointSolveOne(const JointDev& J, int j, float h, int warm
         jointRowSolve(flags, LC, A0, A1, A0t, A1t, softp, total, h, biasFactor, warmStart, im0, im1, v0, w0, v1, w1);
         J.lambda[idx] = total;
     }
-    if (b0 >= 0) { velLive[b0] = f4(v0); angvelLive[b0] = f4(w0); }
-    if (b1 >= 0) { velLive[b1] = f4(v1); angvelLive[b1] = f4(w1); }
+    if (b0 >= 0) { velLive[2 * b0] = f4(v0, im0); angvelLive[2 * b0] = f4(w0); }
+    if (b1 >= 0) { velLive[2 * b1] = f4(v1, im1); angvelLive[2 * b1] = f4(w1); }
 }
 

@@ -67,6 +67,8 @@ struct pb_ctx {
     int* rowEntity = nullptr;        // [rows] entt::entity integer
     float4* pos = nullptr;           // [rows] xyz
     float4* quat = nullptr;          // [rows] xyzw
+    // velocity buffers interleave {v.xyz, invMass}, {w.xyz, 0} per body: X[2*i] is v of body i, angX == X + 1 so angX[2*i] is w
+    float4* velBuf[3] = {nullptr, nullptr, nullptr};   // owning allocations (2 float4 per body)
     float4* vel = nullptr;           // [dyn] component velocity (substep-start value)
     float4* angvel = nullptr;
     float4* velPre = nullptr;        // [dyn] post-gravity/gyro value friction rows read (quirk Q3)

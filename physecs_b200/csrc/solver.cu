@@ -23,6 +23,8 @@
 //   vel      = component velocity at substep start (what contact prep reads for the friction direction, :406-412)
 //   velPre   = post-gravity/gyro component velocity (what friction rows read all substep long, quirk Q3, ContactConstraints.cpp:92-102)
 //   velLive  = velocityTemp, iterated by the solver; becomes `vel` of the next substep by pointer swap (:523-530).
+// Each buffer interleaves {v.xyz, invMass} and {w.xyz, 0} per body (32 bytes = one DRAM sector), so a solver gather of a
+// body's velocity state is one sector instead of three (v, w and the invMass word of comInvMass).
 // The friction increment relVel_t / kT is therefore constant within a substep and is precomputed in the prep phase.
 //
 // Memory: every array a step mutates is read with __ldcg (L2) -- other SMs write it between barriers and L1 is not
@@ -77,11 +79,15 @@ __device__ __forceinline__ V3 solve33(const M3& A, V3 b) {
 
 // ---- phases (one unit of work each) -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const float4* vel, const float4* angvel, float4* velLive, float4* angvelLive) {
-    if (P.kinematic[i]) return;
+    if (P.kinematic[i]) {    // not integrated (Physecs.cpp:446); the component value just follows the buffer swap
+        velLive[2 * i] = __ldcg(&vel[2 * i]); angvelLive[2 * i] = __ldcg(&angvel[2 * i]);
+        return;
+    }
     M3 rot = mat3_cast(mkq(__ldcg(&P.quat[i])));
     M3 invRot = transpose(rot);
-    V3 v = mk3(__ldcg(&vel[i])) + P.h * mk3(0.f, -P.g, 0.f);
-    V3 wl = mul(invRot, mk3(__ldcg(&angvel[i])));
+    float4 vin = __ldcg(&vel[2 * i]);          // .w carries invMass (the solver's gathers get it for free)
+    V3 v = mk3(vin) + P.h * mk3(0.f, -P.g, 0.f);
+    V3 wl = mul(invRot, mk3(__ldcg(&angvel[2 * i])));
     M3 invI = loadM3ro(P.invIL, i);
     M3 I = inverse(invI);
     V3 Iw = mul(I, wl);
@@ -89,8 +95,8 @@ __device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const 
     M3 J = I + P.h * (mul(matrixCross3(wl), I) - matrixCross3(Iw));
     wl = wl - solve33(J, f);
     V3 w = mul(rot, wl);
-    P.velPre[i] = f4(v); P.angvelPre[i] = f4(w);
-    velLive[i] = f4(v); angvelLive[i] = f4(w);
+    P.velPre[2 * i] = f4(v, vin.w); P.angvelPre[2 * i] = f4(w);
+    velLive[2 * i] = f4(v, vin.w); angvelLive[2 * i] = f4(w);
     P.pseudoLin[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
     P.pseudoAng[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     storeM3(P.invIW, i, mul(mul(rot, invI), invRot));
@@ -110,13 +116,13 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
     if (bb.x >= 0) {
         float4 c = P.comInvMass[bb.x];
         com0 = mk3(__ldcg(&P.pos[rr.x])) + rotate(q0, mk3(c)); im0 = c.w;
-        v0 = mk3(__ldcg(&vel[bb.x])); w0 = mk3(__ldcg(&angvel[bb.x])); vp0 = mk3(__ldcg(&P.velPre[bb.x])); wp0 = mk3(__ldcg(&P.angvelPre[bb.x]));
+        v0 = mk3(__ldcg(&vel[2 * bb.x])); w0 = mk3(__ldcg(&angvel[2 * bb.x])); vp0 = mk3(__ldcg(&P.velPre[2 * bb.x])); wp0 = mk3(__ldcg(&P.angvelPre[2 * bb.x]));
         I0 = loadM3(P.invIW, bb.x);
     }
     if (bb.y >= 0) {
         float4 c = P.comInvMass[bb.y];
         com1 = mk3(__ldcg(&P.pos[rr.y])) + rotate(q1, mk3(c)); im1 = c.w;
-        v1 = mk3(__ldcg(&vel[bb.y])); w1 = mk3(__ldcg(&angvel[bb.y])); vp1 = mk3(__ldcg(&P.velPre[bb.y])); wp1 = mk3(__ldcg(&P.angvelPre[bb.y]));
+        v1 = mk3(__ldcg(&vel[2 * bb.y])); w1 = mk3(__ldcg(&angvel[2 * bb.y])); vp1 = mk3(__ldcg(&P.velPre[2 * bb.y])); wp1 = mk3(__ldcg(&P.angvelPre[2 * bb.y]));
         I1 = loadM3(P.invIW, bb.y);
     }
     int po = hd.z, np = hd.w & 0xff;
@@ -210,15 +216,15 @@ __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int 
         float4 A = __ldcg(&P.rowA[po]), B = __ldcg(&P.rowB[po]), C = __ldcg(&P.rowC[po]), D = __ldcg(&P.rowD[po]);
         float4 E = __ldcg(&P.rowE[po]), F = __ldcg(&P.rowF[po]), G = __ldcg(&P.rowG[po]);
         float2 L = __ldcg(&P.rowL[po]);
-        if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
-        if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+        if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+        if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
         float lamN = L.x, lamT = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
         __stcg(&P.rowL[po], make_float2(lamN, lamT));
     } else {
-        if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
-        if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+        if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+        if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
         float lamN[4], lamT[4];
         for (int k = 0; k < np; ++k) {
             float4 A = __ldcg(&P.rowA[po + k]), B = __ldcg(&P.rowB[po + k]), C = __ldcg(&P.rowC[po + k]), D = __ldcg(&P.rowD[po + k]);
@@ -233,8 +239,8 @@ __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int 
             __stcg(&P.rowL[po + k], make_float2(lamN[k], lamT[k]));
         }
     }
-    if (b0 >= 0) { __stcg(&velLive[b0], f4(v0)); __stcg(&angvelLive[b0], f4(w0)); }
-    if (b1 >= 0) { __stcg(&velLive[b1], f4(v1)); __stcg(&angvelLive[b1], f4(w1)); }
+    if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
+    if (b1 >= 0) { __stcg(&velLive[2 * b1], f4(v1, im1)); __stcg(&angvelLive[2 * b1], f4(w1)); }
 }
 
 // FOUR lanes per manifold: lane k holds point k, so all rows of the manifold are loaded in one wave; the points are then
@@ -262,8 +268,8 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
     }
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { v0 = mk3(__ldcg(&velLive[b0])); w0 = mk3(__ldcg(&angvelLive[b0])); im0 = P.comInvMass[b0].w; }
-    if (b1 >= 0) { v1 = mk3(__ldcg(&velLive[b1])); w1 = mk3(__ldcg(&angvelLive[b1])); im1 = P.comInvMass[b1].w; }
+    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
     float lamN = L.x, lamT = L.y;
 #define PB_PASS_ON(r) \
     v0.x = __shfl_sync(gmask, v0.x, r, 4); v0.y = __shfl_sync(gmask, v0.y, r, 4); v0.z = __shfl_sync(gmask, v0.z, r, 4); \
@@ -281,8 +287,8 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
 #undef PB_PASS_ON
     if (mine) __stcg(&P.rowL[po + lane4], make_float2(lamN, lamT));
     if (lane4 == 0) {
-        if (b0 >= 0) { __stcg(&velLive[b0], f4(v0)); __stcg(&angvelLive[b0], f4(w0)); }
-        if (b1 >= 0) { __stcg(&velLive[b1], f4(v1)); __stcg(&angvelLive[b1], f4(w1)); }
+        if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
+        if (b1 >= 0) { __stcg(&velLive[2 * b1], f4(v1, im1)); __stcg(&angvelLive[2 * b1], f4(w1)); }
     }
 }
 
@@ -294,9 +300,9 @@ __device__ __forceinline__ void integrateX(const SubstepParams& P, int i, const 
     V3 p = mk3(__ldcg(&P.pos[i]));
     Q4 q = mkq(__ldcg(&P.quat[i]));
     V3 com = mk3(P.comInvMass[i]);
-    p = p + (P.h * mk3(__ldcg(&velLive[i])) + scale * mk3(pl));
+    p = p + (P.h * mk3(__ldcg(&velLive[2 * i])) + scale * mk3(pl));
     V3 prevCom = rotate(q, com);
-    V3 hw = 0.5f * (P.h * mk3(__ldcg(&angvelLive[i])) + scale * mk3(__ldcg(&P.pseudoAng[i])));
+    V3 hw = 0.5f * (P.h * mk3(__ldcg(&angvelLive[2 * i])) + scale * mk3(__ldcg(&P.pseudoAng[i])));
     Q4 dq; dq.w = 0.f; dq.x = hw.x; dq.y = hw.y; dq.z = hw.z;
     Q4 add = qmul(dq, q);
     q.x += add.x; q.y += add.y; q.z += add.z; q.w += add.w;
@@ -318,10 +324,11 @@ struct GridBarrier {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
-            __threadfence();
-            atomicAdd(counter, 1u);
-            while (*((volatile unsigned int*)counter) < target) { }
-            __threadfence();
+            // release: the CTA barrier above ordered every thread's writes before this increment (cumulativity);
+            // acquire: the polling load orders every later read of the CTA after the last arrival
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+            unsigned int seen;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
             if (profNs && blockIdx.x == 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -346,8 +353,8 @@ __global__ void __launch_bounds__(128) k_contact_prep(const __grid_constant__ Su
 
 // Joint routines are called, not inlined: their register appetite (row builders, 3x3 products) then spills inside the
 // callee only, and the contact colour loops -- the bandwidth-critical part -- keep a spill-free 64-register budget.
-__device__ __noinline__ void jointPrepCall(const SubstepParams& P, int j, int doNgs) {
-    jointPrepOne(P.J, j, doNgs, P.kinematic, P.pos, P.quat, P.comInvMass, P.invIW, P.pseudoLin, P.pseudoAng);
+__device__ __noinline__ void jointNgsCall(const SubstepParams& P, int j) {
+    jointNgsOne(P.J, j, P.kinematic, P.comInvMass, P.pseudoLin, P.pseudoAng);
 }
 __device__ __noinline__ void jointSolveCall(const SubstepParams& P, int j, int lane8, unsigned gmask, int warmStart, float4* velLive, float4* angvelLive) {
     jointSolveOct(P.J, j, lane8, gmask, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
@@ -362,7 +369,13 @@ __device__ __noinline__ void contactSolveSeqCall(const SubstepParams& P, int sta
     for (int i = 0; i < count; ++i) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive);
 }
 
-// Everything of one substep that is ordered by colour: joint prep (colours share bodies through the pseudo velocities),
+// joint row fill for every joint of the scene (makeConstraints + effective masses): independent of the joint colours
+__global__ void __launch_bounds__(128) k_joint_fill(const __grid_constant__ SubstepParams P) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < P.J.n) jointPrepOne(P.J, j, 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.invIW, P.pseudoLin, P.pseudoAng);
+}
+
+// Everything of one substep that is ordered by colour: joint NGS pass (colours share bodies through the pseudo velocities),
 // the solver iterations (contact colours, then joint colours), position integration and the relaxation pass.
 __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,16 +406,15 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     };
 
     if (P.hasJoints) {
+        // rows were filled by k_joint_fill; the NGS pass accumulates into per-body pseudo velocities, colour by colour
         for (int c = 0; c < 8; ++c) {
             int start = P.jointColorStart[c], count = P.jointColorStart[c + 1] - start;
             if (count <= 0) continue;
-            for (int i = tid; i < count; i += nth) jointPrepCall(P, start + i, 1);
+            for (int i = tid; i < count; i += nth) jointNgsCall(P, start + i);
             bar.sync(PH_PREP);
         }
         int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
-        if (count > 0) {                    // overflow bucket: parallel row fill, then the sequential NGS pass
-            for (int i = tid; i < count; i += nth) jointPrepCall(P, start + i, 0);
-            bar.sync(PH_PREP);
+        if (count > 0) {                    // overflow bucket: the sequential NGS pass
             if (tid == 0) jointNgsSeqCall(P, start, count);
             bar.sync(PH_PREP);
         }
@@ -465,6 +477,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
         P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
         ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(P);
         if (workBound > 0) ++ctx->launches, k_contact_prep<<<pb_grid(workBound, 128), 128, 0, ctx->stream>>>(P);
+        if (P.hasJoints) ++ctx->launches, k_joint_fill<<<pb_grid(ctx->nJoints, 128), 128, 0, ctx->stream>>>(P);
         PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
         void* args[] = { &P };
         ++ctx->launches;
