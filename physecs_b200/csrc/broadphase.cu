@@ -185,7 +185,7 @@ __device__ __forceinline__ int deltaKey(const unsigned int* __restrict__ keys, i
 
 // child encoding: >= 0 internal node index, < 0 leaf: ~(sorted leaf position)
 __global__ void k_lbvh_build(int n, const unsigned int* __restrict__ keys, int* __restrict__ left, int* __restrict__ right,
-                             int* __restrict__ parent, int* __restrict__ leafParent, int* __restrict__ flag) {
+                             int* __restrict__ parent, int* __restrict__ leafParent, int* __restrict__ flag, int2* __restrict__ nodeRange) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     flag[i] = 0;
@@ -209,16 +209,22 @@ __global__ void k_lbvh_build(int n, const unsigned int* __restrict__ keys, int* 
     int lc = (lo == gamma) ? ~gamma : gamma;
     int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     left[i] = lc; right[i] = rc;
+    nodeRange[i] = make_int2(gamma, hi);     // last sorted-leaf position under the left child / under the node
     if (lc >= 0) parent[lc] = i; else leafParent[~lc] = i;
     if (rc >= 0) parent[rc] = i; else leafParent[~rc] = i;
     if (i == 0) parent[0] = -1;
 }
 
 // node layout for traversal: nodeMin[2*i] = left child box min (w = left child), nodeMax[2*i] = left box max (w = right child)
-//                            nodeMin[2*i+1] = right child box min,                nodeMax[2*i+1] = right box max
+//                            nodeMin[2*i+1] = right child box min (w = last sorted-leaf position under the LEFT child,
+//                                             bit 31 = the left subtree holds a non-dynamic collider),
+//                            nodeMax[2*i+1] = right box max (w = last position under the RIGHT child, bit 31 likewise)
 // leaf children are re-encoded as ~colliderIndex so the traversal needs no indirection.
+// The position / flag words let a query at sorted position i skip every subtree that only holds dynamic colliders at
+// positions <= i: those pairs are reported by the other collider's query (each dynamic pair is found exactly once).
 __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* __restrict__ left, const int* __restrict__ right,
                              const int* __restrict__ parent, const int* __restrict__ leafParent, int* __restrict__ flag,
+                             const int2* __restrict__ nodeRange, const int* __restrict__ colFlags,
                              const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
                              float4* __restrict__ nodeMin, float4* __restrict__ nodeMax) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,21 +236,27 @@ __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* _
         int lc = left[p], rc = right[p];
         float4 lmn, lmx, rmn, rmx;
         int lenc, renc;
-        if (lc < 0) { int c = leafId[~lc]; lmn = aabbMin[c]; lmx = aabbMax[c]; lenc = ~c; }
+        unsigned int lstat, rstat;   // subtree holds a collider that never issues a query (static / kinematic / disabled)
+        if (lc < 0) { int c = leafId[~lc]; lmn = aabbMin[c]; lmx = aabbMax[c]; lenc = ~c; lstat = (colFlags[c] & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC); }
         else {
             float4 a0 = __ldcg(&nodeMin[2 * lc]), a1 = __ldcg(&nodeMax[2 * lc]), b0 = __ldcg(&nodeMin[2 * lc + 1]), b1 = __ldcg(&nodeMax[2 * lc + 1]);
+            lstat = ((unsigned int)__float_as_int(b0.w) | (unsigned int)__float_as_int(b1.w)) >> 31;
             lmn = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.f);
             lmx = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
             lenc = lc;
         }
-        if (rc < 0) { int c = leafId[~rc]; rmn = aabbMin[c]; rmx = aabbMax[c]; renc = ~c; }
+        if (rc < 0) { int c = leafId[~rc]; rmn = aabbMin[c]; rmx = aabbMax[c]; renc = ~c; rstat = (colFlags[c] & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC); }
         else {
             float4 a0 = __ldcg(&nodeMin[2 * rc]), a1 = __ldcg(&nodeMax[2 * rc]), b0 = __ldcg(&nodeMin[2 * rc + 1]), b1 = __ldcg(&nodeMax[2 * rc + 1]);
+            rstat = ((unsigned int)__float_as_int(b0.w) | (unsigned int)__float_as_int(b1.w)) >> 31;
             rmn = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.f);
             rmx = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
             renc = rc;
         }
         lmn.w = __int_as_float(lenc); lmx.w = __int_as_float(renc);
+        int2 rg = nodeRange[p];
+        rmn.w = __int_as_float((int)((unsigned int)rg.x | (lstat << 31)));
+        rmx.w = __int_as_float((int)((unsigned int)rg.y | (rstat << 31)));
         nodeMin[2 * p] = lmn; nodeMax[2 * p] = lmx; nodeMin[2 * p + 1] = rmn; nodeMax[2 * p + 1] = rmx;
         p = parent[p];
     }
@@ -290,7 +302,11 @@ __global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* _
         int node = stack[--sp];
         float4 lmn = nodeMin[2 * node], lmx = nodeMax[2 * node], rmn = nodeMin[2 * node + 1], rmx = nodeMax[2 * node + 1];
         int lc = __float_as_int(lmn.w), rc = __float_as_int(lmx.w);
-        bool ol = overlaps(amn, amx, lmn, lmx), orr = overlaps(amn, amx, rmn, rmx);
+        unsigned int lw = (unsigned int)__float_as_int(rmn.w), rw = (unsigned int)__float_as_int(rmx.w);
+        int llast = (int)(lw & 0x7fffffffu), rlast = (int)(rw & 0x7fffffffu);
+        // a subtree of dynamic colliders that all sort at or before this query is the other side's job
+        bool ol = ((lw >> 31) || llast > i) && overlaps(amn, amx, lmn, lmx);
+        bool orr = ((rw >> 31) || rlast > i) && overlaps(amn, amx, rmn, rmx);
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
             bool o = side ? orr : ol;
@@ -301,7 +317,8 @@ __global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* _
             if (b == a) continue;
             int fb = colFlags[b];
             if (!(fb & COLF_ENABLE)) continue;
-            if ((fb & COLF_DYNAMIC) && b < a) continue;     // dynamic-dynamic pairs are found from both sides: keep one
+            // a leaf child sits at position llast (left) / llast + 1 (right): dynamic-dynamic pairs are emitted by the earlier one
+            if ((fb & COLF_DYNAMIC) && (side ? llast + 1 : llast) < i) continue;
             if (colRow[b] == rowA) continue;                // same entity (Physecs.cpp:145)
             emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
         }
@@ -322,9 +339,9 @@ int pb_broadphase(pb_ctx* ctx) {
     if (rc) return rc;
     unsigned int* keys = inA ? ctx->mortonA : ctx->mortonB;
     int* ids = inA ? ctx->leafIdA : ctx->leafIdB;
-    ++ctx->launches, k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag);
+    ++ctx->launches, k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag, ctx->nodeRange);
     ++ctx->launches, k_lbvh_refit<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ids, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag,
-                                                            ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
+                                                            ctx->nodeRange, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
     ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());

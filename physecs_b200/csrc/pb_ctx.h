@@ -107,7 +107,7 @@ struct pb_ctx {
     unsigned int* radixHist = nullptr; int radixTiles = 0;
     float* sceneBounds = nullptr;    // 6 floats (ordered-int encoded) min/max of AABB centres
     int* nodeLeft = nullptr; int* nodeRight = nullptr; int* nodeParent = nullptr; int* leafParent = nullptr;
-    int* nodeRangeLast = nullptr; int* nodeFlag = nullptr;
+    int2* nodeRange = nullptr; int* nodeFlag = nullptr;
     float4* nodeMin = nullptr; float4* nodeMax = nullptr;
     int2* pairs = nullptr;           // [maxPairs] (colA, colB); A is the lower-entity side
     int* pairOrder = nullptr;        // [2*maxPairs] pair indices grouped by bin | bin of each pair
