@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--ref-settle", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batched-scenes", type=int, default=4096, help="ragdoll scenes for the sharded-batch section (0 = skip)")
+    ap.add_argument("--scene-bodies", type=int, default=1_000_000, help="bodies for the physecs::Scene end-to-end section (0 = skip)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (never a bench value)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -302,8 +303,10 @@ def main():
 
     # ---- batched independent scenes (BASELINE.json configs[4]): 4096 ragdoll scenes sharded by scene across ranks ----
     if args.batched_scenes > 0:
-        per_rank = args.batched_scenes // world
-        rd = S.ragdolls(per_rank, seed=0xC5 + rank)
+        from physecs_b200 import batch as B
+        b0, b1 = B.shard_range(args.batched_scenes, world, rank)
+        per_rank = b1 - b0
+        rd = S.ragdolls(per_rank, seed=0xC5, first_scene=b0, total_scenes=args.batched_scenes)
         rctx = Context(rd, device=local_rank, max_pairs=64 * rd.n, max_manifolds=16 * rd.n)
         for _ in range(120):
             rctx.step()
@@ -318,11 +321,34 @@ def main():
         barrier(); torch.cuda.synchronize()
         rms = max_over_ranks(r0.elapsed_time(r1))
         rc_ = rctx.counts()
-        out["batched_scenes"] = {"metric": "batched-scene steps/s (4096 independent ragdoll scenes, 11 bodies + 10 joints + ground each, 4 substeps)",
-                                 "value": per_rank * world * args.steps / (rms * 1e-3), "unit": "scene-steps/s", "scenes": per_rank * world,
-                                 "scenes_per_gpu": per_rank, "ms_per_step": rms / args.steps, "scaling": "strong", "bodies": int(rctx.n_dyn) * world,
-                                 "manifolds_last_step": int(rc_.n_manifolds), "joints": len(rd.joints) * world}
+        out["batched_scenes"] = {"metric": "batched-scene steps/s (%d independent ragdoll scenes, 11 bodies + 10 joints + ground each, 4 substeps)" % args.batched_scenes,
+                                 "value": args.batched_scenes * args.steps / (rms * 1e-3), "unit": "scene-steps/s", "scenes": args.batched_scenes,
+                                 "scenes_on_rank0": per_rank, "ms_per_step": rms / args.steps, "scaling": "strong", "sharding": "contiguous blocks of scenes per rank, no collective",
+                                 "bodies_rank0": int(rctx.n_dyn), "manifolds_last_step_rank0": int(rc_.n_manifolds), "joints_rank0": len(rd.joints)}
         rctx.close()
+
+    # ---- the same workload through the host C++ layer: physecs::Scene over an entt::registry (rank 0, N = 1) ------------------
+    if rank == 0 and world == 1 and args.scene_bodies > 0:
+        try:
+            from physecs_b200 import scene_api
+            sd = desc if args.scene_bodies >= n else S.terrain(args.scene_bodies, cells=max(16, int(args.scene_bodies ** 0.5 * 1.024)), drop=0.3)
+            threads = max((os.cpu_count() or 1) - 1, 0)
+            hs = scene_api.HostScene(sd, num_threads=threads, device=local_rank)
+            hs.set_arena_capacity(8 * sd.n + 4096, 6 * sd.n + 4096)
+            for _ in range(args.settle + args.warmup):
+                hs.simulate()
+            tt = time.perf_counter()
+            ks = min(args.steps, 30)
+            for _ in range(ks):
+                hs.simulate()
+            wall = (time.perf_counter() - tt) / ks
+            st = hs.stats()
+            out["e2e_scene"] = {"api": "physecs::Scene::simulate over entt::registry (host gather -> pb_set_state -> pb_step -> pb_get_state -> scatter)",
+                                "value": sd.n_dynamic / wall, "unit": UNIT, "ms_per_step": wall * 1e3, "bodies": sd.n_dynamic, "host_threads": threads + 1,
+                                "gather_ms": st["gather_ms"], "scatter_ms": st["scatter_ms"], "device_ms": st["device_ms"]}
+            hs.close()
+        except Exception as e:
+            out["e2e_scene"] = {"unavailable": str(e)[:200]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -159,12 +159,11 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
     int rc = 0;
 #define A(p, n) if (!rc) rc = pb_alloc(ctx, &ctx->p, (n))
-    A(rowEntity, R); A(pos, R); A(quat, R); A(velBuf[0], 2 * R); A(velBuf[1], 2 * R); A(velBuf[2], 2 * R);
+    A(rowEntity, R); A(pos, R); A(quat, R); A(velBuf[0], 2 * R); A(velBuf[1], 2 * R); A(bodyRec, 8 * R);
     if (!rc) {
-        ctx->vel = ctx->velBuf[0]; ctx->angvel = ctx->velBuf[0] + 1; ctx->velPre = ctx->velBuf[1]; ctx->angvelPre = ctx->velBuf[1] + 1;
-        ctx->velLive = ctx->velBuf[2]; ctx->angvelLive = ctx->velBuf[2] + 1;
+        ctx->vel = ctx->velBuf[0]; ctx->angvel = ctx->velBuf[0] + 1; ctx->velLive = ctx->velBuf[1]; ctx->angvelLive = ctx->velBuf[1] + 1;
     }
-    A(comInvMass, R); A(invIL, 3 * R); A(invIW, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
+    A(comInvMass, R); A(invIL, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
     A(colRow, C); A(colIndex, C); A(colType, C); A(colFlags, C); A(colData, C); A(colMesh, C);
     A(colLPos, C); A(colLQuat, C); A(colParams, C); A(colMat, C); A(colWPos, C); A(colWQuat, C); A(aabbMin, C); A(aabbMax, C);
     A(mortonA, C); A(mortonB, C); A(leafIdA, C); A(leafIdB, C);
@@ -246,7 +245,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pb_joints_free(ctx);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
-    F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(velBuf[2]); F(comInvMass); F(invIL); F(invIW);
+    F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds);

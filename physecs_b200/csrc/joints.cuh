@@ -179,7 +179,7 @@ __device__ inline int buildJointRows(int type, float4 prm0, float4 prm1, float4&
 // inside the persistent substep kernel they are written by other SMs between grid barriers, and L1 is not coherent.
 __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const int* __restrict__ kinematic,
                                     const float4* pos, const float4* quat, const float4* __restrict__ comInvMass,
-                                    const float4* invIW, float4* pseudoLin, float4* pseudoAng) {
+                                    const float4* bodyRec, float4* pseudoLin, float4* pseudoAng) {
     int type = J.type[j];
     int2 rr = J.rows[j];
     int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
@@ -201,11 +201,19 @@ __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const i
     V3 pv0 = mk3(0.f), pw0 = mk3(0.f), pv1 = mk3(0.f), pw1 = mk3(0.f);
     int cnt0 = 0, cnt1 = 0;
     if (b0 >= 0) {
-        im0 = comInvMass[b0].w; I0.c[0] = mk3(__ldcg(&invIW[3 * b0])); I0.c[1] = mk3(__ldcg(&invIW[3 * b0 + 1])); I0.c[2] = mk3(__ldcg(&invIW[3 * b0 + 2]));
+        im0 = comInvMass[b0].w;
+        {   // world inverse inertia from the per-substep body record (solver.cu, BodyRec layout)
+            const float4* r = bodyRec + 8 * (size_t)b0; float4 r2 = __ldcg(r + 2), r6 = __ldcg(r + 6), r7 = __ldcg(r + 7);
+            I0.c[0] = mk3(r6); I0.c[1] = mk3(r6.w, r7.x, r7.y); I0.c[2] = mk3(r7.z, r7.w, r2.w);
+        }
         float4 l = __ldcg(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(__ldcg(&pseudoAng[b0]));
     }
     if (b1 >= 0) {
-        im1 = comInvMass[b1].w; I1.c[0] = mk3(__ldcg(&invIW[3 * b1])); I1.c[1] = mk3(__ldcg(&invIW[3 * b1 + 1])); I1.c[2] = mk3(__ldcg(&invIW[3 * b1 + 2]));
+        im1 = comInvMass[b1].w;
+        {
+            const float4* r = bodyRec + 8 * (size_t)b1; float4 r2 = __ldcg(r + 2), r6 = __ldcg(r + 6), r7 = __ldcg(r + 7);
+            I1.c[0] = mk3(r6); I1.c[1] = mk3(r6.w, r7.x, r7.y); I1.c[2] = mk3(r7.z, r7.w, r2.w);
+        }
         float4 l = __ldcg(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(__ldcg(&pseudoAng[b1]));
     }
     for (int r = 0; r < n; ++r) {

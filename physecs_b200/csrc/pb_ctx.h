@@ -68,16 +68,14 @@ struct pb_ctx {
     float4* pos = nullptr;           // [rows] xyz
     float4* quat = nullptr;          // [rows] xyzw
     // velocity buffers interleave {v.xyz, invMass}, {w.xyz, 0} per body: X[2*i] is v of body i, angX == X + 1 so angX[2*i] is w
-    float4* velBuf[3] = {nullptr, nullptr, nullptr};   // owning allocations (2 float4 per body)
+    float4* velBuf[2] = {nullptr, nullptr};   // owning allocations (2 float4 per body)
     float4* vel = nullptr;           // [dyn] component velocity (substep-start value)
     float4* angvel = nullptr;
-    float4* velPre = nullptr;        // [dyn] post-gravity/gyro value friction rows read (quirk Q3)
-    float4* angvelPre = nullptr;
     float4* velLive = nullptr;       // [dyn] velocityTemp the solver iterates on
     float4* angvelLive = nullptr;
     float4* comInvMass = nullptr;    // [dyn] com xyz, invMass w
     float4* invIL = nullptr;         // [3*dyn] local inverse inertia columns
-    float4* invIW = nullptr;         // [3*dyn] world inverse inertia columns (massTemp)
+    float4* bodyRec = nullptr;       // [8*dyn] per-substep body record for the prep kernels (solver.cu): q, world COM, invMass, v, w, vPre, wPre, world inverse inertia
     int* kinematic = nullptr;        // [dyn]
     float4* pseudoLin = nullptr;     // [dyn] xyz, w = constraintCount (int bits)
     float4* pseudoAng = nullptr;     // [dyn]

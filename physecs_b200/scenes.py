@@ -545,15 +545,18 @@ def ragdoll_template():
     return b.build()
 
 
-def ragdolls(n_scenes=4096, seed=0xC5, substeps=4, iterations=2, spacing=8.0, drop=0.6) -> SceneDesc:
-    """C5: n independent ragdoll scenes (ground box + 11 bodies + 10 joints each) laid out on a grid in one registry."""
+def ragdolls(n_scenes=4096, seed=0xC5, substeps=4, iterations=2, spacing=8.0, drop=0.6, first_scene=0, total_scenes=None) -> SceneDesc:
+    """C5: n independent ragdoll scenes (ground box + 11 bodies + 10 joints each) laid out on a grid in one registry.
+    first_scene / total_scenes select scenes [first_scene, first_scene + n_scenes) of a larger batch (multi-GPU sharding):
+    layout and random root orientations depend on the GLOBAL scene index, so a shard equals that slice of the whole batch."""
     t = ragdoll_template()
     m = t.n  # 12 entities per scene
+    total = n_scenes if total_scenes is None else total_scenes
     rng = SplitMix(seed)
-    side = int(math.ceil(math.sqrt(n_scenes)))
-    s = np.arange(n_scenes)
+    side = int(math.ceil(math.sqrt(total)))
+    s = np.arange(first_scene, first_scene + n_scenes)
     off = np.stack([(s % side - side / 2.0) * spacing, np.zeros(n_scenes), (s // side - side / 2.0) * spacing], 1)
-    rootq = rng.unit_quat(n_scenes).astype(np.float64)
+    rootq = rng.unit_quat(total).astype(np.float64)[first_scene:first_scene + n_scenes]
     pos = np.tile(t.pos.astype(np.float64), (n_scenes, 1)).reshape(n_scenes, m, 3)
     quat = np.tile(t.quat.astype(np.float64), (n_scenes, 1)).reshape(n_scenes, m, 4)
     centre = np.array([0, 1.0, 0])
