@@ -50,6 +50,7 @@ struct SubstepParams {
     const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const int* cPointOfs; const int* cNp;
     const float4* pR0T; const float4* pR1;
     float4* rowA; float4* rowB; float4* rowC; float4* rowD; float4* rowE; float4* rowF; float4* rowG; float2* rowL;
+    int rowExtra;                    // rows of a manifold's FIRST point live at its solve slot s; points k >= 1 at rowExtra + (firstPoint - s) + k - 1
     // joints
     int hasJoints; JointDev J; int jointColorStart[PB_JOINT_COLORS + 1];
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
@@ -84,6 +85,11 @@ __device__ __forceinline__ BodyRec loadBodyRec(const float4* rec, int b) {
     B.I.c[0] = mk3(r6); B.I.c[1] = mk3(r6.w, r7.x, r7.y); B.I.c[2] = mk3(r7.z, r7.w, r2.w);
     return B;
 }
+
+// Row addressing: the first point's rows sit at the manifold's own slot, so the solver can load them together with the
+// header instead of after it (one dependent memory round trip less for the single-point manifolds that dominate big scenes).
+// firstPoint - s is the number of extra points of all earlier manifolds (every manifold has >= 1 point).
+__device__ __forceinline__ int rowIndex(const SubstepParams& P, int s, int po, int k) { return k == 0 ? s : P.rowExtra + (po - s) + (k - 1); }
 
 // ---- phases (one unit of work each) -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const float4* vel, const float4* angvel, float4* velLive, float4* angvelLive) {
@@ -155,14 +161,15 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
             float relT = dot(-t, vp0) + dot(-r0xt, wp0) + dot(t, vp1) + dot(r1xt, wp1);
             lamT0 = relT / kT;
         }
-        __stcg(&P.rowA[po + k], f4(r0xn, cn));
-        __stcg(&P.rowB[po + k], f4(r1xn, kN));
-        __stcg(&P.rowC[po + k], f4(r0xnt, a.w));
-        __stcg(&P.rowD[po + k], f4(r1xnt, lamT0));
-        __stcg(&P.rowE[po + k], f4(t, kT != 0.f ? 1.f : 0.f));
-        __stcg(&P.rowF[po + k], f4(r0xtt, 0.f));
-        __stcg(&P.rowG[po + k], f4(r1xtt, 0.f));
-        __stcg(&P.rowL[po + k], make_float2(0.f, 0.f));
+        const int ri = rowIndex(P, s, po, k);
+        __stcg(&P.rowA[ri], f4(r0xn, cn));
+        __stcg(&P.rowB[ri], f4(r1xn, kN));
+        __stcg(&P.rowC[ri], f4(r0xnt, a.w));
+        __stcg(&P.rowD[ri], f4(r1xnt, lamT0));
+        __stcg(&P.rowE[ri], f4(t, kT != 0.f ? 1.f : 0.f));
+        __stcg(&P.rowF[ri], f4(r0xtt, 0.f));
+        __stcg(&P.rowG[ri], f4(r1xtt, 0.f));
+        __stcg(&P.rowL[ri], make_float2(0.f, 0.f));
     }
 }
 
@@ -206,44 +213,49 @@ __device__ __forceinline__ void frictionRow(float4 D, float4 E, float4 F, float4
 }
 
 __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
+    // first wave: header + every row of the first point (their address is the slot itself, no dependence on the header)
     int4 hd = P.cHead[s];
+    float4 nf = P.cNormal[s];
+    float4 A = __ldcg(&P.rowA[s]), B = __ldcg(&P.rowB[s]), C = __ldcg(&P.rowC[s]), D = __ldcg(&P.rowD[s]);
+    float4 E = __ldcg(&P.rowE[s]), F = __ldcg(&P.rowF[s]), G = __ldcg(&P.rowG[s]);
+    float2 L = __ldcg(&P.rowL[s]);
     const bool isSoft = (hd.w & 0x100) != 0;
     if (skipSoft && isSoft) return;
-    float4 nf = P.cNormal[s];
     float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     V3 n = mk3(nf);
     float friction = nf.w;
     const float h = P.h;
     const int b0 = hd.x, b1 = hd.y, po = hd.z, np = hd.w & 0xff;
+    // second wave: the body velocities (one 32-byte sector per body, invMass rides in v.w)
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
+    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
+    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
     if (np == 1) {
-        // the common case (a body resting on a mesh triangle, a sphere pair): every load of the manifold is issued in one
-        // wave -- the row loads do not depend on the velocity gathers -- so a thread has ~220 bytes in flight at once
-        float4 A = __ldcg(&P.rowA[po]), B = __ldcg(&P.rowB[po]), C = __ldcg(&P.rowC[po]), D = __ldcg(&P.rowD[po]);
-        float4 E = __ldcg(&P.rowE[po]), F = __ldcg(&P.rowF[po]), G = __ldcg(&P.rowG[po]);
-        float2 L = __ldcg(&P.rowL[po]);
-        if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
-        if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
+        // the common case (a body resting on a mesh triangle, a sphere pair): two memory round trips in total
         float lamN = L.x, lamT = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
-        __stcg(&P.rowL[po], make_float2(lamN, lamT));
+        __stcg(&P.rowL[s], make_float2(lamN, lamT));
     } else {
-        if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
-        if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
         float lamN[4], lamT[4];
-        for (int k = 0; k < np; ++k) {
-            float4 A = __ldcg(&P.rowA[po + k]), B = __ldcg(&P.rowB[po + k]), C = __ldcg(&P.rowC[po + k]), D = __ldcg(&P.rowD[po + k]);
-            float2 L = __ldcg(&P.rowL[po + k]);
-            lamN[k] = L.x; lamT[k] = L.y;
-            normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[k]);
+        lamN[0] = L.x; lamT[0] = L.y;
+        normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[0]);
+        for (int k = 1; k < np; ++k) {
+            const int ri = rowIndex(P, s, po, k);
+            float4 Ak = __ldcg(&P.rowA[ri]), Bk = __ldcg(&P.rowB[ri]), Ck = __ldcg(&P.rowC[ri]), Dk = __ldcg(&P.rowD[ri]);
+            float2 Lk = __ldcg(&P.rowL[ri]);
+            lamN[k] = Lk.x; lamT[k] = Lk.y;
+            normalRow(Ak, Bk, Ck, Dk, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[k]);
         }
-        for (int k = 0; k < np; ++k) {
-            float4 E = __ldcg(&P.rowE[po + k]);
-            if (E.w != 0.f)
-                frictionRow(__ldcg(&P.rowD[po + k]), E, __ldcg(&P.rowF[po + k]), __ldcg(&P.rowG[po + k]), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
-            __stcg(&P.rowL[po + k], make_float2(lamN[k], lamT[k]));
+        if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN[0], im0, im1, v0, w0, v1, w1, lamT[0]);
+        __stcg(&P.rowL[s], make_float2(lamN[0], lamT[0]));
+        for (int k = 1; k < np; ++k) {
+            const int ri = rowIndex(P, s, po, k);
+            float4 Ek = __ldcg(&P.rowE[ri]);
+            if (Ek.w != 0.f)
+                frictionRow(__ldcg(&P.rowD[ri]), Ek, __ldcg(&P.rowF[ri]), __ldcg(&P.rowG[ri]), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
+            __stcg(&P.rowL[ri], make_float2(lamN[k], lamT[k]));
         }
     }
     if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
@@ -268,10 +280,11 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
     const bool mine = lane4 < np;
     float4 A = make_float4(0, 0, 0, 0), B = A, C = A, D = A, E = A, F = A, G = A;
     float2 L = make_float2(0.f, 0.f);
+    const int ri = rowIndex(P, s, po, lane4);
     if (mine) {
-        A = __ldcg(&P.rowA[po + lane4]); B = __ldcg(&P.rowB[po + lane4]); C = __ldcg(&P.rowC[po + lane4]); D = __ldcg(&P.rowD[po + lane4]);
-        E = __ldcg(&P.rowE[po + lane4]); F = __ldcg(&P.rowF[po + lane4]); G = __ldcg(&P.rowG[po + lane4]);
-        L = __ldcg(&P.rowL[po + lane4]);
+        A = __ldcg(&P.rowA[ri]); B = __ldcg(&P.rowB[ri]); C = __ldcg(&P.rowC[ri]); D = __ldcg(&P.rowD[ri]);
+        E = __ldcg(&P.rowE[ri]); F = __ldcg(&P.rowF[ri]); G = __ldcg(&P.rowG[ri]);
+        L = __ldcg(&P.rowL[ri]);
     }
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
@@ -292,7 +305,7 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
         PB_PASS_ON(k)
     }
 #undef PB_PASS_ON
-    if (mine) __stcg(&P.rowL[po + lane4], make_float2(lamN, lamT));
+    if (mine) __stcg(&P.rowL[ri], make_float2(lamN, lamT));
     if (lane4 == 0) {
         if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
         if (b1 >= 0) { __stcg(&velLive[2 * b1], f4(v1, im1)); __stcg(&angvelLive[2 * b1], f4(w1)); }
@@ -470,6 +483,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
     P.bodyRec = ctx->bodyRec; P.pseudoLin = ctx->pseudoLin; P.pseudoAng = ctx->pseudoAng;
     P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft;
     P.cPointOfs = ctx->cPointOfsBuf[cur]; P.cNp = ctx->cNpBuf[cur]; P.pR0T = ctx->pR0T[cur]; P.pR1 = ctx->pR1;
+    P.rowExtra = ctx->caps.max_manifolds;
     P.rowA = ctx->rowA; P.rowB = ctx->rowB; P.rowC = ctx->rowC; P.rowD = ctx->rowD; P.rowE = ctx->rowE; P.rowF = ctx->rowF; P.rowG = ctx->rowG; P.rowL = ctx->rowL;
     P.hasJoints = pb_joint_view(ctx, &P.J) ? 1 : 0;
     for (int c = 0; c <= PB_JOINT_COLORS; ++c) P.jointColorStart[c] = ctx->jointColorStart[c];
