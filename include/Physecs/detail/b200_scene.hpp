@@ -36,6 +36,11 @@ public:
     virtual ~OnTriggerExitListener() = default;
 };
 
+struct OverlapHit {
+    entt::entity entity;
+    int colIndex;
+};
+
 enum ContactType { COLLISION, TRIGGER };
 PHYSECS_API ContactType defaultContactFilter(bool isTrigger0, int data0, bool isTrigger1, int data1);
 
@@ -54,6 +59,7 @@ class PHYSECS_API Scene {
     void onDynamicCreate(entt::registry&, entt::entity);
     void onDynamicDelete(entt::registry&, entt::entity);
     void addJoint(Joint* joint);
+    void prepareDevice();
 
 public:
     // numThreads: host worker threads for the registry gather / scatter (the reference's pool runs its narrowphase,
@@ -68,6 +74,13 @@ public:
     void setGravity(float gravity) { this->g = gravity; }
     // == reference Scene::simulate (src/Physecs.cpp:112-561).  Throws std::runtime_error on CUDA failure.
     void simulate(float timeStep);
+
+    // Scene queries (reference Physecs.h:205-207).  They see the state of the last simulate() plus every change announced since
+    // (structural edits, registry.patch<TransformComponent>).  Hits are exact per collider; results of overlap() are sorted by
+    // (entity, collider index).  Triangle-mesh colliders are invisible to both, as in the reference (no ray / overlap routine).
+    entt::entity raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, glm::vec3* hitPos = nullptr);
+    entt::entity raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, const std::function<bool(entt::entity)>& filter, glm::vec3* hitPos = nullptr);
+    std::vector<OverlapHit> overlap(glm::vec3 pos, glm::quat ori, Geometry geometry, int filter);
 
     template <typename T>
     T* createJoint(entt::entity entity0, glm::vec3 anchor0Pos, glm::quat anchor0Or, entt::entity entity1, glm::vec3 anchor1Pos, glm::quat anchor1Or) {

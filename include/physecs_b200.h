@@ -175,6 +175,17 @@ int pb_get_bounds(pb_ctx* ctx, float* out6);
 int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* num_points, float* normal3, float* points24,
                      int* color, int* n);
 
+/* ---- scene queries (reference Scene::raycastClosest / overlap, Physecs.cpp:571-650) -------------------------- */
+/* Every collider hit by each ray within max_dist (leaf bounds test, then the geometry at its current pose; triangle meshes
+ * have no ray routine in the reference).  Rows (ray, entity, colIdx, t), unordered; *n_hits may exceed cap (retry larger).
+ * The caller picks the closest hit that passes its filter (the reference's filter is a host std::function). */
+int pb_query_raycast(pb_ctx* ctx, int n_rays, const float* orig3, const float* dir3, float max_dist, int cap, int* out_ray,
+                     int* out_entity, int* out_col_idx, float* out_t, int* n_hits);
+/* Colliders overlapping a query shape (physecs::overlap, query shape first); filter != 0 keeps colliders whose data & filter
+ * is non-zero.  mesh: convex handle for a convex query shape. */
+int pb_query_overlap(pb_ctx* ctx, const float* pos3, const float* quat4, int type, const float* params4, int mesh, int filter,
+                     int cap, int* out_entity, int* out_col_idx, int* n_hits);
+
 /* optional per-stage CUDA-event profiling (bench.py roofline): stage ids 0 = one contact-solve pass over all
  * colours, 1 = contact prep, 2 = body integration, 3 = joints.  pb_set_profile(ctx,1) resets the accumulators. */
 int pb_set_profile(pb_ctx* ctx, int on);

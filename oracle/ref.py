@@ -174,6 +174,18 @@ class RefScene:
     def set_can_collide(self, e0, e1, can):
         self.lib.ph_set_can_collide(self.h, int(e0), int(e1), int(can))
 
+    def raycast(self, orig, direction, max_dist, mod=0, skip=0):
+        hit = np.zeros(3, np.float32)
+        e = self.lib.ph_raycast(self.h, _p(_f(orig)), _p(_f(direction)), C.c_float(max_dist), int(mod), int(skip), _p(hit))
+        return e, hit
+
+    def overlap(self, pos, quat, gtype, params, mesh=-1, flt=0):
+        cap = 4096
+        out = np.zeros((cap, 2), np.int32)
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        n = self.lib.ph_overlap(self.h, _p(_f(pos)), _p(_f(quat)), int(gtype), _p(prm), int(mesh), int(flt), cap, _p(out, C.c_int))
+        return out[:n]
+
     def triggers(self):
         """Overlapping trigger pairs of the last simulate, rows (e0, c0, e1, c1)."""
         n = self.lib.ph_num_triggers(self.h)

@@ -478,6 +478,22 @@ void ph_add_collider(void* hp, int e, const float* lpos, const float* lquat, int
 }
 void ph_clear_colliders(void* hp, int e) { auto* h = (Harness*)hp; h->scene->clearColliders(h->entities[e]); }
 
+// Scene::raycastClosest (filtered overload) with the filter `entity % mod != skip` (mod 0: accept all)
+int ph_raycast(void* hp, const float* orig, const float* dir, float maxDist, int mod, int skip, float* hitPos3) {
+    auto* h = (Harness*)hp;
+    glm::vec3 hit(0);
+    auto e = h->scene->raycastClosest(v3(orig), v3(dir), maxDist, [=](entt::entity x) { return mod == 0 || (int)((unsigned)x % (unsigned)mod) != skip; }, &hit);
+    for (int k = 0; k < 3; ++k) hitPos3[k] = hit[k];
+    return e == entt::null ? -1 : (int)e;
+}
+// Scene::overlap: rows (entity, colIndex); returns the count
+int ph_overlap(void* hp, const float* pos, const float* quat, int type, const float* params, int mesh, int filter, int cap, int* out2) {
+    auto* h = (Harness*)hp;
+    auto hits = h->scene->overlap(v3(pos), q4(quat), makeGeometry(h, type, params, mesh), filter);
+    for (size_t i = 0; i < hits.size() && (int)i < cap; ++i) { out2[2 * i] = (int)hits[i].entity; out2[2 * i + 1] = hits[i].colIndex; }
+    return (int)hits.size();
+}
+
 int ph_num_dynamic(void* hp) {
     auto* h = (Harness*)hp;
     return (int)h->registry.storage<physecs::RigidBodyDynamicComponent>().size();

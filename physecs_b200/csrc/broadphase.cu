@@ -325,8 +325,9 @@ __global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* _
     }
 }
 
-// n == 2..: general path.  n < 2: no pairs.
-int pb_broadphase(pb_ctx* ctx) {
+// Morton sort + LBVH build + refit over the current collider bounds (n >= 2).  Shared by the step's pair search and the
+// scene queries (queries.cu); ctx->treeLeafIds is the sorted leaf -> collider table of the tree just built.
+int pb_build_tree(pb_ctx* ctx) {
     int n = ctx->nCol;
     if (n < 2) return PB_OK;
     int* sb = (int*)ctx->sceneBounds;
@@ -342,6 +343,18 @@ int pb_broadphase(pb_ctx* ctx) {
     ++ctx->launches, k_lbvh_build<<<pb_grid(n - 1, 256), 256, 0, ctx->stream>>>(n, keys, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag, ctx->nodeRange);
     ++ctx->launches, k_lbvh_refit<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ids, ctx->nodeLeft, ctx->nodeRight, ctx->nodeParent, ctx->leafParent, ctx->nodeFlag,
                                                             ctx->nodeRange, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
+    ctx->treeLeafIds = ids;
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
+// n == 2..: general path.  n < 2: no pairs.
+int pb_broadphase(pb_ctx* ctx) {
+    int n = ctx->nCol;
+    if (n < 2) return PB_OK;
+    int rc = pb_build_tree(ctx);
+    if (rc) return rc;
+    const int* ids = ctx->treeLeafIds;
     ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());

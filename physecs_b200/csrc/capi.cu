@@ -253,7 +253,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
-    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs);
+    F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
@@ -271,6 +271,7 @@ int pb_sync(pb_ctx* ctx) {
 int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, const float* pos3, const float* quat4, const int* kinematic,
                      const float* vel3, const float* angvel3, const float* invMass, const float* com3, const float* invI9) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     int rows = nDyn + nStatic;
     if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
     ctx->nDyn = nDyn; ctx->nStatic = nStatic; ctx->nRows = rows;
@@ -302,6 +303,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
 int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIndex, const float* lpos3, const float* lquat4, const int* type,
                         const float* params4, const int* mesh, const float* material3, const int* flags, const int* data) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
     ctx->nCol = n;
     ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
@@ -482,6 +484,7 @@ int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* pairs2) {
 
 int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
     // one staged H2D burst (13 floats / body), then unpack into the float4 SoA
@@ -503,6 +506,7 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
 
 int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (n <= 0) return PB_OK;
     size_t bytes = sizeof(float) * 8 * (size_t)n;
     int rc = ensureStage(ctx, bytes); if (rc) return rc;
@@ -523,6 +527,7 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
 
 int pb_refresh_bounds(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     return pb_update_bounds_all(ctx, 0.01f, 1);
 }
 
@@ -534,6 +539,7 @@ static int readCounters(pb_ctx* ctx) {
 
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
     int rc;
     cudaEventRecord(ctx->ev[0], ctx->stream);
@@ -593,6 +599,7 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
 
 int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (nStatic != ctx->nStatic) return pb_fail(ctx, PB_EINVAL, "pb_set_static_poses: n_static mismatch");
     if (!nStatic) return PB_OK;
     size_t n = (size_t)nStatic;
@@ -609,6 +616,7 @@ int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float
 
 int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (n <= 0) return PB_OK;
     for (int i = 0; i < n; ++i) if (cols[i] < 0 || cols[i] >= ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_bounds: collider out of range");
     int rc = ensureStage(ctx, sizeof(float) * 7 * (size_t)n); if (rc) return rc;
@@ -622,6 +630,7 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
 
 int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
     cudaSetDevice(ctx->device);
+    ctx->queryTreeValid = false;
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->kinematic, kinematic, sizeof(int) * nDyn, cudaMemcpyHostToDevice, ctx->stream));

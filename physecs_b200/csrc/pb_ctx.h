@@ -106,6 +106,9 @@ struct pb_ctx {
     float* sceneBounds = nullptr;    // 6 floats (ordered-int encoded) min/max of AABB centres
     int* nodeLeft = nullptr; int* nodeRight = nullptr; int* nodeParent = nullptr; int* leafParent = nullptr;
     int2* nodeRange = nullptr; int* nodeFlag = nullptr;
+    const int* treeLeafIds = nullptr;   // sorted leaf -> collider of the last pb_build_tree
+    bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)
+    int* queryOut = nullptr; int queryCap = 0;   // device result buffer of the scene queries (queries.cu)
     float4* nodeMin = nullptr; float4* nodeMax = nullptr;
     int2* pairs = nullptr;           // [maxPairs] (colA, colB); A is the lower-entity side
     int* pairOrder = nullptr;        // [2*maxPairs] pair indices grouped by bin | bin of each pair
@@ -182,6 +185,7 @@ static inline int pb_grid(long long n, int block) { long long g = (n + block - 1
 
 // stage launches (implemented in the .cu files)
 int pb_broadphase(pb_ctx* ctx);
+int pb_build_tree(pb_ctx* ctx);
 int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);
 int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin);
 int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);

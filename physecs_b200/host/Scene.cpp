@@ -328,6 +328,89 @@ const std::vector<glm::vec3>& Scene::getContactPoints() {
     return out;
 }
 
+// ---- scene queries (reference Physecs.cpp:571-688) -------------------------------------------------------------------------------
+// They run on the device tree over the state of the last simulate() plus everything announced since (structural edits,
+// patched transforms): the per-body registry gather of simulate() is not repeated for a query.
+entt::entity Scene::raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, const std::function<bool(entt::entity)>& filter, glm::vec3* hitPos) {
+    Impl& S = *impl;
+    prepareDevice();
+    int cap = 256;
+    std::vector<int> ray, ent, col; std::vector<float> t;
+    int n = 0;
+    for (;;) {
+        ray.resize(cap); ent.resize(cap); col.resize(cap); t.resize(cap);
+        S.check(pb_query_raycast(S.ctx, 1, &rayOrig.x, &rayDir.x, maxDistance, cap, ray.data(), ent.data(), col.data(), t.data(), &n), "pb_query_raycast");
+        if (n <= cap) break;
+        cap = n + 64;
+    }
+    // the closest hit whose entity passes the filter (the reference evaluates the filter per leaf and keeps the nearer subtree hit)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return t[a] != t[b] ? t[a] < t[b] : (unsigned)ent[a] < (unsigned)ent[b]; });
+    for (int i : order) {
+        entt::entity e = (entt::entity)(unsigned)ent[i];
+        if (filter && !filter(e)) continue;
+        if (hitPos) *hitPos = rayOrig + rayDir * t[i];
+        return e;
+    }
+    return entt::null;
+}
+
+// The reference's unfiltered overload hands an EMPTY std::function to the walk, whose `filter && filter(e)` test then rejects
+// every hit (Physecs.cpp:582, :612): it can only return entt::null.  Here the overload accepts every entity, which is what its
+// signature promises; use the filtered overload for bit-for-bit reference behaviour.
+entt::entity Scene::raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, glm::vec3* hitPos) {
+    return raycastClosest(rayOrig, rayDir, maxDistance, std::function<bool(entt::entity)>(), hitPos);
+}
+
+std::vector<OverlapHit> Scene::overlap(glm::vec3 pos, glm::quat ori, Geometry geometry, int filter) {
+    Impl& S = *impl;
+    prepareDevice();
+    float prm[4] = { 0, 0, 0, 0 };
+    int mesh = -1;
+    switch (geometry.type) {
+        case SPHERE: prm[0] = geometry.sphere.radius; break;
+        case CAPSULE: prm[0] = geometry.capsule.halfHeight; prm[1] = geometry.capsule.radius; break;
+        case BOX: std::memcpy(prm, &geometry.box.halfExtents, sizeof(float) * 3); break;
+        case CONVEX_MESH: {
+            std::memcpy(prm, &geometry.convex.scale, sizeof(float) * 3);
+            auto it = S.convexHandle.find(geometry.convex.mesh);
+            if (it == S.convexHandle.end()) {
+                // a convex mesh no collider uses yet: register it with the context for the query
+                const ConvexMesh* m = geometry.convex.mesh;
+                std::vector<float> v((size_t)3 * m->vertices.size()), fn((size_t)3 * m->faces.size()), fc((size_t)3 * m->faces.size());
+                for (int i = 0; i < m->vertices.size(); ++i) std::memcpy(&v[3 * i], &m->vertices[i], sizeof(float) * 3);
+                std::vector<int> off(m->faces.size() + 1, 0), idx;
+                for (size_t f = 0; f < m->faces.size(); ++f) {
+                    idx.insert(idx.end(), m->faces[f].indices.begin(), m->faces[f].indices.end());
+                    off[f + 1] = (int)idx.size();
+                    std::memcpy(&fn[3 * f], &m->faces[f].normal, sizeof(float) * 3);
+                    std::memcpy(&fc[3 * f], &m->faces[f].centroid, sizeof(float) * 3);
+                }
+                int h = -1;
+                S.check(pb_register_convex(S.ctx, v.data(), m->vertices.size(), off.data(), idx.data(), (int)m->faces.size(), fn.data(), fc.data(), &h), "pb_register_convex");
+                it = S.convexHandle.emplace(m, h).first;
+            }
+            mesh = it->second;
+        } break;
+        case TRIANGLE_MESH: return {};      // physecs::overlap has no triangle-mesh case
+    }
+    float q[4] = { ori.x, ori.y, ori.z, ori.w };
+    int cap = 256, n = 0;
+    std::vector<int> ent, col;
+    for (;;) {
+        ent.resize(cap); col.resize(cap);
+        S.check(pb_query_overlap(S.ctx, &pos.x, q, (int)geometry.type, prm, mesh, filter, cap, ent.data(), col.data(), &n), "pb_query_overlap");
+        if (n <= cap) break;
+        cap = n + 64;
+    }
+    std::vector<OverlapHit> out((size_t)n);
+    for (int i = 0; i < n; ++i) out[i] = { (entt::entity)(unsigned)ent[i], col[i] };
+    std::sort(out.begin(), out.end(), [](const OverlapHit& a, const OverlapHit& b) {
+        return a.entity != b.entity ? entt::to_integral(a.entity) < entt::to_integral(b.entity) : a.colIndex < b.colIndex; });
+    return out;
+}
+
 // ---- the step ----------------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -339,9 +422,10 @@ inline T& packedAt(entt::storage_for_t<T>& st, size_t pos) {
 
 } // namespace
 
-void Scene::simulate(float timeStep) {
+// Bring the device scene description up to date with everything the signals / API calls recorded since the last step:
+// structural changes, joints, non-colliding pairs, contact filter, patched transforms.  Shared by simulate() and the queries.
+void Scene::prepareDevice() {
     Impl& S = *impl;
-    auto tStart = Clock::now();
     auto& dynStore = registry.storage<RigidBodyDynamicComponent>();
     auto& colStore = registry.storage<RigidBodyCollisionComponent>();
     auto& trStore = registry.storage<TransformComponent>();
@@ -576,7 +660,6 @@ void Scene::simulate(float timeStep) {
     };
 
     if (S.topologyDirty) rebuild(false);
-    const int nDyn = S.nDyn, nStatic = S.nStatic;
     if (S.jointsDirty) uploadJoints();
     else {
         bool dirty = false;
@@ -608,6 +691,15 @@ void Scene::simulate(float timeStep) {
         if (!rows.empty()) S.check(pb_move_rows(S.ctx, (int)rows.size(), rows.data(), p.data(), q.data()), "pb_move_rows");
         S.moved.clear();
     }
+}
+
+void Scene::simulate(float timeStep) {
+    Impl& S = *impl;
+    auto tStart = Clock::now();
+    prepareDevice();
+    auto& dynStore = registry.storage<RigidBodyDynamicComponent>();
+    auto& trStore = registry.storage<TransformComponent>();
+    const int nDyn = S.nDyn, nStatic = S.nStatic;
 
     // ---- gather: registry -> pinned SoA ------------------------------------------------------------------------------------------
     auto tGather = Clock::now();

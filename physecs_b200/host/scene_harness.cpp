@@ -269,6 +269,27 @@ void psh_get_state(void* hp, float* pos, float* quat, float* vel, float* angvel)
     }
 }
 
+// Scene::raycastClosest with a filter that accepts entities whose integer id % mod != skip (mod == 0: accept all);
+// returns the entity (or -1) and writes the hit position
+int psh_raycast(void* hp, const float* orig, const float* dir, float maxDist, int mod, int skip, float* hitPos3) {
+    auto* h = (Harness*)hp;
+    glm::vec3 hit(0);
+    try {
+        auto e = h->scene->raycastClosest(v3(orig), v3(dir), maxDist, [=](entt::entity x) { return mod == 0 || (int)((unsigned)x % (unsigned)mod) != skip; }, &hit);
+        for (int k = 0; k < 3; ++k) hitPos3[k] = hit[k];
+        return e == entt::null ? -1 : (int)e;
+    } catch (const std::exception& ex) { h->error = ex.what(); return -2; }
+}
+// Scene::overlap with a query shape; rows (entity, colIndex); returns the count (or < 0 on error)
+int psh_overlap(void* hp, const float* pos, const float* quat, int type, const float* params, int mesh, int filter, int cap, int* out2) {
+    auto* h = (Harness*)hp;
+    try {
+        auto hits = h->scene->overlap(v3(pos), q4(quat), makeGeometry(h, type, params, mesh), filter);
+        for (size_t i = 0; i < hits.size() && (int)i < cap; ++i) { out2[2 * i] = (int)hits[i].entity; out2[2 * i + 1] = hits[i].colIndex; }
+        return (int)hits.size();
+    } catch (const std::exception& ex) { h->error = ex.what(); return -1; }
+}
+
 // the Scene's C-ABI context (pb_ctx*) for the parity taps, and the statistics of the last step
 void* psh_native_context(void* hp) { return ((Harness*)hp)->scene->nativeContext(); }
 void psh_get_stats(void* hp, double* out9) {

@@ -22,7 +22,7 @@ EXPORTS = [
     "psh_add_collider", "psh_clear_colliders", "psh_add_joint", "psh_set_revolute_drive", "psh_destroy_joint", "psh_set_params",
     "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter", "psh_record_trigger_events",
     "psh_take_trigger_events", "psh_set_state", "psh_simulate", "psh_num_entities", "psh_get_state", "psh_native_context",
-    "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity",
+    "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity", "psh_raycast", "psh_overlap",
 ]
 
 _lib = None
@@ -171,6 +171,23 @@ class HostScene:
     def set_revolute_drive(self, j, enabled, velocity, max_torque):
         if self.lib.psh_set_revolute_drive(self.h, int(j), int(enabled), C.c_float(velocity), C.c_float(max_torque)) != 0:
             raise SceneError("joint is not a RevoluteJoint")
+
+    def raycast(self, orig, direction, max_dist, mod=0, skip=0):
+        """Scene::raycastClosest with the filter `entity % mod != skip` (mod 0 = accept all): (entity or -1, hit position)."""
+        hit = np.zeros(3, np.float32)
+        e = self.lib.psh_raycast(self.h, _p(_f(orig)), _p(_f(direction)), C.c_float(max_dist), int(mod), int(skip), _p(hit))
+        if e == -2:
+            raise SceneError(self._err())
+        return e, hit
+
+    def overlap(self, pos, quat, gtype, params, mesh=-1, flt=0):
+        cap = 4096
+        out = np.zeros((cap, 2), np.int32)
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        n = self.lib.psh_overlap(self.h, _p(_f(pos)), _p(_f(quat)), int(gtype), _p(prm), int(mesh), int(flt), cap, _p(out, C.c_int))
+        if n < 0:
+            raise SceneError(self._err())
+        return out[:n]
 
     def stats(self):
         out = (C.c_double * 9)()
