@@ -89,6 +89,11 @@ class RefScene:
         except Exception:
             pass
 
+    def presort(self):
+        """Stable-sort the Scene's broadphase entries by bounds.min.x, as its own first-step insertion sort would (O(n log n)
+        instead of O(n^2)); makes the oracle usable on freshly created 100k..1M-collider scenes."""
+        self.lib.ph_presort(self.h)
+
     def simulate(self, dt=None):
         """One Scene::simulate; returns its wall time in ms."""
         return float(self.lib.ph_simulate(self.h, C.c_float(self.desc.dt if dt is None else dt)))
@@ -136,7 +141,7 @@ class RefScene:
     def narrowphase(self, pairs4):
         """physecs::collision on the current state for pairs (e0,c0,e1,c1). Returns dict like Context.manifolds()."""
         pr = _i(pairs4).reshape(-1, 4)
-        cap = max(8 * len(pr), 64)
+        cap = max(8 * len(pr), 64) if len(pr) < 100_000 else 2 * len(pr)   # retried below if a mesh pair list outgrows it
         while True:
             keys = np.zeros((cap, 5), np.int32); nrm = np.zeros((cap, 3), np.float32); pts = np.zeros((cap, 4, 2, 3), np.float32)
             m = self.lib.ph_narrowphase(self.h, _p(pr, C.c_int), len(pr), cap, _p(keys, C.c_int), _p(nrm), _p(pts))

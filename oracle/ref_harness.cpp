@@ -29,6 +29,7 @@
 #include <GearJoint.h>
 #include <ServoJoint.h>
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -492,6 +493,17 @@ int ph_overlap(void* hp, const float* pos, const float* quat, int type, const fl
     auto hits = h->scene->overlap(v3(pos), q4(quat), makeGeometry(h, type, params, mesh), filter);
     for (size_t i = 0; i < hits.size() && (int)i < cap; ++i) { out2[2 * i] = (int)hits[i].entity; out2[2 * i + 1] = hits[i].colIndex; }
     return (int)hits.size();
+}
+
+// Bring broadPhaseEntries into the order the reference's own insertion sort (Physecs.cpp:121-133) leaves them in -- that sort
+// shifts an entry left only past entries with a strictly larger bounds.min.x, i.e. it is a stable sort by min.x -- but in
+// O(n log n).  The first simulate() of a freshly filled 100k..1M-collider scene otherwise spends minutes in that O(n^2) pass
+// (75 s at 100k, 570 s at 250k); results are unchanged (same final order), only the checker gets usable at full size.
+void ph_presort(void* hp) {
+    auto* h = (Harness*)hp;
+    auto& be = h->scene->broadPhaseEntries;
+    std::stable_sort(be.begin(), be.end(), [](const auto& a, const auto& b) { return a.bounds.min.x < b.bounds.min.x; });
+    for (size_t i = 0; i < be.size(); ++i) h->scene->colToBroadPhaseEntry[{ be[i].entity, be[i].colliderIndex }] = (int)i;
 }
 
 int ph_num_dynamic(void* hp) {

@@ -75,6 +75,49 @@ def compare_manifolds(gm, rm, tol=TOL, allow_tri_alias=False):
     return len(r), worst
 
 
+# ---- vectorised variants for BASELINE.json's full sizes (10^5 .. 10^6 bodies, millions of pairs / manifolds) -------------
+def _lexorder(rows):
+    rows = np.asarray(rows)
+    return np.lexsort(rows.T[::-1])
+
+
+def compare_pairs_bulk(gpu_pairs, ref_pairs):
+    g = np.asarray(gpu_pairs, np.int32).reshape(-1, 4); r = np.asarray(ref_pairs, np.int32).reshape(-1, 4)
+    g = g[_lexorder(g)]; r = r[_lexorder(r)]
+    assert len(g) < 2 or (g[1:] != g[:-1]).any(1).all(), "device emitted duplicate pairs"
+    assert g.shape == r.shape and np.array_equal(g, r), f"pair sets differ: {len(g)} device vs {len(r)} reference pairs"
+    return len(g)
+
+
+def compare_bounds_bulk(ctx, ref):
+    ids, rb = ref.bounds()
+    gb = ctx.bounds()
+    gk = ctx.col_entity.astype(np.int64) * 65536 + ctx.col_index
+    rk = ids[:, 0].astype(np.int64) * 65536 + ids[:, 1]
+    go, ro = np.argsort(gk), np.argsort(rk)
+    assert np.array_equal(gk[go], rk[ro]), "collider sets differ"
+    a, b = gb[go], rb[ro]
+    same = (a.view(np.int32) == b.view(np.int32)) | (a == b)
+    assert same.all(), f"{(~same).any(1).sum()} of {len(a)} collider bounds differ"
+    return len(a)
+
+
+def compare_manifolds_bulk(gm, rm, tol=TOL):
+    gk = np.asarray(gm["keys"], np.int32); rk = np.asarray(rm["keys"], np.int32)
+    go, ro = _lexorder(gk), _lexorder(rk)
+    gk, rk = gk[go], rk[ro]
+    assert len(gk) < 2 or (gk[1:] != gk[:-1]).any(1).all(), "duplicate manifold keys on the device"
+    assert gk.shape == rk.shape and np.array_equal(gk, rk), f"manifold key sets differ: {len(gk)} device vs {len(rk)} reference"
+    gn, rn = np.asarray(gm["num_points"])[go], np.asarray(rm["num_points"])[ro]
+    assert np.array_equal(gn, rn), f"numPoints differ on {(gn != rn).sum()} manifolds"
+    a, b = gm["normal"][go], rm["normal"][ro]
+    assert close(a, b, tol).all(), "normals differ"
+    mask = (np.arange(4)[None, :] < rn[:, None])[:, :, None, None]
+    pa, pb = np.where(mask, gm["points"][go], 0), np.where(mask, rm["points"][ro], 0)
+    assert close(pa, pb, tol).all(), "contact points differ"
+    return len(rk), max(max_err(pa, pb), max_err(a, b))
+
+
 def sync_device_to_oracle(ctx, ref):
     """Teacher forcing: copy the oracle's current state (all dynamic entities) into the device context."""
     p, q, v, w = ref.get_state()
@@ -118,37 +161,43 @@ def compare_triggers(gpu_trig, ref_trig):
     return len(g)
 
 
-def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=False, contact_filter=0):
+def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=False, contact_filter=0, bulk=False, caps=None):
     """All three gates on `steps` consecutive steps, teacher-forced from the oracle's trajectory.
-    Returns a summary dict.  Needs a CUDA device (device path) and oracle/_ref (checker)."""
+    Returns a summary dict.  Needs a CUDA device (device path) and oracle/_ref (checker).
+    bulk: vectorised comparisons + the oracle's broadphase entries pre-sorted (full-size scenes)."""
     from oracle.ref import RefScene
     from physecs_b200.capi import Context
     ref = RefScene(desc, ref_threads, hashfix=True)
-    ctx = Context(desc)
+    if bulk:
+        ref.presort()
+    ctx = Context(desc, **(caps or {}))
+    cmp_bounds = compare_bounds_bulk if bulk else compare_bounds
+    cmp_pairs = compare_pairs_bulk if bulk else compare_pairs
+    cmp_manifolds = compare_manifolds_bulk if bulk else compare_manifolds
     summary = dict(steps=0, pairs=0, manifolds=0, worst_manifold=0.0, worst_solve={}, triggers=0, trigger_changes=0)
     prev_trig = set()
     if contact_filter:
         ref.set_contact_filter(contact_filter)
         ctx.set_contact_filter(FILTERS[contact_filter])
     try:
-        compare_bounds(ctx, ref)
+        cmp_bounds(ctx, ref)
         for k in range(steps):
             sync_device_to_oracle(ctx, ref)
             if k > 0:
                 ctx.refresh_bounds()
-                compare_bounds(ctx, ref)
+                cmp_bounds(ctx, ref)
             ctx.step()
             gm = ctx.manifolds()
             gp = ctx.pairs()
             if k % check_every == 0:
                 rm = ref.narrowphase(gp)
-                nm, worst = compare_manifolds(gm, rm, tol)
+                nm, worst = cmp_manifolds(gm, rm, tol)
                 summary["worst_manifold"] = max(summary["worst_manifold"], worst)
             ref.set_manifold_order(gm["keys"])
             ref.simulate()
             matched, missing, extra = ref.order_stats()
             assert missing == 0 and extra == 0, f"step {k}: manifold sets differ: matched={matched} missing={missing} extra={extra}"
-            npairs = compare_pairs(gp, ref.pairs())
+            npairs = cmp_pairs(gp, ref.pairs())
             gt = ctx.triggers()
             summary["triggers"] = max(summary["triggers"], compare_triggers(gt, ref.triggers()))
             cur_trig = pair_set(gt)
