@@ -13,6 +13,7 @@
 // There is no CPU fallback: constructing a Scene without a CUDA device makes the first simulate() throw.
 #pragma once
 #include <functional>
+#include "../BVH.h"
 #include <memory>
 #include <vector>
 #include <entt.hpp>
@@ -39,6 +40,13 @@ public:
 struct OverlapHit {
     entt::entity entity;
     int colIndex;
+};
+
+struct OverlapMtdHit {
+    entt::entity entity;
+    int colIndex;
+    glm::vec3 normal;   // collider -> query shape
+    float mtd;          // deepest penetration along the normal (>= 0)
 };
 
 enum ContactType { COLLISION, TRIGGER };
@@ -77,10 +85,12 @@ public:
 
     // Scene queries (reference Physecs.h:205-207).  They see the state of the last simulate() plus every change announced since
     // (structural edits, registry.patch<TransformComponent>).  Hits are exact per collider; results of overlap() are sorted by
-    // (entity, collider index).  Triangle-mesh colliders are invisible to both, as in the reference (no ray / overlap routine).
+    // (entity, collider index).  Triangle-mesh colliders are invisible to raycastClosest and overlap, as in the reference (no ray / overlap routine).
     entt::entity raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, glm::vec3* hitPos = nullptr);
     entt::entity raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float maxDistance, const std::function<bool(entt::entity)>& filter, glm::vec3* hitPos = nullptr);
     std::vector<OverlapHit> overlap(glm::vec3 pos, glm::quat ori, Geometry geometry, int filter);
+    // one hit per contact manifold between a collider (triangle meshes included: one per touched triangle) and the query shape
+    std::vector<OverlapMtdHit> overlapWithMinTranslationalDistance(glm::vec3 pos, glm::quat ori, Geometry geometry);
 
     template <typename T>
     T* createJoint(entt::entity entity0, glm::vec3 anchor0Pos, glm::quat anchor0Or, entt::entity entity1, glm::vec3 anchor1Pos, glm::quat anchor1Or) {
@@ -101,6 +111,9 @@ public:
     entt::registry& getRegistry() { return registry; }
     // world-space contact points (position1 of every manifold point) of the last step -- debug getter, downloads on call
     const std::vector<glm::vec3>& getContactPoints();
+    // snapshot of the device tree in the reference's node format (debug getters, Physecs.h:227-228); root = getBHVRootId()
+    const std::vector<BVHNode>& getBVH();
+    const int getBHVRootId();
 
     // ---- additions of this implementation ----------------------------------------------------------------------------------
     void setDevice(int cudaDevice);          // before the first simulate(); default 0

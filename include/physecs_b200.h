@@ -186,6 +186,20 @@ int pb_query_raycast(pb_ctx* ctx, int n_rays, const float* orig3, const float* d
 int pb_query_overlap(pb_ctx* ctx, const float* pos3, const float* quat4, int type, const float* params4, int mesh, int filter,
                      int cap, int* out_entity, int* out_col_idx, int* n_hits);
 
+/* Scene::overlapWithMinTranslationalDistance (Physecs.cpp:652-688): physecs::collision(collider, query shape) for every collider
+ * whose bounds meet the query bounds; one row per manifold with points (triangle-mesh colliders give one per touched triangle):
+ * entity, colIdx, normal (collider -> query shape), mtd = deepest penetration along the normal (>= 0).  Rows are unordered.
+ * When *n_hits > cap nothing was written: call again with cap >= *n_hits. */
+int pb_query_overlap_mtd(pb_ctx* ctx, const float* pos3, const float* quat4, int type, const float* params4, int mesh, int cap,
+                         int* out_entity, int* out_col_idx, float* out_normal3, float* out_mtd, int* n_hits);
+
+/* The device tree the queries (and the broadphase) walk, for debug drawing (reference Scene::getBVH / getBHVRootId,
+ * Physecs.cpp:807-813).  Internal nodes 0 .. *n_internal-1, node 0 is the root; per node the boxes of its two children
+ * (min xyz, max xyz, left then right) and two links: >= 0 an internal node, < 0 the collider -1 - link (pb_collider_ids names it).
+ * Fewer than two colliders: *n_internal = 0.  cap < *n_internal: nothing written. */
+int pb_get_tree(pb_ctx* ctx, int cap, float* child_boxes12, int* child_links2, int* n_internal);
+int pb_collider_ids(pb_ctx* ctx, int n, const int* cols, int* out_entity, int* out_col_idx);
+
 /* optional per-stage CUDA-event profiling (bench.py roofline): stage ids 0 = one contact-solve pass over all
  * colours, 1 = contact prep, 2 = body integration, 3 = joints.  pb_set_profile(ctx,1) resets the accumulators. */
 int pb_set_profile(pb_ctx* ctx, int on);

@@ -191,6 +191,14 @@ class RefScene:
         n = self.lib.ph_overlap(self.h, _p(_f(pos)), _p(_f(quat)), int(gtype), _p(prm), int(mesh), int(flt), cap, _p(out, C.c_int))
         return out[:n]
 
+    def overlap_mtd(self, pos, quat, gtype, params, mesh=-1):
+        """Scene::overlapWithMinTranslationalDistance: (rows (entity, colIndex), rows (normal xyz, mtd))."""
+        cap = 4096
+        ids = np.zeros((cap, 2), np.int32); val = np.zeros((cap, 4), np.float32)
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        n = self.lib.ph_overlap_mtd(self.h, _p(_f(pos)), _p(_f(quat)), int(gtype), _p(prm), int(mesh), cap, _p(ids, C.c_int), _p(val))
+        return ids[:n], val[:n]
+
     def triggers(self):
         """Overlapping trigger pairs of the last simulate, rows (e0, c0, e1, c1)."""
         n = self.lib.ph_num_triggers(self.h)

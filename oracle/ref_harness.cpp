@@ -495,6 +495,18 @@ int ph_overlap(void* hp, const float* pos, const float* quat, int type, const fl
     return (int)hits.size();
 }
 
+// Scene::overlapWithMinTranslationalDistance: rows (entity, colIndex), (normal xyz, mtd); returns the count
+int ph_overlap_mtd(void* hp, const float* pos, const float* quat, int type, const float* params, int mesh, int cap, int* out2, float* out4) {
+    auto* h = (Harness*)hp;
+    auto hits = h->scene->overlapWithMinTranslationalDistance(v3(pos), q4(quat), makeGeometry(h, type, params, mesh));
+    for (size_t i = 0; i < hits.size() && (int)i < cap; ++i) {
+        out2[2 * i] = (int)hits[i].entity; out2[2 * i + 1] = hits[i].colIndex;
+        for (int k = 0; k < 3; ++k) out4[4 * i + k] = hits[i].normal[k];
+        out4[4 * i + 3] = hits[i].mtd;
+    }
+    return (int)hits.size();
+}
+
 // Bring broadPhaseEntries into the order the reference's own insertion sort (Physecs.cpp:121-133) leaves them in -- that sort
 // shifts an entry left only past entries with a strictly larger bounds.min.x, i.e. it is a stable sort by min.x -- but in
 // O(n log n).  The first simulate() of a freshly filled 100k..1M-collider scene otherwise spends minutes in that O(n^2) pass

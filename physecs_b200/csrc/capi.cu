@@ -164,8 +164,9 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
         ctx->vel = ctx->velBuf[0]; ctx->angvel = ctx->velBuf[0] + 1; ctx->velLive = ctx->velBuf[1]; ctx->angvelLive = ctx->velBuf[1] + 1;
     }
     A(comInvMass, R); A(invIL, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
-    A(colRow, C); A(colIndex, C); A(colType, C); A(colFlags, C); A(colData, C); A(colMesh, C);
-    A(colLPos, C); A(colLQuat, C); A(colParams, C); A(colMat, C); A(colWPos, C); A(colWQuat, C); A(aabbMin, C); A(aabbMax, C);
+    // + 1: slot nCol holds the query shape of pb_query_overlap_mtd while the bin kernels run on it
+    A(colRow, C); A(colIndex, C); A(colType, C + 1); A(colFlags, C); A(colData, C); A(colMesh, C + 1);
+    A(colLPos, C); A(colLQuat, C); A(colParams, C + 1); A(colMat, C); A(colWPos, C + 1); A(colWQuat, C + 1); A(aabbMin, C); A(aabbMax, C);
     A(mortonA, C); A(mortonB, C); A(leafIdA, C); A(leafIdB, C);
     size_t sortMax = std::max(C, M);
     ctx->radixTiles = (int)((sortMax + 511) / 512);
@@ -254,6 +255,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
+    F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }

@@ -372,6 +372,42 @@ __global__ void __launch_bounds__(128) k_np_trigger(const int2* __restrict__ pai
     }
 }
 
+// ---- query mode (Scene::overlapWithMinTranslationalDistance, Physecs.cpp:652-688) ------------------------------------------------
+// physecs::collision(collider, query shape) for every candidate pair: the SAME bin kernels as the step, pointed at a private
+// arena.  No trigger / nonColliding filter: the reference's query calls collision() directly (:659).
+__global__ void k_query_classify(const int2* __restrict__ pairs, int* __restrict__ pairBin, int* __restrict__ counters, int cap,
+                                 const int* __restrict__ colType) {
+    int n = min(counters[CNT_PAIRS], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int2 p = pairs[i];
+        int bin = binOf(colType[p.x], colType[p.y]);
+        if (bin >= 0) atomicAdd(&counters[CNT_BIN0 + bin], 1);
+        pairBin[i] = bin;
+    }
+}
+
+int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts) {
+    const int blocks = 8;
+    int* pairBin = pairOrder + cap;
+    ++ctx->launches, k_query_classify<<<blocks, 256, 0, ctx->stream>>>(pairs, pairBin, counters, cap, ctx->colType);
+    ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(counters);
+    ++ctx->launches, k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, pairOrder, counters, cap);
+#define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, pairOrder, counters, ctx->colType, ctx->colParams, \
+        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, mKey, mNormal, mPts, cap)
+    LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
+    if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
+#undef LAUNCH_PRIM
+#define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<blocks, 128, 0, ctx->stream>>>(pairs, pairOrder, counters, ctx->colType, ctx->colParams, ctx->colMesh, \
+        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, mKey, mNormal, mPts, cap)
+    if (!ctx->triMeshes.empty()) {
+        if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
+        LAUNCH_MESH(PB_BOX); LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE);
+    }
+#undef LAUNCH_MESH
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
 int pb_narrowphase(pb_ctx* ctx) {
     if (ctx->nCol < 2) return PB_OK;
     int blocks = ctx->numSMs * 8;

@@ -109,6 +109,9 @@ struct pb_ctx {
     const int* treeLeafIds = nullptr;   // sorted leaf -> collider of the last pb_build_tree
     bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)
     int* queryOut = nullptr; int queryCap = 0;   // device result buffer of the scene queries (queries.cu)
+    // overlapWithMinTranslationalDistance: a private pair / manifold arena the narrowphase bin kernels run on in query mode
+    int* qCounters = nullptr; int2* qPairs = nullptr; int* qPairOrder = nullptr; int4* qmKey = nullptr; float4* qmNormal = nullptr;
+    float4* qmPts = nullptr; int qArenaCap = 0;
     float4* nodeMin = nullptr; float4* nodeMax = nullptr;
     int2* pairs = nullptr;           // [maxPairs] (colA, colB); A is the lower-entity side
     int* pairOrder = nullptr;        // [2*maxPairs] pair indices grouped by bin | bin of each pair
@@ -191,6 +194,8 @@ int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin)
 int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);
 int pb_world_poses(pb_ctx* ctx);
 int pb_narrowphase(pb_ctx* ctx);
+// the same bin kernels on a private arena: pairs (collider, query collider slot) -> manifolds, no filters (queries.cu)
+int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts);
 int pb_contact_build(pb_ctx* ctx, int nRaw);
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound);
 int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset);

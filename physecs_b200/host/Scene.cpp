@@ -110,6 +110,7 @@ inline double msSince(Clock::time_point t0) { return std::chrono::duration<doubl
 } // namespace
 
 struct Scene::Impl {
+    bool queryShape(const Geometry& geometry, float prm[4], int& mesh);
     explicit Impl(int threads) : workers(std::max(threads, 0)) {}
 
     Workers workers;
@@ -157,6 +158,7 @@ struct Scene::Impl {
     ContactType (*filter)(bool, int, bool, int) = defaultContactFilter;
 
     std::vector<glm::vec3> contactPoints;
+    std::vector<BVHNode> bvhSnapshot; int bvhRoot = -1;
     StepStats stats{};
 
     [[noreturn]] void fail(const char* what, int rc) {
@@ -328,6 +330,62 @@ const std::vector<glm::vec3>& Scene::getContactPoints() {
     return out;
 }
 
+const std::vector<BVHNode>& Scene::getBVH() {
+    Impl& S = *impl;
+    auto& out = S.bvhSnapshot;
+    out.clear();
+    S.bvhRoot = BVH::null;
+    prepareDevice();
+    if (!S.ctx) return out;
+    int nInt = 0;
+    S.check(pb_get_tree(S.ctx, 0, nullptr, nullptr, &nInt), "pb_get_tree");
+    auto leafNode = [&](int col, const float* box, int parent) {
+        BVHNode n;
+        n.bounds.min = glm::vec3(box[0], box[1], box[2]); n.bounds.max = glm::vec3(box[3], box[4], box[5]);
+        n.parent = parent; n.isLeaf = true;
+        int e = 0, ci = 0;
+        S.check(pb_collider_ids(S.ctx, 1, &col, &e, &ci), "pb_collider_ids");
+        n.leaf.entity = (entt::entity)(unsigned)e; n.leaf.colliderIndex = ci;
+        return n;
+    };
+    if (nInt == 0) {
+        // zero or one collider: the tree is that leaf
+        int n = (int)S.cols.size();
+        if (n == 1) {
+            std::vector<float> b(6);
+            S.check(pb_get_bounds(S.ctx, b.data()), "pb_get_bounds");
+            out.push_back(leafNode(0, b.data(), BVH::null));
+            S.bvhRoot = 0;
+        }
+        return out;
+    }
+    std::vector<float> boxes((size_t)12 * nInt); std::vector<int> links((size_t)2 * nInt);
+    S.check(pb_get_tree(S.ctx, nInt, boxes.data(), links.data(), &nInt), "pb_get_tree");
+    out.resize(nInt);
+    for (int i = 0; i < nInt; ++i) {
+        BVHNode& n = out[i];
+        n.isLeaf = false;
+        if (i == 0) n.parent = BVH::null;
+        const float* b = &boxes[(size_t)12 * i];
+        n.bounds.min = glm::min(glm::vec3(b[0], b[1], b[2]), glm::vec3(b[6], b[7], b[8]));
+        n.bounds.max = glm::max(glm::vec3(b[3], b[4], b[5]), glm::vec3(b[9], b[10], b[11]));
+    }
+    for (int i = 0; i < nInt; ++i)
+        for (int side = 0; side < 2; ++side) {
+            int link = links[2 * i + side], id;
+            if (link >= 0) { id = link; out[link].parent = i; }
+            else { id = (int)out.size(); out.push_back(leafNode(-1 - link, &boxes[(size_t)12 * i + 6 * side], i)); }
+            if (side == 0) out[i].internal.left = id; else out[i].internal.right = id;
+        }
+    S.bvhRoot = 0;
+    return out;
+}
+
+const int Scene::getBHVRootId() {
+    if (impl->bvhSnapshot.empty()) getBVH();
+    return impl->bvhRoot;
+}
+
 // ---- scene queries (reference Physecs.cpp:571-688) -------------------------------------------------------------------------------
 // They run on the device tree over the state of the last simulate() plus everything announced since (structural edits,
 // patched transforms): the per-body registry gather of simulate() is not repeated for a query.
@@ -363,11 +421,11 @@ entt::entity Scene::raycastClosest(glm::vec3 rayOrig, glm::vec3 rayDir, float ma
     return raycastClosest(rayOrig, rayDir, maxDistance, std::function<bool(entt::entity)>(), hitPos);
 }
 
-std::vector<OverlapHit> Scene::overlap(glm::vec3 pos, glm::quat ori, Geometry geometry, int filter) {
-    Impl& S = *impl;
-    prepareDevice();
-    float prm[4] = { 0, 0, 0, 0 };
-    int mesh = -1;
+// query shape -> (params, convex handle) of the C ABI; false for a triangle mesh (no query routine takes one)
+bool Scene::Impl::queryShape(const Geometry& geometry, float prm[4], int& mesh) {
+    Impl& S = *this;
+    prm[0] = prm[1] = prm[2] = prm[3] = 0.f;
+    mesh = -1;
     switch (geometry.type) {
         case SPHERE: prm[0] = geometry.sphere.radius; break;
         case CAPSULE: prm[0] = geometry.capsule.halfHeight; prm[1] = geometry.capsule.radius; break;
@@ -393,8 +451,17 @@ std::vector<OverlapHit> Scene::overlap(glm::vec3 pos, glm::quat ori, Geometry ge
             }
             mesh = it->second;
         } break;
-        case TRIANGLE_MESH: return {};      // physecs::overlap has no triangle-mesh case
+        case TRIANGLE_MESH: return false;
     }
+    return true;
+}
+
+std::vector<OverlapHit> Scene::overlap(glm::vec3 pos, glm::quat ori, Geometry geometry, int filter) {
+    Impl& S = *impl;
+    prepareDevice();
+    float prm[4];
+    int mesh;
+    if (!S.queryShape(geometry, prm, mesh)) return {};      // physecs::overlap has no triangle-mesh case
     float q[4] = { ori.x, ori.y, ori.z, ori.w };
     int cap = 256, n = 0;
     std::vector<int> ent, col;
@@ -407,6 +474,31 @@ std::vector<OverlapHit> Scene::overlap(glm::vec3 pos, glm::quat ori, Geometry ge
     std::vector<OverlapHit> out((size_t)n);
     for (int i = 0; i < n; ++i) out[i] = { (entt::entity)(unsigned)ent[i], col[i] };
     std::sort(out.begin(), out.end(), [](const OverlapHit& a, const OverlapHit& b) {
+        return a.entity != b.entity ? entt::to_integral(a.entity) < entt::to_integral(b.entity) : a.colIndex < b.colIndex; });
+    return out;
+}
+
+// == reference Scene::overlapWithMinTranslationalDistance (Physecs.cpp:652-688): physecs::collision(collider, query shape) on the
+// device for every collider whose bounds meet the query's; one hit per manifold that has points (a triangle-mesh collider gives
+// one per touched triangle).  Sorted by (entity, collider index); the hits of one mesh collider keep their generation order.
+std::vector<OverlapMtdHit> Scene::overlapWithMinTranslationalDistance(glm::vec3 pos, glm::quat ori, Geometry geometry) {
+    Impl& S = *impl;
+    prepareDevice();
+    float prm[4];
+    int mesh;
+    if (!S.queryShape(geometry, prm, mesh)) throw std::runtime_error("physecs_b200: a triangle mesh cannot be the query shape of overlapWithMinTranslationalDistance");
+    float q[4] = { ori.x, ori.y, ori.z, ori.w };
+    int cap = 256, n = 0;
+    std::vector<int> ent, col; std::vector<float> nrm, mtd;
+    for (;;) {
+        ent.resize(cap); col.resize(cap); nrm.resize((size_t)3 * cap); mtd.resize(cap);
+        S.check(pb_query_overlap_mtd(S.ctx, &pos.x, q, (int)geometry.type, prm, mesh, cap, ent.data(), col.data(), nrm.data(), mtd.data(), &n), "pb_query_overlap_mtd");
+        if (n <= cap) break;
+        cap = n + 64;
+    }
+    std::vector<OverlapMtdHit> out((size_t)n);
+    for (int i = 0; i < n; ++i) out[i] = { (entt::entity)(unsigned)ent[i], col[i], glm::vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), mtd[i] };
+    std::stable_sort(out.begin(), out.end(), [](const OverlapMtdHit& a, const OverlapMtdHit& b) {
         return a.entity != b.entity ? entt::to_integral(a.entity) < entt::to_integral(b.entity) : a.colIndex < b.colIndex; });
     return out;
 }

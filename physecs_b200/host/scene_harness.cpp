@@ -290,6 +290,56 @@ int psh_overlap(void* hp, const float* pos, const float* quat, int type, const f
     } catch (const std::exception& ex) { h->error = ex.what(); return -1; }
 }
 
+// Scene::overlapWithMinTranslationalDistance; rows (entity, colIndex), (normal xyz, mtd); returns the count (or < 0 on error)
+int psh_overlap_mtd(void* hp, const float* pos, const float* quat, int type, const float* params, int mesh, int cap, int* out2, float* out4) {
+    auto* h = (Harness*)hp;
+    try {
+        auto hits = h->scene->overlapWithMinTranslationalDistance(v3(pos), q4(quat), makeGeometry(h, type, params, mesh));
+        for (size_t i = 0; i < hits.size() && (int)i < cap; ++i) {
+            out2[2 * i] = (int)hits[i].entity; out2[2 * i + 1] = hits[i].colIndex;
+            for (int k = 0; k < 3; ++k) out4[4 * i + k] = hits[i].normal[k];
+            out4[4 * i + 3] = hits[i].mtd;
+        }
+        return (int)hits.size();
+    } catch (const std::exception& ex) { h->error = ex.what(); return -1; }
+}
+
+// Scene::getBVH / getBHVRootId: checks the snapshot's structure and returns the number of leaves (< 0: malformed); every leaf's
+// (entity, colIndex, bounds6) is written while room lasts
+int psh_bvh_leaves(void* hp, int cap, int* ids2, float* bounds6) {
+    auto* h = (Harness*)hp;
+    try {
+        const auto& nodes = h->scene->getBVH();
+        int root = h->scene->getBHVRootId();
+        if (nodes.empty()) return root == physecs::BVH::null ? 0 : -2;
+        if (root < 0 || root >= (int)nodes.size() || nodes[root].parent != physecs::BVH::null) return -3;
+        int leaves = 0;
+        std::vector<int> stack{ root };
+        size_t visited = 0;
+        while (!stack.empty()) {
+            int id = stack.back(); stack.pop_back();
+            ++visited;
+            const auto& n = nodes[id];
+            if (n.isLeaf) {
+                if (leaves < cap) {
+                    ids2[2 * leaves] = (int)n.leaf.entity; ids2[2 * leaves + 1] = n.leaf.colliderIndex;
+                    for (int k = 0; k < 3; ++k) { bounds6[6 * leaves + k] = n.bounds.min[k]; bounds6[6 * leaves + 3 + k] = n.bounds.max[k]; }
+                }
+                ++leaves;
+                continue;
+            }
+            for (int child : { n.internal.left, n.internal.right }) {
+                if (child < 0 || child >= (int)nodes.size() || nodes[child].parent != id) return -4;
+                const auto& c = nodes[child];
+                for (int k = 0; k < 3; ++k) if (c.bounds.min[k] < n.bounds.min[k] || c.bounds.max[k] > n.bounds.max[k]) return -5;   // a parent box holds its children
+                stack.push_back(child);
+            }
+        }
+        if (visited != nodes.size()) return -6;
+        return leaves;
+    } catch (const std::exception& ex) { h->error = ex.what(); return -1; }
+}
+
 // the Scene's C-ABI context (pb_ctx*) for the parity taps, and the statistics of the last step
 void* psh_native_context(void* hp) { return ((Harness*)hp)->scene->nativeContext(); }
 void psh_get_stats(void* hp, double* out9) {

@@ -189,6 +189,25 @@ class HostScene:
             raise SceneError(self._err())
         return out[:n]
 
+    def overlap_mtd(self, pos, quat, gtype, params, mesh=-1):
+        """Scene::overlapWithMinTranslationalDistance: (rows (entity, colIndex), rows (normal xyz, mtd))."""
+        cap = 4096
+        ids = np.zeros((cap, 2), np.int32); val = np.zeros((cap, 4), np.float32)
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        n = self.lib.psh_overlap_mtd(self.h, _p(_f(pos)), _p(_f(quat)), int(gtype), _p(prm), int(mesh), cap, _p(ids, C.c_int), _p(val))
+        if n < 0:
+            raise SceneError(self._err())
+        return ids[:n], val[:n]
+
+    def bvh_leaves(self):
+        """Scene::getBVH walked from getBHVRootId (structure checked in the harness): rows (entity, colIndex), bounds rows."""
+        cap = max(len(self.desc.col_type) + 64, 64)
+        ids = np.zeros((cap, 2), np.int32); b = np.zeros((cap, 6), np.float32)
+        n = self.lib.psh_bvh_leaves(self.h, cap, _p(ids, C.c_int), _p(b))
+        if n < 0:
+            raise SceneError(f"malformed BVH snapshot ({n}): {self._err()}")
+        return ids[:n], b[:n]
+
     def stats(self):
         out = (C.c_double * 9)()
         self.lib.psh_get_stats(self.h, out)

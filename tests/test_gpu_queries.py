@@ -1,4 +1,4 @@
-"""-m gpu: scene queries of the host C++ layer (Scene::raycastClosest, Scene::overlap -- SURVEY.md §8f-3) against the reference's
+"""-m gpu: scene queries of the host C++ layer (Scene::raycastClosest, Scene::overlap, Scene::overlapWithMinTranslationalDistance -- SURVEY.md §8f-3) against the reference's
 own Scene on identical registries: before the first step (creation-time bounds) and after stepping (refreshed bounds, moved bodies)."""
 import numpy as np
 import pytest
@@ -27,8 +27,14 @@ def _rays(n, seed, centre, extent):
     return o.astype(np.float32), d.astype(np.float32)
 
 
-def _compare_queries(hs, ref, d, seed, min_found=30):
-    centre = np.array([0.0, 2.0, 0.0]); extent = np.array([16.0, 4.0, 16.0])
+def _mtd_rows(res):
+    ids, val = res
+    rows = [tuple(i) + tuple(v) for i, v in zip(ids.tolist(), val.view(np.int32).tolist())]    # float bits: the comparison is exact
+    return sorted(rows)
+
+
+def _compare_queries(hs, ref, d, seed, min_found=30, centre_y=2.0):
+    centre = np.array([0.0, centre_y, 0.0]); extent = np.array([16.0, 4.0, 16.0])
     o, dr = _rays(400, seed, centre, extent)
     hits = ties = 0
     for i in range(len(o)):
@@ -46,7 +52,7 @@ def _compare_queries(hs, ref, d, seed, min_found=30):
     assert ties <= 0.1 * hits, f"{ties} of {hits} hits name a different entity at equal distance"
     rng = np.random.default_rng(seed + 1)
     meshes = len(d.convex)
-    found = 0
+    found = found_mtd = 0
     for k in range(120):
         pos = (centre + (rng.random(3) - 0.5) * extent * np.array([1, 0.6, 1])).astype(np.float32)
         q = rng.normal(size=4); q = (q / np.linalg.norm(q)).astype(np.float32)
@@ -60,25 +66,52 @@ def _compare_queries(hs, ref, d, seed, min_found=30):
             b = sorted(map(tuple, ref.overlap(pos, q, t, prm, mesh, flt).tolist()))
             assert a == b, f"overlap query {k} (type {t}, filter {flt}): {a[:4]} vs reference {b[:4]}"
             found += len(a)
+        # overlapWithMinTranslationalDistance: one row per manifold of collision(collider, query shape), triangle meshes included
+        a = _mtd_rows(hs.overlap_mtd(pos, q, t, prm, mesh))
+        b = _mtd_rows(ref.overlap_mtd(pos, q, t, prm, mesh))
+        assert a == b, f"overlapWithMinTranslationalDistance query {k} (type {t}): {len(a)} rows {a[:2]} vs reference {len(b)} rows {b[:2]}"
+        found_mtd += len(a)
     assert found > min_found, "overlap queries found almost nothing"
+    assert found_mtd > min_found or min_found == 0, "overlapWithMinTranslationalDistance queries found almost nothing"
 
 
 # (scene, minimum number of overlap results the random queries must find: the 4-ragdoll scene is 48 small bodies, so few are met: any is enough)
-@pytest.mark.parametrize("maker,min_found", [(lambda: S.trigger_zoo(140), 30), (lambda: S.convex_pile(200, mix_prims=True), 30),
-                                             (lambda: S.ragdolls(4), 0)])
-def test_raycast_and_overlap_match_reference(maker, min_found):
+@pytest.mark.parametrize("maker,min_found,centre_y", [(lambda: S.trigger_zoo(140), 30, 2.0), (lambda: S.convex_pile(200, mix_prims=True), 30, 2.0),
+                                                      (lambda: S.ragdolls(4), 0, 2.0), (lambda: S.terrain_mixed(600, cells=40), 30, 0.8)])
+def test_raycast_and_overlap_match_reference(maker, min_found, centre_y):
     from oracle.ref import RefScene
     d = maker()
     ref = RefScene(d, 0, hashfix=True)
     hs = scene_api.HostScene(d, num_threads=2)
     try:
-        _compare_queries(hs, ref, d, 11, min_found)          # before the first simulate: creation-time bounds, no margin
+        _compare_queries(hs, ref, d, 11, min_found, centre_y)          # before the first simulate: creation-time bounds, no margin
         _step_both(hs, ref, 25)
-        _compare_queries(hs, ref, d, 23, min_found)          # after stepping: refreshed bounds, moved bodies
+        _compare_queries(hs, ref, d, 23, min_found, centre_y)          # after stepping: refreshed bounds, moved bodies
         # a static body announced through registry.patch is seen by the next query without a simulate in between
         st = int(d.static_entities()[0])
         for s in (hs, ref):
             s.set_state([st], d.pos[[st]] + np.array([[0.0, 0.4, 0.0]], np.float32), d.quat[[st]], patch=True)
-        _compare_queries(hs, ref, d, 37, min_found)
+        _compare_queries(hs, ref, d, 37, min_found, centre_y)
+    finally:
+        hs.close(); ref.close()
+
+
+def test_bvh_debug_snapshot():
+    """Scene::getBVH / getBHVRootId (debug getters, Physecs.h:227-228): a well-formed tree (checked in the harness: parent links,
+    parent boxes hold their children, every node reachable from the root) whose leaves are exactly the reference Scene's
+    broadphase entries with bit-identical bounds."""
+    from oracle.ref import RefScene
+    d = S.mixed_bin(400, spacing=0.8)
+    ref = RefScene(d, 0, hashfix=True)
+    hs = scene_api.HostScene(d, num_threads=0)
+    try:
+        for phase in range(2):
+            ids, b = hs.bvh_leaves()
+            rid, rb = ref.bounds()
+            assert len(ids) == len(rid) == len(d.col_type)
+            o, ro = np.lexsort(ids.T[::-1]), np.lexsort(rid.T[::-1])
+            assert np.array_equal(ids[o], rid[ro])
+            assert np.array_equal(b[o], rb[ro]), "leaf bounds differ from BroadPhaseEntry::bounds"
+            _step_both(hs, ref, 10)
     finally:
         hs.close(); ref.close()
