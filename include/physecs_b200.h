@@ -204,6 +204,8 @@ int pb_collider_ids(pb_ctx* ctx, int n, const int* cols, int* out_entity, int* o
  * colours, 1 = contact prep, 2 = body integration, 3 = joints.  pb_set_profile(ctx,1) resets the accumulators. */
 int pb_set_profile(pb_ctx* ctx, int on);
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8);
+/* the contact-pass share of it per solver colour: accumulated ms and number of phases for colours 0..63 */
+int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64);
 /* kernels launched by this context since creation */
 unsigned long long pb_get_launches(pb_ctx* ctx);
 /* cudaProfilerStart/Stop, so `ncu --profile-from-start off` captures only the timed region of bench.py */

@@ -269,6 +269,12 @@ class Context:
         names = ["integrate_v", "prep", "contact_pass", "joint_solve", "integrate_x"]
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
+    def profile_colors(self):
+        """(ms, phases) accumulated per contact colour since profiling was switched on."""
+        ms = (C.c_double * 64)(); cnt = (C.c_longlong * 64)()
+        self._check(self.lib.pb_get_profile_colors(self.ctx, ms, cnt))
+        return [(ms[i], cnt[i]) for i in range(64)]
+
     def launches(self):
         return int(self.lib.pb_get_launches(self.ctx))
 

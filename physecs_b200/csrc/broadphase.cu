@@ -282,37 +282,57 @@ __device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ c
     }
 }
 
-// One thread per sorted leaf; only colliders of non-kinematic dynamic bodies issue queries (a pair needs one,
-// Physecs.cpp:147), which keeps huge static boxes / terrain from walking the whole tree.
-__global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* __restrict__ colFlags, const int* __restrict__ colRow,
+// One WARP per 32 consecutive sorted leaves, walking the tree as a packet: the warp keeps one stack (shared memory), pops one
+// node at a time, every lane tests its own box against the two child boxes, and a child is descended when ANY lane overlaps it.
+// Morton-sorted neighbours take nearly the same path, so the union of the 32 paths is a small multiple of one path, while every
+// node is fetched once per warp from one address (a broadcast: 4 L1 wavefronts) instead of 32 lanes fetching 32 different
+// 64-byte nodes (128 wavefronts per step of a per-thread walk -- what bounded the per-thread version at 0.8 ms for 1 M leaves).
+// Only colliders of non-kinematic dynamic bodies issue queries (a pair needs one, Physecs.cpp:147), which keeps huge static
+// boxes / terrain from walking the whole tree; the other lanes carry an empty box.
+#define PAIRS_WARPS 4
+__global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* __restrict__ colFlags, const int* __restrict__ colRow,
                              const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
                              const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax,
                              int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
+    __shared__ int sstack[PAIRS_WARPS][64];
+    const unsigned FULL = 0xffffffffu;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int a = leafId[i];
-    int fa = colFlags[a];
-    if ((fa & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC)) return;
-    V3 amn = mk3(aabbMin[a]), amx = mk3(aabbMax[a]);
-    int rowA = colRow[a];
-    int stack[64];
-    int sp = 0;
-    stack[sp++] = 0;
+    int a = -1, rowA = -1;
+    bool active = false;
+    V3 amn = mk3(FLT_MAX), amx = mk3(-FLT_MAX);     // empty box: overlaps nothing
+    if (i < n) {
+        a = leafId[i];
+        active = (colFlags[a] & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
+        if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = colRow[a]; }
+    }
+    if (!__any_sync(FULL, active)) return;
+    int* st = sstack[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    int sp = 0;                        // warp-uniform
+    if (lane == 0) st[0] = 0;
+    sp = 1;
+    __syncwarp();
     while (sp > 0) {
-        int node = stack[--sp];
+        int node = st[--sp];
+        __syncwarp();                  // everyone has read the slot before lane 0 may overwrite it
         float4 lmn = nodeMin[2 * node], lmx = nodeMax[2 * node], rmn = nodeMin[2 * node + 1], rmx = nodeMax[2 * node + 1];
         int lc = __float_as_int(lmn.w), rc = __float_as_int(lmx.w);
         unsigned int lw = (unsigned int)__float_as_int(rmn.w), rw = (unsigned int)__float_as_int(rmx.w);
         int llast = (int)(lw & 0x7fffffffu), rlast = (int)(rw & 0x7fffffffu);
         // a subtree of dynamic colliders that all sort at or before this query is the other side's job
-        bool ol = ((lw >> 31) || llast > i) && overlaps(amn, amx, lmn, lmx);
-        bool orr = ((rw >> 31) || rlast > i) && overlaps(amn, amx, rmn, rmx);
+        bool ol = active && ((lw >> 31) || llast > i) && overlaps(amn, amx, lmn, lmx);
+        bool orr = active && ((rw >> 31) || rlast > i) && overlaps(amn, amx, rmn, rmx);
+        unsigned int bl = __ballot_sync(FULL, ol), br = __ballot_sync(FULL, orr);
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            bool o = side ? orr : ol;
+            unsigned int any = side ? br : bl;
             int c = side ? rc : lc;
-            if (!o) continue;
-            if (c >= 0) { if (sp < 64) stack[sp++] = c; continue; }
+            if (!any) continue;                          // warp-uniform
+            if (c >= 0) {                                // warp-uniform: the link is the same word for every lane
+                if (sp < 64) { if (lane == 0) st[sp] = c; ++sp; }
+                continue;
+            }
+            if (!(side ? orr : ol)) continue;
             int b = ~c;
             if (b == a) continue;
             int fb = colFlags[b];
@@ -322,6 +342,7 @@ __global__ void k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* _
             if (colRow[b] == rowA) continue;                // same entity (Physecs.cpp:145)
             emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
         }
+        __syncwarp();
     }
 }
 
@@ -355,7 +376,7 @@ int pb_broadphase(pb_ctx* ctx) {
     int rc = pb_build_tree(ctx);
     if (rc) return rc;
     const int* ids = ctx->treeLeafIds;
-    ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 128), 128, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
+    ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

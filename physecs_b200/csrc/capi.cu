@@ -135,6 +135,14 @@ int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
     for (int k = 0; k < 8; ++k) { ms8[k] = k < 5 ? raw[k] * 1e-6 : 0.0; count8[k] = k < 5 ? (long long)raw[5 + k] : 0; }
     return PB_OK;
 }
+int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64) {
+    cudaSetDevice(ctx->device);
+    unsigned long long raw[2 * PB_MAX_COLORS];
+    int rc = pb_solve_profile_colors(ctx, raw);
+    if (rc) return rc;
+    for (int k = 0; k < PB_MAX_COLORS; ++k) { ms64[k] = raw[k] * 1e-6; count64[k] = (long long)raw[PB_MAX_COLORS + k]; }
+    return PB_OK;
+}
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
 void pb_profiler_range(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
 

@@ -199,6 +199,7 @@ int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pai
 int pb_contact_build(pb_ctx* ctx, int nRaw);
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound);
 int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset);
+int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out128);
 int pb_joint_begin_step(pb_ctx* ctx);
 int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew);
 void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long* oldTag, const int4* oldVal, int newSize, unsigned long long* newTag, int4* newVal);

@@ -59,6 +59,7 @@ struct SubstepParams {
 };
 
 enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_KINDS };
+#define PROF_WORDS (2 * PH_KINDS + 2 * PB_MAX_COLORS)   // ns + count per phase kind, then ns + count per contact colour
 
 __device__ __forceinline__ M3 loadM3ro(const float4* __restrict__ p, int i) {
     M3 r; r.c[0] = mk3(p[3 * i]); r.c[1] = mk3(p[3 * i + 1]); r.c[2] = mk3(p[3 * i + 2]); return r;
@@ -84,6 +85,42 @@ __device__ __forceinline__ BodyRec loadBodyRec(const float4* rec, int b) {
     B.q = mkq(r0); B.com = mk3(r1); B.im = r1.w; B.v = mk3(r2); B.w = mk3(r3); B.vp = mk3(r4); B.wp = mk3(r5);
     B.I.c[0] = mk3(r6); B.I.c[1] = mk3(r6.w, r7.x, r7.y); B.I.c[2] = mk3(r7.z, r7.w, r2.w);
     return B;
+}
+
+
+// ---- L2 eviction hints -------------------------------------------------------------------------------------------------------------
+// A contact pass streams ~150 B of rows per manifold (hundreds of MB per pass, no reuse before the next pass: L2 cannot hold
+// them) and gathers / scatters 32-byte velocity records that ARE reused (every body sits in several manifolds, all colours, all
+// passes; 32 MB at 1 M bodies).  Rows are therefore read and written evict-first and velocity records evict-last, so the row
+// stream does not flush the velocity working set out of L2.  All of it stays .cg (L2 only): other SMs write these arrays
+// between grid barriers and L1 is not coherent.
+struct L2Hints { unsigned long long first, last; };
+__device__ __forceinline__ L2Hints makeL2Hints() {
+    L2Hints h;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(h.first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(h.last));
+    return h;
+}
+__device__ __forceinline__ float4 ldHint(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int4 ldHint(const int4* p, unsigned long long pol) {
+    int4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ldHint(const float2* p, unsigned long long pol) {
+    float2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stHint(float4* p, float4 v, unsigned long long pol) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stHint(float2* p, float2 v, unsigned long long pol) {
+    asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
 
 // Row addressing: the first point's rows sit at the manifold's own slot, so the solver can load them together with the
@@ -212,13 +249,13 @@ __device__ __forceinline__ void frictionRow(float4 D, float4 E, float4 F, float4
     v1 -= lambda * im1 * t; w1 -= lambda * mk3(G);
 }
 
-__device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
+__device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int useBias, int skipSoft, float4* velLive, float4* angvelLive, const L2Hints& H) {
     // first wave: header + every row of the first point (their address is the slot itself, no dependence on the header)
-    int4 hd = P.cHead[s];
-    float4 nf = P.cNormal[s];
-    float4 A = __ldcg(&P.rowA[s]), B = __ldcg(&P.rowB[s]), C = __ldcg(&P.rowC[s]), D = __ldcg(&P.rowD[s]);
-    float4 E = __ldcg(&P.rowE[s]), F = __ldcg(&P.rowF[s]), G = __ldcg(&P.rowG[s]);
-    float2 L = __ldcg(&P.rowL[s]);
+    int4 hd = ldHint(&P.cHead[s], H.first);
+    float4 nf = ldHint(&P.cNormal[s], H.first);
+    float4 A = ldHint(&P.rowA[s], H.first), B = ldHint(&P.rowB[s], H.first), C = ldHint(&P.rowC[s], H.first), D = ldHint(&P.rowD[s], H.first);
+    float4 E = ldHint(&P.rowE[s], H.first), F = ldHint(&P.rowF[s], H.first), G = ldHint(&P.rowG[s], H.first);
+    float2 L = ldHint(&P.rowL[s], H.first);
     const bool isSoft = (hd.w & 0x100) != 0;
     if (skipSoft && isSoft) return;
     float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,37 +266,37 @@ __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int 
     // second wave: the body velocities (one 32-byte sector per body, invMass rides in v.w)
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
-    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
+    if (b0 >= 0) { float4 t_ = ldHint(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldHint(&angvelLive[2 * b0], H.last)); }
+    if (b1 >= 0) { float4 t_ = ldHint(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldHint(&angvelLive[2 * b1], H.last)); }
     if (np == 1) {
         // the common case (a body resting on a mesh triangle, a sphere pair): two memory round trips in total
         float lamN = L.x, lamT = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
-        __stcg(&P.rowL[s], make_float2(lamN, lamT));
+        stHint(&P.rowL[s], make_float2(lamN, lamT), H.first);
     } else {
         float lamN[4], lamT[4];
         lamN[0] = L.x; lamT[0] = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[0]);
         for (int k = 1; k < np; ++k) {
             const int ri = rowIndex(P, s, po, k);
-            float4 Ak = __ldcg(&P.rowA[ri]), Bk = __ldcg(&P.rowB[ri]), Ck = __ldcg(&P.rowC[ri]), Dk = __ldcg(&P.rowD[ri]);
-            float2 Lk = __ldcg(&P.rowL[ri]);
+            float4 Ak = ldHint(&P.rowA[ri], H.first), Bk = ldHint(&P.rowB[ri], H.first), Ck = ldHint(&P.rowC[ri], H.first), Dk = ldHint(&P.rowD[ri], H.first);
+            float2 Lk = ldHint(&P.rowL[ri], H.first);
             lamN[k] = Lk.x; lamT[k] = Lk.y;
             normalRow(Ak, Bk, Ck, Dk, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[k]);
         }
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN[0], im0, im1, v0, w0, v1, w1, lamT[0]);
-        __stcg(&P.rowL[s], make_float2(lamN[0], lamT[0]));
+        stHint(&P.rowL[s], make_float2(lamN[0], lamT[0]), H.first);
         for (int k = 1; k < np; ++k) {
             const int ri = rowIndex(P, s, po, k);
-            float4 Ek = __ldcg(&P.rowE[ri]);
+            float4 Ek = ldHint(&P.rowE[ri], H.first);
             if (Ek.w != 0.f)
-                frictionRow(__ldcg(&P.rowD[ri]), Ek, __ldcg(&P.rowF[ri]), __ldcg(&P.rowG[ri]), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
-            __stcg(&P.rowL[ri], make_float2(lamN[k], lamT[k]));
+                frictionRow(ldHint(&P.rowD[ri], H.first), Ek, ldHint(&P.rowF[ri], H.first), ldHint(&P.rowG[ri], H.first), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
+            stHint(&P.rowL[ri], make_float2(lamN[k], lamT[k]), H.first);
         }
     }
-    if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
-    if (b1 >= 0) { __stcg(&velLive[2 * b1], f4(v1, im1)); __stcg(&angvelLive[2 * b1], f4(w1)); }
+    if (b0 >= 0) { stHint(&velLive[2 * b0], f4(v0, im0), H.last); stHint(&angvelLive[2 * b0], f4(w0), H.last); }
+    if (b1 >= 0) { stHint(&velLive[2 * b1], f4(v1, im1), H.last); stHint(&angvelLive[2 * b1], f4(w1), H.last); }
 }
 
 // FOUR lanes per manifold: lane k holds point k, so all rows of the manifold are loaded in one wave; the points are then
@@ -267,11 +304,11 @@ __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int 
 // Same arithmetic as contactSolve; used when manifolds have several points on average (box stacks, ragdolls), where the
 // one-thread version serialises ~3 memory round trips per point.
 __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, int lane4, unsigned gmask, int useBias, int skipSoft,
-                                                 float4* velLive, float4* angvelLive) {
-    int4 hd = P.cHead[s];
+                                                 float4* velLive, float4* angvelLive, const L2Hints& H) {
+    int4 hd = ldHint(&P.cHead[s], H.first);
     const bool isSoft = (hd.w & 0x100) != 0;
     if (skipSoft && isSoft) return;          // uniform across the four lanes
-    float4 nf = P.cNormal[s];
+    float4 nf = ldHint(&P.cNormal[s], H.first);
     float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     V3 n = mk3(nf);
     float friction = nf.w;
@@ -282,14 +319,14 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
     float2 L = make_float2(0.f, 0.f);
     const int ri = rowIndex(P, s, po, lane4);
     if (mine) {
-        A = __ldcg(&P.rowA[ri]); B = __ldcg(&P.rowB[ri]); C = __ldcg(&P.rowC[ri]); D = __ldcg(&P.rowD[ri]);
-        E = __ldcg(&P.rowE[ri]); F = __ldcg(&P.rowF[ri]); G = __ldcg(&P.rowG[ri]);
-        L = __ldcg(&P.rowL[ri]);
+        A = ldHint(&P.rowA[ri], H.first); B = ldHint(&P.rowB[ri], H.first); C = ldHint(&P.rowC[ri], H.first); D = ldHint(&P.rowD[ri], H.first);
+        E = ldHint(&P.rowE[ri], H.first); F = ldHint(&P.rowF[ri], H.first); G = ldHint(&P.rowG[ri], H.first);
+        L = ldHint(&P.rowL[ri], H.first);
     }
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
-    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
+    if (b0 >= 0) { float4 t_ = ldHint(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldHint(&angvelLive[2 * b0], H.last)); }
+    if (b1 >= 0) { float4 t_ = ldHint(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldHint(&angvelLive[2 * b1], H.last)); }
     float lamN = L.x, lamT = L.y;
 #define PB_PASS_ON(r) \
     v0.x = __shfl_sync(gmask, v0.x, r, 4); v0.y = __shfl_sync(gmask, v0.y, r, 4); v0.z = __shfl_sync(gmask, v0.z, r, 4); \
@@ -305,10 +342,10 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
         PB_PASS_ON(k)
     }
 #undef PB_PASS_ON
-    if (mine) __stcg(&P.rowL[ri], make_float2(lamN, lamT));
+    if (mine) stHint(&P.rowL[ri], make_float2(lamN, lamT), H.first);
     if (lane4 == 0) {
-        if (b0 >= 0) { __stcg(&velLive[2 * b0], f4(v0, im0)); __stcg(&angvelLive[2 * b0], f4(w0)); }
-        if (b1 >= 0) { __stcg(&velLive[2 * b1], f4(v1, im1)); __stcg(&angvelLive[2 * b1], f4(w1)); }
+        if (b0 >= 0) { stHint(&velLive[2 * b0], f4(v0, im0), H.last); stHint(&angvelLive[2 * b0], f4(w0), H.last); }
+        if (b1 >= 0) { stHint(&velLive[2 * b1], f4(v1, im1), H.last); stHint(&angvelLive[2 * b1], f4(w1), H.last); }
     }
 }
 
@@ -340,7 +377,7 @@ struct GridBarrier {
     unsigned int target;
     unsigned long long* profNs;
     unsigned long long tPrev;
-    __device__ __forceinline__ void sync(int kind) {
+    __device__ __forceinline__ void sync(int kind, int color = -1) {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
@@ -354,6 +391,7 @@ struct GridBarrier {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                 atomicAdd(&profNs[kind], t - tPrev);
                 atomicAdd(&profNs[PH_KINDS + kind], 1ull);
+                if (color >= 0 && color < PB_MAX_COLORS) { atomicAdd(&profNs[2 * PH_KINDS + color], t - tPrev); atomicAdd(&profNs[2 * PH_KINDS + PB_MAX_COLORS + color], 1ull); }
                 tPrev = t;
             }
         }
@@ -386,7 +424,8 @@ __device__ __noinline__ void jointSolveSeqCall(const SubstepParams& P, int start
     jointSolveSeq(P.J, start, count, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
 }
 __device__ __noinline__ void contactSolveSeqCall(const SubstepParams& P, int start, int count, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
-    for (int i = 0; i < count; ++i) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive);
+    L2Hints H = makeL2Hints();
+    for (int i = 0; i < count; ++i) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
 }
 
 // joint row fill for every joint of the scene (makeConstraints + effective masses): independent of the joint colours
@@ -407,6 +446,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     const int ncol = P.counters[CNT_NCOLORS];
     float4* velLive = P.velB; float4* angvelLive = P.angvelB;
     const int lane = threadIdx.x & 31;
+    const L2Hints H = makeL2Hints();
     // several points per manifold on average -> four lanes per manifold (one memory wave per manifold instead of one per point)
     const bool quad = 2 * (long long)P.counters[CNT_POINTS] > 3 * (long long)P.counters[CNT_MANIFOLDS];
     // one contact pass over all colours, a barrier after each non-empty colour
@@ -417,11 +457,11 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
                 if (tid == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
             } else if (quad) {
-                for (int i = tid >> 2; i < count; i += nth >> 2) contactSolveQuad(P, start + i, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive);
+                for (int i = tid >> 2; i < count; i += nth >> 2) contactSolveQuad(P, start + i, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
             } else {
-                for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive);
+                for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
             }
-            bar.sync(PH_CONTACT_PASS);
+            bar.sync(PH_CONTACT_PASS, c);
         }
     };
 
@@ -471,8 +511,8 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
         if (perSM < 1) return pb_fail(ctx, PB_ECUDA, "k_substep_solve does not fit on an SM");
         ctx->solveGrid = perSM * ctx->numSMs;
         int rc = pb_alloc(ctx, &ctx->solveBarrier, 64); if (rc) return rc;
-        rc = pb_alloc(ctx, &ctx->solveProfNs, 2 * PH_KINDS); if (rc) return rc;
-        PB_CUDA(ctx, cudaMemsetAsync(ctx->solveProfNs, 0, sizeof(unsigned long long) * 2 * PH_KINDS, ctx->stream));
+        rc = pb_alloc(ctx, &ctx->solveProfNs, PROF_WORDS); if (rc) return rc;
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->solveProfNs, 0, sizeof(unsigned long long) * PROF_WORDS, ctx->stream));
     }
     const int cur = ctx->curBuf;
     SubstepParams P{};
@@ -517,6 +557,15 @@ int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset) {
     if (!ctx->solveProfNs) { for (int i = 0; i < 2 * PH_KINDS; ++i) out[i] = 0; return PB_OK; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     PB_CUDA(ctx, cudaMemcpy(out, ctx->solveProfNs, sizeof(unsigned long long) * 2 * PH_KINDS, cudaMemcpyDeviceToHost));
-    if (reset) PB_CUDA(ctx, cudaMemset(ctx->solveProfNs, 0, sizeof(unsigned long long) * 2 * PH_KINDS));
+    if (reset) PB_CUDA(ctx, cudaMemset(ctx->solveProfNs, 0, sizeof(unsigned long long) * PROF_WORDS));
+    return PB_OK;
+}
+
+// per contact colour: accumulated ns and phase count (out[0..63] ns, out[64..127] counts)
+int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out128) {
+    for (int i = 0; i < 2 * PB_MAX_COLORS; ++i) out128[i] = 0;
+    if (!ctx->solveProfNs) return PB_OK;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaMemcpy(out128, ctx->solveProfNs + 2 * PH_KINDS, sizeof(unsigned long long) * 2 * PB_MAX_COLORS, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
