@@ -20,8 +20,8 @@ __device__ __forceinline__ int solverIndex(int row, int nDyn, const int* __restr
 __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counters, int maxManifolds, const int* __restrict__ colRow,
                         int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMask,
                         unsigned int* __restrict__ sortKey, int* __restrict__ sortVal) {
-    __shared__ int hist[PB_MAX_COLORS];
-    if (threadIdx.x < PB_MAX_COLORS) hist[threadIdx.x] = 0;
+    __shared__ int hist[2 * PB_MAX_COLORS];     // [colour] all manifolds, [PB_MAX_COLORS + colour] the single-point ones
+    if (threadIdx.x < 2 * PB_MAX_COLORS) hist[threadIdx.x] = 0;
     __syncthreads();
     int n = min(counters[CNT_RAWM], maxManifolds);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -52,12 +52,17 @@ __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counter
                 }
             }
             atomicAdd(&hist[color], 1);
+            if (key.w == 1) atomicAdd(&hist[PB_MAX_COLORS + color], 1);
+            // inside a colour the single-point manifolds sort first: the solver gives them one thread each and the multi-point
+            // ones four lanes each, so neither path waits on the other's dependent loads
+            color = 2u * color + (key.w > 1 ? 1u : 0u);
         }
         sortKey[i] = color;
         sortVal[i] = i;
     }
     __syncthreads();
     if (threadIdx.x < PB_MAX_COLORS && hist[threadIdx.x]) atomicAdd(&counters[CNT_COLORSTART + threadIdx.x], hist[threadIdx.x]);
+    if (threadIdx.x < PB_MAX_COLORS && hist[PB_MAX_COLORS + threadIdx.x]) atomicAdd(&counters[CNT_MULTISTART + threadIdx.x], hist[PB_MAX_COLORS + threadIdx.x]);
 }
 
 __global__ void k_color_starts(int* counters) {
@@ -66,6 +71,7 @@ __global__ void k_color_starts(int* counters) {
         for (int c = 0; c < PB_MAX_COLORS; ++c) {
             int cnt = counters[CNT_COLORSTART + c];
             counters[CNT_COLORSTART + c] = run;
+            counters[CNT_MULTISTART + c] = run + counters[CNT_MULTISTART + c];     // count of singles -> first multi-point slot
             run += cnt;
             if (cnt) ncol = c + 1;
             if (c == PB_OVERFLOW_COLOR) counters[CNT_OVERFLOW] = cnt;

@@ -52,7 +52,8 @@ enum {
     CNT_BIN0 = 16,                      // PB_NUM_BINS bin counters
     CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
     CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
-    CNT_TOTAL = 192
+    CNT_MULTISTART = 130,               // PB_MAX_COLORS: where the multi-point manifolds of each colour start (singles come first)
+    CNT_TOTAL = 256
 };
 
 struct pb_ctx {

@@ -447,19 +447,32 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     float4* velLive = P.velB; float4* angvelLive = P.angvelB;
     const int lane = threadIdx.x & 31;
     const L2Hints H = makeL2Hints();
-    // several points per manifold on average -> four lanes per manifold (one memory wave per manifold instead of one per point)
-    const bool quad = 2 * (long long)P.counters[CNT_POINTS] > 3 * (long long)P.counters[CNT_MANIFOLDS];
-    // one contact pass over all colours, a barrier after each non-empty colour
+    // one contact pass over all colours, a barrier after each non-empty colour.  Inside a colour the single-point manifolds come
+    // first (one thread each: two memory round trips), then the multi-point ones (four lanes each, lane k = point k: also one wave
+    // of row loads) -- a one-thread walk over a 2..4-point manifold chains ~3 dependent round trips per point, and since a phase
+    // lasts as long as its slowest thread that chain used to set the duration of every small colour.
+    const int* multiStart = P.counters + CNT_MULTISTART;
+    const int ngroups = nth >> 2;
     auto contactPass = [&](int useBias, int skipSoft) {
         for (int c = 0; c < ncol; ++c) {
             int start = colorStart[c], count = colorStart[c + 1] - start;
             if (count <= 0) continue;
             if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
                 if (tid == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
-            } else if (quad) {
-                for (int i = tid >> 2; i < count; i += nth >> 2) contactSolveQuad(P, start + i, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
             } else {
-                for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+                const int mid = multiStart[c];
+                const int singles = mid - start, multis = count - singles;
+                if (singles + 4 * multis <= nth) {
+                    // the colour fits one round of the grid: its duration is the longest dependent chain, so the multi-point
+                    // manifolds take four lanes each (all rows in one wave), at the far end of the grid from the singles
+                    if (tid < singles) contactSolve(P, start + tid, useBias, skipSoft, velLive, angvelLive, H);
+                    int g = ngroups - 1 - (tid >> 2);
+                    if (g < multis) contactSolveQuad(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
+                } else {
+                    // several rounds: throughput matters, one thread per manifold keeps every lane busy (the multi-point manifolds sit
+                    // together at the end of the colour, so their longer path diverges in few warps)
+                    for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+                }
             }
             bar.sync(PH_CONTACT_PASS, c);
         }
