@@ -242,7 +242,10 @@ def main():
     launch_ms = kernel_ms                  # CUDA events around the k_substeps launch, on the context's stream
     stamp_ms = sum(phase_ms.values())      # the same from CTA 0's %globaltimer stamps at every grid barrier (splits the launch into phases)
     achieved = bytes_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
-    pass_ms = phase_ms.get("contact_pass", 0.0)
+    islands = ctx.island_stats()
+    # islands on: most colour phases run inside per-CTA sweeps (no grid barrier, so no per-phase stamp); this scene has no joints,
+    # so those sweeps are contact passes and are counted with the device-wide ones
+    pass_ms = phase_ms.get("contact_pass", 0.0) + phase_ms.get("local_sweeps", 0.0)
     pass_gbs = bytes_solve / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
     prep_ms = phase_ms.get("prep", 0.0)
     traffic = None
@@ -258,6 +261,7 @@ def main():
                 "phases": {"contact_solve_passes": {"ms": pass_ms, "GB/s": pass_gbs, "frac": pass_gbs / peak, "bytes": bytes_solve},
                            "contact_prep": {"ms": prep_ms, "GB/s": bytes_prep / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0, "bytes": bytes_prep},
                            "integrate": {"ms": phase_ms.get("integrate_v", 0.0) + phase_ms.get("integrate_x", 0.0), "bytes": bytes_bodies}},
+                "islands": islands,
                 "note": "one launch = the whole TGS substep loop of a step (persistent cooperative kernel, grid barriers between phases); "
                         "algorithmic bytes = sum over phases of SURVEY.md 8d's per-unit figures x units; duration = in-kernel phase stamps"}
 

@@ -24,6 +24,7 @@ UNITS = [
     ("contacts.cu", ["-fmad=false"]),
     ("solver.cu", ["-fmad=false"]),
     ("joints.cu", ["-fmad=false"]),
+    ("islands.cu", []),
     ("queries.cu", ["-fmad=false"]),
     ("trimesh_build.cpp", []),
 ]

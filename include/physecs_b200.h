@@ -200,8 +200,16 @@ int pb_query_overlap_mtd(pb_ctx* ctx, const float* pos3, const float* quat4, int
 int pb_get_tree(pb_ctx* ctx, int cap, float* child_boxes12, int* child_links2, int* n_internal);
 int pb_collider_ids(pb_ctx* ctx, int n, const int* cols, int* out_entity, int* out_col_idx);
 
-/* optional per-stage CUDA-event profiling (bench.py roofline): stage ids 0 = one contact-solve pass over all
- * colours, 1 = contact prep, 2 = body integration, 3 = joints.  pb_set_profile(ctx,1) resets the accumulators. */
+/* Simulation islands.  Connected components of the body / constraint graph that are small enough are solved inside one CTA each
+ * (no device-wide barrier per colour): what makes batches of independent little scenes (config 5) fast.  Results do not depend on
+ * the mode.  0 = off, 1 = on, 2 = auto (default: on while at least half of the constraints sit in small islands).
+ * pb_get_island_stats: {on in the last step, constraints in small islands, constraints in all islands} of the last step that looked. */
+int pb_set_islands(pb_ctx* ctx, int mode);
+int pb_get_island_stats(pb_ctx* ctx, int* out3);
+
+/* optional in-kernel phase profile of the persistent substep kernel (bench.py roofline), accumulated since pb_set_profile(ctx, 1):
+ * kinds 0 = integrate velocities, 1 = joint NGS phases, 2 = contact colour phases of the device-wide sweep, 3 = joint solve phases,
+ * 4 = integrate positions, 5 = the per-CTA island sweeps (all their contact and joint colours; islands on). */
 int pb_set_profile(pb_ctx* ctx, int on);
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8);
 /* the contact-pass share of it per solver colour: accumulated ms and number of phases for colours 0..63 */

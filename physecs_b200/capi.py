@@ -266,7 +266,7 @@ class Context:
         ms = (C.c_double * 8)(); cnt = (C.c_longlong * 8)()
         self._check(self.lib.pb_get_profile(self.ctx, ms, cnt))
         # (milliseconds, number of phases) per phase kind of the persistent substep kernel
-        names = ["integrate_v", "prep", "contact_pass", "joint_solve", "integrate_x"]
+        names = ["integrate_v", "prep", "contact_pass", "joint_solve", "integrate_x", "local_sweeps"]
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
     def profile_colors(self):
@@ -274,6 +274,15 @@ class Context:
         ms = (C.c_double * 64)(); cnt = (C.c_longlong * 64)()
         self._check(self.lib.pb_get_profile_colors(self.ctx, ms, cnt))
         return [(ms[i], cnt[i]) for i in range(64)]
+
+    def set_islands(self, mode):
+        """0 off, 1 on, 2 auto: small simulation islands solved inside one CTA each (results are identical either way)."""
+        self._check(self.lib.pb_set_islands(self.ctx, int(mode)))
+
+    def island_stats(self):
+        out = (C.c_int * 3)()
+        self._check(self.lib.pb_get_island_stats(self.ctx, out))
+        return dict(on=bool(out[0]), local=out[1], total=out[2])
 
     def launches(self):
         return int(self.lib.pb_get_launches(self.ctx))

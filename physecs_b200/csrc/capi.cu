@@ -125,14 +125,15 @@ int pb_set_profile(pb_ctx* ctx, int on) {
     return pb_solve_profile(ctx, tmp, true);
 }
 // accumulated phase times since pb_set_profile(1): ms8 / count8 indexed by phase kind
-// (0 = integrate velocities, 1 = contact + joint prep, 2 = contact solve colour phases, 3 = joint solve, 4 = integrate positions);
+// (0 = integrate velocities, 1 = contact + joint prep, 2 = contact solve colour phases, 3 = joint solve, 4 = integrate positions,
+// 5 = per-CTA island sweeps);
 // count = number of phases (grid barriers) of that kind
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
     cudaSetDevice(ctx->device);
     unsigned long long raw[16] = {0};
     int rc = pb_solve_profile(ctx, raw, false);
     if (rc) return rc;
-    for (int k = 0; k < 8; ++k) { ms8[k] = k < 5 ? raw[k] * 1e-6 : 0.0; count8[k] = k < 5 ? (long long)raw[5 + k] : 0; }
+    for (int k = 0; k < 8; ++k) { ms8[k] = k < 6 ? raw[k] * 1e-6 : 0.0; count8[k] = k < 6 ? (long long)raw[6 + k] : 0; }
     return PB_OK;
 }
 int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64) {
@@ -141,6 +142,15 @@ int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64) {
     int rc = pb_solve_profile_colors(ctx, raw);
     if (rc) return rc;
     for (int k = 0; k < PB_MAX_COLORS; ++k) { ms64[k] = raw[k] * 1e-6; count64[k] = (long long)raw[PB_MAX_COLORS + k]; }
+    return PB_OK;
+}
+int pb_set_islands(pb_ctx* ctx, int mode) {
+    if (mode < 0 || mode > 2) return pb_fail(ctx, PB_EINVAL, "pb_set_islands: mode 0 (off), 1 (on) or 2 (auto)");
+    ctx->islandsMode = mode; ctx->islandsHold = 0;
+    return PB_OK;
+}
+int pb_get_island_stats(pb_ctx* ctx, int* out3) {
+    out3[0] = ctx->islandsOn ? 1 : 0; out3[1] = ctx->lastIslandLocal; out3[2] = ctx->lastIslandTotal;
     return PB_OK;
 }
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
@@ -191,9 +201,12 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     ctx->cacheSize = (int)cs;
     for (int b = 0; b < 2; ++b) { A(cacheTag[b], cs); A(cacheVal[b], cs); }
     A(counters, CNT_TOTAL);
+    ctx->islandGroups = ctx->numSMs * 3;     // co-resident 256-thread CTAs of the persistent substep kernel
+    A(keyStart, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1);
     A(triMeshDev, 64); A(convexDev, 256);
 #undef A
-    if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * CNT_TOTAL) != cudaSuccess) rc = PB_ECUDA;
+    if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * (CNT_TOTAL + 4)) != cudaSuccess) rc = PB_ECUDA;
+    if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
     cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);
     *out = ctx;
@@ -264,6 +277,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
     F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
+    F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
@@ -543,8 +557,23 @@ int pb_refresh_bounds(pb_ctx* ctx) {
 
 static int readCounters(pb_ctx* ctx) {
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
+    // island statistics of the PREVIOUS step ride along (no extra sync): constraints in small islands, constraints in all
+    const bool stats = ctx->islandsOn && ctx->islandStats;
+    if (stats) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) { ctx->lastIslandLocal = ctx->hCounters[CNT_TOTAL]; ctx->lastIslandTotal = ctx->hCounters[CNT_TOTAL + 1]; }
     return PB_OK;
+}
+
+// Local (per-CTA) sweeps pay off when a worthwhile share of the constraints sits in small islands; finding the islands costs a few
+// kernels per step, so in auto mode a scene that turned out to be one big pile is only looked at again every 64 steps.
+static void chooseIslands(pb_ctx* ctx) {
+    const bool wasOn = ctx->islandsOn;
+    if (ctx->islandsMode == 0) { ctx->islandsOn = false; return; }
+    if (ctx->islandsMode == 1) { ctx->islandsOn = true; return; }
+    if (wasOn && ctx->lastIslandTotal > 0 && 2ll * ctx->lastIslandLocal < ctx->lastIslandTotal) { ctx->islandsOn = false; ctx->islandsHold = 63; return; }
+    if (!wasOn && ctx->islandsHold > 0) { --ctx->islandsHold; return; }
+    ctx->islandsOn = true;
 }
 
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
@@ -573,10 +602,11 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     }
     if (status & 0x100) return pb_fail(ctx, PB_EUNSUPPORTED, "a candidate pair involves a shape combination not implemented on the device path");
     ctx->curBuf ^= 1;
+    chooseIslands(ctx);
+    if ((rc = pb_joint_begin_step(ctx))) return rc;      // solver body indices of the joints: the island search hooks through them
     if ((rc = pb_contact_build(ctx, nRaw))) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
     ctx->countsStale = nRaw > 0;     // manifold / colour / point counts stay on the device until someone asks (pb_get_counts)
-    if ((rc = pb_joint_begin_step(ctx))) return rc;
     if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity, nRaw))) return rc;
     ctx->cacheValid = true;
     ctx->cacheBuilt = true;
@@ -796,8 +826,8 @@ int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* no
     std::vector<int> rowEnt(ctx->nRows), colIdx(ctx->nCol);
     PB_CUDA(ctx, cudaMemcpy(rowEnt.data(), ctx->rowEntity, sizeof(int) * ctx->nRows, cudaMemcpyDeviceToHost));
     PB_CUDA(ctx, cudaMemcpy(colIdx.data(), ctx->colIndex, sizeof(int) * ctx->nCol, cudaMemcpyDeviceToHost));
-    const int* cs = ctx->hCounters + CNT_COLORSTART;
-    int c = 0;
+    std::vector<unsigned int> skeys(nm);
+    PB_CUDA(ctx, cudaMemcpy(skeys.data(), ctx->mSortedKeys, sizeof(unsigned int) * nm, cudaMemcpyDeviceToHost));
     for (int s = 0; s < nm && s < cap; ++s) {
         int raw = sorted[s];
         int4 k = key[raw];
@@ -809,8 +839,7 @@ int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* no
             float4 v = p < k.w ? pts[8 * (size_t)raw + 2 * p + side] : make_float4(0, 0, 0, 0);
             points24[24 * s + 6 * p + 3 * side] = v.x; points24[24 * s + 6 * p + 3 * side + 1] = v.y; points24[24 * s + 6 * p + 3 * side + 2] = v.z;
         }
-        while (c < PB_MAX_COLORS - 1 && s >= cs[c + 1]) ++c;
-        if (color) color[s] = c;
+        if (color) color[s] = (int)((skeys[s] % PB_KEY_COLORS) >> 1);      // key = group * 128 + colour * 2 + multi
     }
     return PB_OK;
 }

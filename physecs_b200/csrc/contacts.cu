@@ -65,20 +65,51 @@ __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counter
     if (threadIdx.x < PB_MAX_COLORS && hist[PB_MAX_COLORS + threadIdx.x]) atomicAdd(&counters[CNT_MULTISTART + threadIdx.x], hist[PB_MAX_COLORS + threadIdx.x]);
 }
 
-__global__ void k_color_starts(int* counters) {
-    if (threadIdx.x == 0) {
-        int run = 0, ncol = 0;
-        for (int c = 0; c < PB_MAX_COLORS; ++c) {
-            int cnt = counters[CNT_COLORSTART + c];
-            counters[CNT_COLORSTART + c] = run;
-            counters[CNT_MULTISTART + c] = run + counters[CNT_MULTISTART + c];     // count of singles -> first multi-point slot
-            run += cnt;
-            if (cnt) ncol = c + 1;
-            if (c == PB_OVERFLOW_COLOR) counters[CNT_OVERFLOW] = cnt;
-        }
+// colour starts (taps, counters) and, for the plain colour-major order (islands off), the run table of group G: entry c * 2 = first
+// single-point slot of colour c, c * 2 + 1 = first multi-point slot, [PB_KEY_COLORS] = end
+__global__ void k_color_starts(int* counters, int* __restrict__ keyStartG) {
+    // one warp, two colours per lane: exclusive scan of the colour counts
+    const int lane = threadIdx.x;
+    int cnt[2], singles[2];
+    for (int k = 0; k < 2; ++k) { cnt[k] = counters[CNT_COLORSTART + 2 * lane + k]; singles[k] = counters[CNT_MULTISTART + 2 * lane + k]; }
+    int sum = cnt[0] + cnt[1], inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    int run = inc - sum;
+    int top = cnt[1] > 0 ? 2 * lane + 2 : (cnt[0] > 0 ? 2 * lane + 1 : 0);      // colours in use = highest non-empty colour + 1
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
+    for (int k = 0; k < 2; ++k) {
+        int c = 2 * lane + k;
+        counters[CNT_COLORSTART + c] = run;
+        counters[CNT_MULTISTART + c] = run + singles[k];
+        if (keyStartG) { keyStartG[2 * c] = run; keyStartG[2 * c + 1] = run + singles[k]; }
+        if (c == PB_OVERFLOW_COLOR) counters[CNT_OVERFLOW] = cnt[k];
+        run += cnt[k];
+    }
+    if (lane == 31) {
         counters[CNT_COLORSTART + PB_MAX_COLORS] = run;
+        if (keyStartG) keyStartG[PB_KEY_COLORS] = run;
         counters[CNT_MANIFOLDS] = run;
-        counters[CNT_NCOLORS] = ncol;
+        counters[CNT_NCOLORS] = top;
+    }
+}
+
+// islands on: solve-order key = group * 128 + colour * 2 + multi; histogram of the keys (scanned into the run table)
+__global__ void k_island_keys(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
+                              int nDyn, const int* __restrict__ kinematic, const int* __restrict__ bodyGroup, int G,
+                              unsigned int* __restrict__ sortKey, int* __restrict__ keyHist) {
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned int k = sortKey[i];
+        if (k >= PB_KEY_COLORS) { sortKey[i] = 0xFFFFu; continue; }      // discarded (no points): sorts behind every group
+        int4 key = mKey[i];
+        int b = solverIndex(colRow[key.x], nDyn, kinematic);
+        if (b < 0) b = solverIndex(colRow[key.y], nDyn, kinematic);
+        int g = b >= 0 ? bodyGroup[b] : G;
+        unsigned int full = (unsigned int)g * PB_KEY_COLORS + k;
+        sortKey[i] = full;
+        atomicAdd(&keyHist[full], 1);
     }
 }
 
@@ -239,10 +270,17 @@ int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
 int pb_contact_build(pb_ctx* ctx, int nRaw) {
     int blocks = ctx->numSMs * 8;
     int maxM = ctx->caps.max_manifolds;
+    const int G = ctx->islandGroups, nKeys = (G + 1) * PB_KEY_COLORS;
+    int rc;
     cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
     ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
                                              ctx->mSortKeyA, ctx->mSortTmp);
-    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
+    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->keyStart + (size_t)G * PB_KEY_COLORS);
+    if (ctx->islandsOn) {
+        if ((rc = pb_islands_build(ctx))) return rc;
+        if ((rc = pb_joint_lists(ctx))) return rc;
+    }
     // group by colour: one stable 8-bit radix pass over the raw arena (nRaw was read back after the narrowphase)
     int n = nRaw;
     if (n <= 0) {
@@ -251,9 +289,19 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
         return PB_OK;
     }
     bool inA = true;
-    int rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 8, ctx->radixHist, ctx->radixTiles, &inA);
+    if (ctx->islandsOn) {
+        // group-major order: every local group's manifolds are contiguous (colour by colour inside), the global group comes last
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
+        ++ctx->launches, k_island_keys<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mKey, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->bodyGroup, G,
+                                                                       ctx->mSortKeyA, ctx->keyStart);
+        if ((rc = pb_exclusive_scan(ctx, ctx->keyStart, ctx->keyStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
+        rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 16, ctx->radixHist, ctx->radixTiles, &inA);
+    } else {
+        rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 8, ctx->radixHist, ctx->radixTiles, &inA);
+    }
     if (rc) return rc;
     ctx->mSorted = inA ? ctx->mSortTmp : ctx->mSortValB;
+    ctx->mSortedKeys = inA ? ctx->mSortKeyA : ctx->mSortKeyB;
     int cur = ctx->curBuf, prev = cur ^ 1;
     int* pointOfs = ctx->cPointOfsBuf[cur];
     ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);

@@ -1,0 +1,127 @@
+// Simulation islands: connected components of the body / constraint graph, so that small islands (a ragdoll, a separate
+// little pile) are solved entirely inside ONE CTA of the persistent substep kernel, colour after colour with CTA barriers,
+// instead of paying a device-wide barrier per colour (solver.cu, "local mode").
+//
+// The reference solves every contact, then every joint colour, in one global order (src/Physecs.cpp:482-490).  Constraints of
+// different islands share no dynamic body, so running the islands' sub-sequences concurrently is the same arithmetic as any
+// interleaving of them -- in particular as the (group, colour, slot) order the parity tap reports and the oracle is fed.
+//
+//   k_island_init / k_island_hook_*   lock-free union-find over the solver bodies (hook the larger root under the smaller)
+//   k_island_compress                 root of every body
+//   k_island_count_*                  constraints per island (an overflow-colour joint marks its island as not local)
+//   k_island_group                    island -> group: local islands are spread over G CTAs by the position of their root
+//                                     body (neighbouring bodies -> neighbouring groups), large islands go to group G = "global"
+#include "pb_ctx.h"
+#include "joints.cuh"
+
+bool pb_joint_view(pb_ctx* ctx, JointDev* out);
+
+__device__ __forceinline__ int islandFind(int* parent, int x) {
+    while (true) {
+        int p = ((volatile int*)parent)[x];
+        if (p == x) return x;
+        int gp = ((volatile int*)parent)[p];
+        if (gp != p) ((volatile int*)parent)[x] = gp;      // path halving; a benign race: any ancestor is a valid parent
+        x = p;
+    }
+}
+
+__device__ __forceinline__ void islandUnion(int* parent, int a, int b) {
+    while (true) {
+        a = islandFind(parent, a); b = islandFind(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }            // a = larger root, hooked under the smaller one
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+
+__global__ void k_island_init(int n, int* __restrict__ parent, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = i; cnt[i] = 0; }
+}
+
+__device__ __forceinline__ int islandSolverIndex(int row, int nDyn, const int* __restrict__ kinematic) {
+    return (row < nDyn && !kinematic[row]) ? row : -1;
+}
+
+__global__ void k_island_hook_contacts(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
+                                       int nDyn, const int* __restrict__ kinematic, int* parent) {
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 key = mKey[i];
+        if (key.w <= 0) continue;
+        int b0 = islandSolverIndex(colRow[key.x], nDyn, kinematic), b1 = islandSolverIndex(colRow[key.y], nDyn, kinematic);
+        if (b0 >= 0 && b1 >= 0 && b0 != b1) islandUnion(parent, b0, b1);
+    }
+}
+
+__global__ void k_island_hook_joints(int nJ, const int2* __restrict__ bodies, int* parent) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nJ) return;
+    int2 b = bodies[j];
+    if (b.x >= 0 && b.y >= 0 && b.x != b.y) islandUnion(parent, b.x, b.y);
+}
+
+// roots go to a separate array: a concurrent path-halving write of another thread may still land on parent[i] after this one
+__global__ void k_island_compress(int n, int* parent, int* __restrict__ root) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) root[i] = islandFind(parent, i);
+}
+
+__global__ void k_island_count_contacts(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
+                                        int nDyn, const int* __restrict__ kinematic, const int* __restrict__ root, int* __restrict__ cnt) {
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 key = mKey[i];
+        if (key.w <= 0) continue;
+        int b = islandSolverIndex(colRow[key.x], nDyn, kinematic);
+        if (b < 0) b = islandSolverIndex(colRow[key.y], nDyn, kinematic);
+        if (b >= 0) atomicAdd(&cnt[root[b]], 1);
+    }
+}
+
+__global__ void k_island_count_joints(int nJ, const int2* __restrict__ bodies, int overflowStart, int localMax, const int* __restrict__ root, int* __restrict__ cnt) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nJ) return;
+    int2 bb = bodies[j];
+    int b = bb.x >= 0 ? bb.x : bb.y;
+    // joints of the sequential overflow bucket (scalar semantics, creation order) stay in the global sweep, with their whole island
+    if (b >= 0) atomicAdd(&cnt[root[b]], j >= overflowStart ? localMax + 1 : 1);
+}
+
+// group of every body; stats[0] += constraints of local islands, stats[1] += constraints of all islands
+__global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict__ cnt, int G, int localMax, int* __restrict__ stats) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int* group = rootThenGroup;
+    int r = rootThenGroup[i];
+    int c = cnt[r];
+    bool local = c <= localMax;
+    group[i] = local ? (int)min((long long)G - 1, (long long)r * G / n) : G;
+    if (r == i && c > 0) { atomicAdd(&stats[1], min(c, 1 << 24)); if (local) atomicAdd(&stats[0], c); }
+}
+
+int pb_islands_build(pb_ctx* ctx) {
+    const int n = ctx->nDyn;
+    if (n <= 0) return PB_OK;
+    if (!ctx->islandParent) {
+        int rc;
+        if ((rc = pb_alloc(ctx, &ctx->islandParent, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandCount, (size_t)ctx->caps.max_bodies)) ||
+            (rc = pb_alloc(ctx, &ctx->bodyGroup, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandStats, 4))) return rc;
+    }
+    const int blocks = ctx->numSMs * 8;
+    const int G = ctx->islandGroups;
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->islandStats, 0, sizeof(int) * 4, ctx->stream));
+    ++ctx->launches, k_island_init<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->islandCount);
+    ++ctx->launches, k_island_hook_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->islandParent);
+    JointDev J;
+    const bool joints = pb_joint_view(ctx, &J);
+    if (joints) ++ctx->launches, k_island_hook_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->islandParent);
+    ++ctx->launches, k_island_compress<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->bodyGroup);
+    ++ctx->launches, k_island_count_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->bodyGroup, ctx->islandCount);
+    if (joints) ++ctx->launches, k_island_count_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->jointColorStart[8], PB_ISLAND_LOCAL_MAX, ctx->bodyGroup, ctx->islandCount);
+    // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
+    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, PB_ISLAND_LOCAL_MAX, ctx->islandStats);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}

@@ -162,6 +162,48 @@ int pb_joint_begin_step(pb_ctx* ctx) {
     return PB_OK;
 }
 
+// ---- per-group joint lists (islands on) -------------------------------------------------------------------------------------------
+// jointOrder lists the joints by (group, colour), stable; jointStart[g * 8 + c] (local groups g < G, colours 0..7) and
+// jointStart[G * 8 + c] (global group, colours 0..8) are the run starts.  A local group's CTA walks its own runs; the device-wide
+// sweep walks the global runs.  Overflow-bucket joints are always global (islands.cu), so that run equals the static range.
+struct JointColorStarts { int s[PB_JOINT_COLORS + 1]; };
+__global__ void k_joint_keys(int nJ, const int2* __restrict__ bodies, const int* __restrict__ bodyGroup, int G, JointColorStarts cs,
+                             unsigned int* __restrict__ key, int* __restrict__ val, int* __restrict__ hist) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nJ) return;
+    int2 bb = bodies[j];
+    int b = bb.x >= 0 ? bb.x : bb.y;
+    int g = b >= 0 ? bodyGroup[b] : G;
+    int c = 0;
+    while (c < PB_JOINT_COLORS - 1 && j >= cs.s[c + 1]) ++c;
+    if (c == 8) g = G;
+    unsigned int k = (unsigned int)(g * 8 + c);
+    key[j] = k; val[j] = j;
+    atomicAdd(&hist[k], 1);
+}
+
+int pb_joint_lists(pb_ctx* ctx) {
+    JointStore* s = store(ctx);
+    if (!s || !ctx->nJoints) return PB_OK;
+    const int n = s->n, G = ctx->islandGroups, nKeys = G * 8 + 9;
+    int rc;
+    if (ctx->jointListCap < n || !ctx->jointStart) {
+        if ((rc = pb_alloc(ctx, &ctx->jointKey, (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[0], (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[1], (size_t)n)) ||
+            (rc = pb_alloc(ctx, &ctx->jointSortTmp[2], (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointStart, (size_t)nKeys + 1))) return rc;
+        ctx->jointListCap = n;
+    }
+    JointColorStarts cs;
+    for (int c = 0; c <= PB_JOINT_COLORS; ++c) cs.s[c] = ctx->jointColorStart[c];
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->jointStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
+    ++ctx->launches, k_joint_keys<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, s->bodies, ctx->bodyGroup, G, cs, (unsigned int*)ctx->jointKey, ctx->jointSortTmp[1], ctx->jointStart);
+    if ((rc = pb_exclusive_scan(ctx, ctx->jointStart, ctx->jointStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
+    bool inA = true;
+    if ((rc = pb_radix_sort_pairs(ctx, (unsigned int*)ctx->jointKey, ctx->jointSortTmp[1], (unsigned int*)ctx->jointSortTmp[0], ctx->jointSortTmp[2], n, 16, ctx->radixHist, ctx->radixTiles, &inA))) return rc;
+    ctx->jointOrder = inA ? ctx->jointSortTmp[1] : ctx->jointSortTmp[2];
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
 // device view for the persistent substep kernel (solver.cu); false when the scene has no joints
 bool pb_joint_view(pb_ctx* ctx, JointDev* out) {
     if (!ctx->nJoints || !store(ctx)) return false;

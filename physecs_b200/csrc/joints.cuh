@@ -16,6 +16,11 @@
 #include "pb_ctx.h"
 #include "pb_math.cuh"
 
+// L1 = true: the caller is a per-CTA island sweep (solver.cu): everything it touches is private to its CTA for the whole kernel, so
+// loads may hit L1 (a dependent chain then costs ~40 ns per link instead of an L2 round trip); otherwise L2 (.cg): other SMs write
+// the arrays between grid barriers and L1 is not coherent across SMs.
+template <bool L1, class T> __device__ __forceinline__ T ldm(const T* p) { return L1 ? *p : __ldcg(p); }
+
 #define JF_SOFT 1
 #define JF_ANGULAR 2
 #define JF_LIMITED 4
@@ -251,23 +256,24 @@ __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const i
 // NGS pseudo-velocity pass of one joint from the rows jointPrepOne(doNgs = 0) stored (Constraint1DW.cpp:57-115): the same
 // lambda = c / k accumulation, row by row, as the fused version above.  Splitting it off lets the expensive row fill run once
 // for all joints in a plain kernel while only this light pass is ordered by joint colour.
+template <bool L1>
 __device__ inline void jointNgsOne(const JointDev& J, int j, const int* __restrict__ kinematic, const float4* __restrict__ comInvMass,
                                    float4* pseudoLin, float4* pseudoAng) {
     int type = J.type[j];
     int2 rr = J.rows[j];
     int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
-    float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
+    float4 prm0 = J.prm[2 * j], st0 = ldm<L1>(&J.state[2 * j]);
     int n = jointRowCount(type, prm0, st0);
     float im0 = 0.f, im1 = 0.f;
     V3 pv0 = mk3(0.f), pw0 = mk3(0.f), pv1 = mk3(0.f), pw1 = mk3(0.f);
     int cnt0 = 0, cnt1 = 0;
-    if (b0 >= 0) { im0 = comInvMass[b0].w; float4 l = __ldcg(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(__ldcg(&pseudoAng[b0])); }
-    if (b1 >= 0) { im1 = comInvMass[b1].w; float4 l = __ldcg(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(__ldcg(&pseudoAng[b1])); }
+    if (b0 >= 0) { im0 = comInvMass[b0].w; float4 l = ldm<L1>(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(ldm<L1>(&pseudoAng[b0])); }
+    if (b1 >= 0) { im1 = comInvMass[b1].w; float4 l = ldm<L1>(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(ldm<L1>(&pseudoAng[b1])); }
     for (int r = 0; r < n; ++r) {
         int flags = jointRowFlags(type, r, prm0, st0);
         if (flags & JF_SOFT) continue;
         int idx = r * J.n + j;
-        float4 LC = __ldcg(&J.linC[idx]), A1 = __ldcg(&J.a1K[idx]), A0t = __ldcg(&J.a0tMin[idx]), A1t = __ldcg(&J.a1tMax[idx]);
+        float4 LC = ldm<L1>(&J.linC[idx]), A1 = ldm<L1>(&J.a1K[idx]), A0t = ldm<L1>(&J.a0tMin[idx]), A1t = ldm<L1>(&J.a1tMax[idx]);
         float c = LC.w, k = A1.w;
         if (c != 0.f && k != 0.f) {            // masked per lane in the reference (quirk Q10)
             float lambda = c / k;
@@ -447,17 +453,18 @@ __device__ __forceinline__ void jointRowSolve(int flags, float4 LC, float4 A0, f
 // per iteration and colour, EIGHT lanes per joint: lane r holds row r, so every load of the joint is issued in one wave;
 // the rows are then applied in order (the Gauss-Seidel dependence is real) by passing the 12 running velocity components
 // from lane to lane with shuffles.  Same arithmetic as the one-thread version below, ~3 memory round trips instead of ~9.
+template <bool L1>
 __device__ inline void jointSolveOct(const JointDev& J, int j, int lane8, unsigned gmask, float h, int warmStart, const int* __restrict__ kinematic,
                                      const float4* __restrict__ comInvMass, float4* velLive, float4* angvelLive) {
     int type = J.type[j];
     int2 rr = J.rows[j];
     int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
-    float4 prm0 = J.prm[2 * j], st0 = __ldcg(&J.state[2 * j]);
+    float4 prm0 = J.prm[2 * j], st0 = ldm<L1>(&J.state[2 * j]);
     int n = jointRowCount(type, prm0, st0);
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { float4 t_ = __ldcg(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(__ldcg(&angvelLive[2 * b0])); }
-    if (b1 >= 0) { float4 t_ = __ldcg(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(__ldcg(&angvelLive[2 * b1])); }
+    if (b0 >= 0) { float4 t_ = ldm<L1>(&velLive[2 * b0]); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldm<L1>(&angvelLive[2 * b0])); }
+    if (b1 >= 0) { float4 t_ = ldm<L1>(&velLive[2 * b1]); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldm<L1>(&angvelLive[2 * b1])); }
     const float biasFactor = (float)(0.2 / (double)h);
     const bool mine = lane8 < n;
     int flags = 0; float total = 0.f;
@@ -465,9 +472,9 @@ __device__ inline void jointSolveOct(const JointDev& J, int j, int lane8, unsign
     int idx = lane8 * J.n + j;
     if (mine) {
         flags = jointRowFlags(type, lane8, prm0, st0);
-        LC = __ldcg(&J.linC[idx]); A0 = __ldcg(&J.a0T[idx]); A1 = __ldcg(&J.a1K[idx]); A0t = __ldcg(&J.a0tMin[idx]); A1t = __ldcg(&J.a1tMax[idx]);
-        total = __ldcg(&J.lambda[idx]);
-        if (flags & JF_SOFT) softp = __ldcg(&J.soft[idx]);
+        LC = ldm<L1>(&J.linC[idx]); A0 = ldm<L1>(&J.a0T[idx]); A1 = ldm<L1>(&J.a1K[idx]); A0t = ldm<L1>(&J.a0tMin[idx]); A1t = ldm<L1>(&J.a1tMax[idx]);
+        total = ldm<L1>(&J.lambda[idx]);
+        if (flags & JF_SOFT) softp = ldm<L1>(&J.soft[idx]);
     }
     for (int r = 0; r < n; ++r) {
         if (lane8 == r) jointRowSolve(flags, LC, A0, A1, A0t, A1t, softp, total, h, biasFactor, warmStart, im0, im1, v0, w0, v1, w1);

@@ -13,6 +13,8 @@
 #define PB_MAX_TRI_CONTACTS 24    // triangle contacts kept per (shape, mesh) pair
 #define PB_NUM_BINS 16            // narrowphase shape-pair bins
 #define PB_MAX_JOINT_ROWS 8
+#define PB_ISLAND_LOCAL_MAX 1024  // constraints (manifolds + joints) an island may hold and still be solved inside one CTA
+#define PB_KEY_COLORS 128         // solve-order key of a manifold: group * 128 + colour * 2 + (numPoints > 1)
 
 struct PbTriMesh {
     int nVerts = 0, nTris = 0, nNodes = 0;
@@ -165,6 +167,17 @@ struct pb_ctx {
     int* colClass = nullptr; unsigned char* filterLut = nullptr; int nFilterClasses = 0;
     bool anyTriggerFlag = false, triggersPossible = false;
     int2* trigPairs = nullptr;       // [maxPairs] overlapping TRIGGER pairs of the last step (collider indices)
+    // simulation islands (islands.cu): group of every solver body; local groups 0..islandGroups-1 (one CTA each), group islandGroups = global
+    int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
+    int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)
+    int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)
+    bool islandsOn = false;          // this step
+    int islandsHold = 0;             // auto: steps left before small islands are looked for again
+    int lastIslandLocal = 0, lastIslandTotal = 0;   // constraints in small islands / in all islands, last step that looked
+    int* keyStart = nullptr;         // [(G + 1) * PB_KEY_COLORS + 1] first solve slot of every (group, colour, single | multi) run
+    unsigned int* mSortedKeys = nullptr;   // solve-order keys of the last step (taps: colour of a slot)
+    // per-group joint lists of the step (joints.cu): jointOrder = joints sorted by (group, colour), jointStart[g * 8 + c] their runs (g = G: the global group, colours 0..8)
+    int* jointKey = nullptr; int* jointOrder = nullptr; int* jointStart = nullptr; int* jointSortTmp[3] = {nullptr, nullptr, nullptr}; int jointListCap = 0;
     // persistent substep kernel (solver.cu)
     int solveGrid = 0; unsigned int* solveBarrier = nullptr; unsigned long long* solveProfNs = nullptr;
     bool countsStale = false;        // lastCounts lacks the post-build numbers until the counters are read back
@@ -202,6 +215,8 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
 int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset);
 int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out128);
 int pb_joint_begin_step(pb_ctx* ctx);
+int pb_islands_build(pb_ctx* ctx);
+int pb_joint_lists(pb_ctx* ctx);   // per-group joint lists of the step (joints.cu), needs pb_islands_build
 int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew);
 void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long* oldTag, const int4* oldVal, int newSize, unsigned long long* newTag, int4* newVal);
 

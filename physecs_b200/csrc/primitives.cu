@@ -88,9 +88,43 @@ __global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, 
     }
 }
 
+// small inputs: one block walks the array tile by tile with a running carry (one launch instead of three)
+__global__ void k_scan_small(const int* in, int* out, int n) {
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SCAN_TILE) {
+        int v[SCAN_ITEMS];
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int idx = base + threadIdx.x * SCAN_ITEMS + i;
+            v[i] = idx < n ? in[idx] : 0;
+            s += v[i];
+        }
+        int total;
+        int inc = blockInclusiveScan(s, &total);
+        int run = carry + inc - s;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int idx = base + threadIdx.x * SCAN_ITEMS + i;
+            if (idx < n) out[idx] = run;
+            run += v[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+
 // out[i] = sum(in[0..i-1]); in and out may alias.  scratch: at least ceil(n/4096)+1 ints.
 int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch) {
     if (n <= 0) return PB_OK;
+    if (n <= 8 * SCAN_TILE) {
+        ++ctx->launches, k_scan_small<<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n);
+        PB_CUDA(ctx, cudaGetLastError());
+        return PB_OK;
+    }
     int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     ++ctx->launches, k_scan_reduce<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, scratch, n);
     ++ctx->launches, k_scan_blocksums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scratch, nb);
@@ -101,9 +135,9 @@ int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch)
 
 // ---------------------------------------------------------------------------------------------------------
 #define RS_WARPS 8
-#define RS_ITEMS 16
-#define RS_WARP_TILE (32 * RS_ITEMS)        // keys per warp tile
-
+// keys per warp tile = 32 * RS_ITEMS: 16 rounds per warp for large inputs; 4 for small ones, where a 512-key tile would leave
+// most SMs idle (a 45 k-key sort had 11 CTAs and took ~20 us per kernel, ncu)
+template <int RS_ITEMS>
 __global__ void k_radix_hist(const unsigned int* __restrict__ keys, unsigned int* __restrict__ hist, int n, int shift, int numTiles) {
     __shared__ unsigned int sh[RS_WARPS][256];
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +145,7 @@ __global__ void k_radix_hist(const unsigned int* __restrict__ keys, unsigned int
     __syncwarp();
     int tile = blockIdx.x * RS_WARPS + w;
     if (tile < numTiles) {
-        int base = tile * RS_WARP_TILE;
+        int base = tile * (32 * RS_ITEMS);
 #pragma unroll
         for (int r = 0; r < RS_ITEMS; ++r) {
             int idx = base + r * 32 + lane;
@@ -122,6 +156,7 @@ __global__ void k_radix_hist(const unsigned int* __restrict__ keys, unsigned int
     }
 }
 
+template <int RS_ITEMS>
 __global__ void k_radix_scatter(const unsigned int* __restrict__ keys, const int* __restrict__ vals,
                                 unsigned int* __restrict__ keysOut, int* __restrict__ valsOut,
                                 const unsigned int* __restrict__ hist, int n, int shift, int numTiles) {
@@ -131,7 +166,7 @@ __global__ void k_radix_scatter(const unsigned int* __restrict__ keys, const int
     if (tile >= numTiles) return;
     for (int i = lane; i < 256; i += 32) sh[w][i] = hist[(size_t)i * numTiles + tile];
     __syncwarp();
-    int base = tile * RS_WARP_TILE;
+    int base = tile * (32 * RS_ITEMS);
     unsigned int ltMask = (1u << lane) - 1u;
 #pragma unroll 1
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -160,17 +195,22 @@ int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned i
                         unsigned int* hist, int histCapTiles, bool* resultInA) {
     *resultInA = true;
     if (n <= 1) return PB_OK;
-    int numTiles = (n + RS_WARP_TILE - 1) / RS_WARP_TILE;
+    int items = 16;
+    if ((n + 127) / 128 <= histCapTiles && n <= (1 << 19)) items = 4;
+    const int tileKeys = 32 * items;
+    int numTiles = (n + tileKeys - 1) / tileKeys;
     if (numTiles > histCapTiles) return pb_fail(ctx, PB_ECAPACITY, "radix sort histogram capacity");
     int blocks = (numTiles + RS_WARPS - 1) / RS_WARPS;
     int histN = 256 * numTiles;
     int* scanScratch = (int*)(hist + (size_t)256 * histCapTiles);
     unsigned int* src = keysA; int* srcV = valsA; unsigned int* dst = keysB; int* dstV = valsB;
     for (int shift = 0; shift < bits; shift += 8) {
-        ++ctx->launches, k_radix_hist<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
+        if (items == 4) ++ctx->launches, k_radix_hist<4><<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
+        else ++ctx->launches, k_radix_hist<16><<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, hist, n, shift, numTiles);
         int rc = pb_exclusive_scan(ctx, (const int*)hist, (int*)hist, histN, scanScratch);
         if (rc) return rc;
-        ++ctx->launches, k_radix_scatter<<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
+        if (items == 4) ++ctx->launches, k_radix_scatter<4><<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
+        else ++ctx->launches, k_radix_scatter<16><<<blocks, RS_WARPS * 32, 0, ctx->stream>>>(src, srcV, dst, dstV, hist, n, shift, numTiles);
         unsigned int* t = src; src = dst; dst = t;
         int* tv = srcV; srcV = dstV; dstV = tv;
         *resultInA = !*resultInA;

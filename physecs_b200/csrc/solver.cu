@@ -32,6 +32,7 @@
 #include "pb_ctx.h"
 #include "pb_math.cuh"
 #include "joints.cuh"
+#include <type_traits>
 
 bool pb_joint_view(pb_ctx* ctx, JointDev* out);
 
@@ -53,12 +54,16 @@ struct SubstepParams {
     int rowExtra;                    // rows of a manifold's FIRST point live at its solve slot s; points k >= 1 at rowExtra + (firstPoint - s) + k - 1
     // joints
     int hasJoints; JointDev J; int jointColorStart[PB_JOINT_COLORS + 1];
+    // solve-order run table (contacts.cu): keyStart[g * PB_KEY_COLORS + 2 c (+1)] = first single- (multi-) point slot of colour c in group g.
+    // Groups 0..G-1 are islands small enough for one CTA (islands.cu, only when islandsOn), group G is the device-wide sweep.
+    const int* keyStart; int G; int islandsOn;
+    const int* jointOrder; const int* jointStart;     // per-group joint runs (islandsOn): jointStart[g * 8 + c]
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
     unsigned int* barrier;
     unsigned long long* profNs;
 };
 
-enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_KINDS };
+enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_LOCAL, PH_KINDS };
 #define PROF_WORDS (2 * PH_KINDS + 2 * PB_MAX_COLORS)   // ns + count per phase kind, then ns + count per contact colour
 
 __device__ __forceinline__ M3 loadM3ro(const float4* __restrict__ p, int i) {
@@ -122,6 +127,10 @@ __device__ __forceinline__ void stHint(float4* p, float4 v, unsigned long long p
 __device__ __forceinline__ void stHint(float2* p, float2 v, unsigned long long pol) {
     asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
+
+// the same accessors for a per-CTA island sweep (L1 = true): plain cached loads / stores, see ldm() in joints.cuh
+template <bool L1, class T> __device__ __forceinline__ T ldSolve(const T* p, unsigned long long pol) { if (L1) return *p; return ldHint(p, pol); }
+template <bool L1, class T> __device__ __forceinline__ void stSolve(T* p, T v, unsigned long long pol) { if (L1) *p = v; else stHint(p, v, pol); }
 
 // Row addressing: the first point's rows sit at the manifold's own slot, so the solver can load them together with the
 // header instead of after it (one dependent memory round trip less for the single-point manifolds that dominate big scenes).
@@ -249,13 +258,14 @@ __device__ __forceinline__ void frictionRow(float4 D, float4 E, float4 F, float4
     v1 -= lambda * im1 * t; w1 -= lambda * mk3(G);
 }
 
+template <bool L1>
 __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int useBias, int skipSoft, float4* velLive, float4* angvelLive, const L2Hints& H) {
     // first wave: header + every row of the first point (their address is the slot itself, no dependence on the header)
-    int4 hd = ldHint(&P.cHead[s], H.first);
-    float4 nf = ldHint(&P.cNormal[s], H.first);
-    float4 A = ldHint(&P.rowA[s], H.first), B = ldHint(&P.rowB[s], H.first), C = ldHint(&P.rowC[s], H.first), D = ldHint(&P.rowD[s], H.first);
-    float4 E = ldHint(&P.rowE[s], H.first), F = ldHint(&P.rowF[s], H.first), G = ldHint(&P.rowG[s], H.first);
-    float2 L = ldHint(&P.rowL[s], H.first);
+    int4 hd = ldSolve<L1>(&P.cHead[s], H.first);
+    float4 nf = ldSolve<L1>(&P.cNormal[s], H.first);
+    float4 A = ldSolve<L1>(&P.rowA[s], H.first), B = ldSolve<L1>(&P.rowB[s], H.first), C = ldSolve<L1>(&P.rowC[s], H.first), D = ldSolve<L1>(&P.rowD[s], H.first);
+    float4 E = ldSolve<L1>(&P.rowE[s], H.first), F = ldSolve<L1>(&P.rowF[s], H.first), G = ldSolve<L1>(&P.rowG[s], H.first);
+    float2 L = ldSolve<L1>(&P.rowL[s], H.first);
     const bool isSoft = (hd.w & 0x100) != 0;
     if (skipSoft && isSoft) return;
     float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -266,49 +276,50 @@ __device__ __forceinline__ void contactSolve(const SubstepParams& P, int s, int 
     // second wave: the body velocities (one 32-byte sector per body, invMass rides in v.w)
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { float4 t_ = ldHint(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldHint(&angvelLive[2 * b0], H.last)); }
-    if (b1 >= 0) { float4 t_ = ldHint(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldHint(&angvelLive[2 * b1], H.last)); }
+    if (b0 >= 0) { float4 t_ = ldSolve<L1>(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldSolve<L1>(&angvelLive[2 * b0], H.last)); }
+    if (b1 >= 0) { float4 t_ = ldSolve<L1>(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldSolve<L1>(&angvelLive[2 * b1], H.last)); }
     if (np == 1) {
         // the common case (a body resting on a mesh triangle, a sphere pair): two memory round trips in total
         float lamN = L.x, lamT = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN);
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN, im0, im1, v0, w0, v1, w1, lamT);
-        stHint(&P.rowL[s], make_float2(lamN, lamT), H.first);
+        stSolve<L1>(&P.rowL[s], make_float2(lamN, lamT), H.first);
     } else {
         float lamN[4], lamT[4];
         lamN[0] = L.x; lamT[0] = L.y;
         normalRow(A, B, C, D, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[0]);
         for (int k = 1; k < np; ++k) {
             const int ri = rowIndex(P, s, po, k);
-            float4 Ak = ldHint(&P.rowA[ri], H.first), Bk = ldHint(&P.rowB[ri], H.first), Ck = ldHint(&P.rowC[ri], H.first), Dk = ldHint(&P.rowD[ri], H.first);
-            float2 Lk = ldHint(&P.rowL[ri], H.first);
+            float4 Ak = ldSolve<L1>(&P.rowA[ri], H.first), Bk = ldSolve<L1>(&P.rowB[ri], H.first), Ck = ldSolve<L1>(&P.rowC[ri], H.first), Dk = ldSolve<L1>(&P.rowD[ri], H.first);
+            float2 Lk = ldSolve<L1>(&P.rowL[ri], H.first);
             lamN[k] = Lk.x; lamT[k] = Lk.y;
             normalRow(Ak, Bk, Ck, Dk, soft, useBias, h, n, im0, im1, v0, w0, v1, w1, lamN[k]);
         }
         if (E.w != 0.f) frictionRow(D, E, F, G, friction, lamN[0], im0, im1, v0, w0, v1, w1, lamT[0]);
-        stHint(&P.rowL[s], make_float2(lamN[0], lamT[0]), H.first);
+        stSolve<L1>(&P.rowL[s], make_float2(lamN[0], lamT[0]), H.first);
         for (int k = 1; k < np; ++k) {
             const int ri = rowIndex(P, s, po, k);
-            float4 Ek = ldHint(&P.rowE[ri], H.first);
+            float4 Ek = ldSolve<L1>(&P.rowE[ri], H.first);
             if (Ek.w != 0.f)
-                frictionRow(ldHint(&P.rowD[ri], H.first), Ek, ldHint(&P.rowF[ri], H.first), ldHint(&P.rowG[ri], H.first), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
-            stHint(&P.rowL[ri], make_float2(lamN[k], lamT[k]), H.first);
+                frictionRow(ldSolve<L1>(&P.rowD[ri], H.first), Ek, ldSolve<L1>(&P.rowF[ri], H.first), ldSolve<L1>(&P.rowG[ri], H.first), friction, lamN[k], im0, im1, v0, w0, v1, w1, lamT[k]);
+            stSolve<L1>(&P.rowL[ri], make_float2(lamN[k], lamT[k]), H.first);
         }
     }
-    if (b0 >= 0) { stHint(&velLive[2 * b0], f4(v0, im0), H.last); stHint(&angvelLive[2 * b0], f4(w0), H.last); }
-    if (b1 >= 0) { stHint(&velLive[2 * b1], f4(v1, im1), H.last); stHint(&angvelLive[2 * b1], f4(w1), H.last); }
+    if (b0 >= 0) { stSolve<L1>(&velLive[2 * b0], f4(v0, im0), H.last); stSolve<L1>(&angvelLive[2 * b0], f4(w0), H.last); }
+    if (b1 >= 0) { stSolve<L1>(&velLive[2 * b1], f4(v1, im1), H.last); stSolve<L1>(&angvelLive[2 * b1], f4(w1), H.last); }
 }
 
 // FOUR lanes per manifold: lane k holds point k, so all rows of the manifold are loaded in one wave; the points are then
 // applied in order (normal rows, then friction rows) by handing the running body velocities from lane to lane with shuffles.
 // Same arithmetic as contactSolve; used when manifolds have several points on average (box stacks, ragdolls), where the
 // one-thread version serialises ~3 memory round trips per point.
+template <bool L1>
 __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, int lane4, unsigned gmask, int useBias, int skipSoft,
                                                  float4* velLive, float4* angvelLive, const L2Hints& H) {
-    int4 hd = ldHint(&P.cHead[s], H.first);
+    int4 hd = ldSolve<L1>(&P.cHead[s], H.first);
     const bool isSoft = (hd.w & 0x100) != 0;
     if (skipSoft && isSoft) return;          // uniform across the four lanes
-    float4 nf = ldHint(&P.cNormal[s], H.first);
+    float4 nf = ldSolve<L1>(&P.cNormal[s], H.first);
     float4 soft = isSoft ? P.cSoft[s] : make_float4(0.f, 0.f, 0.f, 0.f);
     V3 n = mk3(nf);
     float friction = nf.w;
@@ -319,14 +330,14 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
     float2 L = make_float2(0.f, 0.f);
     const int ri = rowIndex(P, s, po, lane4);
     if (mine) {
-        A = ldHint(&P.rowA[ri], H.first); B = ldHint(&P.rowB[ri], H.first); C = ldHint(&P.rowC[ri], H.first); D = ldHint(&P.rowD[ri], H.first);
-        E = ldHint(&P.rowE[ri], H.first); F = ldHint(&P.rowF[ri], H.first); G = ldHint(&P.rowG[ri], H.first);
-        L = ldHint(&P.rowL[ri], H.first);
+        A = ldSolve<L1>(&P.rowA[ri], H.first); B = ldSolve<L1>(&P.rowB[ri], H.first); C = ldSolve<L1>(&P.rowC[ri], H.first); D = ldSolve<L1>(&P.rowD[ri], H.first);
+        E = ldSolve<L1>(&P.rowE[ri], H.first); F = ldSolve<L1>(&P.rowF[ri], H.first); G = ldSolve<L1>(&P.rowG[ri], H.first);
+        L = ldSolve<L1>(&P.rowL[ri], H.first);
     }
     V3 v0 = mk3(0.f), w0 = mk3(0.f), v1 = mk3(0.f), w1 = mk3(0.f);
     float im0 = 0.f, im1 = 0.f;
-    if (b0 >= 0) { float4 t_ = ldHint(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldHint(&angvelLive[2 * b0], H.last)); }
-    if (b1 >= 0) { float4 t_ = ldHint(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldHint(&angvelLive[2 * b1], H.last)); }
+    if (b0 >= 0) { float4 t_ = ldSolve<L1>(&velLive[2 * b0], H.last); v0 = mk3(t_); im0 = t_.w; w0 = mk3(ldSolve<L1>(&angvelLive[2 * b0], H.last)); }
+    if (b1 >= 0) { float4 t_ = ldSolve<L1>(&velLive[2 * b1], H.last); v1 = mk3(t_); im1 = t_.w; w1 = mk3(ldSolve<L1>(&angvelLive[2 * b1], H.last)); }
     float lamN = L.x, lamT = L.y;
 #define PB_PASS_ON(r) \
     v0.x = __shfl_sync(gmask, v0.x, r, 4); v0.y = __shfl_sync(gmask, v0.y, r, 4); v0.z = __shfl_sync(gmask, v0.z, r, 4); \
@@ -342,10 +353,10 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
         PB_PASS_ON(k)
     }
 #undef PB_PASS_ON
-    if (mine) stHint(&P.rowL[ri], make_float2(lamN, lamT), H.first);
+    if (mine) stSolve<L1>(&P.rowL[ri], make_float2(lamN, lamT), H.first);
     if (lane4 == 0) {
-        if (b0 >= 0) { stHint(&velLive[2 * b0], f4(v0, im0), H.last); stHint(&angvelLive[2 * b0], f4(w0), H.last); }
-        if (b1 >= 0) { stHint(&velLive[2 * b1], f4(v1, im1), H.last); stHint(&angvelLive[2 * b1], f4(w1), H.last); }
+        if (b0 >= 0) { stSolve<L1>(&velLive[2 * b0], f4(v0, im0), H.last); stSolve<L1>(&angvelLive[2 * b0], f4(w0), H.last); }
+        if (b1 >= 0) { stSolve<L1>(&velLive[2 * b1], f4(v1, im1), H.last); stSolve<L1>(&angvelLive[2 * b1], f4(w1), H.last); }
     }
 }
 
@@ -383,9 +394,12 @@ struct GridBarrier {
             target += gridDim.x;
             // release: the CTA barrier above ordered every thread's writes before this increment (cumulativity);
             // acquire: the polling load orders every later read of the CTA after the last arrival
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+            // (atom, not red: the returned count tells the last arriver that it is last, so it leaves without a polling round trip --
+            // measured 1.29 us instead of 1.67 us per barrier on 444 CTAs, tools/micro/barrier_bench.cu)
             unsigned int seen;
-            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+            ++seen;
+            while (seen < target) { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); }
             if (profNs && blockIdx.x == 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -411,11 +425,13 @@ __global__ void __launch_bounds__(128) k_contact_prep(const __grid_constant__ Su
 
 // Joint routines are called, not inlined: their register appetite (row builders, 3x3 products) then spills inside the
 // callee only, and the contact colour loops -- the bandwidth-critical part -- keep a spill-free 64-register budget.
+template <bool L1>
 __device__ __noinline__ void jointNgsCall(const SubstepParams& P, int j) {
-    jointNgsOne(P.J, j, P.kinematic, P.comInvMass, P.pseudoLin, P.pseudoAng);
+    jointNgsOne<L1>(P.J, j, P.kinematic, P.comInvMass, P.pseudoLin, P.pseudoAng);
 }
+template <bool L1>
 __device__ __noinline__ void jointSolveCall(const SubstepParams& P, int j, int lane8, unsigned gmask, int warmStart, float4* velLive, float4* angvelLive) {
-    jointSolveOct(P.J, j, lane8, gmask, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
+    jointSolveOct<L1>(P.J, j, lane8, gmask, P.h, warmStart, P.kinematic, P.comInvMass, velLive, angvelLive);
 }
 __device__ __noinline__ void jointNgsSeqCall(const SubstepParams& P, int start, int count) {
     jointNgsSeq(P.J, start, count, P.kinematic, P.comInvMass, P.pseudoLin, P.pseudoAng);
@@ -425,7 +441,7 @@ __device__ __noinline__ void jointSolveSeqCall(const SubstepParams& P, int start
 }
 __device__ __noinline__ void contactSolveSeqCall(const SubstepParams& P, int start, int count, int useBias, int skipSoft, float4* velLive, float4* angvelLive) {
     L2Hints H = makeL2Hints();
-    for (int i = 0; i < count; ++i) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+    for (int i = 0; i < count; ++i) contactSolve<false>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
 }
 
 // joint row fill for every joint of the scene (makeConstraints + effective masses): independent of the joint colours
@@ -436,72 +452,108 @@ __global__ void __launch_bounds__(128) k_joint_fill(const __grid_constant__ Subs
 
 // Everything of one substep that is ordered by colour: joint NGS pass (colours share bodies through the pseudo velocities),
 // the solver iterations (contact colours, then joint colours), position integration and the relaxation pass.
+//
+// Two sweeps run the same colour sequence.  The DEVICE-WIDE sweep (group G of the run table) spreads every colour over the whole
+// grid and separates colours with the grid barrier.  The LOCAL sweeps (islandsOn) give each group of small islands to one CTA,
+// which walks its colours with __syncthreads only: a ragdoll batch or a field of separate little piles then pays two grid
+// barriers per substep instead of one per colour and pass.  Islands share no dynamic body, so the interleaving is immaterial.
 __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
+    __shared__ int sRuns[PB_KEY_COLORS + 1];
+    __shared__ int sJoint[PB_JOINT_COLORS + 1];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     GridBarrier bar;
     bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
     if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
-    const int* colorStart = P.counters + CNT_COLORSTART;
     const int ncol = P.counters[CNT_NCOLORS];
     float4* velLive = P.velB; float4* angvelLive = P.angvelB;
     const int lane = threadIdx.x & 31;
     const L2Hints H = makeL2Hints();
-    // one contact pass over all colours, a barrier after each non-empty colour.  Inside a colour the single-point manifolds come
-    // first (one thread each: two memory round trips), then the multi-point ones (four lanes each, lane k = point k: also one wave
-    // of row loads) -- a one-thread walk over a 2..4-point manifold chains ~3 dependent round trips per point, and since a phase
-    // lasts as long as its slowest thread that chain used to set the duration of every small colour.
-    const int* multiStart = P.counters + CNT_MULTISTART;
-    const int ngroups = nth >> 2;
-    auto contactPass = [&](int useBias, int skipSoft) {
+    const int G = P.G;
+    const std::integral_constant<bool, true> LOCAL;
+    const std::integral_constant<bool, false> GLOBAL;
+
+    // One contact pass over the colour runs `runs` (129 ints).  id / nthr: this thread's index and the thread count of the sweep.
+    // Inside a colour the single-point manifolds come first (one thread each: two memory round trips), then the multi-point ones.
+    // A colour that fits one round of the sweep lasts as long as its longest dependent chain, so its multi-point manifolds take
+    // four lanes each (lane k = point k, all rows in one wave); over several rounds throughput matters and every manifold gets one
+    // thread (the multi-point ones sit together at the end of the colour, so their longer path diverges in few warps).
+    auto contactPass = [&](auto localTag, const int* runs, int id, int nthr, int useBias, int skipSoft) {
+        constexpr bool local = decltype(localTag)::value;
+        const int ngroups = nthr >> 2;
         for (int c = 0; c < ncol; ++c) {
-            int start = colorStart[c], count = colorStart[c + 1] - start;
+            const int start = runs[2 * c], mid = runs[2 * c + 1], count = runs[2 * c + 2] - start;
             if (count <= 0) continue;
             if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
-                if (tid == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
+                if (id == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
             } else {
-                const int mid = multiStart[c];
                 const int singles = mid - start, multis = count - singles;
-                if (singles + 4 * multis <= nth) {
-                    // the colour fits one round of the grid: its duration is the longest dependent chain, so the multi-point
-                    // manifolds take four lanes each (all rows in one wave), at the far end of the grid from the singles
-                    if (tid < singles) contactSolve(P, start + tid, useBias, skipSoft, velLive, angvelLive, H);
-                    int g = ngroups - 1 - (tid >> 2);
-                    if (g < multis) contactSolveQuad(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
+                if (singles + 4 * multis <= nthr) {
+                    if (id < singles) contactSolve<local>(P, start + id, useBias, skipSoft, velLive, angvelLive, H);
+                    int g = ngroups - 1 - (id >> 2);      // from the far end: the low threads hold the singles
+                    if (g < multis) contactSolveQuad<local>(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
                 } else {
-                    // several rounds: throughput matters, one thread per manifold keeps every lane busy (the multi-point manifolds sit
-                    // together at the end of the colour, so their longer path diverges in few warps)
-                    for (int i = tid; i < count; i += nth) contactSolve(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+                    for (int i = id; i < count; i += nthr) contactSolve<local>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
                 }
             }
-            bar.sync(PH_CONTACT_PASS, c);
+            if (local) __syncthreads(); else bar.sync(PH_CONTACT_PASS, c);
         }
     };
+    // joint colour runs of a sweep: jr[c] .. jr[c + 1] index P.jointOrder (islandsOn) or are the joint slots themselves
+    auto jointNgsPass = [&](auto localTag, const int* jr, int id, int nthr) {
+        constexpr bool local = decltype(localTag)::value;
+        for (int c = 0; c < 8; ++c) {
+            const int start = jr[c], count = jr[c + 1] - start;
+            if (count <= 0) continue;
+            for (int i = id; i < count; i += nthr) jointNgsCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i);
+            if (local) __syncthreads(); else bar.sync(PH_PREP);
+        }
+    };
+    auto jointSolvePass = [&](auto localTag, const int* jr, int id, int nthr, int warmStart) {
+        constexpr bool local = decltype(localTag)::value;
+        for (int c = 0; c < 8; ++c) {
+            const int start = jr[c], count = jr[c + 1] - start;
+            if (count <= 0) continue;
+            for (int i = id >> 3; i < count; i += nthr >> 3)
+                jointSolveCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i, lane & 7, 0xFFu << (lane & 24), warmStart, velLive, angvelLive);
+            if (local) __syncthreads(); else bar.sync(PH_JOINT_SOLVE);
+        }
+    };
+    // a local group's tables into shared memory (the colour loops then cost no global round trip per colour)
+    auto loadLocal = [&](int g) {
+        __syncthreads();
+        for (int i = threadIdx.x; i <= PB_KEY_COLORS; i += blockDim.x) sRuns[i] = P.keyStart[g * PB_KEY_COLORS + i];
+        if (P.hasJoints && threadIdx.x <= 8) sJoint[threadIdx.x] = P.jointStart[g * 8 + threadIdx.x];
+        __syncthreads();
+    };
 
+    // ---- phase A: NGS pass of the joints, then the iterations --------------------------------------------------------------------
+    if (P.islandsOn) {
+        for (int g = blockIdx.x; g < G; g += gridDim.x) {
+            loadLocal(g);
+            if (sRuns[PB_KEY_COLORS] == sRuns[0] && (!P.hasJoints || sJoint[8] == sJoint[0])) continue;     // empty group
+            if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
+            for (int it = 0; it < P.iterations; ++it) {
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
+                if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
+            }
+        }
+    }
+    const int* gRuns = P.keyStart + G * PB_KEY_COLORS;
+    const int* gJoint = P.islandsOn ? P.jointStart + G * 8 : P.jointColorStart;
     if (P.hasJoints) {
         // rows were filled by k_joint_fill; the NGS pass accumulates into per-body pseudo velocities, colour by colour
-        for (int c = 0; c < 8; ++c) {
-            int start = P.jointColorStart[c], count = P.jointColorStart[c + 1] - start;
-            if (count <= 0) continue;
-            for (int i = tid; i < count; i += nth) jointNgsCall(P, start + i);
-            bar.sync(PH_PREP);
-        }
+        jointNgsPass(GLOBAL, gJoint, tid, nth);
         int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
-        if (count > 0) {                    // overflow bucket: the sequential NGS pass
+        if (count > 0) {                    // overflow bucket: the sequential NGS pass (always part of the device-wide sweep)
             if (tid == 0) jointNgsSeqCall(P, start, count);
             bar.sync(PH_PREP);
         }
     }
-
     for (int it = 0; it < P.iterations; ++it) {
-        contactPass(1, 0);
+        contactPass(GLOBAL, gRuns, tid, nth, 1, 0);
         if (P.hasJoints) {
-            for (int c = 0; c < 8; ++c) {
-                int start = P.jointColorStart[c], count = P.jointColorStart[c + 1] - start;
-                if (count <= 0) continue;
-                for (int i = tid >> 3; i < count; i += nth >> 3) jointSolveCall(P, start + i, lane & 7, 0xFFu << (lane & 24), it == 0, velLive, angvelLive);
-                bar.sync(PH_JOINT_SOLVE);
-            }
+            jointSolvePass(GLOBAL, gJoint, tid, nth, it == 0);
             int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
             if (count > 0) {
                 if (tid == 0) jointSolveSeqCall(P, start, count, it == 0, velLive, angvelLive);
@@ -509,10 +561,21 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             }
         }
     }
+    // the local sweeps end without a grid barrier: bodies are integrated by whichever thread owns their index
+    if (P.islandsOn) bar.sync(PH_LOCAL);
 
     for (int i = tid; i < P.nDyn; i += nth) integrateX(P, i, velLive, angvelLive);
     bar.sync(PH_INTEGRATE_X);
-    contactPass(0, 1);      // relaxation
+
+    // ---- relaxation ----------------------------------------------------------------------------------------------------------------
+    if (P.islandsOn) {
+        for (int g = blockIdx.x; g < G; g += gridDim.x) {
+            loadLocal(g);
+            contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
+        }
+    }
+    contactPass(GLOBAL, gRuns, tid, nth, 0, 1);
+    if (P.islandsOn && P.profNs) bar.sync(PH_LOCAL);     // profiling only: closes the local relaxation sweeps of every CTA
 }
 
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound) {
@@ -540,6 +603,8 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
     P.rowA = ctx->rowA; P.rowB = ctx->rowB; P.rowC = ctx->rowC; P.rowD = ctx->rowD; P.rowE = ctx->rowE; P.rowF = ctx->rowF; P.rowG = ctx->rowG; P.rowL = ctx->rowL;
     P.hasJoints = pb_joint_view(ctx, &P.J) ? 1 : 0;
     for (int c = 0; c <= PB_JOINT_COLORS; ++c) P.jointColorStart[c] = ctx->jointColorStart[c];
+    P.keyStart = ctx->keyStart; P.G = ctx->islandGroups; P.islandsOn = ctx->islandsOn ? 1 : 0;
+    P.jointOrder = (ctx->islandsOn && P.hasJoints) ? ctx->jointOrder : nullptr; P.jointStart = ctx->jointStart;
     P.barrier = ctx->solveBarrier;
     P.profNs = ctx->profile ? ctx->solveProfNs : nullptr;
     // persistent grid: co-resident by construction; small scenes use fewer CTAs so the barrier stays cheap
