@@ -138,10 +138,13 @@ int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
 }
 int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64) {
     cudaSetDevice(ctx->device);
-    unsigned long long raw[2 * PB_MAX_COLORS];
+    unsigned long long raw[2 * PB_MAX_COLORS + 6];
     int rc = pb_solve_profile_colors(ctx, raw);
     if (rc) return rc;
     for (int k = 0; k < PB_MAX_COLORS; ++k) { ms64[k] = raw[k] * 1e-6; count64[k] = (long long)raw[PB_MAX_COLORS + k]; }
+    // colours 61..63 never hold timed phases of their own here (63 is the sequential bucket): the last three slots carry CTA 0's
+    // local sweep split -- NGS, contact, joint colour phases
+    for (int k = 0; k < 3; ++k) { ms64[61 + k] = raw[2 * PB_MAX_COLORS + k] * 1e-6; count64[61 + k] = (long long)raw[2 * PB_MAX_COLORS + 3 + k]; }
     return PB_OK;
 }
 int pb_set_islands(pb_ctx* ctx, int mode) {

@@ -64,7 +64,8 @@ struct SubstepParams {
 };
 
 enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_LOCAL, PH_KINDS };
-#define PROF_WORDS (2 * PH_KINDS + 2 * PB_MAX_COLORS)   // ns + count per phase kind, then ns + count per contact colour
+#define PROF_LOCAL (2 * PH_KINDS + 2 * PB_MAX_COLORS)   // CTA 0's own island sweep, split by colour-phase kind: ns[3] then count[3] (NGS, contact, joint)
+#define PROF_WORDS (PROF_LOCAL + 6)                     // ns + count per phase kind, then ns + count per contact colour, then the local split
 
 __device__ __forceinline__ M3 loadM3ro(const float4* __restrict__ p, int i) {
     M3 r; r.c[0] = mk3(p[3 * i]); r.c[1] = mk3(p[3 * i + 1]); r.c[2] = mk3(p[3 * i + 2]); return r;
@@ -470,6 +471,14 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     const int lane = threadIdx.x & 31;
     const L2Hints H = makeL2Hints();
     const int G = P.G;
+    unsigned long long tLocal = 0;
+    auto stampLocal = [&](int kind) {       // profiling only: CTA 0 times its own local colour phases
+        if (P.profNs && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (kind >= 0) { atomicAdd(&P.profNs[PROF_LOCAL + kind], t - tLocal); atomicAdd(&P.profNs[PROF_LOCAL + 3 + kind], 1ull); }
+            tLocal = t;
+        }
+    };
     const std::integral_constant<bool, true> LOCAL;
     const std::integral_constant<bool, false> GLOBAL;
 
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
                     for (int i = id; i < count; i += nthr) contactSolve<local>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
                 }
             }
-            if (local) __syncthreads(); else bar.sync(PH_CONTACT_PASS, c);
+            if (local) { __syncthreads(); stampLocal(1); } else bar.sync(PH_CONTACT_PASS, c);
         }
     };
     // joint colour runs of a sweep: jr[c] .. jr[c + 1] index P.jointOrder (islandsOn) or are the joint slots themselves
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             const int start = jr[c], count = jr[c + 1] - start;
             if (count <= 0) continue;
             for (int i = id; i < count; i += nthr) jointNgsCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i);
-            if (local) __syncthreads(); else bar.sync(PH_PREP);
+            if (local) { __syncthreads(); stampLocal(0); } else bar.sync(PH_PREP);
         }
     };
     auto jointSolvePass = [&](auto localTag, const int* jr, int id, int nthr, int warmStart) {
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             if (count <= 0) continue;
             for (int i = id >> 3; i < count; i += nthr >> 3)
                 jointSolveCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i, lane & 7, 0xFFu << (lane & 24), warmStart, velLive, angvelLive);
-            if (local) __syncthreads(); else bar.sync(PH_JOINT_SOLVE);
+            if (local) { __syncthreads(); stampLocal(2); } else bar.sync(PH_JOINT_SOLVE);
         }
     };
     // a local group's tables into shared memory (the colour loops then cost no global round trip per colour)
@@ -531,6 +540,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     if (P.islandsOn) {
         for (int g = blockIdx.x; g < G; g += gridDim.x) {
             loadLocal(g);
+            stampLocal(-1);
             if (sRuns[PB_KEY_COLORS] == sRuns[0] && (!P.hasJoints || sJoint[8] == sJoint[0])) continue;     // empty group
             if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
             for (int it = 0; it < P.iterations; ++it) {
@@ -571,6 +581,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     if (P.islandsOn) {
         for (int g = blockIdx.x; g < G; g += gridDim.x) {
             loadLocal(g);
+            stampLocal(-1);
             contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
         }
     }
@@ -639,11 +650,11 @@ int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset) {
     return PB_OK;
 }
 
-// per contact colour: accumulated ns and phase count (out[0..63] ns, out[64..127] counts)
-int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out128) {
-    for (int i = 0; i < 2 * PB_MAX_COLORS; ++i) out128[i] = 0;
+// per contact colour: accumulated ns and phase count (out[0..63] ns, out[64..127] counts); then CTA 0's local split (ns[3], count[3])
+int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out134) {
+    for (int i = 0; i < 2 * PB_MAX_COLORS + 6; ++i) out134[i] = 0;
     if (!ctx->solveProfNs) return PB_OK;
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PB_CUDA(ctx, cudaMemcpy(out128, ctx->solveProfNs + 2 * PH_KINDS, sizeof(unsigned long long) * 2 * PB_MAX_COLORS, cudaMemcpyDeviceToHost));
+    PB_CUDA(ctx, cudaMemcpy(out134, ctx->solveProfNs + 2 * PH_KINDS, sizeof(unsigned long long) * (2 * PB_MAX_COLORS + 6), cudaMemcpyDeviceToHost));
     return PB_OK;
 }

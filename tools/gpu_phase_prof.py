@@ -35,4 +35,8 @@ print(f"{d.name}: bodies={ctx.n_dyn} pairs={c.n_pairs} manifolds={c.n_manifolds}
 print(f"wall ms/step (async loop) {wall:.3f}; stage ms: broad {acc[0]:.3f} narrow {acc[1]:.3f} build {acc[2]:.3f} solve {acc[3]:.3f} total {acc[4]:.3f} (solve kernels {acc[5]:.3f})")
 for k, (ms, cnt) in prof.items():
     print(f"  {k:14s} {ms / steps:8.4f} ms/step  phases/step {cnt / steps:6.1f}  us/phase {1e3 * ms / max(cnt, 1):7.2f}")
+pc = ctx.profile_colors()
+for k, nm in enumerate(["local NGS", "local contact", "local joint"]):
+    ms, cnt = pc[61 + k]
+    print(f"  CTA0 {nm:14s} {ms / steps:8.4f} ms/step  phases/step {cnt / steps:6.1f}  us/phase {1e3 * ms / max(cnt, 1):7.2f}")
 print("launches/step", ctx.launches() / (settle + steps + 10))
