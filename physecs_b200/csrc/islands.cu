@@ -89,8 +89,8 @@ __global__ void k_island_count_joints(int nJ, const int2* __restrict__ bodies, i
     if (b >= 0) atomicAdd(&cnt[root[b]], j >= overflowStart ? localMax + 1 : 1);
 }
 
-// group of every body; stats[0] += constraints of local islands, stats[1] += constraints of all islands
-__global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict__ cnt, int G, int localMax, int* __restrict__ stats) {
+// group of every body
+__global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict__ cnt, int G, int localMax) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int* group = rootThenGroup;
@@ -98,7 +98,17 @@ __global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict_
     int c = cnt[r];
     bool local = c <= localMax;
     group[i] = local ? (int)min((long long)G - 1, (long long)r * G / n) : G;
-    if (r == i && c > 0) { atomicAdd(&stats[1], min(c, 1 << 24)); if (local) atomicAdd(&stats[0], c); }
+}
+
+// stats[0] = constraints of local islands, stats[1] = constraints of all islands (one atomic pair per warp)
+__global__ void k_island_stats(int n, const int* __restrict__ group, const int* __restrict__ cnt, int G, int* __restrict__ stats) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // after k_island_group the roots are gone from `group`, but cnt[] is non-zero exactly at the roots
+    int c = i < n ? min(cnt[i], 1 << 20) : 0;
+    int loc = (i < n && c > 0 && group[i] != G) ? c : 0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); loc += __shfl_xor_sync(0xffffffffu, loc, d); }
+    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&stats[1], c); if (loc) atomicAdd(&stats[0], loc); }
 }
 
 int pb_islands_build(pb_ctx* ctx) {
@@ -121,7 +131,8 @@ int pb_islands_build(pb_ctx* ctx) {
     ++ctx->launches, k_island_count_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->bodyGroup, ctx->islandCount);
     if (joints) ++ctx->launches, k_island_count_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->jointColorStart[8], PB_ISLAND_LOCAL_MAX, ctx->bodyGroup, ctx->islandCount);
     // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
-    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, PB_ISLAND_LOCAL_MAX, ctx->islandStats);
+    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, PB_ISLAND_LOCAL_MAX);
+    ++ctx->launches, k_island_stats<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandStats);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

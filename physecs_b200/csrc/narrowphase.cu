@@ -175,6 +175,73 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
     }
 }
 
+// ---- GJK bin in two launches (the step; scene queries use k_np_prim<BIN_GJK>) ------------------------------------------------------
+// k_np_gjk_hits: GJK on every pair of the bin; the intersecting ones are appended, with their simplex, to a dense hit list.
+// k_np_gjk_manifolds: EPA + contact patch on the hit list: every lane of every warp has a penetrating pair.
+__global__ void __launch_bounds__(128) k_np_gjk_hits(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                     const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                     const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                     const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                     int* __restrict__ hitPair, float4* __restrict__ hitSimplex, int maxHits) {
+    int start = counters[CNT_BINSTART + BIN_GJK], end = counters[CNT_BINSTART + BIN_GJK + 1];
+    int lane = threadIdx.x & 31;
+    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+        int idx = base + lane;
+        bool hit = false;
+        GjkV simplex[4];
+        int pi = 0;
+        if (idx < end) {
+            pi = pairOrder[idx];
+            int2 p = pairs[pi];
+            GjkPair g = gjkPairSetup(colType[p.x], colParams[p.x], mk3(wpos[p.x]), mkq(wquat[p.x]), colMesh[p.x],
+                                     colType[p.y], colParams[p.y], mk3(wpos[p.y]), mkq(wquat[p.y]), colMesh[p.y]);
+            hit = gjkPairIntersect(g, convexes, simplex);
+        }
+        int slot = warpReserve(hit ? 1 : 0, &counters[CNT_GJK_HITS]);
+        if (hit) {
+            if (slot < maxHits) {
+                hitPair[slot] = pi;
+                float4* o = hitSimplex + 9 * (size_t)slot;
+                const float* f = (const float*)simplex;        // 4 x {pos, sp0, sp1} = 36 floats
+#pragma unroll
+                for (int k = 0; k < 9; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+            } else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_np_gjk_manifolds(const int2* __restrict__ pairs, int* __restrict__ counters,
+                                                          const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                          const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                          const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                          const int* __restrict__ hitPair, const float4* __restrict__ hitSimplex, int maxHits,
+                                                          int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    int n = min(counters[CNT_GJK_HITS], maxHits);
+    int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+        int h = base + lane;
+        bool hit = false, flip = false;
+        Manifold m; m.np = 0; m.tri = -1;
+        int a = 0, b = 0;
+        if (h < n) {
+            int2 p = pairs[hitPair[h]];
+            a = p.x; b = p.y;
+            GjkPair g = gjkPairSetup(colType[a], colParams[a], mk3(wpos[a]), mkq(wquat[a]), colMesh[a],
+                                     colType[b], colParams[b], mk3(wpos[b]), mkq(wquat[b]), colMesh[b]);
+            flip = g.flip;
+            GjkV simplex[4];
+            float* f = (float*)simplex;
+            const float4* in = hitSimplex + 9 * (size_t)h;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { float4 v = in[k]; f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w; }
+            gjkPairManifold(g, convexes, simplex, m, counters);
+            hit = m.np > 0;
+        }
+        int slot = warpReserve(hit ? 1 : 0, &counters[CNT_RAWM]);
+        if (hit) storeManifold(slot, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+    }
+}
+
 // ---- mesh bins -------------------------------------------------------------------------------------------------------
 // Collect triangle contacts of one (shape, mesh) pair in the reference's traversal order (TriangleMesh.cpp:166-192:
 // explicit stack, left child popped first; CollisionTriangleMesh.cpp:895-907).
@@ -421,7 +488,20 @@ int pb_narrowphase(pb_ctx* ctx) {
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
-    if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
+    if (!ctx->convexes.empty()) {
+        // hit list: one entry per intersecting pair, i.e. per manifold of the bin -> the manifold capacity bounds it
+        int want = ctx->caps.max_manifolds < ctx->caps.max_pairs ? ctx->caps.max_manifolds : ctx->caps.max_pairs;
+        if (ctx->gjkHitCap < want) {
+            int rc;
+            if ((rc = pb_alloc(ctx, &ctx->gjkHitPair, (size_t)want)) || (rc = pb_alloc(ctx, &ctx->gjkHitSimplex, 9 * (size_t)want))) return rc;
+            ctx->gjkHitCap = want;
+        }
+        ++ctx->launches, k_np_gjk_hits<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat,
+                                                                     ctx->convexDev, ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap);
+        ++ctx->launches, k_np_gjk_manifolds<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat, ctx->convexDev,
+                                                                          ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap, ctx->mKey, ctx->mNormal, ctx->mPts,
+                                                                          ctx->caps.max_manifolds);
+    }
 #undef LAUNCH_PRIM
 #define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
         ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)

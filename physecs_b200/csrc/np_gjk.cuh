@@ -41,7 +41,11 @@ struct Shape {
     const float4* verts; int nVertsPadded;
 };
 
-__device__ inline V3 support(const Shape& s, V3 dir) {
+// __noinline__ on the big routines of this file: GJK and EPA call support() from a dozen places, and the X-vs-convex kernels inline
+// GJK, EPA and a clipping routine per shape combination -- k_np_prim<GJK> was 474 KB of SASS, whose divergent lanes (5 of 32 threads
+// active per instruction) spent most of their time on instruction-cache misses (ncu: stall_no_instruction dominant).  One shared
+// copy of each routine keeps the kernel inside the instruction cache; the arithmetic is unchanged.
+static __device__ __noinline__ V3 support(const Shape& s, V3 dir) {
     switch (s.type) {
         case PB_SPHERE: return s.pos + dir * s.prm.x;
         case PB_CAPSULE: return s.pos + s.basis.c[0] * gsign(dot(dir, s.basis.c[0])) * s.prm.x + dir * s.prm.y;
@@ -102,7 +106,7 @@ __device__ __forceinline__ float sqrDistPointToLineF(V3 p, V3 a, V3 b) {
 __device__ __forceinline__ float distPointToPlaneF(V3 p, V3 o, V3 n) { return fabsf(dot(p - o, n)); }
 
 // arbitrary tetrahedron around a degenerate start (GJK.h:232-245 / :253-264 / :270-277): fills s[2] (optionally) and s[3]
-__device__ inline void gjkDegenerate(const Shape& s0, const Shape& s1, GjkV* s, bool needS2) {
+static __device__ __noinline__ void gjkDegenerate(const Shape& s0, const Shape& s1, GjkV* s, bool needS2) {
     D3 p0 = mkd(s[0].pos), p1 = mkd(s[1].pos);
     if (needS2) {
         D3 dir = dcross(p0 - p1, mkd(0.0, 1.0, 0.0));
@@ -116,7 +120,7 @@ __device__ inline void gjkDegenerate(const Shape& s0, const Shape& s1, GjkV* s, 
     if (distPointToPlaneF(s[3].pos, s[0].pos, tof(dir)) < 0.0001f) s[3] = minkowski(s0, s1, tof(-dir));
 }
 
-__device__ inline bool gjk(const Shape& s0, const Shape& s1, V3 startDir, GjkV* s) {
+static __device__ __noinline__ bool gjk(const Shape& s0, const Shape& s1, V3 startDir, GjkV* s) {
     D3 dir = mkd(normalize(startDir));
     s[0] = minkowski(s0, s1, tof(dir));
     if (gjkIsZero(s[0].pos)) {
@@ -172,7 +176,7 @@ __device__ __forceinline__ void epaCreateFace(Epa& p, int i0, int i1, int i2) {
 }
 
 // returns the EPA normal; cp0 / cp1 = witness points (with the reference's projection quirk)
-__device__ inline V3 epa(const Shape& s0, const Shape& s1, const GjkV* s, V3& cp0, V3& cp1, Epa& p, int* counters) {
+static __device__ __noinline__ V3 epa(const Shape& s0, const Shape& s1, const GjkV* s, V3& cp0, V3& cp1, Epa& p, int* counters) {
     p.nv = 4; p.nf = 0; p.overflow = false;
     for (int i = 0; i < 4; ++i) p.v[i] = s[i];
     {
@@ -265,7 +269,7 @@ __device__ inline int pickConvexFace(const PbConvexDev& cm, const M3& toWorld, Q
 }
 
 // Collision.cpp:352-412
-__device__ inline void convexConvexContacts(V3 pos0, Q4 or0, const PbConvexDev& m0, V3 sc0, V3 pos1, Q4 or1, const PbConvexDev& m1, V3 sc1,
+static __device__ __noinline__ void convexConvexContacts(V3 pos0, Q4 or0, const PbConvexDev& m0, V3 sc0, V3 pos1, Q4 or1, const PbConvexDev& m1, V3 sc1,
                                             V3 normal, Manifold& m, int* counters) {
     M3 dummy;
     int f0 = pickConvexFace(m0, dummy, or0, true, sc0, normal, true);
@@ -301,7 +305,7 @@ __device__ inline void convexConvexContacts(V3 pos0, Q4 or0, const PbConvexDev& 
 }
 
 // Collision.cpp:694-785
-__device__ inline void capsuleConvexContacts(V3 p0L, V3 p1L, float radius, V3 meshPos, const M3& convexToWorld, const PbConvexDev& cm, V3 sc,
+static __device__ __noinline__ void capsuleConvexContacts(V3 p0L, V3 p1L, float radius, V3 meshPos, const M3& convexToWorld, const PbConvexDev& cm, V3 sc,
                                              Manifold& m, int* counters) {
     Q4 qdummy;
     int f = pickConvexFace(cm, convexToWorld, qdummy, false, sc, m.n, false);
@@ -343,7 +347,7 @@ __device__ inline void capsuleConvexContacts(V3 p0L, V3 p1L, float radius, V3 me
 }
 
 // Collision.cpp:809-871
-__device__ inline void boxConvexContacts(V3 boxCenter, const M3& boxBasis, V3 he, V3 cPos, Q4 cOr, const PbConvexDev& cm, V3 sc, V3 normal,
+static __device__ __noinline__ void boxConvexContacts(V3 boxCenter, const M3& boxBasis, V3 he, V3 cPos, Q4 cOr, const PbConvexDev& cm, V3 sc, V3 normal,
                                          Manifold& m, int* counters) {
     int boxAxis = 0; float boxAxisSign = 0.f, maxDot = 0.f;
     for (int i = 0; i < 3; ++i) {
@@ -371,27 +375,44 @@ __device__ inline void boxConvexContacts(V3 boxCenter, const M3& boxBasis, V3 he
     contactsPolygonBoxFace<GJK_POLY>(boxCenter, boxBasis, boxAxis, boxAxisSign, he, incOrig, incNormal, poly, clipX, clipY, m.p0, m.p1, m.np);
 }
 
-// Dispatch for the GJK bin (Collision.cpp:926-1013): returns true on contact; `flip` when the routine ran with swapped arguments.
-__device__ inline bool collideGjkPair(int t0, float4 q0, V3 pos0, Q4 or0, int mesh0, int t1, float4 q1, V3 pos1, Q4 or1, int mesh1,
-                                      const PbConvexDev* convexes, Manifold& m, bool& flip, int* counters) {
+// Dispatch for the GJK bin (Collision.cpp:926-1013), in two stages so that a step can run them as two launches with the
+// intersecting pairs compacted in between (narrowphase.cu): in a pile most candidate pairs do not intersect, and lanes that left
+// after GJK would otherwise idle through the EPA expansion and the face clipping of their warp mates.
+struct GjkPair {
+    int ta, tb, ma, mb; float4 qa, qb; V3 pa, pb; Q4 oa, ob; bool flip;
+};
+__device__ __forceinline__ GjkPair gjkPairSetup(int t0, float4 q0, V3 pos0, Q4 or0, int mesh0, int t1, float4 q1, V3 pos1, Q4 or1, int mesh1) {
+    GjkPair g;
     // the convex mesh is always argument 1 of the reference routine unless both are convex
-    flip = (t0 == PB_CONVEX_MESH && t1 != PB_CONVEX_MESH);
-    int ta = flip ? t1 : t0, tb = flip ? t0 : t1;
-    float4 qa = flip ? q1 : q0, qb = flip ? q0 : q1;
-    V3 pa = flip ? pos1 : pos0, pb = flip ? pos0 : pos1;
-    Q4 oa = flip ? or1 : or0, ob = flip ? or0 : or1;
-    int ma = flip ? mesh1 : mesh0, mb = flip ? mesh0 : mesh1;
-    Shape sa = makeShape(ta, qa, pa, oa, convexes, ma);
-    Shape sb = makeShape(tb, qb, pb, ob, convexes, mb);
-    GjkV simplex[4];
-    if (!gjk(sa, sb, pb - pa, simplex)) return false;
+    g.flip = (t0 == PB_CONVEX_MESH && t1 != PB_CONVEX_MESH);
+    g.ta = g.flip ? t1 : t0; g.tb = g.flip ? t0 : t1;
+    g.qa = g.flip ? q1 : q0; g.qb = g.flip ? q0 : q1;
+    g.pa = g.flip ? pos1 : pos0; g.pb = g.flip ? pos0 : pos1;
+    g.oa = g.flip ? or1 : or0; g.ob = g.flip ? or0 : or1;
+    g.ma = g.flip ? mesh1 : mesh0; g.mb = g.flip ? mesh0 : mesh1;
+    return g;
+}
+// stage 1: do the shapes intersect?  (simplex out)
+__device__ inline bool gjkPairIntersect(const GjkPair& g, const PbConvexDev* convexes, GjkV* simplex) {
+    Shape sa = makeShape(g.ta, g.qa, g.pa, g.oa, convexes, g.ma);
+    Shape sb = makeShape(g.tb, g.qb, g.pb, g.ob, convexes, g.mb);
+    return gjk(sa, sb, g.pb - g.pa, simplex);
+}
+// stage 2: penetration by EPA, then the contact patch of the shape combination
+__device__ inline void gjkPairManifold(const GjkPair& g, const PbConvexDev* convexes, const GjkV* simplex, Manifold& m, int* counters) {
+    Shape sa = makeShape(g.ta, g.qa, g.pa, g.oa, convexes, g.ma);
+    Shape sb = makeShape(g.tb, g.qb, g.pb, g.ob, convexes, g.mb);
+    const int ta = g.ta, ma = g.ma, mb = g.mb;
+    const float4 qa = g.qa, qb = g.qb;
+    const V3 pa = g.pa, pb = g.pb;
+    const Q4 oa = g.oa, ob = g.ob;
     Epa poly;
     V3 cp0, cp1;
     m.n = epa(sa, sb, simplex, cp0, cp1, poly, counters);
     m.p0[0] = cp0; m.p1[0] = cp1;
     V3 scb = mk3(qb.x, qb.y, qb.z);
     const PbConvexDev& cb = convexes[mb];
-    if (ta == PB_SPHERE) { m.np = 1; return true; }
+    if (ta == PB_SPHERE) { m.np = 1; return; }
     if (ta == PB_CAPSULE) {
         M3 convexToWorld = mat3_cast(ob);
         M3 worldToConvex = inverse(convexToWorld);
@@ -401,17 +422,27 @@ __device__ inline bool collideGjkPair(int t0, float4 q0, V3 pos0, Q4 or0, int me
         Manifold t = m;
         capsuleConvexContacts(p + axisLc * qa.x, p - axisLc * qa.x, qa.y, pb, convexToWorld, cb, scb, t, counters);
         if (t.np) { m = t; } else m.np = 1;
-        return true;
+        return;
     }
     if (ta == PB_BOX) {
         Manifold t = m;
         boxConvexContacts(pa, mat3_cast(oa), mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, counters);
         if (t.np) { m = t; } else m.np = 1;
-        return true;
+        return;
     }
     // convex - convex
     Manifold t = m;
     convexConvexContacts(pa, oa, convexes[ma], mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, counters);
     if (t.np) { m = t; } else m.np = 1;
+}
+
+// both stages in one call (scene queries, where the handful of pairs does not warrant two launches)
+__device__ inline bool collideGjkPair(int t0, float4 q0, V3 pos0, Q4 or0, int mesh0, int t1, float4 q1, V3 pos1, Q4 or1, int mesh1,
+                                      const PbConvexDev* convexes, Manifold& m, bool& flip, int* counters) {
+    GjkPair g = gjkPairSetup(t0, q0, pos0, or0, mesh0, t1, q1, pos1, or1, mesh1);
+    flip = g.flip;
+    GjkV simplex[4];
+    if (!gjkPairIntersect(g, convexes, simplex)) return false;
+    gjkPairManifold(g, convexes, simplex, m, counters);
     return true;
 }

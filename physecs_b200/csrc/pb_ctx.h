@@ -51,6 +51,7 @@ struct PbConvexDev {
 enum {
     CNT_PAIRS = 0, CNT_MANIFOLDS, CNT_POINTS, CNT_STATUS, CNT_MESH_PAIRS, CNT_TRIGGERS, CNT_OVERFLOW, CNT_NCOLORS,
     CNT_RAWM,                           // raw manifold arena entries (incl. 0-point holes); CNT_MANIFOLDS = solve count
+    CNT_GJK_HITS,                       // GJK-bin pairs whose shapes intersect (stage 2 of the split GJK / EPA launch works on these)
     CNT_BIN0 = 16,                      // PB_NUM_BINS bin counters
     CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
     CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
@@ -124,6 +125,7 @@ struct pb_ctx {
     float4* mNormal = nullptr;       // xyz
     float4* mPts = nullptr;          // [8*maxManifolds]: slot 2k = position0, 2k+1 = position1
     int* mColor = nullptr;           // colour per raw manifold
+    int* gjkHitPair = nullptr; float4* gjkHitSimplex = nullptr; int gjkHitCap = 0;   // intersecting GJK-bin pairs + their simplices (9 float4 each)
     int* mSorted = nullptr;          // [maxManifolds] raw index per solve slot
     int* mSortTmp = nullptr; unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
 
