@@ -94,6 +94,7 @@ def reference_sample(n_sample, cells, settle, warmup, steps, threads):
     from physecs_b200 import scenes as S
     d = S.terrain(n_sample, cells=cells, drop=0.3)
     ref = RefScene(d, threads, hashfix=True)
+    ref.presort()      # the order the reference's own first-step insertion sort would reach, without its O(n^2) first step
     for _ in range(settle + warmup):
         ref.simulate()
     t0 = time.perf_counter()
@@ -138,12 +139,13 @@ def main():
     ap.add_argument("--bodies", type=int, default=1_000_000)
     ap.add_argument("--cells", type=int, default=1024)
     ap.add_argument("--settle", type=int, default=150)
-    ap.add_argument("--ref-bodies", type=int, default=4000)
-    ap.add_argument("--ref-cells", type=int, default=80)
+    ap.add_argument("--ref-bodies", type=int, default=32000)
+    ap.add_argument("--ref-cells", type=int, default=200)
     ap.add_argument("--ref-settle", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batched-scenes", type=int, default=4096, help="ragdoll scenes for the sharded-batch section (0 = skip)")
     ap.add_argument("--scene-bodies", type=int, default=1_000_000, help="bodies for the physecs::Scene end-to-end section (0 = skip)")
+    ap.add_argument("--other-configs", type=int, default=1, help="also time BASELINE.json's C1 / C2 / C3 scenes at full size (0 = skip)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (never a bench value)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -330,6 +332,34 @@ def main():
                                  "scenes_on_rank0": per_rank, "ms_per_step": rms / args.steps, "scaling": "strong", "sharding": "contiguous blocks of scenes per rank, no collective",
                                  "bodies_rank0": int(rctx.n_dyn), "manifolds_last_step_rank0": int(rc_.n_manifolds), "joints_rank0": len(rd.joints)}
         rctx.close()
+
+    # ---- the other BASELINE.json configurations at full size (device-resident ms/step; parity for them is tests/test_gpu_fullsize.py) ----
+    if rank == 0 and world == 1 and args.other_configs:
+        other = {}
+        for key, mk, settle in (("C1_pyramid_1k_boxes_8_substeps", lambda: S.pyramid(1000), 60), ("C2_mixed_bin_100k", lambda: S.mixed_bin(100_000), 150),
+                                ("C3_convex_pile_250k", lambda: S.convex_pile(250_000), 100)):
+            try:
+                od = mk()
+                octx = Context(od, device=local_rank, max_pairs=32 * od.n + 4096, max_manifolds=12 * od.n + 4096)
+                for _ in range(settle):
+                    octx.step()
+                octx.sync()
+                ostream = torch.cuda.ExternalStream(octx.stream_ptr(), device=torch.device("cuda", local_rank))
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ks = 50
+                o0.record(ostream)
+                for _ in range(ks):
+                    octx.step()
+                o1.record(ostream)
+                torch.cuda.synchronize()
+                oc = octx.counts()
+                other[key] = {"ms_per_step": o0.elapsed_time(o1) / ks, "body_steps_per_s": octx.n_dyn * ks / (o0.elapsed_time(o1) * 1e-3), "bodies": int(octx.n_dyn),
+                              "pairs": int(oc.n_pairs), "manifolds": int(oc.n_manifolds), "colors": int(oc.n_colors), "substeps": od.substeps,
+                              "settle_steps": settle, "islands": octx.island_stats()}
+                octx.close()
+            except Exception as e:
+                other[key] = {"unavailable": str(e)[:200]}
+        out["other_configs"] = other
 
     # ---- the same workload through the host C++ layer: physecs::Scene over an entt::registry (rank 0, N = 1) ------------------
     if rank == 0 and world == 1 and args.scene_bodies > 0:
