@@ -113,6 +113,13 @@ template <class T> static int uploadRaw(pb_ctx* ctx, const T* host, size_t n, T*
     return PB_OK;
 }
 
+int pb_wait_velocities(pb_ctx* ctx) {
+    if (!ctx->velPending) return PB_OK;
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evVelReady, 0));
+    ctx->velPending = false;
+    return PB_OK;
+}
+
 extern "C" {
 
 // enable/disable per-phase timing inside the persistent substep kernel (CTA 0 stamps %globaltimer at every grid barrier);
@@ -176,6 +183,8 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->numSMs = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    cudaEventCreateWithFlags(&ctx->evMainAtSet, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evVelReady, cudaEventDisableTiming);
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
     int rc = 0;
@@ -267,8 +276,13 @@ int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
 void pb_ctx_destroy(pb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pb_joints_free(ctx);
+    if (ctx->stageVel) cudaFree(ctx->stageVel);
+    if (ctx->evMainAtSet) cudaEventDestroy(ctx->evMainAtSet);
+    if (ctx->evVelReady) cudaEventDestroy(ctx->evVelReady);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
@@ -291,6 +305,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
 }
 
 int pb_sync(pb_ctx* ctx) {
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }
@@ -298,6 +313,7 @@ int pb_sync(pb_ctx* ctx) {
 int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, const float* pos3, const float* quat4, const int* kinematic,
                      const float* vel3, const float* angvel3, const float* invMass, const float* com3, const float* invI9) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     int rows = nDyn + nStatic;
     if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
@@ -518,15 +534,30 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
     size_t n = (size_t)nDyn;
     int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
     float* s = ctx->stage;
+    PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));      // the copy stream starts after everything queued so far
     if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     int g = pb_grid(nDyn, 256);
     if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
     if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
-    if (vel3 || angvel3)
-        ++ctx->launches, k_unpack_vel<<<g, 256, 0, ctx->stream>>>(nDyn, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr, ctx->comInvMass, ctx->vel);
+    if (vel3 || angvel3) {
+        // velocities go up on the copy stream (own staging buffer): ordered after everything already queued on the main stream,
+        // and every reader of ctx->vel on the main stream waits for evVelReady (pb_wait_velocities)
+        if (ctx->stageVelBytes < sizeof(float) * 6 * n) {
+            PB_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+            if (ctx->stageVel) cudaFree(ctx->stageVel);
+            ctx->stageVel = nullptr; ctx->stageVelBytes = 0;
+            PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageVel, sizeof(float) * 6 * n));
+            ctx->stageVelBytes = sizeof(float) * 6 * n;
+        }
+        float* sv = ctx->stageVel;
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evMainAtSet, 0));
+        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(sv, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->copyStream));
+        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(sv + 3 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->copyStream));
+        ++ctx->launches, k_unpack_vel<<<g, 256, 0, ctx->copyStream>>>(nDyn, vel3 ? sv : nullptr, angvel3 ? sv + 3 * n : nullptr, ctx->comInvMass, ctx->vel);
+        PB_CUDA(ctx, cudaEventRecord(ctx->evVelReady, ctx->copyStream));
+        ctx->velPending = true;
+    }
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -605,6 +636,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     }
     if (status & 0x100) return pb_fail(ctx, PB_EUNSUPPORTED, "a candidate pair involves a shape combination not implemented on the device path");
     ctx->curBuf ^= 1;
+    if ((rc = pb_wait_velocities(ctx))) return rc;      // first readers of the velocities: contact build, then the solver
     chooseIslands(ctx);
     if ((rc = pb_joint_begin_step(ctx))) return rc;      // solver body indices of the joints: the island search hooks through them
     if ((rc = pb_contact_build(ctx, nRaw))) return rc;
@@ -622,6 +654,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
 
 int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     int nDyn = ctx->nDyn;
     if (!nDyn) return PB_OK;
     size_t n = (size_t)nDyn;
@@ -684,6 +717,7 @@ int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
 
 int pb_set_mass(pb_ctx* ctx, int nDyn, const float* invMass, const float* com3, const float* invI9) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }      // the pending unpack reads invMass and writes the same records
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_mass: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
     int rc = ensureStage(ctx, sizeof(float) * 13 * (size_t)nDyn); if (rc) return rc;

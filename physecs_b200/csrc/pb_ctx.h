@@ -86,6 +86,10 @@ struct pb_ctx {
     unsigned long long* colorMask = nullptr; // [dyn] contact colours in use per body
     float* stage = nullptr;          // device staging for packed host uploads/downloads
     size_t stageBytes = 0;
+    // pb_set_state uploads the velocities on a second stream: nothing before the contact build reads them, so their H2D copy
+    // overlaps the broadphase and narrowphase of the pb_step that follows (pb_wait_velocities orders every reader after it)
+    cudaStream_t copyStream = nullptr; cudaEvent_t evMainAtSet = nullptr, evVelReady = nullptr; bool velPending = false;
+    float* stageVel = nullptr; size_t stageVelBytes = 0;
 
     // ---- colliders ------------------------------------------------------------------------------
     int nCol = 0;
@@ -203,6 +207,7 @@ template <class T> static inline int pb_alloc(pb_ctx* ctx, T** p, size_t n) {
 static inline int pb_grid(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
 
 // stage launches (implemented in the .cu files)
+int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending velocity upload (capi.cu)
 int pb_broadphase(pb_ctx* ctx);
 int pb_build_tree(pb_ctx* ctx);
 int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);
