@@ -147,9 +147,16 @@ __global__ void k_scene_bounds(int n, const float4* __restrict__ aabbMin, const 
         mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, d));
         mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, d));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&sb[0], floatToOrdered(mn.x)); atomicMin(&sb[1], floatToOrdered(mn.y)); atomicMin(&sb[2], floatToOrdered(mn.z));
-        atomicMax(&sb[3], floatToOrdered(mx.x)); atomicMax(&sb[4], floatToOrdered(mx.y)); atomicMax(&sb[5], floatToOrdered(mx.z));
+    // block-level reduction first: six atomics per CTA, not per warp (57 k atomics on six addresses were most of this kernel's 45 us)
+    __shared__ float red[8][6];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[w][0] = mn.x; red[w][1] = mn.y; red[w][2] = mn.z; red[w][3] = mx.x; red[w][4] = mx.y; red[w][5] = mx.z; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[0][threadIdx.x];
+        const int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; ++k) v = threadIdx.x < 3 ? fminf(v, red[k][threadIdx.x]) : fmaxf(v, red[k][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&sb[threadIdx.x], floatToOrdered(v)); else atomicMax(&sb[threadIdx.x], floatToOrdered(v));
     }
 }
 __device__ __forceinline__ unsigned int expandBits(unsigned int v) {

@@ -88,21 +88,39 @@ __global__ void k_bin_starts(int* counters) {
     }
 }
 
-__global__ void k_pair_scatter(const int* __restrict__ pairBin, int* __restrict__ pairOrder, int* __restrict__ counters, int maxPairs) {
-    int n = min(counters[CNT_PAIRS], maxPairs);
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
-        int i = base + (threadIdx.x & 31);
+// Pairs grouped by bin.  One CTA ranks a tile of blockDim pairs: warps rank their lanes per bin (match_any), the CTA adds the warp
+// counts up in shared memory and reserves ONE range per bin and tile (the per-warp atomics on three or four hot counters were
+// most of this kernel's time at 2 M pairs).
+#define SCATTER_THREADS 1024
+__global__ void __launch_bounds__(SCATTER_THREADS) k_pair_scatter(const int* __restrict__ pairBin, int* __restrict__ pairOrder, int* __restrict__ counters, int maxPairs) {
+    __shared__ int warpCount[SCATTER_THREADS / 32][BIN_COUNT];
+    __shared__ int binStart[BIN_COUNT];
+    const int n = min(counters[CNT_PAIRS], maxPairs);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < BIN_COUNT) binStart[threadIdx.x] = counters[CNT_BINSTART + threadIdx.x];
+    for (int tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x) {
+        for (int b = lane; b < BIN_COUNT; b += 32) warpCount[w][b] = 0;
+        __syncthreads();
+        int i = tile + threadIdx.x;
         int bin = i < n ? pairBin[i] : -1;
         unsigned int act = __ballot_sync(0xffffffffu, bin >= 0);
+        int rank = 0;
         if (bin >= 0) {
             unsigned int peers = __match_any_sync(act, bin);
-            int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-            int leader = __ffs(peers) - 1;
-            int b = 0;
-            if (rank == 0) b = atomicAdd(&counters[CNT_BIN0 + bin], __popc(peers));
-            b = __shfl_sync(peers, b, leader);
-            pairOrder[counters[CNT_BINSTART + bin] + b + rank] = i;
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0) warpCount[w][bin] = __popc(peers);
         }
+        __syncthreads();
+        if (threadIdx.x < BIN_COUNT) {
+            // exclusive prefix over the warps of this bin, then one reservation for the whole tile
+            int run = 0;
+            for (int k = 0; k < SCATTER_THREADS / 32; ++k) { int c = warpCount[k][threadIdx.x]; warpCount[k][threadIdx.x] = run; run += c; }
+            int base = run ? atomicAdd(&counters[CNT_BIN0 + threadIdx.x], run) : 0;
+            for (int k = 0; k < SCATTER_THREADS / 32; ++k) warpCount[k][threadIdx.x] += base;
+        }
+        __syncthreads();
+        if (bin >= 0) pairOrder[binStart[bin] + warpCount[w][bin] + rank] = i;
+        __syncthreads();
     }
 }
 
@@ -458,7 +476,7 @@ int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pai
     int* pairBin = pairOrder + cap;
     ++ctx->launches, k_query_classify<<<blocks, 256, 0, ctx->stream>>>(pairs, pairBin, counters, cap, ctx->colType);
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(counters);
-    ++ctx->launches, k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, pairOrder, counters, cap);
+    ++ctx->launches, k_pair_scatter<<<1, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, pairOrder, counters, cap);
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, pairOrder, counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, mKey, mNormal, mPts, cap)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
@@ -483,7 +501,7 @@ int pb_narrowphase(pb_ctx* ctx) {
                                                       ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding,
                                                       ctx->colClass, ctx->filterLut, ctx->nFilterClasses);
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
-    ++ctx->launches, k_pair_scatter<<<blocks, 256, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
+    ++ctx->launches, k_pair_scatter<<<ctx->numSMs * 2, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
