@@ -622,6 +622,9 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
     long long work = std::max<long long>(std::max<long long>(nDyn, 4ll * workBound), 8ll * ctx->nJoints);
     int grid = (int)std::min<long long>(ctx->solveGrid, (work + 255) / 256);
     if (grid < 1) grid = 1;
+    // islands on: one CTA per group, so that no CTA walks several groups' colour sequences back to back (a sweep costs its ~25 colour
+    // phases of latency however few constraints the group holds); the two grid barriers per substep are cheap next to that
+    if (ctx->islandsOn) grid = std::min(ctx->solveGrid, ctx->islandGroups);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     for (int sub = 0; sub < substeps; ++sub) {
         P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
