@@ -32,6 +32,7 @@
 #include "pb_ctx.h"
 #include "pb_math.cuh"
 #include "joints.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 bool pb_joint_view(pb_ctx* ctx, JointDev* out);
@@ -62,6 +63,8 @@ struct SubstepParams {
     unsigned int* barrier;
     unsigned long long* profNs;
 };
+
+template <bool LOCAL_SYNC, bool L1> struct SweepMode { static constexpr bool local = LOCAL_SYNC, l1 = L1; };
 
 enum { PH_INTEGRATE_V = 0, PH_PREP, PH_CONTACT_PASS, PH_JOINT_SOLVE, PH_INTEGRATE_X, PH_LOCAL, PH_KINDS };
 #define PROF_LOCAL (2 * PH_KINDS + 2 * PB_MAX_COLORS)   // CTA 0's own island sweep, split by colour-phase kind: ns[3] then count[3] (NGS, contact, joint)
@@ -458,16 +461,13 @@ __global__ void __launch_bounds__(128) k_joint_fill(const __grid_constant__ Subs
 // grid and separates colours with the grid barrier.  The LOCAL sweeps (islandsOn) give each group of small islands to one CTA,
 // which walks its colours with __syncthreads only: a ragdoll batch or a field of separate little piles then pays two grid
 // barriers per substep instead of one per colour and pass.  Islands share no dynamic body, so the interleaving is immaterial.
-__global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
-    __shared__ int sRuns[PB_KEY_COLORS + 1];
-    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+// L1LOCAL: the per-CTA sweeps may use L1-cached accesses -- true when everything they read was written before this kernel started or
+// by their own CTA (k_substep_solve); false in the fused small-scene kernel, where other SMs rewrite the rows every substep.
+template <bool L1LOCAL>
+__device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarrier& bar, float4* velLive, float4* angvelLive, int* sRuns, int* sJoint) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
-    GridBarrier bar;
-    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
-    if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
     const int ncol = P.counters[CNT_NCOLORS];
-    float4* velLive = P.velB; float4* angvelLive = P.angvelB;
     const int lane = threadIdx.x & 31;
     const L2Hints H = makeL2Hints();
     const int G = P.G;
@@ -479,16 +479,17 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             tLocal = t;
         }
     };
-    const std::integral_constant<bool, true> LOCAL;
-    const std::integral_constant<bool, false> GLOBAL;
+    // sweep modes: (CTA-local barriers?, L1-cached accesses?)
+    const SweepMode<true, L1LOCAL> LOCAL;
+    const SweepMode<false, false> GLOBAL;
 
     // One contact pass over the colour runs `runs` (129 ints).  id / nthr: this thread's index and the thread count of the sweep.
     // Inside a colour the single-point manifolds come first (one thread each: two memory round trips), then the multi-point ones.
     // A colour that fits one round of the sweep lasts as long as its longest dependent chain, so its multi-point manifolds take
     // four lanes each (lane k = point k, all rows in one wave); over several rounds throughput matters and every manifold gets one
     // thread (the multi-point ones sit together at the end of the colour, so their longer path diverges in few warps).
-    auto contactPass = [&](auto localTag, const int* runs, int id, int nthr, int useBias, int skipSoft) {
-        constexpr bool local = decltype(localTag)::value;
+    auto contactPass = [&](auto mode, const int* runs, int id, int nthr, int useBias, int skipSoft) {
+        constexpr bool local = decltype(mode)::local, l1 = decltype(mode)::l1;
         const int ngroups = nthr >> 2;
         for (int c = 0; c < ncol; ++c) {
             const int start = runs[2 * c], mid = runs[2 * c + 1], count = runs[2 * c + 2] - start;
@@ -498,33 +499,33 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
             } else {
                 const int singles = mid - start, multis = count - singles;
                 if (singles + 4 * multis <= nthr) {
-                    if (id < singles) contactSolve<local>(P, start + id, useBias, skipSoft, velLive, angvelLive, H);
+                    if (id < singles) contactSolve<l1>(P, start + id, useBias, skipSoft, velLive, angvelLive, H);
                     int g = ngroups - 1 - (id >> 2);      // from the far end: the low threads hold the singles
-                    if (g < multis) contactSolveQuad<local>(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
+                    if (g < multis) contactSolveQuad<l1>(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
                 } else {
-                    for (int i = id; i < count; i += nthr) contactSolve<local>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+                    for (int i = id; i < count; i += nthr) contactSolve<l1>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
                 }
             }
             if (local) { __syncthreads(); stampLocal(1); } else bar.sync(PH_CONTACT_PASS, c);
         }
     };
     // joint colour runs of a sweep: jr[c] .. jr[c + 1] index P.jointOrder (islandsOn) or are the joint slots themselves
-    auto jointNgsPass = [&](auto localTag, const int* jr, int id, int nthr) {
-        constexpr bool local = decltype(localTag)::value;
+    auto jointNgsPass = [&](auto mode, const int* jr, int id, int nthr) {
+        constexpr bool local = decltype(mode)::local, l1 = decltype(mode)::l1;
         for (int c = 0; c < 8; ++c) {
             const int start = jr[c], count = jr[c + 1] - start;
             if (count <= 0) continue;
-            for (int i = id; i < count; i += nthr) jointNgsCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i);
+            for (int i = id; i < count; i += nthr) jointNgsCall<l1>(P, P.jointOrder ? P.jointOrder[start + i] : start + i);
             if (local) { __syncthreads(); stampLocal(0); } else bar.sync(PH_PREP);
         }
     };
-    auto jointSolvePass = [&](auto localTag, const int* jr, int id, int nthr, int warmStart) {
-        constexpr bool local = decltype(localTag)::value;
+    auto jointSolvePass = [&](auto mode, const int* jr, int id, int nthr, int warmStart) {
+        constexpr bool local = decltype(mode)::local, l1 = decltype(mode)::l1;
         for (int c = 0; c < 8; ++c) {
             const int start = jr[c], count = jr[c + 1] - start;
             if (count <= 0) continue;
             for (int i = id >> 3; i < count; i += nthr >> 3)
-                jointSolveCall<local>(P, P.jointOrder ? P.jointOrder[start + i] : start + i, lane & 7, 0xFFu << (lane & 24), warmStart, velLive, angvelLive);
+                jointSolveCall<l1>(P, P.jointOrder ? P.jointOrder[start + i] : start + i, lane & 7, 0xFFu << (lane & 24), warmStart, velLive, angvelLive);
             if (local) { __syncthreads(); stampLocal(2); } else bar.sync(PH_JOINT_SOLVE);
         }
     };
@@ -586,7 +587,45 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
         }
     }
     contactPass(GLOBAL, gRuns, tid, nth, 0, 1);
+}
+
+
+__global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
+    __shared__ int sRuns[PB_KEY_COLORS + 1];
+    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+    GridBarrier bar;
+    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
+    if (P.profNs && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
+    substepColoured<true>(P, bar, P.velB, P.angvelB, sRuns, sJoint);
     if (P.islandsOn && P.profNs) bar.sync(PH_LOCAL);     // profiling only: closes the local relaxation sweeps of every CTA
+}
+
+// Small scenes (a box pyramid, a few hundred ragdolls): the WHOLE substep loop of a step in one launch -- velocity integration,
+// contact prep and joint row fill become grid-stride phases in front of the coloured part, and the velocity buffers swap inside the
+// kernel.  A step then costs one launch instead of four or five per substep, which is most of what such a step costs; the register
+// appetite of the prep phases (114) does not matter at this size.  Same device functions, same arithmetic, same order.
+__global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_constant__ SubstepParams P) {
+    __shared__ int sRuns[PB_KEY_COLORS + 1];
+    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    GridBarrier bar;
+    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
+    if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
+    const int nManifolds = P.counters[CNT_MANIFOLDS];
+    float4* vel = P.velA; float4* angvel = P.angvelA; float4* velLive = P.velB; float4* angvelLive = P.angvelB;
+    for (int sub = 0; sub < P.substeps; ++sub) {
+        for (int i = tid; i < P.nDyn; i += nth) integrateV(P, i, vel, angvel, velLive, angvelLive);
+        bar.sync(PH_INTEGRATE_V);
+        for (int s = tid; s < nManifolds; s += nth) contactPrep(P, s, vel, angvel);
+        if (P.hasJoints) for (int j = tid; j < P.J.n; j += nth) jointPrepOne(P.J, j, 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.bodyRec, P.pseudoLin, P.pseudoAng);
+        bar.sync(PH_PREP);
+        substepColoured<false>(P, bar, velLive, angvelLive, sRuns, sJoint);
+        bar.sync(PH_LOCAL);       // the relaxation pass of every sweep is in before the next substep reads the velocities
+        // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity of the next substep
+        float4* t = vel; vel = velLive; velLive = t;
+        t = angvel; angvel = angvelLive; angvelLive = t;
+    }
 }
 
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound) {
@@ -596,6 +635,10 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
         int perSM = 0;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_substep_solve, 256, 0));
         if (perSM < 1) return pb_fail(ctx, PB_ECUDA, "k_substep_solve does not fit on an SM");
+        int perSM2 = 0;
+        PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, k_step_solve_small, 256, 0));
+        if (perSM2 < perSM) perSM = perSM2;       // both persistent kernels use the same co-resident grid
+        if (perSM < 1) return pb_fail(ctx, PB_ECUDA, "k_step_solve_small does not fit on an SM");
         ctx->solveGrid = perSM * ctx->numSMs;
         int rc = pb_alloc(ctx, &ctx->solveBarrier, 64); if (rc) return rc;
         rc = pb_alloc(ctx, &ctx->solveProfNs, PROF_WORDS); if (rc) return rc;
@@ -626,6 +669,21 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
     // phases of latency however few constraints the group holds); the two grid barriers per substep are cheap next to that
     if (ctx->islandsOn) grid = std::min(ctx->solveGrid, ctx->islandGroups);
     cudaEventRecord(ctx->ev[5], ctx->stream);
+    // small scenes: the whole substep loop in one launch (k_step_solve_small); PB_FUSED=0 / 1 overrides the size rule
+    static const int fusedEnv = [] { const char* e = getenv("PB_FUSED"); return e ? atoi(e) : -1; }();
+    // (measured: equal or slightly ahead up to ~1 k bodies -- 64 ragdolls 0.78 vs 0.80 ms/step, 1 k-box pyramid 1.50 vs 1.52 -- and behind
+    // from ~5 k bodies on, where the 3-CTA/SM register cap makes the prep phases spill; such steps are bound by the latency of their
+    // ~30 colour phases per substep, not by launches)
+    const bool fused = fusedEnv >= 0 ? fusedEnv != 0 : (nDyn <= 2048 && workBound <= 8192 && ctx->nJoints <= 4096);
+    if (fused) {
+        P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
+        int fgrid = ctx->islandsOn ? std::min(ctx->solveGrid, ctx->islandGroups) : grid;
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
+        void* args[] = { &P };
+        ++ctx->launches;
+        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small, dim3(fgrid), dim3(256), args, 0, ctx->stream));
+        if (substeps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); }
+    } else
     for (int sub = 0; sub < substeps; ++sub) {
         P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
         ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(P);
