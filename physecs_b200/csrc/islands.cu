@@ -129,9 +129,9 @@ int pb_islands_build(pb_ctx* ctx) {
     if (joints) ++ctx->launches, k_island_hook_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->islandParent);
     ++ctx->launches, k_island_compress<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->bodyGroup);
     ++ctx->launches, k_island_count_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->bodyGroup, ctx->islandCount);
-    if (joints) ++ctx->launches, k_island_count_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->jointColorStart[8], PB_ISLAND_LOCAL_MAX, ctx->bodyGroup, ctx->islandCount);
+    if (joints) ++ctx->launches, k_island_count_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->jointColorStart[8], ctx->islandLocalMax, ctx->bodyGroup, ctx->islandCount);
     // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
-    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, PB_ISLAND_LOCAL_MAX);
+    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandLocalMax);
     ++ctx->launches, k_island_stats<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandStats);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

@@ -177,6 +177,7 @@ struct pb_ctx {
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
     int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)
     int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)
+    int islandLocalMax = PB_ISLAND_LOCAL_MAX;   // env PB_ISLAND_LOCAL_MAX overrides (tests: force a mix of local and device-wide sweeps)
     bool islandsOn = false;          // this step
     int islandsHold = 0;             // auto: steps left before small islands are looked for again
     int lastIslandLocal = 0, lastIslandTotal = 0;   // constraints in small islands / in all islands, last step that looked

@@ -50,3 +50,23 @@ def test_trigger_pairs(contact_filter):
     assert s["steps"] == 70
     assert s["triggers"] > 20, "no overlapping trigger pairs: the test checks nothing"
     assert s["trigger_changes"] > 40, "trigger sets never changed: enter / exit not exercised"
+
+
+@pytest.mark.parametrize("local_max", [4, 1024])
+@pytest.mark.parametrize("maker,steps", [
+    (lambda: S.ragdolls(8), 50), (lambda: S.terrain_mixed(500, cells=32), 60), (lambda: S.mixed_bin(700, spacing=0.8), 50), (lambda: S.joint_star(12), 40),
+])
+def test_three_gates_with_island_sweeps(maker, steps, local_max, monkeypatch):
+    """Simulation islands forced on (default: auto): small islands are swept per CTA, the rest device-wide.  local_max = 4 pushes
+    every island with more than four constraints into the device-wide sweep, so both kinds run side by side in one step; the solve
+    order handed to the oracle is then (group, colour, slot).  Results must stay identical to the reference in every mode."""
+    monkeypatch.setenv("PB_ISLANDS", "1")
+    monkeypatch.setenv("PB_ISLAND_LOCAL_MAX", str(local_max))
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps and s["worst_manifold"] <= parity.TOL
+
+
+def test_islands_off_matches(monkeypatch):
+    monkeypatch.setenv("PB_ISLANDS", "0")
+    s = parity.run_gates(S.ragdolls(8), steps=40)
+    assert s["steps"] == 40
