@@ -70,3 +70,12 @@ def test_islands_off_matches(monkeypatch):
     monkeypatch.setenv("PB_ISLANDS", "0")
     s = parity.run_gates(S.ragdolls(8), steps=40)
     assert s["steps"] == 40
+
+
+@pytest.mark.parametrize("maker,steps", [(lambda: S.mixed_bin(900, spacing=0.8), 40), (lambda: S.trigger_zoo(160), 40), (lambda: S.ragdolls(8), 40)])
+def test_three_gates_tree_broadphase_on_small_scenes(maker, steps, monkeypatch):
+    """Scenes up to 8192 colliders normally take the all-pairs kernel; PB_BRUTE_FORCE_MAX=0 sends them through the Morton sort /
+    LBVH / packet walk that large scenes use (the full-size tests cover it at 10^5..10^6 colliders)."""
+    monkeypatch.setenv("PB_BRUTE_FORCE_MAX", "0")
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps
