@@ -189,12 +189,86 @@ __global__ void k_radix_scatter(const unsigned int* __restrict__ keys, const int
     }
 }
 
+// Small inputs (n <= SORT_SMALL_MAX): every pass of the LSD sort inside ONE CTA, keys and payloads ping-ponging in shared memory
+// -- one launch instead of (histogram + scan + scatter) x passes.  Same stable 8-bit passes: each warp owns a contiguous chunk,
+// ranks its keys round by round with match_any, and the per-(digit, warp) counts are scanned digit-major by the whole CTA.
+#define SORT_SMALL_MAX 8192
+#define SORT_SMALL_THREADS 1024
+__global__ void __launch_bounds__(SORT_SMALL_THREADS) k_sort_small(unsigned int* __restrict__ keys, int* __restrict__ vals, int n, int bits) {
+    extern __shared__ unsigned int smem[];
+    unsigned int* k0 = smem; unsigned int* k1 = k0 + SORT_SMALL_MAX;
+    int* v0 = (int*)(k1 + SORT_SMALL_MAX); int* v1 = v0 + SORT_SMALL_MAX;
+    unsigned int* cnt = (unsigned int*)(v1 + SORT_SMALL_MAX);        // [256 digits][32 warps], digit-major
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nWarps = SORT_SMALL_THREADS / 32;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { k0[i] = keys[i]; v0[i] = vals[i]; }
+    const int chunk = ((n + nWarps - 1) / nWarps + 31) & ~31;          // keys per warp, a multiple of 32
+    const int begin = min(w * chunk, n), end = min(begin + chunk, n);
+    const unsigned int ltMask = (1u << lane) - 1u;
+    for (int shift = 0; shift < bits; shift += 8) {
+        for (int i = threadIdx.x; i < 256 * nWarps; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        // per-warp digit counts
+        for (int base = begin; base < end; base += 32) {
+            int idx = base + lane;
+            if (idx < end) atomicAdd(&cnt[((k0[idx] >> shift) & 255u) * nWarps + w], 1u);
+        }
+        __syncthreads();
+        // exclusive scan over the 256 * nWarps counts (digit-major == output order), 8 entries per thread
+        {
+            const int per = 256 * nWarps / SORT_SMALL_THREADS;      // 8
+            unsigned int loc[8]; unsigned int s = 0;
+#pragma unroll
+            for (int q = 0; q < per; ++q) { loc[q] = cnt[threadIdx.x * per + q]; s += loc[q]; }
+            int inc = warpInclusiveScan((int)s, lane);
+            __shared__ int warpTot[32];
+            if (lane == 31) warpTot[w] = inc;
+            __syncthreads();
+            if (w == 0) { int t = warpTot[lane]; t = warpInclusiveScan(t, lane); warpTot[lane] = t; }
+            __syncthreads();
+            unsigned int run = (unsigned int)(inc - (int)s + (w ? warpTot[w - 1] : 0));
+#pragma unroll
+            for (int q = 0; q < per; ++q) { cnt[threadIdx.x * per + q] = run; run += loc[q]; }
+        }
+        __syncthreads();
+        // stable scatter: each warp walks its chunk in order
+        for (int base = begin; base < end; base += 32) {
+            int idx = base + lane;
+            bool valid = idx < end;
+            unsigned int active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                unsigned int k = k0[idx];
+                int v = v0[idx];
+                unsigned int d = (k >> shift) & 255u;
+                unsigned int peers = __match_any_sync(active, d);
+                unsigned int rank = __popc(peers & ltMask);
+                unsigned int b = cnt[d * nWarps + w];
+                __syncwarp(active);
+                if (rank == 0) cnt[d * nWarps + w] = b + __popc(peers);
+                __syncwarp(active);
+                k1[b + rank] = k; v1[b + rank] = v;
+            }
+        }
+        __syncthreads();
+        unsigned int* tk = k0; k0 = k1; k1 = tk;
+        int* tv = v0; v0 = v1; v1 = tv;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = k0[i]; vals[i] = v0[i]; }
+}
+
 // Sort (keysA, valsA) by the low `bits` bits of the key, 8 bits per pass, ping-ponging with (keysB, valsB).
 // hist must hold 256 * ceil(n/512) (+ scan scratch of ceil(that/4096)+1) uints.
 int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,
                         unsigned int* hist, int histCapTiles, bool* resultInA) {
     *resultInA = true;
     if (n <= 1) return PB_OK;
+    if (n <= SORT_SMALL_MAX) {
+        const size_t smemBytes = sizeof(unsigned int) * (4 * SORT_SMALL_MAX + 256 * (SORT_SMALL_THREADS / 32));
+        if (!ctx->sortSmallOptIn) { PB_CUDA(ctx, cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes)); ctx->sortSmallOptIn = true; }
+        ++ctx->launches, k_sort_small<<<1, SORT_SMALL_THREADS, smemBytes, ctx->stream>>>(keysA, valsA, n, bits);    // sorted in place: result in A
+        PB_CUDA(ctx, cudaGetLastError());
+        return PB_OK;
+    }
     int items = 16;
     if ((n + 127) / 128 <= histCapTiles && n <= (1 << 19)) items = 4;
     const int tileKeys = 32 * items;
