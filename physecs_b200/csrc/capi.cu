@@ -113,7 +113,14 @@ template <class T> static int uploadRaw(pb_ctx* ctx, const T* host, size_t n, T*
     return PB_OK;
 }
 
+int pb_wait_poses(pb_ctx* ctx) {
+    if (!ctx->posePending) return PB_OK;
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evPoseReady, 0));
+    ctx->posePending = false;
+    return PB_OK;
+}
 int pb_wait_velocities(pb_ctx* ctx) {
+    int rc = pb_wait_poses(ctx); if (rc) return rc;
     if (!ctx->velPending) return PB_OK;
     PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evVelReady, 0));
     ctx->velPending = false;
@@ -185,6 +192,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     cudaEventCreateWithFlags(&ctx->evMainAtSet, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evVelReady, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evPoseReady, cudaEventDisableTiming);
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
     int rc = 0;
@@ -232,6 +240,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
 // which is copied / re-hashed so a step that overflowed can simply be run again.
 int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t oldM = ctx->caps.max_manifolds;
     const size_t P = std::max(maxPairs, ctx->caps.max_pairs), M = std::max((size_t)maxManifolds, oldM), C = ctx->caps.max_colliders;
@@ -284,6 +293,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->stageVel) cudaFree(ctx->stageVel);
     if (ctx->evMainAtSet) cudaEventDestroy(ctx->evMainAtSet);
     if (ctx->evVelReady) cudaEventDestroy(ctx->evVelReady);
+    if (ctx->evPoseReady) cudaEventDestroy(ctx->evPoseReady);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
@@ -348,6 +358,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
 int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIndex, const float* lpos3, const float* lquat4, const int* type,
                         const float* params4, const int* mesh, const float* material3, const int* flags, const int* data) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
     ctx->nCol = n;
@@ -532,32 +543,34 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
     ctx->queryTreeValid = false;
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
-    // one staged H2D burst (13 floats / body), then unpack into the float4 SoA
+    // One packed H2D burst (13 floats / body) on the COPY stream, unpacked into the float4 SoA there: ordered after everything
+    // already queued on the main stream, and every reader on the main stream waits for evPoseReady / evVelReady (pb_ctx.h).
     size_t n = (size_t)nDyn;
-    int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
-    float* s = ctx->stage;
-    PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));      // the copy stream starts after everything queued so far
-    if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->stageVelBytes < sizeof(float) * 13 * n) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+        if (ctx->stageVel) cudaFree(ctx->stageVel);
+        ctx->stageVel = nullptr; ctx->stageVelBytes = 0;
+        PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageVel, sizeof(float) * 13 * n));
+        ctx->stageVelBytes = sizeof(float) * 13 * n;
+    }
+    float* s = ctx->stageVel;
+    cudaStream_t cs = ctx->copyStream;
+    PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));
+    PB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->evMainAtSet, 0));
     int g = pb_grid(nDyn, 256);
-    if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, ctx->stream>>>(nDyn, s, ctx->pos);
-    if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, ctx->stream>>>(nDyn, s + 3 * n, ctx->quat);
+    if (pos3 || quat4) {
+        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, cs));
+        if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, cs>>>(nDyn, s, ctx->pos);
+        if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, cs>>>(nDyn, s + 3 * n, ctx->quat);
+        PB_CUDA(ctx, cudaEventRecord(ctx->evPoseReady, cs));
+        ctx->posePending = true;
+    }
     if (vel3 || angvel3) {
-        // velocities go up on the copy stream (own staging buffer): ordered after everything already queued on the main stream,
-        // and every reader of ctx->vel on the main stream waits for evVelReady (pb_wait_velocities)
-        if (ctx->stageVelBytes < sizeof(float) * 6 * n) {
-            PB_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
-            if (ctx->stageVel) cudaFree(ctx->stageVel);
-            ctx->stageVel = nullptr; ctx->stageVelBytes = 0;
-            PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageVel, sizeof(float) * 6 * n));
-            ctx->stageVelBytes = sizeof(float) * 6 * n;
-        }
-        float* sv = ctx->stageVel;
-        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evMainAtSet, 0));
-        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(sv, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->copyStream));
-        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(sv + 3 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->copyStream));
-        ++ctx->launches, k_unpack_vel<<<g, 256, 0, ctx->copyStream>>>(nDyn, vel3 ? sv : nullptr, angvel3 ? sv + 3 * n : nullptr, ctx->comInvMass, ctx->vel);
-        PB_CUDA(ctx, cudaEventRecord(ctx->evVelReady, ctx->copyStream));
+        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        ++ctx->launches, k_unpack_vel<<<g, 256, 0, cs>>>(nDyn, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr, ctx->comInvMass, ctx->vel);
+        PB_CUDA(ctx, cudaEventRecord(ctx->evVelReady, cs));
         ctx->velPending = true;
     }
     PB_CUDA(ctx, cudaGetLastError());
@@ -566,6 +579,7 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
 
 int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     if (n <= 0) return PB_OK;
     size_t bytes = sizeof(float) * 8 * (size_t)n;
@@ -587,6 +601,7 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
 
 int pb_refresh_bounds(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     return pb_update_bounds_all(ctx, 0.01f, 1);
 }
@@ -621,6 +636,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     PB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream));
     if ((rc = pb_broadphase(ctx))) return rc;
     cudaEventRecord(ctx->ev[1], ctx->stream);
+    if ((rc = pb_wait_poses(ctx))) return rc;          // the broadphase above ran on the bounds of the previous step's end; from here on poses are read
     if ((rc = pb_world_poses(ctx))) return rc;
     if ((rc = pb_narrowphase(ctx))) return rc;
     cudaEventRecord(ctx->ev[2], ctx->stream);
@@ -677,6 +693,7 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
 
 int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     if (nStatic != ctx->nStatic) return pb_fail(ctx, PB_EINVAL, "pb_set_static_poses: n_static mismatch");
     if (!nStatic) return PB_OK;
@@ -694,6 +711,7 @@ int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float
 
 int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     if (n <= 0) return PB_OK;
     for (int i = 0; i < n; ++i) if (cols[i] < 0 || cols[i] >= ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_bounds: collider out of range");
@@ -708,6 +726,7 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
 
 int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
     cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     ctx->queryTreeValid = false;
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
     if (!nDyn) return PB_OK;

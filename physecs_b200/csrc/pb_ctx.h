@@ -86,10 +86,12 @@ struct pb_ctx {
     unsigned long long* colorMask = nullptr; // [dyn] contact colours in use per body
     float* stage = nullptr;          // device staging for packed host uploads/downloads
     size_t stageBytes = 0;
-    // pb_set_state uploads the velocities on a second stream: nothing before the contact build reads them, so their H2D copy
-    // overlaps the broadphase and narrowphase of the pb_step that follows (pb_wait_velocities orders every reader after it)
-    cudaStream_t copyStream = nullptr; cudaEvent_t evMainAtSet = nullptr, evVelReady = nullptr; bool velPending = false;
-    float* stageVel = nullptr; size_t stageVelBytes = 0;
+    // pb_set_state uploads on a second stream.  The broadphase of the pb_step that follows reads neither poses (it works on the bounds
+    // refreshed at the end of the previous step, like the reference: Physecs.cpp:556-559) nor velocities, the narrowphase needs the
+    // poses, the contact build the velocities: the step waits for evPoseReady after the broadphase and for evVelReady before the
+    // build, so the whole H2D copy hides behind the broadphase.  Every other entry point waits for both (pb_wait_velocities).
+    cudaStream_t copyStream = nullptr; cudaEvent_t evMainAtSet = nullptr, evVelReady = nullptr, evPoseReady = nullptr; bool velPending = false, posePending = false;
+    float* stageVel = nullptr; size_t stageVelBytes = 0;   // staging of the copy stream: 13 floats per body (pos 3, quat 4, vel 3, angvel 3)
 
     // ---- colliders ------------------------------------------------------------------------------
     int nCol = 0;
@@ -210,7 +212,8 @@ template <class T> static inline int pb_alloc(pb_ctx* ctx, T** p, size_t n) {
 static inline int pb_grid(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
 
 // stage launches (implemented in the .cu files)
-int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending velocity upload (capi.cu)
+int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending pb_set_state upload, poses and velocities (capi.cu)
+int pb_wait_poses(pb_ctx* ctx);        // ... for its pose half only
 int pb_broadphase(pb_ctx* ctx);
 int pb_build_tree(pb_ctx* ctx);
 int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);

@@ -114,6 +114,7 @@ __global__ void k_query_candidates(int qType, float4 qPrm, float4 qPos, float4 q
 
 // tree + world collider poses for the current device state (no-op while nothing changed since the last build)
 static int prepareQueries(pb_ctx* ctx, int cap) {
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }      // a pending pb_set_state upload (copy stream) is part of the state
     if (!ctx->queryTreeValid) {
         int rc = pb_world_poses(ctx); if (rc) return rc;
         if (ctx->nCol >= 2) { rc = pb_build_tree(ctx); if (rc) return rc; }
