@@ -228,6 +228,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * (CNT_TOTAL + 4)) != cudaSuccess) rc = PB_ECUDA;
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
+    if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
     if (const char* e = getenv("PB_ISLAND_LOCAL_MAX")) ctx->islandLocalMax = atoi(e) > 0 ? atoi(e) : 1;
     if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
     cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);

@@ -117,6 +117,7 @@ struct pb_ctx {
     int* nodeLeft = nullptr; int* nodeRight = nullptr; int* nodeParent = nullptr; int* leafParent = nullptr;
     int2* nodeRange = nullptr; int* nodeFlag = nullptr;
     const int* treeLeafIds = nullptr;   // sorted leaf -> collider of the last pb_build_tree
+    int fusedMode = -1;                 // -1 size rule, 0 never, 1 always: whole-step kernel for tiny scenes (env PB_FUSED)
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
     int bruteForceMax = 8192;           // colliders up to which the step tests all pairs directly instead of building the tree (env PB_BRUTE_FORCE_MAX)
     bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)

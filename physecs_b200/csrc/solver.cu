@@ -670,7 +670,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
     if (ctx->islandsOn) grid = std::min(ctx->solveGrid, ctx->islandGroups);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     // small scenes: the whole substep loop in one launch (k_step_solve_small); PB_FUSED=0 / 1 overrides the size rule
-    static const int fusedEnv = [] { const char* e = getenv("PB_FUSED"); return e ? atoi(e) : -1; }();
+    const int fusedEnv = ctx->fusedMode;      // env PB_FUSED at context creation
     // (measured: equal or slightly ahead up to ~1 k bodies -- 64 ragdolls 0.78 vs 0.80 ms/step, 1 k-box pyramid 1.50 vs 1.52 -- and behind
     // from ~5 k bodies on, where the 3-CTA/SM register cap makes the prep phases spill; such steps are bound by the latency of their
     // ~30 colour phases per substep, not by launches)
