@@ -16,6 +16,8 @@ namespace cg = cooperative_groups;
 #define COLF_TRIGGER 1
 #define COLF_ENABLE 2
 #define COLF_DYNAMIC 4
+#define COLF_BIG 8            // set per tree build: the collider sits on the step's big-static list instead of in the tree
+#define PB_BIG_MAX 32
 
 // ---- ordered-int float encoding for atomic min/max -------------------------------------------------------
 __device__ __forceinline__ int floatToOrdered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -130,9 +132,10 @@ int pb_world_poses(pb_ctx* ctx) {
 }
 
 // ---- Morton keys --------------------------------------------------------------------------------------------------
-__global__ void k_scene_bounds_init(int* sb) {
+__global__ void k_scene_bounds_init(int* sb, int* bigList) {
     if (threadIdx.x < 3) sb[threadIdx.x] = floatToOrdered(FLT_MAX);
     else if (threadIdx.x < 6) sb[threadIdx.x] = floatToOrdered(-FLT_MAX);
+    else if (threadIdx.x == 6 && bigList) bigList[0] = 0;
 }
 __global__ void k_scene_bounds(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, int* __restrict__ sb) {
     V3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
@@ -166,14 +169,31 @@ __device__ __forceinline__ unsigned int expandBits(unsigned int v) {
     v = (v * 0x00000005u) & 0x49249249u;
     return v;
 }
+// Big statics (step trees only, bigList != nullptr): an enabled collider that never issues a query (static / kinematic owner) and
+// spans more than 1/8 of the scene -- a terrain, a ground box, the walls of a bin -- would put a chain of scene-sized boxes from the
+// root down to its leaf, and EVERY query packet would walk that chain (~25 node visits of ~160 per warp at 1 M bodies).  Up to
+// PB_BIG_MAX of them go on a side list that every querying collider tests directly; in the tree their leaf box is empty.  Which
+// colliders are listed does not change the pair set.
 __global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const int* __restrict__ sb,
-                         unsigned int* __restrict__ keys, int* __restrict__ ids) {
+                         unsigned int* __restrict__ keys, int* __restrict__ ids, int* __restrict__ colFlags, int* __restrict__ bigList) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 lo = mk3(orderedToFloat(sb[0]), orderedToFloat(sb[1]), orderedToFloat(sb[2]));
     V3 hi = mk3(orderedToFloat(sb[3]), orderedToFloat(sb[4]), orderedToFloat(sb[5]));
     V3 c = (mk3(aabbMin[i]) + mk3(aabbMax[i])) * 0.5f;
     V3 ext = hi - lo;
+    {
+        const int old = colFlags[i];
+        int f = old & ~COLF_BIG;
+        if (bigList && (f & (COLF_ENABLE | COLF_DYNAMIC)) == COLF_ENABLE) {
+            V3 e = mk3(aabbMax[i]) - mk3(aabbMin[i]);
+            if (fmaxf(e.x, fmaxf(e.y, e.z)) > 0.125f * fmaxf(ext.x, fmaxf(ext.y, ext.z))) {
+                int slot = atomicAdd(&bigList[0], 1);
+                if (slot < PB_BIG_MAX) { bigList[1 + slot] = i; f |= COLF_BIG; }
+            }
+        }
+        if (f != old) colFlags[i] = f;
+    }
     float sx = ext.x > 0.f ? 1024.f / ext.x : 0.f, sy = ext.y > 0.f ? 1024.f / ext.y : 0.f, sz = ext.z > 0.f ? 1024.f / ext.z : 0.f;
     unsigned int x = (unsigned int)fminf(fmaxf((c.x - lo.x) * sx, 0.f), 1023.f);
     unsigned int y = (unsigned int)fminf(fmaxf((c.y - lo.y) * sy, 0.f), 1023.f);
@@ -244,7 +264,11 @@ __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* _
         float4 lmn, lmx, rmn, rmx;
         int lenc, renc;
         unsigned int lstat, rstat;   // subtree holds a collider that never issues a query (static / kinematic / disabled)
-        if (lc < 0) { int c = leafId[~lc]; lmn = aabbMin[c]; lmx = aabbMax[c]; lenc = ~c; lstat = (colFlags[c] & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC); }
+        if (lc < 0) {
+            int c = leafId[~lc]; int fc = colFlags[c];
+            lmn = aabbMin[c]; lmx = aabbMax[c]; lenc = ~c; lstat = (fc & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC);
+            if (fc & COLF_BIG) { lmn = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f); lmx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f); lstat = 0; }
+        }
         else {
             float4 a0 = __ldcg(&nodeMin[2 * lc]), a1 = __ldcg(&nodeMax[2 * lc]), b0 = __ldcg(&nodeMin[2 * lc + 1]), b1 = __ldcg(&nodeMax[2 * lc + 1]);
             lstat = ((unsigned int)__float_as_int(b0.w) | (unsigned int)__float_as_int(b1.w)) >> 31;
@@ -252,7 +276,11 @@ __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* _
             lmx = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
             lenc = lc;
         }
-        if (rc < 0) { int c = leafId[~rc]; rmn = aabbMin[c]; rmx = aabbMax[c]; renc = ~c; rstat = (colFlags[c] & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC); }
+        if (rc < 0) {
+            int c = leafId[~rc]; int fc = colFlags[c];
+            rmn = aabbMin[c]; rmx = aabbMax[c]; renc = ~c; rstat = (fc & (COLF_ENABLE | COLF_DYNAMIC)) != (COLF_ENABLE | COLF_DYNAMIC);
+            if (fc & COLF_BIG) { rmn = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f); rmx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f); rstat = 0; }
+        }
         else {
             float4 a0 = __ldcg(&nodeMin[2 * rc]), a1 = __ldcg(&nodeMax[2 * rc]), b0 = __ldcg(&nodeMin[2 * rc + 1]), b1 = __ldcg(&nodeMax[2 * rc + 1]);
             rstat = ((unsigned int)__float_as_int(b0.w) | (unsigned int)__float_as_int(b1.w)) >> 31;
@@ -304,7 +332,7 @@ __device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ c
 __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* __restrict__ colFlags, const int* __restrict__ colRow,
                              const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
                              const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax,
-                             int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
+                             int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs, const int* __restrict__ bigList) {
     __shared__ int sstack[PAIRS_WARPS][64];
     const unsigned FULL = 0xffffffffu;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,6 +345,14 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
         if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = colRow[a]; }
     }
     if (!__any_sync(FULL, active)) return;
+    if (bigList) {
+        // the big statics kept out of the tree (k_morton): enabled, never querying, so only the entity test is left of the leaf checks
+        const int nb = min(bigList[0], PB_BIG_MAX);
+        for (int k = 0; k < nb; ++k) {
+            const int b = bigList[1 + k];
+            if (active && colRow[b] != rowA && overlaps(amn, amx, aabbMin[b], aabbMax[b])) emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
+        }
+    }
     int* st = sstack[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     int sp = 0;                        // warp-uniform
@@ -402,14 +438,15 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
 
 // Morton sort + LBVH build + refit over the current collider bounds (n >= 2).  Shared by the step's pair search and the
 // scene queries (queries.cu); ctx->treeLeafIds is the sorted leaf -> collider table of the tree just built.
-int pb_build_tree(pb_ctx* ctx) {
+int pb_build_tree(pb_ctx* ctx, bool forStep) {
     int n = ctx->nCol;
     if (n < 2) return PB_OK;
     int* sb = (int*)ctx->sceneBounds;
-    ++ctx->launches, k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb);
+    int* bigList = (forStep && ctx->bigListMode) ? ctx->bigList : nullptr;     // scene queries walk a tree that holds every collider
+    ++ctx->launches, k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb, bigList);
     int blocks = pb_grid(n, 256); if (blocks > ctx->numSMs * 8) blocks = ctx->numSMs * 8;
     ++ctx->launches, k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
-    ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA);
+    ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA, ctx->colFlags, bigList);
     bool inA = true;
     int rc = pb_radix_sort_pairs(ctx, ctx->mortonA, ctx->leafIdA, ctx->mortonB, ctx->leafIdB, n, 30, ctx->radixHist, ctx->radixTiles, &inA);
     if (rc) return rc;
@@ -438,11 +475,12 @@ int pb_broadphase(pb_ctx* ctx) {
         PB_CUDA(ctx, cudaGetLastError());
         return PB_OK;
     }
-    int rc = pb_build_tree(ctx);
+    int rc = pb_build_tree(ctx, true);
     if (rc) return rc;
     const int* ids = ctx->treeLeafIds;
     ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
-                                                            ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
+                                                            ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs,
+                                                            ctx->bigListMode ? ctx->bigList : nullptr);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

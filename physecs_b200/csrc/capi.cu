@@ -209,7 +209,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     size_t sortMax = std::max(C, M);
     ctx->radixTiles = (int)((sortMax + 511) / 512);
     A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
-    A(sceneBounds, 32);
+    A(sceneBounds, 32); A(bigList, 64);
     A(nodeLeft, C); A(nodeRight, C); A(nodeParent, C); A(leafParent, C); A(nodeFlag, C); A(nodeRange, C); A(nodeMin, 2 * C); A(nodeMax, 2 * C);
     A(pairs, P); A(pairOrder, 2 * P); A(trigPairs, P); A(colClass, C);
     A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortTmp, M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
@@ -229,6 +229,9 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
     if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
+    if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
+    if (const char* e = getenv("PB_MESH_LIGHT")) ctx->meshLightMode = atoi(e);
+    if (const char* e = getenv("PB_NP_WAVES")) ctx->npWaves = atoi(e) >= 0 ? atoi(e) : 4;
     if (const char* e = getenv("PB_ISLAND_LOCAL_MAX")) ctx->islandLocalMax = atoi(e) > 0 ? atoi(e) : 1;
     if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
     cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);
@@ -300,7 +303,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
-    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds);
+    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
     F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
@@ -309,7 +312,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(gjkHitPair); F(gjkHitSimplex); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
     F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
-    for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
+    for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.triRec); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }
     if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -409,7 +412,7 @@ static int syncMeshTables(pb_ctx* ctx) {
     for (size_t i = 0; i < t.size(); ++i) {
         auto& m = ctx->triMeshes[i];
         t[i] = { m.verts, m.tris, m.triNormal, m.triCentroid, m.nodeMin, m.nodeMax, m.nTris, m.nNodes,
-                 { m.bmin[0], m.bmin[1], m.bmin[2] }, { m.bmax[0], m.bmax[1], m.bmax[2] } };
+                 { m.bmin[0], m.bmin[1], m.bmin[2] }, { m.bmax[0], m.bmax[1], m.bmax[2] }, m.triRec };
     }
     std::vector<PbConvexDev> c(ctx->convexes.size());
     for (size_t i = 0; i < c.size(); ++i) {
@@ -463,6 +466,7 @@ int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsi
     m.nVerts = nVerts; m.nTris = h.nTris; m.nNodes = h.nNodes;
     std::vector<float4> v(nVerts), tn(h.nTris), tc(h.nTris), nmn(h.nNodes), nmx(h.nNodes);
     std::vector<int4> ti(h.nTris);
+    std::vector<float4> rec(4 * (size_t)h.nTris);
     for (int k = 0; k < 3; ++k) { m.bmin[k] = 3.4e38f; m.bmax[k] = -3.4e38f; }
     for (int i = 0; i < nVerts; ++i) {
         v[i] = make_float4(verts3[3 * i], verts3[3 * i + 1], verts3[3 * i + 2], 0.f);
@@ -472,6 +476,13 @@ int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsi
         ti[i] = make_int4((int)h.triIdx[3 * i], (int)h.triIdx[3 * i + 1], (int)h.triIdx[3 * i + 2], 0);
         tn[i] = make_float4(h.triNormal[3 * i], h.triNormal[3 * i + 1], h.triNormal[3 * i + 2], 0.f);
         tc[i] = make_float4(h.triCentroid[3 * i], h.triCentroid[3 * i + 1], h.triCentroid[3 * i + 2], 0.f);
+        for (int k = 0; k < 3; ++k) {
+            const float4& vk = v[h.triIdx[3 * i + k]];
+            rec[4 * (size_t)i + k] = make_float4(vk.x, vk.y, vk.z, h.triNormal[3 * i + k]);
+        }
+        float ix[3];
+        for (int k = 0; k < 3; ++k) { int id = (int)h.triIdx[3 * i + k]; memcpy(&ix[k], &id, 4); }
+        rec[4 * (size_t)i + 3] = make_float4(ix[0], ix[1], ix[2], 0.f);
     }
     for (int i = 0; i < h.nNodes; ++i) {
         int cnt = h.nodeCountIndex[2 * i], idx = h.nodeCountIndex[2 * i + 1];
@@ -484,6 +495,7 @@ int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsi
     if (!rc) rc = pb_alloc(ctx, &m.tris, (size_t)h.nTris);
     if (!rc) rc = pb_alloc(ctx, &m.triNormal, (size_t)h.nTris);
     if (!rc) rc = pb_alloc(ctx, &m.triCentroid, (size_t)h.nTris);
+    if (!rc) rc = pb_alloc(ctx, &m.triRec, 4 * (size_t)h.nTris);
     if (!rc) rc = pb_alloc(ctx, &m.nodeMin, (size_t)h.nNodes);
     if (!rc) rc = pb_alloc(ctx, &m.nodeMax, (size_t)h.nNodes);
     if (rc) return rc;
@@ -491,6 +503,7 @@ int pb_register_trimesh(pb_ctx* ctx, const float* verts3, int nVerts, const unsi
     PB_CUDA(ctx, cudaMemcpy(m.tris, ti.data(), sizeof(int4) * h.nTris, cudaMemcpyHostToDevice));
     PB_CUDA(ctx, cudaMemcpy(m.triNormal, tn.data(), sizeof(float4) * h.nTris, cudaMemcpyHostToDevice));
     PB_CUDA(ctx, cudaMemcpy(m.triCentroid, tc.data(), sizeof(float4) * h.nTris, cudaMemcpyHostToDevice));
+    PB_CUDA(ctx, cudaMemcpy(m.triRec, rec.data(), sizeof(float4) * 4 * (size_t)h.nTris, cudaMemcpyHostToDevice));
     PB_CUDA(ctx, cudaMemcpy(m.nodeMin, nmn.data(), sizeof(float4) * h.nNodes, cudaMemcpyHostToDevice));
     PB_CUDA(ctx, cudaMemcpy(m.nodeMax, nmx.data(), sizeof(float4) * h.nNodes, cudaMemcpyHostToDevice));
     ctx->triMeshes.push_back(m);
@@ -645,6 +658,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     int nPairs = ctx->hCounters[CNT_PAIRS], nRaw = ctx->hCounters[CNT_RAWM], status = ctx->hCounters[CNT_STATUS];
     ctx->lastCounts = pb_counts{};
     ctx->lastCounts.n_pairs = nPairs;
+    ctx->pairsHint = nPairs;
     ctx->lastCounts.n_mesh_pairs = ctx->hCounters[CNT_MESH_PAIRS];
     ctx->lastCounts.n_triggers = ctx->hCounters[CNT_TRIGGERS];
     if (nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY)) {

@@ -321,6 +321,51 @@ __device__ inline int meshCollect(float4 prm, V3 localPos, Q4 localOr, const PbT
     return cnt;
 }
 
+// The reference's two-pass feature filter over the triangle contacts of one (shape, mesh) pair (CTM.cpp:913-953): writes the
+// generation order (indices into contacts) and returns how many contacts survive.
+__device__ inline int meshFilter(const PbTriMeshDev& mesh, const TriContact* contacts, int cnt, unsigned char* order) {
+    int nGen = 0;
+    // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
+    unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
+    int nVoid = 0;
+    unsigned char live[PB_MAX_TRI_CONTACTS];
+    int nLive = cnt;
+    for (int i = 0; i < cnt; ++i) live[i] = (unsigned char)i;
+    for (int i = nLive - 1; i >= 0; --i) {
+        int ci = live[i];
+        if (contacts[ci].feature == TF_FACE) {
+            int4 ti = mesh.tris[contacts[ci].tri];
+            voidInsert(voidSet, nVoid, (unsigned)ti.x); voidInsert(voidSet, nVoid, (unsigned)ti.y); voidInsert(voidSet, nVoid, (unsigned)ti.z);
+            order[nGen++] = (unsigned char)ci;
+            live[i] = live[nLive - 1];
+            --nLive;
+        }
+    }
+    // stable insertion sort by distance (std::sort on <=16 elements is an insertion sort, CTM.cpp:932)
+    for (int i = 1; i < nLive; ++i) {
+        unsigned char v = live[i];
+        float d = contacts[v].dist;
+        int j = i;
+        while (j > 0 && d < contacts[live[j - 1]].dist) { live[j] = live[j - 1]; --j; }
+        live[j] = v;
+    }
+    // pass 2 (CTM.cpp:934-953)
+    for (int i = 0; i < nLive; ++i) {
+        int ci = live[i];
+        const TriContact& tc = contacts[ci];
+        int4 ti = mesh.tris[tc.tri];
+        unsigned int vi[3] = { (unsigned)ti.x, (unsigned)ti.y, (unsigned)ti.z };
+        if (tc.feature == TF_EDGE) {
+            if (voided(voidSet, nVoid, vi[(tc.fidx + 1) % 3]) && voided(voidSet, nVoid, vi[(tc.fidx + 2) % 3])) continue;
+        } else {
+            if (voided(voidSet, nVoid, vi[tc.fidx])) continue;
+        }
+        order[nGen++] = (unsigned char)ci;
+        voidInsert(voidSet, nVoid, vi[0]); voidInsert(voidSet, nVoid, vi[1]); voidInsert(voidSet, nVoid, vi[2]);
+    }
+    return nGen;
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
@@ -361,45 +406,7 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
                 Epa scratch;
                 int cnt = meshCollect<TYPE>(prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow, HEAVY ? &scratch : nullptr, counters);
                 if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
-                // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
-                unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
-                int nVoid = 0;
-                unsigned char live[PB_MAX_TRI_CONTACTS];
-                int nLive = cnt;
-                for (int i = 0; i < cnt; ++i) live[i] = (unsigned char)i;
-                const PbTriMeshDev& mesh = meshes[meshId];
-                for (int i = nLive - 1; i >= 0; --i) {
-                    int ci = live[i];
-                    if (contacts[ci].feature == TF_FACE) {
-                        int4 ti = mesh.tris[contacts[ci].tri];
-                        voidInsert(voidSet, nVoid, (unsigned)ti.x); voidInsert(voidSet, nVoid, (unsigned)ti.y); voidInsert(voidSet, nVoid, (unsigned)ti.z);
-                        order[nGen++] = (unsigned char)ci;
-                        live[i] = live[nLive - 1];
-                        --nLive;
-                    }
-                }
-                // stable insertion sort by distance (std::sort on <=16 elements is an insertion sort, CTM.cpp:932)
-                for (int i = 1; i < nLive; ++i) {
-                    unsigned char v = live[i];
-                    float d = contacts[v].dist;
-                    int j = i;
-                    while (j > 0 && d < contacts[live[j - 1]].dist) { live[j] = live[j - 1]; --j; }
-                    live[j] = v;
-                }
-                // pass 2 (CTM.cpp:934-953)
-                for (int i = 0; i < nLive; ++i) {
-                    int ci = live[i];
-                    const TriContact& tc = contacts[ci];
-                    int4 ti = mesh.tris[tc.tri];
-                    unsigned int vi[3] = { (unsigned)ti.x, (unsigned)ti.y, (unsigned)ti.z };
-                    if (tc.feature == TF_EDGE) {
-                        if (voided(voidSet, nVoid, vi[(tc.fidx + 1) % 3]) && voided(voidSet, nVoid, vi[(tc.fidx + 2) % 3])) continue;
-                    } else {
-                        if (voided(voidSet, nVoid, vi[tc.fidx])) continue;
-                    }
-                    order[nGen++] = (unsigned char)ci;
-                    voidInsert(voidSet, nVoid, vi[0]); voidInsert(voidSet, nVoid, vi[1]); voidInsert(voidSet, nVoid, vi[2]);
-                }
+                nGen = meshFilter(meshes[meshId], contacts, cnt, order);
             }
         }
         int slot = warpReserve(nGen, &counters[CNT_RAWM]);
@@ -426,6 +433,137 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             }
             m.tri = tc.tri;
             // a == side 0 of the pair; manifolds are computed shape->mesh, flip when the mesh is side 0
+            storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+        }
+    }
+}
+
+// ---- sphere / capsule vs mesh: the 1 M-body terrain scene's bins -------------------------------------------------------------
+// Same result as k_np_mesh<PB_SPHERE|PB_CAPSULE> (same node / triangle predicates, same candidate and contact order), laid out for
+// latency: (1) the cull walk tests BOTH children of a node per step -- siblings are adjacent in nodeMin / nodeMax, so one round
+// of four independent loads replaces two dependent visits and boxes that miss are never popped; a right child whose left sibling
+// still has a subtree to walk waits on the stack (leaf: as ~node), which keeps the reference's left-first order
+// (TriangleMesh.cpp:166-192); (2) a triangle is one 64-byte record (vertices + normal) instead of index -> three vertices +
+// normal, and the next candidate's record is in flight while the current one is tested.
+// (Measured and dropped: laying the (pair, candidate) items of a warp's 32 pairs end to end and testing 32 at a time through shared
+// memory -- bit-identical, but 1.46 vs 1.07 ms of narrowphase at 1 M bodies: the cull walk, not the tests, is what the lanes wait on.)
+#define ML_WARPS 4
+
+__device__ __forceinline__ bool aabbHits(const Aabb& lb, float4 mn, float4 mx) {      // physecs::intersects (BoundsUtil.cpp:87-92)
+    if (lb.mx.x < mn.x || lb.mn.x > mx.x) return false;
+    if (lb.mx.y < mn.y || lb.mn.y > mx.y) return false;
+    if (lb.mx.z < mn.z || lb.mn.z > mx.z) return false;
+    return true;
+}
+
+__device__ inline int meshCullDual(const Aabb& lb, const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax, int* cand, bool* overflow) {
+    int nc = 0;
+#define ML_ADD_LEAF(cnt_, idx_) do { for (int k_ = 0; k_ < (cnt_); ++k_) { if (nc < PB_MAX_TRI_CAND) cand[nc++] = (idx_) + k_; else *overflow = true; } } while (0)
+#define ML_PUSH(v_) do { if (sp < 64) stack[sp++] = (v_); else *overflow = true; } while (0)
+    float4 mn = nodeMin[0], mx = nodeMax[0];
+    if (!aabbHits(lb, mn, mx)) return 0;
+    if (__float_as_int(mn.w)) { ML_ADD_LEAF(__float_as_int(mn.w), __float_as_int(mx.w)); return nc; }
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = __float_as_int(mx.w);
+    while (sp > 0) {
+        int e = stack[--sp];
+        if (e < 0) {                                    // a leaf that had to wait for its left sibling's subtree
+            int cnt = __float_as_int(nodeMin[~e].w), idx = __float_as_int(nodeMax[~e].w);
+            ML_ADD_LEAF(cnt, idx);
+            continue;
+        }
+        float4 lmn = nodeMin[e], lmx = nodeMax[e], rmn = nodeMin[e + 1], rmx = nodeMax[e + 1];
+        bool ol = aabbHits(lb, lmn, lmx), orr = aabbHits(lb, rmn, rmx);
+        int lcnt = __float_as_int(lmn.w), lidx = __float_as_int(lmx.w), rcnt = __float_as_int(rmn.w), ridx = __float_as_int(rmx.w);
+        bool leftSubtree = ol && !lcnt;
+        if (ol && lcnt) ML_ADD_LEAF(lcnt, lidx);
+        if (orr) {
+            if (rcnt && !leftSubtree) ML_ADD_LEAF(rcnt, ridx);
+            else ML_PUSH(rcnt ? ~(e + 1) : ridx);
+        }
+        if (leftSubtree) ML_PUSH(lidx);
+    }
+#undef ML_ADD_LEAF
+#undef ML_PUSH
+    return nc;
+}
+
+template <int TYPE>
+__device__ __forceinline__ bool lightTriTest(V3 localPos, Q4 localOr, float rA, float rB, float4 r0, float4 r1, float4 r2, TriContact& tc) {
+    V3 a = mk3(r0), b = mk3(r1), c = mk3(r2), n = mk3(r0.w, r1.w, r2.w);
+    tc.boxFeature = 0; tc.boxAxis = 0; tc.fidx = 0; tc.feature = TF_FACE; tc.dist = 0.f;
+    tc.normal = tc.cpBody = tc.cpTri = mk3(0.f);
+    if (TYPE == PB_SPHERE) return sphereTriangle(localPos, rA, a, b, c, n, tc);
+    return capsuleTriangle(localPos, localOr, rA, rB, a, b, c, n, tc);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                 const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
+                                                 const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                 const PbTriMeshDev* __restrict__ meshes,
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    const int BIN = BIN_MESH_S + TYPE;
+    int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
+    const int lane = threadIdx.x & 31;
+    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+        int idx = base + lane;
+        TriContact contacts[PB_MAX_TRI_CONTACTS];
+        unsigned char order[PB_MAX_TRI_CONTACTS];
+        int cand[PB_MAX_TRI_CAND];
+        int nc = 0, cnt = 0, nGen = 0;
+        int a = 0, b = 0;
+        bool flip = false, overflow = false;
+        V3 pos1 = mk3(0.f), localPos = mk3(0.f); Q4 or1 = mkq(make_float4(0, 0, 0, 1)), localOr = or1;
+        float4 prm = make_float4(0, 0, 0, 0);
+        int meshId = 0;
+        const float4* rec = nullptr;
+        if (idx < end) {
+            int2 p = pairs[pairOrder[idx]];
+            a = p.x; b = p.y;
+            flip = colType[a] == PB_TRIANGLE_MESH;      // Collision.cpp:897-907: mesh on side 0 -> collide (shape1, mesh0) and flip
+            int shape = flip ? b : a;
+            int meshCol = flip ? a : b;
+            prm = colParams[shape];
+            meshId = colMesh[meshCol];
+            V3 pos0 = mk3(wpos[shape]); Q4 or0 = mkq(wquat[shape]);
+            pos1 = mk3(wpos[meshCol]); or1 = mkq(wquat[meshCol]);
+            Q4 invOr1 = qinverse(or1);
+            localPos = rotate(invOr1, pos0 - pos1);
+            localOr = qmul(invOr1, or0);
+            Aabb lb = shapeBounds(localPos, localOr, TYPE, prm, nullptr, 0);
+            const PbTriMeshDev& mesh = meshes[meshId];
+            rec = mesh.triRec;
+            nc = meshCullDual(lb, mesh.nodeMin, mesh.nodeMax, cand, &overflow);
+        }
+        {
+            // per-pair loop in candidate order, the next triangle's record in flight while this one is tested
+            float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+            if (nc > 0) { const float4* r = rec + 4 * (size_t)cand[0]; q0 = r[0]; q1 = r[1]; q2 = r[2]; }
+            for (int i = 0; i < nc; ++i) {
+                float4 r0 = q0, r1 = q1, r2 = q2;
+                if (i + 1 < nc) { const float4* r = rec + 4 * (size_t)cand[i + 1]; q0 = r[0]; q1 = r[1]; q2 = r[2]; }
+                TriContact tc;
+                if (lightTriTest<TYPE>(localPos, localOr, prm.x, prm.y, r0, r1, r2, tc)) {
+                    tc.tri = cand[i];
+                    if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
+                    else overflow = true;
+                }
+            }
+        }
+        if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+        if (idx < end) nGen = meshFilter(meshes[meshId], contacts, cnt, order);
+        int slot = warpReserve(nGen, &counters[CNT_RAWM]);
+        for (int g = 0; g < nGen; ++g) {
+            const TriContact& tc = contacts[order[g]];
+            Manifold m; m.np = 0; m.tri = tc.tri;
+            if (TYPE == PB_CAPSULE && tc.feature == TF_FACE) {
+                if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
+            } else {
+                manifoldFromClosest(pos1, or1, tc, m);
+            }
+            m.tri = tc.tri;
             storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
         }
     }
@@ -471,6 +609,28 @@ __global__ void k_query_classify(const int2* __restrict__ pairs, int* __restrict
     }
 }
 
+// Grid of a grid-stride bin kernel: a whole number of waves of co-resident CTAs (occupancy x SMs x waves).  numSMs * 8 CTAs of a
+// kernel that fits 7 per SM ran as one full wave plus a 1/7 wave: the mesh bins lost a third of their time to that tail.
+template <typename K>
+static int npGrid(pb_ctx* ctx, K kernel, int threads) {
+    if (ctx->npWaves <= 0) return ctx->numSMs * 8;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+    int grid = ctx->numSMs * occ * ctx->npWaves;
+    if (ctx->pairsHint >= 0) {            // a bin holds at most every pair: no point in launching CTAs far beyond that on small scenes
+        long long need = (2LL * ctx->pairsHint + 4096) / threads + ctx->numSMs;
+        if (need < grid) grid = (int)need;
+    }
+    return grid;
+}
+
+static void launchMeshLight(pb_ctx* ctx, const int2* pairs, const int* pairOrder, int* counters, int4* mKey, float4* mNormal, float4* mPts, int cap, int blocksOverride) {
+#define LAUNCH_LIGHT(TYPE) ++ctx->launches, k_np_mesh_light<TYPE><<<blocksOverride ? blocksOverride : npGrid(ctx, k_np_mesh_light<TYPE>, 32 * ML_WARPS), 32 * ML_WARPS, 0, ctx->stream>>>( \
+        pairs, pairOrder, counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, mKey, mNormal, mPts, cap)
+    LAUNCH_LIGHT(PB_CAPSULE); LAUNCH_LIGHT(PB_SPHERE);
+#undef LAUNCH_LIGHT
+}
+
 int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts) {
     const int blocks = 8;
     int* pairBin = pairOrder + cap;
@@ -486,7 +646,9 @@ int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pai
         ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, mKey, mNormal, mPts, cap)
     if (!ctx->triMeshes.empty()) {
         if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
-        LAUNCH_MESH(PB_BOX); LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE);
+        LAUNCH_MESH(PB_BOX);
+        if (ctx->meshLightMode == 0) { LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE); }
+        else launchMeshLight(ctx, pairs, pairOrder, counters, mKey, mNormal, mPts, cap, blocks);
     }
 #undef LAUNCH_MESH
     PB_CUDA(ctx, cudaGetLastError());
@@ -503,7 +665,7 @@ int pb_narrowphase(pb_ctx* ctx) {
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
     ++ctx->launches, k_pair_scatter<<<ctx->numSMs * 2, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
-#define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
+#define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<npGrid(ctx, k_np_prim<BIN>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
     if (!ctx->convexes.empty()) {
@@ -514,23 +676,25 @@ int pb_narrowphase(pb_ctx* ctx) {
             if ((rc = pb_alloc(ctx, &ctx->gjkHitPair, (size_t)want)) || (rc = pb_alloc(ctx, &ctx->gjkHitSimplex, 9 * (size_t)want))) return rc;
             ctx->gjkHitCap = want;
         }
-        ++ctx->launches, k_np_gjk_hits<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat,
+        ++ctx->launches, k_np_gjk_hits<<<npGrid(ctx, k_np_gjk_hits, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat,
                                                                      ctx->convexDev, ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap);
-        ++ctx->launches, k_np_gjk_manifolds<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat, ctx->convexDev,
+        ++ctx->launches, k_np_gjk_manifolds<<<npGrid(ctx, k_np_gjk_manifolds, 128), 128, 0, ctx->stream>>>(pairs, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat, ctx->convexDev,
                                                                           ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap, ctx->mKey, ctx->mNormal, ctx->mPts,
                                                                           ctx->caps.max_manifolds);
     }
 #undef LAUNCH_PRIM
-#define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
+#define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<npGrid(ctx, k_np_mesh<TYPE>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
         ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
     if (!ctx->triMeshes.empty()) {
         // heavy shapes first: their long threads overlap with the tail of nothing else, the light bins fill in after
         if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
-        LAUNCH_MESH(PB_BOX); LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE);
+        LAUNCH_MESH(PB_BOX);
+        if (ctx->meshLightMode == 0) { LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE); }
+        else launchMeshLight(ctx, pairs, ctx->pairOrder, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, 0);
     }
 #undef LAUNCH_MESH
     if (ctx->triggersPossible)
-        ++ctx->launches, k_np_trigger<<<blocks, 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
+        ++ctx->launches, k_np_trigger<<<npGrid(ctx, k_np_trigger, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                     ctx->colWQuat, ctx->convexDev, ctx->trigPairs, ctx->caps.max_pairs);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

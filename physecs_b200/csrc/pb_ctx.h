@@ -22,6 +22,7 @@ struct PbTriMesh {
     int4* tris = nullptr;          // i0,i1,i2 (post-build order), w unused
     float4* triNormal = nullptr;   // xyz
     float4* triCentroid = nullptr; // xyz
+    float4* triRec = nullptr;      // [4*nTris] packed triangle record for the sphere / capsule bins: {a.xyz, n.x} {b.xyz, n.y} {c.xyz, n.z} {i0, i1, i2 (int bits), 0}
     float4* nodeMin = nullptr;     // xyz, w = triCount (int bits)
     float4* nodeMax = nullptr;     // xyz, w = index    (int bits)
     float bmin[3], bmax[3];        // local-space bounds of all vertices (BoundsUtil.cpp:77-85 needs every vertex)
@@ -41,6 +42,7 @@ struct PbTriMeshDev {
     const float4* verts; const int4* tris; const float4* triNormal; const float4* triCentroid;
     const float4* nodeMin; const float4* nodeMax; int nTris; int nNodes;
     float bmin[3]; float bmax[3];
+    const float4* triRec;          // 64-byte record per triangle (vertices + normal + vertex indices): one gather instead of index -> vertex -> normal
 };
 struct PbConvexDev {
     const float4* verts; const int* faceOffsets; const int* faceIndices; const float4* faceNormal;
@@ -119,6 +121,12 @@ struct pb_ctx {
     const int* treeLeafIds = nullptr;   // sorted leaf -> collider of the last pb_build_tree
     int fusedMode = -1;                 // -1 size rule, 0 never, 1 always: whole-step kernel for tiny scenes (env PB_FUSED)
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
+    int meshLightMode = 1;              // sphere / capsule vs mesh bins: 0 = k_np_mesh, 1 = k_np_mesh_light (dual-child cull walk + packed
+                                        // triangle records) (env PB_MESH_LIGHT)
+    int* bigList = nullptr;             // [1 + 32] count + colliders of the step's big-static side list (broadphase.cu k_morton)
+    int bigListMode = 1;                // 0: every collider stays in the step's tree (env PB_BIG_LIST)
+    int pairsHint = -1;                 // candidate pairs of the previous step (-1: none yet): bounds the bin kernels' grids on small scenes
+    int npWaves = 4;                    // narrowphase bin kernels: grid = SMs x co-resident CTAs x npWaves (env PB_NP_WAVES; 0 = the former numSMs * 8)
     int bruteForceMax = 8192;           // colliders up to which the step tests all pairs directly instead of building the tree (env PB_BRUTE_FORCE_MAX)
     bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)
     int* queryOut = nullptr; int queryCap = 0;   // device result buffer of the scene queries (queries.cu)
@@ -216,7 +224,7 @@ static inline int pb_grid(long long n, int block) { long long g = (n + block - 1
 int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending pb_set_state upload, poses and velocities (capi.cu)
 int pb_wait_poses(pb_ctx* ctx);        // ... for its pose half only
 int pb_broadphase(pb_ctx* ctx);
-int pb_build_tree(pb_ctx* ctx);
+int pb_build_tree(pb_ctx* ctx, bool forStep = false);
 int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);
 int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin);
 int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);

@@ -439,10 +439,11 @@ def terrain_height(x, z):
     return 2.0 * np.sin(0.05 * x) * np.cos(0.05 * z)
 
 
-def terrain(n_bodies=1_000_000, cells=1024, seed=0xC4, substeps=4, iterations=2, spacing=1.0, drop=1.0) -> SceneDesc:
-    """C4: spheres (even i) and capsules (odd i) on a sqrt(n) x sqrt(n) grid over a static triangle-mesh terrain."""
+def terrain(n_bodies=1_000_000, cells=1024, seed=0xC4, substeps=4, iterations=2, spacing=1.0, drop=1.0, mesh_spacing=1.0) -> SceneDesc:
+    """C4: spheres (even i) and capsules (odd i) on a sqrt(n) x sqrt(n) grid over a static triangle-mesh terrain.
+    mesh_spacing < body size gives every body tens of candidate triangles (tests only)."""
     rng = SplitMix(seed)
-    mesh = terrain_mesh(cells, 1.0, seed)
+    mesh = terrain_mesh(cells, mesh_spacing, seed)
     side = int(math.ceil(math.sqrt(n_bodies)))
     i = np.arange(n_bodies)
     gx, gz = i % side, i // side

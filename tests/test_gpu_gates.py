@@ -79,3 +79,32 @@ def test_three_gates_tree_broadphase_on_small_scenes(maker, steps, monkeypatch):
     monkeypatch.setenv("PB_BRUTE_FORCE_MAX", "0")
     s = parity.run_gates(maker(), steps=steps)
     assert s["steps"] == steps
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("maker,steps", [
+    (lambda: S.terrain(1500, cells=48, drop=0.3), 50),
+    (lambda: S.terrain(400, cells=80, drop=0.3, mesh_spacing=0.3), 50),     # tens of candidate triangles per body, several contacts each
+    (lambda: S.terrain_mixed(600, cells=40), 40),
+])
+def test_three_gates_mesh_light_modes(maker, steps, mode, monkeypatch):
+    """Sphere / capsule vs triangle mesh: k_np_mesh (0) and k_np_mesh_light (1, the default: dual-child cull walk, packed triangle
+    records) must both give the reference's manifolds, bit for bit."""
+    monkeypatch.setenv("PB_MESH_LIGHT", str(mode))
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps and s["manifolds"] > 0 and s["worst_manifold"] <= parity.TOL
+
+
+@pytest.mark.parametrize("big", [0, 1])
+@pytest.mark.parametrize("maker,steps", [
+    (lambda: S.mixed_bin(900, spacing=0.8), 40),                 # floor + four walls go on the side list
+    (lambda: S.terrain(1200, cells=48, drop=0.3), 40),           # the terrain does
+    (lambda: S.trigger_zoo(160), 40),
+])
+def test_three_gates_big_static_list(maker, steps, big, monkeypatch):
+    """Tree broadphase with (1, default) and without (0) the big-static side list: scene-sized static colliders are tested directly by
+    every querying collider instead of sitting in the tree.  The pair set must equal the reference's either way."""
+    monkeypatch.setenv("PB_BRUTE_FORCE_MAX", "0")
+    monkeypatch.setenv("PB_BIG_LIST", str(big))
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps and s["manifolds"] > 0
