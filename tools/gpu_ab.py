@@ -13,7 +13,7 @@ for var in variants:
     kv = [x.split("=") for x in var.split(",") if x]
     for k, v in kv:
         os.environ[k] = v
-    ctx = Context(d, max_pairs=8 * d.n + 4096, max_manifolds=6 * d.n + 4096)
+    ctx = Context(d, max_pairs=(8 if name == 'terrain' else 64) * d.n + 4096, max_manifolds=(6 if name == 'terrain' else 16) * d.n + 4096)
     for _ in range(settle):
         ctx.step()
     ctx.sync()
