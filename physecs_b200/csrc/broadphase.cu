@@ -258,9 +258,12 @@ __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* _
     if (i >= n) return;
     int p = leafParent[i];
     while (p >= 0) {
+        // the node's topology words are fetched BEFORE the fence / arrival counter: they do not depend on the sibling, and behind the
+        // atomic they were a fourth dependent memory round trip per level of a ~30-level chain
+        const int lc = left[p], rc = right[p], up = parent[p];
+        const int2 rg = nodeRange[p];
         __threadfence();
         if (atomicAdd(&flag[p], 1) == 0) return;  // first arrival waits for the sibling subtree
-        int lc = left[p], rc = right[p];
         float4 lmn, lmx, rmn, rmx;
         int lenc, renc;
         unsigned int lstat, rstat;   // subtree holds a collider that never issues a query (static / kinematic / disabled)
@@ -289,11 +292,10 @@ __global__ void k_lbvh_refit(int n, const int* __restrict__ leafId, const int* _
             renc = rc;
         }
         lmn.w = __int_as_float(lenc); lmx.w = __int_as_float(renc);
-        int2 rg = nodeRange[p];
         rmn.w = __int_as_float((int)((unsigned int)rg.x | (lstat << 31)));
         rmx.w = __int_as_float((int)((unsigned int)rg.y | (rstat << 31)));
         nodeMin[2 * p] = lmn; nodeMax[2 * p] = lmx; nodeMin[2 * p + 1] = rmn; nodeMax[2 * p + 1] = rmx;
-        p = parent[p];
+        p = up;
     }
 }
 

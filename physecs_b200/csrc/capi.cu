@@ -222,7 +222,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     for (int b = 0; b < 2; ++b) { A(cacheTag[b], cs); A(cacheVal[b], cs); }
     A(counters, CNT_TOTAL);
     ctx->islandGroups = ctx->numSMs * 3;     // co-resident 256-thread CTAs of the persistent substep kernel
-    A(keyStart, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1);
+    A(keyStart, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1); A(keyCursor, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1);
     A(triMeshDev, 64); A(convexDev, 256);
 #undef A
     if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * (CNT_TOTAL + 4)) != cudaSuccess) rc = PB_ECUDA;
@@ -310,7 +310,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
     F(gjkHitPair); F(gjkHitSimplex); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
-    F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
+    F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(keyCursor); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.triRec); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
     for (auto& m : ctx->convexes) { cudaFree(m.verts); cudaFree(m.faceOffsets); cudaFree(m.faceIndices); cudaFree(m.faceNormal); cudaFree(m.faceCentroid); }

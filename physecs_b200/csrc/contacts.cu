@@ -102,7 +102,7 @@ __global__ void k_island_keys(const int* __restrict__ counters, int maxManifolds
     int n = min(counters[CNT_RAWM], maxManifolds);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned int k = sortKey[i];
-        if (k >= PB_KEY_COLORS) { sortKey[i] = 0xFFFFu; continue; }      // discarded (no points): sorts behind every group
+        if (k >= PB_KEY_COLORS) { sortKey[i] = 0xFFFFFFFFu; continue; }      // discarded (no points): sorts behind every group
         int4 key = mKey[i];
         int b = solverIndex(colRow[key.x], nDyn, kinematic);
         if (b < 0) b = solverIndex(colRow[key.y], nDyn, kinematic);
@@ -110,6 +110,29 @@ __global__ void k_island_keys(const int* __restrict__ counters, int maxManifolds
         unsigned int full = (unsigned int)g * PB_KEY_COLORS + k;
         sortKey[i] = full;
         atomicAdd(&keyHist[full], 1);
+    }
+}
+
+// counting-sort scatter: sortKey[i] (< keyLimit; anything else is a discarded manifold) + keyBase indexes the run cursors
+__global__ void __launch_bounds__(256) k_scatter_by_key(const int* __restrict__ counters, int maxManifolds, const unsigned int* __restrict__ sortKey,
+                                                        unsigned int keyBase, unsigned int keyLimit, int* __restrict__ cursor,
+                                                        int* __restrict__ outRaw, unsigned int* __restrict__ outKey) {
+    const int n = min(counters[CNT_RAWM], maxManifolds);
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const unsigned int k = i < n ? sortKey[i] : 0xFFFFFFFFu;
+        const bool valid = k < keyLimit;
+        const unsigned int act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned int peers = __match_any_sync(act, k);
+            const int leader = __ffs(peers) - 1;
+            int slot = 0;
+            if (lane == leader) slot = atomicAdd(&cursor[keyBase + k], __popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+            outRaw[slot] = i;
+            outKey[slot] = k;
+        }
     }
 }
 
@@ -288,20 +311,25 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
         cudaMemsetAsync(ctx->cacheTag[ctx->curBuf], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
         return PB_OK;
     }
-    bool inA = true;
+    // Solve order = a counting sort by (group, colour, single | multi): the run table holds the first slot of every key (scanned key
+    // histogram), so one scatter pass places every manifold (slot = run start + arrival rank, one atomic per distinct key per warp).
+    // The order inside a run is arrival order: a run's manifolds share no dynamic body (the overflow bucket is solved in slot order,
+    // whatever that is), and the taps report the order that was used.  (This replaced a stable radix sort: 2 passes, ~0.13 ms at 2 M manifolds.)
+    unsigned int keyBase = 0, keyLimit = PB_KEY_COLORS;
     if (ctx->islandsOn) {
         // group-major order: every local group's manifolds are contiguous (colour by colour inside), the global group comes last
         PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
         ++ctx->launches, k_island_keys<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mKey, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->bodyGroup, G,
                                                                        ctx->mSortKeyA, ctx->keyStart);
         if ((rc = pb_exclusive_scan(ctx, ctx->keyStart, ctx->keyStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
-        rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 16, ctx->radixHist, ctx->radixTiles, &inA);
+        keyLimit = (unsigned int)nKeys;
     } else {
-        rc = pb_radix_sort_pairs(ctx, ctx->mSortKeyA, ctx->mSortTmp, ctx->mSortKeyB, ctx->mSortValB, n, 8, ctx->radixHist, ctx->radixTiles, &inA);
+        keyBase = (unsigned int)G * PB_KEY_COLORS;     // plain colour-major order: the run table of group G (k_color_starts)
     }
-    if (rc) return rc;
-    ctx->mSorted = inA ? ctx->mSortTmp : ctx->mSortValB;
-    ctx->mSortedKeys = inA ? ctx->mSortKeyA : ctx->mSortKeyB;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->keyCursor, ctx->keyStart, sizeof(int) * ((size_t)nKeys + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    ++ctx->launches, k_scatter_by_key<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mSortKeyA, keyBase, keyLimit, ctx->keyCursor, ctx->mSortValB, ctx->mSortKeyB);
+    ctx->mSorted = ctx->mSortValB;
+    ctx->mSortedKeys = ctx->mSortKeyB;
     int cur = ctx->curBuf, prev = cur ^ 1;
     int* pointOfs = ctx->cPointOfsBuf[cur];
     ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);

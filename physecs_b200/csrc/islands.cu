@@ -100,15 +100,23 @@ __global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict_
     group[i] = local ? (int)min((long long)G - 1, (long long)r * G / n) : G;
 }
 
-// stats[0] = constraints of local islands, stats[1] = constraints of all islands (one atomic pair per warp)
-__global__ void k_island_stats(int n, const int* __restrict__ group, const int* __restrict__ cnt, int G, int* __restrict__ stats) {
+// stats[0] = constraints of local islands, stats[1] = constraints of all islands (one atomic pair per CTA: 31 k warps adding to two
+// words were most of this kernel's 45 us at 1 M bodies)
+__global__ void __launch_bounds__(256) k_island_stats(int n, const int* __restrict__ group, const int* __restrict__ cnt, int G, int* __restrict__ stats) {
+    __shared__ int red[2][8];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     // after k_island_group the roots are gone from `group`, but cnt[] is non-zero exactly at the roots
     int c = i < n ? min(cnt[i], 1 << 20) : 0;
     int loc = (i < n && c > 0 && group[i] != G) ? c : 0;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); loc += __shfl_xor_sync(0xffffffffu, loc, d); }
-    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&stats[1], c); if (loc) atomicAdd(&stats[0], loc); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = c; red[1][threadIdx.x >> 5] = loc; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int t = 0;
+        for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+        if (t) atomicAdd(&stats[1 - threadIdx.x], t);
+    }
 }
 
 int pb_islands_build(pb_ctx* ctx) {

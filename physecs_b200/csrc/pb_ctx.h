@@ -195,6 +195,7 @@ struct pb_ctx {
     int islandsHold = 0;             // auto: steps left before small islands are looked for again
     int lastIslandLocal = 0, lastIslandTotal = 0;   // constraints in small islands / in all islands, last step that looked
     int* keyStart = nullptr;         // [(G + 1) * PB_KEY_COLORS + 1] first solve slot of every (group, colour, single | multi) run
+    int* keyCursor = nullptr;              // [(G+1)*128+1] running copy of keyStart for the counting-sort scatter (contacts.cu)
     unsigned int* mSortedKeys = nullptr;   // solve-order keys of the last step (taps: colour of a slot)
     // per-group joint lists of the step (joints.cu): jointOrder = joints sorted by (group, colour), jointStart[g * 8 + c] their runs (g = G: the global group, colours 0..8)
     int* jointKey = nullptr; int* jointOrder = nullptr; int* jointStart = nullptr; int* jointSortTmp[3] = {nullptr, nullptr, nullptr}; int jointListCap = 0;
