@@ -174,6 +174,9 @@ int pb_get_bounds(pb_ctx* ctx, float* out6);
  * num_points, normal3, points rows [4][2][3] world space at narrowphase time, color */
 int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* num_points, float* normal3, float* points24,
                      int* color, int* n);
+/* the device key / payload sort that orders the broadphase leaves (stands where the reference keeps its entries ordered by
+ * insertion sort, Physecs.cpp:121-133): sorts n host (key, payload) pairs by the low `bits` key bits (rounded up to whole 8-bit passes), stable, and returns them */
+int pb_debug_sort_pairs(pb_ctx* ctx, int n, int bits, const unsigned int* keys_in, const int* vals_in, unsigned int* keys_out, int* vals_out);
 
 /* ---- scene queries (reference Scene::raycastClosest / overlap, Physecs.cpp:571-650) -------------------------- */
 /* Every collider hit by each ray within max_dist (leaf bounds test, then the geometry at its current pose; triangle meshes

@@ -229,6 +229,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
     if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
+    if (const char* e = getenv("PB_SORT_COOP")) ctx->sortCoopMode = atoi(e);
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
     if (const char* e = getenv("PB_MESH_LIGHT")) ctx->meshLightMode = atoi(e);
     if (const char* e = getenv("PB_NP_WAVES")) ctx->npWaves = atoi(e) >= 0 ? atoi(e) : 4;
@@ -303,7 +304,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
-    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList);
+    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
     F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
@@ -915,6 +916,31 @@ int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* no
         if (color) color[s] = (int)((skeys[s] % PB_KEY_COLORS) >> 1);      // key = group * 128 + colour * 2 + multi
     }
     return PB_OK;
+}
+
+int pb_debug_sort_pairs(pb_ctx* ctx, int n, int bits, const unsigned int* keysIn, const int* valsIn, unsigned int* keysOut, int* valsOut) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return PB_OK;
+    unsigned int *kA = nullptr, *kB = nullptr, *hist = nullptr; int *vA = nullptr, *vB = nullptr;
+    const int tiles = (n + 127) / 128 + 4;
+    int rc = pb_alloc(ctx, &kA, (size_t)n);
+    if (!rc) rc = pb_alloc(ctx, &kB, (size_t)n);
+    if (!rc) rc = pb_alloc(ctx, &vA, (size_t)n);
+    if (!rc) rc = pb_alloc(ctx, &vB, (size_t)n);
+    if (!rc) rc = pb_alloc(ctx, &hist, (size_t)256 * tiles + (size_t)256 * tiles / 4096 + 1024);
+    if (!rc) {
+        cudaMemcpyAsync(kA, keysIn, sizeof(unsigned int) * n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(vA, valsIn, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+        bool inA = true;
+        rc = pb_radix_sort_pairs(ctx, kA, vA, kB, vB, n, bits, hist, tiles, &inA);
+        if (!rc) {
+            cudaMemcpyAsync(keysOut, inA ? kA : kB, sizeof(unsigned int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(valsOut, inA ? vA : vB, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = pb_fail(ctx, PB_ECUDA, "pb_debug_sort_pairs");
+        }
+    }
+    cudaFree(kA); cudaFree(kB); cudaFree(vA); cudaFree(vB); cudaFree(hist);
+    return rc;
 }
 
 } // extern "C"

@@ -120,6 +120,8 @@ struct pb_ctx {
     int2* nodeRange = nullptr; int* nodeFlag = nullptr;
     const int* treeLeafIds = nullptr;   // sorted leaf -> collider of the last pb_build_tree
     int fusedMode = -1;                 // -1 size rule, 0 never, 1 always: whole-step kernel for tiny scenes (env PB_FUSED)
+    int sortCoopMode = 1;               // 1: sorts above 8192 keys run as one cooperative launch (k_radix_sort_coop); 0: three launches per pass (env PB_SORT_COOP)
+    int sortCoopGrid = 0; unsigned int* sortBarrier = nullptr;
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
     int meshLightMode = 1;              // sphere / capsule vs mesh bins: 0 = k_np_mesh, 1 = k_np_mesh_light (dual-child cull walk + packed
                                         // triangle records) (env PB_MESH_LIGHT)

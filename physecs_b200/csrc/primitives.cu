@@ -256,6 +256,102 @@ __global__ void __launch_bounds__(SORT_SMALL_THREADS) k_sort_small(unsigned int*
     for (int i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = k0[i]; vals[i] = v0[i]; }
 }
 
+// Large inputs: every pass of the LSD sort inside ONE cooperative launch.  The multi-launch version above costs three launches and a
+// 524 k-entry histogram scan per pass (56 us per pass at 1 M keys, of which the keys themselves are ~3 us of traffic); here each CTA
+// owns a contiguous chunk, histograms are per CTA (256 x grid entries), the columns are scanned by the first 256 CTAs, and the three
+// phases of a pass are separated by device-wide barriers (atom.acq_rel + ld.acquire on one counter, as in the substep solver).
+// Same stable 8-bit passes: chunk order, then warp order inside the chunk, then lane order inside a round (match_any ranks).
+// Everything another CTA may have written is read through L2 (__ldcg): L1 is not coherent across SMs and the buffers ping-pong.
+#define RC_THREADS 256
+#define RC_WARPS (RC_THREADS / 32)
+__device__ __forceinline__ void coopBarrier(unsigned int* counter, unsigned int& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        unsigned int seen;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+        ++seen;
+        while (seen < target) { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_radix_sort_coop(unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits, int chunk,
+                                                                unsigned int* hist, unsigned int* barrier) {
+    __shared__ unsigned int sh[RC_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x, nCta = gridDim.x;
+    unsigned int* totals = hist + 256 * (size_t)nCta;
+    const int wchunk = chunk / RC_WARPS;                 // a multiple of 32
+    const long long first = (long long)cta * chunk + (long long)w * wchunk;
+    const int begin = (int)(first < n ? first : n), end = min(begin + wchunk, n);
+    const unsigned int ltMask = (1u << lane) - 1u;
+    unsigned int target = 0;
+    unsigned int* src = keysA; int* srcV = valsA; unsigned int* dst = keysB; int* dstV = valsB;
+    for (int shift = 0; shift < bits; shift += 8) {
+        // phase 1: digit counts of this CTA's chunk (per warp, then summed; the per-warp exclusive prefixes stay in shared memory)
+        for (int i = lane; i < 256; i += 32) sh[w][i] = 0;
+        __syncwarp();
+        for (int base = begin; base < end; base += 32) {
+            int idx = base + lane;
+            if (idx < end) atomicAdd(&sh[w][(__ldcg(&src[idx]) >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        {
+            const int d = threadIdx.x;
+            unsigned int run = 0;
+#pragma unroll
+            for (int k = 0; k < RC_WARPS; ++k) { unsigned int t = sh[k][d]; sh[k][d] = run; run += t; }
+            hist[(size_t)d * nCta + cta] = run;
+        }
+        coopBarrier(barrier, target);
+        // phase 2: exclusive scan of every digit's column over the CTAs, digit totals
+        for (int d = cta; d < 256; d += nCta) {
+            unsigned int carry = 0;
+            for (int base = 0; base < nCta; base += RC_THREADS) {
+                int j = base + threadIdx.x;
+                int v = j < nCta ? (int)__ldcg(&hist[(size_t)d * nCta + j]) : 0;
+                int total;
+                int inc = blockInclusiveScan(v, &total);
+                if (j < nCta) hist[(size_t)d * nCta + j] = carry + (unsigned int)(inc - v);
+                carry += (unsigned int)total;
+            }
+            if (threadIdx.x == 0) totals[d] = carry;
+        }
+        coopBarrier(barrier, target);
+        // phase 3: first output slot of (digit, this CTA, warp), then the stable scatter
+        {
+            const int d = threadIdx.x;
+            int tot = (int)__ldcg(&totals[d]);
+            int inc = blockInclusiveScan(tot, nullptr);
+            unsigned int base = (unsigned int)(inc - tot) + __ldcg(&hist[(size_t)d * nCta + cta]);
+#pragma unroll
+            for (int k = 0; k < RC_WARPS; ++k) sh[k][d] += base;
+        }
+        __syncthreads();
+        for (int base = begin; base < end; base += 32) {
+            int idx = base + lane;
+            bool valid = idx < end;
+            unsigned int active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                unsigned int k = __ldcg(&src[idx]);
+                int v = __ldcg(&srcV[idx]);
+                unsigned int d = (k >> shift) & 255u;
+                unsigned int peers = __match_any_sync(active, d);
+                unsigned int rank = __popc(peers & ltMask);
+                unsigned int b = sh[w][d];
+                __syncwarp(active);
+                if (rank == 0) sh[w][d] = b + __popc(peers);
+                __syncwarp(active);
+                dst[b + rank] = k;
+                dstV[b + rank] = v;
+            }
+        }
+        coopBarrier(barrier, target);
+        unsigned int* tk = src; src = dst; dst = tk;
+        int* tv = srcV; srcV = dstV; dstV = tv;
+    }
+}
+
 // Sort (keysA, valsA) by the low `bits` bits of the key, 8 bits per pass, ping-ponging with (keysB, valsB).
 // hist must hold 256 * ceil(n/512) (+ scan scratch of ceil(that/4096)+1) uints.
 int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,
@@ -268,6 +364,27 @@ int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned i
         ++ctx->launches, k_sort_small<<<1, SORT_SMALL_THREADS, smemBytes, ctx->stream>>>(keysA, valsA, n, bits);    // sorted in place: result in A
         PB_CUDA(ctx, cudaGetLastError());
         return PB_OK;
+    }
+    if (ctx->sortCoopMode) {
+        if (!ctx->sortCoopGrid) {
+            int occ = 0;
+            PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_radix_sort_coop, RC_THREADS, 0));
+            if (occ > 4) occ = 4;
+            ctx->sortCoopGrid = occ * ctx->numSMs;
+            if (ctx->sortCoopGrid > 0) { int rc = pb_alloc(ctx, &ctx->sortBarrier, 64); if (rc) return rc; }
+        }
+        int nCta = (n + 1535) / 1536;
+        if (nCta > ctx->sortCoopGrid) nCta = ctx->sortCoopGrid;
+        if (nCta >= 1 && nCta + 2 <= histCapTiles) {
+            int chunk = (((n + nCta - 1) / nCta) + RC_THREADS - 1) / RC_THREADS * RC_THREADS;
+            int passes = (bits + 7) / 8;
+            PB_CUDA(ctx, cudaMemsetAsync(ctx->sortBarrier, 0, sizeof(unsigned int), ctx->stream));
+            void* args[] = { &keysA, &valsA, &keysB, &valsB, &n, &bits, &chunk, &hist, &ctx->sortBarrier };
+            ++ctx->launches;
+            PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_radix_sort_coop, dim3(nCta), dim3(RC_THREADS), args, 0, ctx->stream));
+            *resultInA = (passes & 1) == 0;
+            return PB_OK;
+        }
     }
     int items = 16;
     if ((n + 127) / 128 <= histCapTiles && n <= (1 << 19)) items = 4;

@@ -108,3 +108,29 @@ def test_three_gates_big_static_list(maker, steps, big, monkeypatch):
     monkeypatch.setenv("PB_BIG_LIST", str(big))
     s = parity.run_gates(maker(), steps=steps)
     assert s["steps"] == steps and s["manifolds"] > 0
+
+
+@pytest.mark.parametrize("coop", [0, 1])
+@pytest.mark.parametrize("n,bits", [(5000, 30), (8193, 30), (100_000, 30), (1_000_003, 30), (2_000_000, 16), (300_000, 8), (50_001, 32), (20_000, 20)])
+def test_device_sort(n, bits, coop, monkeypatch):
+    """The key / payload sort behind the broadphase (Morton order): one-CTA sort up to 8192 keys, above that one cooperative launch
+    (coop=1, the default) or three launches per pass (coop=0).  Must equal a stable sort by the low `bits` bits, rounded up to whole 8-bit passes."""
+    import ctypes as C
+    from physecs_b200.capi import Context
+    monkeypatch.setenv("PB_SORT_COOP", str(coop))
+    ctx = Context(S.pyramid(10))
+    rng = np.random.default_rng(n + bits)
+    keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if bits == 16:
+        keys &= np.uint32(0x3FFF)          # many duplicates: stability is visible in the payload order
+    vals = np.arange(n, dtype=np.int32)
+    ko, vo = np.empty_like(keys), np.empty_like(vals)
+    rc = ctx.lib.pb_debug_sort_pairs(ctx.ctx, n, bits, keys.ctypes.data_as(C.POINTER(C.c_uint)), vals.ctypes.data_as(C.POINTER(C.c_int)),
+                                     ko.ctypes.data_as(C.POINTER(C.c_uint)), vo.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0, ctx.lib.pb_last_error(ctx.ctx).decode()
+    sorted_bits = (bits + 7) // 8 * 8          # whole 8-bit passes
+    mask = np.uint32((1 << sorted_bits) - 1) if sorted_bits < 32 else np.uint32(0xFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(vo, order.astype(np.int32))
+    assert np.array_equal(ko, keys[order])
+    ctx.close()
