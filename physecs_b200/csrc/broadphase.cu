@@ -175,7 +175,8 @@ __device__ __forceinline__ unsigned int expandBits(unsigned int v) {
 // PB_BIG_MAX of them go on a side list that every querying collider tests directly; in the tree their leaf box is empty.  Which
 // colliders are listed does not change the pair set.
 __global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const int* __restrict__ sb,
-                         unsigned int* __restrict__ keys, int* __restrict__ ids, int* __restrict__ colFlags, int* __restrict__ bigList) {
+                         unsigned int* __restrict__ keys, int* __restrict__ ids, int* __restrict__ colFlags, int* __restrict__ bigList,
+                         const int* __restrict__ colRow, const int* __restrict__ rowEntity, int4* __restrict__ colInfo) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 lo = mk3(orderedToFloat(sb[0]), orderedToFloat(sb[1]), orderedToFloat(sb[2]));
@@ -193,6 +194,10 @@ __global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4
             }
         }
         if (f != old) colFlags[i] = f;
+        // everything the pair walk needs to know about a collider in ONE 16-byte word (flags, body row, entity): the walk's leaf test
+        // was three dependent loads (flags -> row -> entity of the row)
+        const int row = colRow[i];
+        colInfo[i] = make_int4(f, row, rowEntity[row], 0);
     }
     float sx = ext.x > 0.f ? 1024.f / ext.x : 0.f, sy = ext.y > 0.f ? 1024.f / ext.y : 0.f, sz = ext.z > 0.f ? 1024.f / ext.z : 0.f;
     unsigned int x = (unsigned int)fminf(fmaxf((c.x - lo.x) * sx, 0.f), 1023.f);
@@ -323,6 +328,19 @@ __device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ c
     }
 }
 
+// emitPair with the entity ids already at hand (k_lbvh_pairs reads them from colInfo)
+__device__ __forceinline__ void emitPairEnt(int a, int b, unsigned int ea, unsigned int eb, int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
+    const unsigned int m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[CNT_PAIRS], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    int slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot < maxPairs) pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
+    else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+}
+
 // One WARP per 32 consecutive sorted leaves, walking the tree as a packet: the warp keeps one stack (shared memory), pops one
 // node at a time, every lane tests its own box against the two child boxes, and a child is descended when ANY lane overlaps it.
 // Morton-sorted neighbours take nearly the same path, so the union of the 32 paths is a small multiple of one path, while every
@@ -331,20 +349,22 @@ __device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ c
 // Only colliders of non-kinematic dynamic bodies issue queries (a pair needs one, Physecs.cpp:147), which keeps huge static
 // boxes / terrain from walking the whole tree; the other lanes carry an empty box.
 #define PAIRS_WARPS 4
-__global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const int* __restrict__ leafId, const int* __restrict__ colFlags, const int* __restrict__ colRow,
-                             const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+__global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const int* __restrict__ leafId, const int4* __restrict__ colInfo,
+                             const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
                              const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax,
                              int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs, const int* __restrict__ bigList) {
     __shared__ int sstack[PAIRS_WARPS][64];
     const unsigned FULL = 0xffffffffu;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int a = -1, rowA = -1;
+    unsigned int entA = 0;
     bool active = false;
     V3 amn = mk3(FLT_MAX), amx = mk3(-FLT_MAX);     // empty box: overlaps nothing
     if (i < n) {
         a = leafId[i];
-        active = (colFlags[a] & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
-        if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = colRow[a]; }
+        const int4 ia = colInfo[a];
+        active = (ia.x & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
+        if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = ia.y; entA = (unsigned int)ia.z; }
     }
     if (!__any_sync(FULL, active)) return;
     if (bigList) {
@@ -352,7 +372,8 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
         const int nb = min(bigList[0], PB_BIG_MAX);
         for (int k = 0; k < nb; ++k) {
             const int b = bigList[1 + k];
-            if (active && colRow[b] != rowA && overlaps(amn, amx, aabbMin[b], aabbMax[b])) emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
+            const int4 ib = colInfo[b];
+            if (active && ib.y != rowA && overlaps(amn, amx, aabbMin[b], aabbMax[b])) emitPairEnt(a, b, entA, (unsigned int)ib.z, pairs, counters, maxPairs);
         }
     }
     int* st = sstack[threadIdx.x >> 5];
@@ -384,12 +405,12 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
             if (!(side ? orr : ol)) continue;
             int b = ~c;
             if (b == a) continue;
-            int fb = colFlags[b];
-            if (!(fb & COLF_ENABLE)) continue;
+            const int4 ib = colInfo[b];
+            if (!(ib.x & COLF_ENABLE)) continue;
             // a leaf child sits at position llast (left) / llast + 1 (right): dynamic-dynamic pairs are emitted by the earlier one
-            if ((fb & COLF_DYNAMIC) && (side ? llast + 1 : llast) < i) continue;
-            if (colRow[b] == rowA) continue;                // same entity (Physecs.cpp:145)
-            emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
+            if ((ib.x & COLF_DYNAMIC) && (side ? llast + 1 : llast) < i) continue;
+            if (ib.y == rowA) continue;                     // same entity (Physecs.cpp:145)
+            emitPairEnt(a, b, entA, (unsigned int)ib.z, pairs, counters, maxPairs);
         }
         __syncwarp();
     }
@@ -448,7 +469,8 @@ int pb_build_tree(pb_ctx* ctx, bool forStep) {
     ++ctx->launches, k_scene_bounds_init<<<1, 32, 0, ctx->stream>>>(sb, bigList);
     int blocks = pb_grid(n, 256); if (blocks > ctx->numSMs * 8) blocks = ctx->numSMs * 8;
     ++ctx->launches, k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
-    ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA, ctx->colFlags, bigList);
+    ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA, ctx->colFlags, bigList,
+                                                                       ctx->colRow, ctx->rowEntity, ctx->colInfo);
     bool inA = true;
     int rc = pb_radix_sort_pairs(ctx, ctx->mortonA, ctx->leafIdA, ctx->mortonB, ctx->leafIdB, n, 30, ctx->radixHist, ctx->radixTiles, &inA);
     if (rc) return rc;
@@ -480,7 +502,7 @@ int pb_broadphase(pb_ctx* ctx) {
     int rc = pb_build_tree(ctx, true);
     if (rc) return rc;
     const int* ids = ctx->treeLeafIds;
-    ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
+    ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colInfo, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs,
                                                             ctx->bigListMode ? ctx->bigList : nullptr);
     PB_CUDA(ctx, cudaGetLastError());

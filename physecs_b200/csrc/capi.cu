@@ -203,7 +203,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     }
     A(comInvMass, R); A(invIL, 3 * R); A(kinematic, R); A(pseudoLin, R); A(pseudoAng, R); A(colorMask, R); A(rowMark, R);
     // + 1: slot nCol holds the query shape of pb_query_overlap_mtd while the bin kernels run on it
-    A(colRow, C); A(colIndex, C); A(colType, C + 1); A(colFlags, C); A(colData, C); A(colMesh, C + 1);
+    A(colRow, C); A(colIndex, C); A(colType, C + 1); A(colFlags, C); A(colInfo, C + 1); A(colData, C); A(colMesh, C + 1);
     A(colLPos, C); A(colLQuat, C); A(colParams, C + 1); A(colMat, C); A(colWPos, C + 1); A(colWQuat, C + 1); A(aabbMin, C); A(aabbMax, C);
     A(mortonA, C); A(mortonB, C); A(leafIdA, C); A(leafIdB, C);
     size_t sortMax = std::max(C, M);
@@ -303,7 +303,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
-    F(colRow); F(colIndex); F(colType); F(colFlags); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
+    F(colRow); F(colIndex); F(colType); F(colFlags); F(colInfo); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
     F(mKey); F(mNormal); F(mPts); F(mSortTmp); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);

@@ -15,6 +15,8 @@
 #include "np_gjk.cuh"
 #include "np_mesh_heavy.cuh"
 #include "np_overlap.cuh"
+#include <mutex>
+#include <unordered_map>
 
 #define COLF_TRIGGER 1
 #define COLF_ENABLE 2
@@ -616,8 +618,19 @@ __global__ void k_query_classify(const int2* __restrict__ pairs, int* __restrict
 template <typename K>
 static int npGrid(pb_ctx* ctx, K kernel, int threads, bool heavy = false) {
     if (ctx->npWaves <= 0) return ctx->numSMs * 8;
+    // occupancy per kernel, asked once per process (every device of a box is the same part)
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find((const void*)kernel);
+        if (it != cache.end()) occ = it->second;
+        else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+            cache[(const void*)kernel] = occ;
+        }
+    }
     int grid = ctx->numSMs * occ * ctx->npWaves * (heavy ? 2 : 1);
     if (ctx->pairsHint >= 0) {            // a bin holds at most every pair: no point in launching CTAs far beyond that on small scenes
         long long need = (2LL * ctx->pairsHint + 4096) / threads + ctx->numSMs;

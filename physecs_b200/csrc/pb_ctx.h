@@ -125,6 +125,7 @@ struct pb_ctx {
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
     int meshLightMode = 1;              // sphere / capsule vs mesh bins: 0 = k_np_mesh, 1 = k_np_mesh_light (dual-child cull walk + packed
                                         // triangle records) (env PB_MESH_LIGHT)
+    int4* colInfo = nullptr;            // [colliders] (flags, body row, entity, 0) per collider, rewritten by k_morton for the pair walk
     int* bigList = nullptr;             // [1 + 32] count + colliders of the step's big-static side list (broadphase.cu k_morton)
     int bigListMode = 1;                // 0: every collider stays in the step's tree (env PB_BIG_LIST)
     int pairsHint = -1;                 // candidate pairs of the previous step (-1: none yet): bounds the bin kernels' grids on small scenes
