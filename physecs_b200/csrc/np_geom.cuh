@@ -271,17 +271,24 @@ __device__ inline float sqrDistPointTriangle(V3 p, V3 a, V3 b, V3 c, V3& q, int&
     return distance2(p, q);
 }
 
+// Same cases, same expressions as the reference's early-return form, evaluated without branches: the four exits (degenerate,
+// s <= 0, s >= 1, interior) differ only in which (q, t) feeds the common tail, and lanes of a warp land in all four.
 __device__ inline float sqrDistLineSegment(V3 p, V3 dir, V3 a, V3 b, float& t, V3& q, int& vflag) {
     V3 ab = b - a;
     float v1v2 = dot(dir, ab), v2v2 = dot(ab, ab);
     V3 r = p - a;
     float rv1 = dot(r, dir), rv2 = dot(r, ab);
     float denom = (v1v2 * v1v2 - v2v2);
-    if (fabsf(denom) <= 1e-6f) { q = a; t = -rv1; vflag = 0; V3 d = p + t * dir - a; return dot(d, d); }
-    float s = (rv1 * v1v2 - rv2) / denom;
-    if (s <= 0.f) { q = a; t = -rv1; vflag = 1; V3 d = p + t * dir - a; return dot(d, d); }
-    if (s >= 1.f) { q = b; t = -dot(p - b, dir); vflag = 2; V3 d = p + t * dir - b; return dot(d, d); }
-    q = a + s * ab; t = s * v1v2 - rv1; vflag = 0;
+    const bool degenerate = fabsf(denom) <= 1e-6f;
+    float s = (rv1 * v1v2 - rv2) / denom;          // unused (and possibly inf / nan) when degenerate
+    const bool atA = degenerate || s <= 0.f;
+    const bool atB = !atA && s >= 1.f;
+    float tB = -dot(p - b, dir);
+    float tI = s * v1v2 - rv1;
+    V3 qI = a + s * ab;
+    t = atA ? -rv1 : (atB ? tB : tI);
+    q.x = atA ? a.x : (atB ? b.x : qI.x); q.y = atA ? a.y : (atB ? b.y : qI.y); q.z = atA ? a.z : (atB ? b.z : qI.z);
+    vflag = degenerate ? 0 : (atA ? 1 : (atB ? 2 : 0));
     V3 d = p + t * dir - q;
     return dot(d, d);
 }
@@ -305,13 +312,19 @@ __device__ inline float sqrDistLineTriangle(V3 p, V3 dir, V3 a, V3 b, V3 c, floa
             return 0.f;
         }
     }
-    float t1; V3 q1; int vf, vf1;
+    // edges (a,b) -> fidx 2, (b,c) -> 0, (c,a) -> 1, the later one wins only when strictly closer; one copy of the routine, the
+    // vertices rotate through registers
+    int vf = 0;
+    float dist = 0.f;
     fidx = 2;
-    float dist = sqrDistLineSegment(p, dir, a, b, t, q, vf);
-    float dist1 = sqrDistLineSegment(p, dir, b, c, t1, q1, vf1);
-    if (dist1 < dist) { fidx = 0; t = t1; q = q1; vf = vf1; dist = dist1; }
-    dist1 = sqrDistLineSegment(p, dir, c, a, t1, q1, vf1);
-    if (dist1 < dist) { fidx = 1; t = t1; q = q1; vf = vf1; dist = dist1; }
+    V3 x = a, y = b, z = c;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        float t1; V3 q1; int vf1;
+        float dist1 = sqrDistLineSegment(p, dir, x, y, t1, q1, vf1);
+        if (k == 0 || dist1 < dist) { fidx = (k + 2) % 3; t = t1; q = q1; vf = vf1; dist = dist1; }
+        V3 w = x; x = y; y = z; z = w;
+    }
     if (vf) { feature = TF_VERTEX; fidx = (fidx + vf) % 3; }
     else feature = TF_EDGE;
     return dist;
@@ -319,8 +332,10 @@ __device__ inline float sqrDistLineTriangle(V3 p, V3 dir, V3 a, V3 b, V3 c, floa
 
 __device__ inline float sqrDistSegmentTriangle(V3 p, V3 dir, float mn, float mx, V3 a, V3 b, V3 c, float& t, V3& q, int& feature, int& fidx) {
     float sq = sqrDistLineTriangle(p, dir, a, b, c, t, q, feature, fidx);
-    if (t < mn) { t = mn; sq = sqrDistPointTriangle(p + dir * t, a, b, c, q, feature, fidx); }
-    else if (t > mx) { t = mx; sq = sqrDistPointTriangle(p + dir * t, a, b, c, q, feature, fidx); }
+    if (t < mn || t > mx) {          // one copy of the point routine for both ends
+        t = t < mn ? mn : mx;
+        sq = sqrDistPointTriangle(p + dir * t, a, b, c, q, feature, fidx);
+    }
     return sq;
 }
 
