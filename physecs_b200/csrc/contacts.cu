@@ -4,7 +4,8 @@
 //                    The reference solves contacts strictly sequentially (src/Physecs.cpp:484-486); within one
 //                    colour no two manifolds share a dynamic body, so a parallel colour == a sequential sub-sweep
 //                    and the whole step equals the reference fed the (colour, slot) order (north_star gate 3).
-//   radix pass       manifolds grouped by colour (stable), exclusive scan of point counts -> point offsets
+//   k_scatter_by_key manifolds placed in solve order (counting sort over the run table of (group, colour, single | multi) keys),
+//                    exclusive scan of point counts -> point offsets
 //   k_contact_build  material mix, body indices, body-local arms, restitution target with the previous step's
 //                    contact cache (src/Physecs.cpp:215-315; cache semantics :237, :291-300, :313)
 #include "pb_ctx.h"
@@ -19,7 +20,7 @@ __device__ __forceinline__ int solverIndex(int row, int nDyn, const int* __restr
 
 __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counters, int maxManifolds, const int* __restrict__ colRow,
                         int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMask,
-                        unsigned int* __restrict__ sortKey, int* __restrict__ sortVal) {
+                        unsigned int* __restrict__ sortKey) {
     __shared__ int hist[2 * PB_MAX_COLORS];     // [colour] all manifolds, [PB_MAX_COLORS + colour] the single-point ones
     if (threadIdx.x < 2 * PB_MAX_COLORS) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -58,7 +59,6 @@ __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counter
             color = 2u * color + (key.w > 1 ? 1u : 0u);
         }
         sortKey[i] = color;
-        sortVal[i] = i;
     }
     __syncthreads();
     if (threadIdx.x < PB_MAX_COLORS && hist[threadIdx.x]) atomicAdd(&counters[CNT_COLORSTART + threadIdx.x], hist[threadIdx.x]);
@@ -298,13 +298,13 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
     ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
-                                             ctx->mSortKeyA, ctx->mSortTmp);
+                                             ctx->mSortKeyA);
     ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->keyStart + (size_t)G * PB_KEY_COLORS);
     if (ctx->islandsOn) {
         if ((rc = pb_islands_build(ctx))) return rc;
         if ((rc = pb_joint_lists(ctx))) return rc;
     }
-    // group by colour: one stable 8-bit radix pass over the raw arena (nRaw was read back after the narrowphase)
+    // nRaw was read back after the narrowphase
     int n = nRaw;
     if (n <= 0) {
         // no manifolds this step: the contact cache of this step must still read as empty for the next one

@@ -147,7 +147,7 @@ struct pb_ctx {
     int* mColor = nullptr;           // colour per raw manifold
     int* gjkHitPair = nullptr; float4* gjkHitSimplex = nullptr; int gjkHitCap = 0;   // intersecting GJK-bin pairs + their simplices (9 float4 each)
     int* mSorted = nullptr;          // [maxManifolds] raw index per solve slot
-    int* mSortTmp = nullptr; unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
+    unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
 
     // ---- contact constraints (solve order) ---------------------------------------------------------------
     int4* cHead = nullptr;           // packed solve header: b0, b1, first point, numPoints | isSoft << 8 (one 16-byte load)
