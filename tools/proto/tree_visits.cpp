@@ -105,6 +105,36 @@ static Tree implicitTree() {      // median split by index over the sorted leave
     return t;
 }
 
+// K > 0: a subtree of at most K leaves is not walked but tested leaf by leaf against the whole packet (one event of `size` leaves)
+static void walkBrute(const Tree& t, int P, int K, const std::vector<int>& first, const char* name) {
+    long long visits = 0, events = 0, tested = 0;
+    int packets = 0;
+    std::vector<int> st;
+    auto sizeOf = [&](int node) { return std::max(t.lastL[node], t.lastR[node]) - first[node] + 1; };
+    for (int base = 0; base < n; base += P, ++packets) {
+        int cnt = std::min(P, n - base);
+        st.clear(); st.push_back(t.root);
+        while (!st.empty()) {
+            int node = st.back(); st.pop_back();
+            if (sizeOf(node) <= K) { ++events; tested += sizeOf(node); continue; }
+            ++visits;
+            bool anyL = false, anyR = false;
+            for (int q = 0; q < cnt; ++q) {
+                int i = base + q;
+                anyL |= t.lastL[node] > i && ov(leaf[i], t.boxL[node]);
+                anyR |= t.lastR[node] > i && ov(leaf[i], t.boxR[node]);
+            }
+            if (anyL && t.left[node] >= 0) st.push_back(t.left[node]);
+            if (anyR && t.right[node] >= 0) st.push_back(t.right[node]);
+        }
+    }
+    // instruction model from the SASS of k_lbvh_pairs: ~96 per node visit (x1.3 with two boxes per lane), ~30 + 28 per leaf for a direct test
+    double perVisit = P == 64 ? 96 * 1.3 : 96, perLeaf = P == 64 ? 28 * 1.6 : 28;
+    double instr = visits * perVisit + events * 30.0 + tested * perLeaf;
+    printf("%-8s %2d/packet, direct below %2d leaves: %7.1f visits + %5.1f direct events (%6.1f leaves) per packet -> ~%.0f instructions per leaf\n", name, P, K,
+           (double)visits / packets, (double)events / packets, (double)tested / packets, instr / n);
+}
+
 static void walk(const Tree& t, int P, const char* name) {
     long long visits = 0, pairs = 0, maxVisits = 0;
     int packets = 0;
@@ -161,6 +191,15 @@ int main(int argc, char** argv) {
     printf("%d leaves\n", n);
     Tree tk = karras();
     walk(tk, 32, "karras"); walk(tk, 64, "karras");
+    {
+        // first sorted position under every node (lastL / lastR hold the last ones)
+        std::vector<int> first(tk.left.size());
+        std::vector<int> order2; order2.reserve(tk.left.size());
+        std::vector<int> stck{ tk.root };
+        while (!stck.empty()) { int nd = stck.back(); stck.pop_back(); order2.push_back(nd); if (tk.left[nd] >= 0) stck.push_back(tk.left[nd]); if (tk.right[nd] >= 0) stck.push_back(tk.right[nd]); }
+        for (int k = (int)order2.size() - 1; k >= 0; --k) { int nd = order2[k]; first[nd] = tk.left[nd] < 0 ? ~tk.left[nd] : first[tk.left[nd]]; }
+        for (int P : { 32, 64 }) for (int K : { 0, 4, 8, 16, 32 }) walkBrute(tk, P, K, first, "karras");
+    }
     Tree ti = implicitTree();
     walk(ti, 32, "implicit"); walk(ti, 64, "implicit");
     return 0;
