@@ -849,10 +849,11 @@ void Scene::simulate(float timeStep) {
     const double gatherMs = msSince(tGather);
 
     // ---- device step ---------------------------------------------------------------------------------------------------------------
-    if (full || !S.touched.empty()) {
+    // static poses first: pb_set_static_poses runs on the main stream and waits for any pending pb_set_state upload, so issued after
+    // it the dynamic state's H2D (copy stream, meant to hide behind the broadphase) would be serialised in front of the step
+    if (full) S.check(pb_set_static_poses(S.ctx, nStatic, S.hSPos.p, S.hSQuat.p), "pb_set_static_poses");
+    if (full || !S.touched.empty())
         S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
-        if (full) S.check(pb_set_static_poses(S.ctx, nStatic, S.hSPos.p, S.hSQuat.p), "pb_set_static_poses");
-    }
     S.touched.clear();
     int rc = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
     for (int attempt = 0; rc == PB_ECAPACITY && attempt < 4; ++attempt) {
