@@ -27,7 +27,10 @@ typedef struct pb_ctx pb_ctx;
 enum {
     PB_OK = 0,
     PB_ECUDA = 1,        /* CUDA runtime error (message in pb_last_error) */
-    PB_ECAPACITY = 2,    /* a per-step arena overflowed (pairs / manifolds / triangle contacts); results of the step are invalid */
+    PB_ECAPACITY = 2,    /* a per-step ARENA overflowed (candidate pairs / manifolds / trigger pairs): nothing persistent was touched, grow
+                            (pb_grow_arenas) and run the step again.  Per-pair work (EPA polytope, clip polygons, triangles met by one
+                            shape) is unbounded like the reference's std::vectors: pairs that outgrow the per-thread buffers are redone
+                            by spill kernels on global-memory scratch and never fail a step (pb_counts.cause tells when that happened) */
     PB_EINVAL = 3,       /* bad argument */
     PB_EUNSUPPORTED = 4  /* a shape pair the reference itself has no routine for (mesh vs mesh) reached the narrowphase */
 };
@@ -49,6 +52,16 @@ typedef struct pb_caps {
     int reserved[3];
 } pb_caps;
 
+/* pb_counts.cause bits: which limit the last step (or query) ran into.  PAIRS / MANIFOLDS / TRIGGERS come with PB_ECAPACITY; the
+ * SPILLED_* bits are informational (those pairs took the spill path, results are complete); SPILL_LIST / SPILL_SCRATCH mean even the
+ * spill path's (much larger) bounds were exceeded: the step completed, the affected pairs carry the contacts that fit. */
+enum {
+    PB_CAUSE_PAIRS = 0x1, PB_CAUSE_MANIFOLDS = 0x2, PB_CAUSE_TRIGGERS = 0x4, PB_CAUSE_WALK_STACK = 0x8,
+    PB_CAUSE_SPILLED_EPA_FACES = 0x10, PB_CAUSE_SPILLED_EPA_LOOSE = 0x20, PB_CAUSE_SPILLED_EPA_VERTS = 0x40, PB_CAUSE_SPILLED_CLIP = 0x80,
+    PB_CAUSE_SPILLED_TRI_CAND = 0x100, PB_CAUSE_SPILLED_TRI_CONTACTS = 0x200, PB_CAUSE_SPILLED_MESH_STACK = 0x400,
+    PB_CAUSE_SPILL_LIST = 0x1000, PB_CAUSE_SPILL_SCRATCH = 0x2000
+};
+
 /* per-step counters (pb_get_counts) */
 typedef struct pb_counts {
     int n_pairs;         /* broadphase candidate pairs (== reference potentialContacts.size()) */
@@ -59,6 +72,8 @@ typedef struct pb_counts {
     int status;          /* PB_OK or PB_ECAPACITY */
     int n_mesh_pairs;
     int n_triggers;      /* overlapping trigger pairs (== triggerCacheTemp.size()) */
+    int cause;           /* PB_CAUSE_* bits of the last step */
+    int n_spilled;       /* pairs the spill kernels redid in the last step (GJK / EPA bin + mesh bins) */
 } pb_counts;
 
 /* device times of the last pb_step in milliseconds (CUDA events on the context's stream) */
@@ -154,8 +169,15 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
 /* recompute bounds (+0.01 margin) of every collider of a non-kinematic dynamic body, as the end of
  * simulate does (Physecs.cpp:556-559); used after pb_set_state when the caller wants bounds to follow */
 int pb_refresh_bounds(pb_ctx* ctx);
-/* == physecs::Scene::simulate(timeStep) with the scene's knobs (Physecs.cpp:100-110, :112-561) */
+/* == physecs::Scene::simulate(timeStep) with the scene's knobs (Physecs.cpp:100-110, :112-561).
+ * pb_step ENQUEUES the step on the context's stream and returns without waiting for the device.  The arena checks run on the device:
+ * a step whose pair / manifold arena overflowed skips its solve, integration and bounds refresh, i.e. leaves the scene exactly as
+ * it was.  The outcome is reported by the next call that synchronises with the step -- pb_collect_step, pb_sync, pb_get_state,
+ * pb_get_counts, the taps, or the next pb_step (which then enqueues nothing) -- as PB_ECAPACITY: grow the arenas (pb_grow_arenas)
+ * and call pb_step again.  A caller that wants the status of a step before doing anything else calls pb_collect_step. */
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
+/* waits for the narrowphase of the last pb_step (not for the whole step) and returns its status; PB_OK when nothing is pending */
+int pb_collect_step(pb_ctx* ctx);
 int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3);
 int pb_sync(pb_ctx* ctx);
 

@@ -17,6 +17,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PHYSECS_B200_LIB") or os.path.join(_HERE, "lib", "libphysecs_b200.so")
 
 PB_OK, PB_ECUDA, PB_ECAPACITY, PB_EINVAL, PB_EUNSUPPORTED = 0, 1, 2, 3, 4
+# pb_counts.cause bits (include/physecs_b200.h)
+PB_CAUSE_PAIRS, PB_CAUSE_MANIFOLDS, PB_CAUSE_TRIGGERS, PB_CAUSE_WALK_STACK = 0x1, 0x2, 0x4, 0x8
+PB_CAUSE_SPILLED_EPA_FACES, PB_CAUSE_SPILLED_EPA_LOOSE, PB_CAUSE_SPILLED_EPA_VERTS, PB_CAUSE_SPILLED_CLIP = 0x10, 0x20, 0x40, 0x80
+PB_CAUSE_SPILLED_TRI_CAND, PB_CAUSE_SPILLED_TRI_CONTACTS, PB_CAUSE_SPILLED_MESH_STACK = 0x100, 0x200, 0x400
+PB_CAUSE_SPILL_LIST, PB_CAUSE_SPILL_SCRATCH = 0x1000, 0x2000
 
 EXPORTS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_host_alloc", "pb_host_free", "pb_stream",
@@ -37,7 +42,7 @@ class Caps(C.Structure):
 
 class Counts(C.Structure):
     _fields_ = [("n_pairs", C.c_int), ("n_manifolds", C.c_int), ("n_points", C.c_int), ("n_colors", C.c_int), ("n_overflow", C.c_int),
-                ("status", C.c_int), ("n_mesh_pairs", C.c_int), ("n_triggers", C.c_int)]
+                ("status", C.c_int), ("n_mesh_pairs", C.c_int), ("n_triggers", C.c_int), ("cause", C.c_int), ("n_spilled", C.c_int)]
 
 
 class Timings(C.Structure):

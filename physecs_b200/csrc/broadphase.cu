@@ -28,9 +28,11 @@ __global__ void k_update_bounds(int n, int mode, const int* __restrict__ rowMark
                                 const int* __restrict__ colRow, const int* __restrict__ colType, const int* __restrict__ colFlags,
                                 const int* __restrict__ colMesh, const float4* __restrict__ colLPos, const float4* __restrict__ colLQuat,
                                 const float4* __restrict__ colParams, const float4* __restrict__ pos, const float4* __restrict__ quat,
-                                const PbConvexDev* __restrict__ convexes, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax) {
+                                const PbConvexDev* __restrict__ convexes, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax,
+                                const int* __restrict__ skipStatus) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (skipStatus && (*skipStatus & (PB_ECAPACITY | 0x100))) return;      // end-of-step refresh of a step whose solve was skipped (capi.cu collectStep)
     int type = colType[i];
     if (type == PB_TRIANGLE_MESH) return;  // separate reduction kernel
     int flags = colFlags[i];
@@ -74,31 +76,38 @@ __global__ void k_trimesh_bounds_init(int* acc) {
     if (threadIdx.x < 3) acc[threadIdx.x] = floatToOrdered(FLT_MAX);
     else if (threadIdx.x < 6) acc[threadIdx.x] = floatToOrdered(-FLT_MAX);
 }
-__global__ void k_trimesh_bounds_store(int col, float margin, const int* __restrict__ acc, float4* aabbMin, float4* aabbMax) {
+__global__ void k_trimesh_bounds_store(int col, float margin, const int* __restrict__ acc, float4* aabbMin, float4* aabbMax, const int* __restrict__ skipStatus) {
+    if (skipStatus && (*skipStatus & (PB_ECAPACITY | 0x100))) return;
     V3 mn = mk3(orderedToFloat(acc[0]), orderedToFloat(acc[1]), orderedToFloat(acc[2]));
     V3 mx = mk3(orderedToFloat(acc[3]), orderedToFloat(acc[4]), orderedToFloat(acc[5]));
     mx = mx + mk3(margin); mn = mn - mk3(margin);
     aabbMin[col] = f4(mn); aabbMax[col] = f4(mx);
 }
 
-static int launchTrimeshBounds(pb_ctx* ctx, int col, float margin) {
+static int launchTrimeshBounds(pb_ctx* ctx, int col, float margin, const int* skipStatus = nullptr) {
     int mesh = ctx->hColMesh[col];
     const PbTriMesh& tm = ctx->triMeshes[mesh];
     int* acc = (int*)ctx->sceneBounds + 8;
     ++ctx->launches, k_trimesh_bounds_init<<<1, 32, 0, ctx->stream>>>(acc);
     int blocks = pb_grid(tm.nVerts, 256); if (blocks > 1024) blocks = 1024;
     ++ctx->launches, k_trimesh_bounds<<<blocks, 256, 0, ctx->stream>>>(col, ctx->colRow, ctx->colLPos, ctx->colLQuat, ctx->pos, ctx->quat, tm.verts, tm.nVerts, acc);
-    ++ctx->launches, k_trimesh_bounds_store<<<1, 1, 0, ctx->stream>>>(col, margin, acc, ctx->aabbMin, ctx->aabbMax);
+    ++ctx->launches, k_trimesh_bounds_store<<<1, 1, 0, ctx->stream>>>(col, margin, acc, ctx->aabbMin, ctx->aabbMax, skipStatus);
     return PB_OK;
 }
 
-int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic) {
+// onlyDynamic: the colliders of non-kinematic dynamic bodies (updateBounds(entity) for every moving body, Physecs.cpp:556-559) --
+// triangle-mesh colliders riding on such a body included (one vertex reduction each; found through the host mirrors).
+// skipStatus: device status word of the step this refresh ends (nullptr outside pb_step).
+int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic, const int* skipStatus) {
     if (ctx->nCol == 0) return PB_OK;
     ++ctx->launches, k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, onlyDynamic ? 1 : 0, nullptr, margin, ctx->colRow, ctx->colType,
-        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
-    if (!onlyDynamic) {
-        auto& types = ctx->hColType;
-        for (int c = 0; c < ctx->nCol; ++c) if (types[c] == PB_TRIANGLE_MESH) launchTrimeshBounds(ctx, c, margin);
+        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax, skipStatus);
+    {
+        for (int c : ctx->hTrimeshCols) {
+            const int row = ctx->hColRow[c];
+            const bool moving = row < ctx->nDyn && row < (int)ctx->hKinematic.size() && !ctx->hKinematic[row];
+            if (!onlyDynamic || moving) launchTrimeshBounds(ctx, c, margin, skipStatus);
+        }
     }
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
@@ -108,7 +117,7 @@ int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic) {
 int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin) {
     if (ctx->nCol == 0) return PB_OK;
     ++ctx->launches, k_update_bounds<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, 2, dRowMark, margin, ctx->colRow, ctx->colType,
-        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax);
+        ctx->colFlags, ctx->colMesh, ctx->colLPos, ctx->colLQuat, ctx->colParams, ctx->pos, ctx->quat, ctx->convexDev, ctx->aabbMin, ctx->aabbMax, nullptr);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -324,7 +333,7 @@ __device__ __forceinline__ void emitPair(int a, int b, const int* __restrict__ c
         unsigned int ea = (unsigned int)rowEntity[colRow[a]], eb = (unsigned int)rowEntity[colRow[b]];
         pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
     } else {
-        atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+        atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS);
     }
 }
 
@@ -338,7 +347,7 @@ __device__ __forceinline__ void emitPairEnt(int a, int b, unsigned int ea, unsig
     base = __shfl_sync(m, base, leader);
     int slot = base + __popc(m & ((1u << lane) - 1u));
     if (slot < maxPairs) pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
-    else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+    else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
 }
 
 // One WARP per 32 consecutive sorted leaves, walking the tree as a packet: the warp keeps one stack (shared memory), pops one
@@ -399,7 +408,11 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
             int c = side ? rc : lc;
             if (!any) continue;                          // warp-uniform
             if (c >= 0) {                                // warp-uniform: the link is the same word for every lane
+                // 64 slots cannot run out: a root-to-leaf path has at most 62 internal nodes (deltaKey takes 62 distinct values: 2..31 on
+                // 30-bit keys, 32..63 on the index tie-break) and a depth-first walk holds one pending sibling per level.  Should a
+                // future key layout break that, the step fails loudly instead of dropping the subtree.
                 if (sp < 64) { if (lane == 0) st[sp] = c; ++sp; }
+                else if (lane == 0) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_WALK_STACK); }
                 continue;
             }
             if (!(side ? orr : ol)) continue;

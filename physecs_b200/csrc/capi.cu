@@ -193,6 +193,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     cudaEventCreateWithFlags(&ctx->evMainAtSet, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evVelReady, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evPoseReady, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evCounters, cudaEventDisableTiming);
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     const size_t R = caps->max_bodies, C = caps->max_colliders, P = caps->max_pairs, M = caps->max_manifolds;
     int rc = 0;
@@ -245,6 +246,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
 // which is copied / re-hashed so a step that overflowed can simply be run again.
 int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
     cudaSetDevice(ctx->device);
+    pb_collect_step(ctx);        // (an overflow it reports is what the caller is here for)
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t oldM = ctx->caps.max_manifolds;
@@ -270,7 +272,11 @@ int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
         size_t cs = 1; while (cs < 2 * M) cs <<= 1;
         unsigned long long* nTag[2] = { nullptr, nullptr }; int4* nVal[2] = { nullptr, nullptr };
         for (int b = 0; b < 2 && !rc; ++b) { rc = pb_alloc(ctx, &nTag[b], cs); if (!rc) rc = pb_alloc(ctx, &nVal[b], cs); }
-        if (rc) return rc;
+        if (rc) {       // allocation failed half way: the live context keeps its old arenas
+            cudaFree(nR); cudaFree(nOfs); cudaFree(nNp);
+            for (int b = 0; b < 2; ++b) { cudaFree(nTag[b]); cudaFree(nVal[b]); }
+            return rc;
+        }
         PB_CUDA(ctx, cudaMemcpyAsync(nR, ctx->pR0T[keep], sizeof(float4) * oldPT, cudaMemcpyDeviceToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(nOfs, ctx->cPointOfsBuf[keep], sizeof(int) * (oldM + 1), cudaMemcpyDeviceToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(nNp, ctx->cNpBuf[keep], sizeof(int) * (oldM + 1), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -286,6 +292,8 @@ int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
     if (rc) return rc;
     ctx->caps.max_pairs = (int)P;
     ctx->caps.max_manifolds = (int)M;
+    // the solve-order taps pointed into buffers that may just have been replaced
+    ctx->mSorted = nullptr; ctx->mSortedKeys = nullptr; ctx->lastCounts.n_manifolds = 0; ctx->countsStale = false;
     return PB_OK;
 }
 
@@ -299,6 +307,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->evMainAtSet) cudaEventDestroy(ctx->evMainAtSet);
     if (ctx->evVelReady) cudaEventDestroy(ctx->evVelReady);
     if (ctx->evPoseReady) cudaEventDestroy(ctx->evPoseReady);
+    if (ctx->evCounters) cudaEventDestroy(ctx->evCounters);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
@@ -310,7 +319,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
-    F(gjkHitPair); F(gjkHitSimplex); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
+    F(gjkHitPair); F(gjkHitSimplex); F(spillList); F(spillEpa); F(spillMesh); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
     F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(keyCursor); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.triRec); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
@@ -322,9 +331,10 @@ void pb_ctx_destroy(pb_ctx* ctx) {
 }
 
 int pb_sync(pb_ctx* ctx) {
+    cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PB_OK;
+    return pb_collect_step(ctx);
 }
 
 int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, const float* pos3, const float* quat4, const int* kinematic,
@@ -340,6 +350,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
     if ((rc = uploadRaw(ctx, entity, rows, ctx->rowEntity))) return rc;
     if ((rc = uploadVec(ctx, pos3, rows, 3, ctx->pos))) return rc;
     if ((rc = uploadVec(ctx, quat4, rows, 4, ctx->quat))) return rc;
+    ctx->hKinematic.assign(kinematic, kinematic + nDyn);
     if (nDyn) {
         if ((rc = uploadRaw(ctx, kinematic, nDyn, ctx->kinematic))) return rc;
         size_t bytes = sizeof(float) * (size_t)nDyn * 19;
@@ -369,11 +380,12 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
     ctx->nCol = n;
     ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
     ctx->hColIndex.assign(colIndex, colIndex + n);
+    ctx->hTrimeshCols.clear();
+    for (int i = 0; i < n; ++i) if (type[i] == PB_TRIANGLE_MESH) ctx->hTrimeshCols.push_back(i);
     // a custom filter table is indexed by collider: it has to be set again after every collider upload
     if (ctx->filterLut) { cudaFree(ctx->filterLut); ctx->filterLut = nullptr; ctx->nFilterClasses = 0; }
     // device flags: bit0 trigger, bit1 enableSimulation, bit2 owner is a non-kinematic dynamic body (BroadPhaseEntry::isDynamic)
-    std::vector<int> kin(ctx->nDyn);
-    if (ctx->nDyn) PB_CUDA(ctx, cudaMemcpy(kin.data(), ctx->kinematic, sizeof(int) * ctx->nDyn, cudaMemcpyDeviceToHost));
+    const std::vector<int>& kin = ctx->hKinematic;
     std::vector<int> f(n);
     std::vector<float> mat4((size_t)4 * n);
     bool trig = false;
@@ -418,7 +430,7 @@ static int syncMeshTables(pb_ctx* ctx) {
     std::vector<PbConvexDev> c(ctx->convexes.size());
     for (size_t i = 0; i < c.size(); ++i) {
         auto& m = ctx->convexes[i];
-        c[i] = { m.verts, m.faceOffsets, m.faceIndices, m.faceNormal, m.faceCentroid, m.nVerts, m.nVertsPadded, m.nFaces, 0 };
+        c[i] = { m.verts, m.faceOffsets, m.faceIndices, m.faceNormal, m.faceCentroid, m.nVerts, m.nVertsPadded, m.nFaces, m.maxFaceVerts };
     }
     if (t.size() > 64 || c.size() > 256) return pb_fail(ctx, PB_ECAPACITY, "too many meshes");
     if (!t.empty()) PB_CUDA(ctx, cudaMemcpy(ctx->triMeshDev, t.data(), sizeof(PbTriMeshDev) * t.size(), cudaMemcpyHostToDevice));
@@ -442,6 +454,7 @@ int pb_register_convex(pb_ctx* ctx, const float* verts3, int nVerts, const int* 
         fc[i] = make_float4(faceCentroids3[3 * i], faceCentroids3[3 * i + 1], faceCentroids3[3 * i + 2], 0.f);
     }
     int nIdx = faceOffsets[nFaces];
+    for (int i = 0; i < nFaces; ++i) m.maxFaceVerts = std::max(m.maxFaceVerts, faceOffsets[i + 1] - faceOffsets[i]);
     int rc = 0;
     if (!rc) rc = pb_alloc(ctx, &m.verts, v.size());
     if (!rc) rc = pb_alloc(ctx, &m.faceOffsets, (size_t)nFaces + 1);
@@ -608,8 +621,8 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
     if ((rc = pb_update_bounds_rows(ctx, ctx->rowMark, n, 0.01f))) return rc;
     std::vector<char> moved(ctx->nRows, 0);
     for (int i = 0; i < n; ++i) if (rows[i] >= 0 && rows[i] < ctx->nRows) moved[rows[i]] = 1;
-    for (int c = 0; c < ctx->nCol; ++c)
-        if (ctx->hColType[c] == PB_TRIANGLE_MESH && moved[ctx->hColRow[c]]) pb_update_bounds_trimesh_col(ctx, c, 0.01f);
+    for (int c : ctx->hTrimeshCols)
+        if (moved[ctx->hColRow[c]]) pb_update_bounds_trimesh_col(ctx, c, 0.01f);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }
@@ -623,11 +636,7 @@ int pb_refresh_bounds(pb_ctx* ctx) {
 
 static int readCounters(pb_ctx* ctx) {
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
-    // island statistics of the PREVIOUS step ride along (no extra sync): constraints in small islands, constraints in all
-    const bool stats = ctx->islandsOn && ctx->islandStats;
-    if (stats) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (stats) { ctx->lastIslandLocal = ctx->hCounters[CNT_TOTAL]; ctx->lastIslandTotal = ctx->hCounters[CNT_TOTAL + 1]; }
     return PB_OK;
 }
 
@@ -642,11 +651,58 @@ static void chooseIslands(pb_ctx* ctx) {
     ctx->islandsOn = true;
 }
 
+// The outcome of the last enqueued pb_step.  pb_step never waits for the device: the arena checks run there (a step whose
+// narrowphase overflowed skips its solve, integration and bounds refresh -- solver.cu stepSkipped), the counters are copied to
+// pinned memory right after the narrowphase, and the host looks at them here, at the next call that needs the step to have
+// happened (pb_sync, pb_get_*, the taps, the next pb_step).  On overflow the host-side bookkeeping of the step is rolled back, so
+// the scene is exactly what it was before the failed step: grow the arenas (pb_grow_arenas) and call pb_step again.
+int pb_collect_step(pb_ctx* ctx) {
+    if (!ctx->stepPending) return PB_OK;
+    ctx->stepPending = false;
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->evCounters));
+    const int* h = ctx->hCounters;
+    const int nPairs = h[CNT_PAIRS], nRaw = h[CNT_RAWM], status = h[CNT_STATUS], cause = h[CNT_CAUSE];
+    if (ctx->islandsOn && ctx->islandStats) { ctx->lastIslandLocal = h[CNT_TOTAL]; ctx->lastIslandTotal = h[CNT_TOTAL + 1]; }    // of the step before (rode along)
+    ctx->lastCounts = pb_counts{};
+    ctx->lastCounts.n_pairs = nPairs;
+    ctx->lastCounts.n_mesh_pairs = h[CNT_MESH_PAIRS];
+    ctx->lastCounts.n_triggers = h[CNT_TRIGGERS];
+    ctx->lastCounts.cause = cause;
+    ctx->lastCounts.n_spilled = h[CNT_SPILLED];
+    ctx->pairsHint = std::min(nPairs, ctx->caps.max_pairs);
+    ctx->rawHint = std::min(nRaw, ctx->caps.max_manifolds);
+    const bool overflow = nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY);
+    if (overflow || (status & 0x100)) {
+        // roll the host side back: the double buffers the build wrote into become "other" again, the velocity pointers return to the
+        // buffer that still holds the pre-step velocities (the device skipped every kernel that writes scene state)
+        ctx->curBuf ^= 1;
+        if (ctx->undoVelSwaps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); }
+        ctx->cacheValid = ctx->undoCacheValid; ctx->cacheBuilt = ctx->undoCacheBuilt;
+        ctx->countsStale = false;             // nothing was built: a later pb_get_counts must not replace n_manifolds by the post-build counter
+        ctx->mSorted = nullptr; ctx->mSortedKeys = nullptr;
+        if (!overflow) return pb_fail(ctx, PB_EUNSUPPORTED, "a candidate pair involves a shape combination not implemented on the device path (the step was not applied)");
+        ctx->lastCounts.status = PB_ECAPACITY;
+        ctx->lastCounts.n_manifolds = nRaw;   // what the arenas would have needed (counters keep counting past the capacity)
+        std::string why;
+        if (nPairs > ctx->caps.max_pairs || (cause & PB_CAUSE_PAIRS)) why += " candidate pairs";
+        if (nRaw > ctx->caps.max_manifolds || (cause & PB_CAUSE_MANIFOLDS)) why += " manifolds";
+        if (cause & PB_CAUSE_TRIGGERS) why += " trigger pairs";
+        if (cause & PB_CAUSE_WALK_STACK) why += " broadphase walk stack";
+        char hex[16]; snprintf(hex, sizeof hex, "%x", cause);
+        return pb_fail(ctx, PB_ECAPACITY, "per-step arena overflow (" + (why.empty() ? std::string(" unknown") : why) + " ): pairs=" + std::to_string(nPairs) + "/" +
+                       std::to_string(ctx->caps.max_pairs) + " manifolds=" + std::to_string(nRaw) + "/" + std::to_string(ctx->caps.max_manifolds) +
+                       " triggers=" + std::to_string(h[CNT_TRIGGERS]) + " cause=0x" + hex + "; the step was not applied: pb_grow_arenas, then pb_step again");
+    }
+    ctx->countsStale = true;     // manifold / colour / point counts stay on the device until someone asks (pb_get_counts)
+    return PB_OK;
+}
+
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
     cudaSetDevice(ctx->device);
-    ctx->queryTreeValid = false;
     if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
     int rc;
+    if ((rc = pb_collect_step(ctx))) return rc;          // the PREVIOUS step overflowed and was not applied: nothing new is enqueued
+    ctx->queryTreeValid = false;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream));
     if ((rc = pb_broadphase(ctx))) return rc;
@@ -655,32 +711,24 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     if ((rc = pb_world_poses(ctx))) return rc;
     if ((rc = pb_narrowphase(ctx))) return rc;
     cudaEventRecord(ctx->ev[2], ctx->stream);
-    if ((rc = readCounters(ctx))) return rc;
-    int nPairs = ctx->hCounters[CNT_PAIRS], nRaw = ctx->hCounters[CNT_RAWM], status = ctx->hCounters[CNT_STATUS];
-    ctx->lastCounts = pb_counts{};
-    ctx->lastCounts.n_pairs = nPairs;
-    ctx->pairsHint = nPairs;
-    ctx->lastCounts.n_mesh_pairs = ctx->hCounters[CNT_MESH_PAIRS];
-    ctx->lastCounts.n_triggers = ctx->hCounters[CNT_TRIGGERS];
-    if (nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY)) {
-        ctx->lastCounts.status = PB_ECAPACITY;
-        ctx->lastCounts.n_manifolds = nRaw;   // what the arenas would have needed (counters keep counting past the capacity)
-        return pb_fail(ctx, PB_ECAPACITY, "per-step arena overflow: pairs=" + std::to_string(nPairs) + "/" + std::to_string(ctx->caps.max_pairs) +
-                       " manifolds=" + std::to_string(nRaw) + "/" + std::to_string(ctx->caps.max_manifolds) + " (or triangle contacts per pair)");
-    }
-    if (status & 0x100) return pb_fail(ctx, PB_EUNSUPPORTED, "a candidate pair involves a shape combination not implemented on the device path");
+    // counters of the narrowphase (pairs, raw manifolds, status, triggers) to pinned memory; the island statistics of the PREVIOUS
+    // step ride along.  Nobody waits here: pb_collect_step looks at them later.
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->islandsOn && ctx->islandStats) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaEventRecord(ctx->evCounters, ctx->stream));
+    ctx->undoCacheValid = ctx->cacheValid; ctx->undoCacheBuilt = ctx->cacheBuilt; ctx->undoVelSwaps = 0;
+    ctx->stepPending = true;
     ctx->curBuf ^= 1;
     if ((rc = pb_wait_velocities(ctx))) return rc;      // first readers of the velocities: contact build, then the solver
     chooseIslands(ctx);
     if ((rc = pb_joint_begin_step(ctx))) return rc;      // solver body indices of the joints: the island search hooks through them
-    if ((rc = pb_contact_build(ctx, nRaw))) return rc;
+    if ((rc = pb_contact_build(ctx))) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
-    ctx->countsStale = nRaw > 0;     // manifold / colour / point counts stay on the device until someone asks (pb_get_counts)
-    if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity, nRaw))) return rc;
+    if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
     ctx->cacheValid = true;
     ctx->cacheBuilt = true;
     // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
-    if ((rc = pb_update_bounds_all(ctx, 0.01f, 1))) return rc;
+    if ((rc = pb_update_bounds_all(ctx, 0.01f, 1, ctx->counters + CNT_STATUS))) return rc;
     cudaEventRecord(ctx->ev[4], ctx->stream);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
@@ -688,6 +736,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
 
 int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3) {
     cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }      // the step before overflowed: its status instead of a state it did not produce
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     int nDyn = ctx->nDyn;
     if (!nDyn) return PB_OK;
@@ -746,6 +795,7 @@ int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
     ctx->queryTreeValid = false;
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
+    ctx->hKinematic.assign(kinematic, kinematic + nDyn);
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->kinematic, kinematic, sizeof(int) * nDyn, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->nCol) ++ctx->launches, k_col_dynamic_flag<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colFlags);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -804,6 +854,7 @@ int pb_set_contact_filter(pb_ctx* ctx, int nColliders, const int* colliderClass,
 
 int pb_get_triggers(pb_ctx* ctx, int* out4, int cap, int* n) {
     cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int nt = std::min(ctx->lastCounts.n_triggers, ctx->caps.max_pairs);
     *n = nt;
@@ -832,13 +883,15 @@ static int refreshCounts(pb_ctx* ctx) {
 
 int pb_get_counts(pb_ctx* ctx, pb_counts* out) {
     cudaSetDevice(ctx->device);
-    int rc = refreshCounts(ctx);
+    int rc = pb_collect_step(ctx);
+    if (!rc) rc = refreshCounts(ctx);
     *out = ctx->lastCounts;
     return rc;
 }
 
 int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
     cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     pb_timings t{};
     cudaEventElapsedTime(&t.broadphase, ctx->ev[0], ctx->ev[1]);
@@ -853,6 +906,7 @@ int pb_get_timings(pb_ctx* ctx, pb_timings* out) {
 
 int pb_get_pairs(pb_ctx* ctx, int* out4, int cap, int* n) {
     cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int np = std::min(ctx->lastCounts.n_pairs, ctx->caps.max_pairs);
     *n = np;
@@ -885,9 +939,10 @@ int pb_get_bounds(pb_ctx* ctx, float* out6) {
 
 int pb_get_manifolds(pb_ctx* ctx, int cap, int* keys5, int* numPoints, float* normal3, float* points24, int* color, int* n) {
     cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     { int rc = refreshCounts(ctx); if (rc) return rc; }
-    int nm = ctx->lastCounts.n_manifolds;
+    int nm = ctx->mSorted ? ctx->lastCounts.n_manifolds : 0;     // no solve order: the last step failed or the arenas were just replaced
     *n = nm;
     if (nm == 0 || cap == 0) return PB_OK;
     std::vector<int> sorted(nm);

@@ -11,6 +11,7 @@
 #include "pb_ctx.h"
 #include "pb_math.cuh"
 #include <utility>
+#include <algorithm>
 
 #define DISCARD_COLOR 255u
 
@@ -136,10 +137,9 @@ __global__ void __launch_bounds__(256) k_scatter_by_key(const int* __restrict__ 
     }
 }
 
-__global__ void k_gather_np(const int* __restrict__ counters, const int* __restrict__ mSorted, const int4* __restrict__ mKey, int* __restrict__ np, int maxManifolds) {
+__global__ void k_gather_np(const int* __restrict__ counters, const int* __restrict__ mSorted, const int4* __restrict__ mKey, int* __restrict__ np) {
     int n = counters[CNT_MANIFOLDS];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < maxManifolds; i += gridDim.x * blockDim.x)
-        np[i] = i < n ? mKey[mSorted[i]].w : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) np[i] = mKey[mSorted[i]].w;
 }
 
 __global__ void k_count_points(int* counters, const int* __restrict__ pointOfs, const int* __restrict__ np) {
@@ -290,8 +290,13 @@ int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
     return PB_OK;
 }
 
-int pb_contact_build(pb_ctx* ctx, int nRaw) {
+// Nothing here needs a count on the host: every kernel reads the manifold count from the device counters, launch shapes follow
+// ctx->rawHint (the previous step's count, a guess that only shapes grids) or the arena capacity.  When the narrowphase overflowed an
+// arena (CNT_STATUS), the kernels still run over the clamped counts -- everything they write is per-step scratch or the "current"
+// half of a double buffer that the host flips back when it collects the step's status (capi.cu collectStep).
+int pb_contact_build(pb_ctx* ctx) {
     int blocks = ctx->numSMs * 8;
+    if (ctx->rawHint >= 0) blocks = std::max(ctx->numSMs, std::min(blocks, (2 * ctx->rawHint + 4096) / 256 + 1));
     int maxM = ctx->caps.max_manifolds;
     const int G = ctx->islandGroups, nKeys = (G + 1) * PB_KEY_COLORS;
     int rc;
@@ -303,13 +308,6 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     if (ctx->islandsOn) {
         if ((rc = pb_islands_build(ctx))) return rc;
         if ((rc = pb_joint_lists(ctx))) return rc;
-    }
-    // nRaw was read back after the narrowphase
-    int n = nRaw;
-    if (n <= 0) {
-        // no manifolds this step: the contact cache of this step must still read as empty for the next one
-        cudaMemsetAsync(ctx->cacheTag[ctx->curBuf], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
-        return PB_OK;
     }
     // Solve order = a counting sort by (group, colour, single | multi): the run table holds the first slot of every key (scanned key
     // histogram), so one scatter pass places every manifold (slot = run start + arrival rank, one atomic per distinct key per warp).
@@ -332,8 +330,8 @@ int pb_contact_build(pb_ctx* ctx, int nRaw) {
     ctx->mSortedKeys = ctx->mSortKeyB;
     int cur = ctx->curBuf, prev = cur ^ 1;
     int* pointOfs = ctx->cPointOfsBuf[cur];
-    ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur], n);
-    rc = pb_exclusive_scan(ctx, ctx->cNpBuf[cur], pointOfs, n, (int*)ctx->radixHist);
+    ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur]);
+    rc = pb_exclusive_scan_dev(ctx, ctx->cNpBuf[cur], pointOfs, ctx->counters + CNT_MANIFOLDS, maxM, ctx->rawHint < 0 ? -1 : 2 * ctx->rawHint + 4096, (int*)ctx->radixHist);
     if (rc) return rc;
     ++ctx->launches, k_count_points<<<1, 1, 0, ctx->stream>>>(ctx->counters, pointOfs, ctx->cNpBuf[cur]);
     cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);

@@ -140,9 +140,18 @@ __device__ __forceinline__ int warpReserve(int want, int* counter) {
     return base + inc - want;
 }
 
+// A pair outgrew the per-thread containers of its bin kernel (`cause` = PB_CAUSE_SPILLED_* bits): no result is stored, the pair goes
+// on the bin family's spill list and k_np_gjk_spill / k_np_mesh_spill redo it on global-memory scratch.
+__device__ __forceinline__ void spillAppend(int* counters, int which, int* __restrict__ list, int pairIndex, int cause) {
+    atomicOr(&counters[CNT_CAUSE], cause);
+    int s = atomicAdd(&counters[which], 1);
+    if (s < PB_SPILL_CAP) list[s] = pairIndex;
+    else atomicOr(&counters[CNT_CAUSE], PB_CAUSE_SPILL_LIST);
+}
+
 __device__ __forceinline__ void storeManifold(int slot, int maxManifolds, int colA, int colB, const Manifold& m, bool flip,
                                               int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int* counters) {
-    if (slot >= maxManifolds) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); return; }
+    if (slot >= maxManifolds) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_MANIFOLDS); return; }
     mKey[slot] = make_int4(colA, colB, m.tri, m.np);
     V3 n = flip ? -m.n : m.n;
     mNormal[slot] = f4(n);
@@ -158,7 +167,8 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams,
                                                  const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                  const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
-                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                 int* __restrict__ spillList) {
     int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
     int lane = threadIdx.x & 31;
     for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
@@ -167,7 +177,8 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
         Manifold m; m.np = 0; m.tri = -1;
         int a = 0, b = 0;
         if (idx < end) {
-            int2 p = pairs[pairOrder[idx]];
+            const int pi = pairOrder[idx];
+            int2 p = pairs[pi];
             a = p.x; b = p.y;
             int t0 = colType[a], t1 = colType[b];
             float4 q0 = colParams[a], q1 = colParams[b];
@@ -186,7 +197,9 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
                 if (t0 == PB_CAPSULE) hit = collideCapsuleBox(pos0, or0, q0.x, q0.y, pos1, or1, mk3(q1.x, q1.y, q1.z), m);
                 else { hit = collideCapsuleBox(pos1, or1, q1.x, q1.y, pos0, or0, mk3(q0.x, q0.y, q0.z), m); flip = true; }
             } else if (BIN == BIN_GJK) {
-                hit = collideGjkPair(t0, q0, pos0, or0, colMesh[a], t1, q1, pos1, or1, colMesh[b], convexes, m, flip, counters);
+                Epa poly; int ovf = 0;
+                hit = collideGjkPair<LimFast>(t0, q0, pos0, or0, colMesh[a], t1, q1, pos1, or1, colMesh[b], convexes, m, flip, poly, &ovf);
+                if (ovf) { hit = false; spillAppend(counters, CNT_SPILL_GJK, spillList, pi, ovf); }
             }
             hit = hit && m.np > 0;
         }
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(128) k_np_gjk_hits(const int2* __restrict__ pa
                 const float* f = (const float*)simplex;        // 4 x {pos, sp0, sp1} = 36 floats
 #pragma unroll
                 for (int k = 0; k < 9; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-            } else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+            } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_MANIFOLDS); }    // hit list capacity == the manifold arena's
         }
     }
 }
@@ -235,7 +248,8 @@ __global__ void __launch_bounds__(128) k_np_gjk_manifolds(const int2* __restrict
                                                           const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                           const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
                                                           const int* __restrict__ hitPair, const float4* __restrict__ hitSimplex, int maxHits,
-                                                          int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+                                                          int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                          int* __restrict__ spillList) {
     int n = min(counters[CNT_GJK_HITS], maxHits);
     int lane = threadIdx.x & 31;
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
@@ -254,8 +268,10 @@ __global__ void __launch_bounds__(128) k_np_gjk_manifolds(const int2* __restrict
             const float4* in = hitSimplex + 9 * (size_t)h;
 #pragma unroll
             for (int k = 0; k < 9; ++k) { float4 v = in[k]; f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w; }
-            gjkPairManifold(g, convexes, simplex, m, counters);
+            Epa poly; int ovf = 0;
+            gjkPairManifold<LimFast>(g, convexes, simplex, m, poly, &ovf);
             hit = m.np > 0;
+            if (ovf) { hit = false; spillAppend(counters, CNT_SPILL_GJK, spillList, hitPair[h], ovf); }
         }
         int slot = warpReserve(hit ? 1 : 0, &counters[CNT_RAWM]);
         if (hit) storeManifold(slot, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(128) k_np_gjk_manifolds(const int2* __restrict
 // explicit stack, left child popped first; CollisionTriangleMesh.cpp:895-907).
 template <int TYPE>
 __device__ inline int meshCollect(float4 prm, V3 localPos, Q4 localOr, const PbTriMeshDev& mesh,
-                                  const PbConvexDev* convexes, int convexId, TriContact* contacts, bool* overflow, Epa* scratch, int* counters) {
+                                  const PbConvexDev* convexes, int convexId, TriContact* contacts, int* ovf, Epa* scratch) {
     constexpr bool HEAVY = TYPE >= PB_BOX;
     Aabb lb = shapeBounds(localPos, localOr, TYPE, prm, convexes, convexId);
     Shape convexShape;
@@ -290,11 +306,11 @@ __device__ inline int meshCollect(float4 prm, V3 localPos, Q4 localOr, const PbT
             if (triCount) {
                 for (int k = 0; k < triCount; ++k) {
                     if (nc < PB_MAX_TRI_CAND) cand[nc++] = index + k;
-                    else *overflow = true;
+                    else *ovf |= PB_CAUSE_SPILLED_TRI_CAND;
                 }
             } else {
                 if (sp + 2 <= 64) { stack[sp++] = index + 1; stack[sp++] = index; }
-                else *overflow = true;
+                else *ovf |= PB_CAUSE_SPILLED_MESH_STACK;
             }
         }
     }
@@ -312,15 +328,62 @@ __device__ inline int meshCollect(float4 prm, V3 localPos, Q4 localOr, const PbT
         if (TYPE == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, a, b, c, n, tc);
         else if (TYPE == PB_CAPSULE) hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, a, b, c, n, tc);
         else if (TYPE == PB_BOX) hit = boxTriangle(localPos, localOr, mk3(prm.x, prm.y, prm.z), a, b, c, n, tc);
-        else hit = convexTriangle(convexShape, a, b, c, mk3(mesh.triCentroid[tri]), tc, *scratch, counters);
+        else hit = convexTriangle(convexShape, a, b, c, mk3(mesh.triCentroid[tri]), tc, *scratch, ovf);
         if (hit) {
             tc.tri = tri;
             if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
-            else *overflow = true;
+            else *ovf |= PB_CAUSE_SPILLED_TRI_CONTACTS;
         }
     }
     (void)HEAVY;
     return cnt;
+}
+
+// std::sort(contacts.begin(), contacts.end()) of the delayed edge / vertex contacts (CTM.cpp:932; operator< compares distance,
+// :32-34), on an index array.  The oracle is the reference built with libstdc++, whose std::sort is: introsort partitioning
+// (median of three to the front, unguarded Hoare partition) while a range holds more than 16 elements, then one insertion sort
+// over everything -- restated here move for move so that contacts at EQUAL distance end up in the same order (up to 16 elements
+// it is a plain insertion sort).  `less(i, j)`: contact i sorts strictly before contact j.
+template <class IdxT, class Less>
+__device__ inline void sortLikeStdSort(IdxT* v, int n, Less less) {
+    if (n > 16) {
+        int depth = 2 * (31 - __clz(n));
+        int stackLo[64], stackHi[64], stackD[64];      // pending right-hand ranges (the recursion of __introsort_loop)
+        int sp = 0;
+        int first = 0, last = n;
+        for (;;) {
+            while (last - first > 16 && depth > 0) {
+                --depth;
+                int mid = first + (last - first) / 2;
+                // __move_median_to_first(first, first + 1, mid, last - 1)
+                int a = first + 1, b = mid, c = last - 1, r;
+                if (less(v[a], v[b])) r = less(v[b], v[c]) ? b : (less(v[a], v[c]) ? c : a);
+                else r = less(v[a], v[c]) ? a : (less(v[b], v[c]) ? c : b);
+                { IdxT t = v[first]; v[first] = v[r]; v[r] = t; }
+                // __unguarded_partition(first + 1, last, pivot = first)
+                int i = first + 1, j = last;
+                for (;;) {
+                    while (less(v[i], v[first])) ++i;
+                    --j;
+                    while (less(v[first], v[j])) --j;
+                    if (!(i < j)) break;
+                    IdxT t = v[i]; v[i] = v[j]; v[j] = t;
+                    ++i;
+                }
+                if (sp < 64) { stackLo[sp] = i; stackHi[sp] = last; stackD[sp] = depth; ++sp; }     // __introsort_loop(cut, last, depth_limit)
+                last = i;
+            }
+            // (depth exhausted: libstdc++ heap-sorts the range; the final insertion sort below orders it as well, equal keys may differ)
+            if (!sp) break;
+            --sp; first = stackLo[sp]; last = stackHi[sp]; depth = stackD[sp];
+        }
+    }
+    for (int i = 1; i < n; ++i) {          // __final_insertion_sort
+        IdxT x = v[i];
+        int j = i;
+        while (j > 0 && less(x, v[j - 1])) { v[j] = v[j - 1]; --j; }
+        v[j] = x;
+    }
 }
 
 // The reference's two-pass feature filter over the triangle contacts of one (shape, mesh) pair (CTM.cpp:913-953): writes the
@@ -343,14 +406,7 @@ __device__ inline int meshFilter(const PbTriMeshDev& mesh, const TriContact* con
             --nLive;
         }
     }
-    // stable insertion sort by distance (std::sort on <=16 elements is an insertion sort, CTM.cpp:932)
-    for (int i = 1; i < nLive; ++i) {
-        unsigned char v = live[i];
-        float d = contacts[v].dist;
-        int j = i;
-        while (j > 0 && d < contacts[live[j - 1]].dist) { live[j] = live[j - 1]; --j; }
-        live[j] = v;
-    }
+    sortLikeStdSort(live, nLive, [&](unsigned char x, unsigned char y) { return contacts[x].dist < contacts[y].dist; });
     // pass 2 (CTM.cpp:934-953)
     for (int i = 0; i < nLive; ++i) {
         int ci = live[i];
@@ -373,7 +429,8 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
                                                  const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                  const PbTriMeshDev* __restrict__ meshes, const PbConvexDev* __restrict__ convexes,
-                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                 int* __restrict__ spillList) {
     constexpr bool HEAVY = TYPE >= PB_BOX;
     const int BIN = BIN_MESH_S + TYPE;
     int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
@@ -389,8 +446,10 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
         V3 pos1 = mk3(0.f), localPos = mk3(0.f); Q4 or1 = mkq(make_float4(0, 0, 0, 1)), localOr = or1;
         float4 prm = make_float4(0, 0, 0, 0);
         int meshId = 0;
+        int ovf = 0, pi = 0;
         if (idx < end) {
-            int2 p = pairs[pairOrder[idx]];
+            pi = pairOrder[idx];
+            int2 p = pairs[pi];
             a = p.x; b = p.y;
             // Collision.cpp:897-907: mesh on side 0 -> collide (shape1, mesh0) and flip
             flip = colType[a] == PB_TRIANGLE_MESH;
@@ -404,17 +463,20 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             localPos = rotate(invOr1, pos0 - pos1);
             localOr = qmul(invOr1, or0);
             {
-                bool overflow = false;
                 Epa scratch;
-                int cnt = meshCollect<TYPE>(prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &overflow, HEAVY ? &scratch : nullptr, counters);
-                if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
-                nGen = meshFilter(meshes[meshId], contacts, cnt, order);
+                int cnt = meshCollect<TYPE>(prm, localPos, localOr, meshes[meshId], convexes, colMesh[shape], contacts, &ovf, HEAVY ? &scratch : nullptr);
+                if (!ovf) nGen = meshFilter(meshes[meshId], contacts, cnt, order);
             }
         }
+        // the convex generators clip a face against a triangle (or the reverse): at most (face vertices + 3) points.  Decided before the
+        // arena slots are reserved, so a spilled pair stores nothing here.
+        if (TYPE == PB_CONVEX_MESH && nGen && convexes[colMesh[shape]].maxFaceVerts + 3 > LimFast::POLY) ovf |= PB_CAUSE_SPILLED_CLIP;
+        if (ovf) { nGen = 0; spillAppend(counters, CNT_SPILL_MESH, spillList, pi, ovf); }
         int slot = warpReserve(nGen, &counters[CNT_RAWM]);
         for (int g = 0; g < nGen; ++g) {
             const TriContact& tc = contacts[order[g]];
             Manifold m; m.np = 0; m.tri = tc.tri;
+            int ovfGen = 0;
             if (!HEAVY) {
                 if (type == PB_CAPSULE && tc.feature == TF_FACE) {
                     if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
@@ -430,8 +492,9 @@ __global__ void __launch_bounds__(128) k_np_mesh(const int2* __restrict__ pairs,
             } else {
                 const PbConvexDev& cm = convexes[colMesh[shape]];
                 V3 sc = mk3(prm.x, prm.y, prm.z);
-                if (tc.feature == TF_FACE) convexTriangleFaceManifold(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, counters);
-                else convexFaceTriangleManifold(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, counters);
+                if (tc.feature == TF_FACE) convexTriangleFaceManifold<LimFast>(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, &ovfGen);
+                else convexFaceTriangleManifold<LimFast>(localPos, localOr, cm, sc, pos1, or1, meshes[meshId], tc, m, &ovfGen);
+                if (ovfGen) atomicOr(&counters[CNT_CAUSE], ovfGen | PB_CAUSE_SPILL_SCRATCH);      // unreachable: bounded by the maxFaceVerts test above
             }
             m.tri = tc.tri;
             // a == side 0 of the pair; manifolds are computed shape->mesh, flip when the mesh is side 0
@@ -459,10 +522,10 @@ __device__ __forceinline__ bool aabbHits(const Aabb& lb, float4 mn, float4 mx) {
     return true;
 }
 
-__device__ inline int meshCullDual(const Aabb& lb, const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax, int* cand, bool* overflow) {
+__device__ inline int meshCullDual(const Aabb& lb, const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax, int* cand, int* ovf) {
     int nc = 0;
-#define ML_ADD_LEAF(cnt_, idx_) do { for (int k_ = 0; k_ < (cnt_); ++k_) { if (nc < PB_MAX_TRI_CAND) cand[nc++] = (idx_) + k_; else *overflow = true; } } while (0)
-#define ML_PUSH(v_) do { if (sp < 64) stack[sp++] = (v_); else *overflow = true; } while (0)
+#define ML_ADD_LEAF(cnt_, idx_) do { for (int k_ = 0; k_ < (cnt_); ++k_) { if (nc < PB_MAX_TRI_CAND) cand[nc++] = (idx_) + k_; else *ovf |= PB_CAUSE_SPILLED_TRI_CAND; } } while (0)
+#define ML_PUSH(v_) do { if (sp < 64) stack[sp++] = (v_); else *ovf |= PB_CAUSE_SPILLED_MESH_STACK; } while (0)
     float4 mn = nodeMin[0], mx = nodeMax[0];
     if (!aabbHits(lb, mn, mx)) return 0;
     if (__float_as_int(mn.w)) { ML_ADD_LEAF(__float_as_int(mn.w), __float_as_int(mx.w)); return nc; }
@@ -506,7 +569,8 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
                                                  const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
                                                  const float4* __restrict__ wpos, const float4* __restrict__ wquat,
                                                  const PbTriMeshDev* __restrict__ meshes,
-                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                 int* __restrict__ spillList) {
     const int BIN = BIN_MESH_S + TYPE;
     int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
     const int lane = threadIdx.x & 31;
@@ -517,13 +581,15 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
         int cand[PB_MAX_TRI_CAND];
         int nc = 0, cnt = 0, nGen = 0;
         int a = 0, b = 0;
-        bool flip = false, overflow = false;
+        bool flip = false;
+        int ovf = 0, pi = 0;
         V3 pos1 = mk3(0.f), localPos = mk3(0.f); Q4 or1 = mkq(make_float4(0, 0, 0, 1)), localOr = or1;
         float4 prm = make_float4(0, 0, 0, 0);
         int meshId = 0;
         const float4* rec = nullptr;
         if (idx < end) {
-            int2 p = pairs[pairOrder[idx]];
+            pi = pairOrder[idx];
+            int2 p = pairs[pi];
             a = p.x; b = p.y;
             flip = colType[a] == PB_TRIANGLE_MESH;      // Collision.cpp:897-907: mesh on side 0 -> collide (shape1, mesh0) and flip
             int shape = flip ? b : a;
@@ -538,7 +604,8 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
             Aabb lb = shapeBounds(localPos, localOr, TYPE, prm, nullptr, 0);
             const PbTriMeshDev& mesh = meshes[meshId];
             rec = mesh.triRec;
-            nc = meshCullDual(lb, mesh.nodeMin, mesh.nodeMax, cand, &overflow);
+            nc = meshCullDual(lb, mesh.nodeMin, mesh.nodeMax, cand, &ovf);
+            if (ovf) nc = 0;         // goes to the spill kernel: no point in testing the candidates that fit
         }
         {
             // per-pair loop in candidate order, the next triangle's record in flight while this one is tested
@@ -551,12 +618,12 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
                 if (lightTriTest<TYPE>(localPos, localOr, prm.x, prm.y, r0, r1, r2, tc)) {
                     tc.tri = cand[i];
                     if (cnt < PB_MAX_TRI_CONTACTS) contacts[cnt++] = tc;
-                    else overflow = true;
+                    else ovf |= PB_CAUSE_SPILLED_TRI_CONTACTS;
                 }
             }
         }
-        if (overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
-        if (idx < end) nGen = meshFilter(meshes[meshId], contacts, cnt, order);
+        if (ovf) spillAppend(counters, CNT_SPILL_MESH, spillList, pi, ovf);
+        else if (idx < end) nGen = meshFilter(meshes[meshId], contacts, cnt, order);
         int slot = warpReserve(nGen, &counters[CNT_RAWM]);
         for (int g = 0; g < nGen; ++g) {
             const TriContact& tc = contacts[order[g]];
@@ -570,6 +637,232 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
             storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
         }
     }
+}
+
+// ---- spill kernels: pairs that outgrew the per-thread containers ----------------------------------------------------------------
+// The reference keeps per-pair work in std::vectors (EPA polytope EPA.h:22-124, overlapBvh's triangle list TriangleMesh.cpp:166-192,
+// the contact list CTM.cpp:893-907) and in 128-point clip buffers (Clipping.cpp:6).  The bin kernels above hold them in per-thread
+// local memory, sized for the common case; a pair that needs more lands on a spill list and is redone here from scratch with the
+// same routines on global-memory scratch sized far beyond anything observed (LimSpill; MS_* below).  Exceeding even those sets
+// PB_CAUSE_SPILL_SCRATCH and keeps what fits -- a step never fails because of one pair.
+
+// GJK / EPA bin: one thread per spilled pair, polytope in epaScratch[global thread].
+__global__ void __launch_bounds__(PB_SPILL_GJK_THREADS) k_np_gjk_spill(const int2* __restrict__ pairs, const int* __restrict__ spillList, int* __restrict__ counters,
+                                                     const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                     const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                     const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                     LimSpill::Epa* __restrict__ epaScratch,
+                                                     int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    const int n = min(counters[CNT_SPILL_GJK], PB_SPILL_CAP);
+    if (n == 0) return;
+    if (threadIdx.x == 0) atomicAdd(&counters[CNT_SPILLED], n);
+    LimSpill::Epa& poly = epaScratch[threadIdx.x];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int2 p = pairs[spillList[e]];
+        const int a = p.x, b = p.y;
+        Manifold m; m.np = 0; m.tri = -1;
+        bool flip = false;
+        int ovf = 0;
+        bool hit = collideGjkPair<LimSpill>(colType[a], colParams[a], mk3(wpos[a]), mkq(wquat[a]), colMesh[a],
+                                            colType[b], colParams[b], mk3(wpos[b]), mkq(wquat[b]), colMesh[b], convexes, m, flip, poly, &ovf);
+        if (ovf) atomicOr(&counters[CNT_CAUSE], PB_CAUSE_SPILL_SCRATCH);
+        if (hit && m.np > 0) storeManifold(atomicAdd(&counters[CNT_RAWM], 1), maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+    }
+}
+
+// Mesh bins (all four shape kinds): one WARP per spilled pair.  Lane 0 walks the mesh BVH in the reference's order into the
+// candidate list; the lanes test 32 candidates at a time and append the hits in candidate order (ballot prefix); the feature
+// filter runs warp-wide with identical control flow in every lane (the voided-vertex lookups are strided over the lanes); the
+// surviving contacts' manifolds are generated one per lane.
+#define MS_CAND 65536
+#define MS_CONTACTS 8192
+#define MS_STACK 4096
+struct MeshSpillScratch {
+    int cand[MS_CAND];
+    TriContact contacts[MS_CONTACTS];
+    unsigned short live[MS_CONTACTS], order[MS_CONTACTS];
+    unsigned int voidSet[3 * MS_CONTACTS];
+    int stack[MS_STACK];
+};
+
+__device__ __forceinline__ bool voidedW(const unsigned int* set, int n, unsigned int v, int lane) {
+    bool f = false;
+    for (int i = lane; i < n; i += 32) f |= set[i] == v;
+    return __any_sync(0xffffffffu, f);
+}
+__device__ __forceinline__ void voidInsertW(unsigned int* set, int& n, unsigned int v, int lane) {
+    if (voidedW(set, n, v, lane)) return;
+    if (lane == 0) set[n] = v;
+    ++n;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) k_np_mesh_spill(const int2* __restrict__ pairs, const int* __restrict__ spillList, int* __restrict__ counters,
+                                                       const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
+                                                       const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                       const PbTriMeshDev* __restrict__ meshes, const PbConvexDev* __restrict__ convexes,
+                                                       MeshSpillScratch* __restrict__ scratch, LimSpill::Epa* __restrict__ epaScratch,
+                                                       int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds) {
+    const int n = min(counters[CNT_SPILL_MESH], PB_SPILL_CAP);
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    if (warp == 0 && lane == 0) atomicAdd(&counters[CNT_SPILLED], n);
+    MeshSpillScratch& S = scratch[warp];
+    LimSpill::Epa* myEpa = epaScratch ? epaScratch + PB_SPILL_GJK_THREADS + (size_t)warp * 32 + lane : nullptr;
+    for (int e = warp; e < n; e += nWarps) {
+        int2 p = pairs[spillList[e]];
+        const int a = p.x, b = p.y;
+        const bool flip = colType[a] == PB_TRIANGLE_MESH;      // Collision.cpp:897-907
+        const int shape = flip ? b : a, meshCol = flip ? a : b;
+        const int type = colType[shape];
+        const float4 prm = colParams[shape];
+        const PbTriMeshDev& mesh = meshes[colMesh[meshCol]];
+        const V3 pos0 = mk3(wpos[shape]); const Q4 or0 = mkq(wquat[shape]);
+        const V3 pos1 = mk3(wpos[meshCol]); const Q4 or1 = mkq(wquat[meshCol]);
+        const Q4 invOr1 = qinverse(or1);
+        const V3 localPos = rotate(invOr1, pos0 - pos1);
+        const Q4 localOr = qmul(invOr1, or0);
+        const int convexId = colMesh[shape];
+        int ovf = 0;
+        // ---- cull (TriangleMesh.cpp:166-192), lane 0
+        int nc = 0;
+        if (lane == 0) {
+            Aabb lb = shapeBounds(localPos, localOr, type, prm, convexes, convexId);
+            int sp = 0;
+            S.stack[sp++] = 0;
+            while (sp > 0) {
+                int node = S.stack[--sp];
+                float4 nmn = mesh.nodeMin[node], nmx = mesh.nodeMax[node];
+                if (!aabbHits(lb, nmn, nmx)) continue;
+                int triCount = __float_as_int(nmn.w), index = __float_as_int(nmx.w);
+                if (triCount) {
+                    for (int k = 0; k < triCount; ++k) { if (nc < MS_CAND) S.cand[nc++] = index + k; else ovf |= PB_CAUSE_SPILL_SCRATCH; }
+                } else if (sp + 2 <= MS_STACK) { S.stack[sp++] = index + 1; S.stack[sp++] = index; }
+                else ovf |= PB_CAUSE_SPILL_SCRATCH;
+            }
+        }
+        nc = __shfl_sync(0xffffffffu, nc, 0);
+        __syncwarp();
+        // ---- per-triangle tests, 32 candidates at a time, hits appended in candidate order (CTM.cpp:895-907)
+        Shape convexShape;
+        if (type == PB_CONVEX_MESH) convexShape = makeShape(type, prm, localPos, localOr, convexes, convexId);
+        int cnt = 0;
+        for (int base = 0; base < nc; base += 32) {
+            const int i = base + lane;
+            bool hit = false;
+            TriContact tc;
+            if (i < nc) {
+                const int tri = S.cand[i];
+                int4 ti = mesh.tris[tri];
+                V3 va = mk3(mesh.verts[ti.x]), vb = mk3(mesh.verts[ti.y]), vc = mk3(mesh.verts[ti.z]);
+                V3 nn = mk3(mesh.triNormal[tri]);
+                tc.boxFeature = 0; tc.boxAxis = 0; tc.fidx = 0; tc.feature = TF_FACE; tc.dist = 0.f;
+                tc.normal = tc.cpBody = tc.cpTri = mk3(0.f);
+                if (type == PB_SPHERE) hit = sphereTriangle(localPos, prm.x, va, vb, vc, nn, tc);
+                else if (type == PB_CAPSULE) hit = capsuleTriangle(localPos, localOr, prm.x, prm.y, va, vb, vc, nn, tc);
+                else if (type == PB_BOX) hit = boxTriangle(localPos, localOr, mk3(prm.x, prm.y, prm.z), va, vb, vc, nn, tc);
+                else hit = convexTriangle(convexShape, va, vb, vc, mk3(mesh.triCentroid[tri]), tc, *myEpa, &ovf);
+                tc.tri = tri;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            if (hit) { if (pos < MS_CONTACTS) S.contacts[pos] = tc; else ovf |= PB_CAUSE_SPILL_SCRATCH; }
+            cnt += __popc(mask);
+        }
+        if (cnt > MS_CONTACTS) cnt = MS_CONTACTS;
+        __syncwarp();
+        // ---- feature filter (CTM.cpp:913-953), every lane in lock step
+        int nGen = 0, nVoid = 0, nLive = cnt;
+        for (int i = lane; i < cnt; i += 32) S.live[i] = (unsigned short)i;
+        __syncwarp();
+        for (int i = nLive - 1; i >= 0; --i) {
+            const int ci = S.live[i];
+            if (S.contacts[ci].feature == TF_FACE) {
+                int4 ti = mesh.tris[S.contacts[ci].tri];
+                voidInsertW(S.voidSet, nVoid, (unsigned)ti.x, lane); voidInsertW(S.voidSet, nVoid, (unsigned)ti.y, lane); voidInsertW(S.voidSet, nVoid, (unsigned)ti.z, lane);
+                const unsigned short lastLive = S.live[nLive - 1];
+                __syncwarp();
+                if (lane == 0) { S.order[nGen] = (unsigned short)ci; S.live[i] = lastLive; }
+                ++nGen; --nLive;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) sortLikeStdSort(S.live, nLive, [&](unsigned short x, unsigned short y) { return S.contacts[x].dist < S.contacts[y].dist; });
+        __syncwarp();
+        for (int i = 0; i < nLive; ++i) {
+            const int ci = S.live[i];
+            const int feature = S.contacts[ci].feature, fidx = S.contacts[ci].fidx;
+            int4 ti = mesh.tris[S.contacts[ci].tri];
+            unsigned int vi[3] = { (unsigned)ti.x, (unsigned)ti.y, (unsigned)ti.z };
+            if (feature == TF_EDGE) {
+                if (voidedW(S.voidSet, nVoid, vi[(fidx + 1) % 3], lane) && voidedW(S.voidSet, nVoid, vi[(fidx + 2) % 3], lane)) continue;
+            } else {
+                if (voidedW(S.voidSet, nVoid, vi[fidx], lane)) continue;
+            }
+            if (lane == 0) S.order[nGen] = (unsigned short)ci;
+            ++nGen;
+            voidInsertW(S.voidSet, nVoid, vi[0], lane); voidInsertW(S.voidSet, nVoid, vi[1], lane); voidInsertW(S.voidSet, nVoid, vi[2], lane);
+        }
+        __syncwarp();
+        // ---- manifolds, one per lane (CTM.cpp:826-880 dispatch)
+        int slot = 0;
+        if (lane == 0 && nGen) slot = atomicAdd(&counters[CNT_RAWM], nGen);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        for (int g = lane; g < nGen; g += 32) {
+            const TriContact tc = S.contacts[S.order[g]];
+            Manifold m; m.np = 0; m.tri = tc.tri;
+            if (type == PB_SPHERE || type == PB_CAPSULE) {
+                if (type == PB_CAPSULE && tc.feature == TF_FACE) {
+                    if (!capsuleTriangleFaceManifold(localPos, localOr, prm.x, prm.y, pos1, or1, mesh, tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
+                } else manifoldFromClosest(pos1, or1, tc, m);
+            } else if (type == PB_BOX) {
+                V3 he = mk3(prm.x, prm.y, prm.z);
+                if (tc.feature == TF_FACE) boxTriangleFaceManifold(localPos, localOr, he, pos1, or1, mesh, tc, m);
+                else if (tc.feature == TF_EDGE && tc.boxFeature != BOXF_FACE) boxEdgeTriangleEdgeManifold(localPos, localOr, he, pos1, or1, mesh, tc, m);
+                else boxFaceTriangleManifold(localPos, localOr, he, pos1, or1, mesh, tc, m);
+            } else {
+                const PbConvexDev& cm = convexes[convexId];
+                V3 sc = mk3(prm.x, prm.y, prm.z);
+                if (tc.feature == TF_FACE) convexTriangleFaceManifold<LimSpill>(localPos, localOr, cm, sc, pos1, or1, mesh, tc, m, &ovf);
+                else convexFaceTriangleManifold<LimSpill>(localPos, localOr, cm, sc, pos1, or1, mesh, tc, m, &ovf);
+            }
+            m.tri = tc.tri;
+            storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
+        }
+        if (ovf) atomicOr(&counters[CNT_CAUSE], PB_CAUSE_SPILL_SCRATCH);
+        __syncwarp();
+    }
+}
+
+// scratch of the spill kernels, allocated the first time a scene could need it (convex meshes / triangle meshes registered)
+static int ensureSpillScratch(pb_ctx* ctx) {
+    int rc;
+    if (!ctx->spillList) {
+        int* p = nullptr;
+        if ((rc = pb_alloc(ctx, &p, 2 * (size_t)PB_SPILL_CAP))) return rc;
+        ctx->spillList = p;
+    }
+    if (!ctx->convexes.empty() && !ctx->spillEpa) {
+        LimSpill::Epa* p = nullptr;
+        if ((rc = pb_alloc(ctx, &p, (size_t)PB_SPILL_GJK_THREADS + 32 * (size_t)PB_SPILL_MESH_WARPS))) return rc;
+        ctx->spillEpa = p;
+    }
+    if (!ctx->triMeshes.empty() && !ctx->spillMesh) {
+        MeshSpillScratch* p = nullptr;
+        if ((rc = pb_alloc(ctx, &p, (size_t)PB_SPILL_MESH_WARPS))) return rc;
+        ctx->spillMesh = p;
+    }
+    return PB_OK;
+}
+
+static void launchSpill(pb_ctx* ctx, const int2* pairs, int* counters, int4* mKey, float4* mNormal, float4* mPts, int cap) {
+    if (!ctx->convexes.empty())
+        ++ctx->launches, k_np_gjk_spill<<<1, PB_SPILL_GJK_THREADS, 0, ctx->stream>>>(pairs, ctx->spillList, counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat,
+            ctx->convexDev, ctx->colMesh, (LimSpill::Epa*)ctx->spillEpa, mKey, mNormal, mPts, cap);
+    if (!ctx->triMeshes.empty())
+        ++ctx->launches, k_np_mesh_spill<<<PB_SPILL_MESH_WARPS / 4, 128, 0, ctx->stream>>>(pairs, ctx->spillList + PB_SPILL_CAP, counters, ctx->colType, ctx->colParams, ctx->colMesh,
+            ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, (MeshSpillScratch*)ctx->spillMesh, (LimSpill::Epa*)ctx->spillEpa, mKey, mNormal, mPts, cap);
 }
 
 // ---- trigger pairs (Physecs.cpp:200-207) --------------------------------------------------------------------------------
@@ -593,7 +886,7 @@ __global__ void __launch_bounds__(128) k_np_trigger(const int2* __restrict__ pai
         int slot = warpReserve(hit ? 1 : 0, &counters[CNT_TRIGGERS]);
         if (hit) {
             if (slot < maxTrig) trigPairs[slot] = p;
-            else atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+            else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_TRIGGERS); }
         }
     }
 }
@@ -641,7 +934,7 @@ static int npGrid(pb_ctx* ctx, K kernel, int threads, bool heavy = false) {
 
 static void launchMeshLight(pb_ctx* ctx, const int2* pairs, const int* pairOrder, int* counters, int4* mKey, float4* mNormal, float4* mPts, int cap, int blocksOverride) {
 #define LAUNCH_LIGHT(TYPE) ++ctx->launches, k_np_mesh_light<TYPE><<<blocksOverride ? blocksOverride : npGrid(ctx, k_np_mesh_light<TYPE>, 32 * ML_WARPS), 32 * ML_WARPS, 0, ctx->stream>>>( \
-        pairs, pairOrder, counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, mKey, mNormal, mPts, cap)
+        pairs, pairOrder, counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, mKey, mNormal, mPts, cap, ctx->spillList + PB_SPILL_CAP)
     LAUNCH_LIGHT(PB_CAPSULE); LAUNCH_LIGHT(PB_SPHERE);
 #undef LAUNCH_LIGHT
 }
@@ -649,16 +942,17 @@ static void launchMeshLight(pb_ctx* ctx, const int2* pairs, const int* pairOrder
 int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts) {
     const int blocks = 8;
     int* pairBin = pairOrder + cap;
+    { int rc = ensureSpillScratch(ctx); if (rc) return rc; }
     ++ctx->launches, k_query_classify<<<blocks, 256, 0, ctx->stream>>>(pairs, pairBin, counters, cap, ctx->colType);
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(counters);
     ++ctx->launches, k_pair_scatter<<<1, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, pairOrder, counters, cap);
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<blocks, 128, 0, ctx->stream>>>(pairs, pairOrder, counters, ctx->colType, ctx->colParams, \
-        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, mKey, mNormal, mPts, cap)
+        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, mKey, mNormal, mPts, cap, ctx->spillList)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
     if (!ctx->convexes.empty()) LAUNCH_PRIM(BIN_GJK);
 #undef LAUNCH_PRIM
 #define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<blocks, 128, 0, ctx->stream>>>(pairs, pairOrder, counters, ctx->colType, ctx->colParams, ctx->colMesh, \
-        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, mKey, mNormal, mPts, cap)
+        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, mKey, mNormal, mPts, cap, ctx->spillList + PB_SPILL_CAP)
     if (!ctx->triMeshes.empty()) {
         if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
         LAUNCH_MESH(PB_BOX);
@@ -666,6 +960,7 @@ int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pai
         else launchMeshLight(ctx, pairs, pairOrder, counters, mKey, mNormal, mPts, cap, blocks);
     }
 #undef LAUNCH_MESH
+    launchSpill(ctx, pairs, counters, mKey, mNormal, mPts, cap);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
@@ -674,6 +969,7 @@ int pb_narrowphase(pb_ctx* ctx) {
     if (ctx->nCol < 2) return PB_OK;
     int blocks = ctx->numSMs * 8;
     int* pairBin = ctx->pairOrder + ctx->caps.max_pairs;   // second half of the pairOrder allocation
+    { int rc = ensureSpillScratch(ctx); if (rc) return rc; }
     ++ctx->launches, k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
                                                       ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding,
                                                       ctx->colClass, ctx->filterLut, ctx->nFilterClasses);
@@ -681,7 +977,7 @@ int pb_narrowphase(pb_ctx* ctx) {
     ++ctx->launches, k_pair_scatter<<<ctx->numSMs * 2, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<npGrid(ctx, k_np_prim<BIN>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
-        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
+        ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, ctx->spillList)
     LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
     if (!ctx->convexes.empty()) {
         // hit list: one entry per intersecting pair, i.e. per manifold of the bin -> the manifold capacity bounds it
@@ -695,11 +991,11 @@ int pb_narrowphase(pb_ctx* ctx) {
                                                                      ctx->convexDev, ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap);
         ++ctx->launches, k_np_gjk_manifolds<<<npGrid(ctx, k_np_gjk_manifolds, 128, true), 128, 0, ctx->stream>>>(pairs, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat, ctx->convexDev,
                                                                           ctx->colMesh, ctx->gjkHitPair, ctx->gjkHitSimplex, ctx->gjkHitCap, ctx->mKey, ctx->mNormal, ctx->mPts,
-                                                                          ctx->caps.max_manifolds);
+                                                                          ctx->caps.max_manifolds, ctx->spillList);
     }
 #undef LAUNCH_PRIM
 #define LAUNCH_MESH(TYPE) ++ctx->launches, k_np_mesh<TYPE><<<npGrid(ctx, k_np_mesh<TYPE>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
-        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds)
+        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, ctx->convexDev, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, ctx->spillList + PB_SPILL_CAP)
     if (!ctx->triMeshes.empty()) {
         // heavy shapes first: their long threads overlap with the tail of nothing else, the light bins fill in after
         if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
@@ -708,6 +1004,7 @@ int pb_narrowphase(pb_ctx* ctx) {
         else launchMeshLight(ctx, pairs, ctx->pairOrder, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, 0);
     }
 #undef LAUNCH_MESH
+    launchSpill(ctx, pairs, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);
     if (ctx->triggersPossible)
         ++ctx->launches, k_np_trigger<<<npGrid(ctx, k_np_trigger, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, ctx->colWPos,
                                                     ctx->colWQuat, ctx->convexDev, ctx->trigPairs, ctx->caps.max_pairs);

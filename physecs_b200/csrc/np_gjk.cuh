@@ -6,16 +6,17 @@
 //   EPA                          src/EPA.h:22-186 (incl. the witness-point quirk at :133, Q11, and float narrowing at :70-71)
 //   manifold generators          src/Collision.cpp:352-426 (convex-convex), :488-499 (sphere-convex),
 //                                :694-807 (capsule-convex), :809-887 (box-convex)
-// One thread per pair; simplex / polytope live in per-thread local memory (<= 104 vertices, <= 256 faces).
+// One thread per pair; simplex / polytope live in per-thread local memory (<= 104 vertices -- 4 + the 100 iterations EPA.h:172 allows --,
+// <= 256 faces, <= 64 horizon edges, clip polygons of <= 24 points: `LimFast`).  The reference's containers are unbounded
+// (std::vector polytope, EPA.h:22-124; 128-point clip buffers, Clipping.cpp:6): a pair that outgrows the fast limits reports the
+// cause through `ovf` (no result is stored) and is redone by a spill kernel with `LimSpill`: the polytope in global-memory scratch
+// (2048 faces, 1024 horizon edges), 128-point polygons.  Same routines, same arithmetic -- only the container bounds differ.
 #pragma once
 #include "np_clip.cuh"
 #include "pb_ctx.h"
 
 #define PB_STATUS_UNSUPPORTED_SHAPE 0x100
 #define EPA_MAX_VERTS 104
-#define EPA_MAX_FACES 256
-#define EPA_MAX_LOOSE 64
-#define GJK_POLY 24
 
 struct D3 { double x, y, z; };
 __device__ __forceinline__ D3 mkd(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -161,23 +162,34 @@ static __device__ __noinline__ bool gjk(const Shape& s0, const Shape& s1, V3 sta
 
 // ---- EPA -------------------------------------------------------------------------------------------------------------
 struct EpaFace { unsigned char i0, i1, i2; D3 n; };
-struct Epa {
+template <int NF, int NL>
+struct EpaT {
+    static constexpr int MAX_FACES = NF, MAX_LOOSE = NL;
     GjkV v[EPA_MAX_VERTS]; int nv;
-    EpaFace f[EPA_MAX_FACES]; int nf;
-    bool overflow;
+    EpaFace f[NF]; int nf;
+    unsigned char le0[NL], le1[NL];     // horizon ("loose") edges of the vertex being inserted
+    int overflow;                       // PB_CAUSE_SPILLED_* bits
 };
-__device__ __forceinline__ void epaCreateFace(Epa& p, int i0, int i1, int i2) {
+// container bounds of the per-pair routines: the per-thread fast path and the spill kernels' global-memory scratch
+struct LimFast  { typedef EpaT<256, 64> Epa;    static constexpr int POLY = 24; };
+struct LimSpill { typedef EpaT<2048, 1024> Epa; static constexpr int POLY = 128; };   // POLY == the reference's own bound (Clipping.cpp:6)
+typedef LimFast::Epa Epa;
+
+template <class E>
+__device__ __forceinline__ void epaCreateFace(E& p, int i0, int i1, int i2) {
     D3 a = mkd(p.v[i0].pos), b = mkd(p.v[i1].pos), c = mkd(p.v[i2].pos);
     D3 n = dcross(a - b, c - b);
     double len = sqrt(ddot(n, n));
     if (len) n = n / len;
-    if (p.nf < EPA_MAX_FACES) { EpaFace& F = p.f[p.nf++]; F.i0 = (unsigned char)i0; F.i1 = (unsigned char)i1; F.i2 = (unsigned char)i2; F.n = n; }
-    else p.overflow = true;
+    if (p.nf < E::MAX_FACES) { EpaFace& F = p.f[p.nf++]; F.i0 = (unsigned char)i0; F.i1 = (unsigned char)i1; F.i2 = (unsigned char)i2; F.n = n; }
+    else p.overflow |= PB_CAUSE_SPILLED_EPA_FACES;
 }
 
-// returns the EPA normal; cp0 / cp1 = witness points (with the reference's projection quirk)
-static __device__ __noinline__ V3 epa(const Shape& s0, const Shape& s1, const GjkV* s, V3& cp0, V3& cp1, Epa& p, int* counters) {
-    p.nv = 4; p.nf = 0; p.overflow = false;
+// returns the EPA normal; cp0 / cp1 = witness points (with the reference's projection quirk).  *ovf collects PB_CAUSE_SPILLED_* bits
+// when a container bound was hit (the result is then not the reference's and must not be used).
+template <class E>
+static __device__ __noinline__ V3 epa(const Shape& s0, const Shape& s1, const GjkV* s, V3& cp0, V3& cp1, E& p, int* ovf) {
+    p.nv = 4; p.nf = 0; p.overflow = 0;
     for (int i = 0; i < 4; ++i) p.v[i] = s[i];
     {
         D3 a = mkd(p.v[0].pos), b = mkd(p.v[1].pos), c = mkd(p.v[2].pos), d = mkd(p.v[3].pos);
@@ -198,7 +210,7 @@ static __device__ __noinline__ V3 epa(const Shape& s0, const Shape& s1, const Gj
         GjkV v = minkowski(s0, s1, tof(normal));
         if (ddot(mkd(v.pos), normal) - (double)minDist < (double)0.00001f) break;
         // insertVertex (EPA.h:83-124)
-        unsigned char le0[EPA_MAX_LOOSE], le1[EPA_MAX_LOOSE];
+        unsigned char* le0 = p.le0; unsigned char* le1 = p.le1;
         int nl = 0;
         D3 vp = mkd(v.pos);
         for (int i = p.nf - 1; i >= 0; --i) {
@@ -217,17 +229,17 @@ static __device__ __noinline__ V3 epa(const Shape& s0, const Shape& s1, const Gj
                 }
                 for (int j = 0; j < 3; ++j) {
                     if (found[j]) continue;
-                    if (nl < EPA_MAX_LOOSE) { le0[nl] = e0[j]; le1[nl] = e1[j]; ++nl; } else p.overflow = true;
+                    if (nl < E::MAX_LOOSE) { le0[nl] = e0[j]; le1[nl] = e1[j]; ++nl; } else p.overflow |= PB_CAUSE_SPILLED_EPA_LOOSE;
                 }
                 p.f[i] = p.f[p.nf - 1]; --p.nf;
             }
         }
-        if (p.nv >= EPA_MAX_VERTS) { p.overflow = true; break; }
+        if (p.nv >= EPA_MAX_VERTS) { p.overflow |= PB_CAUSE_SPILLED_EPA_VERTS; break; }     // unreachable: 4 + 100 iterations
         int vi = p.nv;
         p.v[p.nv++] = v;
         for (int e = 0; e < nl; ++e) epaCreateFace(p, vi, le0[e], le1[e]);
     }
-    if (p.overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+    *ovf |= p.overflow;
     // getClosestPoints (EPA.h:126-168)
     if (faceIndex >= p.nf) faceIndex = p.nf - 1;
     if (faceIndex < 0) { cp0 = s0.pos; cp1 = s1.pos; return tof(normal); }
@@ -269,8 +281,10 @@ __device__ inline int pickConvexFace(const PbConvexDev& cm, const M3& toWorld, Q
 }
 
 // Collision.cpp:352-412
+template <class L>
 static __device__ __noinline__ void convexConvexContacts(V3 pos0, Q4 or0, const PbConvexDev& m0, V3 sc0, V3 pos1, Q4 or1, const PbConvexDev& m1, V3 sc1,
-                                            V3 normal, Manifold& m, int* counters) {
+                                            V3 normal, Manifold& m, int* ovf) {
+    constexpr int GJK_POLY = L::POLY;
     M3 dummy;
     int f0 = pickConvexFace(m0, dummy, or0, true, sc0, normal, true);
     int f1 = pickConvexFace(m1, dummy, or1, true, sc1, normal, false);
@@ -286,7 +300,7 @@ static __device__ __noinline__ void convexConvexContacts(V3 pos0, Q4 or0, const 
     M3 c0ToRef = transpose(basis);
     M3 worldToRef = mul(c0ToRef, worldToC0);
     V2 clip[GJK_POLY];
-    if (n0 > GJK_POLY || n1 > GJK_POLY) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); m.np = 0; return; }
+    if (n0 > GJK_POLY || n1 > GJK_POLY) { *ovf |= PB_CAUSE_SPILLED_CLIP; m.np = 0; return; }
     for (int i = 0; i < n0; ++i) {
         V3 v = mul(c0ToRef, sc0 * mk3(m0.verts[m0.faceIndices[o0 + i]]));
         clip[i] = mk2(v.z, v.x);
@@ -297,7 +311,7 @@ static __device__ __noinline__ void convexConvexContacts(V3 pos0, Q4 or0, const 
         poly.p[i] = mk2(v.z, v.x);
     }
     suthHodgClip<GJK_POLY, GJK_POLY>(poly, clip, n0);
-    if (poly.overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+    if (poly.overflow) *ovf |= PB_CAUSE_SPILLED_CLIP;
     V3 incOrigin = mul(worldToRef, pos1 + rotate(or1, sc1 * mk3(m1.faceCentroid[f1])) - pos0);
     V3 incNormal = mul(worldToRef, rotate(or1, normalize(mk3(m1.faceNormal[f1]) / sc1)));
     M3 refToWorld = transpose(worldToRef);
@@ -305,8 +319,10 @@ static __device__ __noinline__ void convexConvexContacts(V3 pos0, Q4 or0, const 
 }
 
 // Collision.cpp:694-785
+template <class L>
 static __device__ __noinline__ void capsuleConvexContacts(V3 p0L, V3 p1L, float radius, V3 meshPos, const M3& convexToWorld, const PbConvexDev& cm, V3 sc,
-                                             Manifold& m, int* counters) {
+                                             Manifold& m, int* ovf) {
+    constexpr int GJK_POLY = L::POLY;
     Q4 qdummy;
     int f = pickConvexFace(cm, convexToWorld, qdummy, false, sc, m.n, false);
     V3 refOrigin = sc * mk3(cm.faceCentroid[f]);
@@ -317,7 +333,7 @@ static __device__ __noinline__ void capsuleConvexContacts(V3 p0L, V3 p1L, float 
     M3 basis; basis.c[0] = u0; basis.c[1] = u1; basis.c[2] = u2;
     M3 convexToRef = transpose(basis);
     V2 clip[GJK_POLY];
-    if (n > GJK_POLY) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); m.np = 0; return; }
+    if (n > GJK_POLY) { *ovf |= PB_CAUSE_SPILLED_CLIP; m.np = 0; return; }
     for (int i = 0; i < n; ++i) {
         V3 v = mul(convexToRef, sc * mk3(cm.verts[cm.faceIndices[o + i]]));
         clip[i] = mk2(v.z, v.x);
@@ -347,8 +363,10 @@ static __device__ __noinline__ void capsuleConvexContacts(V3 p0L, V3 p1L, float 
 }
 
 // Collision.cpp:809-871
+template <class L>
 static __device__ __noinline__ void boxConvexContacts(V3 boxCenter, const M3& boxBasis, V3 he, V3 cPos, Q4 cOr, const PbConvexDev& cm, V3 sc, V3 normal,
-                                         Manifold& m, int* counters) {
+                                         Manifold& m, int* ovf) {
+    constexpr int GJK_POLY = L::POLY;
     int boxAxis = 0; float boxAxisSign = 0.f, maxDot = 0.f;
     for (int i = 0; i < 3; ++i) {
         float d = dot(normal, boxBasis.c[i]);
@@ -360,7 +378,7 @@ static __device__ __noinline__ void boxConvexContacts(V3 boxCenter, const M3& bo
     int o = cm.faceOffsets[f], n = cm.faceOffsets[f + 1] - o;
     int clipX = (boxAxis + 1) % 3, clipY = (boxAxis + 2) % 3;
     M3 worldToBox = transpose(boxBasis);
-    if (n > GJK_POLY) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); m.np = 0; return; }
+    if (n > GJK_POLY) { *ovf |= PB_CAUSE_SPILLED_CLIP; m.np = 0; return; }
     Poly<GJK_POLY> poly; poly.n = n; poly.overflow = false;
     for (int i = 0; i < n; ++i) {
         V3 v = mul(worldToBox, cPos + rotate(cOr, sc * mk3(cm.verts[cm.faceIndices[o + i]])) - boxCenter);
@@ -369,7 +387,7 @@ static __device__ __noinline__ void boxConvexContacts(V3 boxCenter, const M3& bo
     float hx = get(he, clipX), hy = get(he, clipY);
     V2 clip[4] = { mk2(hx, hy), mk2(hx, -hy), mk2(-hx, -hy), mk2(-hx, hy) };
     suthHodgClip<GJK_POLY, 4>(poly, clip, 4);
-    if (poly.overflow) atomicOr(&counters[CNT_STATUS], PB_ECAPACITY);
+    if (poly.overflow) *ovf |= PB_CAUSE_SPILLED_CLIP;
     V3 incOrig = mul(worldToBox, cPos + rotate(cOr, sc * mk3(cm.faceCentroid[f])) - boxCenter);
     V3 incNormal = normalize(mul(worldToBox, rotate(cOr, mk3(cm.faceNormal[f]) / sc)));
     contactsPolygonBoxFace<GJK_POLY>(boxCenter, boxBasis, boxAxis, boxAxisSign, he, incOrig, incNormal, poly, clipX, clipY, m.p0, m.p1, m.np);
@@ -398,17 +416,18 @@ __device__ inline bool gjkPairIntersect(const GjkPair& g, const PbConvexDev* con
     Shape sb = makeShape(g.tb, g.qb, g.pb, g.ob, convexes, g.mb);
     return gjk(sa, sb, g.pb - g.pa, simplex);
 }
-// stage 2: penetration by EPA, then the contact patch of the shape combination
-__device__ inline void gjkPairManifold(const GjkPair& g, const PbConvexDev* convexes, const GjkV* simplex, Manifold& m, int* counters) {
+// stage 2: penetration by EPA, then the contact patch of the shape combination.  `poly` = polytope scratch (local memory for LimFast,
+// global-memory scratch for LimSpill); *ovf != 0 afterwards: a container bound was hit, m is not to be used.
+template <class L>
+__device__ inline void gjkPairManifold(const GjkPair& g, const PbConvexDev* convexes, const GjkV* simplex, Manifold& m, typename L::Epa& poly, int* ovf) {
     Shape sa = makeShape(g.ta, g.qa, g.pa, g.oa, convexes, g.ma);
     Shape sb = makeShape(g.tb, g.qb, g.pb, g.ob, convexes, g.mb);
     const int ta = g.ta, ma = g.ma, mb = g.mb;
     const float4 qa = g.qa, qb = g.qb;
     const V3 pa = g.pa, pb = g.pb;
     const Q4 oa = g.oa, ob = g.ob;
-    Epa poly;
     V3 cp0, cp1;
-    m.n = epa(sa, sb, simplex, cp0, cp1, poly, counters);
+    m.n = epa(sa, sb, simplex, cp0, cp1, poly, ovf);
     m.p0[0] = cp0; m.p1[0] = cp1;
     V3 scb = mk3(qb.x, qb.y, qb.z);
     const PbConvexDev& cb = convexes[mb];
@@ -420,29 +439,30 @@ __device__ inline void gjkPairManifold(const GjkPair& g, const PbConvexDev* conv
         V3 p = mul(worldToConvex, pa - pb);
         V3 axisLc = mul(worldToConvex, capsuleAxis);
         Manifold t = m;
-        capsuleConvexContacts(p + axisLc * qa.x, p - axisLc * qa.x, qa.y, pb, convexToWorld, cb, scb, t, counters);
+        capsuleConvexContacts<L>(p + axisLc * qa.x, p - axisLc * qa.x, qa.y, pb, convexToWorld, cb, scb, t, ovf);
         if (t.np) { m = t; } else m.np = 1;
         return;
     }
     if (ta == PB_BOX) {
         Manifold t = m;
-        boxConvexContacts(pa, mat3_cast(oa), mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, counters);
+        boxConvexContacts<L>(pa, mat3_cast(oa), mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, ovf);
         if (t.np) { m = t; } else m.np = 1;
         return;
     }
     // convex - convex
     Manifold t = m;
-    convexConvexContacts(pa, oa, convexes[ma], mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, counters);
+    convexConvexContacts<L>(pa, oa, convexes[ma], mk3(qa.x, qa.y, qa.z), pb, ob, cb, scb, m.n, t, ovf);
     if (t.np) { m = t; } else m.np = 1;
 }
 
-// both stages in one call (scene queries, where the handful of pairs does not warrant two launches)
+// both stages in one call (scene queries, where the handful of pairs does not warrant two launches; the spill kernel)
+template <class L>
 __device__ inline bool collideGjkPair(int t0, float4 q0, V3 pos0, Q4 or0, int mesh0, int t1, float4 q1, V3 pos1, Q4 or1, int mesh1,
-                                      const PbConvexDev* convexes, Manifold& m, bool& flip, int* counters) {
+                                      const PbConvexDev* convexes, Manifold& m, bool& flip, typename L::Epa& poly, int* ovf) {
     GjkPair g = gjkPairSetup(t0, q0, pos0, or0, mesh0, t1, q1, pos1, or1, mesh1);
     flip = g.flip;
     GjkV simplex[4];
     if (!gjkPairIntersect(g, convexes, simplex)) return false;
-    gjkPairManifold(g, convexes, simplex, m, counters);
+    gjkPairManifold<L>(g, convexes, simplex, m, poly, ovf);
     return true;
 }

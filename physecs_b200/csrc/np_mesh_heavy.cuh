@@ -172,11 +172,12 @@ __device__ inline void boxEdgeTriangleEdgeManifold(V3 boxPos, Q4 boxOr, V3 he, V
 }
 
 // ---- convex mesh vs triangle ---------------------------------------------------------------------------------------------
-__device__ inline bool convexTriangle(const Shape& convex, V3 a, V3 b, V3 c, V3 centroid, TriContact& tc, Epa& scratch, int* counters) {
+template <class E>
+__device__ inline bool convexTriangle(const Shape& convex, V3 a, V3 b, V3 c, V3 centroid, TriContact& tc, E& scratch, int* ovf) {
     Shape tri; tri.type = 5; tri.pos = centroid; tri.basis.c[0] = a; tri.basis.c[1] = b; tri.basis.c[2] = c; tri.prm = mk3(0.f); tri.verts = nullptr; tri.nVertsPadded = 0;
     GjkV s[4];
     if (!gjk(convex, tri, centroid - convex.pos, s)) return false;
-    tc.normal = epa(convex, tri, s, tc.cpBody, tc.cpTri, scratch, counters);
+    tc.normal = epa(convex, tri, s, tc.cpBody, tc.cpTri, scratch, ovf);
     tc.dist = dot(tc.cpTri - tc.cpBody, tc.normal);
     V3 v0 = b - a, v1 = c - a, v2 = tc.cpTri - a;
     float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
@@ -200,21 +201,24 @@ __device__ inline bool convexTriangle(const Shape& convex, V3 a, V3 b, V3 c, V3 
 }
 
 // CTM.cpp:701-755
+template <class L>
 __device__ inline void convexTriangleFaceManifold(V3 cPos, Q4 cOr, const PbConvexDev& cm, V3 sc, V3 meshPos, Q4 meshOr, const PbTriMeshDev& mesh,
-                                                  const TriContact& tc, Manifold& m, int* counters) {
+                                                  const TriContact& tc, Manifold& m, int* ovf) {
+    constexpr int GJK_POLY = L::POLY;
     TriFrame f = triFrame(mesh, tc.tri, false);
     V2 clip[3];
     for (int i = 0; i < 3; ++i) { V3 v = mul(f.meshToRef, f.va[i]); clip[3 - i - 1] = mk2(v.z, v.x); }
     M3 dummy;
     int face = pickConvexFace(cm, dummy, cOr, true, sc, f.n, false);
     int o = cm.faceOffsets[face], n = cm.faceOffsets[face + 1] - o;
-    if (n > GJK_POLY) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); m.np = 0; return; }
+    if (n > GJK_POLY) { *ovf |= PB_CAUSE_SPILLED_CLIP; m.np = 0; return; }
     Poly<GJK_POLY> poly; poly.n = n; poly.overflow = false;
     for (int i = 0; i < n; ++i) {
         V3 v = mul(f.meshToRef, cPos + rotate(cOr, sc * mk3(cm.verts[cm.faceIndices[o + i]])));
         poly.p[i] = mk2(v.z, v.x);
     }
     suthHodgClip<GJK_POLY, 3>(poly, clip, 3);
+    if (poly.overflow) *ovf |= PB_CAUSE_SPILLED_CLIP;
     V3 incOrigin = mul(f.meshToRef, cPos + rotate(cOr, sc * mk3(cm.faceCentroid[face])));
     V3 incNormal = mul(f.meshToRef, rotate(cOr, normalize(mk3(cm.faceNormal[face]) / sc)));
     M3 meshToWorld = mat3_cast(meshOr);
@@ -226,8 +230,10 @@ __device__ inline void convexTriangleFaceManifold(V3 cPos, Q4 cOr, const PbConve
 }
 
 // CTM.cpp:757-824
+template <class L>
 __device__ inline void convexFaceTriangleManifold(V3 cPos, Q4 cOr, const PbConvexDev& cm, V3 sc, V3 meshPos, Q4 meshOr, const PbTriMeshDev& mesh,
-                                                  const TriContact& tc, Manifold& m, int* counters) {
+                                                  const TriContact& tc, Manifold& m, int* ovf) {
+    constexpr int GJK_POLY = L::POLY;
     int4 ti = mesh.tris[tc.tri];
     int idx[3] = { ti.x, ti.y, ti.z };
     V3 centroid = mk3(mesh.triCentroid[tc.tri]), triN = mk3(mesh.triNormal[tc.tri]);
@@ -243,12 +249,13 @@ __device__ inline void convexFaceTriangleManifold(V3 cPos, Q4 cOr, const PbConve
     M3 basis; basis.c[0] = u0; basis.c[1] = u1; basis.c[2] = u2;
     M3 convexToRef = transpose(basis);
     M3 meshToRef = mul(convexToRef, meshToConvex);
-    if (n > GJK_POLY) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); m.np = 0; return; }
+    if (n > GJK_POLY) { *ovf |= PB_CAUSE_SPILLED_CLIP; m.np = 0; return; }
     V2 clip[GJK_POLY];
     for (int i = 0; i < n; ++i) { V3 v = mul(convexToRef, sc * mk3(cm.verts[cm.faceIndices[o + i]])); clip[i] = mk2(v.z, v.x); }
     Poly<GJK_POLY> poly; poly.n = 3; poly.overflow = false;
     for (int i = 0; i < 3; ++i) { V3 v = mul(meshToRef, mk3(mesh.verts[idx[i]]) - cPos); poly.p[i] = mk2(v.z, v.x); }
     suthHodgClip<GJK_POLY, GJK_POLY>(poly, clip, n);
+    if (poly.overflow) *ovf |= PB_CAUSE_SPILLED_CLIP;
     V3 incOrigin = mul(meshToRef, centroid - cPos);
     V3 incNormal = mul(meshToRef, triN);
     M3 meshToWorld = mat3_cast(meshOr);

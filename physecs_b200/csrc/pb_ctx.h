@@ -15,6 +15,9 @@
 #define PB_MAX_JOINT_ROWS 8
 #define PB_ISLAND_LOCAL_MAX 1024  // constraints (manifolds + joints) an island may hold and still be solved inside one CTA
 #define PB_KEY_COLORS 128         // solve-order key of a manifold: group * 128 + colour * 2 + (numPoints > 1)
+#define PB_SPILL_CAP 65536        // pairs per spill list (GJK / EPA bin, mesh bins) and step
+#define PB_SPILL_GJK_THREADS 128  // threads of k_np_gjk_spill == polytope scratch slots it owns
+#define PB_SPILL_MESH_WARPS 32    // warps of k_np_mesh_spill == mesh scratch slots (each lane of each warp owns a polytope slot too)
 
 struct PbTriMesh {
     int nVerts = 0, nTris = 0, nNodes = 0;
@@ -29,7 +32,7 @@ struct PbTriMesh {
 };
 
 struct PbConvex {
-    int nVerts = 0, nVertsPadded = 0, nFaces = 0;
+    int nVerts = 0, nVertsPadded = 0, nFaces = 0, maxFaceVerts = 0;
     float4* verts = nullptr;        // padded to x4 by repeating the last vertex (ConvexMesh.cpp:8-10)
     int* faceOffsets = nullptr;     // nFaces+1
     int* faceIndices = nullptr;
@@ -46,7 +49,7 @@ struct PbTriMeshDev {
 };
 struct PbConvexDev {
     const float4* verts; const int* faceOffsets; const int* faceIndices; const float4* faceNormal;
-    const float4* faceCentroid; int nVerts; int nVertsPadded; int nFaces; int pad;
+    const float4* faceCentroid; int nVerts; int nVertsPadded; int nFaces; int maxFaceVerts;
 };
 
 // header of the per-step device counters block (one int each, zeroed at step start)
@@ -54,6 +57,9 @@ enum {
     CNT_PAIRS = 0, CNT_MANIFOLDS, CNT_POINTS, CNT_STATUS, CNT_MESH_PAIRS, CNT_TRIGGERS, CNT_OVERFLOW, CNT_NCOLORS,
     CNT_RAWM,                           // raw manifold arena entries (incl. 0-point holes); CNT_MANIFOLDS = solve count
     CNT_GJK_HITS,                       // GJK-bin pairs whose shapes intersect (stage 2 of the split GJK / EPA launch works on these)
+    CNT_SPILL_GJK, CNT_SPILL_MESH,      // pairs that outgrew the per-thread containers of their bin kernel (redone by the spill kernels)
+    CNT_CAUSE,                          // PB_CAUSE_* bits (include/physecs_b200.h)
+    CNT_SPILLED,                        // pairs the spill kernels redid
     CNT_BIN0 = 16,                      // PB_NUM_BINS bin counters
     CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
     CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
@@ -146,6 +152,8 @@ struct pb_ctx {
     float4* mPts = nullptr;          // [8*maxManifolds]: slot 2k = position0, 2k+1 = position1
     int* mColor = nullptr;           // colour per raw manifold
     int* gjkHitPair = nullptr; float4* gjkHitSimplex = nullptr; int gjkHitCap = 0;   // intersecting GJK-bin pairs + their simplices (9 float4 each)
+    // spill path (narrowphase.cu): pair lists [2][PB_SPILL_CAP] (GJK / EPA bin, mesh bins) + global-memory scratch of the spill kernels
+    int* spillList = nullptr; void* spillEpa = nullptr; void* spillMesh = nullptr;
     int* mSorted = nullptr;          // [maxManifolds] raw index per solve slot
     unsigned int* mSortKeyA = nullptr; unsigned int* mSortKeyB = nullptr; int* mSortValB = nullptr;
 
@@ -205,6 +213,14 @@ struct pb_ctx {
     // persistent substep kernel (solver.cu)
     int solveGrid = 0; unsigned int* solveBarrier = nullptr; unsigned long long* solveProfNs = nullptr;
     bool countsStale = false;        // lastCounts lacks the post-build numbers until the counters are read back
+    // A step is enqueued without a host sync: the arena checks happen on the device (a step that overflowed skips its solve and leaves
+    // the scene untouched) and the host COLLECTS the outcome -- counters snapshot, status -- at the next call that synchronises with the
+    // step (capi.cu collectStep).  stepPending: a step's outcome has not been collected yet; undo*: host bookkeeping to roll back then.
+    cudaEvent_t evCounters = nullptr; bool stepPending = false;
+    int rawHint = -1;                // raw manifold count of the last collected step (-1: none yet): shapes grids only
+    bool undoCacheValid = false, undoCacheBuilt = false; int undoVelSwaps = 0;
+    std::vector<int> hTrimeshCols;   // colliders of type PB_TRIANGLE_MESH (their bounds are a vertex reduction each)
+    std::vector<int> hKinematic;     // host mirror of `kinematic` (which trimesh colliders ride on moving bodies)
     unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
     bool profile = false;            // per-phase device timing inside the persistent substep kernel (pb_set_profile)
 };
@@ -229,15 +245,15 @@ int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending pb_set
 int pb_wait_poses(pb_ctx* ctx);        // ... for its pose half only
 int pb_broadphase(pb_ctx* ctx);
 int pb_build_tree(pb_ctx* ctx, bool forStep = false);
-int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic);
+int pb_update_bounds_all(pb_ctx* ctx, float margin, int onlyDynamic, const int* skipStatus = nullptr);
 int pb_update_bounds_rows(pb_ctx* ctx, const int* dRowMark, int n, float margin);
 int pb_update_bounds_trimesh_col(pb_ctx* ctx, int col, float margin);
 int pb_world_poses(pb_ctx* ctx);
 int pb_narrowphase(pb_ctx* ctx);
 // the same bin kernels on a private arena: pairs (collider, query collider slot) -> manifolds, no filters (queries.cu)
 int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts);
-int pb_contact_build(pb_ctx* ctx, int nRaw);
-int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound);
+int pb_contact_build(pb_ctx* ctx);
+int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
 int pb_solve_profile(pb_ctx* ctx, unsigned long long* out, bool reset);
 int pb_solve_profile_colors(pb_ctx* ctx, unsigned long long* out128);
 int pb_joint_begin_step(pb_ctx* ctx);
@@ -250,3 +266,4 @@ void pb_contact_cache_rehash(pb_ctx* ctx, int oldSize, const unsigned long long*
 int pb_radix_sort_pairs(pb_ctx* ctx, unsigned int* keysA, int* valsA, unsigned int* keysB, int* valsB, int n, int bits,
                         unsigned int* hist, int histCapTiles, bool* resultInA);
 int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch);
+int pb_exclusive_scan_dev(pb_ctx* ctx, const int* in, int* out, const int* nDev, int cap, int bound, int* scratch);

@@ -133,6 +133,89 @@ int pb_exclusive_scan(pb_ctx* ctx, const int* in, int* out, int n, int* scratch)
     return PB_OK;
 }
 
+// The same scan over a DEVICE-side element count (*nDev, clamped to cap): the launch shape follows the capacity, blocks past the
+// count only publish a zero block sum.  Lets a step order its manifolds without the host ever reading how many there are.
+__global__ void k_scan_reduce_dev(const int* __restrict__ in, int* __restrict__ blockSums, const int* __restrict__ nDev, int cap) {
+    const int n = min(*nDev, cap);
+    if (blockIdx.x * SCAN_TILE >= n) { if (threadIdx.x == 0) blockSums[blockIdx.x] = 0; return; }      // uniform per CTA
+    int base = blockIdx.x * SCAN_TILE;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n) s += in[idx];
+    }
+    int total;
+    blockInclusiveScan(s, &total);
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+__global__ void k_scan_final_dev(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ blockSums, const int* __restrict__ nDev, int cap) {
+    const int n = min(*nDev, cap);
+    if (blockIdx.x * SCAN_TILE >= n) return;
+    int base = blockIdx.x * SCAN_TILE;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        v[i] = idx < n ? in[idx] : 0;
+        s += v[i];
+    }
+    int inc = blockInclusiveScan(s, nullptr);
+    int run = blockSums[blockIdx.x] + inc - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n) out[idx] = run;
+        run += v[i];
+    }
+}
+__global__ void k_scan_small_dev(const int* in, int* out, const int* __restrict__ nDev, int cap) {
+    __shared__ int carry;
+    const int n = min(*nDev, cap);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SCAN_TILE) {
+        int v[SCAN_ITEMS];
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int idx = base + threadIdx.x * SCAN_ITEMS + i;
+            v[i] = idx < n ? in[idx] : 0;
+            s += v[i];
+        }
+        int total;
+        int inc = blockInclusiveScan(s, &total);
+        int run = carry + inc - s;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int idx = base + threadIdx.x * SCAN_ITEMS + i;
+            if (idx < n) out[idx] = run;
+            run += v[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+// `bound`: host-side guess of the count (shapes the launch only; any value is correct).  One CTA walks the array while the guess is
+// small, the three-launch form covers the whole capacity otherwise.
+int pb_exclusive_scan_dev(pb_ctx* ctx, const int* in, int* out, const int* nDev, int cap, int bound, int* scratch) {
+    if (cap <= 0) return PB_OK;
+    if (bound < 0 || bound > cap) bound = cap;
+    if (bound <= 8 * SCAN_TILE) {
+        ++ctx->launches, k_scan_small_dev<<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, nDev, cap);
+        PB_CUDA(ctx, cudaGetLastError());
+        return PB_OK;
+    }
+    int nb = (cap + SCAN_TILE - 1) / SCAN_TILE;
+    ++ctx->launches, k_scan_reduce_dev<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, scratch, nDev, cap);
+    ++ctx->launches, k_scan_blocksums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scratch, nb);
+    ++ctx->launches, k_scan_final_dev<<<nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, scratch, nDev, cap);
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 #define RS_WARPS 8
 // keys per warp tile = 32 * RS_ITEMS: 16 rounds per warp for large inputs; 4 for small ones, where a 512-key tile would leave

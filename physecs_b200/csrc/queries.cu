@@ -246,7 +246,8 @@ int pb_query_overlap_mtd(pb_ctx* ctx, const float* pos3, const float* quat4, int
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int nPairs = hc[CNT_PAIRS], nM = hc[CNT_RAWM];
     if (nPairs > cap || nM > cap || nM > outCap) { *nHits = (nPairs > nM ? nPairs : nM) + PB_MAX_TRI_CONTACTS; return PB_OK; }   // caller retries with that capacity
-    if (hc[CNT_STATUS] & PB_ECAPACITY) return pb_fail(ctx, PB_ECAPACITY, "pb_query_overlap_mtd: the query shape meets more triangles of one mesh than a (shape, mesh) pair may hold");
+    // (a query shape that meets more triangles / needs a larger polytope than the per-thread containers hold went through the spill kernels)
+    if (hc[CNT_STATUS] & PB_ECAPACITY) { *nHits = 2 * cap + PB_MAX_TRI_CONTACTS; return PB_OK; }      // a manifold slot past the arena: retry larger
     if (nM == 0) return PB_OK;
     std::vector<int4> key((size_t)nM); std::vector<float4> nrm((size_t)nM), pts((size_t)8 * nM);
     PB_CUDA(ctx, cudaMemcpyAsync(key.data(), ctx->qmKey, sizeof(int4) * nM, cudaMemcpyDeviceToHost, ctx->stream));

@@ -421,14 +421,21 @@ struct GridBarrier {
     }
 };
 
+// The narrowphase overflowed an arena (or met an unsupported shape pair): the step's solve is skipped as a whole -- poses, velocities,
+// joint state and bounds stay what they were, so the host can grow the arenas and run the step again (capi.cu collectStep).
+__device__ __forceinline__ bool stepSkipped(const int* __restrict__ counters) { return (counters[CNT_STATUS] & (PB_ECAPACITY | 0x100)) != 0; }
+
 __global__ void __launch_bounds__(256) k_integrate_v(const __grid_constant__ SubstepParams P) {
+    if (stepSkipped(P.counters)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.nDyn) integrateV(P, i, P.velA, P.angvelA, P.velB, P.angvelB);
 }
 
+// grid-stride: the grid follows the host's guess of the manifold count, the count itself stays on the device
 __global__ void __launch_bounds__(128) k_contact_prep(const __grid_constant__ SubstepParams P) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P.counters[CNT_MANIFOLDS]) contactPrep(P, s, P.velA, P.angvelA);
+    if (stepSkipped(P.counters)) return;
+    const int n = P.counters[CNT_MANIFOLDS];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) contactPrep(P, s, P.velA, P.angvelA);
 }
 
 // Joint routines are called, not inlined: their register appetite (row builders, 3x3 products) then spills inside the
@@ -454,6 +461,7 @@ __device__ __noinline__ void contactSolveSeqCall(const SubstepParams& P, int sta
 
 // joint row fill for every joint of the scene (makeConstraints + effective masses): independent of the joint colours
 __global__ void __launch_bounds__(128) k_joint_fill(const __grid_constant__ SubstepParams P) {
+    if (stepSkipped(P.counters)) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < P.J.n) jointPrepOne(P.J, j, 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.bodyRec, P.pseudoLin, P.pseudoAng);
 }
@@ -597,6 +605,7 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
 __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant__ SubstepParams P) {
     __shared__ int sRuns[PB_KEY_COLORS + 1];
     __shared__ int sJoint[PB_JOINT_COLORS + 1];
+    if (stepSkipped(P.counters)) return;       // uniform over the grid: nobody reaches a barrier
     GridBarrier bar;
     bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
     if (P.profNs && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
@@ -613,6 +622,7 @@ __global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_consta
     __shared__ int sJoint[PB_JOINT_COLORS + 1];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
+    if (stepSkipped(P.counters)) return;
     GridBarrier bar;
     bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
     if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
@@ -632,9 +642,12 @@ __global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_consta
     }
 }
 
-int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity, int workBound) {
+int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
     const int nDyn = ctx->nDyn;
     if (nDyn == 0) return PB_OK;
+    // manifold count as far as the host knows it: the previous step's, with headroom (no step collected yet: the arena capacity).
+    // Shapes grids and picks between equivalent kernels, nothing else -- the kernels read the count from the device.
+    const int workBound = ctx->rawHint < 0 ? ctx->caps.max_manifolds : std::min(ctx->caps.max_manifolds, ctx->rawHint + ctx->rawHint / 4 + 1024);
     if (!ctx->solveGrid) {
         int perSM = 0;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_substep_solve, 256, 0));
@@ -686,12 +699,12 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
         void* args[] = { &P };
         ++ctx->launches;
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small, dim3(fgrid), dim3(256), args, 0, ctx->stream));
-        if (substeps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); }
+        if (substeps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); ++ctx->undoVelSwaps; }
     } else
     for (int sub = 0; sub < substeps; ++sub) {
         P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
         ++ctx->launches, k_integrate_v<<<pb_grid(nDyn, 256), 256, 0, ctx->stream>>>(P);
-        if (workBound > 0) ++ctx->launches, k_contact_prep<<<pb_grid(workBound, 128), 128, 0, ctx->stream>>>(P);
+        ++ctx->launches, k_contact_prep<<<pb_grid(workBound, 128), 128, 0, ctx->stream>>>(P);
         if (P.hasJoints) ++ctx->launches, k_joint_fill<<<pb_grid(ctx->nJoints, 128), 128, 0, ctx->stream>>>(P);
         PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
         void* args[] = { &P };
@@ -700,6 +713,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity,
         // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity of the next substep
         std::swap(ctx->vel, ctx->velLive);
         std::swap(ctx->angvel, ctx->angvelLive);
+        ++ctx->undoVelSwaps;
     }
     cudaEventRecord(ctx->ev[6], ctx->stream);
     PB_CUDA(ctx, cudaGetLastError());

@@ -855,22 +855,27 @@ void Scene::simulate(float timeStep) {
     if (full || !S.touched.empty())
         S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
     S.touched.clear();
-    int rc = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
-    for (int attempt = 0; rc == PB_ECAPACITY && attempt < 4; ++attempt) {
-        // a per-step arena overflowed.  Nothing persistent was touched (poses, bounds and the contact cache change only
-        // after the narrowphase has fitted), so enlarge the arenas in place and run the step again.  The device counters
-        // keep counting past the capacity, so they tell how much room the step needs.
+    // pb_step only enqueues: an arena that overflows is noticed on the device (the step then skips its solve and leaves the scene as it
+    // was) and reported by the next call that synchronises with the step -- pb_get_state here.  Nothing persistent was touched, so the
+    // arenas are enlarged in place and the step is run again.  The device counters keep counting past the capacity, so they tell
+    // how much room the step needs.
+    auto stepAndFetch = [&]() {
+        int r = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
+        if (r == PB_OK) r = pb_get_state(S.ctx, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p);
+        return r;
+    };
+    int rc = stepAndFetch();
+    for (int attempt = 0; rc == PB_ECAPACITY && attempt < 6; ++attempt) {
         pb_counts need{};
         pb_get_counts(S.ctx, &need);
         int wantP = std::max(S.caps.max_pairs, need.n_pairs + need.n_pairs / 2 + 1024);
         int wantM = std::max(S.caps.max_manifolds, need.n_manifolds + need.n_manifolds / 2 + 1024);
-        if (need.n_pairs <= S.caps.max_pairs && need.n_manifolds <= S.caps.max_manifolds) break;   // not an arena problem (triangle contacts per pair)
+        if (need.n_pairs <= S.caps.max_pairs && need.n_manifolds <= S.caps.max_manifolds) break;   // not a pair / manifold arena (pb_last_error names the cause)
         S.check(pb_grow_arenas(S.ctx, wantP, wantM), "pb_grow_arenas");
         S.caps.max_pairs = S.wantPairs = wantP; S.caps.max_manifolds = S.wantManifolds = wantM;
-        rc = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
+        rc = stepAndFetch();
     }
-    S.check(rc, "pb_step");
-    S.check(pb_get_state(S.ctx, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_get_state");
+    S.check(rc, "pb_step / pb_get_state");
     S.stagingValid = true;
 
     // ---- scatter: pinned SoA -> registry (kinematic bodies are not integrated, Physecs.cpp:446, :497) ---------------------------

@@ -809,3 +809,87 @@ def trigger_zoo(n=160, seed=0x7216) -> SceneDesc:
             cols.append(halo)
         b.add_body((x, 1.6 + 1.2 * u[k], z), quat=tuple(qs[2 * i + 1]), colliders=cols, mass=1.0, vel=(0.5 * (u[k + 1] - 0.5), 0, 0.5 * (u[k + 2] - 0.5))); k += 3
     return b.build(substeps=4, iterations=2)
+
+
+# ---- adversarial per-pair workloads: the spill paths of the narrowphase (narrowphase.cu k_np_gjk_spill / k_np_mesh_spill) --------
+def prism(sides=32, half_height=0.5, radius=1.0) -> ConvexMeshDesc:
+    """A `sides`-gon prism ("cylinder"): two faces with `sides` vertices -- more than the 24-point polygons the per-thread clipping holds."""
+    pts = [(radius * math.cos(2 * math.pi * k / sides), y, radius * math.sin(2 * math.pi * k / sides)) for k in range(sides) for y in (-half_height, half_height)]
+    return convex_from_points(np.array(pts, np.float64))
+
+
+def big_on_fine_mesh(cells=80, mesh_spacing=0.1, seed=0xAD, substeps=4, iterations=2) -> SceneDesc:
+    """Large shapes resting on / sunk into a finely tessellated mesh: every (shape, mesh) pair meets hundreds to thousands of
+    triangles (the per-thread path holds 128 candidates / 24 contacts), including a 3 m capsule on a 0.1 m mesh, a flat box,
+    a big sphere, big convex hulls (one with 32-gon faces), next to ordinary small bodies that stay on the fast path."""
+    rng = SplitMix(seed)
+    nv = cells + 1
+    ix, iz = np.meshgrid(np.arange(nv), np.arange(nv), indexing="ij")
+    x = (ix - cells / 2) * mesh_spacing; z = (iz - cells / 2) * mesh_spacing
+    u = rng.uniform(nv * nv, -1, 1).reshape(nv, nv)
+    y = 0.05 * np.sin(1.3 * x) * np.cos(1.1 * z) + 0.01 * u
+    verts = np.stack([x, y, z], -1).reshape(-1, 3).astype(f32)
+    cx, cz = np.meshgrid(np.arange(cells), np.arange(cells), indexing="ij")
+    v00 = (cx * nv + cz).ravel(); v10 = ((cx + 1) * nv + cz).ravel(); v01 = (cx * nv + cz + 1).ravel(); v11 = ((cx + 1) * nv + cz + 1).ravel()
+    tris = np.stack([np.stack([v00, v01, v11], 1), np.stack([v00, v11, v10], 1)], 1).reshape(-1, 3)
+    mesh = TriMeshDesc(verts=np.ascontiguousarray(verts), indices=np.ascontiguousarray(tris.reshape(-1).astype(np.uint32)))
+    b = SceneBuilder("big_on_fine_mesh")
+    tm = b.add_trimesh(mesh)
+    templates = convex_templates()
+    hexp = b.add_convex(templates[3]); dod = b.add_convex(templates[5]); cyl = b.add_convex(prism(32, 0.3, 1.0))
+    b.add_body((0, 0, 0), colliders=[dict(type=TRIANGLE_MESH, params=(0, 0, 0), mesh=tm)], dynamic=False)
+    lying = tuple(axis_angle((0, 0, 1), math.pi / 2))
+    tilted = tuple(axis_angle((1, 0, 0.3), 0.4))
+    b.add_body((-2.0, 0.25, -2.5), quat=lying, colliders=[dict(type=CAPSULE, params=(1.5, 0.3))], mass=8.0)            # 3 m capsule lying on the mesh
+    b.add_body((1.5, 0.9, -2.0), colliders=[dict(type=SPHERE, params=(1.0,))], mass=10.0)                                   # sunk 0.1 m: a wide contact cap
+    b.add_body((-1.0, 0.15, 0.0), colliders=[dict(type=BOX, params=(1.2, 0.2, 0.9))], mass=6.0)                             # flat box: face contacts on ~400 triangles
+    b.add_body((2.0, 0.5, 1.0), quat=tilted, colliders=[dict(type=BOX, params=(0.8, 0.5, 0.6))], mass=6.0)
+    b.add_body((-2.2, 0.45, 2.4), colliders=[dict(type=CONVEX_MESH, params=(1.0, 0.6, 1.0), mesh=hexp)], mass=5.0)         # hexagonal prism, face down
+    b.add_body((0.6, 0.75, 2.6), quat=tilted, colliders=[dict(type=CONVEX_MESH, params=(0.9, 0.9, 0.9), mesh=dod)], mass=5.0)
+    b.add_body((2.4, 0.28, -0.6), colliders=[dict(type=CONVEX_MESH, params=(0.8, 1.0, 0.8), mesh=cyl)], mass=5.0)          # 32-gon cylinder, cap down
+    for k in range(24):      # ordinary bodies: the fast path next to the spilled pairs
+        t = k % 4
+        px, pz = -3.2 + 0.28 * k, 3.4 - 0.05 * k
+        q = tuple(rng.unit_quat(1)[0])
+        if t == SPHERE: col = dict(type=SPHERE, params=(0.07,))
+        elif t == CAPSULE: col = dict(type=CAPSULE, params=(0.06, 0.05))
+        elif t == BOX: col = dict(type=BOX, params=(0.06, 0.05, 0.07))
+        else: col = dict(type=CONVEX_MESH, params=(0.07, 0.07, 0.07), mesh=dod)
+        b.add_body((px, 0.16, pz), quat=q, colliders=[col], mass=0.2)
+    return b.build(substeps=substeps, iterations=iterations)
+
+
+def degenerate_convex(seed=0xDE6, substeps=4, iterations=2) -> SceneDesc:
+    """Convex pairs that stress GJK / EPA and the face clipping: coincident and nested hulls, deep overlaps, needle / plate scales,
+    face-to-face stacks of 32-gon prisms (clip polygons of up to 64 points), prisms against every primitive."""
+    rng = SplitMix(seed)
+    b = SceneBuilder("degenerate_convex")
+    templates = convex_templates()
+    ids = [b.add_convex(m) for m in templates]
+    cyl = b.add_convex(prism(32, 0.4, 0.5)); cyl48 = b.add_convex(prism(48, 0.2, 0.6))
+    b.add_body((0, -1, 0), colliders=[dict(type=BOX, params=(30, 1, 30))], dynamic=False)
+    x = -12.0
+    def place(cols_and_offsets):
+        nonlocal x
+        for col, off, q in cols_and_offsets:
+            b.add_body((x + off[0], off[1], off[2]), quat=q, colliders=[col], mass=1.0)
+        x += 2.0
+    I = (0, 0, 0, 1)
+    for k, cid in enumerate(ids):     # coincident centres, same hull twice (EPA starts from a degenerate simplex)
+        place([(dict(type=CONVEX_MESH, params=(0.4, 0.4, 0.4), mesh=cid), (0, 0.5, 0), I), (dict(type=CONVEX_MESH, params=(0.4, 0.4, 0.4), mesh=cid), (0, 0.5, 0), I)])
+    for k, cid in enumerate(ids):     # nested: a small hull deep inside a big one, slightly off centre
+        q = tuple(rng.unit_quat(1)[0])
+        place([(dict(type=CONVEX_MESH, params=(0.8, 0.8, 0.8), mesh=cid), (0, 0.9, 6), I), (dict(type=CONVEX_MESH, params=(0.15, 0.15, 0.15), mesh=ids[(k + 1) % 6]), (0.01 * k, 0.9, 6.02), q)])
+    x = -12.0
+    for k in range(6):                # needles and plates
+        q = tuple(rng.unit_quat(1)[0])
+        place([(dict(type=CONVEX_MESH, params=(0.02, 0.9, 0.02), mesh=ids[k]), (0, 1.0, -6), q), (dict(type=CONVEX_MESH, params=(0.9, 0.01, 0.9), mesh=ids[(k + 2) % 6]), (0.05, 1.0, -6), I)])
+    x = -12.0
+    tilt = tuple(axis_angle((0, 1, 0), 0.1))
+    # 32 / 48-gon prisms: stacked cap to cap (convex-convex clip of two big faces), on the ground box, under a box, beside a capsule / sphere
+    place([(dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl), (0, 0.39, -12), I), (dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl), (0.1, 1.17, -12), tilt)])
+    place([(dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl48), (0, 0.19, -12), I), (dict(type=CONVEX_MESH, params=(1.2, 1, 0.8), mesh=cyl), (0.05, 0.78, -12), tilt)])
+    place([(dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl48), (0, 0.19, -12), I), (dict(type=BOX, params=(0.3, 0.2, 0.3)), (0.02, 0.58, -12), tilt)])
+    place([(dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl), (0, 0.39, -12), I), (dict(type=CAPSULE, params=(0.3, 0.1)), (0, 0.88, -12), tuple(axis_angle((0, 0, 1), math.pi / 2)))])
+    place([(dict(type=CONVEX_MESH, params=(1, 1, 1), mesh=cyl), (0, 0.39, -12), I), (dict(type=SPHERE, params=(0.2,)), (0.1, 0.97, -12), I)])
+    return b.build(substeps=substeps, iterations=iterations)

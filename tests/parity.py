@@ -174,7 +174,7 @@ def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=Fal
     cmp_bounds = compare_bounds_bulk if bulk else compare_bounds
     cmp_pairs = compare_pairs_bulk if bulk else compare_pairs
     cmp_manifolds = compare_manifolds_bulk if bulk else compare_manifolds
-    summary = dict(steps=0, pairs=0, manifolds=0, worst_manifold=0.0, worst_solve={}, triggers=0, trigger_changes=0)
+    summary = dict(steps=0, pairs=0, manifolds=0, worst_manifold=0.0, worst_solve={}, triggers=0, trigger_changes=0, spilled=0, cause=0)
     prev_trig = set()
     if contact_filter:
         ref.set_contact_filter(contact_filter)
@@ -189,6 +189,8 @@ def run_gates(desc, steps=10, check_every=1, tol=TOL, ref_threads=0, verbose=Fal
             ctx.step()
             gm = ctx.manifolds()
             gp = ctx.pairs()
+            cnt = ctx.counts()
+            summary["spilled"] = max(summary["spilled"], int(cnt.n_spilled)); summary["cause"] |= int(cnt.cause)
             if k % check_every == 0:
                 rm = ref.narrowphase(gp)
                 nm, worst = cmp_manifolds(gm, rm, tol)

@@ -1,0 +1,98 @@
+"""-m gpu: per-pair work beyond the per-thread containers (the spill kernels) and long soaks of the pile configurations.
+
+The reference keeps the EPA polytope, a mesh's overlapping triangles and a pair's triangle contacts in std::vectors
+(EPA.h:22-124, TriangleMesh.cpp:166-192, CollisionTriangleMesh.cpp:893-907).  The device's bin kernels hold them per thread
+(256 faces / 128 candidates / 24 contacts / 24-point polygons); pairs that need more are redone by k_np_gjk_spill /
+k_np_mesh_spill on global-memory scratch.  Here: adversarial scenes where that happens must pass the same three gates as every
+other scene, bit for bit, and the pile configurations (C2, C3) must run for hundreds of steps without a non-OK status.
+"""
+import numpy as np
+import pytest
+
+from physecs_b200 import scenes as S
+from physecs_b200 import capi
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+FATAL_CAUSES = capi.PB_CAUSE_SPILL_LIST | capi.PB_CAUSE_SPILL_SCRATCH | capi.PB_CAUSE_PAIRS | capi.PB_CAUSE_MANIFOLDS | capi.PB_CAUSE_WALK_STACK
+
+
+def test_big_shapes_on_fine_mesh():
+    """A 3 m capsule, a 1 m sphere, flat boxes and big hulls (one with 32-gon faces) on a 0.1 m mesh: hundreds of candidate
+    triangles and contacts per pair."""
+    s = parity.run_gates(S.big_on_fine_mesh(), steps=8)
+    assert s["steps"] == 8 and s["worst_manifold"] == 0.0
+    assert s["spilled"] >= 5, f"the scene was meant to overflow the per-thread containers: {s}"
+    assert s["cause"] & (capi.PB_CAUSE_SPILLED_TRI_CAND | capi.PB_CAUSE_SPILLED_TRI_CONTACTS)
+    assert not s["cause"] & FATAL_CAUSES, hex(s["cause"])
+    print(s)
+
+
+def test_big_shapes_on_fine_mesh_generic_kernels(monkeypatch):
+    """the same through k_np_mesh<sphere|capsule> instead of k_np_mesh_light"""
+    monkeypatch.setenv("PB_MESH_LIGHT", "0")
+    s = parity.run_gates(S.big_on_fine_mesh(), steps=4)
+    assert s["spilled"] >= 5 and not s["cause"] & FATAL_CAUSES
+    assert s["worst_manifold"] == 0.0
+
+
+def test_degenerate_convex_pairs():
+    """Coincident / nested hulls, needles against plates, 32- and 48-gon prism faces (clip polygons beyond 24 points)."""
+    s = parity.run_gates(S.degenerate_convex(), steps=8)
+    assert s["steps"] == 8 and s["worst_manifold"] == 0.0
+    assert s["cause"] & capi.PB_CAUSE_SPILLED_CLIP, f"the prism faces were meant to overflow the 24-point polygons: {s}"
+    assert not s["cause"] & FATAL_CAUSES, hex(s["cause"])
+    print(s)
+
+
+def test_mtd_query_with_a_big_shape():
+    """overlapWithMinTranslationalDistance with query shapes that meet thousands of triangles: the query runs the same bin and spill
+    kernels (Physecs.cpp:652-688 calls collision() per collider); rows compared bit for bit with the reference's Scene."""
+    from oracle.ref import RefScene
+    from physecs_b200 import scene_api
+    d = S.big_on_fine_mesh()
+    ref = RefScene(d, 0, hashfix=True)
+    hs = scene_api.HostScene(d, num_threads=0)
+
+    def rows(res):
+        ids, val = res
+        return sorted(tuple(i) + tuple(v) for i, v in zip(ids.tolist(), val.view(np.int32).tolist()))
+    try:
+        pos = np.array([0.3, 0.2, 0.4], np.float32); quat = np.array([0, 0, 0, 1], np.float32)
+        for typ, prm in ((S.SPHERE, (1.5,)), (S.BOX, (2.0, 0.3, 1.5)), (S.CAPSULE, (1.2, 0.4))):
+            g = rows(hs.overlap_mtd(pos, quat, typ, prm, -1))
+            r = rows(ref.overlap_mtd(pos, quat, typ, prm, -1))
+            assert len(g) == len(r) and len(g) > 24, (typ, len(g), len(r))
+            assert g == r, f"type {typ}: first rows {g[:2]} vs {r[:2]}"
+    finally:
+        hs.close(); ref.close()
+
+
+SOAK = [
+    ("C3_convex_pile_250k", lambda seed: S.convex_pile(250_000, seed=seed), 500),
+    ("C2_mixed_bin_100k", lambda seed: S.mixed_bin(100_000, seed=seed), 500),
+]
+
+
+@pytest.mark.parametrize("name,maker,steps", SOAK, ids=[c[0] for c in SOAK])
+@pytest.mark.parametrize("seed", [0xC3, 0x51, 0x77])
+def test_soak(name, maker, steps, seed):
+    """>= 500 steps per seed: every step's status is OK, nothing exceeds the spill path's bounds, the state stays finite."""
+    from physecs_b200.capi import Context
+    d = maker(seed)
+    ctx = Context(d, max_pairs=32 * d.n + 4096, max_manifolds=12 * d.n + 4096)
+    cause, spilled = 0, 0
+    try:
+        for k in range(steps):
+            ctx.step()            # raises on any non-OK status
+            if k % 10 == 9 or k == steps - 1:
+                c = ctx.counts()
+                cause |= int(c.cause); spilled = max(spilled, int(c.n_spilled))
+                assert c.status == 0
+        P, Q, V, W = ctx.get_state_entities()
+        assert np.isfinite(P).all() and np.isfinite(V).all() and np.isfinite(Q).all() and np.isfinite(W).all()
+    finally:
+        ctx.close()
+    assert not cause & FATAL_CAUSES, hex(cause)
+    print(name, hex(seed), "cause", hex(cause), "max spilled pairs per step", spilled)
