@@ -27,6 +27,7 @@ UNITS = [
     ("islands.cu", []),
     ("queries.cu", ["-fmad=false"]),
     ("trimesh_build.cpp", []),
+    ("batch.cpp", []),
 ]
 
 

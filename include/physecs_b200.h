@@ -184,6 +184,9 @@ int pb_sync(pb_ctx* ctx);
 /* ---- parity / debug taps ----------------------------------------------------------------------------- */
 int pb_get_counts(pb_ctx* ctx, pb_counts* out);
 int pb_get_timings(pb_ctx* ctx, pb_timings* out);
+/* candidate pairs of the last step per narrowphase bin: sphere-sphere, sphere-capsule, capsule-capsule, sphere-box, capsule-box, box-box,
+ * GJK/EPA (any pair with a convex mesh), mesh-sphere, mesh-capsule, mesh-box, mesh-convex, trigger (reference dispatch Collision.cpp:895-1016) */
+int pb_get_bin_counts(pb_ctx* ctx, int* out12);
 /* candidate pairs of the last step as rows (entity0, colIdx0, entity1, colIdx1), entity0 < entity1 */
 int pb_get_pairs(pb_ctx* ctx, int* out4, int cap, int* n);
 /* overlapping TRIGGER pairs of the last step (reference triggerCacheTemp, Physecs.cpp:200-207) as rows
@@ -232,6 +235,14 @@ int pb_collider_ids(pb_ctx* ctx, int n, const int* cols, int* out_entity, int* o
 int pb_set_islands(pb_ctx* ctx, int mode);
 int pb_get_island_stats(pb_ctx* ctx, int* out3);
 
+/* Deterministic mode (also env PB_DETERMINISTIC=1 at pb_ctx_create).  The reference is reproducible with numThreads = 0
+ * (src/ThreadPool.cpp:30-46: everything on the caller); the device's default colouring claims colours with atomics, so the solve order
+ * and with it the trajectory differ from run to run (every run is a valid colour-batched order, which is what the parity gates
+ * compare through).  With this switch the colours come from fixed priorities (a hash of each manifold's collider pair + triangle)
+ * and the sequential bucket is ordered by the same hash: two runs of the same scene then produce bit-identical states.  Costs a few
+ * colouring rounds per step; meant for debugging and bisecting. */
+int pb_set_deterministic(pb_ctx* ctx, int on);
+
 /* optional in-kernel phase profile of the persistent substep kernel (bench.py roofline), accumulated since pb_set_profile(ctx, 1):
  * kinds 0 = integrate velocities, 1 = joint NGS phases, 2 = contact colour phases of the device-wide sweep, 3 = joint solve phases,
  * 4 = integrate positions, 5 = the per-CTA island sweeps (all their contact and joint colours; islands on). */
@@ -243,6 +254,29 @@ int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64);
 unsigned long long pb_get_launches(pb_ctx* ctx);
 /* cudaProfilerStart/Stop, so `ncu --profile-from-start off` captures only the timed region of bench.py */
 void pb_profiler_range(int start);
+
+/* ---- batches of independent scenes over several devices (BASELINE.json configs[4]) ------------------------
+ * The reference has one Scene driven by one thread (src/Physecs.cpp:112); an application simulating many independent worlds runs
+ * many Scenes.  A pb_batch shards such a set by scene: shard k = one context on devices[k] holding a contiguous block of scenes
+ * concatenated into one arena (upload it through pb_batch_ctx(batch, k) with the ordinary pb_upload_* calls: scenes that do not
+ * touch produce no cross-scene pairs, and simulation islands keep them apart in the solver), driven by its own host thread on its
+ * own stream.  No collective and no peer access on the data path.  All calls are asynchronous except sync / get_state. */
+typedef struct pb_batch pb_batch;
+/* contiguous block [begin, end) of scene indices owned by `shard`; block sizes differ by at most one */
+int  pb_batch_shard_range(int n_scenes, int n_shards, int shard, int* begin, int* end);
+int  pb_batch_create(int n_shards, const int* devices, const pb_caps* caps_per_shard, pb_batch** out);
+void pb_batch_destroy(pb_batch* batch);
+int  pb_batch_shards(pb_batch* batch);
+pb_ctx* pb_batch_ctx(pb_batch* batch, int shard);
+/* every shard's thread enqueues n_steps x pb_step; returns at once */
+int  pb_batch_step(pb_batch* batch, int n_steps, float dt, int substeps, int iterations, float gravity);
+/* waits for every shard; first non-OK status of any call since the last sync (pb_batch_last_error names shard and cause) */
+int  pb_batch_sync(pb_batch* batch);
+/* per-shard host arrays (array of n_shards pointers each, any of them null = not transferred); n_dynamic[k] rows in shard k */
+int  pb_batch_set_state(pb_batch* batch, const float* const* pos3, const float* const* quat4, const float* const* vel3,
+                        const float* const* angvel3, const int* n_dynamic);
+int  pb_batch_get_state(pb_batch* batch, float* const* pos3, float* const* quat4, float* const* vel3, float* const* angvel3);
+const char* pb_batch_last_error(pb_batch* batch);
 
 #ifdef __cplusplus
 }

@@ -260,6 +260,15 @@ class Context:
         self._check(self.lib.pb_get_counts(self.ctx, C.byref(c)))
         return c
 
+    BIN_NAMES = ["sphere_sphere", "sphere_capsule", "capsule_capsule", "sphere_box", "capsule_box", "box_box", "gjk_epa", "mesh_sphere", "mesh_capsule",
+                 "mesh_box", "mesh_convex", "trigger"]
+
+    def bin_counts(self):
+        """candidate pairs of the last step per narrowphase bin"""
+        out = (C.c_int * 12)()
+        self._check(self.lib.pb_get_bin_counts(self.ctx, out))
+        return {n: int(out[i]) for i, n in enumerate(self.BIN_NAMES)}
+
     def timings(self) -> Timings:
         t = Timings()
         self._check(self.lib.pb_get_timings(self.ctx, C.byref(t)))
@@ -284,6 +293,10 @@ class Context:
     def set_islands(self, mode):
         """0 off, 1 on, 2 auto: small simulation islands solved inside one CTA each (results are identical either way)."""
         self._check(self.lib.pb_set_islands(self.ctx, int(mode)))
+
+    def set_deterministic(self, on=True):
+        """colours from fixed priorities: two runs of the same scene give bit-identical states (reference: numThreads = 0)"""
+        self._check(self.lib.pb_set_deterministic(self.ctx, int(on)))
 
     def island_stats(self):
         out = (C.c_int * 3)()

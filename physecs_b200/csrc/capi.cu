@@ -170,6 +170,7 @@ int pb_get_island_stats(pb_ctx* ctx, int* out3) {
     out3[0] = ctx->islandsOn ? 1 : 0; out3[1] = ctx->lastIslandLocal; out3[2] = ctx->lastIslandTotal;
     return PB_OK;
 }
+int pb_set_deterministic(pb_ctx* ctx, int on) { ctx->deterministic = on != 0; return PB_OK; }
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
 void pb_profiler_range(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
 
@@ -234,6 +235,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
     if (const char* e = getenv("PB_MESH_LIGHT")) ctx->meshLightMode = atoi(e);
     if (const char* e = getenv("PB_NP_WAVES")) ctx->npWaves = atoi(e) >= 0 ? atoi(e) : 4;
+    if (const char* e = getenv("PB_DETERMINISTIC")) ctx->deterministic = atoi(e) != 0;
     if (const char* e = getenv("PB_ISLAND_LOCAL_MAX")) ctx->islandLocalMax = atoi(e) > 0 ? atoi(e) : 1;
     if (rc) { std::string e = ctx->err; pb_ctx_destroy(ctx); return rc; }
     cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream);
@@ -319,7 +321,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
-    F(gjkHitPair); F(gjkHitSimplex); F(spillList); F(spillEpa); F(spillMesh); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
+    F(jpBest); F(jpScratch); F(gjkHitPair); F(gjkHitSimplex); F(spillList); F(spillEpa); F(spillMesh); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
     F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(keyCursor); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.triRec); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }
@@ -887,6 +889,17 @@ int pb_get_counts(pb_ctx* ctx, pb_counts* out) {
     if (!rc) rc = refreshCounts(ctx);
     *out = ctx->lastCounts;
     return rc;
+}
+
+// candidate pairs per narrowphase bin of the last step (narrowphase.cu: sphere-sphere, sphere-capsule, capsule-capsule, sphere-box,
+// capsule-box, box-box, GJK/EPA, mesh-sphere, mesh-capsule, mesh-box, mesh-convex, trigger)
+int pb_get_bin_counts(pb_ctx* ctx, int* out12) {
+    cudaSetDevice(ctx->device);
+    int rc = pb_collect_step(ctx);
+    if (!rc) { ctx->countsStale = true; rc = refreshCounts(ctx); }
+    if (rc) return rc;
+    for (int b = 0; b < 12; ++b) out12[b] = ctx->hCounters[CNT_BINSTART + b + 1] - ctx->hCounters[CNT_BINSTART + b];
+    return PB_OK;
 }
 
 int pb_get_timings(pb_ctx* ctx, pb_timings* out) {

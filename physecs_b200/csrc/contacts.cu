@@ -66,6 +66,112 @@ __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counter
     if (threadIdx.x < PB_MAX_COLORS && hist[PB_MAX_COLORS + threadIdx.x]) atomicAdd(&counters[CNT_MULTISTART + threadIdx.x], hist[PB_MAX_COLORS + threadIdx.x]);
 }
 
+// ---- deterministic colouring (PB_DETERMINISTIC=1) -------------------------------------------------------------------------------
+// k_color's claims race, so colours -- and with them the solve order and the trajectory -- differ from run to run; the reference with
+// numThreads = 0 is reproducible (ThreadPool.cpp:30-46 runs everything on the caller).  This variant is a Jones-Plassmann colouring
+// with fixed priorities: every manifold's priority is a 64-bit hash of its key (collider pair + triangle), a manifold is coloured in
+// the round in which it holds the smallest priority among the uncoloured manifolds of BOTH its dynamic bodies, and it takes the
+// lowest colour free on both.  Winners of a round share no body, so their colour sets do not race; the result is a function of the
+// manifold SET alone (not of arena order, thread timing or grid shape).  One cooperative launch, two grid barriers per round;
+// rounds ~ the longest priority-decreasing chain (tens).  Slower than k_color (every round walks all manifolds): a debugging mode.
+__device__ __forceinline__ unsigned long long hashKey(int a, int b, int tri);
+struct JpBarrier {
+    unsigned int* counter; unsigned int target;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            unsigned int seen;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+            ++seen;
+            while (seen < target) { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); }
+        }
+        __syncthreads();
+    }
+};
+#define JP_UNCOLOURED 0xFFFFFFFEu
+__global__ void __launch_bounds__(256) k_color_jp(const int4* __restrict__ mKey, int* __restrict__ counters, int maxManifolds, const int* __restrict__ colRow,
+                                                  int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMask,
+                                                  unsigned long long* __restrict__ bodyBest, unsigned int* __restrict__ sortKey,
+                                                  unsigned int* __restrict__ barrier, int* __restrict__ remaining) {
+    __shared__ int hist[2 * PB_MAX_COLORS];
+    if (threadIdx.x < 2 * PB_MAX_COLORS) hist[threadIdx.x] = 0;
+    JpBarrier bar; bar.counter = barrier; bar.target = 0;
+    const int n = min(counters[CNT_RAWM], maxManifolds);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int b = tid; b < nDyn; b += nth) bodyBest[b] = ~0ull;
+    for (int i = tid; i < n; i += nth) {
+        int4 key = mKey[i];
+        unsigned int k = DISCARD_COLOR;
+        if (key.w > 0) {
+            int b0 = solverIndex(colRow[key.x], nDyn, kinematic), b1 = solverIndex(colRow[key.y], nDyn, kinematic);
+            if (b0 < 0 && b1 < 0) { k = key.w > 1 ? 1u : 0u; atomicAdd(&hist[0], 1); if (key.w == 1) atomicAdd(&hist[PB_MAX_COLORS], 1); }     // colour 0
+            else k = JP_UNCOLOURED;
+        }
+        sortKey[i] = k;
+    }
+    if (tid == 0) { remaining[0] = 0; remaining[1] = 0; }
+    bar.sync();
+    for (int round = 0; ; ++round) {
+        // post: every uncoloured manifold offers its priority to its bodies
+        for (int i = tid; i < n; i += nth) {
+            if (sortKey[i] != JP_UNCOLOURED) continue;
+            int4 key = mKey[i];
+            int b0 = solverIndex(colRow[key.x], nDyn, kinematic), b1 = solverIndex(colRow[key.y], nDyn, kinematic);
+            unsigned long long pr = hashKey(key.x, key.y, key.z);
+            if (b0 >= 0) atomicMin(&bodyBest[b0], pr);
+            if (b1 >= 0 && b1 != b0) atomicMin(&bodyBest[b1], pr);
+        }
+        if (tid == 0) remaining[(round + 1) & 1] = 0;
+        bar.sync();
+        // decide: the holder of the smallest priority on both bodies colours itself and re-opens its bodies
+        int lost = 0;
+        for (int i = tid; i < n; i += nth) {
+            if (sortKey[i] != JP_UNCOLOURED) continue;
+            int4 key = mKey[i];
+            int b0 = solverIndex(colRow[key.x], nDyn, kinematic), b1 = solverIndex(colRow[key.y], nDyn, kinematic);
+            unsigned long long pr = hashKey(key.x, key.y, key.z);
+            const bool win = (b0 < 0 || __ldcg(&bodyBest[b0]) == pr) && (b1 < 0 || __ldcg(&bodyBest[b1]) == pr);
+            if (!win) { ++lost; continue; }
+            unsigned long long m0 = b0 >= 0 ? __ldcg(&colorMask[b0]) : 0ull, m1 = b1 >= 0 ? __ldcg(&colorMask[b1]) : 0ull;
+            unsigned long long freeSet = ~(m0 | m1) & ~(1ull << PB_OVERFLOW_COLOR);
+            unsigned int color = PB_OVERFLOW_COLOR;
+            if (freeSet) {
+                color = (unsigned int)(__ffsll((long long)freeSet) - 1);
+                if (b0 >= 0) __stcg(&colorMask[b0], m0 | (1ull << color));
+                if (b1 >= 0 && b1 != b0) __stcg(&colorMask[b1], m1 | (1ull << color));
+            }
+            if (b0 >= 0) __stcg(&bodyBest[b0], ~0ull);
+            if (b1 >= 0) __stcg(&bodyBest[b1], ~0ull);
+            atomicAdd(&hist[color], 1);
+            if (key.w == 1) atomicAdd(&hist[PB_MAX_COLORS + color], 1);
+            sortKey[i] = 2u * color + (key.w > 1 ? 1u : 0u);
+        }
+        if (lost) atomicAdd(&remaining[round & 1], lost);
+        bar.sync();
+        if (__ldcg(&remaining[round & 1]) == 0) break;       // uniform over the grid
+    }
+    __syncthreads();
+    if (threadIdx.x < PB_MAX_COLORS && hist[threadIdx.x]) atomicAdd(&counters[CNT_COLORSTART + threadIdx.x], hist[threadIdx.x]);
+    if (threadIdx.x < PB_MAX_COLORS && hist[PB_MAX_COLORS + threadIdx.x]) atomicAdd(&counters[CNT_MULTISTART + threadIdx.x], hist[PB_MAX_COLORS + threadIdx.x]);
+}
+
+// deterministic mode: the sequential bucket (colour 63, manifolds that may share bodies) is solved in slot order, and the counting-sort
+// scatter fills slots in arrival order -- re-order that one run by key hash.  One thread: the bucket holds the few manifolds of bodies
+// with more than 63 contacts, usually none.
+__global__ void k_sort_overflow_run(int nGroups, const int* __restrict__ keyStart, const int4* __restrict__ mKey, int* __restrict__ outRaw) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per group's run table (islands off: only the last one is filled)
+    if (g >= nGroups) return;
+    const int* keyStartG = keyStart + (size_t)g * PB_KEY_COLORS;
+    const int start = keyStartG[2 * PB_OVERFLOW_COLOR], end = keyStartG[2 * PB_OVERFLOW_COLOR + 2];
+    for (int i = start + 1; i < end; ++i) {
+        int x = outRaw[i]; int4 kx = mKey[x]; unsigned long long hx = hashKey(kx.x, kx.y, kx.z);
+        int j = i;
+        while (j > start) { int4 kp = mKey[outRaw[j - 1]]; if (hashKey(kp.x, kp.y, kp.z) <= hx) break; outRaw[j] = outRaw[j - 1]; --j; }
+        outRaw[j] = x;
+    }
+}
+
 // colour starts (taps, counters) and, for the plain colour-major order (islands off), the run table of group G: entry c * 2 = first
 // single-point slot of colour c, c * 2 + 1 = first multi-point slot, [PB_KEY_COLORS] = end
 __global__ void k_color_starts(int* counters, int* __restrict__ keyStartG) {
@@ -302,6 +408,21 @@ int pb_contact_build(pb_ctx* ctx) {
     int rc;
     cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
+    if (ctx->deterministic) {
+        if (!ctx->jpBest) {
+            if ((rc = pb_alloc(ctx, &ctx->jpBest, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->jpScratch, 64))) return rc;
+            int perSM = 0;
+            PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_color_jp, 256, 0));
+            ctx->jpGrid = ctx->numSMs * std::max(1, std::min(perSM, 4));
+        }
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->jpScratch, 0, sizeof(int) * 64, ctx->stream));
+        const int4* mKey = ctx->mKey; int* counters = ctx->counters; const int* colRow = ctx->colRow; int nDyn = ctx->nDyn; const int* kin = ctx->kinematic;
+        unsigned long long* mask = ctx->colorMask; unsigned long long* best = ctx->jpBest; unsigned int* sk = ctx->mSortKeyA;
+        unsigned int* bar = (unsigned int*)ctx->jpScratch; int* rem = ctx->jpScratch + 16;
+        void* args[] = { &mKey, &counters, &maxM, &colRow, &nDyn, &kin, &mask, &best, &sk, &bar, &rem };
+        ++ctx->launches;
+        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_color_jp, dim3(ctx->jpGrid), dim3(256), args, 0, ctx->stream));
+    } else
     ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
                                              ctx->mSortKeyA);
     ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->keyStart + (size_t)G * PB_KEY_COLORS);
@@ -326,6 +447,7 @@ int pb_contact_build(pb_ctx* ctx) {
     }
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->keyCursor, ctx->keyStart, sizeof(int) * ((size_t)nKeys + 1), cudaMemcpyDeviceToDevice, ctx->stream));
     ++ctx->launches, k_scatter_by_key<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mSortKeyA, keyBase, keyLimit, ctx->keyCursor, ctx->mSortValB, ctx->mSortKeyB);
+    if (ctx->deterministic) ++ctx->launches, k_sort_overflow_run<<<pb_grid(G + 1, 128), 128, 0, ctx->stream>>>(G + 1, ctx->keyStart, ctx->mKey, ctx->mSortValB);
     ctx->mSorted = ctx->mSortValB;
     ctx->mSortedKeys = ctx->mSortKeyB;
     int cur = ctx->curBuf, prev = cur ^ 1;

@@ -219,6 +219,9 @@ struct pb_ctx {
     cudaEvent_t evCounters = nullptr; bool stepPending = false;
     int rawHint = -1;                // raw manifold count of the last collected step (-1: none yet): shapes grids only
     bool undoCacheValid = false, undoCacheBuilt = false; int undoVelSwaps = 0;
+    // PB_DETERMINISTIC=1 (or pb_set_deterministic): colours by fixed priorities (contacts.cu k_color_jp) -- two runs of the same scene give
+    // bit-identical trajectories, like the reference with numThreads = 0 (ThreadPool.cpp:30-46)
+    bool deterministic = false; unsigned long long* jpBest = nullptr; int* jpScratch = nullptr; int jpGrid = 0;
     std::vector<int> hTrimeshCols;   // colliders of type PB_TRIANGLE_MESH (their bounds are a vertex reduction each)
     std::vector<int> hKinematic;     // host mirror of `kinematic` (which trimesh colliders ride on moving bodies)
     unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
