@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(ROOT, "physecs_b200", "csrc")
-OUT = os.path.join(ROOT, "physecs_b200", "lib")
+OUT = os.environ.get("PB_BUILD_OUT") or os.path.join(ROOT, "physecs_b200", "lib")   # PB_BUILD_OUT: compile somewhere else (a check build that leaves the shipped .so alone)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "--expt-relaxed-constexpr", "-w"]
 

@@ -35,6 +35,12 @@ struct Bounds {
     glm::vec3 getCenter() const { return (min + max) * 0.5f; }
     glm::vec3 getHalfExtents() const { return (max - min) * 0.5f; }
     void addMargin(const glm::vec3& m) { min -= m; max += m; }
+    void expand(glm::vec3 e) {      // grows the box on the side the expansion points to (reference src/Bounds.cpp:12-21)
+        if (e.x < 0) min.x += e.x; else max.x += e.x;
+        if (e.y < 0) min.y += e.y; else max.y += e.y;
+        if (e.z < 0) min.z += e.z; else max.z += e.z;
+    }
+    float area() const { const glm::vec3 d = max - min; return 2 * (d.x * d.y + d.y * d.z + d.z * d.x); }
 };
 
 // ---- meshes (user-owned, must outlive the Scene: Colliders.h:24-31 holds raw pointers) ---------------------------------

@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(256) k_color_jp(const int4* __restrict__ mKey,
             if (b0 >= 0) atomicMin(&bodyBest[b0], pr);
             if (b1 >= 0 && b1 != b0) atomicMin(&bodyBest[b1], pr);
         }
-        if (tid == 0) remaining[(round + 1) & 1] = 0;
         bar.sync();
+        // (every CTA is past its read of the previous round's counter -- the read sits before the barrier above -- so the slot the next
+        // round will count into can be cleared now)
+        if (tid == 0) remaining[(round + 1) & 1] = 0;
         // decide: the holder of the smallest priority on both bodies colours itself and re-opens its bodies
         int lost = 0;
         for (int i = tid; i < n; i += nth) {

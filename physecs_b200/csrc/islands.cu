@@ -13,6 +13,7 @@
 //                                     body (neighbouring bodies -> neighbouring groups), large islands go to group G = "global"
 #include "pb_ctx.h"
 #include "joints.cuh"
+#include <algorithm>
 
 bool pb_joint_view(pb_ctx* ctx, JointDev* out);
 
@@ -100,6 +101,33 @@ __global__ void k_island_group(int n, int* rootThenGroup, const int* __restrict_
     group[i] = local ? (int)min((long long)G - 1, (long long)r * G / n) : G;
 }
 
+// per-group body lists: bodies counted per group (CTA-local histogram first), then placed with one atomic per distinct group per warp
+__global__ void __launch_bounds__(256) k_island_body_hist(int n, const int* __restrict__ group, int G, int* __restrict__ hist) {
+    extern __shared__ int sh[];
+    for (int i = threadIdx.x; i <= G; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[group[i]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= G; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+__global__ void __launch_bounds__(256) k_island_body_scatter(int n, const int* __restrict__ group, int* __restrict__ cursor, int* __restrict__ order) {
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        const int g = valid ? group[i] : -1;
+        const unsigned int act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned int peers = __match_any_sync(act, g);
+            const int leader = __ffs(peers) - 1;
+            int slot = 0;
+            if (lane == leader) slot = atomicAdd(&cursor[g], __popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+            order[slot] = i;
+        }
+    }
+}
+
 // stats[0] = constraints of local islands, stats[1] = constraints of all islands (one atomic pair per CTA: 31 k warps adding to two
 // words were most of this kernel's 45 us at 1 M bodies)
 __global__ void __launch_bounds__(256) k_island_stats(int n, const int* __restrict__ group, const int* __restrict__ cnt, int G, int* __restrict__ stats) {
@@ -141,6 +169,21 @@ int pb_islands_build(pb_ctx* ctx) {
     // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
     ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandLocalMax);
     ++ctx->launches, k_island_stats<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandStats);
+    // body lists per group for the whole-step kernel's group-by-group form (solver.cu k_step_solve_small): only scenes small enough to take it
+    ctx->bodyListsBuilt = false;
+    if (n <= ctx->fusedLocalMax && ctx->fusedMode != 0) {
+        if (!ctx->bodyOrder) {
+            int rc;
+            if ((rc = pb_alloc(ctx, &ctx->bodyOrder, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->bodyStart, (size_t)G + 2)) || (rc = pb_alloc(ctx, &ctx->bodyCursor, (size_t)G + 2))) return rc;
+        }
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->bodyStart, 0, sizeof(int) * ((size_t)G + 2), ctx->stream));
+        const int hb = std::min(pb_grid(n, 256), ctx->numSMs * 4);
+        ++ctx->launches, k_island_body_hist<<<hb, 256, sizeof(int) * (G + 1), ctx->stream>>>(n, ctx->bodyGroup, G, ctx->bodyStart);
+        int rc = pb_exclusive_scan(ctx, ctx->bodyStart, ctx->bodyStart, G + 2, (int*)ctx->radixHist); if (rc) return rc;
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->bodyCursor, ctx->bodyStart, sizeof(int) * ((size_t)G + 2), cudaMemcpyDeviceToDevice, ctx->stream));
+        ++ctx->launches, k_island_body_scatter<<<hb, 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->bodyCursor, ctx->bodyOrder);
+        ctx->bodyListsBuilt = true;
+    }
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

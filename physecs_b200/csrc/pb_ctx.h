@@ -199,6 +199,9 @@ struct pb_ctx {
     int2* trigPairs = nullptr;       // [maxPairs] overlapping TRIGGER pairs of the last step (collider indices)
     // simulation islands (islands.cu): group of every solver body; local groups 0..islandGroups-1 (one CTA each), group islandGroups = global
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
+    // per-group body lists (built when the whole-step kernel may run group by group): bodyOrder = bodies sorted by group, bodyStart[g] their runs
+    int* bodyOrder = nullptr; int* bodyStart = nullptr; int* bodyCursor = nullptr; bool bodyListsBuilt = false;
+    int fusedLocalMax = 65536;       // bodies up to which an all-local scene takes the one-launch whole-step kernel (env PB_FUSED_LOCAL_MAX)
     int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)
     int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)
     int islandLocalMax = PB_ISLAND_LOCAL_MAX;   // env PB_ISLAND_LOCAL_MAX overrides (tests: force a mix of local and device-wide sweeps)

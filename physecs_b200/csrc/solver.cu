@@ -59,6 +59,7 @@ struct SubstepParams {
     // Groups 0..G-1 are islands small enough for one CTA (islands.cu, only when islandsOn), group G is the device-wide sweep.
     const int* keyStart; int G; int islandsOn;
     const int* jointOrder; const int* jointStart;     // per-group joint runs (islandsOn): jointStart[g * 8 + c]
+    const int* bodyOrder; const int* bodyStart;       // per-group body lists (islands.cu; nullptr unless the whole-step kernel may run group by group)
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
     unsigned int* barrier;
     unsigned long long* profNs;
@@ -475,8 +476,11 @@ __global__ void __launch_bounds__(128) k_joint_fill(const __grid_constant__ Subs
 // barriers per substep instead of one per colour and pass.  Islands share no dynamic body, so the interleaving is immaterial.
 // L1LOCAL: the per-CTA sweeps may use L1-cached accesses -- true when everything they read was written before this kernel started or
 // by their own CTA (k_substep_solve); false in the fused small-scene kernel, where other SMs rewrite the rows every substep.
-template <bool L1LOCAL>
-__device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarrier& bar, float4* velLive, float4* angvelLive, int* sRuns, int* sJoint) {
+// ONLYGROUP: the caller (k_step_solve_small, every constraint of the scene in small islands) walks its groups one at a time through the
+// whole substep loop: this call then sweeps group `onlyGroup` alone, integrates that group's bodies (bodyOrder list) and never touches
+// the grid barrier -- a batch of little scenes steps without a single device-wide synchronisation.
+template <bool L1LOCAL, bool ONLYGROUP = false>
+__device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarrier& bar, float4* velLive, float4* angvelLive, int* sRuns, int* sJoint, int onlyGroup = -1) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     const int ncol = P.counters[CNT_NCOLORS];
@@ -549,6 +553,23 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         __syncthreads();
     };
 
+    if (ONLYGROUP) {
+        const int g = onlyGroup;
+        loadLocal(g);
+        const bool empty = sRuns[PB_KEY_COLORS] == sRuns[0] && (!P.hasJoints || sJoint[8] == sJoint[0]);
+        if (!empty) {
+            if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
+            for (int it = 0; it < P.iterations; ++it) {
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
+                if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
+            }
+        }
+        __syncthreads();
+        for (int k = P.bodyStart[g] + threadIdx.x; k < P.bodyStart[g + 1]; k += blockDim.x) integrateX(P, P.bodyOrder[k], velLive, angvelLive);
+        __syncthreads();
+        if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
+        return;
+    }
     // ---- phase A: NGS pass of the joints, then the iterations --------------------------------------------------------------------
     if (P.islandsOn) {
         for (int g = blockIdx.x; g < G; g += gridDim.x) {
@@ -628,6 +649,35 @@ __global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_consta
     if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
     const int nManifolds = P.counters[CNT_MANIFOLDS];
     float4* vel = P.velA; float4* angvel = P.angvelA; float4* velLive = P.velB; float4* angvelLive = P.angvelB;
+    // Every constraint sits in a small island (nothing in the device-wide group G, no overflow-bucket joints): groups are independent
+    // for the WHOLE step, so each CTA takes its groups through all substeps on its own -- integration, prep, sweeps, relaxation --
+    // with CTA barriers only.  (Decided from device data, uniformly over the grid; otherwise the grid-barrier form below runs.)
+    if (P.islandsOn && P.bodyOrder) {
+        const int* gRuns = P.keyStart + P.G * PB_KEY_COLORS;
+        const bool globalEmpty = gRuns[PB_KEY_COLORS] == gRuns[0] && (!P.hasJoints || P.jointStart[P.G * 8 + 9] == P.jointStart[P.G * 8]);
+        if (globalEmpty) {
+            for (int g = blockIdx.x; g < P.G; g += gridDim.x) {
+                const int b0 = P.bodyStart[g], b1 = P.bodyStart[g + 1];
+                if (b0 == b1) continue;
+                const int m0 = P.keyStart[g * PB_KEY_COLORS], m1 = P.keyStart[(g + 1) * PB_KEY_COLORS];
+                const int j0 = P.hasJoints ? P.jointStart[g * 8] : 0, j1 = P.hasJoints ? P.jointStart[g * 8 + 8] : 0;
+                float4* v = P.velA; float4* w = P.angvelA; float4* vL = P.velB; float4* wL = P.angvelB;
+                for (int sub = 0; sub < P.substeps; ++sub) {
+                    for (int k = b0 + threadIdx.x; k < b1; k += blockDim.x) integrateV(P, P.bodyOrder[k], v, w, vL, wL);
+                    __syncthreads();
+                    for (int s = m0 + threadIdx.x; s < m1; s += blockDim.x) contactPrep(P, s, v, w);
+                    for (int k = j0 + threadIdx.x; k < j1; k += blockDim.x)
+                        jointPrepOne(P.J, P.jointOrder[k], 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.bodyRec, P.pseudoLin, P.pseudoAng);
+                    __syncthreads();
+                    substepColoured<false, true>(P, bar, vL, wL, sRuns, sJoint, g);
+                    __syncthreads();
+                    float4* t = v; v = vL; vL = t;
+                    t = w; w = wL; wL = t;
+                }
+            }
+            return;
+        }
+    }
     for (int sub = 0; sub < P.substeps; ++sub) {
         for (int i = tid; i < P.nDyn; i += nth) integrateV(P, i, vel, angvel, velLive, angvelLive);
         bar.sync(PH_INTEGRATE_V);
@@ -676,6 +726,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     for (int c = 0; c <= PB_JOINT_COLORS; ++c) P.jointColorStart[c] = ctx->jointColorStart[c];
     P.keyStart = ctx->keyStart; P.G = ctx->islandGroups; P.islandsOn = ctx->islandsOn ? 1 : 0;
     P.jointOrder = (ctx->islandsOn && P.hasJoints) ? ctx->jointOrder : nullptr; P.jointStart = ctx->jointStart;
+    P.bodyOrder = (ctx->islandsOn && ctx->bodyListsBuilt) ? ctx->bodyOrder : nullptr; P.bodyStart = ctx->bodyStart;
     P.barrier = ctx->solveBarrier;
     P.profNs = ctx->profile ? ctx->solveProfNs : nullptr;
     // persistent grid: co-resident by construction; small scenes use fewer CTAs so the barrier stays cheap
@@ -691,7 +742,11 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     // (measured: equal or slightly ahead up to ~1 k bodies -- 64 ragdolls 0.78 vs 0.80 ms/step, 1 k-box pyramid 1.50 vs 1.52 -- and behind
     // from ~5 k bodies on, where the 3-CTA/SM register cap makes the prep phases spill; such steps are bound by the latency of their
     // ~30 colour phases per substep, not by launches)
-    const bool fused = fusedEnv >= 0 ? fusedEnv != 0 : (nDyn <= 2048 && workBound <= 8192 && ctx->nJoints <= 4096);
+    // ... except when every constraint sits in a small island (as far as the last collected step knows; the kernel decides from device
+    // data and falls back to its grid-barrier form otherwise): then the groups go through the whole step independently, no grid barrier
+    // at all, and the one-launch form wins up to batches of tens of thousands of bodies (4096 ragdoll scenes)
+    const bool allLocal = ctx->islandsOn && ctx->bodyListsBuilt && (ctx->lastIslandTotal == 0 || ctx->lastIslandLocal == ctx->lastIslandTotal);
+    const bool fused = fusedEnv >= 0 ? fusedEnv != 0 : ((nDyn <= 2048 && workBound <= 8192 && ctx->nJoints <= 4096) || (allLocal && nDyn <= ctx->fusedLocalMax));
     if (fused) {
         P.velA = ctx->vel; P.angvelA = ctx->angvel; P.velB = ctx->velLive; P.angvelB = ctx->angvelLive;
         int fgrid = ctx->islandsOn ? std::min(ctx->solveGrid, ctx->islandGroups) : grid;

@@ -772,10 +772,21 @@ void Scene::prepareDevice() {
 
     // ---- bodies announced through registry.patch<TransformComponent>: pose + bounds (+0.01) from the patch-time transform -----
     if (!S.moved.empty()) {
+        // an entity patched several times between two steps: the LAST patch wins, as in the reference (every patch calls
+        // updateBounds, Physecs.cpp:51-54).  One row per entity goes to the device (duplicate rows would race in the scatter).
         std::vector<int> rows; std::vector<float> p, q;
+        std::unordered_map<int, size_t> slotOfRow;
         for (auto& mv : S.moved) {
             int r = S.rowOf(mv.e);
             if (r < 0) continue;
+            auto it = slotOfRow.find(r);
+            if (it != slotOfRow.end()) {
+                const size_t k = it->second;
+                p[3 * k] = mv.p.x; p[3 * k + 1] = mv.p.y; p[3 * k + 2] = mv.p.z;
+                q[4 * k] = mv.q.x; q[4 * k + 1] = mv.q.y; q[4 * k + 2] = mv.q.z; q[4 * k + 3] = mv.q.w;
+                continue;
+            }
+            slotOfRow[r] = rows.size();
             rows.push_back(r);
             p.insert(p.end(), { mv.p.x, mv.p.y, mv.p.z });
             q.insert(q.end(), { mv.q.x, mv.q.y, mv.q.z, mv.q.w });

@@ -134,3 +134,15 @@ def test_device_sort(n, bits, coop, monkeypatch):
     assert np.array_equal(vo, order.astype(np.int32))
     assert np.array_equal(ko, keys[order])
     ctx.close()
+
+
+@pytest.mark.parametrize("fused_local_max", [0, 65536])
+@pytest.mark.parametrize("maker,steps", [(lambda: S.ragdolls(300), 30), (lambda: S.terrain(3000, cells=64, drop=0.3), 30)])
+def test_whole_step_kernel_group_by_group(maker, steps, fused_local_max, monkeypatch):
+    """Scenes whose constraints all sit in small islands (ragdoll batches, bodies spread over a terrain) take the one-launch whole-step
+    kernel group by group -- every CTA carries its groups through all substeps with CTA barriers only (solver.cu k_step_solve_small);
+    PB_FUSED_LOCAL_MAX=0 keeps them on the per-substep launches.  Same results either way, bit for bit against the oracle."""
+    monkeypatch.setenv("PB_FUSED_LOCAL_MAX", str(fused_local_max))
+    monkeypatch.setenv("PB_ISLANDS", "1")
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps and s["manifolds"] > 0 and s["worst_manifold"] <= parity.TOL
