@@ -160,6 +160,10 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* colliders, const float* bounds6
 /* push registry state of the dynamic rows (what the reference reads through registry.get each step) */
 int pb_set_state(pb_ctx* ctx, int n_dynamic, const float* pos3, const float* quat4, const float* vel3,
                  const float* angvel3);
+/* the same for rows [first, first + count) of the dynamic storage; the pointers address the first row of the range.  Lets a host
+ * that gathers its registry in chunks start each chunk's upload as soon as it is gathered. */
+int pb_set_state_rows(pb_ctx* ctx, int first, int count, const float* pos3, const float* quat4, const float* vel3,
+                      const float* angvel3);
 /* transforms of the static rows [n_dynamic, n_dynamic + n_static): the reference reads every Transform live in the
  * narrowphase (Physecs.cpp:191-198) while bounds only follow registry.patch (pb_move_rows) */
 int pb_set_static_poses(pb_ctx* ctx, int n_static, const float* pos3, const float* quat4);
@@ -176,9 +180,19 @@ int pb_refresh_bounds(pb_ctx* ctx);
  * pb_get_counts, the taps, or the next pb_step (which then enqueues nothing) -- as PB_ECAPACITY: grow the arenas (pb_grow_arenas)
  * and call pb_step again.  A caller that wants the status of a step before doing anything else calls pb_collect_step. */
 int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
+/* Optional head of a step: counters reset + broadphase, which need nothing from the host -- the reference's sweep, too, runs on the
+ * bounds the previous simulate left behind (Physecs.cpp:119-173, bounds refreshed at :556-559 / by registry.patch), not on this
+ * step's transforms.  Call it first, then gather and upload the new state (pb_set_state / pb_set_state_rows) while the broadphase
+ * runs, then pb_step, which continues behind it.  Calling pb_step alone is equivalent. */
+int pb_step_begin(pb_ctx* ctx);
 /* waits for the narrowphase of the last pb_step (not for the whole step) and returns its status; PB_OK when nothing is pending */
 int pb_collect_step(pb_ctx* ctx);
 int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3);
+/* pb_get_state in up to 32 chunks of rows: _begin enqueues the copies (asynchronous; reports a failed step like pb_get_state),
+ * _wait blocks until chunk `chunk` has arrived and names its row range -- the host can scatter a chunk into its registry while the
+ * next one is still on the bus.  chunk >= the number of chunks: *count = 0. */
+int pb_get_state_begin(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3, int n_chunks);
+int pb_get_state_wait(pb_ctx* ctx, int chunk, int* first, int* count);
 int pb_sync(pb_ctx* ctx);
 
 /* ---- parity / debug taps ----------------------------------------------------------------------------- */

@@ -311,6 +311,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->evVelReady) cudaEventDestroy(ctx->evVelReady);
     if (ctx->evPoseReady) cudaEventDestroy(ctx->evPoseReady);
     if (ctx->evCounters) cudaEventDestroy(ctx->evCounters);
+    for (auto& e : ctx->evRead) if (e) cudaEventDestroy(e);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
@@ -344,7 +345,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
                      const float* vel3, const float* angvel3, const float* invMass, const float* com3, const float* invI9) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     int rows = nDyn + nStatic;
     if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
     ctx->nDyn = nDyn; ctx->nStatic = nStatic; ctx->nRows = rows;
@@ -378,7 +379,7 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
                         const float* params4, const int* mesh, const float* material3, const int* flags, const int* data) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
     ctx->nCol = n;
     ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
@@ -569,38 +570,38 @@ int pb_set_noncolliding_pairs(pb_ctx* ctx, int n, const int* pairs2) {
     return PB_OK;
 }
 
-int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
-    cudaSetDevice(ctx->device);
+// rows [first, first + count) of the dynamic state; the pointers address the first row of the range
+static int setStateRange(pb_ctx* ctx, int first, int count, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
     ctx->queryTreeValid = false;
-    if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state: n_dynamic mismatch");
-    if (!nDyn) return PB_OK;
+    if (count <= 0) return PB_OK;
     // One packed H2D burst (13 floats / body) on the COPY stream, unpacked into the float4 SoA there: ordered after everything
-    // already queued on the main stream, and every reader on the main stream waits for evPoseReady / evVelReady (pb_ctx.h).
-    size_t n = (size_t)nDyn;
-    if (ctx->stageVelBytes < sizeof(float) * 13 * n) {
+    // already queued on the main stream (or after the mark pb_step_begin left), and every reader on the main stream waits for
+    // evPoseReady / evVelReady (pb_ctx.h).
+    const size_t N = (size_t)ctx->nDyn, f = (size_t)first, n = (size_t)count;
+    if (ctx->stageVelBytes < sizeof(float) * 13 * N) {
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
         if (ctx->stageVel) cudaFree(ctx->stageVel);
         ctx->stageVel = nullptr; ctx->stageVelBytes = 0;
-        PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageVel, sizeof(float) * 13 * n));
-        ctx->stageVelBytes = sizeof(float) * 13 * n;
+        PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageVel, sizeof(float) * 13 * N));
+        ctx->stageVelBytes = sizeof(float) * 13 * N;
     }
     float* s = ctx->stageVel;
     cudaStream_t cs = ctx->copyStream;
-    PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));
+    if (!ctx->mainMarked) PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));
     PB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->evMainAtSet, 0));
-    int g = pb_grid(nDyn, 256);
+    int g = pb_grid(count, 256);
     if (pos3 || quat4) {
-        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
-        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * n, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, cs));
-        if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, cs>>>(nDyn, s, ctx->pos);
-        if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, cs>>>(nDyn, s + 3 * n, ctx->quat);
+        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * f, pos3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(s + 3 * N + 4 * f, quat4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, cs));
+        if (pos3) ++ctx->launches, k_unpack3<<<g, 256, 0, cs>>>(count, s + 3 * f, ctx->pos + f);
+        if (quat4) ++ctx->launches, k_unpack4<<<g, 256, 0, cs>>>(count, s + 3 * N + 4 * f, ctx->quat + f);
         PB_CUDA(ctx, cudaEventRecord(ctx->evPoseReady, cs));
         ctx->posePending = true;
     }
     if (vel3 || angvel3) {
-        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * n, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
-        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * n, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
-        ++ctx->launches, k_unpack_vel<<<g, 256, 0, cs>>>(nDyn, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr, ctx->comInvMass, ctx->vel);
+        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 7 * N + 3 * f, vel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(s + 10 * N + 3 * f, angvel3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs));
+        ++ctx->launches, k_unpack_vel<<<g, 256, 0, cs>>>(count, vel3 ? s + 7 * N + 3 * f : nullptr, angvel3 ? s + 10 * N + 3 * f : nullptr, ctx->comInvMass + f, ctx->vel + 2 * f);
         PB_CUDA(ctx, cudaEventRecord(ctx->evVelReady, cs));
         ctx->velPending = true;
     }
@@ -608,10 +609,22 @@ int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, c
     return PB_OK;
 }
 
+int pb_set_state(pb_ctx* ctx, int nDyn, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
+    cudaSetDevice(ctx->device);
+    if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state: n_dynamic mismatch");
+    return setStateRange(ctx, 0, nDyn, pos3, quat4, vel3, angvel3);
+}
+
+int pb_set_state_rows(pb_ctx* ctx, int first, int count, const float* pos3, const float* quat4, const float* vel3, const float* angvel3) {
+    cudaSetDevice(ctx->device);
+    if (first < 0 || count < 0 || first + count > ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_state_rows: range outside the dynamic rows");
+    return setStateRange(ctx, first, count, pos3, quat4, vel3, angvel3);
+}
+
 int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     if (n <= 0) return PB_OK;
     size_t bytes = sizeof(float) * 8 * (size_t)n;
     int rc = ensureStage(ctx, bytes); if (rc) return rc;
@@ -633,7 +646,7 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
 int pb_refresh_bounds(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     return pb_update_bounds_all(ctx, 0.01f, 1);
 }
 
@@ -700,16 +713,32 @@ int pb_collect_step(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
+// The head of a step that needs nothing from the host: counters reset + broadphase.  The reference's sweep runs on the bounds the
+// previous simulate left behind (Physecs.cpp:119-173 reads BroadPhaseEntry::bounds, refreshed at :556-559 and by registry.patch), not
+// on the transforms of this step -- so it can run while the host still gathers / uploads the new state.
+int pb_step_begin(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
-    if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
     int rc;
     if ((rc = pb_collect_step(ctx))) return rc;          // the PREVIOUS step overflowed and was not applied: nothing new is enqueued
     ctx->queryTreeValid = false;
+    // uploads issued from here on (pb_set_state / pb_set_state_rows, copy stream) wait for what the main stream holds NOW -- the
+    // previous step -- and not for the broadphase below, which reads neither poses nor velocities
+    PB_CUDA(ctx, cudaEventRecord(ctx->evMainAtSet, ctx->stream));
+    ctx->mainMarked = true;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_TOTAL, ctx->stream));
     if ((rc = pb_broadphase(ctx))) return rc;
     cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->stepBegun = true;
+    return PB_OK;
+}
+
+int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
+    cudaSetDevice(ctx->device);
+    if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
+    int rc;
+    if (!ctx->stepBegun && (rc = pb_step_begin(ctx))) return rc;
+    ctx->stepBegun = false; ctx->mainMarked = false;
     if ((rc = pb_wait_poses(ctx))) return rc;          // the broadphase above ran on the bounds of the previous step's end; from here on poses are read
     if ((rc = pb_world_poses(ctx))) return rc;
     if ((rc = pb_narrowphase(ctx))) return rc;
@@ -759,6 +788,51 @@ int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* ang
     return PB_OK;
 }
 
+// The read-back in chunks: the pack kernels run once, then every chunk's four copies are followed by an event.  The caller scatters
+// chunk c into its own data structures while chunk c + 1 is still crossing the bus (host/Scene.cpp).
+int pb_get_state_begin(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3, int nChunks) {
+    cudaSetDevice(ctx->device);
+    { int rcc = pb_collect_step(ctx); if (rcc) return rcc; }
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
+    if (nChunks < 1) nChunks = 1;
+    if (nChunks > PB_MAX_READ_CHUNKS) nChunks = PB_MAX_READ_CHUNKS;
+    const int nDyn = ctx->nDyn;
+    ctx->readChunks = 0;
+    if (!nDyn) return PB_OK;
+    const size_t n = (size_t)nDyn;
+    int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
+    float* s = ctx->stage;
+    const int g = pb_grid(nDyn, 256);
+    if (pos3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
+    if (quat4) ++ctx->launches, k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
+    if (vel3 || angvel3)
+        ++ctx->launches, k_pack_vel<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr);
+    const int per = (nDyn + nChunks - 1) / nChunks;
+    for (int c = 0; c < nChunks; ++c) {
+        const size_t f = (size_t)c * per;
+        if (f >= n) break;
+        const size_t m = std::min(n - f, (size_t)per);
+        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3 + 3 * f, s + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4 + 4 * f, s + 3 * n + 4 * f, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3 + 3 * f, s + 7 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(angvel3 + 3 * f, s + 10 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!ctx->evRead[c]) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evRead[c], cudaEventDisableTiming));
+        PB_CUDA(ctx, cudaEventRecord(ctx->evRead[c], ctx->stream));
+        ctx->readFirst[c] = (int)f; ctx->readCount[c] = (int)m;
+        ctx->readChunks = c + 1;
+    }
+    return PB_OK;
+}
+
+int pb_get_state_wait(pb_ctx* ctx, int chunk, int* first, int* count) {
+    cudaSetDevice(ctx->device);
+    if (chunk < 0 || chunk >= ctx->readChunks) { if (first) *first = 0; if (count) *count = 0; return chunk < 0 ? PB_EINVAL : PB_OK; }
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->evRead[chunk]));
+    if (first) *first = ctx->readFirst[chunk];
+    if (count) *count = ctx->readCount[chunk];
+    return PB_OK;
+}
+
 int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
@@ -780,7 +854,7 @@ int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float
 int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     if (n <= 0) return PB_OK;
     for (int i = 0; i < n; ++i) if (cols[i] < 0 || cols[i] >= ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_bounds: collider out of range");
     int rc = ensureStage(ctx, sizeof(float) * 7 * (size_t)n); if (rc) return rc;
@@ -795,7 +869,7 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
 int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false;
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
     ctx->hKinematic.assign(kinematic, kinematic + nDyn);

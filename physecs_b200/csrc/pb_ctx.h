@@ -15,6 +15,7 @@
 #define PB_MAX_JOINT_ROWS 8
 #define PB_ISLAND_LOCAL_MAX 1024  // constraints (manifolds + joints) an island may hold and still be solved inside one CTA
 #define PB_KEY_COLORS 128         // solve-order key of a manifold: group * 128 + colour * 2 + (numPoints > 1)
+#define PB_MAX_READ_CHUNKS 32     // chunks of a pb_get_state_begin read-back
 #define PB_SPILL_CAP 65536        // pairs per spill list (GJK / EPA bin, mesh bins) and step
 #define PB_SPILL_GJK_THREADS 128  // threads of k_np_gjk_spill == polytope scratch slots it owns
 #define PB_SPILL_MESH_WARPS 32    // warps of k_np_mesh_spill == mesh scratch slots (each lane of each warp owns a polytope slot too)
@@ -220,6 +221,9 @@ struct pb_ctx {
     // the scene untouched) and the host COLLECTS the outcome -- counters snapshot, status -- at the next call that synchronises with the
     // step (capi.cu collectStep).  stepPending: a step's outcome has not been collected yet; undo*: host bookkeeping to roll back then.
     cudaEvent_t evCounters = nullptr; bool stepPending = false;
+    bool stepBegun = false;          // pb_step_begin ran: the next pb_step continues behind its broadphase
+    bool mainMarked = false;         // evMainAtSet already holds "the main stream before this step's broadphase": uploads wait for that
+    cudaEvent_t evRead[PB_MAX_READ_CHUNKS] = {nullptr}; int readFirst[PB_MAX_READ_CHUNKS] = {0}, readCount[PB_MAX_READ_CHUNKS] = {0}, readChunks = 0;   // pb_get_state_begin / _wait
     int rawHint = -1;                // raw manifold count of the last collected step (-1: none yet): shapes grids only
     bool undoCacheValid = false, undoCacheBuilt = false; int undoVelSwaps = 0;
     // PB_DETERMINISTIC=1 (or pb_set_deterministic): colours by fixed priorities (contacts.cu k_color_jp) -- two runs of the same scene give

@@ -840,8 +840,24 @@ void Scene::simulate(float timeStep) {
             }
         }
     };
+    // The step's head goes to the device first: counters reset + broadphase, which run on the bounds the previous step left (as the
+    // reference's sweep does, Physecs.cpp:119-173) and need nothing from the registry.  The gather below overlaps it.
+    S.check(pb_step_begin(S.ctx), "pb_step_begin");
+    // dynamic rows in chunks: each chunk's upload (copy stream) starts as soon as the worker threads have gathered it
+    const int nChunks = nDyn >= 65536 ? 8 : 1;
+    const size_t perChunk = ((size_t)nDyn + nChunks - 1) / nChunks;
+    auto gatherAndUpload = [&]() {
+        for (int c = 0; c < nChunks; ++c) {
+            const size_t first = (size_t)c * perChunk;
+            if (first >= (size_t)nDyn) break;
+            const size_t count = std::min(perChunk, (size_t)nDyn - first);
+            S.workers.parallelFor(count, [&](size_t b, size_t e) { gatherDyn(first + b, first + e); });
+            S.check(pb_set_state_rows(S.ctx, (int)first, (int)count, S.hPos.p + 3 * first, S.hQuat.p + 4 * first, S.hVel.p + 3 * first, S.hAng.p + 3 * first), "pb_set_state_rows");
+        }
+    };
     if (full) {
-        S.workers.parallelFor((size_t)nDyn, gatherDyn);
+        // static poses first: pb_set_static_poses runs on the main stream and waits for any pending state upload, so issued after the
+        // dynamic rows it would serialise their H2D (copy stream, hidden behind the broadphase) in front of the rest of the step
         S.workers.parallelFor((size_t)nStatic, [&](size_t b, size_t e) {
             for (size_t i = b; i < e; ++i) {
                 const TransformComponent& t = transformOf(nDyn + (int)i);
@@ -850,29 +866,31 @@ void Scene::simulate(float timeStep) {
                 q[0] = t.orientation.x; q[1] = t.orientation.y; q[2] = t.orientation.z; q[3] = t.orientation.w;
             }
         });
+        S.check(pb_set_static_poses(S.ctx, nStatic, S.hSPos.p, S.hSQuat.p), "pb_set_static_poses");
+        gatherAndUpload();
     } else if (!S.touched.empty()) {
         // device-authoritative: the staging buffers still hold the previous step's result; refresh only announced rows
-        if (!S.stagingValid) S.workers.parallelFor((size_t)nDyn, gatherDyn);
-        else for (unsigned r : S.touched) if ((int)r < nDyn) gatherDyn(r, r + 1);
+        if (!S.stagingValid) gatherAndUpload();
+        else {
+            for (unsigned r : S.touched) if ((int)r < nDyn) gatherDyn(r, r + 1);
+            S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
+        }
     }
+    S.touched.clear();
+    // direct writes to isKinematic / mass properties seen during the gather (the reference reads them live): these calls wait for the
+    // uploads; a kinematic flip also changes which colliders query the broadphase, so the head of the step is redone (pb_step does it)
     if (kinChanged.load()) S.check(pb_set_kinematic(S.ctx, nDyn, S.kin.data()), "pb_set_kinematic");
     if (massChanged.load()) S.check(pb_set_mass(S.ctx, nDyn, S.invMass.data(), S.com.data(), S.invI.data()), "pb_set_mass");
     const double gatherMs = msSince(tGather);
 
     // ---- device step ---------------------------------------------------------------------------------------------------------------
-    // static poses first: pb_set_static_poses runs on the main stream and waits for any pending pb_set_state upload, so issued after
-    // it the dynamic state's H2D (copy stream, meant to hide behind the broadphase) would be serialised in front of the step
-    if (full) S.check(pb_set_static_poses(S.ctx, nStatic, S.hSPos.p, S.hSQuat.p), "pb_set_static_poses");
-    if (full || !S.touched.empty())
-        S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
-    S.touched.clear();
     // pb_step only enqueues: an arena that overflows is noticed on the device (the step then skips its solve and leaves the scene as it
-    // was) and reported by the next call that synchronises with the step -- pb_get_state here.  Nothing persistent was touched, so the
+    // was) and reported by the next call that synchronises with the step -- the read-back here.  Nothing persistent was touched, so the
     // arenas are enlarged in place and the step is run again.  The device counters keep counting past the capacity, so they tell
     // how much room the step needs.
     auto stepAndFetch = [&]() {
         int r = pb_step(S.ctx, timeStep, numSubSteps, numIterations, g);
-        if (r == PB_OK) r = pb_get_state(S.ctx, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p);
+        if (r == PB_OK) r = pb_get_state_begin(S.ctx, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p, nChunks);
         return r;
     };
     int rc = stepAndFetch();
@@ -886,24 +904,31 @@ void Scene::simulate(float timeStep) {
         S.caps.max_pairs = S.wantPairs = wantP; S.caps.max_manifolds = S.wantManifolds = wantM;
         rc = stepAndFetch();
     }
-    S.check(rc, "pb_step / pb_get_state");
+    S.check(rc, "pb_step / pb_get_state_begin");
     S.stagingValid = true;
 
-    // ---- scatter: pinned SoA -> registry (kinematic bodies are not integrated, Physecs.cpp:446, :497) ---------------------------
-    auto tScatter = Clock::now();
-    S.workers.parallelFor((size_t)nDyn, [&](size_t b, size_t e) {
-        for (size_t r = b; r < e; ++r) {
-            if (S.kin[r]) continue;
-            TransformComponent& t = transformOf((int)r);
-            RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
-            const float* p = S.hPos.p + 3 * r; const float* q = S.hQuat.p + 4 * r; const float* v = S.hVel.p + 3 * r; const float* w = S.hAng.p + 3 * r;
-            t.position = glm::vec3(p[0], p[1], p[2]);
-            t.orientation = glm::quat(q[3], q[0], q[1], q[2]);
-            d.velocity = glm::vec3(v[0], v[1], v[2]);
-            d.angularVelocity = glm::vec3(w[0], w[1], w[2]);
-        }
-    });
-    const double scatterMs = msSince(tScatter);
+    // ---- scatter: pinned SoA -> registry, chunk by chunk as the read-back arrives (kinematic bodies are not integrated,
+    // Physecs.cpp:446, :497)
+    double scatterMs = 0.0;
+    for (int c = 0; ; ++c) {
+        int first = 0, count = 0;
+        S.check(pb_get_state_wait(S.ctx, c, &first, &count), "pb_get_state_wait");
+        if (count <= 0) break;
+        auto tScatter = Clock::now();
+        S.workers.parallelFor((size_t)count, [&](size_t b, size_t e) {
+            for (size_t r = (size_t)first + b; r < (size_t)first + e; ++r) {
+                if (S.kin[r]) continue;
+                TransformComponent& t = transformOf((int)r);
+                RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
+                const float* p = S.hPos.p + 3 * r; const float* q = S.hQuat.p + 4 * r; const float* v = S.hVel.p + 3 * r; const float* w = S.hAng.p + 3 * r;
+                t.position = glm::vec3(p[0], p[1], p[2]);
+                t.orientation = glm::quat(q[3], q[0], q[1], q[2]);
+                d.velocity = glm::vec3(v[0], v[1], v[2]);
+                d.angularVelocity = glm::vec3(w[0], w[1], w[2]);
+            }
+        });
+        scatterMs += msSince(tScatter);
+    }
 
     // ---- triggers: enter / exit diff against the previous step (Physecs.cpp:538-553) ---------------------------------------------
     pb_counts counts{};

@@ -60,11 +60,14 @@ def test_mtd_query_with_a_big_shape():
         return sorted(tuple(i) + tuple(v) for i, v in zip(ids.tolist(), val.view(np.int32).tolist()))
     try:
         pos = np.array([0.3, 0.2, 0.4], np.float32); quat = np.array([0, 0, 0, 1], np.float32)
+        most = 0
         for typ, prm in ((S.SPHERE, (1.5,)), (S.BOX, (2.0, 0.3, 1.5)), (S.CAPSULE, (1.2, 0.4))):
             g = rows(hs.overlap_mtd(pos, quat, typ, prm, -1))
             r = rows(ref.overlap_mtd(pos, quat, typ, prm, -1))
-            assert len(g) == len(r) and len(g) > 24, (typ, len(g), len(r))
+            assert len(g) == len(r) and len(g) > 16, (typ, len(g), len(r))
             assert g == r, f"type {typ}: first rows {g[:2]} vs {r[:2]}"
+            most = max(most, len(g))
+        assert most > 24, "no query met more triangles than a per-thread contact list holds: the spill path was not exercised"
     finally:
         hs.close(); ref.close()
 
