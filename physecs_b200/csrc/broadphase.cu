@@ -435,28 +435,67 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
 // The tree is still built on demand for the scene queries (queries.cu).
 #define PB_BRUTE_FORCE_MAX 8192
 #define BF_TILE 128
+// Tile culling: colliders are stored in creation order, and creation order is spatially coherent in the scenes this path exists for
+// (a batch of little scenes laid out side by side: 128 consecutive colliders are ~10 neighbouring scenes).  k_tile_bounds keeps the
+// union box of every tile of 128 colliders (enabled ones only); a CTA skips, as a whole, every tile whose box misses the union box of
+// its own 128 queries, and a thread skips a tile its own box misses.  Pure culling of tests that cannot succeed: same pair set.
+__global__ void __launch_bounds__(BF_TILE) k_tile_bounds(int n, const int* __restrict__ colFlags, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                                                        float4* __restrict__ tileMin, float4* __restrict__ tileMax) {
+    __shared__ float red[BF_TILE / 32][6];
+    const int i = blockIdx.x * BF_TILE + threadIdx.x;
+    V3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
+    if (i < n && (colFlags[i] & COLF_ENABLE)) { mn = mk3(aabbMin[i]); mx = mk3(aabbMax[i]); }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, d)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, d)); mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, d));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, d)); mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, d));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[w][0] = mn.x; red[w][1] = mn.y; red[w][2] = mn.z; red[w][3] = mx.x; red[w][4] = mx.y; red[w][5] = mx.z; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < BF_TILE / 32; ++k) {
+            mn = vmin(mn, mk3(red[k][0], red[k][1], red[k][2])); mx = vmax(mx, mk3(red[k][3], red[k][4], red[k][5]));
+        }
+        tileMin[blockIdx.x] = f4(mn); tileMax[blockIdx.x] = f4(mx);
+    }
+}
+
 __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPerSlice, const int* __restrict__ colFlags, const int* __restrict__ colRow,
                                                              const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                                                             const float4* __restrict__ tileMin, const float4* __restrict__ tileMax,
                                                              int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
     __shared__ float4 smn[BF_TILE], smx[BF_TILE];
     __shared__ int sflag[BF_TILE], srow[BF_TILE];
+    __shared__ float qred[BF_TILE / 32][6];
     const int a = blockIdx.x * BF_TILE + threadIdx.x;
     bool active = false;
-    V3 amn = mk3(0.f), amx = mk3(0.f);
+    V3 amn = mk3(FLT_MAX), amx = mk3(-FLT_MAX);       // empty box: meets nothing
     int rowA = -1;
     if (a < n) {
         active = (colFlags[a] & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
         if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = colRow[a]; }
     }
+    // union box of this CTA's queries
+    V3 qmn = amn, qmx = amx;
+    for (int d = 16; d > 0; d >>= 1) {
+        qmn.x = fminf(qmn.x, __shfl_xor_sync(0xffffffffu, qmn.x, d)); qmn.y = fminf(qmn.y, __shfl_xor_sync(0xffffffffu, qmn.y, d)); qmn.z = fminf(qmn.z, __shfl_xor_sync(0xffffffffu, qmn.z, d));
+        qmx.x = fmaxf(qmx.x, __shfl_xor_sync(0xffffffffu, qmx.x, d)); qmx.y = fmaxf(qmx.y, __shfl_xor_sync(0xffffffffu, qmx.y, d)); qmx.z = fmaxf(qmx.z, __shfl_xor_sync(0xffffffffu, qmx.z, d));
+    }
+    if ((threadIdx.x & 31) == 0) { float* r = qred[threadIdx.x >> 5]; r[0] = qmn.x; r[1] = qmn.y; r[2] = qmn.z; r[3] = qmx.x; r[4] = qmx.y; r[5] = qmx.z; }
+    __syncthreads();
+    for (int k = 0; k < BF_TILE / 32; ++k) { qmn = vmin(qmn, mk3(qred[k][0], qred[k][1], qred[k][2])); qmx = vmax(qmx, mk3(qred[k][3], qred[k][4], qred[k][5])); }
+    if (qmn.x > qmx.x) return;                 // no querying collider in this CTA (uniform)
     const int firstTile = blockIdx.y * tilesPerSlice;
     for (int t = firstTile; t < firstTile + tilesPerSlice; ++t) {
         const int base = t * BF_TILE;
         if (base >= n) break;                 // uniform across the CTA
+        const float4 tmn = tileMin[t], tmx = tileMax[t];
+        if (!overlaps(qmn, qmx, tmn, tmx)) continue;      // uniform across the CTA: the whole tile is out of reach
         const int b0 = base + threadIdx.x;
         if (b0 < n) { smn[threadIdx.x] = aabbMin[b0]; smx[threadIdx.x] = aabbMax[b0]; sflag[threadIdx.x] = colFlags[b0]; srow[threadIdx.x] = colRow[b0]; }
         else sflag[threadIdx.x] = 0;
         __syncthreads();
-        if (active) {
+        if (active && overlaps(amn, amx, tmn, tmx)) {
             const int cnt = min(BF_TILE, n - base);
             for (int j = 0; j < cnt; ++j) {
                 const int fb = sflag[j];
@@ -507,8 +546,10 @@ int pb_broadphase(pb_ctx* ctx) {
         if (slices > tiles) slices = tiles;
         if (slices < 1) slices = 1;
         const int tilesPerSlice = (tiles + slices - 1) / slices;
+        // tile boxes live in the (otherwise idle) tree node arrays: tiles <= 64 entries of nodeMin / nodeMax
+        ++ctx->launches, k_tile_bounds<<<tiles, BF_TILE, 0, ctx->stream>>>(n, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
         ++ctx->launches, k_pairs_bruteforce<<<dim3(tiles, slices), BF_TILE, 0, ctx->stream>>>(n, tilesPerSlice, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
-                                                                                          (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
+                                                                                          ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
         PB_CUDA(ctx, cudaGetLastError());
         return PB_OK;
     }

@@ -182,22 +182,24 @@ __device__ inline int buildJointRows(int type, float4 prm0, float4 prm1, float4&
 // per substep and colour: fill rows (makeConstraints), effective masses, NGS pseudo-velocity pass (Constraint1DW.cpp:6-115)
 // All arrays a step mutates (poses, pseudo velocities, world inertia, joint rows / state / impulses) are read with __ldcg:
 // inside the persistent substep kernel they are written by other SMs between grid barriers, and L1 is not coherent.
+// L1: see ldm() above (the whole-step kernel's group-by-group form)
+template <bool L1 = false>
 __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const int* __restrict__ kinematic,
                                     const float4* pos, const float4* quat, const float4* __restrict__ comInvMass,
                                     const float4* bodyRec, float4* pseudoLin, float4* pseudoAng) {
     int type = J.type[j];
     int2 rr = J.rows[j];
     int2 bb_ = J.bodies[j]; int b0 = bb_.x, b1 = bb_.y;
-    Q4 q0 = mkq(__ldcg(&quat[rr.x])), q1 = mkq(__ldcg(&quat[rr.y]));
+    Q4 q0 = mkq(ldm<L1>(&quat[rr.x])), q1 = mkq(ldm<L1>(&quat[rr.y]));
     V3 a0p = mk3(J.a0p[j]), a1p = mk3(J.a1p[j]);
     // JointSolverData r0/r1 (Physecs.cpp:344-345) and calculateWorldSpaceData (Joint.cpp:5-14)
     V3 r0l = b0 >= 0 ? a0p - mk3(comInvMass[b0]) : a0p;
     V3 r1l = b1 >= 0 ? a1p - mk3(comInvMass[b1]) : a1p;
     M3 u0 = mat3_cast(qmul(q0, mkq(J.a0q[j]))), u1 = mat3_cast(qmul(q1, mkq(J.a1q[j])));
     V3 r0 = rotate(q0, r0l), r1 = rotate(q1, r1l);
-    V3 p0 = mk3(__ldcg(&pos[rr.x])) + rotate(q0, a0p), p1 = mk3(__ldcg(&pos[rr.y])) + rotate(q1, a1p);
+    V3 p0 = mk3(ldm<L1>(&pos[rr.x])) + rotate(q0, a0p), p1 = mk3(ldm<L1>(&pos[rr.y])) + rotate(q1, a1p);
     float4 prm0 = J.prm[2 * j], prm1 = J.prm[2 * j + 1];
-    float4 st0 = __ldcg(&J.state[2 * j]), st1 = __ldcg(&J.state[2 * j + 1]);
+    float4 st0 = ldm<L1>(&J.state[2 * j]), st1 = ldm<L1>(&J.state[2 * j + 1]);
     Row rows[MAXR];
     int n = buildJointRows(type, prm0, prm1, st0, st1, true, p0, p1, r0, r1, u0, u1, rows);
     if (type == PB_JOINT_GEAR) { J.state[2 * j] = st0; J.state[2 * j + 1] = st1; }
@@ -208,18 +210,18 @@ __device__ inline void jointPrepOne(const JointDev& J, int j, int doNgs, const i
     if (b0 >= 0) {
         im0 = comInvMass[b0].w;
         {   // world inverse inertia from the per-substep body record (solver.cu, BodyRec layout)
-            const float4* r = bodyRec + 8 * (size_t)b0; float4 r2 = __ldcg(r + 2), r6 = __ldcg(r + 6), r7 = __ldcg(r + 7);
+            const float4* r = bodyRec + 8 * (size_t)b0; float4 r2 = ldm<L1>(r + 2), r6 = ldm<L1>(r + 6), r7 = ldm<L1>(r + 7);
             I0.c[0] = mk3(r6); I0.c[1] = mk3(r6.w, r7.x, r7.y); I0.c[2] = mk3(r7.z, r7.w, r2.w);
         }
-        float4 l = __ldcg(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(__ldcg(&pseudoAng[b0]));
+        float4 l = ldm<L1>(&pseudoLin[b0]); pv0 = mk3(l); cnt0 = __float_as_int(l.w); pw0 = mk3(ldm<L1>(&pseudoAng[b0]));
     }
     if (b1 >= 0) {
         im1 = comInvMass[b1].w;
         {
-            const float4* r = bodyRec + 8 * (size_t)b1; float4 r2 = __ldcg(r + 2), r6 = __ldcg(r + 6), r7 = __ldcg(r + 7);
+            const float4* r = bodyRec + 8 * (size_t)b1; float4 r2 = ldm<L1>(r + 2), r6 = ldm<L1>(r + 6), r7 = ldm<L1>(r + 7);
             I1.c[0] = mk3(r6); I1.c[1] = mk3(r6.w, r7.x, r7.y); I1.c[2] = mk3(r7.z, r7.w, r2.w);
         }
-        float4 l = __ldcg(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(__ldcg(&pseudoAng[b1]));
+        float4 l = ldm<L1>(&pseudoLin[b1]); pv1 = mk3(l); cnt1 = __float_as_int(l.w); pw1 = mk3(ldm<L1>(&pseudoAng[b1]));
     }
     for (int r = 0; r < n; ++r) {
         int flags = jointRowFlags(type, r, prm0, st0);

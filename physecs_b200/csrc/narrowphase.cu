@@ -17,6 +17,7 @@
 #include "np_overlap.cuh"
 #include <mutex>
 #include <unordered_map>
+#include <algorithm>
 
 #define COLF_TRIGGER 1
 #define COLF_ENABLE 2
@@ -163,15 +164,15 @@ __device__ __forceinline__ void storeManifold(int slot, int maxManifolds, int co
 
 // ---- analytic bins ------------------------------------------------------------------------------------------------
 template <int BIN>
-__global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
-                                                 const int* __restrict__ colType, const float4* __restrict__ colParams,
-                                                 const float4* __restrict__ wpos, const float4* __restrict__ wquat,
-                                                 const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
-                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
-                                                 int* __restrict__ spillList) {
+__device__ __forceinline__ void npPrimBody(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                           const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                           const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                           const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                           int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                           int* __restrict__ spillList, const int bx, const int gx) {
     int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1];
     int lane = threadIdx.x & 31;
-    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
+    for (int base = start + ((bx * blockDim.x + threadIdx.x) & ~31); base < end; base += gx * blockDim.x) {
         int idx = base + lane;
         bool hit = false, flip = false;
         Manifold m; m.np = 0; m.tri = -1;
@@ -206,6 +207,29 @@ __global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs,
         int slot = warpReserve(hit ? 1 : 0, &counters[CNT_RAWM]);
         if (hit) storeManifold(slot, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
     }
+}
+
+template <int BIN>
+__global__ void __launch_bounds__(128) k_np_prim(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                 const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                 const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                 const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                 int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                 int* __restrict__ spillList) {
+    npPrimBody<BIN>(pairs, pairOrder, counters, colType, colParams, wpos, wquat, convexes, colMesh, mKey, mNormal, mPts, maxManifolds, spillList, blockIdx.x, gridDim.x);
+}
+
+// Small scenes: the six analytic bins in ONE launch (blockIdx.y = bin) -- they then overlap instead of queueing behind one another, and a
+// step saves five launches; each bin of such a scene holds a few thousand pairs at most and cannot fill the device on its own.
+__global__ void __launch_bounds__(128) k_np_prim_all(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
+                                                     const int* __restrict__ colType, const float4* __restrict__ colParams,
+                                                     const float4* __restrict__ wpos, const float4* __restrict__ wquat,
+                                                     const PbConvexDev* __restrict__ convexes, const int* __restrict__ colMesh,
+                                                     int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
+                                                     int* __restrict__ spillList) {
+#define PB_BIN_CASE(B) case B: npPrimBody<B>(pairs, pairOrder, counters, colType, colParams, wpos, wquat, convexes, colMesh, mKey, mNormal, mPts, maxManifolds, spillList, blockIdx.x, gridDim.x); break;
+    switch (blockIdx.y) { PB_BIN_CASE(BIN_SS) PB_BIN_CASE(BIN_SC) PB_BIN_CASE(BIN_CC) PB_BIN_CASE(BIN_SB) PB_BIN_CASE(BIN_CB) PB_BIN_CASE(BIN_BB) }
+#undef PB_BIN_CASE
 }
 
 // ---- GJK bin in two launches (the step; scene queries use k_np_prim<BIN_GJK>) ------------------------------------------------------
@@ -978,7 +1002,13 @@ int pb_narrowphase(pb_ctx* ctx) {
     const int2* pairs = (const int2*)ctx->pairs;
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<npGrid(ctx, k_np_prim<BIN>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, ctx->spillList)
-    LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
+    if (ctx->pairsHint >= 0 && ctx->pairsHint <= 131072 && ctx->npFuseSmall) {
+        const int gx = std::max(1, std::min(ctx->numSMs * 2, (ctx->pairsHint + 127) / 128 + 1));
+        ++ctx->launches, k_np_prim_all<<<dim3(gx, 6), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colWPos, ctx->colWQuat,
+            ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, ctx->spillList);
+    } else {
+        LAUNCH_PRIM(BIN_SS); LAUNCH_PRIM(BIN_SC); LAUNCH_PRIM(BIN_CC); LAUNCH_PRIM(BIN_SB); LAUNCH_PRIM(BIN_CB); LAUNCH_PRIM(BIN_BB);
+    }
     if (!ctx->convexes.empty()) {
         // hit list: one entry per intersecting pair, i.e. per manifold of the bin -> the manifold capacity bounds it
         int want = ctx->caps.max_manifolds < ctx->caps.max_pairs ? ctx->caps.max_manifolds : ctx->caps.max_pairs;

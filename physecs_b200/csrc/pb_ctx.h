@@ -136,6 +136,7 @@ struct pb_ctx {
     int* bigList = nullptr;             // [1 + 32] count + colliders of the step's big-static side list (broadphase.cu k_morton)
     int bigListMode = 1;                // 0: every collider stays in the step's tree (env PB_BIG_LIST)
     int pairsHint = -1;                 // candidate pairs of the previous step (-1: none yet): bounds the bin kernels' grids on small scenes
+    int npFuseSmall = 1;                // small scenes: the six analytic bins in one launch (env PB_NP_FUSE=0: one launch per bin)
     int npWaves = 4;                    // narrowphase bin kernels: grid = SMs x co-resident CTAs x npWaves (env PB_NP_WAVES; 0 = the former numSMs * 8)
     int bruteForceMax = 8192;           // colliders up to which the step tests all pairs directly instead of building the tree (env PB_BRUTE_FORCE_MAX)
     bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)

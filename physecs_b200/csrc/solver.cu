@@ -88,9 +88,15 @@ __device__ __forceinline__ V3 solve33(const M3& A, V3 b) {
 //   r0 q.xyzw | r1 comWorld.xyz, invMass | r2 v.xyz (substep start), I.c2.z | r3 w.xyz (substep start) |
 //   r4 vPre.xyz | r5 wPre.xyz | r6 I.c0.xyz, I.c1.x | r7 I.c1.y, I.c1.z, I.c2.x, I.c2.y        (I = world inverse inertia)
 struct BodyRec { Q4 q; V3 com; float im; V3 v, w, vp, wp; M3 I; };
+// CL = "CTA-local": the caller is the whole-step kernel carrying ONE group of islands through the step (k_step_solve_small, group by
+// group): every mutable word it touches is written by its own CTA only, for the whole kernel, so plain (L1-cached) loads and stores
+// are coherent -- a dependent access then costs an L1 hit instead of an L2 round trip.  Otherwise L2 (.cg), as everywhere else.
+template <bool CL, class T> __device__ __forceinline__ T ldq(const T* p) { if (CL) return *p; return __ldcg(p); }
+template <bool CL, class T> __device__ __forceinline__ void stq(T* p, T v) { if (CL) *p = v; else __stcg(p, v); }
+template <bool CL = false>
 __device__ __forceinline__ BodyRec loadBodyRec(const float4* rec, int b) {
     const float4* r = rec + 8 * (size_t)b;
-    float4 r0 = __ldcg(r), r1 = __ldcg(r + 1), r2 = __ldcg(r + 2), r3 = __ldcg(r + 3), r4 = __ldcg(r + 4), r5 = __ldcg(r + 5), r6 = __ldcg(r + 6), r7 = __ldcg(r + 7);
+    float4 r0 = ldq<CL>(r), r1 = ldq<CL>(r + 1), r2 = ldq<CL>(r + 2), r3 = ldq<CL>(r + 3), r4 = ldq<CL>(r + 4), r5 = ldq<CL>(r + 5), r6 = ldq<CL>(r + 6), r7 = ldq<CL>(r + 7);
     BodyRec B;
     B.q = mkq(r0); B.com = mk3(r1); B.im = r1.w; B.v = mk3(r2); B.w = mk3(r3); B.vp = mk3(r4); B.wp = mk3(r5);
     B.I.c[0] = mk3(r6); B.I.c[1] = mk3(r6.w, r7.x, r7.y); B.I.c[2] = mk3(r7.z, r7.w, r2.w);
@@ -143,16 +149,17 @@ template <bool L1, class T> __device__ __forceinline__ void stSolve(T* p, T v, u
 __device__ __forceinline__ int rowIndex(const SubstepParams& P, int s, int po, int k) { return k == 0 ? s : P.rowExtra + (po - s) + (k - 1); }
 
 // ---- phases (one unit of work each) -------------------------------------------------------------------------------------------------
+template <bool CL = false>
 __device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const float4* vel, const float4* angvel, float4* velLive, float4* angvelLive) {
     if (P.kinematic[i]) {    // not integrated (Physecs.cpp:446); the component value just follows the buffer swap
-        velLive[2 * i] = __ldcg(&vel[2 * i]); angvelLive[2 * i] = __ldcg(&angvel[2 * i]);
+        velLive[2 * i] = ldq<CL>(&vel[2 * i]); angvelLive[2 * i] = ldq<CL>(&angvel[2 * i]);
         return;
     }
-    M3 rot = mat3_cast(mkq(__ldcg(&P.quat[i])));
+    M3 rot = mat3_cast(mkq(ldq<CL>(&P.quat[i])));
     M3 invRot = transpose(rot);
-    float4 vin = __ldcg(&vel[2 * i]);          // .w carries invMass (the solver's gathers get it for free)
+    float4 vin = ldq<CL>(&vel[2 * i]);          // .w carries invMass (the solver's gathers get it for free)
     V3 v = mk3(vin) + P.h * mk3(0.f, -P.g, 0.f);
-    V3 wl = mul(invRot, mk3(__ldcg(&angvel[2 * i])));
+    V3 wl = mul(invRot, mk3(ldq<CL>(&angvel[2 * i])));
     M3 invI = loadM3ro(P.invIL, i);
     M3 I = inverse(invI);
     V3 Iw = mul(I, wl);
@@ -167,15 +174,16 @@ __device__ __forceinline__ void integrateV(const SubstepParams& P, int i, const 
     }
     M3 IW = mul(mul(rot, invI), invRot);
     float4 c = P.comInvMass[i];
-    Q4 q = mkq(__ldcg(&P.quat[i]));
-    V3 comW = mk3(__ldcg(&P.pos[i])) + rotate(q, mk3(c));      // same expression contact prep used to evaluate per manifold
+    Q4 q = mkq(ldq<CL>(&P.quat[i]));
+    V3 comW = mk3(ldq<CL>(&P.pos[i])) + rotate(q, mk3(c));      // same expression contact prep used to evaluate per manifold
     float4* r = P.bodyRec + 8 * (size_t)i;
     r[0] = f4(q); r[1] = f4(comW, c.w);
-    r[2] = f4(mk3(vin), IW.c[2].z); r[3] = f4(mk3(__ldcg(&angvel[2 * i])));
+    r[2] = f4(mk3(vin), IW.c[2].z); r[3] = f4(mk3(ldq<CL>(&angvel[2 * i])));
     r[4] = f4(v); r[5] = f4(w);
     r[6] = f4(IW.c[0], IW.c[1].x); r[7] = make_float4(IW.c[1].y, IW.c[1].z, IW.c[2].x, IW.c[2].y);
 }
 
+template <bool CL = false>
 __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const float4* vel, const float4* angvel) {
     int4 hd = P.cHead[s];
     int2 bb = make_int2(hd.x, hd.y);
@@ -187,10 +195,10 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
     float im0 = 0.f, im1 = 0.f;
     M3 I0, I1;
     I0.c[0] = I0.c[1] = I0.c[2] = mk3(0.f); I1 = I0;
-    if (bb.x >= 0) { BodyRec B = loadBodyRec(P.bodyRec, bb.x); q0 = B.q; com0 = B.com; im0 = B.im; v0 = B.v; w0 = B.w; vp0 = B.vp; wp0 = B.wp; I0 = B.I; }
-    else q0 = mkq(__ldcg(&P.quat[rr.x]));       // static / kinematic side: only its orientation matters (quirk Q25)
-    if (bb.y >= 0) { BodyRec B = loadBodyRec(P.bodyRec, bb.y); q1 = B.q; com1 = B.com; im1 = B.im; v1 = B.v; w1 = B.w; vp1 = B.vp; wp1 = B.wp; I1 = B.I; }
-    else q1 = mkq(__ldcg(&P.quat[rr.y]));
+    if (bb.x >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.x); q0 = B.q; com0 = B.com; im0 = B.im; v0 = B.v; w0 = B.w; vp0 = B.vp; wp0 = B.wp; I0 = B.I; }
+    else q0 = mkq(ldq<CL>(&P.quat[rr.x]));       // static / kinematic side: only its orientation matters (quirk Q25)
+    if (bb.y >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.y); q1 = B.q; com1 = B.com; im1 = B.im; v1 = B.v; w1 = B.w; vp1 = B.vp; wp1 = B.wp; I1 = B.I; }
+    else q1 = mkq(ldq<CL>(&P.quat[rr.y]));
     int po = hd.z, np = hd.w & 0xff;
     for (int k = 0; k < np; ++k) {
         float4 a = P.pR0T[po + k];
@@ -215,14 +223,14 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
             lamT0 = relT / kT;
         }
         const int ri = rowIndex(P, s, po, k);
-        __stcg(&P.rowA[ri], f4(r0xn, cn));
-        __stcg(&P.rowB[ri], f4(r1xn, kN));
-        __stcg(&P.rowC[ri], f4(r0xnt, a.w));
-        __stcg(&P.rowD[ri], f4(r1xnt, lamT0));
-        __stcg(&P.rowE[ri], f4(t, kT != 0.f ? 1.f : 0.f));
-        __stcg(&P.rowF[ri], f4(r0xtt, 0.f));
-        __stcg(&P.rowG[ri], f4(r1xtt, 0.f));
-        __stcg(&P.rowL[ri], make_float2(0.f, 0.f));
+        stq<CL>(&P.rowA[ri], f4(r0xn, cn));
+        stq<CL>(&P.rowB[ri], f4(r1xn, kN));
+        stq<CL>(&P.rowC[ri], f4(r0xnt, a.w));
+        stq<CL>(&P.rowD[ri], f4(r1xnt, lamT0));
+        stq<CL>(&P.rowE[ri], f4(t, kT != 0.f ? 1.f : 0.f));
+        stq<CL>(&P.rowF[ri], f4(r0xtt, 0.f));
+        stq<CL>(&P.rowG[ri], f4(r1xtt, 0.f));
+        stq<CL>(&P.rowL[ri], make_float2(0.f, 0.f));
     }
 }
 
@@ -367,19 +375,20 @@ __device__ __forceinline__ void contactSolveQuad(const SubstepParams& P, int s, 
     }
 }
 
+template <bool CL = false>
 __device__ __forceinline__ void integrateX(const SubstepParams& P, int i, const float4* velLive, const float4* angvelLive) {
     if (P.kinematic[i]) return;
     // no joints: nobody wrote the pseudo velocities, the same zeros go through the same arithmetic without the 64 B per body of traffic
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-    float4 pl = P.hasJoints ? __ldcg(&P.pseudoLin[i]) : zero4;
+    float4 pl = P.hasJoints ? ldq<CL>(&P.pseudoLin[i]) : zero4;
     int cnt = __float_as_int(pl.w);
     float scale = cnt ? 1.f / (float)cnt : 1.f;
-    V3 p = mk3(__ldcg(&P.pos[i]));
-    Q4 q = mkq(__ldcg(&P.quat[i]));
+    V3 p = mk3(ldq<CL>(&P.pos[i]));
+    Q4 q = mkq(ldq<CL>(&P.quat[i]));
     V3 com = mk3(P.comInvMass[i]);
-    p = p + (P.h * mk3(__ldcg(&velLive[2 * i])) + scale * mk3(pl));
+    p = p + (P.h * mk3(ldq<CL>(&velLive[2 * i])) + scale * mk3(pl));
     V3 prevCom = rotate(q, com);
-    V3 hw = 0.5f * (P.h * mk3(__ldcg(&angvelLive[2 * i])) + scale * mk3(P.hasJoints ? __ldcg(&P.pseudoAng[i]) : zero4));
+    V3 hw = 0.5f * (P.h * mk3(ldq<CL>(&angvelLive[2 * i])) + scale * mk3(P.hasJoints ? ldq<CL>(&P.pseudoAng[i]) : zero4));
     Q4 dq; dq.w = 0.f; dq.x = hw.x; dq.y = hw.y; dq.z = hw.z;
     Q4 add = qmul(dq, q);
     q.x += add.x; q.y += add.y; q.z += add.z; q.w += add.w;
@@ -565,7 +574,7 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
             }
         }
         __syncthreads();
-        for (int k = P.bodyStart[g] + threadIdx.x; k < P.bodyStart[g + 1]; k += blockDim.x) integrateX(P, P.bodyOrder[k], velLive, angvelLive);
+        for (int k = P.bodyStart[g] + threadIdx.x; k < P.bodyStart[g + 1]; k += blockDim.x) integrateX<true>(P, P.bodyOrder[k], velLive, angvelLive);
         __syncthreads();
         if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
         return;
@@ -663,13 +672,13 @@ __global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_consta
                 const int j0 = P.hasJoints ? P.jointStart[g * 8] : 0, j1 = P.hasJoints ? P.jointStart[g * 8 + 8] : 0;
                 float4* v = P.velA; float4* w = P.angvelA; float4* vL = P.velB; float4* wL = P.angvelB;
                 for (int sub = 0; sub < P.substeps; ++sub) {
-                    for (int k = b0 + threadIdx.x; k < b1; k += blockDim.x) integrateV(P, P.bodyOrder[k], v, w, vL, wL);
+                    for (int k = b0 + threadIdx.x; k < b1; k += blockDim.x) integrateV<true>(P, P.bodyOrder[k], v, w, vL, wL);
                     __syncthreads();
-                    for (int s = m0 + threadIdx.x; s < m1; s += blockDim.x) contactPrep(P, s, v, w);
+                    for (int s = m0 + threadIdx.x; s < m1; s += blockDim.x) contactPrep<true>(P, s, v, w);
                     for (int k = j0 + threadIdx.x; k < j1; k += blockDim.x)
-                        jointPrepOne(P.J, P.jointOrder[k], 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.bodyRec, P.pseudoLin, P.pseudoAng);
+                        jointPrepOne<true>(P.J, P.jointOrder[k], 0, P.kinematic, P.pos, P.quat, P.comInvMass, P.bodyRec, P.pseudoLin, P.pseudoAng);
                     __syncthreads();
-                    substepColoured<false, true>(P, bar, vL, wL, sRuns, sJoint, g);
+                    substepColoured<true, true>(P, bar, vL, wL, sRuns, sJoint, g);
                     __syncthreads();
                     float4* t = v; v = vL; vL = t;
                     t = w; w = wL; wL = t;

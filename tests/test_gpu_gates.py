@@ -137,7 +137,7 @@ def test_device_sort(n, bits, coop, monkeypatch):
 
 
 @pytest.mark.parametrize("fused_local_max", [0, 65536])
-@pytest.mark.parametrize("maker,steps", [(lambda: S.ragdolls(300), 30), (lambda: S.terrain(3000, cells=64, drop=0.05), 40)])
+@pytest.mark.parametrize("maker,steps", [(lambda: S.ragdolls(300), 60), (lambda: S.terrain(3000, cells=64, drop=0.05), 40)])
 def test_whole_step_kernel_group_by_group(maker, steps, fused_local_max, monkeypatch):
     """Scenes whose constraints all sit in small islands (ragdoll batches, bodies spread over a terrain) take the one-launch whole-step
     kernel group by group -- every CTA carries its groups through all substeps with CTA barriers only (solver.cu k_step_solve_small);
