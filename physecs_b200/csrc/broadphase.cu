@@ -495,6 +495,9 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
         if (b0 < n) { smn[threadIdx.x] = aabbMin[b0]; smx[threadIdx.x] = aabbMax[b0]; sflag[threadIdx.x] = colFlags[b0]; srow[threadIdx.x] = colRow[b0]; }
         else sflag[threadIdx.x] = 0;
         __syncthreads();
+        // hits of this thread in this tile as a 128-bit mask; the pairs are appended afterwards with ONE atomic per warp and tile (a
+        // batch of 512 little scenes emits ~10 k pairs per step: one atomic per pair on the one counter was most of this kernel's time)
+        unsigned int hit[BF_TILE / 32] = {0, 0, 0, 0};
         if (active && overlaps(amn, amx, tmn, tmx)) {
             const int cnt = min(BF_TILE, n - base);
             for (int j = 0; j < cnt; ++j) {
@@ -504,7 +507,37 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
                 if ((fb & COLF_DYNAMIC) && b <= a) continue;      // a pair of two querying colliders is emitted by the lower index
                 if (srow[j] == rowA) continue;                    // same entity (Physecs.cpp:145)
                 if (!overlaps(amn, amx, smn[j], smx[j])) continue;
-                emitPair(a, b, colRow, rowEntity, pairs, counters, maxPairs);
+                hit[j >> 5] |= 1u << (j & 31);
+            }
+        }
+        {
+            const int mine = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
+            const int lane = threadIdx.x & 31;
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total) {                                          // warp-uniform
+                int wbase = 0;
+                if (lane == 31) wbase = atomicAdd(&counters[CNT_PAIRS], total);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                int slot = wbase + inc - mine;
+                if (mine) {
+                    const unsigned int ea = (unsigned int)rowEntity[rowA];
+                    for (int w = 0; w < BF_TILE / 32; ++w) {
+                        unsigned int m = hit[w];
+                        while (m) {
+                            const int j = 32 * w + __ffs(m) - 1;
+                            m &= m - 1;
+                            const int b = base + j;
+                            if (slot < maxPairs) {
+                                const unsigned int eb = (unsigned int)rowEntity[srow[j]];
+                                pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
+                            } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
+                            ++slot;
+                        }
+                    }
+                }
             }
         }
         __syncthreads();

@@ -224,6 +224,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     for (int b = 0; b < 2; ++b) { A(cacheTag[b], cs); A(cacheVal[b], cs); }
     A(counters, CNT_TOTAL);
     ctx->islandGroups = ctx->numSMs * 3;     // co-resident 256-thread CTAs of the persistent substep kernel
+    if (const char* e = getenv("PB_ISLAND_GROUPS")) if (atoi(e) > 0) ctx->islandGroups = atoi(e);      // experiments: more groups than CTAs (each CTA walks several)
     A(keyStart, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1); A(keyCursor, (size_t)(ctx->islandGroups + 1) * PB_KEY_COLORS + 1);
     A(triMeshDev, 64); A(convexDev, 256);
 #undef A

@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(128) k_contact_build(
     const int* __restrict__ prevNp, const float4* __restrict__ prevR0T,
     unsigned long long* __restrict__ curTag, int4* __restrict__ curVal, int cacheMask) {
     int n = counters[CNT_MANIFOLDS];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_POINTS] = n > 0 ? pointOfs[n - 1] + mKey[mSorted[n - 1]].w : 0;      // contact points of the step (taps)
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         int raw = mSorted[s];
         int4 key = mKey[raw];
@@ -457,7 +458,6 @@ int pb_contact_build(pb_ctx* ctx) {
     ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur]);
     rc = pb_exclusive_scan_dev(ctx, ctx->cNpBuf[cur], pointOfs, ctx->counters + CNT_MANIFOLDS, maxM, ctx->rawHint < 0 ? -1 : 2 * ctx->rawHint + 4096, (int*)ctx->radixHist);
     if (rc) return rc;
-    ++ctx->launches, k_count_points<<<1, 1, 0, ctx->stream>>>(ctx->counters, pointOfs, ctx->cNpBuf[cur]);
     cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
     ++ctx->launches, k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
         ctx->nDyn, ctx->kinematic, ctx->pos, ctx->quat, ctx->vel, ctx->angvel, ctx->comInvMass,

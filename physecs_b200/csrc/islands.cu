@@ -62,6 +62,66 @@ __global__ void k_island_hook_joints(int nJ, const int2* __restrict__ bodies, in
     int2 b = bodies[j];
     if (b.x >= 0 && b.y >= 0 && b.x != b.y) islandUnion(parent, b.x, b.y);
 }
+// both hooks in one launch (grid-stride over manifolds, then over joints): a step of a small scene is a chain of few-microsecond launches
+__global__ void k_island_hook(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
+                              int nDyn, const int* __restrict__ kinematic, int nJ, const int2* __restrict__ bodies, int* parent) {
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 key = mKey[i];
+        if (key.w <= 0) continue;
+        int b0 = islandSolverIndex(colRow[key.x], nDyn, kinematic), b1 = islandSolverIndex(colRow[key.y], nDyn, kinematic);
+        if (b0 >= 0 && b1 >= 0 && b0 != b1) islandUnion(parent, b0, b1);
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nJ; j += gridDim.x * blockDim.x) {
+        int2 b = bodies[j];
+        if (b.x >= 0 && b.y >= 0 && b.x != b.y) islandUnion(parent, b.x, b.y);
+    }
+}
+__global__ void k_island_count(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
+                               int nDyn, const int* __restrict__ kinematic, int nJ, const int2* __restrict__ bodies, int overflowStart, int localMax,
+                               const int* __restrict__ root, int* __restrict__ cnt) {
+    int n = min(counters[CNT_RAWM], maxManifolds);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 key = mKey[i];
+        if (key.w <= 0) continue;
+        int b = islandSolverIndex(colRow[key.x], nDyn, kinematic);
+        if (b < 0) b = islandSolverIndex(colRow[key.y], nDyn, kinematic);
+        if (b >= 0) atomicAdd(&cnt[root[b]], 1);
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nJ; j += gridDim.x * blockDim.x) {
+        int2 bb = bodies[j];
+        int b = bb.x >= 0 ? bb.x : bb.y;
+        if (b >= 0) atomicAdd(&cnt[root[b]], j >= overflowStart ? localMax + 1 : 1);     // overflow-bucket joints keep their island in the global sweep
+    }
+}
+// group of every body + the island statistics + (optionally) the per-group body histogram, one launch
+__global__ void __launch_bounds__(256) k_island_group_stats(int n, int* rootThenGroup, const int* __restrict__ cnt, int G, int localMax, int* __restrict__ stats,
+                                                            int* __restrict__ bodyHist) {
+    extern __shared__ int sh[];          // [G + 1] body histogram (bodyHist != nullptr)
+    __shared__ int red[2][8];
+    if (bodyHist) { for (int i = threadIdx.x; i <= G; i += blockDim.x) sh[i] = 0; __syncthreads(); }
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0, loc = 0;
+    if (i < n) {
+        int r = rootThenGroup[i];
+        int cr = cnt[r];
+        int g = cr <= localMax ? (int)min((long long)G - 1, (long long)r * G / n) : G;
+        rootThenGroup[i] = g;
+        if (bodyHist) atomicAdd(&sh[g], 1);
+        c = min(cnt[i], 1 << 20);            // cnt[] is non-zero exactly at the roots
+        loc = (c > 0 && g != G) ? c : 0;     // (a root's group is its island's group)
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); loc += __shfl_xor_sync(0xffffffffu, loc, d); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = c; red[1][threadIdx.x >> 5] = loc; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int t = 0;
+        for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+        if (t) atomicAdd(&stats[1 - threadIdx.x], t);
+    }
+    if (bodyHist) for (int k = threadIdx.x; k <= G; k += blockDim.x) if (sh[k]) atomicAdd(&bodyHist[k], sh[k]);
+}
 
 // roots go to a separate array: a concurrent path-halving write of another thread may still land on parent[i] after this one
 __global__ void k_island_compress(int n, int* parent, int* __restrict__ root) {
@@ -159,28 +219,33 @@ int pb_islands_build(pb_ctx* ctx) {
     const int G = ctx->islandGroups;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->islandStats, 0, sizeof(int) * 4, ctx->stream));
     ++ctx->launches, k_island_init<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->islandCount);
-    ++ctx->launches, k_island_hook_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->islandParent);
     JointDev J;
     const bool joints = pb_joint_view(ctx, &J);
-    if (joints) ++ctx->launches, k_island_hook_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->islandParent);
+    const int nJ = joints ? J.n : 0;
+    const int2* jb = joints ? J.bodies : nullptr;
+    int hookBlocks = blocks;
+    if (ctx->rawHint >= 0) hookBlocks = std::max(ctx->numSMs, std::min(blocks, (std::max(ctx->rawHint, nJ) + 255) / 256 + 1));
+    ++ctx->launches, k_island_hook<<<hookBlocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, nJ, jb, ctx->islandParent);
     ++ctx->launches, k_island_compress<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->bodyGroup);
-    ++ctx->launches, k_island_count_contacts<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, ctx->bodyGroup, ctx->islandCount);
-    if (joints) ++ctx->launches, k_island_count_joints<<<pb_grid(J.n, 256), 256, 0, ctx->stream>>>(J.n, J.bodies, ctx->jointColorStart[8], ctx->islandLocalMax, ctx->bodyGroup, ctx->islandCount);
-    // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
-    ++ctx->launches, k_island_group<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandLocalMax);
-    ++ctx->launches, k_island_stats<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandStats);
+    ++ctx->launches, k_island_count<<<hookBlocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, nJ, jb,
+                                                                         ctx->jointColorStart[8], ctx->islandLocalMax, ctx->bodyGroup, ctx->islandCount);
     // body lists per group for the whole-step kernel's group-by-group form (solver.cu k_step_solve_small): only scenes small enough to take it
+    const bool lists = n <= ctx->fusedLocalMax && ctx->fusedMode != 0;
     ctx->bodyListsBuilt = false;
-    if (n <= ctx->fusedLocalMax && ctx->fusedMode != 0) {
+    if (lists) {
         if (!ctx->bodyOrder) {
             int rc;
             if ((rc = pb_alloc(ctx, &ctx->bodyOrder, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->bodyStart, (size_t)G + 2)) || (rc = pb_alloc(ctx, &ctx->bodyCursor, (size_t)G + 2))) return rc;
         }
         PB_CUDA(ctx, cudaMemsetAsync(ctx->bodyStart, 0, sizeof(int) * ((size_t)G + 2), ctx->stream));
-        const int hb = std::min(pb_grid(n, 256), ctx->numSMs * 4);
-        ++ctx->launches, k_island_body_hist<<<hb, 256, sizeof(int) * (G + 1), ctx->stream>>>(n, ctx->bodyGroup, G, ctx->bodyStart);
+    }
+    // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
+    ++ctx->launches, k_island_group_stats<<<pb_grid(n, 256), 256, lists ? sizeof(int) * (G + 1) : 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandLocalMax, ctx->islandStats,
+                                                                                                                 lists ? ctx->bodyStart : nullptr);
+    if (lists) {
         int rc = pb_exclusive_scan(ctx, ctx->bodyStart, ctx->bodyStart, G + 2, (int*)ctx->radixHist); if (rc) return rc;
         PB_CUDA(ctx, cudaMemcpyAsync(ctx->bodyCursor, ctx->bodyStart, sizeof(int) * ((size_t)G + 2), cudaMemcpyDeviceToDevice, ctx->stream));
+        const int hb = std::min(pb_grid(n, 256), ctx->numSMs * 4);
         ++ctx->launches, k_island_body_scatter<<<hb, 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->bodyCursor, ctx->bodyOrder);
         ctx->bodyListsBuilt = true;
     }

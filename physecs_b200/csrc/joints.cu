@@ -168,7 +168,7 @@ int pb_joint_begin_step(pb_ctx* ctx) {
 // sweep walks the global runs.  Overflow-bucket joints are always global (islands.cu), so that run equals the static range.
 struct JointColorStarts { int s[PB_JOINT_COLORS + 1]; };
 __global__ void k_joint_keys(int nJ, const int2* __restrict__ bodies, const int* __restrict__ bodyGroup, int G, JointColorStarts cs,
-                             unsigned int* __restrict__ key, int* __restrict__ val, int* __restrict__ hist) {
+                             unsigned int* __restrict__ key, int* __restrict__ hist) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nJ) return;
     int2 bb = bodies[j];
@@ -178,8 +178,17 @@ __global__ void k_joint_keys(int nJ, const int2* __restrict__ bodies, const int*
     while (c < PB_JOINT_COLORS - 1 && j >= cs.s[c + 1]) ++c;
     if (c == 8) g = G;
     unsigned int k = (unsigned int)(g * 8 + c);
-    key[j] = k; val[j] = j;
+    key[j] = k;
     atomicAdd(&hist[k], 1);
+}
+
+// placed by a counting sort: the run table (scanned key histogram) gives every (group, colour) run its first slot, a joint takes run
+// start + arrival rank.  The order inside a run is immaterial: joints of one colour share no body (Physecs.cpp:690-710), and the
+// sequential overflow bucket is not listed here (the solver walks its static range in creation order).
+__global__ void k_joint_scatter(int nJ, const unsigned int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nJ) return;
+    order[atomicAdd(&cursor[key[j]], 1)] = j;
 }
 
 int pb_joint_lists(pb_ctx* ctx) {
@@ -188,18 +197,19 @@ int pb_joint_lists(pb_ctx* ctx) {
     const int n = s->n, G = ctx->islandGroups, nKeys = G * 8 + 9;
     int rc;
     if (ctx->jointListCap < n || !ctx->jointStart) {
-        if ((rc = pb_alloc(ctx, &ctx->jointKey, (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[0], (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[1], (size_t)n)) ||
-            (rc = pb_alloc(ctx, &ctx->jointSortTmp[2], (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointStart, (size_t)nKeys + 1))) return rc;
+        if ((rc = pb_alloc(ctx, &ctx->jointKey, (size_t)n)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[0], (size_t)nKeys + 1)) || (rc = pb_alloc(ctx, &ctx->jointSortTmp[1], (size_t)n)) ||
+            (rc = pb_alloc(ctx, &ctx->jointStart, (size_t)nKeys + 1))) return rc;
         ctx->jointListCap = n;
     }
     JointColorStarts cs;
     for (int c = 0; c <= PB_JOINT_COLORS; ++c) cs.s[c] = ctx->jointColorStart[c];
     PB_CUDA(ctx, cudaMemsetAsync(ctx->jointStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
-    ++ctx->launches, k_joint_keys<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, s->bodies, ctx->bodyGroup, G, cs, (unsigned int*)ctx->jointKey, ctx->jointSortTmp[1], ctx->jointStart);
+    ++ctx->launches, k_joint_keys<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, s->bodies, ctx->bodyGroup, G, cs, (unsigned int*)ctx->jointKey, ctx->jointStart);
     if ((rc = pb_exclusive_scan(ctx, ctx->jointStart, ctx->jointStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
-    bool inA = true;
-    if ((rc = pb_radix_sort_pairs(ctx, (unsigned int*)ctx->jointKey, ctx->jointSortTmp[1], (unsigned int*)ctx->jointSortTmp[0], ctx->jointSortTmp[2], n, 16, ctx->radixHist, ctx->radixTiles, &inA))) return rc;
-    ctx->jointOrder = inA ? ctx->jointSortTmp[1] : ctx->jointSortTmp[2];
+    int* cursor = ctx->jointSortTmp[0];
+    PB_CUDA(ctx, cudaMemcpyAsync(cursor, ctx->jointStart, sizeof(int) * ((size_t)nKeys + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    ++ctx->launches, k_joint_scatter<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const unsigned int*)ctx->jointKey, cursor, ctx->jointSortTmp[1]);
+    ctx->jointOrder = ctx->jointSortTmp[1];
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }
