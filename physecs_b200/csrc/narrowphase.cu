@@ -412,7 +412,8 @@ __device__ inline void sortLikeStdSort(IdxT* v, int n, Less less) {
 
 // The reference's two-pass feature filter over the triangle contacts of one (shape, mesh) pair (CTM.cpp:913-953): writes the
 // generation order (indices into contacts) and returns how many contacts survive.
-__device__ inline int meshFilter(const PbTriMeshDev& mesh, const TriContact* contacts, int cnt, unsigned char* order) {
+template <class Contact>
+__device__ inline int meshFilter(const PbTriMeshDev& mesh, const Contact* contacts, int cnt, unsigned char* order) {
     int nGen = 0;
     // pass 1 (CTM.cpp:913-929): face contacts, reverse order, swap-remove; they void their vertices
     unsigned int voidSet[3 * PB_MAX_TRI_CONTACTS];
@@ -434,7 +435,7 @@ __device__ inline int meshFilter(const PbTriMeshDev& mesh, const TriContact* con
     // pass 2 (CTM.cpp:934-953)
     for (int i = 0; i < nLive; ++i) {
         int ci = live[i];
-        const TriContact& tc = contacts[ci];
+        const Contact& tc = contacts[ci];
         int4 ti = mesh.tris[tc.tri];
         unsigned int vi[3] = { (unsigned)ti.x, (unsigned)ti.y, (unsigned)ti.z };
         if (tc.feature == TF_EDGE) {
@@ -764,9 +765,13 @@ __global__ void __launch_bounds__(128) k_mesh_finish(const int2* __restrict__ pa
     const int BIN = BIN_MESH_S + TYPE;
     const int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1], first = counters[CNT_BINSTART + BIN_MESH_S];
     const int lane = threadIdx.x & 31;
+    // what the feature filter needs of a hit (16 bytes); normal and witness points stay in the candidate arena until a manifold is made of
+    // them -- a full TriContact per hit put 1.5 KB of local memory behind every thread (most of this kernel's DRAM traffic, ncu)
+    struct Hit { int tri, feature, fidx; float dist; };
     for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
         const int idx = base + lane;
-        TriContact contacts[PB_MAX_TRI_CONTACTS];
+        Hit contacts[PB_MAX_TRI_CONTACTS];
+        int hitSlot[PB_MAX_TRI_CONTACTS];
         unsigned char order[PB_MAX_TRI_CONTACTS];
         int cnt = 0, nGen = 0, a = 0, b = 0, meshId = 0, ovf = 0, pi = 0;
         bool flip = false;
@@ -787,22 +792,24 @@ __global__ void __launch_bounds__(128) k_mesh_finish(const int2* __restrict__ pa
             for (int i = 0; i < nc; ++i) {                   // nc < 0: the pair was spilled by the cull stage
                 const int sl = TYPE == PB_SPHERE ? slot0 + i : M.cap - 1 - (slot0 + i);
                 const float4* r = M.res + 3 * (size_t)sl;
-                const float4 r1 = r[1];
-                const int bits = __float_as_int(r1.w);
+                const int bits = __float_as_int(r[1].w);
                 if (!(bits & 0x10000)) continue;
                 if (cnt >= PB_MAX_TRI_CONTACTS) { ovf |= PB_CAUSE_SPILLED_TRI_CONTACTS; break; }
-                const float4 r0 = r[0], r2 = r[2];
-                TriContact& tc = contacts[cnt++];
-                tc.tri = M.candTri[sl];
-                tc.normal = mk3(r0); tc.dist = r0.w; tc.cpBody = mk3(r1); tc.cpTri = mk3(r2);
-                tc.feature = bits & 0xff; tc.fidx = (bits >> 8) & 0xff; tc.boxFeature = 0; tc.boxAxis = 0;
+                Hit& h = contacts[cnt];
+                h.tri = M.candTri[sl]; h.dist = r[0].w; h.feature = bits & 0xff; h.fidx = (bits >> 8) & 0xff;
+                hitSlot[cnt++] = sl;
             }
             if (ovf) spillAppend(counters, CNT_SPILL_MESH, spillList, pi, ovf);
             else nGen = meshFilter(meshes[meshId], contacts, cnt, order);
         }
         int slot = warpReserve(nGen, &counters[CNT_RAWM]);
         for (int g = 0; g < nGen; ++g) {
-            const TriContact& tc = contacts[order[g]];
+            const int ci = order[g];
+            const float4* r = M.res + 3 * (size_t)hitSlot[ci];
+            const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+            TriContact tc;
+            tc.tri = contacts[ci].tri; tc.feature = contacts[ci].feature; tc.fidx = contacts[ci].fidx; tc.dist = r0.w;
+            tc.normal = mk3(r0); tc.cpBody = mk3(r1); tc.cpTri = mk3(r2); tc.boxFeature = 0; tc.boxAxis = 0;
             Manifold m; m.np = 0; m.tri = tc.tri;
             if (TYPE == PB_CAPSULE && tc.feature == TF_FACE) {
                 if (!capsuleTriangleFaceManifold(localPos, localOr, rA, rB, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }

@@ -133,6 +133,7 @@ struct pb_ctx {
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
     int meshLightMode = 1;              // sphere / capsule vs mesh bins: 0 = k_np_mesh, 1 = k_np_mesh_light (dual-child cull walk + packed
                                         // triangle records) (env PB_MESH_LIGHT)
+    int walkMode = 1; bool walkOptIn = false;   // tree broadphase: 1 = walk by packet union box (k_lbvh_pairs_union), 0 = k_lbvh_pairs (env PB_WALK)
     int meshSplitMode = 1;              // large scenes: sphere / capsule vs mesh as cull -> test per candidate -> finish (env PB_MESH_SPLIT=0: k_np_mesh_light)
     int* mcCandTri = nullptr; int* mcCandPair = nullptr; float4* mcRes = nullptr; float4* mcPairInfo = nullptr; int mcCap = 0;
     int4* colInfo = nullptr;            // [colliders] (flags, body row, entity, 0) per collider, rewritten by k_morton for the pair walk
