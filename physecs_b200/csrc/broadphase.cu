@@ -497,81 +497,115 @@ __global__ void __launch_bounds__(32 * UW_WARPS) k_lbvh_pairs_union(int n, const
             addHit(active && ib.y != rowA && overlaps(amn, amx, aabbMin[b], aabbMax[b]), b, (unsigned int)ib.z);
         }
     }
-    // union box of the packet's queries, the first querying position (for pruning) 
-    V3 umn = amn, umx = amx;
+    // Ranges of lanes walked with one union box each.  32 consecutive Morton leaves are usually a few body sizes apart, but the curve
+    // jumps: a packet that straddles a jump would walk with a box spanning half the scene and meet every leaf in it.  A range is
+    // therefore split in two while its union box is much larger than the boxes of its halves (a tight cluster costs one extra
+    // pair of reductions; a straddling one falls apart into tight pieces).
+    auto unionOf = [&](int lo, int hi, V3& mn, V3& mx) {
+        const bool in = active && lane >= lo && lane < hi;
+        mn = in ? amn : mk3(FLT_MAX); mx = in ? amx : mk3(-FLT_MAX);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        umn.x = fminf(umn.x, __shfl_xor_sync(FULL, umn.x, d)); umn.y = fminf(umn.y, __shfl_xor_sync(FULL, umn.y, d)); umn.z = fminf(umn.z, __shfl_xor_sync(FULL, umn.z, d));
-        umx.x = fmaxf(umx.x, __shfl_xor_sync(FULL, umx.x, d)); umx.y = fmaxf(umx.y, __shfl_xor_sync(FULL, umx.y, d)); umx.z = fmaxf(umx.z, __shfl_xor_sync(FULL, umx.z, d));
-    }
-    const int iFirst = (i & ~31) + __ffs(actMask) - 1;
-    int np = 1, nc = 0;                 // pool / candidate counts: warp-uniform
-    if (lane == 0) pool[0] = 0;
-    __syncwarp();
-    // all 32 queries against the collected candidates
+        for (int d = 16; d > 0; d >>= 1) {
+            mn.x = fminf(mn.x, __shfl_xor_sync(FULL, mn.x, d)); mn.y = fminf(mn.y, __shfl_xor_sync(FULL, mn.y, d)); mn.z = fminf(mn.z, __shfl_xor_sync(FULL, mn.z, d));
+            mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL, mx.y, d)); mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL, mx.z, d));
+        }
+    };
+    auto volume = [](V3 mn, V3 mx) { return mn.x > mx.x ? 0.f : (mx.x - mn.x + 0.05f) * (mx.y - mn.y + 0.05f) * (mx.z - mn.z + 0.05f); };
+    int rlo[6], rhi[6], nr = 1;          // pending ranges (warp-uniform): halving 32 lanes leaves at most 6 on the stack
+    rlo[0] = 0; rhi[0] = 32;
+    int np = 0, nc = 0;                  // pool / candidate counts: warp-uniform
+    bool rangeActive = false;
+    // all queries of the current range against the collected candidates
     auto drain = [&]() {
         for (int k = 0; k < nc; ++k) {
             const float4 bmn = cmn[k], bmx = cmx[k];
             const int4 ib = cinf[k];
             const int pos = __float_as_int(bmn.w);
-            bool hit = active && ib.w != a && ib.y != rowA && !((ib.x & COLF_DYNAMIC) && pos < i) && overlaps(amn, amx, bmn, bmx);
+            bool hit = rangeActive && ib.w != a && ib.y != rowA && !((ib.x & COLF_DYNAMIC) && pos < i) && overlaps(amn, amx, bmn, bmx);
             addHit(hit, ib.w, (unsigned int)ib.z);
         }
         nc = 0;
         __syncwarp();
     };
-    while (np > 0) {
-        if (nc > UW_CAND - 64) drain();
-        const int take = np > UW_POOL - 128 ? 1 : min(np, 32);
-        const bool mine = lane < take;
-        int node = mine ? pool[np - 1 - lane] : 0;
-        np -= take;
-        __syncwarp();
-        bool lInt = false, rInt = false, lLeaf = false, rLeaf = false;
-        int lc = 0, rc = 0, lpos = 0, rpos = 0;
-        float4 lmn, lmx, rmn, rmx;
-        if (mine) {
-            lmn = nodeMin[2 * node]; lmx = nodeMax[2 * node]; rmn = nodeMin[2 * node + 1]; rmx = nodeMax[2 * node + 1];
-            lc = __float_as_int(lmn.w); rc = __float_as_int(lmx.w);
-            const unsigned int lw = (unsigned int)__float_as_int(rmn.w), rw = (unsigned int)__float_as_int(rmx.w);
-            const int llast = (int)(lw & 0x7fffffffu), rlast = (int)(rw & 0x7fffffffu);
-            // a subtree of dynamic colliders that all sort at or before EVERY query of the packet is the other side's job
-            const bool ol = ((lw >> 31) || llast > iFirst) && overlaps(umn, umx, lmn, lmx);
-            const bool orr = ((rw >> 31) || rlast > iFirst) && overlaps(umn, umx, rmn, rmx);
-            lInt = ol && lc >= 0; rInt = orr && rc >= 0; lLeaf = ol && lc < 0; rLeaf = orr && rc < 0;
-            lpos = llast; rpos = llast + 1;
-        }
-        // internal children -> pool
-        {
-            const int cntI = (lInt ? 1 : 0) + (rInt ? 1 : 0);
-            int inc = cntI;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-            const int total = __shfl_sync(FULL, inc, 31);
-            int at = np + inc - cntI;
-            if (np + total > UW_POOL) {          // cannot happen (bound above); loud if a future tree shape breaks it
-                if (lane == 0) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_WALK_STACK); }
-                return;
+    while (nr > 0) {
+        --nr;
+        const int lo = rlo[nr], hi = rhi[nr];
+        const unsigned int rmask = actMask & (hi == 32 ? 0xffffffffu << lo : ((1u << hi) - 1u) & ~((1u << lo) - 1u));
+        if (!rmask) continue;
+        V3 umn, umx;
+        unionOf(lo, hi, umn, umx);
+        if (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            V3 m0, x0, m1, x1;
+            unionOf(lo, mid, m0, x0); unionOf(mid, hi, m1, x1);
+            if (volume(umn, umx) > 4.f * (volume(m0, x0) + volume(m1, x1))) {
+                rlo[nr] = mid; rhi[nr] = hi; ++nr;
+                rlo[nr] = lo; rhi[nr] = mid; ++nr;
+                continue;
             }
-            if (lInt) pool[at++] = lc;
-            if (rInt) pool[at++] = rc;
-            np += total;
         }
-        // leaf children -> candidates (the finding lane fetches the collider word)
-        {
-            const int cntL = (lLeaf ? 1 : 0) + (rLeaf ? 1 : 0);
-            int inc = cntL;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-            const int total = __shfl_sync(FULL, inc, 31);
-            int at = nc + inc - cntL;
-            if (lLeaf) { const int b = ~lc; const int4 ib = colInfo[b]; lmn.w = __int_as_float(lpos); cmn[at] = lmn; cmx[at] = lmx; cinf[at] = make_int4((ib.x & COLF_ENABLE) ? ib.x : 0, (ib.x & COLF_ENABLE) ? ib.y : rowA, ib.z, (ib.x & COLF_ENABLE) ? b : a); ++at; }
-            if (rLeaf) { const int b = ~rc; const int4 ib = colInfo[b]; rmn.w = __int_as_float(rpos); cmn[at] = rmn; cmx[at] = rmx; cinf[at] = make_int4((ib.x & COLF_ENABLE) ? ib.x : 0, (ib.x & COLF_ENABLE) ? ib.y : rowA, ib.z, (ib.x & COLF_ENABLE) ? b : a); ++at; }
-            nc += total;
-        }
+        rangeActive = active && lane >= lo && lane < hi;
+        const int iFirst = (i & ~31) + __ffs(rmask) - 1;
+        np = 1;
+        if (lane == 0) pool[0] = 0;
         __syncwarp();
+        while (np > 0) {
+            if (nc > UW_CAND - 64) drain();
+            const int take = np > UW_POOL - 128 ? 1 : min(np, 32);
+            const bool mine = lane < take;
+            int node = mine ? pool[np - 1 - lane] : 0;
+            np -= take;
+            __syncwarp();
+            bool lInt = false, rInt = false, lLeaf = false, rLeaf = false;
+            int lc = 0, rc = 0, lpos = 0, rpos = 0;
+            float4 lmn, lmx, rmn, rmx;
+            int4 lib = make_int4(0, 0, 0, 0), rib = lib;
+            if (mine) {
+                lmn = nodeMin[2 * node]; lmx = nodeMax[2 * node]; rmn = nodeMin[2 * node + 1]; rmx = nodeMax[2 * node + 1];
+                lc = __float_as_int(lmn.w); rc = __float_as_int(lmx.w);
+                const unsigned int lw = (unsigned int)__float_as_int(rmn.w), rw = (unsigned int)__float_as_int(rmx.w);
+                const int llast = (int)(lw & 0x7fffffffu), rlast = (int)(rw & 0x7fffffffu);
+                // a subtree of dynamic colliders that all sort at or before EVERY query of the range is the other side's job
+                const bool ol = ((lw >> 31) || llast > iFirst) && overlaps(umn, umx, lmn, lmx);
+                const bool orr = ((rw >> 31) || rlast > iFirst) && overlaps(umn, umx, rmn, rmx);
+                lInt = ol && lc >= 0; rInt = orr && rc >= 0; lLeaf = ol && lc < 0; rLeaf = orr && rc < 0;
+                lpos = llast; rpos = llast + 1;
+                // the finding lane fetches the collider word; a disabled collider is no candidate for anybody (k_lbvh_pairs' first leaf check)
+                if (lLeaf) { lib = colInfo[~lc]; lLeaf = (lib.x & COLF_ENABLE) != 0; }
+                if (rLeaf) { rib = colInfo[~rc]; rLeaf = (rib.x & COLF_ENABLE) != 0; }
+            }
+            // internal children -> pool
+            {
+                const int cntI = (lInt ? 1 : 0) + (rInt ? 1 : 0);
+                int inc = cntI;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+                const int total = __shfl_sync(FULL, inc, 31);
+                int at = np + inc - cntI;
+                if (np + total > UW_POOL) {          // cannot happen (bound above); loud if a future tree shape breaks it
+                    if (lane == 0) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_WALK_STACK); }
+                    return;
+                }
+                if (lInt) pool[at++] = lc;
+                if (rInt) pool[at++] = rc;
+                np += total;
+            }
+            // leaf children -> candidates
+            {
+                const int cntL = (lLeaf ? 1 : 0) + (rLeaf ? 1 : 0);
+                int inc = cntL;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+                const int total = __shfl_sync(FULL, inc, 31);
+                int at = nc + inc - cntL;
+                if (lLeaf) { lmn.w = __int_as_float(lpos); cmn[at] = lmn; cmx[at] = lmx; cinf[at] = make_int4(lib.x, lib.y, lib.z, ~lc); ++at; }
+                if (rLeaf) { rmn.w = __int_as_float(rpos); cmn[at] = rmn; cmx[at] = rmx; cinf[at] = make_int4(rib.x, rib.y, rib.z, ~rc); ++at; }
+                nc += total;
+            }
+            __syncwarp();
+        }
+        drain();        // candidates belong to this range's queries
     }
-    drain();
     flush();
 }
 

@@ -78,3 +78,57 @@ def test_energy_and_penetration_statistics(maker, steps):
         assert abs(np.percentile(sd, qt) - np.percentile(sr, qt)) < 0.15, (qt, np.percentile(sd, qt), np.percentile(sr, qt))
     assert np.percentile(sd, 90) < 0.5
     ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("name,maker,steps", [
+    ("ragdolls", lambda: S.ragdolls(24), 420),                                   # joints + contacts: bodies fall, fold up and come to rest
+    ("terrain", lambda: S.terrain(1200, cells=48, drop=0.3), 420),               # spheres / capsules rolling on a triangle mesh
+    ("terrain_mixed", lambda: S.terrain_mixed(600, cells=40), 360),              # all four shape kinds on the mesh
+])
+def test_long_horizon_joints_and_terrain(name, maker, steps):
+    """The same statistical comparison on the scene families the bin scenes do not cover: jointed bodies in contact (ragdolls) and
+    bodies on a triangle mesh.  Device and oracle free-run with their own constraint orders; trajectories differ, distributions agree."""
+    from oracle.ref import RefScene
+    d = maker()
+    ref = RefScene(d, 0, hashfix=True)
+    ctx = Context(d)
+    e_dev, e_ref = [], []
+    for k in range(steps):
+        ctx.step(); ref.simulate()
+        if k % 20 == 0 or k == steps - 1:
+            P, Q, V, W = ctx.get_state_entities()
+            assert np.isfinite(P).all() and np.isfinite(V).all() and np.isfinite(Q).all() and np.isfinite(W).all()
+            e_dev.append(_energy(d, P, Q, V, W))
+            e_ref.append(_energy(d, *ref.get_state()))
+    e_dev, e_ref = np.array(e_dev), np.array(e_ref)
+    drop = abs(e_ref[0] - e_ref[-1]) + 1e-9
+    # the energy shed over the run agrees (rolling bodies on a slope keep shedding: compare the curves loosely, the end points tighter)
+    assert np.max(np.abs(e_dev - e_ref)) < max(0.12 * drop, 5e-3 * abs(e_ref[0])), (e_dev, e_ref)
+    assert abs(e_dev[-1] - e_ref[-1]) < max(0.06 * drop, 3e-3 * abs(e_ref[0])), (e_dev[-1], e_ref[-1])
+    # no energy is created: the device's curve never rises above its start by more than the oracle's does
+    assert e_dev.max() - e_dev[0] < max(e_ref.max() - e_ref[0], 0.0) + 2e-3 * abs(e_ref[0]) + 0.01 * drop
+    gm, rm = ctx.manifolds(), ref.narrowphase(ref.pairs())
+    pd, pr = _penetration(gm), _penetration(rm)
+    assert abs(len(gm["keys"]) - len(rm["keys"])) < 0.15 * len(rm["keys"]) + 10
+    assert pd.size and pr.size and pd.max() < 0.08 and abs(pd.max() - pr.max()) < 0.03, (pd.max(), pr.max())
+    assert abs(pd.mean() - pr.mean()) < 0.004, (pd.mean(), pr.mean())
+    P, _, V, _ = ctx.get_state_entities()
+    p, _, v, _ = ref.get_state()
+    dyn = d.dynamic_entities()
+    assert abs(np.median(P[dyn, 1]) - np.median(p[dyn, 1])) < 0.05
+    sd, sr = np.linalg.norm(V[dyn], axis=1), np.linalg.norm(v[dyn], axis=1)
+    assert abs(np.percentile(sd, 50) - np.percentile(sr, 50)) < 0.2 and abs(np.percentile(sd, 90) - np.percentile(sr, 90)) < 0.4
+    if name == "ragdolls":
+        # joints hold: the distance between the bodies of every joint stays what the oracle's is (anchors coincide up to solver slack)
+        def gaps(pos, quat):
+            out = []
+            for (t, e0, a0p, a0q, e1, a1p, a1q, prm) in d.joints:
+                w0 = pos[e0] + S.qrot(quat[e0].astype(np.float64), a0p.astype(np.float64))
+                w1 = pos[e1] + S.qrot(quat[e1].astype(np.float64), a1p.astype(np.float64))
+                out.append(np.linalg.norm(w0 - w1))
+            return np.array(out)
+        _, Qd, _, _ = ctx.get_state_entities()
+        pr_, qr_, _, _ = ref.get_state()
+        gd, gr = gaps(P, Qd), gaps(pr_, qr_)
+        assert gd.max() < max(2.0 * gr.max(), 0.02), (gd.max(), gr.max())
+    ctx.close(); ref.close()
