@@ -185,7 +185,7 @@ __device__ __forceinline__ unsigned int expandBits(unsigned int v) {
 // colliders are listed does not change the pair set.
 __global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const int* __restrict__ sb,
                          unsigned int* __restrict__ keys, int* __restrict__ ids, int* __restrict__ colFlags, int* __restrict__ bigList,
-                         const int* __restrict__ colRow, const int* __restrict__ rowEntity, int4* __restrict__ colInfo) {
+                         const int* __restrict__ colRow, const int* __restrict__ rowEntity, int4* __restrict__ colInfo, int isotropic) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 lo = mk3(orderedToFloat(sb[0]), orderedToFloat(sb[1]), orderedToFloat(sb[2]));
@@ -209,6 +209,10 @@ __global__ void k_morton(int n, const float4* __restrict__ aabbMin, const float4
         colInfo[i] = make_int4(f, row, rowEntity[row], 0);
     }
     float sx = ext.x > 0.f ? 1024.f / ext.x : 0.f, sy = ext.y > 0.f ? 1024.f / ext.y : 0.f, sz = ext.z > 0.f ? 1024.f / ext.z : 0.f;
+    // Cubic cells: one scale for the three axes.  A scene that is wide and flat (a million bodies on a 1 km terrain, 6 m of height)
+    // otherwise spends a third of its key bits on millimetres of height, and leaves that are neighbours in the order lie scattered
+    // along a height contour of a 30 m cell instead of side by side -- the packet walks live on that neighbourhood.
+    if (isotropic) { const float m = fmaxf(ext.x, fmaxf(ext.y, ext.z)); sx = sy = sz = m > 0.f ? 1024.f / m : 0.f; }
     unsigned int x = (unsigned int)fminf(fmaxf((c.x - lo.x) * sx, 0.f), 1023.f);
     unsigned int y = (unsigned int)fminf(fmaxf((c.y - lo.y) * sy, 0.f), 1023.f);
     unsigned int z = (unsigned int)fminf(fmaxf((c.z - lo.z) * sz, 0.f), 1023.f);
@@ -429,186 +433,6 @@ __global__ void __launch_bounds__(32 * PAIRS_WARPS) k_lbvh_pairs(int n, const in
     }
 }
 
-// ---- the walk by packet UNION box ---------------------------------------------------------------------------------------------------
-// k_lbvh_pairs tests every visited node against all 32 query boxes of the packet (~114 node visits x ~96 instructions per packet at
-// 1 M bodies: issue-bound, ncu).  Morton-sorted neighbours are a few body sizes apart, so their UNION box is small too -- this variant
-// walks the tree ONCE per packet with the union box, 32 nodes at a time (each lane expands one node of a shared pool: two child boxes
-// against one box), and collects the leaves it meets as candidates in shared memory (box + collider word, fetched by the lane that
-// found them).  Only then do the 32 queries meet the candidates: every lane tests its own box against one candidate after the other
-// (smem broadcasts, no tree words, no stack).  The leaf predicates are k_lbvh_pairs' own (enabled, not itself, not the same entity,
-// closed-interval overlap, a dynamic pair emitted by the earlier leaf), so the pair SET is identical; a subtree is pruned when every
-// query of the packet would prune it.  Pairs are buffered per lane and appended with one atomic per flush.
-#define UW_WARPS 4
-#define UW_POOL 512           // pending nodes per warp.  Rounds expand up to 32 nodes (the pool grows by <= 32); above UW_POOL - 128 entries a
-                              // round expands only the top node -- plain depth-first, which adds at most one pending sibling per level
-                              // (<= 62 levels, see k_lbvh_pairs) before it shrinks again: the pool cannot run over
-#define UW_CAND 96            // candidate leaves per warp between two flushes (an expansion round adds at most 64)
-#define UW_HITS 6             // buffered pairs per lane
-__global__ void __launch_bounds__(32 * UW_WARPS) k_lbvh_pairs_union(int n, const int* __restrict__ leafId, const int4* __restrict__ colInfo,
-                             const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
-                             const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax,
-                             int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs, const int* __restrict__ bigList) {
-    extern __shared__ int uwsm[];
-    const unsigned FULL = 0xffffffffu;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* pool = uwsm + w * UW_POOL;
-    float4* cmn = (float4*)(uwsm + UW_WARPS * UW_POOL) + w * UW_CAND;
-    float4* cmx = (float4*)(uwsm + UW_WARPS * UW_POOL) + (UW_WARPS + w) * UW_CAND;
-    int4* cinf = (int4*)(uwsm + UW_WARPS * UW_POOL) + (2 * UW_WARPS + w) * UW_CAND;       // (flags, row, entity, collider); box .w of cmn = sorted position
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int a = -1, rowA = -1;
-    unsigned int entA = 0;
-    bool active = false;
-    V3 amn = mk3(FLT_MAX), amx = mk3(-FLT_MAX);     // empty box: overlaps nothing
-    if (i < n) {
-        a = leafId[i];
-        const int4 ia = colInfo[a];
-        active = (ia.x & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
-        if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = ia.y; entA = (unsigned int)ia.z; }
-    }
-    const unsigned int actMask = __ballot_sync(FULL, active);
-    if (!actMask) return;
-    // pairs found by this lane, flushed warp-wide (one atomic) when any lane's buffer is full and at the end
-    int hb[UW_HITS]; unsigned int he[UW_HITS]; int nh = 0;
-    auto flush = [&]() {
-        int inc = nh;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-        const int total = __shfl_sync(FULL, inc, 31);
-        if (!total) return;
-        int base = 0;
-        if (lane == 31) base = atomicAdd(&counters[CNT_PAIRS], total);
-        base = __shfl_sync(FULL, base, 31) + inc - nh;
-        for (int k = 0; k < nh; ++k) {
-            if (base + k < maxPairs) pairs[base + k] = (entA < he[k]) ? make_int2(a, hb[k]) : make_int2(hb[k], a);   // lower entity id first (Physecs.cpp:158-168)
-            else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
-        }
-        nh = 0;
-    };
-    auto addHit = [&](bool hit, int b, unsigned int eb) {
-        if (__any_sync(FULL, nh == UW_HITS)) flush();
-        if (hit) { hb[nh] = b; he[nh] = eb; ++nh; }
-    };
-    if (bigList) {
-        const int nb = min(bigList[0], PB_BIG_MAX);
-        for (int k = 0; k < nb; ++k) {
-            const int b = bigList[1 + k];
-            const int4 ib = colInfo[b];
-            addHit(active && ib.y != rowA && overlaps(amn, amx, aabbMin[b], aabbMax[b]), b, (unsigned int)ib.z);
-        }
-    }
-    // Ranges of lanes walked with one union box each.  32 consecutive Morton leaves are usually a few body sizes apart, but the curve
-    // jumps: a packet that straddles a jump would walk with a box spanning half the scene and meet every leaf in it.  A range is
-    // therefore split in two while its union box is much larger than the boxes of its halves (a tight cluster costs one extra
-    // pair of reductions; a straddling one falls apart into tight pieces).
-    auto unionOf = [&](int lo, int hi, V3& mn, V3& mx) {
-        const bool in = active && lane >= lo && lane < hi;
-        mn = in ? amn : mk3(FLT_MAX); mx = in ? amx : mk3(-FLT_MAX);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mn.x = fminf(mn.x, __shfl_xor_sync(FULL, mn.x, d)); mn.y = fminf(mn.y, __shfl_xor_sync(FULL, mn.y, d)); mn.z = fminf(mn.z, __shfl_xor_sync(FULL, mn.z, d));
-            mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL, mx.x, d)); mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL, mx.y, d)); mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL, mx.z, d));
-        }
-    };
-    auto volume = [](V3 mn, V3 mx) { return mn.x > mx.x ? 0.f : (mx.x - mn.x + 0.05f) * (mx.y - mn.y + 0.05f) * (mx.z - mn.z + 0.05f); };
-    int rlo[6], rhi[6], nr = 1;          // pending ranges (warp-uniform): halving 32 lanes leaves at most 6 on the stack
-    rlo[0] = 0; rhi[0] = 32;
-    int np = 0, nc = 0;                  // pool / candidate counts: warp-uniform
-    bool rangeActive = false;
-    // all queries of the current range against the collected candidates
-    auto drain = [&]() {
-        for (int k = 0; k < nc; ++k) {
-            const float4 bmn = cmn[k], bmx = cmx[k];
-            const int4 ib = cinf[k];
-            const int pos = __float_as_int(bmn.w);
-            bool hit = rangeActive && ib.w != a && ib.y != rowA && !((ib.x & COLF_DYNAMIC) && pos < i) && overlaps(amn, amx, bmn, bmx);
-            addHit(hit, ib.w, (unsigned int)ib.z);
-        }
-        nc = 0;
-        __syncwarp();
-    };
-    while (nr > 0) {
-        --nr;
-        const int lo = rlo[nr], hi = rhi[nr];
-        const unsigned int rmask = actMask & (hi == 32 ? 0xffffffffu << lo : ((1u << hi) - 1u) & ~((1u << lo) - 1u));
-        if (!rmask) continue;
-        V3 umn, umx;
-        unionOf(lo, hi, umn, umx);
-        if (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            V3 m0, x0, m1, x1;
-            unionOf(lo, mid, m0, x0); unionOf(mid, hi, m1, x1);
-            if (volume(umn, umx) > 4.f * (volume(m0, x0) + volume(m1, x1))) {
-                rlo[nr] = mid; rhi[nr] = hi; ++nr;
-                rlo[nr] = lo; rhi[nr] = mid; ++nr;
-                continue;
-            }
-        }
-        rangeActive = active && lane >= lo && lane < hi;
-        const int iFirst = (i & ~31) + __ffs(rmask) - 1;
-        np = 1;
-        if (lane == 0) pool[0] = 0;
-        __syncwarp();
-        while (np > 0) {
-            if (nc > UW_CAND - 64) drain();
-            const int take = np > UW_POOL - 128 ? 1 : min(np, 32);
-            const bool mine = lane < take;
-            int node = mine ? pool[np - 1 - lane] : 0;
-            np -= take;
-            __syncwarp();
-            bool lInt = false, rInt = false, lLeaf = false, rLeaf = false;
-            int lc = 0, rc = 0, lpos = 0, rpos = 0;
-            float4 lmn, lmx, rmn, rmx;
-            int4 lib = make_int4(0, 0, 0, 0), rib = lib;
-            if (mine) {
-                lmn = nodeMin[2 * node]; lmx = nodeMax[2 * node]; rmn = nodeMin[2 * node + 1]; rmx = nodeMax[2 * node + 1];
-                lc = __float_as_int(lmn.w); rc = __float_as_int(lmx.w);
-                const unsigned int lw = (unsigned int)__float_as_int(rmn.w), rw = (unsigned int)__float_as_int(rmx.w);
-                const int llast = (int)(lw & 0x7fffffffu), rlast = (int)(rw & 0x7fffffffu);
-                // a subtree of dynamic colliders that all sort at or before EVERY query of the range is the other side's job
-                const bool ol = ((lw >> 31) || llast > iFirst) && overlaps(umn, umx, lmn, lmx);
-                const bool orr = ((rw >> 31) || rlast > iFirst) && overlaps(umn, umx, rmn, rmx);
-                lInt = ol && lc >= 0; rInt = orr && rc >= 0; lLeaf = ol && lc < 0; rLeaf = orr && rc < 0;
-                lpos = llast; rpos = llast + 1;
-                // the finding lane fetches the collider word; a disabled collider is no candidate for anybody (k_lbvh_pairs' first leaf check)
-                if (lLeaf) { lib = colInfo[~lc]; lLeaf = (lib.x & COLF_ENABLE) != 0; }
-                if (rLeaf) { rib = colInfo[~rc]; rLeaf = (rib.x & COLF_ENABLE) != 0; }
-            }
-            // internal children -> pool
-            {
-                const int cntI = (lInt ? 1 : 0) + (rInt ? 1 : 0);
-                int inc = cntI;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-                const int total = __shfl_sync(FULL, inc, 31);
-                int at = np + inc - cntI;
-                if (np + total > UW_POOL) {          // cannot happen (bound above); loud if a future tree shape breaks it
-                    if (lane == 0) { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_WALK_STACK); }
-                    return;
-                }
-                if (lInt) pool[at++] = lc;
-                if (rInt) pool[at++] = rc;
-                np += total;
-            }
-            // leaf children -> candidates
-            {
-                const int cntL = (lLeaf ? 1 : 0) + (rLeaf ? 1 : 0);
-                int inc = cntL;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-                const int total = __shfl_sync(FULL, inc, 31);
-                int at = nc + inc - cntL;
-                if (lLeaf) { lmn.w = __int_as_float(lpos); cmn[at] = lmn; cmx[at] = lmx; cinf[at] = make_int4(lib.x, lib.y, lib.z, ~lc); ++at; }
-                if (rLeaf) { rmn.w = __int_as_float(rpos); cmn[at] = rmn; cmx[at] = rmx; cinf[at] = make_int4(rib.x, rib.y, rib.z, ~rc); ++at; }
-                nc += total;
-            }
-            __syncwarp();
-        }
-        drain();        // candidates belong to this range's queries
-    }
-    flush();
-}
-
 // Small scenes (n <= PB_BRUTE_FORCE_MAX colliders): every dynamic collider against every collider, tile by tile through shared
 // memory.  Same predicates, same pair set; it replaces a Morton sort (4 radix passes), tree build, refit and walk whose ~25 tiny
 // launches and dependent-latency chains cost ~0.2 ms however small the scene is (6 k colliders: 19 M box tests, a few microseconds).
@@ -735,7 +559,7 @@ int pb_build_tree(pb_ctx* ctx, bool forStep) {
     int blocks = pb_grid(n, 256); if (blocks > ctx->numSMs * 8) blocks = ctx->numSMs * 8;
     ++ctx->launches, k_scene_bounds<<<blocks, 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb);
     ++ctx->launches, k_morton<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->aabbMin, ctx->aabbMax, sb, ctx->mortonA, ctx->leafIdA, ctx->colFlags, bigList,
-                                                                       ctx->colRow, ctx->rowEntity, ctx->colInfo);
+                                                                       ctx->colRow, ctx->rowEntity, ctx->colInfo, ctx->mortonIso);
     bool inA = true;
     int rc = pb_radix_sort_pairs(ctx, ctx->mortonA, ctx->leafIdA, ctx->mortonB, ctx->leafIdB, n, 30, ctx->radixHist, ctx->radixTiles, &inA);
     if (rc) return rc;
@@ -769,13 +593,6 @@ int pb_broadphase(pb_ctx* ctx) {
     int rc = pb_build_tree(ctx, true);
     if (rc) return rc;
     const int* ids = ctx->treeLeafIds;
-    if (ctx->walkMode == 1) {
-        const size_t smem = sizeof(int) * UW_WARPS * UW_POOL + (sizeof(float4) * 2 + sizeof(int4)) * UW_WARPS * UW_CAND;
-        if (!ctx->walkOptIn) { PB_CUDA(ctx, cudaFuncSetAttribute(k_lbvh_pairs_union, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->walkOptIn = true; }
-        ++ctx->launches, k_lbvh_pairs_union<<<pb_grid(n, 32 * UW_WARPS), 32 * UW_WARPS, smem, ctx->stream>>>(n, ids, ctx->colInfo, ctx->aabbMin, ctx->aabbMax,
-                                                            ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs,
-                                                            ctx->bigListMode ? ctx->bigList : nullptr);
-    } else
     ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colInfo, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs,
                                                             ctx->bigListMode ? ctx->bigList : nullptr);

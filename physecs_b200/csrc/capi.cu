@@ -236,8 +236,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
     if (const char* e = getenv("PB_MESH_LIGHT")) ctx->meshLightMode = atoi(e);
     if (const char* e = getenv("PB_NP_WAVES")) ctx->npWaves = atoi(e) >= 0 ? atoi(e) : 4;
-    if (const char* e = getenv("PB_WALK")) ctx->walkMode = atoi(e);
-    if (const char* e = getenv("PB_MESH_SPLIT")) ctx->meshSplitMode = atoi(e);
+    if (const char* e = getenv("PB_MORTON_ISO")) ctx->mortonIso = atoi(e);
     if (const char* e = getenv("PB_NP_FUSE")) ctx->npFuseSmall = atoi(e);
     if (const char* e = getenv("PB_FUSED_LOCAL_MAX")) ctx->fusedLocalMax = atoi(e);
     if (const char* e = getenv("PB_DETERMINISTIC")) ctx->deterministic = atoi(e) != 0;
@@ -327,7 +326,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);
-    F(mcCandTri); F(mcCandPair); F(mcRes); F(mcPairInfo); F(jpBest); F(jpScratch); F(bodyOrder); F(bodyStart); F(bodyCursor); F(gjkHitPair); F(gjkHitSimplex); F(spillList); F(spillEpa); F(spillMesh); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
+    F(jpBest); F(jpScratch); F(bodyOrder); F(bodyStart); F(bodyCursor); F(gjkHitPair); F(gjkHitSimplex); F(spillList); F(spillEpa); F(spillMesh); F(qCounters); F(qPairs); F(qPairOrder); F(qmKey); F(qmNormal); F(qmPts);
     F(islandParent); F(islandCount); F(bodyGroup); F(islandStats); F(keyStart); F(keyCursor); F(jointKey); F(jointStart); F(jointSortTmp[0]); F(jointSortTmp[1]); F(jointSortTmp[2]);
 #undef F
     for (auto& m : ctx->triMeshes) { cudaFree(m.verts); cudaFree(m.tris); cudaFree(m.triNormal); cudaFree(m.triCentroid); cudaFree(m.triRec); cudaFree(m.nodeMin); cudaFree(m.nodeMax); }

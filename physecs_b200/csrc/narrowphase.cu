@@ -664,164 +664,6 @@ __global__ void __launch_bounds__(32 * ML_WARPS) k_np_mesh_light(const int2* __r
     }
 }
 
-// ---- sphere / capsule vs mesh in three uniform stages (large scenes) -----------------------------------------------------------------
-// k_np_mesh_light does cull walk, triangle tests and feature filter of a pair in one thread: lanes of a warp walk different depths and
-// test different numbers of triangles, and the long capsule-triangle routine runs with ~15 of 32 lanes (ncu, 1 M-body scene).  Here
-// the same work is cut where the divergence is:
-//   k_mesh_cull<TYPE>    thread per pair: the same dual-child walk, candidates written to ONE list (visiting order kept per pair)
-//   k_mesh_test<TYPE>    thread per (pair, triangle) candidate: every lane runs the triangle routine once -- full warps
-//   k_mesh_finish<TYPE>  thread per pair: collects its hits in candidate order, feature filter, manifolds
-// Same routines on the same inputs in the same per-pair order as k_np_mesh_light -> the same manifolds, bit for bit.  Sphere
-// candidates grow from the front of the list, capsule candidates from its back, so the two bins share one arena.  A pair whose
-// candidates do not fit (per-thread buffer, arena) takes the spill path like everywhere else.
-struct MeshSplit {
-    int* candTri; int* candPair; float4* res;      // [cap] candidate list; res: 3 float4 per candidate
-    float4* pairInfo;                               // [3 * maxPairs] per mesh pair: {localPos, prm.x} {localOr} {prm.y, base, nc, meshId}
-    int cap;
-};
-
-template <int TYPE>
-__global__ void __launch_bounds__(128) k_mesh_cull(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
-                                                   const int* __restrict__ colType, const float4* __restrict__ colParams, const int* __restrict__ colMesh,
-                                                   const float4* __restrict__ wpos, const float4* __restrict__ wquat,
-                                                   const PbTriMeshDev* __restrict__ meshes, MeshSplit M, int* __restrict__ spillList) {
-    const int BIN = BIN_MESH_S + TYPE;
-    const int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1], first = counters[CNT_BINSTART + BIN_MESH_S];
-    const int lane = threadIdx.x & 31;
-    const int other = TYPE == PB_SPHERE ? 0 : min(counters[CNT_MC_S], M.cap);      // sphere kernel runs first (stream order): its count is final
-    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
-        const int idx = base + lane;
-        int cand[PB_MAX_TRI_CAND];
-        int nc = 0, ovf = 0, pi = 0, meshId = 0;
-        V3 localPos = mk3(0.f); Q4 localOr = mkq(make_float4(0, 0, 0, 1));
-        float4 prm = make_float4(0, 0, 0, 0);
-        if (idx < end) {
-            pi = pairOrder[idx];
-            int2 p = pairs[pi];
-            const bool flip = colType[p.x] == PB_TRIANGLE_MESH;
-            const int shape = flip ? p.y : p.x, meshCol = flip ? p.x : p.y;
-            prm = colParams[shape];
-            meshId = colMesh[meshCol];
-            V3 pos0 = mk3(wpos[shape]); Q4 or0 = mkq(wquat[shape]);
-            V3 pos1 = mk3(wpos[meshCol]); Q4 or1 = mkq(wquat[meshCol]);
-            Q4 invOr1 = qinverse(or1);
-            localPos = rotate(invOr1, pos0 - pos1);
-            localOr = qmul(invOr1, or0);
-            Aabb lb = shapeBounds(localPos, localOr, TYPE, prm, nullptr, 0);
-            const PbTriMeshDev& mesh = meshes[meshId];
-            nc = meshCullDual(lb, mesh.nodeMin, mesh.nodeMax, cand, &ovf);
-            if (ovf) nc = 0;
-        }
-        int slot0 = warpReserve(nc, &counters[TYPE == PB_SPHERE ? CNT_MC_S : CNT_MC_C]);
-        if (idx < end) {
-            if (!ovf && slot0 + nc + other > M.cap) {
-                // candidate arena full: the pair goes the spill way; the slots it reserved inside this bin's part of the arena are voided
-                ovf = PB_CAUSE_SPILLED_TRI_CAND;
-                for (int i = 0; i < nc; ++i) {
-                    const int sl = TYPE == PB_SPHERE ? slot0 + i : M.cap - 1 - (slot0 + i);
-                    if (sl >= other && sl < M.cap) M.candPair[sl] = -1;
-                }
-            }
-            if (ovf) { spillAppend(counters, CNT_SPILL_MESH, spillList, pi, ovf); nc = -1; }
-            for (int i = 0; i < nc; ++i) {
-                const int sl = TYPE == PB_SPHERE ? slot0 + i : M.cap - 1 - (slot0 + i);
-                M.candTri[sl] = cand[i]; M.candPair[sl] = idx - first;
-            }
-            float4* o = M.pairInfo + 3 * (size_t)(idx - first);
-            o[0] = make_float4(localPos.x, localPos.y, localPos.z, prm.x);
-            o[1] = make_float4(localOr.x, localOr.y, localOr.z, localOr.w);
-            o[2] = make_float4(prm.y, __int_as_float(slot0), __int_as_float(nc), __int_as_float(meshId));
-        }
-    }
-}
-
-template <int TYPE>
-__global__ void __launch_bounds__(128) k_mesh_test(const int* __restrict__ counters, const PbTriMeshDev* __restrict__ meshes, MeshSplit M) {
-    const int nS = min(counters[CNT_MC_S], M.cap);
-    const int n = TYPE == PB_SPHERE ? nS : min(counters[CNT_MC_C], M.cap - nS);       // the capsule part ends where the sphere part begins
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        const int sl = TYPE == PB_SPHERE ? c : M.cap - 1 - c;
-        const int pp = M.candPair[sl];
-        if (pp < 0) continue;                 // voided slot (its pair was spilled)
-        const int tri = M.candTri[sl];
-        const float4* info = M.pairInfo + 3 * (size_t)pp;
-        const float4 i0 = info[0], i1 = info[1], i2 = info[2];
-        const float4* r = meshes[__float_as_int(i2.w)].triRec + 4 * (size_t)tri;
-        const float4 r0 = r[0], r1 = r[1], r2 = r[2];
-        TriContact tc;
-        const bool hit = lightTriTest<TYPE>(mk3(i0), mkq(i1), i0.w, i2.x, r0, r1, r2, tc);
-        float4* o = M.res + 3 * (size_t)sl;
-        o[1] = make_float4(tc.cpBody.x, tc.cpBody.y, tc.cpBody.z, __int_as_float((hit ? 0x10000 : 0) | (tc.fidx << 8) | tc.feature));
-        if (hit) { o[0] = make_float4(tc.normal.x, tc.normal.y, tc.normal.z, tc.dist); o[2] = make_float4(tc.cpTri.x, tc.cpTri.y, tc.cpTri.z, 0.f); }
-    }
-}
-
-template <int TYPE>
-__global__ void __launch_bounds__(128) k_mesh_finish(const int2* __restrict__ pairs, const int* __restrict__ pairOrder, int* __restrict__ counters,
-                                                     const int* __restrict__ colType, const float4* __restrict__ wpos, const float4* __restrict__ wquat,
-                                                     const PbTriMeshDev* __restrict__ meshes, MeshSplit M,
-                                                     int4* __restrict__ mKey, float4* __restrict__ mNormal, float4* __restrict__ mPts, int maxManifolds,
-                                                     int* __restrict__ spillList) {
-    const int BIN = BIN_MESH_S + TYPE;
-    const int start = counters[CNT_BINSTART + BIN], end = counters[CNT_BINSTART + BIN + 1], first = counters[CNT_BINSTART + BIN_MESH_S];
-    const int lane = threadIdx.x & 31;
-    // what the feature filter needs of a hit (16 bytes); normal and witness points stay in the candidate arena until a manifold is made of
-    // them -- a full TriContact per hit put 1.5 KB of local memory behind every thread (most of this kernel's DRAM traffic, ncu)
-    struct Hit { int tri, feature, fidx; float dist; };
-    for (int base = start + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31); base < end; base += gridDim.x * blockDim.x) {
-        const int idx = base + lane;
-        Hit contacts[PB_MAX_TRI_CONTACTS];
-        int hitSlot[PB_MAX_TRI_CONTACTS];
-        unsigned char order[PB_MAX_TRI_CONTACTS];
-        int cnt = 0, nGen = 0, a = 0, b = 0, meshId = 0, ovf = 0, pi = 0;
-        bool flip = false;
-        V3 localPos = mk3(0.f), pos1 = mk3(0.f); Q4 localOr = mkq(make_float4(0, 0, 0, 1)), or1 = localOr;
-        float rA = 0.f, rB = 0.f;
-        if (idx < end) {
-            const float4* info = M.pairInfo + 3 * (size_t)(idx - first);
-            const float4 i0 = info[0], i1 = info[1], i2 = info[2];
-            const int slot0 = __float_as_int(i2.y), nc = __float_as_int(i2.z);
-            meshId = __float_as_int(i2.w);
-            localPos = mk3(i0); localOr = mkq(i1); rA = i0.w; rB = i2.x;
-            pi = pairOrder[idx];
-            int2 p = pairs[pi];
-            a = p.x; b = p.y;
-            flip = colType[a] == PB_TRIANGLE_MESH;
-            const int meshCol = flip ? a : b;
-            pos1 = mk3(wpos[meshCol]); or1 = mkq(wquat[meshCol]);
-            for (int i = 0; i < nc; ++i) {                   // nc < 0: the pair was spilled by the cull stage
-                const int sl = TYPE == PB_SPHERE ? slot0 + i : M.cap - 1 - (slot0 + i);
-                const float4* r = M.res + 3 * (size_t)sl;
-                const int bits = __float_as_int(r[1].w);
-                if (!(bits & 0x10000)) continue;
-                if (cnt >= PB_MAX_TRI_CONTACTS) { ovf |= PB_CAUSE_SPILLED_TRI_CONTACTS; break; }
-                Hit& h = contacts[cnt];
-                h.tri = M.candTri[sl]; h.dist = r[0].w; h.feature = bits & 0xff; h.fidx = (bits >> 8) & 0xff;
-                hitSlot[cnt++] = sl;
-            }
-            if (ovf) spillAppend(counters, CNT_SPILL_MESH, spillList, pi, ovf);
-            else nGen = meshFilter(meshes[meshId], contacts, cnt, order);
-        }
-        int slot = warpReserve(nGen, &counters[CNT_RAWM]);
-        for (int g = 0; g < nGen; ++g) {
-            const int ci = order[g];
-            const float4* r = M.res + 3 * (size_t)hitSlot[ci];
-            const float4 r0 = r[0], r1 = r[1], r2 = r[2];
-            TriContact tc;
-            tc.tri = contacts[ci].tri; tc.feature = contacts[ci].feature; tc.fidx = contacts[ci].fidx; tc.dist = r0.w;
-            tc.normal = mk3(r0); tc.cpBody = mk3(r1); tc.cpTri = mk3(r2); tc.boxFeature = 0; tc.boxAxis = 0;
-            Manifold m; m.np = 0; m.tri = tc.tri;
-            if (TYPE == PB_CAPSULE && tc.feature == TF_FACE) {
-                if (!capsuleTriangleFaceManifold(localPos, localOr, rA, rB, pos1, or1, meshes[meshId], tc, m)) { m.np = 0; m.n = mk3(0.f, 1.f, 0.f); }
-            } else {
-                manifoldFromClosest(pos1, or1, tc, m);
-            }
-            m.tri = tc.tri;
-            storeManifold(slot + g, maxManifolds, a, b, m, flip, mKey, mNormal, mPts, counters);
-        }
-    }
-}
-
 // ---- spill kernels: pairs that outgrew the per-thread containers ----------------------------------------------------------------
 // The reference keeps per-pair work in std::vectors (EPA polytope EPA.h:22-124, overlapBvh's triangle list TriangleMesh.cpp:166-192,
 // the contact list CTM.cpp:893-907) and in 128-point clip buffers (Clipping.cpp:6).  The bin kernels above hold them in per-thread
@@ -1122,38 +964,6 @@ static void launchMeshLight(pb_ctx* ctx, const int2* pairs, const int* pairOrder
 #undef LAUNCH_LIGHT
 }
 
-// the three-stage form for the step of a large scene; false when it does not apply (small scene, switched off, arena allocation failed)
-static bool launchMeshSplit(pb_ctx* ctx, const int2* pairs) {
-    if (ctx->meshSplitMode == 0 || ctx->pairsHint < (ctx->meshSplitMode == 2 ? 0 : 65536)) return false;      // mode 2 (tests): every scene, from its second step on
-    const int maxPairs = ctx->caps.max_pairs;
-    if (!ctx->mcPairInfo) {
-        // candidates: measured ~2.5 per pair on the 1 M-body terrain; room for 4 per possible pair of the previous step's count x 2, at least 1 M
-        long long cap = std::max<long long>(1 << 20, std::min<long long>(2ll * maxPairs, 8ll * std::max(ctx->pairsHint, 1)));
-        if (const char* e = getenv("PB_MESH_SPLIT_CAP")) if (atoi(e) > 0) cap = atoi(e);       // tests: a candidate arena that overflows
-        int rc = 0;
-        if (!rc) rc = pb_alloc(ctx, &ctx->mcPairInfo, 3 * (size_t)maxPairs);
-        if (!rc) rc = pb_alloc(ctx, &ctx->mcCandTri, (size_t)cap);
-        if (!rc) rc = pb_alloc(ctx, &ctx->mcCandPair, (size_t)cap);
-        if (!rc) rc = pb_alloc(ctx, &ctx->mcRes, 3 * (size_t)cap);
-        if (rc) { cudaGetLastError(); ctx->meshSplitMode = 0; return false; }
-        ctx->mcCap = (int)cap;
-    }
-    MeshSplit M{ ctx->mcCandTri, ctx->mcCandPair, ctx->mcRes, ctx->mcPairInfo, ctx->mcCap };
-    int* spill = ctx->spillList + PB_SPILL_CAP;
-#define CULL(TYPE) ++ctx->launches, k_mesh_cull<TYPE><<<npGrid(ctx, k_mesh_cull<TYPE>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, ctx->colMesh, \
-        ctx->colWPos, ctx->colWQuat, ctx->triMeshDev, M, spill)
-#define TEST(TYPE) ++ctx->launches, k_mesh_test<TYPE><<<npGrid(ctx, k_mesh_test<TYPE>, 128), 128, 0, ctx->stream>>>(ctx->counters, ctx->triMeshDev, M)
-#define FINISH(TYPE) ++ctx->launches, k_mesh_finish<TYPE><<<npGrid(ctx, k_mesh_finish<TYPE>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colWPos, ctx->colWQuat, \
-        ctx->triMeshDev, M, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, spill)
-    CULL(PB_SPHERE); CULL(PB_CAPSULE);        // sphere first: the capsule stage reads its final candidate count (shared arena, opposite ends)
-    TEST(PB_CAPSULE); TEST(PB_SPHERE);
-    FINISH(PB_CAPSULE); FINISH(PB_SPHERE);
-#undef CULL
-#undef TEST
-#undef FINISH
-    return true;
-}
-
 int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pairOrder, int cap, int4* mKey, float4* mNormal, float4* mPts) {
     const int blocks = 8;
     int* pairBin = pairOrder + cap;
@@ -1222,7 +1032,7 @@ int pb_narrowphase(pb_ctx* ctx) {
         if (!ctx->convexes.empty()) LAUNCH_MESH(PB_CONVEX_MESH);
         LAUNCH_MESH(PB_BOX);
         if (ctx->meshLightMode == 0) { LAUNCH_MESH(PB_CAPSULE); LAUNCH_MESH(PB_SPHERE); }
-        else if (!launchMeshSplit(ctx, pairs)) launchMeshLight(ctx, pairs, ctx->pairOrder, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, 0);
+        else launchMeshLight(ctx, pairs, ctx->pairOrder, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, 0);
     }
 #undef LAUNCH_MESH
     launchSpill(ctx, pairs, ctx->counters, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds);

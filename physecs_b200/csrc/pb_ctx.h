@@ -61,7 +61,6 @@ enum {
     CNT_SPILL_GJK, CNT_SPILL_MESH,      // pairs that outgrew the per-thread containers of their bin kernel (redone by the spill kernels)
     CNT_CAUSE,                          // PB_CAUSE_* bits (include/physecs_b200.h)
     CNT_SPILLED,                        // pairs the spill kernels redid
-    CNT_MC_S, CNT_MC_C,                 // (pair, triangle) candidates of the sphere / capsule vs mesh bins (three-stage form, narrowphase.cu)
     CNT_BIN0 = 16,                      // PB_NUM_BINS bin counters
     CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
     CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
@@ -133,9 +132,7 @@ struct pb_ctx {
     bool sortSmallOptIn = false;        // k_sort_small's dynamic shared memory opt-in done on this context's device
     int meshLightMode = 1;              // sphere / capsule vs mesh bins: 0 = k_np_mesh, 1 = k_np_mesh_light (dual-child cull walk + packed
                                         // triangle records) (env PB_MESH_LIGHT)
-    int walkMode = 1; bool walkOptIn = false;   // tree broadphase: 1 = walk by packet union box (k_lbvh_pairs_union), 0 = k_lbvh_pairs (env PB_WALK)
-    int meshSplitMode = 1;              // large scenes: sphere / capsule vs mesh as cull -> test per candidate -> finish (env PB_MESH_SPLIT=0: k_np_mesh_light)
-    int* mcCandTri = nullptr; int* mcCandPair = nullptr; float4* mcRes = nullptr; float4* mcPairInfo = nullptr; int mcCap = 0;
+    int mortonIso = 1;                  // Morton keys over cubic cells (one scale for the three axes); 0 = each axis scaled to its own extent (env PB_MORTON_ISO)
     int4* colInfo = nullptr;            // [colliders] (flags, body row, entity, 0) per collider, rewritten by k_morton for the pair walk
     int* bigList = nullptr;             // [1 + 32] count + colliders of the step's big-static side list (broadphase.cu k_morton)
     int bigListMode = 1;                // 0: every collider stays in the step's tree (env PB_BIG_LIST)

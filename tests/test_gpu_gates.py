@@ -146,23 +146,3 @@ def test_whole_step_kernel_group_by_group(maker, steps, fused_local_max, monkeyp
     monkeypatch.setenv("PB_ISLANDS", "1")
     s = parity.run_gates(maker(), steps=steps)
     assert s["steps"] == steps and s["manifolds"] > 0 and s["worst_manifold"] <= parity.TOL
-
-
-@pytest.mark.parametrize("cap", [0, 96])
-@pytest.mark.parametrize("maker,steps", [
-    (lambda: S.terrain(1500, cells=48, drop=0.3), 50),
-    (lambda: S.terrain(400, cells=80, drop=0.3, mesh_spacing=0.3), 50),     # tens of candidate triangles per body, several contacts each
-    (lambda: S.terrain_mixed(600, cells=40), 40),
-    (lambda: S.big_on_fine_mesh(), 8),                                       # pairs beyond the per-thread buffers: cull stage -> spill kernel
-])
-def test_three_gates_mesh_three_stage_form(maker, steps, cap, monkeypatch):
-    """Sphere / capsule vs mesh as three uniform stages (cull -> one thread per candidate triangle -> finish), the form large scenes
-    take; PB_MESH_SPLIT=2 forces it on small ones.  cap = 96: a candidate arena of 96 entries, so most pairs do not fit and go the
-    spill way while the rest share the arena from both ends -- the manifolds must not change."""
-    monkeypatch.setenv("PB_MESH_SPLIT", "2")
-    if cap:
-        monkeypatch.setenv("PB_MESH_SPLIT_CAP", str(cap))
-    s = parity.run_gates(maker(), steps=steps)
-    assert s["steps"] == steps and s["manifolds"] > 0 and s["worst_manifold"] <= parity.TOL
-    if cap:
-        assert s["spilled"] > 0, "the tiny arena was meant to overflow"

@@ -1,5 +1,5 @@
 """Small scenes through every device path, for compute-sanitizer (tools/gpu_sanitize.sh): island sweeps on / off, the whole-step kernel
-(grid-barrier and group-by-group forms), the cooperative sort, tree and all-pairs broadphase, the three-stage mesh form, the spill
+(grid-barrier and group-by-group forms), the cooperative sort, tree and all-pairs broadphase, the spill
 kernels, deterministic colouring.  No oracle: the sanitizer is the checker here."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,9 +23,8 @@ def run(name, desc, steps, **env):
 run("pyramid (one launch per step, grid barriers)", S.pyramid(60), 4)
 run("ragdolls, group by group", S.ragdolls(6), 45, PB_ISLANDS=1)
 run("ragdolls, per-substep launches + island sweeps", S.ragdolls(6), 45, PB_ISLANDS=1, PB_FUSED=0)
-run("mixed bin, tree broadphase (union walk) + cooperative sort + device-wide sweeps", S.mixed_bin(9000, spacing=0.8), 6, PB_BRUTE_FORCE_MAX=0, PB_ISLANDS=0, PB_FUSED=0)
-run("mixed bin, classic packet walk", S.mixed_bin(600, spacing=0.8), 6, PB_BRUTE_FORCE_MAX=0, PB_WALK=0)
-run("terrain, three-stage mesh form", S.terrain(600, cells=32, drop=0.05), 12, PB_MESH_SPLIT=2, PB_BRUTE_FORCE_MAX=0)
+run("mixed bin, tree broadphase (packet walk) + cooperative sort + device-wide sweeps", S.mixed_bin(9000, spacing=0.8), 6, PB_BRUTE_FORCE_MAX=0, PB_ISLANDS=0, PB_FUSED=0)
+run("terrain, tree broadphase + big-static list", S.terrain(600, cells=32, drop=0.05), 12, PB_BRUTE_FORCE_MAX=0)
 run("terrain mixed (all shape kinds on a mesh)", S.terrain_mixed(300, cells=24, drop=0.05), 10)
 run("big shapes on a fine mesh (mesh spill kernel)", S.big_on_fine_mesh(cells=40), 3)
 run("degenerate convex pairs (GJK / EPA spill kernel)", S.degenerate_convex(), 3)
