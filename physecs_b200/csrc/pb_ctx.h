@@ -204,6 +204,7 @@ struct pb_ctx {
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
     // per-group body lists (built when the whole-step kernel may run group by group): bodyOrder = bodies sorted by group, bodyStart[g] their runs
     int* bodyOrder = nullptr; int* bodyStart = nullptr; int* bodyCursor = nullptr; bool bodyListsBuilt = false;
+    int tailColours = 1;             // device-wide sweep: trailing colours of <= 1024 manifolds swept by one CTA (env PB_TAIL)
     int fusedLocalMax = 65536;       // bodies up to which an all-local scene takes the one-launch whole-step kernel (env PB_FUSED_LOCAL_MAX)
     int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)
     int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)

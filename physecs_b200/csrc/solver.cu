@@ -59,6 +59,7 @@ struct SubstepParams {
     // Groups 0..G-1 are islands small enough for one CTA (islands.cu, only when islandsOn), group G is the device-wide sweep.
     const int* keyStart; int G; int islandsOn;
     const int* jointOrder; const int* jointStart;     // per-group joint runs (islandsOn): jointStart[g * 8 + c]
+    int tailColours;                                  // device-wide sweep: small trailing colours swept by one CTA (env PB_TAIL=0: every colour over the grid)
     const int* bodyOrder; const int* bodyStart;       // per-group body lists (islands.cu; nullptr unless the whole-step kernel may run group by group)
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
     unsigned int* barrier;
@@ -513,25 +514,56 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
     // A colour that fits one round of the sweep lasts as long as its longest dependent chain, so its multi-point manifolds take
     // four lanes each (lane k = point k, all rows in one wave); over several rounds throughput matters and every manifold gets one
     // thread (the multi-point ones sit together at the end of the colour, so their longer path diverges in few warps).
-    auto contactPass = [&](auto mode, const int* runs, int id, int nthr, int useBias, int skipSoft) {
-        constexpr bool local = decltype(mode)::local, l1 = decltype(mode)::l1;
-        const int ngroups = nthr >> 2;
+    // one colour of a pass: `id` / `nthr` = this thread's index and the thread count of whoever sweeps it
+    auto contactColour = [&](auto mode, const int* runs, int c, int id, int nthr, int useBias, int skipSoft) {
+        constexpr bool l1 = decltype(mode)::l1;
+        const int start = runs[2 * c], mid = runs[2 * c + 1], count = runs[2 * c + 2] - start;
+        const int singles = mid - start, multis = count - singles;
+        if (singles + 4 * multis <= nthr) {
+            if (id < singles) contactSolve<l1>(P, start + id, useBias, skipSoft, velLive, angvelLive, H);
+            int g = (nthr >> 2) - 1 - (id >> 2);      // from the far end: the low threads hold the singles
+            if (g < multis) contactSolveQuad<l1>(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
+        } else {
+            for (int i = id; i < count; i += nthr) contactSolve<l1>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
+        }
+    };
+    // Device-wide sweep only: the colours from `tailStart` on hold a handful of manifolds each (greedy colour sizes fall off
+    // geometrically: a 100 k-body pile has 18 colours, the last ten with a few hundred manifolds in all).  Spread over the grid each of
+    // them still costs a full phase -- a dependent load chain plus a grid barrier, 3-6 us -- so CTA 0 takes the whole tail alone,
+    // colour after colour with CTA barriers, and the grid meets once behind it.  Colours still run in order: same arithmetic.
+    constexpr int TAIL = 1024;
+    auto tailOf = [&](const int* runs) {
+        int t = ncol;
+        for (int c = ncol - 1; c >= 0; --c) {
+            if (c == PB_OVERFLOW_COLOR) { if (runs[2 * c + 2] - runs[2 * c] > 0) break; t = c; continue; }
+            if (runs[2 * c + 2] - runs[2 * c] > TAIL) break;
+            t = c;
+        }
+        return t;
+    };
+    auto contactPass = [&](auto mode, const int* runs, int id, int nthr, int useBias, int skipSoft, int tailStart) {
+        constexpr bool local = decltype(mode)::local;
         for (int c = 0; c < ncol; ++c) {
-            const int start = runs[2 * c], mid = runs[2 * c + 1], count = runs[2 * c + 2] - start;
+            if (!local && c >= tailStart) break;
+            const int start = runs[2 * c], count = runs[2 * c + 2] - start;
             if (count <= 0) continue;
             if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
                 if (id == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
-            } else {
-                const int singles = mid - start, multis = count - singles;
-                if (singles + 4 * multis <= nthr) {
-                    if (id < singles) contactSolve<l1>(P, start + id, useBias, skipSoft, velLive, angvelLive, H);
-                    int g = ngroups - 1 - (id >> 2);      // from the far end: the low threads hold the singles
-                    if (g < multis) contactSolveQuad<l1>(P, mid + g, lane & 3, 0xFu << (lane & 28), useBias, skipSoft, velLive, angvelLive, H);
-                } else {
-                    for (int i = id; i < count; i += nthr) contactSolve<l1>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
-                }
-            }
+            } else contactColour(mode, runs, c, id, nthr, useBias, skipSoft);
             if (local) { __syncthreads(); stampLocal(1); } else bar.sync(PH_CONTACT_PASS, c);
+        }
+        if (!local && tailStart < ncol) {
+            bool any = false;
+            for (int c = tailStart; c < ncol; ++c) any |= runs[2 * c + 2] - runs[2 * c] > 0;
+            if (any) {          // uniform over the grid
+                if (blockIdx.x == 0)
+                    for (int c = tailStart; c < ncol; ++c) {
+                        if (runs[2 * c + 2] - runs[2 * c] <= 0) continue;
+                        contactColour(mode, runs, c, threadIdx.x, blockDim.x, useBias, skipSoft);
+                        __syncthreads();
+                    }
+                bar.sync(PH_CONTACT_PASS, tailStart);
+            }
         }
     };
     // joint colour runs of a sweep: jr[c] .. jr[c + 1] index P.jointOrder (islandsOn) or are the joint slots themselves
@@ -569,14 +601,14 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         if (!empty) {
             if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
             for (int it = 0; it < P.iterations; ++it) {
-                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0, 0);
                 if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
             }
         }
         __syncthreads();
         for (int k = P.bodyStart[g] + threadIdx.x; k < P.bodyStart[g + 1]; k += blockDim.x) integrateX<true>(P, P.bodyOrder[k], velLive, angvelLive);
         __syncthreads();
-        if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
+        if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1, 0);
         return;
     }
     // ---- phase A: NGS pass of the joints, then the iterations --------------------------------------------------------------------
@@ -587,13 +619,14 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
             if (sRuns[PB_KEY_COLORS] == sRuns[0] && (!P.hasJoints || sJoint[8] == sJoint[0])) continue;     // empty group
             if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
             for (int it = 0; it < P.iterations; ++it) {
-                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0, 0);
                 if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
             }
         }
     }
     const int* gRuns = P.keyStart + G * PB_KEY_COLORS;
     const int* gJoint = P.islandsOn ? P.jointStart + G * 8 : P.jointColorStart;
+    const int gTail = P.tailColours ? tailOf(gRuns) : ncol;
     if (P.hasJoints) {
         // rows were filled by k_joint_fill; the NGS pass accumulates into per-body pseudo velocities, colour by colour
         jointNgsPass(GLOBAL, gJoint, tid, nth);
@@ -604,7 +637,7 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         }
     }
     for (int it = 0; it < P.iterations; ++it) {
-        contactPass(GLOBAL, gRuns, tid, nth, 1, 0);
+        contactPass(GLOBAL, gRuns, tid, nth, 1, 0, gTail);
         if (P.hasJoints) {
             jointSolvePass(GLOBAL, gJoint, tid, nth, it == 0);
             int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
@@ -625,10 +658,10 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         for (int g = blockIdx.x; g < G; g += gridDim.x) {
             loadLocal(g);
             stampLocal(-1);
-            contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
+            contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1, 0);
         }
     }
-    contactPass(GLOBAL, gRuns, tid, nth, 0, 1);
+    contactPass(GLOBAL, gRuns, tid, nth, 0, 1, gTail);
 }
 
 
@@ -736,6 +769,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     P.keyStart = ctx->keyStart; P.G = ctx->islandGroups; P.islandsOn = ctx->islandsOn ? 1 : 0;
     P.jointOrder = (ctx->islandsOn && P.hasJoints) ? ctx->jointOrder : nullptr; P.jointStart = ctx->jointStart;
     P.bodyOrder = (ctx->islandsOn && ctx->bodyListsBuilt) ? ctx->bodyOrder : nullptr; P.bodyStart = ctx->bodyStart;
+    P.tailColours = ctx->tailColours;
     P.barrier = ctx->solveBarrier;
     P.profNs = ctx->profile ? ctx->solveProfNs : nullptr;
     // persistent grid: co-resident by construction; small scenes use fewer CTAs so the barrier stays cheap
