@@ -166,6 +166,7 @@ struct pb_ctx {
     int2* cRowsT = nullptr;          // transform rows (row0, row1)
     float4* cNormal = nullptr;       // n xyz, friction w
     float4* cSoft = nullptr;         // isSoft, frequency, dampingRatio, unused
+    float4* cStatQ = nullptr;        // orientation of the manifold's static / kinematic side (constant within a step)
     // per point, double-buffered (prev step kept for the contact cache)
     float4* pR0T[2] = {nullptr, nullptr};   // local r0 xyz, targetVelocity w
     float4* pR1 = nullptr;                  // local r1 xyz
@@ -204,7 +205,7 @@ struct pb_ctx {
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
     // per-group body lists (built when the whole-step kernel may run group by group): bodyOrder = bodies sorted by group, bodyStart[g] their runs
     int* bodyOrder = nullptr; int* bodyStart = nullptr; int* bodyCursor = nullptr; bool bodyListsBuilt = false;
-    int tailColours = 1;             // device-wide sweep: trailing colours of <= 1024 manifolds swept by one CTA (env PB_TAIL)
+    int fusedNarrowMax = 48;         // all-local scenes with at most this many constraints per group take the 128-thread whole-step kernel (env PB_FUSED_NARROW; 0 = never)
     int fusedLocalMax = 65536;       // bodies up to which an all-local scene takes the one-launch whole-step kernel (env PB_FUSED_LOCAL_MAX)
     int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)
     int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)

@@ -49,7 +49,7 @@ struct SubstepParams {
     float4* bodyRec;                 // 8 float4 (128 B) per dynamic body, written by integrate-v, read by the prep kernels (layout below)
     float4* pseudoLin; float4* pseudoAng;
     // contact constraints
-    const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const int* cPointOfs; const int* cNp;
+    const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const float4* cStatQ; const int* cPointOfs; const int* cNp;
     const float4* pR0T; const float4* pR1;
     float4* rowA; float4* rowB; float4* rowC; float4* rowD; float4* rowE; float4* rowF; float4* rowG; float2* rowL;
     int rowExtra;                    // rows of a manifold's FIRST point live at its solve slot s; points k >= 1 at rowExtra + (firstPoint - s) + k - 1
@@ -59,7 +59,6 @@ struct SubstepParams {
     // Groups 0..G-1 are islands small enough for one CTA (islands.cu, only when islandsOn), group G is the device-wide sweep.
     const int* keyStart; int G; int islandsOn;
     const int* jointOrder; const int* jointStart;     // per-group joint runs (islandsOn): jointStart[g * 8 + c]
-    int tailColours;                                  // device-wide sweep: small trailing colours swept by one CTA (env PB_TAIL=0: every colour over the grid)
     const int* bodyOrder; const int* bodyStart;       // per-group body lists (islands.cu; nullptr unless the whole-step kernel may run group by group)
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
     unsigned int* barrier;
@@ -196,10 +195,14 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
     float im0 = 0.f, im1 = 0.f;
     M3 I0, I1;
     I0.c[0] = I0.c[1] = I0.c[2] = mk3(0.f); I1 = I0;
+    // static / kinematic side: only its orientation matters (quirk Q25), and it does not change within a step -- the contact build keeps
+    // it per manifold (cStatQ: side 1's when that side is static, else side 0's), so it arrives with the body records instead of behind
+    // a third dependent load (header -> transform row -> quaternion; 14 % of this kernel's stall samples at 1 M bodies)
     if (bb.x >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.x); q0 = B.q; com0 = B.com; im0 = B.im; v0 = B.v; w0 = B.w; vp0 = B.vp; wp0 = B.wp; I0 = B.I; }
-    else q0 = mkq(ldq<CL>(&P.quat[rr.x]));       // static / kinematic side: only its orientation matters (quirk Q25)
+    else if (bb.y >= 0) q0 = mkq(P.cStatQ[s]);
+    else q0 = mkq(ldq<CL>(&P.quat[rr.x]));       // both sides static (a kinematic body on the ground): side 0 the long way
     if (bb.y >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.y); q1 = B.q; com1 = B.com; im1 = B.im; v1 = B.v; w1 = B.w; vp1 = B.vp; wp1 = B.wp; I1 = B.I; }
-    else q1 = mkq(ldq<CL>(&P.quat[rr.y]));
+    else q1 = mkq(P.cStatQ[s]);
     int po = hd.z, np = hd.w & 0xff;
     for (int k = 0; k < np; ++k) {
         float4 a = P.pR0T[po + k];
@@ -527,43 +530,18 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
             for (int i = id; i < count; i += nthr) contactSolve<l1>(P, start + i, useBias, skipSoft, velLive, angvelLive, H);
         }
     };
-    // Device-wide sweep only: the colours from `tailStart` on hold a handful of manifolds each (greedy colour sizes fall off
-    // geometrically: a 100 k-body pile has 18 colours, the last ten with a few hundred manifolds in all).  Spread over the grid each of
-    // them still costs a full phase -- a dependent load chain plus a grid barrier, 3-6 us -- so CTA 0 takes the whole tail alone,
-    // colour after colour with CTA barriers, and the grid meets once behind it.  Colours still run in order: same arithmetic.
-    constexpr int TAIL = 1024;
-    auto tailOf = [&](const int* runs) {
-        int t = ncol;
-        for (int c = ncol - 1; c >= 0; --c) {
-            if (c == PB_OVERFLOW_COLOR) { if (runs[2 * c + 2] - runs[2 * c] > 0) break; t = c; continue; }
-            if (runs[2 * c + 2] - runs[2 * c] > TAIL) break;
-            t = c;
-        }
-        return t;
-    };
-    auto contactPass = [&](auto mode, const int* runs, int id, int nthr, int useBias, int skipSoft, int tailStart) {
+    // (Measured and dropped: the small trailing colours of a pile -- a 100 k-body pile has 18 colours, the last ten with a few hundred
+    // manifolds in all -- swept by CTA 0 alone behind one grid barrier: 2.34 vs 2.21 ms/step at 100 k bodies; one CTA's L2 round
+    // trips per colour are no shorter than the grid's.)
+    auto contactPass = [&](auto mode, const int* runs, int id, int nthr, int useBias, int skipSoft) {
         constexpr bool local = decltype(mode)::local;
         for (int c = 0; c < ncol; ++c) {
-            if (!local && c >= tailStart) break;
             const int start = runs[2 * c], count = runs[2 * c + 2] - start;
             if (count <= 0) continue;
             if (c == PB_OVERFLOW_COLOR) {       // sequential bucket: manifolds may share bodies
                 if (id == 0) contactSolveSeqCall(P, start, count, useBias, skipSoft, velLive, angvelLive);
             } else contactColour(mode, runs, c, id, nthr, useBias, skipSoft);
             if (local) { __syncthreads(); stampLocal(1); } else bar.sync(PH_CONTACT_PASS, c);
-        }
-        if (!local && tailStart < ncol) {
-            bool any = false;
-            for (int c = tailStart; c < ncol; ++c) any |= runs[2 * c + 2] - runs[2 * c] > 0;
-            if (any) {          // uniform over the grid
-                if (blockIdx.x == 0)
-                    for (int c = tailStart; c < ncol; ++c) {
-                        if (runs[2 * c + 2] - runs[2 * c] <= 0) continue;
-                        contactColour(mode, runs, c, threadIdx.x, blockDim.x, useBias, skipSoft);
-                        __syncthreads();
-                    }
-                bar.sync(PH_CONTACT_PASS, tailStart);
-            }
         }
     };
     // joint colour runs of a sweep: jr[c] .. jr[c + 1] index P.jointOrder (islandsOn) or are the joint slots themselves
@@ -601,14 +579,14 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         if (!empty) {
             if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
             for (int it = 0; it < P.iterations; ++it) {
-                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0, 0);
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
                 if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
             }
         }
         __syncthreads();
         for (int k = P.bodyStart[g] + threadIdx.x; k < P.bodyStart[g + 1]; k += blockDim.x) integrateX<true>(P, P.bodyOrder[k], velLive, angvelLive);
         __syncthreads();
-        if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1, 0);
+        if (!empty) contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
         return;
     }
     // ---- phase A: NGS pass of the joints, then the iterations --------------------------------------------------------------------
@@ -619,14 +597,13 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
             if (sRuns[PB_KEY_COLORS] == sRuns[0] && (!P.hasJoints || sJoint[8] == sJoint[0])) continue;     // empty group
             if (P.hasJoints) jointNgsPass(LOCAL, sJoint, threadIdx.x, blockDim.x);
             for (int it = 0; it < P.iterations; ++it) {
-                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0, 0);
+                contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 1, 0);
                 if (P.hasJoints) jointSolvePass(LOCAL, sJoint, threadIdx.x, blockDim.x, it == 0);
             }
         }
     }
     const int* gRuns = P.keyStart + G * PB_KEY_COLORS;
     const int* gJoint = P.islandsOn ? P.jointStart + G * 8 : P.jointColorStart;
-    const int gTail = P.tailColours ? tailOf(gRuns) : ncol;
     if (P.hasJoints) {
         // rows were filled by k_joint_fill; the NGS pass accumulates into per-body pseudo velocities, colour by colour
         jointNgsPass(GLOBAL, gJoint, tid, nth);
@@ -637,7 +614,7 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         }
     }
     for (int it = 0; it < P.iterations; ++it) {
-        contactPass(GLOBAL, gRuns, tid, nth, 1, 0, gTail);
+        contactPass(GLOBAL, gRuns, tid, nth, 1, 0);
         if (P.hasJoints) {
             jointSolvePass(GLOBAL, gJoint, tid, nth, it == 0);
             int start = P.jointColorStart[8], count = P.jointColorStart[9] - start;
@@ -658,10 +635,10 @@ __device__ __forceinline__ void substepColoured(const SubstepParams& P, GridBarr
         for (int g = blockIdx.x; g < G; g += gridDim.x) {
             loadLocal(g);
             stampLocal(-1);
-            contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1, 0);
+            contactPass(LOCAL, sRuns, threadIdx.x, blockDim.x, 0, 1);
         }
     }
-    contactPass(GLOBAL, gRuns, tid, nth, 0, 1, gTail);
+    contactPass(GLOBAL, gRuns, tid, nth, 0, 1);
 }
 
 
@@ -680,9 +657,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
 // contact prep and joint row fill become grid-stride phases in front of the coloured part, and the velocity buffers swap inside the
 // kernel.  A step then costs one launch instead of four or five per substep, which is most of what such a step costs; the register
 // appetite of the prep phases (114) does not matter at this size.  Same device functions, same arithmetic, same order.
-__global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_constant__ SubstepParams P) {
-    __shared__ int sRuns[PB_KEY_COLORS + 1];
-    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+__device__ __forceinline__ void stepSolveSmall(const SubstepParams& P, int* sRuns, int* sJoint) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     if (stepSkipped(P.counters)) return;
@@ -734,6 +709,20 @@ __global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_consta
     }
 }
 
+__global__ void __launch_bounds__(256, 3) k_step_solve_small(const __grid_constant__ SubstepParams P) {
+    __shared__ int sRuns[PB_KEY_COLORS + 1];
+    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+    stepSolveSmall(P, sRuns, sJoint);
+}
+// The same kernel for CTAs of 128 threads, three per SM: 168 registers per thread instead of 80.  At 80 the prep and joint routines
+// spill ~2 KB per thread, and a batch of few little scenes -- one ragdoll per group: a step IS the dependent instruction chain of one
+// CTA carrying one ragdoll through four substeps -- pays for every spill on that chain.  Used when the groups hold little work.
+__global__ void __launch_bounds__(128, 3) k_step_solve_small_w(const __grid_constant__ SubstepParams P) {
+    __shared__ int sRuns[PB_KEY_COLORS + 1];
+    __shared__ int sJoint[PB_JOINT_COLORS + 1];
+    stepSolveSmall(P, sRuns, sJoint);
+}
+
 int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
     const int nDyn = ctx->nDyn;
     if (nDyn == 0) return PB_OK;
@@ -760,7 +749,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     P.kinematic = ctx->kinematic; P.comInvMass = ctx->comInvMass; P.invIL = ctx->invIL;
     P.pos = ctx->pos; P.quat = ctx->quat;
     P.bodyRec = ctx->bodyRec; P.pseudoLin = ctx->pseudoLin; P.pseudoAng = ctx->pseudoAng;
-    P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft;
+    P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft; P.cStatQ = ctx->cStatQ;
     P.cPointOfs = ctx->cPointOfsBuf[cur]; P.cNp = ctx->cNpBuf[cur]; P.pR0T = ctx->pR0T[cur]; P.pR1 = ctx->pR1;
     P.rowExtra = ctx->caps.max_manifolds;
     P.rowA = ctx->rowA; P.rowB = ctx->rowB; P.rowC = ctx->rowC; P.rowD = ctx->rowD; P.rowE = ctx->rowE; P.rowF = ctx->rowF; P.rowG = ctx->rowG; P.rowL = ctx->rowL;
@@ -769,7 +758,6 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     P.keyStart = ctx->keyStart; P.G = ctx->islandGroups; P.islandsOn = ctx->islandsOn ? 1 : 0;
     P.jointOrder = (ctx->islandsOn && P.hasJoints) ? ctx->jointOrder : nullptr; P.jointStart = ctx->jointStart;
     P.bodyOrder = (ctx->islandsOn && ctx->bodyListsBuilt) ? ctx->bodyOrder : nullptr; P.bodyStart = ctx->bodyStart;
-    P.tailColours = ctx->tailColours;
     P.barrier = ctx->solveBarrier;
     P.profNs = ctx->profile ? ctx->solveProfNs : nullptr;
     // persistent grid: co-resident by construction; small scenes use fewer CTAs so the barrier stays cheap
@@ -796,7 +784,11 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
         PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
         void* args[] = { &P };
         ++ctx->launches;
-        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small, dim3(fgrid), dim3(256), args, 0, ctx->stream));
+        // few constraints per group (a batch of few little scenes): the 128-thread form, whose threads keep their state in registers
+        const long long perGroup = ((long long)workBound + ctx->nJoints) / std::max(1, ctx->islandGroups);
+        const bool narrow = allLocal && ctx->fusedNarrowMax > 0 && perGroup <= ctx->fusedNarrowMax && ctx->rawHint >= 0;
+        if (narrow) PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small_w, dim3(fgrid), dim3(128), args, 0, ctx->stream));
+        else PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small, dim3(fgrid), dim3(256), args, 0, ctx->stream));
         if (substeps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); ++ctx->undoVelSwaps; }
     } else
     for (int sub = 0; sub < substeps; ++sub) {
