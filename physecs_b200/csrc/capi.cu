@@ -215,7 +215,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     A(nodeLeft, C); A(nodeRight, C); A(nodeParent, C); A(leafParent, C); A(nodeFlag, C); A(nodeRange, C); A(nodeMin, 2 * C); A(nodeMax, 2 * C);
     A(pairs, P); A(pairOrder, 2 * P); A(trigPairs, P); A(colClass, C);
     A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
-    A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M); A(cStatQ, M);
+    A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
     const size_t PT = 4 * M;
     for (int b = 0; b < 2; ++b) { A(pR0T[b], PT); A(cPointOfsBuf[b], M + 1); A(cNpBuf[b], M + 1); }
     A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
@@ -266,7 +266,7 @@ int pb_grow_arenas(pb_ctx* ctx, int maxPairs, int maxManifolds) {
         ctx->radixTiles = (int)((sortMax + 511) / 512);
         A(radixHist, (size_t)256 * ctx->radixTiles + (size_t)256 * ctx->radixTiles / 4096 + 1024);
         A(mKey, M); A(mNormal, M); A(mPts, 8 * M); A(mSortKeyA, M); A(mSortKeyB, M); A(mSortValB, M);
-        A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M); A(cStatQ, M);
+        A(cHead, M); A(cBodies, M); A(cRowsT, M); A(cNormal, M); A(cSoft, M);
         const size_t PT = 4 * M, oldPT = 4 * oldM;
         A(pR1, PT); A(rowA, PT); A(rowB, PT); A(rowC, PT); A(rowD, PT); A(rowE, PT); A(rowF, PT); A(rowG, PT); A(rowL, PT);
         const int keep = ctx->curBuf, other = keep ^ 1;
@@ -323,7 +323,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colInfo); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
-    F(mKey); F(mNormal); F(mPts); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft); F(cStatQ);
+    F(mKey); F(mNormal); F(mPts); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
     F(rowA); F(rowB); F(rowC); F(rowD); F(rowE); F(rowF); F(rowG); F(rowL);
     F(cacheTag[0]); F(cacheTag[1]); F(cacheVal[0]); F(cacheVal[1]); F(counters); F(triMeshDev); F(convexDev); F(nonColliding); F(trigPairs); F(colClass); F(filterLut); F(solveBarrier); F(solveProfNs); F(queryOut);

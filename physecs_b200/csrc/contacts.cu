@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) k_contact_build(
     const float4* __restrict__ mPts, const int* __restrict__ pointOfs, const int* __restrict__ colRow, const float4* __restrict__ colMat,
     int nDyn, const int* __restrict__ kinematic, const float4* __restrict__ pos, const float4* __restrict__ quat,
     const float4* __restrict__ vel, const float4* __restrict__ angvel, const float4* __restrict__ comInvMass,
-    int4* __restrict__ cHead, int2* __restrict__ cBodies, int2* __restrict__ cRowsT, float4* __restrict__ cNormal, float4* __restrict__ cSoft, float4* __restrict__ cStatQ, int* __restrict__ cNp,
+    int4* __restrict__ cHead, int2* __restrict__ cBodies, int2* __restrict__ cRowsT, float4* __restrict__ cNormal, float4* __restrict__ cSoft, int* __restrict__ cNp,
     float4* __restrict__ pR0T, float4* __restrict__ pR1,
     // previous step (contact cache)
     const unsigned long long* __restrict__ prevTag, const int4* __restrict__ prevVal, const int* __restrict__ prevPointOfs,
@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(128) k_contact_build(
         cRowsT[s] = make_int2(row0, row1);
         cNormal[s] = f4(nrm, friction);
         cSoft[s] = make_float4(isSoft, frequency, damping, 0.f);
-        if (b1 < 0) cStatQ[s] = f4(q1); else if (b0 < 0) cStatQ[s] = f4(q0);      // orientation of the static side for the prep kernels (solver.cu contactPrep)
         cNp[s] = np;
         if (useCache) {
             unsigned int h = (unsigned int)(tag >> 1) & cacheMask;
@@ -462,7 +461,7 @@ int pb_contact_build(pb_ctx* ctx) {
     cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
     ++ctx->launches, k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
         ctx->nDyn, ctx->kinematic, ctx->pos, ctx->quat, ctx->vel, ctx->angvel, ctx->comInvMass,
-        ctx->cHead, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cStatQ, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
+        ctx->cHead, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
         ctx->cacheValid ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],
         ctx->cacheTag[cur], ctx->cacheVal[cur], ctx->cacheSize - 1);
     PB_CUDA(ctx, cudaGetLastError());

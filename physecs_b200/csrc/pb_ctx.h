@@ -166,7 +166,6 @@ struct pb_ctx {
     int2* cRowsT = nullptr;          // transform rows (row0, row1)
     float4* cNormal = nullptr;       // n xyz, friction w
     float4* cSoft = nullptr;         // isSoft, frequency, dampingRatio, unused
-    float4* cStatQ = nullptr;        // orientation of the manifold's static / kinematic side (constant within a step)
     // per point, double-buffered (prev step kept for the contact cache)
     float4* pR0T[2] = {nullptr, nullptr};   // local r0 xyz, targetVelocity w
     float4* pR1 = nullptr;                  // local r1 xyz

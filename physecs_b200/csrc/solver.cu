@@ -49,7 +49,7 @@ struct SubstepParams {
     float4* bodyRec;                 // 8 float4 (128 B) per dynamic body, written by integrate-v, read by the prep kernels (layout below)
     float4* pseudoLin; float4* pseudoAng;
     // contact constraints
-    const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const float4* cStatQ; const int* cPointOfs; const int* cNp;
+    const int4* cHead; const int2* cBodies; const int2* cRowsT; const float4* cNormal; const float4* cSoft; const int* cPointOfs; const int* cNp;
     const float4* pR0T; const float4* pR1;
     float4* rowA; float4* rowB; float4* rowC; float4* rowD; float4* rowE; float4* rowF; float4* rowG; float2* rowL;
     int rowExtra;                    // rows of a manifold's FIRST point live at its solve slot s; points k >= 1 at rowExtra + (firstPoint - s) + k - 1
@@ -195,14 +195,12 @@ __device__ __forceinline__ void contactPrep(const SubstepParams& P, int s, const
     float im0 = 0.f, im1 = 0.f;
     M3 I0, I1;
     I0.c[0] = I0.c[1] = I0.c[2] = mk3(0.f); I1 = I0;
-    // static / kinematic side: only its orientation matters (quirk Q25), and it does not change within a step -- the contact build keeps
-    // it per manifold (cStatQ: side 1's when that side is static, else side 0's), so it arrives with the body records instead of behind
-    // a third dependent load (header -> transform row -> quaternion; 14 % of this kernel's stall samples at 1 M bodies)
+    // (Measured and dropped: the static side's orientation kept per manifold by the contact build.  The transform rows load in the
+    // first wave next to the header, so the quaternion is no deeper in the dependency chain than the body records: no gain, 16 B more.)
     if (bb.x >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.x); q0 = B.q; com0 = B.com; im0 = B.im; v0 = B.v; w0 = B.w; vp0 = B.vp; wp0 = B.wp; I0 = B.I; }
-    else if (bb.y >= 0) q0 = mkq(P.cStatQ[s]);
-    else q0 = mkq(ldq<CL>(&P.quat[rr.x]));       // both sides static (a kinematic body on the ground): side 0 the long way
+    else q0 = mkq(ldq<CL>(&P.quat[rr.x]));       // static / kinematic side: only its orientation matters (quirk Q25)
     if (bb.y >= 0) { BodyRec B = loadBodyRec<CL>(P.bodyRec, bb.y); q1 = B.q; com1 = B.com; im1 = B.im; v1 = B.v; w1 = B.w; vp1 = B.vp; wp1 = B.wp; I1 = B.I; }
-    else q1 = mkq(P.cStatQ[s]);
+    else q1 = mkq(ldq<CL>(&P.quat[rr.y]));
     int po = hd.z, np = hd.w & 0xff;
     for (int k = 0; k < np; ++k) {
         float4 a = P.pR0T[po + k];
@@ -749,7 +747,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     P.kinematic = ctx->kinematic; P.comInvMass = ctx->comInvMass; P.invIL = ctx->invIL;
     P.pos = ctx->pos; P.quat = ctx->quat;
     P.bodyRec = ctx->bodyRec; P.pseudoLin = ctx->pseudoLin; P.pseudoAng = ctx->pseudoAng;
-    P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft; P.cStatQ = ctx->cStatQ;
+    P.cHead = ctx->cHead; P.cBodies = ctx->cBodies; P.cRowsT = ctx->cRowsT; P.cNormal = ctx->cNormal; P.cSoft = ctx->cSoft;
     P.cPointOfs = ctx->cPointOfsBuf[cur]; P.cNp = ctx->cNpBuf[cur]; P.pR0T = ctx->pR0T[cur]; P.pR1 = ctx->pR1;
     P.rowExtra = ctx->caps.max_manifolds;
     P.rowA = ctx->rowA; P.rowB = ctx->rowB; P.rowC = ctx->rowC; P.rowD = ctx->rowD; P.rowE = ctx->rowE; P.rowF = ctx->rowF; P.rowG = ctx->rowG; P.rowL = ctx->rowL;
