@@ -276,6 +276,21 @@ def main():
 
     peak, peak_src = peaks()
 
+    def pcie_probe(mb=64):
+        """pinned <-> device copy rates of this box (GB/s): what the end-to-end figures below are made of"""
+        n = mb * 1024 * 1024 // 4
+        h = torch.empty(n, dtype=torch.float32).pin_memory()
+        dbuf = torch.empty(n, dtype=torch.float32, device=dev)
+        out = {}
+        for name, src, dst in (("h2d_gbs", h, dbuf), ("d2h_gbs", dbuf, h)):
+            best = 0.0
+            for _ in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dst.copy_(src, non_blocking=True); b.record(); torch.cuda.synchronize()
+                best = max(best, n * 4 / (a.elapsed_time(b) * 1e-3) / 1e9)
+            out[name] = best
+        return out
+
     # ---- scenes of the ncu captures other than the headline one ------------------------------------------------------------------
     if args.ncu and args.ncu_config != "C4":
         mk = {"C1": lambda: S.pyramid(1000), "C2": lambda: S.mixed_bin(100_000), "C3": lambda: S.convex_pile(250_000),
@@ -521,6 +536,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "p95_ms_per_step": float(np.percentile(e2e_ms, 95)), "checksum": checksum},
         "gpu_launches": int(launches),
+        "pcie": pcie_probe(),
         "roofline": roofline,
         "stage_ms_per_step": st,
     }
