@@ -449,6 +449,7 @@ def main():
         ctx.step()
     prof = ctx.profile()
     ctx.set_profile(False)
+    ksolve_ms, ksolve_launches = prof.pop("k_substep_solve_last_step", (0.0, 0))     # CUDA events around each launch of the last profiled step
     phase_ms = {k: v[0] / prof_steps for k, v in prof.items()}
     islands = ctx.island_stats()
     bins = ctx.bin_counts()
@@ -488,16 +489,25 @@ def main():
     stages["narrowphase"]["bins"] = bins
     stages["narrowphase"]["per_bin_ncu"] = tj.get("narrowphase_bins")      # time, DRAM bytes, threads per instruction per bin kernel (ncu capture named in traffic.json)
     pass_ms = phase_ms.get("contact_pass", 0.0) + phase_ms.get("local_sweeps", 0.0)
-    roofline = {"bound": "hbm", "kernel": "k_integrate_v + k_contact_prep + k_substep_solve (the TGS substep loop: 3 kernels x %d substeps per step)" % S_,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_step": bytes_loop, "ms_per_step": loop_ms, "launches_per_step": 3 * S_, "steps_timed": len(stage["solve_kernels"]),
-                "share_of_step": loop_ms / ms_per_step,
+    # the dominant kernel: k_substep_solve, one launch per substep = every contact colour of (iterations + 1) passes + position integration
+    k_launch_ms = ksolve_ms / ksolve_launches if ksolve_launches else 0.0
+    k_bytes = (bytes_solve + 120.0 * n_dyn * S_) / S_                      # algorithmic bytes of ONE launch (solve passes + integrate-x)
+    k_achieved = k_bytes / (k_launch_ms * 1e-3) / 1e9 if k_launch_ms > 0 else 0.0
+    k_traffic = (tj.get("kernels", {}).get("k_substep_solve", {}) or {}).get("dram_bytes_per_step")
+    k_traffic = k_traffic / S_ if k_traffic else None
+    roofline = {"bound": "hbm", "kernel": "k_substep_solve", "achieved": k_achieved, "peak": peak, "unit": "GB/s", "frac": k_achieved / peak,
+                "traffic": k_traffic, "peak_source": peak_src, "bytes_per_launch": k_bytes, "launch_ms": k_launch_ms, "launches_per_step": S_,
+                "launches_timed": int(ksolve_launches), "share_of_step": k_launch_ms * S_ / ms_per_step,
+                "measured_frac": (k_traffic / (k_launch_ms * 1e-3) / 1e9 / peak) if (k_traffic and k_launch_ms > 0) else None,
+                "substep_loop": {"kernels": "k_integrate_v + k_contact_prep + k_substep_solve, %d substeps" % S_, "achieved": achieved, "frac": achieved / peak,
+                                 "bytes_per_step": bytes_loop, "ms_per_step": loop_ms, "traffic": traffic, "share_of_step": loop_ms / ms_per_step},
                 "phases_from_in_kernel_stamps": {"contact_solve_passes_ms": pass_ms, "contact_solve_passes_GB/s": bytes_solve / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0,
                                                   "all": phase_ms},
                 "stages": stages, "islands": islands,
-                "note": "achieved = SURVEY.md 8d algorithmic bytes of the substep loop / CUDA-event time around its launches (events on the context's stream, "
-                        "a few steps after the timed region); traffic = DRAM bytes ncu measured for the same launches (profiles/traffic.json names the capture); "
-                        "the phase split comes from %globaltimer stamps CTA 0 takes at the grid barriers"}
+                "note": "achieved = SURVEY.md 8d algorithmic bytes of one k_substep_solve launch (contact solve passes x (iterations + 1) + integrate-x) / its average launch "
+                        "duration by CUDA events on the context's stream (the launches of a step a few steps after the timed region); traffic = DRAM bytes ncu measured for "
+                        "the same launch (profiles/traffic.json names the capture), measured_frac = traffic / duration / peak; SURVEY's byte model counts stale-velocity "
+                        "reads the kernel does not make, so achieved overstates what moves; substep_loop / stages = the same for the whole loop and for every stage of the step"}
 
     # ---- timed region B: end to end through the C ABI with pinned host buffers --------------------------------------
     pos_t = torch.empty((n_dyn, 3), dtype=torch.float32).pin_memory(); quat_t = torch.empty((n_dyn, 4), dtype=torch.float32).pin_memory()

@@ -259,7 +259,8 @@ int pb_set_deterministic(pb_ctx* ctx, int on);
 
 /* optional in-kernel phase profile of the persistent substep kernel (bench.py roofline), accumulated since pb_set_profile(ctx, 1):
  * kinds 0 = integrate velocities, 1 = joint NGS phases, 2 = contact colour phases of the device-wide sweep, 3 = joint solve phases,
- * 4 = integrate positions, 5 = the per-CTA island sweeps (all their contact and joint colours; islands on). */
+ * 4 = integrate positions, 5 = the per-CTA island sweeps (all their contact and joint colours; islands on);
+ * slot 6 = the k_substep_solve launches of the LAST step timed by CUDA events on the context's stream (ms summed, number of launches). */
 int pb_set_profile(pb_ctx* ctx, int on);
 int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8);
 /* the contact-pass share of it per solver colour: accumulated ms and number of phases for colours 0..63 */

@@ -282,7 +282,9 @@ class Context:
         self._check(self.lib.pb_get_profile(self.ctx, ms, cnt))
         # (milliseconds, number of phases) per phase kind of the persistent substep kernel
         names = ["integrate_v", "prep", "contact_pass", "joint_solve", "integrate_x", "local_sweeps"]
-        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+        out = {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+        out["k_substep_solve_last_step"] = (ms[6], cnt[6])      # CUDA events around the launches of the last step: (ms summed, launches)
+        return out
 
     def profile_colors(self):
         """(ms, phases) accumulated per contact colour since profiling was switched on."""

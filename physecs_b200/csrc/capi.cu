@@ -148,6 +148,12 @@ int pb_get_profile(pb_ctx* ctx, double* ms8, long long* count8) {
     int rc = pb_solve_profile(ctx, raw, false);
     if (rc) return rc;
     for (int k = 0; k < 8; ++k) { ms8[k] = k < 6 ? raw[k] * 1e-6 : 0.0; count8[k] = k < 6 ? (long long)raw[6 + k] : 0; }
+    // slot 6: the k_substep_solve launches of the LAST step, timed by CUDA events on the context's stream (ms summed, launches)
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < ctx->evSubCount; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evSub[2 * k], ctx->evSub[2 * k + 1]) == cudaSuccess) { ms8[6] += ms; ++count8[6]; }
+    }
     return PB_OK;
 }
 int pb_get_profile_colors(pb_ctx* ctx, double* ms64, long long* count64) {
@@ -316,6 +322,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->evPoseReady) cudaEventDestroy(ctx->evPoseReady);
     if (ctx->evCounters) cudaEventDestroy(ctx->evCounters);
     for (auto& e : ctx->evRead) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evSub) if (e) cudaEventDestroy(e);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);

@@ -236,6 +236,7 @@ struct pb_ctx {
     std::vector<int> hKinematic;     // host mirror of `kinematic` (which trimesh colliders ride on moving bodies)
     unsigned long long launches = 0; // kernels launched by this context since creation (bench: gpu_launches)
     bool profile = false;            // per-phase device timing inside the persistent substep kernel (pb_set_profile)
+    cudaEvent_t evSub[16] = {nullptr}; int evSubCount = 0;     // profiling: events around the k_substep_solve launches of the last step
 };
 
 

@@ -766,6 +766,7 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
     // phases of latency however few constraints the group holds); the two grid barriers per substep are cheap next to that
     if (ctx->islandsOn) grid = std::min(ctx->solveGrid, ctx->islandGroups);
     cudaEventRecord(ctx->ev[5], ctx->stream);
+    ctx->evSubCount = 0;
     // small scenes: the whole substep loop in one launch (k_step_solve_small); PB_FUSED=0 / 1 overrides the size rule
     const int fusedEnv = ctx->fusedMode;      // env PB_FUSED at context creation
     // (measured: equal or slightly ahead up to ~1 k bodies -- 64 ragdolls 0.78 vs 0.80 ms/step, 1 k-box pyramid 1.50 vs 1.52 -- and behind
@@ -797,7 +798,14 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
         PB_CUDA(ctx, cudaMemsetAsync(ctx->solveBarrier, 0, sizeof(unsigned int), ctx->stream));
         void* args[] = { &P };
         ++ctx->launches;
+        // profiling (pb_set_profile): CUDA events around every k_substep_solve launch of the step (bench.py: roofline of the dominant kernel)
+        const bool timeIt = ctx->profile && sub < 8;
+        if (timeIt) {
+            if (!ctx->evSub[2 * sub]) { cudaEventCreate(&ctx->evSub[2 * sub]); cudaEventCreate(&ctx->evSub[2 * sub + 1]); }
+            cudaEventRecord(ctx->evSub[2 * sub], ctx->stream);
+        }
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_substep_solve, dim3(grid), dim3(256), args, 0, ctx->stream));
+        if (timeIt) { cudaEventRecord(ctx->evSub[2 * sub + 1], ctx->stream); ctx->evSubCount = sub + 1; }
         // write-back (Physecs.cpp:523-530): velocityTemp becomes the component velocity of the next substep
         std::swap(ctx->vel, ctx->velLive);
         std::swap(ctx->angvel, ctx->angvelLive);
