@@ -689,7 +689,7 @@ int pb_collect_step(pb_ctx* ctx) {
     PB_CUDA(ctx, cudaEventSynchronize(ctx->evCounters));
     const int* h = ctx->hCounters;
     const int nPairs = h[CNT_PAIRS], nRaw = h[CNT_RAWM], status = h[CNT_STATUS], cause = h[CNT_CAUSE];
-    if (ctx->islandsOn && ctx->islandStats) { ctx->lastIslandLocal = h[CNT_TOTAL]; ctx->lastIslandTotal = h[CNT_TOTAL + 1]; }    // of the step before (rode along)
+    if (ctx->statsCopied) { ctx->lastIslandLocal = h[CNT_TOTAL]; ctx->lastIslandTotal = h[CNT_TOTAL + 1]; }    // of the step before (rode along)
     ctx->lastCounts = pb_counts{};
     ctx->lastCounts.n_pairs = nPairs;
     ctx->lastCounts.n_mesh_pairs = h[CNT_MESH_PAIRS];
@@ -757,7 +757,8 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     // counters of the narrowphase (pairs, raw manifolds, status, triggers) to pinned memory; the island statistics of the PREVIOUS
     // step ride along.  Nobody waits here: pb_collect_step looks at them later.
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->islandsOn && ctx->islandStats) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->statsCopied = ctx->islandsOn && ctx->islandStats;
+    if (ctx->statsCopied) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaEventRecord(ctx->evCounters, ctx->stream));
     ctx->undoCacheValid = ctx->cacheValid; ctx->undoCacheBuilt = ctx->cacheBuilt; ctx->undoVelSwaps = 0;
     ctx->stepPending = true;

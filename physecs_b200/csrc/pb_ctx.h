@@ -223,7 +223,7 @@ struct pb_ctx {
     // A step is enqueued without a host sync: the arena checks happen on the device (a step that overflowed skips its solve and leaves
     // the scene untouched) and the host COLLECTS the outcome -- counters snapshot, status -- at the next call that synchronises with the
     // step (capi.cu collectStep).  stepPending: a step's outcome has not been collected yet; undo*: host bookkeeping to roll back then.
-    cudaEvent_t evCounters = nullptr; bool stepPending = false;
+    cudaEvent_t evCounters = nullptr; bool stepPending = false; bool statsCopied = false;   // statsCopied: the island statistics rode along with the counters
     bool stepBegun = false;          // pb_step_begin ran: the next pb_step continues behind its broadphase
     bool mainMarked = false;         // evMainAtSet already holds "the main stream before this step's broadphase": uploads wait for that
     cudaEvent_t evRead[PB_MAX_READ_CHUNKS] = {nullptr}; int readFirst[PB_MAX_READ_CHUNKS] = {0}, readCount[PB_MAX_READ_CHUNKS] = {0}, readChunks = 0;   // pb_get_state_begin / _wait
