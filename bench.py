@@ -593,9 +593,22 @@ def main():
                 walls.append(time.perf_counter() - tt)
             wall = float(np.mean(walls))
             stt = hs.stats()
-            out["e2e_scene"] = {"api": "physecs::Scene::simulate over entt::registry (host gather -> pb_set_state -> pb_step -> pb_get_state -> scatter)",
+            out["e2e_scene"] = {"api": "physecs::Scene::simulate over entt::registry (pb_step_begin, gather + pb_set_state_rows in chunks behind the broadphase, pb_step, "
+                                       "pb_get_state_begin / _wait + scatter chunk by chunk)",
                                 "value": sd.n_dynamic / wall, "unit": UNIT, "ms_per_step": wall * 1e3, "p95_ms_per_step": float(np.percentile(walls, 95) * 1e3), "bodies": sd.n_dynamic,
                                 "host_threads": threads + 1, "gather_ms": stt["gather_ms"], "scatter_ms": stt["scatter_ms"], "device_ms": stt["device_ms"]}
+            # the same with Scene::setSyncMode(SYNC_DEVICE_AUTHORITATIVE): the registry is written every step but only read for bodies the
+            # application announced (registry.patch / notifyBodyChanged) -- the mode for applications that let the solver own the state
+            hs.set_sync_mode(True)
+            for _ in range(5):
+                hs.simulate()
+            walls = []
+            for _ in range(ks):
+                tt = time.perf_counter()
+                hs.simulate()
+                walls.append(time.perf_counter() - tt)
+            out["e2e_scene"]["device_authoritative"] = {"ms_per_step": float(np.mean(walls)) * 1e3, "p95_ms_per_step": float(np.percentile(walls, 95) * 1e3),
+                                                        "value": sd.n_dynamic / float(np.mean(walls)), "unit": UNIT}
             hs.close()
         except Exception as e:
             out["e2e_scene"] = {"unavailable": str(e)[:200]}
