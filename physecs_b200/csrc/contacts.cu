@@ -404,8 +404,7 @@ int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
 // arena (CNT_STATUS), the kernels still run over the clamped counts -- everything they write is per-step scratch or the "current"
 // half of a double buffer that the host flips back when it collects the step's status (capi.cu collectStep).
 int pb_contact_build(pb_ctx* ctx) {
-    int blocks = ctx->numSMs * 8;
-    if (ctx->rawHint >= 0) blocks = std::max(ctx->numSMs, std::min(blocks, (2 * ctx->rawHint + 4096) / 256 + 1));
+    const int blocks = pb_hint_grid(ctx->rawHint, 256, ctx->numSMs * 8);
     int maxM = ctx->caps.max_manifolds;
     const int G = ctx->islandGroups, nKeys = (G + 1) * PB_KEY_COLORS;
     int rc;

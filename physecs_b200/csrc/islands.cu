@@ -223,8 +223,7 @@ int pb_islands_build(pb_ctx* ctx) {
     const bool joints = pb_joint_view(ctx, &J);
     const int nJ = joints ? J.n : 0;
     const int2* jb = joints ? J.bodies : nullptr;
-    int hookBlocks = blocks;
-    if (ctx->rawHint >= 0) hookBlocks = std::max(ctx->numSMs, std::min(blocks, (std::max(ctx->rawHint, nJ) + 255) / 256 + 1));
+    const int hookBlocks = pb_hint_grid(ctx->rawHint < 0 ? -1 : std::max(ctx->rawHint, nJ), 256, blocks);
     ++ctx->launches, k_island_hook<<<hookBlocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, nJ, jb, ctx->islandParent);
     ++ctx->launches, k_island_compress<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->bodyGroup);
     ++ctx->launches, k_island_count<<<hookBlocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->caps.max_manifolds, ctx->mKey, ctx->colRow, n, ctx->kinematic, nJ, jb,

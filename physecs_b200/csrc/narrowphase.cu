@@ -992,14 +992,14 @@ int pb_narrowphase_query(pb_ctx* ctx, int* counters, const int2* pairs, int* pai
 
 int pb_narrowphase(pb_ctx* ctx) {
     if (ctx->nCol < 2) return PB_OK;
-    int blocks = ctx->numSMs * 8;
+    const int blocks = pb_hint_grid(ctx->pairsHint, 256, ctx->numSMs * 8);
     int* pairBin = ctx->pairOrder + ctx->caps.max_pairs;   // second half of the pairOrder allocation
     { int rc = ensureSpillScratch(ctx); if (rc) return rc; }
     ++ctx->launches, k_pair_classify<<<blocks, 256, 0, ctx->stream>>>((const int2*)ctx->pairs, pairBin, ctx->counters, ctx->caps.max_pairs, ctx->colType, ctx->colFlags,
                                                       ctx->colRow, ctx->rowEntity, ctx->nonColliding, ctx->nNonColliding,
                                                       ctx->colClass, ctx->filterLut, ctx->nFilterClasses);
     ++ctx->launches, k_bin_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters);
-    ++ctx->launches, k_pair_scatter<<<ctx->numSMs * 2, SCATTER_THREADS, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
+    ++ctx->launches, k_pair_scatter<<<pb_hint_grid(ctx->pairsHint, SCATTER_THREADS, ctx->numSMs * 2), SCATTER_THREADS, 0, ctx->stream>>>(pairBin, ctx->pairOrder, ctx->counters, ctx->caps.max_pairs);
     const int2* pairs = (const int2*)ctx->pairs;
 #define LAUNCH_PRIM(BIN) ++ctx->launches, k_np_prim<BIN><<<npGrid(ctx, k_np_prim<BIN>, 128), 128, 0, ctx->stream>>>(pairs, ctx->pairOrder, ctx->counters, ctx->colType, ctx->colParams, \
         ctx->colWPos, ctx->colWQuat, ctx->convexDev, ctx->colMesh, ctx->mKey, ctx->mNormal, ctx->mPts, ctx->caps.max_manifolds, ctx->spillList)

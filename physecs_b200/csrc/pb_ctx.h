@@ -253,6 +253,14 @@ template <class T> static inline int pb_alloc(pb_ctx* ctx, T** p, size_t n) {
 }
 
 static inline int pb_grid(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
+// Grid of a grid-stride kernel over a count only the device knows: `hint` = the host's guess (the previous step's count, -1 = none),
+// with headroom; never more than `most` CTAs.  Only shapes the launch -- a step of a small scene is a chain of few-microsecond kernels,
+// and a thousand empty CTAs per launch are most of what such a kernel costs.
+static inline int pb_hint_grid(int hint, int block, int most) {
+    if (hint < 0) return most;
+    long long g = (2ll * hint + 2048 + block - 1) / block;
+    return (int)(g < 8 ? 8 : (g > most ? most : g));
+}
 
 // stage launches (implemented in the .cu files)
 int pb_wait_velocities(pb_ctx* ctx);   // main stream waits for a pending pb_set_state upload, poses and velocities (capi.cu)
