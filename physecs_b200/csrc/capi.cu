@@ -242,6 +242,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
     if (const char* e = getenv("PB_MESH_LIGHT")) ctx->meshLightMode = atoi(e);
     if (const char* e = getenv("PB_NP_WAVES")) ctx->npWaves = atoi(e) >= 0 ? atoi(e) : 4;
+    if (const char* e = getenv("PB_CLUSTER")) if (atoi(e) == 0) ctx->clusterSize = 0;
     if (const char* e = getenv("PB_FUSED_NARROW")) ctx->fusedNarrowMax = atoi(e);
     if (const char* e = getenv("PB_MORTON_ISO")) ctx->mortonIso = atoi(e);
     if (const char* e = getenv("PB_NP_FUSE")) ctx->npFuseSmall = atoi(e);

@@ -204,6 +204,7 @@ struct pb_ctx {
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
     // per-group body lists (built when the whole-step kernel may run group by group): bodyOrder = bodies sorted by group, bodyStart[g] their runs
     int* bodyOrder = nullptr; int* bodyStart = nullptr; int* bodyCursor = nullptr; bool bodyListsBuilt = false;
+    int clusterSize = -1;            // CTAs of the thread-block cluster small one-pile scenes run their whole-step kernel as (-1: not asked yet, 0: off; env PB_CLUSTER=0)
     int fusedNarrowMax = 48;         // all-local scenes with at most this many constraints per group take the 128-thread whole-step kernel (env PB_FUSED_NARROW; 0 = never)
     int fusedLocalMax = 65536;       // bodies up to which an all-local scene takes the one-launch whole-step kernel (env PB_FUSED_LOCAL_MAX)
     int islandGroups = 0;            // G: fixed per context (the co-resident CTA count of the persistent kernel)

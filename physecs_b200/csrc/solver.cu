@@ -63,6 +63,7 @@ struct SubstepParams {
     // grid barrier + optional phase timing (ns per phase kind, accumulated by CTA 0)
     unsigned int* barrier;
     unsigned long long* profNs;
+    int clusterBarrier;              // the launch is one thread-block cluster: GridBarrier uses barrier.cluster
 };
 
 template <bool LOCAL_SYNC, bool L1> struct SweepMode { static constexpr bool local = LOCAL_SYNC, l1 = L1; };
@@ -408,7 +409,22 @@ struct GridBarrier {
     unsigned int target;
     unsigned long long* profNs;
     unsigned long long tPrev;
+    int cluster;        // the grid is ONE thread-block cluster (k_step_solve_small on small scenes): the hardware cluster barrier replaces the counter
     __device__ __forceinline__ void sync(int kind, int color = -1) {
+        if (cluster) {
+            // barrier.cluster with release / acquire semantics orders the global writes of every CTA of the cluster before the reads
+            // that follow it (PTX ISA, "barrier.cluster"): the same guarantee as the counter below, in hardware, for <= 16 CTAs
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (profNs && blockIdx.x == 0 && threadIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                atomicAdd(&profNs[kind], t - tPrev);
+                atomicAdd(&profNs[PH_KINDS + kind], 1ull);
+                if (color >= 0 && color < PB_MAX_COLORS) { atomicAdd(&profNs[2 * PH_KINDS + color], t - tPrev); atomicAdd(&profNs[2 * PH_KINDS + PB_MAX_COLORS + color], 1ull); }
+                tPrev = t;
+            }
+            return;
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
@@ -645,7 +661,7 @@ __global__ void __launch_bounds__(256, 3) k_substep_solve(const __grid_constant_
     __shared__ int sJoint[PB_JOINT_COLORS + 1];
     if (stepSkipped(P.counters)) return;       // uniform over the grid: nobody reaches a barrier
     GridBarrier bar;
-    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
+    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0; bar.cluster = 0;
     if (P.profNs && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
     substepColoured<true>(P, bar, P.velB, P.angvelB, sRuns, sJoint);
     if (P.islandsOn && P.profNs) bar.sync(PH_LOCAL);     // profiling only: closes the local relaxation sweeps of every CTA
@@ -660,7 +676,7 @@ __device__ __forceinline__ void stepSolveSmall(const SubstepParams& P, int* sRun
     const int nth = gridDim.x * blockDim.x;
     if (stepSkipped(P.counters)) return;
     GridBarrier bar;
-    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0;
+    bar.counter = P.barrier; bar.target = 0; bar.profNs = P.profNs; bar.tPrev = 0; bar.cluster = P.clusterBarrier;
     if (P.profNs && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(bar.tPrev));
     const int nManifolds = P.counters[CNT_MANIFOLDS];
     float4* vel = P.velA; float4* angvel = P.angvelA; float4* velLive = P.velB; float4* angvelLive = P.angvelB;
@@ -736,6 +752,21 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
         if (perSM2 < perSM) perSM = perSM2;       // both persistent kernels use the same co-resident grid
         if (perSM < 1) return pb_fail(ctx, PB_ECUDA, "k_step_solve_small does not fit on an SM");
         ctx->solveGrid = perSM * ctx->numSMs;
+        // largest cluster of 256-thread CTAs of the whole-step kernel the device schedules (16 needs the non-portable opt-in, 8 is portable)
+        if (ctx->clusterSize < 0) {
+            ctx->clusterSize = 0;
+            for (int c : { 16, 8 }) {
+                if (c > 8 && cudaFuncSetAttribute(k_step_solve_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(c); cfg.blockDim = dim3(256);
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, k_step_solve_small, &cfg) == cudaSuccess && n >= 1) { ctx->clusterSize = c; break; }
+                cudaGetLastError();
+            }
+        }
         int rc = pb_alloc(ctx, &ctx->solveBarrier, 64); if (rc) return rc;
         rc = pb_alloc(ctx, &ctx->solveProfNs, PROF_WORDS); if (rc) return rc;
         PB_CUDA(ctx, cudaMemsetAsync(ctx->solveProfNs, 0, sizeof(unsigned long long) * PROF_WORDS, ctx->stream));
@@ -786,7 +817,21 @@ int pb_solve(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity)
         // few constraints per group (a batch of few little scenes): the 128-thread form, whose threads keep their state in registers
         const long long perGroup = ((long long)workBound + ctx->nJoints) / std::max(1, ctx->islandGroups);
         const bool narrow = allLocal && ctx->fusedNarrowMax > 0 && perGroup <= ctx->fusedNarrowMax && ctx->rawHint >= 0;
-        if (narrow) PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small_w, dim3(fgrid), dim3(128), args, 0, ctx->stream));
+        // A small scene whose constraints form one pile (islands off: a box pyramid) sweeps its colours device-wide.  When a handful of
+        // CTAs hold it, they are launched as ONE thread-block cluster: co-scheduled on a GPC by construction (no cooperative launch), and
+        // the ~240 colour phases of a step meet at the hardware cluster barrier instead of an atomic counter in L2.
+        const bool asCluster = !ctx->islandsOn && ctx->clusterSize > 0 && fgrid <= 4 * ctx->clusterSize;
+        if (asCluster) {
+            P.clusterBarrier = 1;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(ctx->clusterSize); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = ctx->clusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_step_solve_small, P));
+        }
+        else if (narrow) PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small_w, dim3(fgrid), dim3(128), args, 0, ctx->stream));
         else PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_solve_small, dim3(fgrid), dim3(256), args, 0, ctx->stream));
         if (substeps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); ++ctx->undoVelSwaps; }
     } else

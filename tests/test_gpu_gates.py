@@ -146,3 +146,16 @@ def test_whole_step_kernel_group_by_group(maker, steps, fused_local_max, monkeyp
     monkeypatch.setenv("PB_ISLANDS", "1")
     s = parity.run_gates(maker(), steps=steps)
     assert s["steps"] == steps and s["manifolds"] > 0 and s["worst_manifold"] <= parity.TOL
+
+
+@pytest.mark.parametrize("cluster", [0, 1])
+@pytest.mark.parametrize("maker,steps", [(lambda: S.pyramid(300), 40), (lambda: S.mixed_bin(900, spacing=0.8), 40), (lambda: S.joint_zoo(), 40)])
+def test_three_gates_cluster_barrier(maker, steps, cluster, monkeypatch):
+    """Small one-pile scenes run their whole-step kernel as ONE thread-block cluster (<= 16 CTAs) whose colour phases meet at the hardware
+    cluster barrier; PB_CLUSTER=0 keeps the cooperative launch with the counter barrier.  Islands off, so every colour goes through the
+    device-wide sweep either way.  Same results, bit for bit against the oracle."""
+    monkeypatch.setenv("PB_CLUSTER", str(cluster))
+    monkeypatch.setenv("PB_ISLANDS", "0")
+    monkeypatch.setenv("PB_FUSED", "1")
+    s = parity.run_gates(maker(), steps=steps)
+    assert s["steps"] == steps and s["worst_manifold"] <= parity.TOL
