@@ -35,7 +35,7 @@ for var in variants:
     pos = ctx.get_state()[0] if hasattr(ctx, "get_state") else None
     chk = float(np.abs(pos).sum()) if pos is not None else 0.0
     print(f"{d.name} [{var or 'default'}]: best {best:.3f} ms/step; broad {acc[0]:.3f} narrow {acc[1]:.3f} build {acc[2]:.3f} solve {acc[3]:.3f} total {acc[4]:.3f}; "
-          f"pairs {c.n_pairs} manifolds {c.n_manifolds} checksum {chk:.6e}", flush=True)
+          f"pairs {c.n_pairs} manifolds {c.n_manifolds} colours {c.n_colors} islands {ctx.island_stats()} checksum {chk:.6e}", flush=True)
     ctx.close()
     for k, _ in kv:
         os.environ.pop(k, None)
