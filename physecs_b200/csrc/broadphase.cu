@@ -576,7 +576,6 @@ int pb_build_tree(pb_ctx* ctx, bool forStep) {
 // n == 2..: general path.  n < 2: no pairs.
 int pb_broadphase(pb_ctx* ctx) {
     int n = ctx->nCol;
-    ctx->stepTree = false;
     if (n < 2) return PB_OK;
     if (n <= ctx->bruteForceMax) {
         const int tiles = (n + BF_TILE - 1) / BF_TILE;
@@ -594,7 +593,6 @@ int pb_broadphase(pb_ctx* ctx) {
     int rc = pb_build_tree(ctx, true);
     if (rc) return rc;
     const int* ids = ctx->treeLeafIds;
-    ctx->stepTree = true;
     ++ctx->launches, k_lbvh_pairs<<<pb_grid(n, 32 * PAIRS_WARPS), 32 * PAIRS_WARPS, 0, ctx->stream>>>(n, ids, ctx->colInfo, ctx->aabbMin, ctx->aabbMax,
                                                             ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs,
                                                             ctx->bigListMode ? ctx->bigList : nullptr);

@@ -173,7 +173,7 @@ int pb_set_islands(pb_ctx* ctx, int mode) {
     return PB_OK;
 }
 int pb_get_island_stats(pb_ctx* ctx, int* out3) {
-    out3[0] = ctx->islandsOn ? 1 : (ctx->blocksOn ? 2 : 0); out3[1] = ctx->blocksOn ? ctx->lastBlockLocal : ctx->lastIslandLocal; out3[2] = ctx->blocksOn ? ctx->lastBlockTotal : ctx->lastIslandTotal;
+    out3[0] = ctx->islandsOn ? 1 : 0; out3[1] = ctx->lastIslandLocal; out3[2] = ctx->lastIslandTotal;
     return PB_OK;
 }
 int pb_set_deterministic(pb_ctx* ctx, int on) { ctx->deterministic = on != 0; return PB_OK; }
@@ -236,7 +236,6 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
 #undef A
     if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * (CNT_TOTAL + 4)) != cudaSuccess) rc = PB_ECUDA;
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
-    if (const char* e = getenv("PB_BLOCKS")) ctx->blocksMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
     if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
     if (const char* e = getenv("PB_SORT_COOP")) ctx->sortCoopMode = atoi(e);
@@ -328,7 +327,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
-    F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(colorMask2); F(rowMark); F(stage);
+    F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colInfo); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
     F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
@@ -671,20 +670,13 @@ static int readCounters(pb_ctx* ctx) {
 
 // Local (per-CTA) sweeps pay off when a worthwhile share of the constraints sits in small islands; finding the islands costs a few
 // kernels per step, so in auto mode a scene that turned out to be one big pile is only looked at again every 64 steps.
-static void chooseIslandsOnly(pb_ctx* ctx) {
+static void chooseIslands(pb_ctx* ctx) {
     const bool wasOn = ctx->islandsOn;
     if (ctx->islandsMode == 0) { ctx->islandsOn = false; return; }
     if (ctx->islandsMode == 1) { ctx->islandsOn = true; return; }
     if (wasOn && ctx->lastIslandTotal > 0 && 2ll * ctx->lastIslandLocal < ctx->lastIslandTotal) { ctx->islandsOn = false; ctx->islandsHold = 63; return; }
     if (!wasOn && ctx->islandsHold > 0) { --ctx->islandsHold; return; }
     ctx->islandsOn = true;
-}
-// ... and a pile that is one island is cut into spatial blocks instead (contacts.cu): needs this step's Morton order, pays off from
-// a few bodies per block upward.  (pb_contact_build drops the request when the step cannot serve it.)
-static void chooseIslands(pb_ctx* ctx) {
-    chooseIslandsOnly(ctx);
-    ctx->blocksOn = !ctx->islandsOn && ctx->stepTree && !ctx->deterministic &&
-                    (ctx->blocksMode == 1 || (ctx->blocksMode == 2 && ctx->nDyn >= 16384));
 }
 
 // The outcome of the last enqueued pb_step.  pb_step never waits for the device: the arena checks run there (a step whose
@@ -698,8 +690,7 @@ int pb_collect_step(pb_ctx* ctx) {
     PB_CUDA(ctx, cudaEventSynchronize(ctx->evCounters));
     const int* h = ctx->hCounters;
     const int nPairs = h[CNT_PAIRS], nRaw = h[CNT_RAWM], status = h[CNT_STATUS], cause = h[CNT_CAUSE];
-    if (ctx->statsCopied && ctx->statsKind == 1) { ctx->lastIslandLocal = h[CNT_TOTAL]; ctx->lastIslandTotal = h[CNT_TOTAL + 1]; }    // of the step before (rode along)
-    if (ctx->statsCopied && ctx->statsKind == 2) { ctx->lastBlockLocal = h[CNT_TOTAL]; ctx->lastBlockTotal = h[CNT_TOTAL + 1]; }
+    if (ctx->statsCopied) { ctx->lastIslandLocal = h[CNT_TOTAL]; ctx->lastIslandTotal = h[CNT_TOTAL + 1]; }    // of the step before (rode along)
     ctx->lastCounts = pb_counts{};
     ctx->lastCounts.n_pairs = nPairs;
     ctx->lastCounts.n_mesh_pairs = h[CNT_MESH_PAIRS];
@@ -767,8 +758,7 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     // counters of the narrowphase (pairs, raw manifolds, status, triggers) to pinned memory; the island statistics of the PREVIOUS
     // step ride along.  Nobody waits here: pb_collect_step looks at them later.
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters, sizeof(int) * CNT_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->statsKind = ctx->islandStats ? (ctx->islandsOn ? 1 : (ctx->blocksOn ? 2 : 0)) : 0;      // whose statistics islandStats holds (the previous step's mode)
-    ctx->statsCopied = ctx->statsKind != 0;
+    ctx->statsCopied = ctx->islandsOn && ctx->islandStats;
     if (ctx->statsCopied) PB_CUDA(ctx, cudaMemcpyAsync(ctx->hCounters + CNT_TOTAL, ctx->islandStats, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaEventRecord(ctx->evCounters, ctx->stream));
     ctx->undoCacheValid = ctx->cacheValid; ctx->undoCacheBuilt = ctx->cacheBuilt; ctx->undoVelSwaps = 0;

@@ -20,8 +20,8 @@ __device__ __forceinline__ int solverIndex(int row, int nDyn, const int* __restr
 }
 
 __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counters, int maxManifolds, const int* __restrict__ colRow,
-                        int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMaskIn,
-                        unsigned int* __restrict__ sortKey, const int* __restrict__ bodyGroup, unsigned long long* __restrict__ colorMaskAcross) {
+                        int nDyn, const int* __restrict__ kinematic, unsigned long long* __restrict__ colorMask,
+                        unsigned int* __restrict__ sortKey) {
     __shared__ int hist[2 * PB_MAX_COLORS];     // [colour] all manifolds, [PB_MAX_COLORS + colour] the single-point ones
     if (threadIdx.x < 2 * PB_MAX_COLORS) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -36,9 +36,6 @@ __global__ void k_color(const int4* __restrict__ mKey, int* __restrict__ counter
             if (lo < 0) { lo = hi; hi = -1; }
             if (lo < 0) color = 0;
             else {
-                // spatial blocks (bodyGroup given): manifolds inside a block and manifolds across blocks are swept in separate phases
-                // (the block's CTA / the device-wide colours), so each kind is coloured on its own colour set
-                unsigned long long* colorMask = (bodyGroup && hi >= 0 && bodyGroup[lo] != bodyGroup[hi]) ? colorMaskAcross : colorMaskIn;
                 while (true) {
                     unsigned long long m0 = *((volatile unsigned long long*)&colorMask[lo]);
                     unsigned long long m1 = hi >= 0 ? *((volatile unsigned long long*)&colorMask[hi]) : 0ull;
@@ -207,36 +204,18 @@ __global__ void k_color_starts(int* counters, int* __restrict__ keyStartG) {
     }
 }
 
-// Spatial blocks: the group of a solver body = the block (run of n / G consecutive Morton-sorted colliders) of its first collider in
-// sorted order.  bodyGroup is preset to 0x7f7f7f7f; a body without colliders keeps that and is never looked up (no manifolds).
-__global__ void k_block_labels(int n, const int* __restrict__ leafId, const int* __restrict__ colRow, int nDyn, const int* __restrict__ kinematic,
-                               int G, int* __restrict__ bodyGroup) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int b = solverIndex(colRow[leafId[i]], nDyn, kinematic);
-    if (b >= 0) atomicMin(&bodyGroup[b], (int)min((long long)G - 1, (long long)i * G / n));
-}
-// blocks: stats[0] = manifolds swept inside a block, stats[1] = all manifolds (what the island search reports for islands)
-__global__ void k_block_stats(const int* __restrict__ keyStart, int G, int* __restrict__ stats) {
-    stats[0] = keyStart[G * PB_KEY_COLORS] - keyStart[0];
-    stats[1] = keyStart[(G + 1) * PB_KEY_COLORS] - keyStart[0];
-}
-
-// islands / blocks on: solve-order key = group * 128 + colour * 2 + multi; histogram of the keys (scanned into the run table).
-// blocks != 0: a manifold whose two dynamic bodies lie in different blocks belongs to the device-wide group G.
+// islands on: solve-order key = group * 128 + colour * 2 + multi; histogram of the keys (scanned into the run table)
 __global__ void k_island_keys(const int* __restrict__ counters, int maxManifolds, const int4* __restrict__ mKey, const int* __restrict__ colRow,
                               int nDyn, const int* __restrict__ kinematic, const int* __restrict__ bodyGroup, int G,
-                              unsigned int* __restrict__ sortKey, int* __restrict__ keyHist, int blocks) {
+                              unsigned int* __restrict__ sortKey, int* __restrict__ keyHist) {
     int n = min(counters[CNT_RAWM], maxManifolds);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned int k = sortKey[i];
         if (k >= PB_KEY_COLORS) { sortKey[i] = 0xFFFFFFFFu; continue; }      // discarded (no points): sorts behind every group
         int4 key = mKey[i];
         int b = solverIndex(colRow[key.x], nDyn, kinematic);
-        const int b1 = solverIndex(colRow[key.y], nDyn, kinematic);
-        if (b < 0) b = b1;
+        if (b < 0) b = solverIndex(colRow[key.y], nDyn, kinematic);
         int g = b >= 0 ? bodyGroup[b] : G;
-        if (blocks && b >= 0 && b1 >= 0 && bodyGroup[b1] != g) g = G;
         unsigned int full = (unsigned int)g * PB_KEY_COLORS + k;
         sortKey[i] = full;
         atomicAdd(&keyHist[full], 1);
@@ -424,7 +403,6 @@ int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
 // ctx->rawHint (the previous step's count, a guess that only shapes grids) or the arena capacity.  When the narrowphase overflowed an
 // arena (CNT_STATUS), the kernels still run over the clamped counts -- everything they write is per-step scratch or the "current"
 // half of a double buffer that the host flips back when it collects the step's status (capi.cu collectStep).
-int pb_islands_alloc(pb_ctx* ctx);
 int pb_contact_build(pb_ctx* ctx) {
     const int blocks = pb_hint_grid(ctx->rawHint, 256, ctx->numSMs * 8);
     int maxM = ctx->caps.max_manifolds;
@@ -432,16 +410,6 @@ int pb_contact_build(pb_ctx* ctx) {
     int rc;
     cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
     PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
-    // spatial blocks: labels first -- the colouring separates the manifolds inside a block from the ones across blocks
-    const bool blocksOn = ctx->blocksOn && !ctx->islandsOn && ctx->stepTree && !ctx->deterministic && ctx->nDyn > 0;
-    ctx->blocksOn = blocksOn;
-    if (blocksOn) {
-        if (!ctx->colorMask2 && (rc = pb_alloc(ctx, &ctx->colorMask2, (size_t)ctx->caps.max_bodies))) return rc;
-        if ((rc = pb_islands_alloc(ctx))) return rc;
-        cudaMemsetAsync(ctx->colorMask2, 0, sizeof(unsigned long long) * (size_t)ctx->nDyn, ctx->stream);
-        cudaMemsetAsync(ctx->bodyGroup, 0x7f, sizeof(int) * (size_t)ctx->nDyn, ctx->stream);
-        ++ctx->launches, k_block_labels<<<pb_grid(ctx->nCol, 256), 256, 0, ctx->stream>>>(ctx->nCol, ctx->treeLeafIds, ctx->colRow, ctx->nDyn, ctx->kinematic, G, ctx->bodyGroup);
-    }
     if (ctx->deterministic) {
         if (!ctx->jpBest) {
             if ((rc = pb_alloc(ctx, &ctx->jpBest, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->jpScratch, 64))) return rc;
@@ -458,7 +426,7 @@ int pb_contact_build(pb_ctx* ctx) {
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_color_jp, dim3(ctx->jpGrid), dim3(256), args, 0, ctx->stream));
     } else
     ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
-                                             ctx->mSortKeyA, blocksOn ? ctx->bodyGroup : nullptr, ctx->colorMask2);
+                                             ctx->mSortKeyA);
     ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->keyStart + (size_t)G * PB_KEY_COLORS);
     if (ctx->islandsOn) {
         if ((rc = pb_islands_build(ctx))) return rc;
@@ -469,16 +437,12 @@ int pb_contact_build(pb_ctx* ctx) {
     // The order inside a run is arrival order: a run's manifolds share no dynamic body (the overflow bucket is solved in slot order,
     // whatever that is), and the taps report the order that was used.  (This replaced a stable radix sort: 2 passes, ~0.13 ms at 2 M manifolds.)
     unsigned int keyBase = 0, keyLimit = PB_KEY_COLORS;
-    if (ctx->islandsOn || blocksOn) {
+    if (ctx->islandsOn) {
         // group-major order: every local group's manifolds are contiguous (colour by colour inside), the global group comes last
         PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
         ++ctx->launches, k_island_keys<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mKey, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->bodyGroup, G,
-                                                                       ctx->mSortKeyA, ctx->keyStart, blocksOn ? 1 : 0);
+                                                                       ctx->mSortKeyA, ctx->keyStart);
         if ((rc = pb_exclusive_scan(ctx, ctx->keyStart, ctx->keyStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
-        if (blocksOn) {
-            PB_CUDA(ctx, cudaMemsetAsync(ctx->islandStats, 0, sizeof(int) * 4, ctx->stream));
-            ++ctx->launches, k_block_stats<<<1, 1, 0, ctx->stream>>>(ctx->keyStart, G, ctx->islandStats);
-        }
         keyLimit = (unsigned int)nKeys;
     } else {
         keyBase = (unsigned int)G * PB_KEY_COLORS;     // plain colour-major order: the run table of group G (k_color_starts)

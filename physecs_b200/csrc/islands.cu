@@ -207,19 +207,14 @@ __global__ void __launch_bounds__(256) k_island_stats(int n, const int* __restri
     }
 }
 
-int pb_islands_alloc(pb_ctx* ctx) {
+int pb_islands_build(pb_ctx* ctx) {
+    const int n = ctx->nDyn;
+    if (n <= 0) return PB_OK;
     if (!ctx->islandParent) {
         int rc;
         if ((rc = pb_alloc(ctx, &ctx->islandParent, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandCount, (size_t)ctx->caps.max_bodies)) ||
             (rc = pb_alloc(ctx, &ctx->bodyGroup, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandStats, 4))) return rc;
     }
-    return PB_OK;
-}
-
-int pb_islands_build(pb_ctx* ctx) {
-    const int n = ctx->nDyn;
-    if (n <= 0) return PB_OK;
-    { int rc = pb_islands_alloc(ctx); if (rc) return rc; }
     const int blocks = ctx->numSMs * 8;
     const int G = ctx->islandGroups;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->islandStats, 0, sizeof(int) * 4, ctx->stream));

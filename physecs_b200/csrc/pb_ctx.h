@@ -211,13 +211,6 @@ struct pb_ctx {
     int islandsMode = 2;             // 0 off, 1 on, 2 auto (on while a worthwhile share of the constraints sits in small islands)
     int islandLocalMax = PB_ISLAND_LOCAL_MAX;   // env PB_ISLAND_LOCAL_MAX overrides (tests: force a mix of local and device-wide sweeps)
     bool islandsOn = false;          // this step
-    // Spatial blocks (contacts.cu k_block_labels): when the scene is one big pile (islands off) and the step sorted its colliders by
-    // Morton key, group g = the g-th run of n / G consecutive sorted colliders.  A manifold whose dynamic bodies lie in one block is
-    // swept by that block's CTA with CTA barriers, the ones across blocks go through the device-wide colours (own colour set).
-    bool blocksOn = false; int blocksMode = 2;      // env PB_BLOCKS: 0 never, 1 whenever the step built the tree, 2 auto (islands off + tree + >= 16384 bodies)
-    int statsKind = 0; int lastBlockLocal = 0, lastBlockTotal = 0;      // statistics riding along with the counters: 1 islands, 2 blocks (manifolds inside a block / all)
-    bool stepTree = false;           // this step's broadphase sorted the colliders (ctx->treeLeafIds is this step's order)
-    unsigned long long* colorMask2 = nullptr;       // [dyn] colours in use per body among the manifolds ACROSS blocks
     int islandsHold = 0;             // auto: steps left before small islands are looked for again
     int lastIslandLocal = 0, lastIslandTotal = 0;   // constraints in small islands / in all islands, last step that looked
     int* keyStart = nullptr;         // [(G + 1) * PB_KEY_COLORS + 1] first solve slot of every (group, colour, single | multi) run

@@ -159,3 +159,29 @@ def test_three_gates_cluster_barrier(maker, steps, cluster, monkeypatch):
     monkeypatch.setenv("PB_FUSED", "1")
     s = parity.run_gates(maker(), steps=steps)
     assert s["steps"] == steps and s["worst_manifold"] <= parity.TOL
+
+
+@pytest.mark.parametrize("islands", ["auto", "0"])
+def test_three_gates_through_landing(islands, monkeypatch):
+    """20 000 bodies dropped into a walled bin, gated from the first step on: the scene goes from no contacts through a field of small
+    islands (per-CTA sweeps) to a mix of small and big islands (both sweeps in one step) while manifold counts grow ten-fold -- every
+    size rule (launch shapes from the previous step's counts, scan forms, whole-step kernel <-> per-substep launches) flips on the way."""
+    if islands != "auto":
+        monkeypatch.setenv("PB_ISLANDS", islands)
+    d = S.mixed_bin(20000)
+    s = parity.run_gates(d, steps=72, bulk=True, check_every=6, caps=dict(max_pairs=64 * d.n + 4096, max_manifolds=16 * d.n + 4096))
+    assert s["steps"] == 72 and s["manifolds"] > 30000 and s["worst_manifold"] <= parity.TOL
+
+
+@pytest.mark.parametrize("maker", [lambda: S.mixed_bin(20000), lambda: S.mixed_bin(3000, spacing=0.8), lambda: S.mixed_bin(40000, spacing=0.9)])
+def test_free_run_bodies_stay_in_the_bin(maker):
+    """free run, no oracle: nothing falls through the floor while the pile forms (a constraint that is built but never swept shows here)"""
+    from physecs_b200.capi import Context
+    d = maker()
+    ctx = Context(d, max_pairs=64 * d.n + 4096, max_manifolds=16 * d.n + 4096)
+    for k in range(150):
+        ctx.step()
+        if k % 30 == 29:
+            P = ctx.get_state()[0]
+            assert np.isfinite(P).all() and P[:, 1].min() > -0.25, (k, float(P[:, 1].min()))
+    ctx.close()
