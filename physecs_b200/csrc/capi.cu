@@ -404,6 +404,7 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
     const std::vector<int>& kin = ctx->hKinematic;
     std::vector<int> f(n);
     std::vector<float> mat4((size_t)4 * n);
+    bool anyRest = false;      // restitution of a pair = mean of the two colliders' (contacts.cu k_contact_build): zero everywhere -> the contact cache is idle
     bool trig = false;
     for (int i = 0; i < n; ++i) {
         int row = bodyRow[i];
@@ -414,6 +415,7 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
         if (type[i] == PB_TRIANGLE_MESH && (mesh[i] < 0 || mesh[i] >= (int)ctx->triMeshes.size())) return pb_fail(ctx, PB_EINVAL, "bad trimesh handle");
         if (type[i] == PB_CONVEX_MESH && (mesh[i] < 0 || mesh[i] >= (int)ctx->convexes.size())) return pb_fail(ctx, PB_EINVAL, "bad convex handle");
         mat4[4 * i] = material3[3 * i]; mat4[4 * i + 1] = material3[3 * i + 1]; mat4[4 * i + 2] = material3[3 * i + 2]; mat4[4 * i + 3] = 0.f;
+        if (material3[3 * i + 1] != 0.f) anyRest = true;
     }
     ctx->anyTriggerFlag = trig;
     if (!ctx->filterLut) ctx->triggersPossible = trig;
@@ -428,6 +430,7 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
     if ((rc = uploadVec(ctx, lquat4, n, 4, ctx->colLQuat))) return rc;
     if ((rc = uploadVec(ctx, params4, n, 4, ctx->colParams))) return rc;
     if ((rc = uploadVec(ctx, mat4.data(), n, 4, ctx->colMat))) return rc;
+    ctx->anyRestitution = anyRest;
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     // creation-time bounds: no margin (Physecs.cpp:32)
     if ((rc = pb_update_bounds_all(ctx, 0.f, 0))) return rc;
@@ -770,8 +773,8 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     if ((rc = pb_contact_build(ctx))) return rc;
     cudaEventRecord(ctx->ev[3], ctx->stream);
     if ((rc = pb_solve(ctx, dt, substeps, iterations, gravity))) return rc;
-    ctx->cacheValid = true;
-    ctx->cacheBuilt = true;
+    ctx->cacheValid = ctx->anyRestitution;      // (a scene without restitution leaves the cache tables alone: nothing valid to look up next step)
+    ctx->cacheBuilt = ctx->anyRestitution;
     // bounds of every non-kinematic dynamic body for the next step, +0.01 margin (Physecs.cpp:556-559)
     if ((rc = pb_update_bounds_all(ctx, 0.01f, 1, ctx->counters + CNT_STATUS))) return rc;
     cudaEventRecord(ctx->ev[4], ctx->stream);

@@ -222,9 +222,19 @@ __global__ void k_island_keys(const int* __restrict__ counters, int maxManifolds
     }
 }
 
+// Every small table a step's build zeroes, in ONE launch (they were a dozen memsets / copies of a few microseconds each, a tenth of the
+// step of a 512-scene batch): up to 8 (pointer, word count) ranges.
+struct ClearList { int* p[8]; int n[8]; };
+__global__ void __launch_bounds__(256) k_build_clear(ClearList L) {
+    for (int k = 0; k < 8; ++k) {
+        int* p = L.p[k]; const int n = L.n[k];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
+    }
+}
+
 // counting-sort scatter: sortKey[i] (< keyLimit; anything else is a discarded manifold) + keyBase indexes the run cursors
 __global__ void __launch_bounds__(256) k_scatter_by_key(const int* __restrict__ counters, int maxManifolds, const unsigned int* __restrict__ sortKey,
-                                                        unsigned int keyBase, unsigned int keyLimit, int* __restrict__ cursor,
+                                                        unsigned int keyBase, unsigned int keyLimit, const int* __restrict__ runStart, int* __restrict__ fill,
                                                         int* __restrict__ outRaw, unsigned int* __restrict__ outKey) {
     const int n = min(counters[CNT_RAWM], maxManifolds);
     const int lane = threadIdx.x & 31;
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(256) k_scatter_by_key(const int* __restrict__ 
             const unsigned int peers = __match_any_sync(act, k);
             const int leader = __ffs(peers) - 1;
             int slot = 0;
-            if (lane == leader) slot = atomicAdd(&cursor[keyBase + k], __popc(peers));
+            if (lane == leader) slot = runStart[keyBase + k] + atomicAdd(&fill[keyBase + k], __popc(peers));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
             outRaw[slot] = i;
             outKey[slot] = k;
@@ -403,13 +413,34 @@ int pb_contact_cache_remap(pb_ctx* ctx, int nOld, const int* dOldToNew) {
 // ctx->rawHint (the previous step's count, a guess that only shapes grids) or the arena capacity.  When the narrowphase overflowed an
 // arena (CNT_STATUS), the kernels still run over the clamped counts -- everything they write is per-step scratch or the "current"
 // half of a double buffer that the host flips back when it collects the step's status (capi.cu collectStep).
+int pb_islands_alloc(pb_ctx* ctx);
+int pb_joint_lists_alloc(pb_ctx* ctx);
 int pb_contact_build(pb_ctx* ctx) {
     const int blocks = pb_hint_grid(ctx->rawHint, 256, ctx->numSMs * 8);
     int maxM = ctx->caps.max_manifolds;
     const int G = ctx->islandGroups, nKeys = (G + 1) * PB_KEY_COLORS;
     int rc;
-    cudaMemsetAsync(ctx->colorMask, 0, sizeof(unsigned long long) * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1), ctx->stream);
-    PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
+    // one launch zeroes the colour sets, the run-fill counters and (islands on) the key histogram, the island statistics, the body and
+    // joint list tables.  Islands off: the run table of group G is written whole by k_color_starts, nothing to clear.
+    {
+        ClearList L{};
+        int k = 0;
+        auto add = [&](void* p, size_t words) { if (p && words) { L.p[k] = (int*)p; L.n[k] = (int)words; ++k; } };
+        add(ctx->colorMask, 2 * (size_t)(ctx->nDyn > 0 ? ctx->nDyn : 1));
+        add(ctx->keyCursor, (size_t)nKeys + 1);
+        if (ctx->islandsOn) {
+            if ((rc = pb_islands_alloc(ctx))) return rc;
+            add(ctx->keyStart, (size_t)nKeys + 1);
+            add(ctx->islandStats, 4);
+            add(ctx->bodyStart, ctx->bodyStart ? (size_t)G + 2 : 0);
+            add(ctx->bodyCursor, ctx->bodyCursor ? (size_t)G + 2 : 0);
+            if (ctx->nJoints && (rc = pb_joint_lists_alloc(ctx))) return rc;
+            if (ctx->nJoints) { add(ctx->jointStart, (size_t)G * 8 + 10); add(ctx->jointSortTmp[0], (size_t)G * 8 + 10); }
+        }
+        size_t most = 0;
+        for (int i = 0; i < k; ++i) most = std::max(most, (size_t)L.n[i]);
+        ++ctx->launches, k_build_clear<<<std::max(1, std::min(ctx->numSMs * 4, (int)((most + 1023) / 1024))), 256, 0, ctx->stream>>>(L);
+    }
     if (ctx->deterministic) {
         if (!ctx->jpBest) {
             if ((rc = pb_alloc(ctx, &ctx->jpBest, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->jpScratch, 64))) return rc;
@@ -427,7 +458,7 @@ int pb_contact_build(pb_ctx* ctx) {
     } else
     ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
                                              ctx->mSortKeyA);
-    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->keyStart + (size_t)G * PB_KEY_COLORS);
+    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->islandsOn ? nullptr : ctx->keyStart + (size_t)G * PB_KEY_COLORS);
     if (ctx->islandsOn) {
         if ((rc = pb_islands_build(ctx))) return rc;
         if ((rc = pb_joint_lists(ctx))) return rc;
@@ -439,7 +470,6 @@ int pb_contact_build(pb_ctx* ctx) {
     unsigned int keyBase = 0, keyLimit = PB_KEY_COLORS;
     if (ctx->islandsOn) {
         // group-major order: every local group's manifolds are contiguous (colour by colour inside), the global group comes last
-        PB_CUDA(ctx, cudaMemsetAsync(ctx->keyStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
         ++ctx->launches, k_island_keys<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mKey, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->bodyGroup, G,
                                                                        ctx->mSortKeyA, ctx->keyStart);
         if ((rc = pb_exclusive_scan(ctx, ctx->keyStart, ctx->keyStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
@@ -447,9 +477,12 @@ int pb_contact_build(pb_ctx* ctx) {
     } else {
         keyBase = (unsigned int)G * PB_KEY_COLORS;     // plain colour-major order: the run table of group G (k_color_starts)
     }
-    PB_CUDA(ctx, cudaMemcpyAsync(ctx->keyCursor, ctx->keyStart, sizeof(int) * ((size_t)nKeys + 1), cudaMemcpyDeviceToDevice, ctx->stream));
-    ++ctx->launches, k_scatter_by_key<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mSortKeyA, keyBase, keyLimit, ctx->keyCursor, ctx->mSortValB, ctx->mSortKeyB);
-    if (ctx->deterministic) ++ctx->launches, k_sort_overflow_run<<<pb_grid(G + 1, 128), 128, 0, ctx->stream>>>(G + 1, ctx->keyStart, ctx->mKey, ctx->mSortValB);
+    ++ctx->launches, k_scatter_by_key<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, maxM, ctx->mSortKeyA, keyBase, keyLimit, ctx->keyStart, ctx->keyCursor, ctx->mSortValB, ctx->mSortKeyB);
+    // (islands off: only the run table of group G is this step's)
+    if (ctx->deterministic) {
+        const int nTables = ctx->islandsOn ? G + 1 : 1;
+        ++ctx->launches, k_sort_overflow_run<<<pb_grid(nTables, 128), 128, 0, ctx->stream>>>(nTables, ctx->keyStart + (ctx->islandsOn ? 0 : (size_t)G * PB_KEY_COLORS), ctx->mKey, ctx->mSortValB);
+    }
     ctx->mSorted = ctx->mSortValB;
     ctx->mSortedKeys = ctx->mSortKeyB;
     int cur = ctx->curBuf, prev = cur ^ 1;
@@ -457,11 +490,12 @@ int pb_contact_build(pb_ctx* ctx) {
     ++ctx->launches, k_gather_np<<<blocks, 256, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->cNpBuf[cur]);
     rc = pb_exclusive_scan_dev(ctx, ctx->cNpBuf[cur], pointOfs, ctx->counters + CNT_MANIFOLDS, maxM, ctx->rawHint < 0 ? -1 : 2 * ctx->rawHint + 4096, (int*)ctx->radixHist);
     if (rc) return rc;
-    cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
+    // (the contact cache only carries restitution targets: a scene without restitution neither fills nor reads it)
+    if (ctx->anyRestitution) cudaMemsetAsync(ctx->cacheTag[cur], 0, sizeof(unsigned long long) * (size_t)ctx->cacheSize, ctx->stream);
     ++ctx->launches, k_contact_build<<<blocks, 128, 0, ctx->stream>>>(ctx->counters, ctx->mSorted, ctx->mKey, ctx->mNormal, ctx->mPts, pointOfs, ctx->colRow, ctx->colMat,
         ctx->nDyn, ctx->kinematic, ctx->pos, ctx->quat, ctx->vel, ctx->angvel, ctx->comInvMass,
         ctx->cHead, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
-        ctx->cacheValid ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],
+        (ctx->cacheValid && ctx->anyRestitution) ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],
         ctx->cacheTag[cur], ctx->cacheVal[cur], ctx->cacheSize - 1);
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_island_body_hist(int n, const int* __re
     __syncthreads();
     for (int i = threadIdx.x; i <= G; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-__global__ void __launch_bounds__(256) k_island_body_scatter(int n, const int* __restrict__ group, int* __restrict__ cursor, int* __restrict__ order) {
+__global__ void __launch_bounds__(256) k_island_body_scatter(int n, const int* __restrict__ group, const int* __restrict__ start, int* __restrict__ fill, int* __restrict__ order) {
     const int lane = threadIdx.x & 31;
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
         const int i = base + lane;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_island_body_scatter(int n, const int* _
             const unsigned int peers = __match_any_sync(act, g);
             const int leader = __ffs(peers) - 1;
             int slot = 0;
-            if (lane == leader) slot = atomicAdd(&cursor[g], __popc(peers));
+            if (lane == leader) slot = start[g] + atomicAdd(&fill[g], __popc(peers));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
             order[slot] = i;
         }
@@ -207,17 +207,28 @@ __global__ void __launch_bounds__(256) k_island_stats(int n, const int* __restri
     }
 }
 
-int pb_islands_build(pb_ctx* ctx) {
-    const int n = ctx->nDyn;
-    if (n <= 0) return PB_OK;
+// buffers of the island search; the per-group body lists exist once a scene small enough for the whole-step kernel's group-by-group form asks
+int pb_islands_alloc(pb_ctx* ctx) {
+    int rc;
     if (!ctx->islandParent) {
-        int rc;
         if ((rc = pb_alloc(ctx, &ctx->islandParent, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandCount, (size_t)ctx->caps.max_bodies)) ||
             (rc = pb_alloc(ctx, &ctx->bodyGroup, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->islandStats, 4))) return rc;
     }
+    const bool lists = ctx->nDyn <= ctx->fusedLocalMax && ctx->fusedMode != 0;
+    if (lists && !ctx->bodyOrder) {
+        const int G = ctx->islandGroups;
+        if ((rc = pb_alloc(ctx, &ctx->bodyOrder, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->bodyStart, (size_t)G + 2)) || (rc = pb_alloc(ctx, &ctx->bodyCursor, (size_t)G + 2))) return rc;
+    }
+    return PB_OK;
+}
+
+// (islandStats, bodyStart and the body fill counters arrive zeroed: contacts.cu k_build_clear)
+int pb_islands_build(pb_ctx* ctx) {
+    const int n = ctx->nDyn;
+    if (n <= 0) return PB_OK;
+    { int rc = pb_islands_alloc(ctx); if (rc) return rc; }
     const int blocks = ctx->numSMs * 8;
     const int G = ctx->islandGroups;
-    PB_CUDA(ctx, cudaMemsetAsync(ctx->islandStats, 0, sizeof(int) * 4, ctx->stream));
     ++ctx->launches, k_island_init<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, ctx->islandParent, ctx->islandCount);
     JointDev J;
     const bool joints = pb_joint_view(ctx, &J);
@@ -231,21 +242,13 @@ int pb_islands_build(pb_ctx* ctx) {
     // body lists per group for the whole-step kernel's group-by-group form (solver.cu k_step_solve_small): only scenes small enough to take it
     const bool lists = n <= ctx->fusedLocalMax && ctx->fusedMode != 0;
     ctx->bodyListsBuilt = false;
-    if (lists) {
-        if (!ctx->bodyOrder) {
-            int rc;
-            if ((rc = pb_alloc(ctx, &ctx->bodyOrder, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->bodyStart, (size_t)G + 2)) || (rc = pb_alloc(ctx, &ctx->bodyCursor, (size_t)G + 2))) return rc;
-        }
-        PB_CUDA(ctx, cudaMemsetAsync(ctx->bodyStart, 0, sizeof(int) * ((size_t)G + 2), ctx->stream));
-    }
     // bodyGroup holds the roots up to here and is converted in place (thread i reads and writes entry i only)
     ++ctx->launches, k_island_group_stats<<<pb_grid(n, 256), 256, lists ? sizeof(int) * (G + 1) : 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->islandCount, G, ctx->islandLocalMax, ctx->islandStats,
                                                                                                                  lists ? ctx->bodyStart : nullptr);
     if (lists) {
         int rc = pb_exclusive_scan(ctx, ctx->bodyStart, ctx->bodyStart, G + 2, (int*)ctx->radixHist); if (rc) return rc;
-        PB_CUDA(ctx, cudaMemcpyAsync(ctx->bodyCursor, ctx->bodyStart, sizeof(int) * ((size_t)G + 2), cudaMemcpyDeviceToDevice, ctx->stream));
         const int hb = std::min(pb_grid(n, 256), ctx->numSMs * 4);
-        ++ctx->launches, k_island_body_scatter<<<hb, 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->bodyCursor, ctx->bodyOrder);
+        ++ctx->launches, k_island_body_scatter<<<hb, 256, 0, ctx->stream>>>(n, ctx->bodyGroup, ctx->bodyStart, ctx->bodyCursor, ctx->bodyOrder);
         ctx->bodyListsBuilt = true;
     }
     PB_CUDA(ctx, cudaGetLastError());

@@ -185,13 +185,14 @@ __global__ void k_joint_keys(int nJ, const int2* __restrict__ bodies, const int*
 // placed by a counting sort: the run table (scanned key histogram) gives every (group, colour) run its first slot, a joint takes run
 // start + arrival rank.  The order inside a run is immaterial: joints of one colour share no body (Physecs.cpp:690-710), and the
 // sequential overflow bucket is not listed here (the solver walks its static range in creation order).
-__global__ void k_joint_scatter(int nJ, const unsigned int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ order) {
+__global__ void k_joint_scatter(int nJ, const unsigned int* __restrict__ key, const int* __restrict__ start, int* __restrict__ fill, int* __restrict__ order) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nJ) return;
-    order[atomicAdd(&cursor[key[j]], 1)] = j;
+    const unsigned int k = key[j];
+    order[start[k] + atomicAdd(&fill[k], 1)] = j;
 }
 
-int pb_joint_lists(pb_ctx* ctx) {
+int pb_joint_lists_alloc(pb_ctx* ctx) {
     JointStore* s = store(ctx);
     if (!s || !ctx->nJoints) return PB_OK;
     const int n = s->n, G = ctx->islandGroups, nKeys = G * 8 + 9;
@@ -201,14 +202,21 @@ int pb_joint_lists(pb_ctx* ctx) {
             (rc = pb_alloc(ctx, &ctx->jointStart, (size_t)nKeys + 1))) return rc;
         ctx->jointListCap = n;
     }
+    return PB_OK;
+}
+
+// (jointStart and the fill counters jointSortTmp[0] arrive zeroed: contacts.cu k_build_clear)
+int pb_joint_lists(pb_ctx* ctx) {
+    JointStore* s = store(ctx);
+    if (!s || !ctx->nJoints) return PB_OK;
+    const int n = s->n, G = ctx->islandGroups, nKeys = G * 8 + 9;
+    int rc;
+    if ((rc = pb_joint_lists_alloc(ctx))) return rc;
     JointColorStarts cs;
     for (int c = 0; c <= PB_JOINT_COLORS; ++c) cs.s[c] = ctx->jointColorStart[c];
-    PB_CUDA(ctx, cudaMemsetAsync(ctx->jointStart, 0, sizeof(int) * ((size_t)nKeys + 1), ctx->stream));
     ++ctx->launches, k_joint_keys<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, s->bodies, ctx->bodyGroup, G, cs, (unsigned int*)ctx->jointKey, ctx->jointStart);
     if ((rc = pb_exclusive_scan(ctx, ctx->jointStart, ctx->jointStart, nKeys + 1, (int*)ctx->radixHist))) return rc;
-    int* cursor = ctx->jointSortTmp[0];
-    PB_CUDA(ctx, cudaMemcpyAsync(cursor, ctx->jointStart, sizeof(int) * ((size_t)nKeys + 1), cudaMemcpyDeviceToDevice, ctx->stream));
-    ++ctx->launches, k_joint_scatter<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const unsigned int*)ctx->jointKey, cursor, ctx->jointSortTmp[1]);
+    ++ctx->launches, k_joint_scatter<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const unsigned int*)ctx->jointKey, ctx->jointStart, ctx->jointSortTmp[0], ctx->jointSortTmp[1]);
     ctx->jointOrder = ctx->jointSortTmp[1];
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;

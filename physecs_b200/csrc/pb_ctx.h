@@ -199,6 +199,7 @@ struct pb_ctx {
     // contact filter (Physecs.cpp:200): optional K x K table over (isTrigger, data) classes; nullptr = defaultContactFilter
     int* colClass = nullptr; unsigned char* filterLut = nullptr; int nFilterClasses = 0;
     bool anyTriggerFlag = false, triggersPossible = false;
+    bool anyRestitution = true;      // some collider has restitution != 0: only then does the contact cache (restitution targets of persisting contacts) do anything
     int2* trigPairs = nullptr;       // [maxPairs] overlapping TRIGGER pairs of the last step (collider indices)
     // simulation islands (islands.cu): group of every solver body; local groups 0..islandGroups-1 (one CTA each), group islandGroups = global
     int* islandParent = nullptr; int* islandCount = nullptr; int* bodyGroup = nullptr; int* islandStats = nullptr;
@@ -214,7 +215,7 @@ struct pb_ctx {
     int islandsHold = 0;             // auto: steps left before small islands are looked for again
     int lastIslandLocal = 0, lastIslandTotal = 0;   // constraints in small islands / in all islands, last step that looked
     int* keyStart = nullptr;         // [(G + 1) * PB_KEY_COLORS + 1] first solve slot of every (group, colour, single | multi) run
-    int* keyCursor = nullptr;              // [(G+1)*128+1] running copy of keyStart for the counting-sort scatter (contacts.cu)
+    int* keyCursor = nullptr;              // [(G+1)*128+1] fill counters of the runs for the counting-sort scatter (contacts.cu; zeroed by k_build_clear)
     unsigned int* mSortedKeys = nullptr;   // solve-order keys of the last step (taps: colour of a slot)
     // per-group joint lists of the step (joints.cu): jointOrder = joints sorted by (group, colour), jointStart[g * 8 + c] their runs (g = G: the global group, colours 0..8)
     int* jointKey = nullptr; int* jointOrder = nullptr; int* jointStart = nullptr; int* jointSortTmp[3] = {nullptr, nullptr, nullptr}; int jointListCap = 0;
