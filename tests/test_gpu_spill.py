@@ -99,3 +99,29 @@ def test_soak(name, maker, steps, seed):
         ctx.close()
     assert not cause & FATAL_CAUSES, hex(cause)
     print(name, hex(seed), "cause", hex(cause), "max spilled pairs per step", spilled)
+
+
+def test_soak_terrain_1m():
+    """The headline configuration for 400 steps from the drop: every status OK, state finite, nobody under the terrain (heights within
+    +-2.3; bodies that start near the rim of the finite mesh may roll off and fall, so the inner ones are looked at)."""
+    from physecs_b200.capi import Context
+    d = S.terrain(1_000_000, drop=0.3)
+    ctx = Context(d, max_pairs=8 * d.n + 4096, max_manifolds=6 * d.n + 4096)
+    start = d.pos[np.asarray(ctx.dyn_entities)]
+    inner = (np.abs(start[:, 0]) < 400) & (np.abs(start[:, 2]) < 400)
+    assert inner.sum() > 500_000
+    cause = 0
+    try:
+        for k in range(400):
+            ctx.step()
+            if k % 50 == 49:
+                c = ctx.counts()
+                cause |= int(c.cause)
+                assert c.status == 0
+                P = ctx.get_state()[0]
+                assert np.isfinite(P).all() and P[inner, 1].min() > -3.5, (k, float(P[inner, 1].min()), int((P[:, 1] < -3.5).sum()))
+        c = ctx.counts()
+        assert c.n_manifolds > 1_500_000
+    finally:
+        ctx.close()
+    assert not cause & FATAL_CAUSES, hex(cause)
