@@ -530,7 +530,54 @@ def main():
             raise RuntimeError(lib.pb_last_error(ctx.ctx).decode())
         e2e_ms.append((time.perf_counter() - ts) * 1e3)
     torch.cuda.synchronize(); barrier()
+    serial_s = max_over_ranks(time.perf_counter() - t0)
+    serial_ms = list(e2e_ms)
+    # The same round trip -- every step's inputs ARE the previous step's results, all of them over the bus both ways -- with the
+    # transfers placed beside the device's work: the result is read back on the read stream, poses first (pb_get_state_begin), the next
+    # step's broadphase is enqueued at once (pb_step_begin: it runs on the bounds the step left behind, not on the new poses), the
+    # poses go back up as soon as they have arrived and the narrowphase behind them (pb_step_narrowphase), the velocities follow
+    # while it runs, pb_step continues with the contact build.  (Measured with 1 / 2 / 3 / 8 / 16 chunks: 4.87 / 5.1 / 5.0 / 5.4 / 6.1
+    # ms -- the per-call latencies of a chunk outweigh what finer overlap of the two directions gains.)
+    CH = 1
+    first_c = C.c_int(); count_c = C.c_int()
+    lib.pb_get_state(ctx.ctx, fp(pos), fp(quat), fp(vel), fp(ang))
+    lib.pb_set_readback_order(ctx.ctx, 1)          # poses of every chunk before the velocities: the narrowphase waits for poses only
+    NULLF = C.POINTER(C.c_float)()
+    barrier(); torch.cuda.synchronize()
+    e2e_ms = []
+    t0 = time.perf_counter()
+    rc = lib.pb_step_begin(ctx.ctx)
+    for k in range(e2e_steps):
+        ts = time.perf_counter()
+        for half in (0, 1):            # poses up first, velocities behind them
+            for c in range(CH if k > 0 else 1):
+                if k > 0:
+                    rc |= (lib.pb_get_state_wait if half else lib.pb_get_state_wait_poses)(ctx.ctx, c, C.byref(first_c), C.byref(count_c))
+                    f0, cnt = first_c.value, count_c.value
+                else:
+                    f0, cnt = 0, n_dyn
+                if cnt:
+                    off = lambda a, w: C.cast(C.c_void_p(a.ctypes.data + 4 * w * f0), C.POINTER(C.c_float))
+                    if half == 0:
+                        rc |= lib.pb_set_state_rows(ctx.ctx, f0, cnt, off(pos, 3), off(quat, 4), NULLF, NULLF)
+                    else:
+                        rc |= lib.pb_set_state_rows(ctx.ctx, f0, cnt, NULLF, NULLF, off(vel, 3), off(ang, 3))
+            if half == 0:
+                rc |= lib.pb_step_narrowphase(ctx.ctx)      # needs the poses only: runs while the velocities come back up
+        rc |= lib.pb_step(ctx.ctx, C.c_float(desc.dt), desc.substeps, desc.iterations, C.c_float(desc.gravity))
+        rc |= lib.pb_get_state_begin(ctx.ctx, fp(pos), fp(quat), fp(vel), fp(ang), CH)
+        if k + 1 < e2e_steps:
+            rc |= lib.pb_step_begin(ctx.ctx)
+        if rc:
+            raise RuntimeError(lib.pb_last_error(ctx.ctx).decode())
+        e2e_ms.append((time.perf_counter() - ts) * 1e3)
+    for c in range(CH):
+        rc |= lib.pb_get_state_wait(ctx.ctx, c, C.byref(first_c), C.byref(count_c))
+    if rc:
+        raise RuntimeError(lib.pb_last_error(ctx.ctx).decode())
+    torch.cuda.synchronize(); barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    lib.pb_set_readback_order(ctx.ctx, 0)
     e2e_value = world * n_dyn * e2e_steps / e2e_s
     bytes_io = 13 * 4 * n_dyn
     checksum = float(np.abs(pos).sum())
@@ -544,7 +591,11 @@ def main():
                    "avg_pairs": avgPairs, "avg_manifolds": avgM, "avg_points": avgP, "avg_colors": avgC},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "p95_ms_per_step": float(np.percentile(e2e_ms, 95)), "checksum": checksum},
+                "p95_ms_per_step": float(np.percentile(e2e_ms[1:] or e2e_ms, 95)), "checksum": checksum,
+                "calls": "per step: pb_get_state_wait_poses / _wait + pb_set_state_rows for each of %d chunks (the previous step's result goes back up as it arrives, poses first), pb_step_narrowphase between poses and velocities, pb_step, "
+                         "pb_get_state_begin, pb_step_begin (the next broadphase beside the read-back); pinned host buffers, every body both ways every step" % CH,
+                "serial": {"ms_per_step": serial_s / e2e_steps * 1e3, "p95_ms_per_step": float(np.percentile(serial_ms, 95)), "value": world * n_dyn * e2e_steps / serial_s,
+                           "calls": "pb_set_state, pb_step, pb_get_state one after the other (round 1's loop)"}},
         "gpu_launches": int(launches),
         "pcie": pcie_probe(),
         "roofline": roofline,

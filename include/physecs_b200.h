@@ -185,14 +185,30 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
  * step's transforms.  Call it first, then gather and upload the new state (pb_set_state / pb_set_state_rows) while the broadphase
  * runs, then pb_step, which continues behind it.  Calling pb_step alone is equivalent. */
 int pb_step_begin(pb_ctx* ctx);
+/* Optional middle of a step: world poses + narrowphase (behind pb_step_begin's broadphase; calls it if it was not).  They read the
+ * new poses but no velocity, so a caller uploads the poses, calls this, uploads the velocities while the narrowphase runs, and then
+ * calls pb_step, which continues with the contact build.  Between this call and pb_step only velocity uploads (pb_set_state /
+ * pb_set_state_rows with null pose pointers) and read-back calls are allowed: scene edits return PB_EINVAL. */
+int pb_step_narrowphase(pb_ctx* ctx);
 /* waits for the narrowphase of the last pb_step (not for the whole step) and returns its status; PB_OK when nothing is pending */
 int pb_collect_step(pb_ctx* ctx);
 int pb_get_state(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3);
 /* pb_get_state in up to 32 chunks of rows: _begin enqueues the copies (asynchronous; reports a failed step like pb_get_state),
  * _wait blocks until chunk `chunk` has arrived and names its row range -- the host can scatter a chunk into its registry while the
- * next one is still on the bus.  chunk >= the number of chunks: *count = 0. */
+ * next one is still on the bus.  chunk >= the number of chunks: *count = 0.
+ * The state is snapshotted on the device when _begin is reached in stream order and copied out on a stream of its own: calls made
+ * after _begin (pb_set_state, pb_step of the NEXT step) do not wait for the transfer and do not disturb it, so a caller that can use
+ * step k's result one step late -- _begin(k), enqueue step k + 1, _wait(k) -- hides the read-back behind the device's work.
+ * One read-back at a time: a second _begin waits (on the device) for the previous one's copies.  Host buffers: pinned, and left
+ * alone until _wait returned for every chunk. */
 int pb_get_state_begin(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, float* angvel3, int n_chunks);
 int pb_get_state_wait(pb_ctx* ctx, int chunk, int* first, int* count);
+/* _wait_poses returns as soon as pos3 / quat4 of the chunk are in (pb_get_state_wait: all four arrays).  pb_set_readback_order(1):
+ * later read-backs copy the poses of EVERY chunk out before any velocity (default 0: chunk by chunk, poses then velocities).  A loop
+ * that sends the result back up for the next step uploads poses first -- the narrowphase waits for them -- and the velocities behind
+ * them, which only the contact build reads. */
+int pb_get_state_wait_poses(pb_ctx* ctx, int chunk, int* first, int* count);
+int pb_set_readback_order(pb_ctx* ctx, int poses_first);
 int pb_sync(pb_ctx* ctx);
 
 /* ---- parity / debug taps ----------------------------------------------------------------------------- */

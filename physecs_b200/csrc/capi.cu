@@ -86,6 +86,12 @@ __global__ void k_col_dynamic_flag(int n, const int* __restrict__ colRow, int nD
     colFlags[i] = (colFlags[i] & 3) | (dyn ? 4 : 0);
 }
 
+// a call that changes bounds / colliders: a broadphase already enqueued by pb_step_begin is stale now (and a narrowphase enqueued by
+// pb_step_narrowphase cannot be taken back: such calls belong before it or after pb_step)
+#define PB_STALE_BROADPHASE(ctx) do { \
+    if ((ctx)->stepNarrowed) return pb_fail((ctx), PB_EINVAL, "the scene cannot be edited between pb_step_narrowphase and pb_step"); \
+    (ctx)->queryTreeValid = false; (ctx)->stepBegun = false; (ctx)->mainMarked = false; } while (0)
+
 static int ensureStage(pb_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->stageBytes) return PB_OK;
     if (ctx->stage) cudaFree(ctx->stage);
@@ -198,6 +204,8 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     ctx->numSMs = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    cudaEventCreateWithFlags(&ctx->evPacked, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evMainAtSet, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evVelReady, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evPoseReady, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evCounters, cudaEventDisableTiming);
@@ -316,6 +324,9 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->readStream) { cudaStreamSynchronize(ctx->readStream); cudaStreamDestroy(ctx->readStream); }
+    if (ctx->evPacked) cudaEventDestroy(ctx->evPacked);
+    if (ctx->stageRead) cudaFree(ctx->stageRead);
     pb_joints_free(ctx);
     if (ctx->stageVel) cudaFree(ctx->stageVel);
     if (ctx->evMainAtSet) cudaEventDestroy(ctx->evMainAtSet);
@@ -323,6 +334,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->evPoseReady) cudaEventDestroy(ctx->evPoseReady);
     if (ctx->evCounters) cudaEventDestroy(ctx->evCounters);
     for (auto& e : ctx->evRead) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evReadPose) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->evSub) if (e) cudaEventDestroy(e);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 #define F(p) if (ctx->p) cudaFree(ctx->p)
@@ -350,6 +362,7 @@ int pb_sync(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->readStream));      // a read-back begun with pb_get_state_begin has landed, too
     return pb_collect_step(ctx);
 }
 
@@ -357,7 +370,7 @@ int pb_upload_bodies(pb_ctx* ctx, int nDyn, int nStatic, const int* entity, cons
                      const float* vel3, const float* angvel3, const float* invMass, const float* com3, const float* invI9) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     int rows = nDyn + nStatic;
     if (rows > ctx->caps.max_bodies) return pb_fail(ctx, PB_ECAPACITY, "max_bodies");
     ctx->nDyn = nDyn; ctx->nStatic = nStatic; ctx->nRows = rows;
@@ -391,7 +404,7 @@ int pb_upload_colliders(pb_ctx* ctx, int n, const int* bodyRow, const int* colIn
                         const float* params4, const int* mesh, const float* material3, const int* flags, const int* data) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     if (n > ctx->caps.max_colliders) return pb_fail(ctx, PB_ECAPACITY, "max_colliders");
     ctx->nCol = n;
     ctx->hColType.assign(type, type + n); ctx->hColMesh.assign(mesh, mesh + n); ctx->hColRow.assign(bodyRow, bodyRow + n);
@@ -639,7 +652,7 @@ int pb_set_state_rows(pb_ctx* ctx, int first, int count, const float* pos3, cons
 int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const float* quat4) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     if (n <= 0) return PB_OK;
     size_t bytes = sizeof(float) * 8 * (size_t)n;
     int rc = ensureStage(ctx, bytes); if (rc) return rc;
@@ -661,7 +674,7 @@ int pb_move_rows(pb_ctx* ctx, int n, const int* rows, const float* pos3, const f
 int pb_refresh_bounds(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     return pb_update_bounds_all(ctx, 0.01f, 1);
 }
 
@@ -707,6 +720,7 @@ int pb_collect_step(pb_ctx* ctx) {
         // roll the host side back: the double buffers the build wrote into become "other" again, the velocity pointers return to the
         // buffer that still holds the pre-step velocities (the device skipped every kernel that writes scene state)
         ctx->curBuf ^= 1;
+        ctx->stepNarrowed = false; ctx->stepBegun = false;      // (collected between pb_step_narrowphase and pb_step: that step starts over)
         if (ctx->undoVelSwaps & 1) { std::swap(ctx->vel, ctx->velLive); std::swap(ctx->angvel, ctx->angvelLive); }
         ctx->cacheValid = ctx->undoCacheValid; ctx->cacheBuilt = ctx->undoCacheBuilt;
         ctx->countsStale = false;             // nothing was built: a later pb_get_counts must not replace n_manifolds by the post-build counter
@@ -748,12 +762,9 @@ int pb_step_begin(pb_ctx* ctx) {
     return PB_OK;
 }
 
-int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
-    cudaSetDevice(ctx->device);
-    if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
+// the middle of a step: world poses + narrowphase behind the broadphase, the counters on their way to the host
+static int stepNarrow(pb_ctx* ctx) {
     int rc;
-    if (!ctx->stepBegun && (rc = pb_step_begin(ctx))) return rc;
-    ctx->stepBegun = false; ctx->mainMarked = false;
     if ((rc = pb_wait_poses(ctx))) return rc;          // the broadphase above ran on the bounds of the previous step's end; from here on poses are read
     if ((rc = pb_world_poses(ctx))) return rc;
     if ((rc = pb_narrowphase(ctx))) return rc;
@@ -767,6 +778,29 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) 
     ctx->undoCacheValid = ctx->cacheValid; ctx->undoCacheBuilt = ctx->cacheBuilt; ctx->undoVelSwaps = 0;
     ctx->stepPending = true;
     ctx->curBuf ^= 1;
+    ctx->stepNarrowed = true;
+    return PB_OK;
+}
+
+// Optional middle of a step: everything that needs the new POSES but not the new velocities (world poses, narrowphase).  A caller
+// that uploads poses first calls this, then uploads the velocities while the narrowphase runs, then pb_step.
+int pb_step_narrowphase(pb_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    int rc;
+    if (ctx->stepNarrowed) return PB_OK;
+    if (!ctx->stepBegun && (rc = pb_step_begin(ctx))) return rc;
+    return stepNarrow(ctx);
+}
+
+int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity) {
+    cudaSetDevice(ctx->device);
+    if (substeps < 1 || iterations < 0) return pb_fail(ctx, PB_EINVAL, "substeps/iterations");
+    int rc;
+    if (!ctx->stepNarrowed) {
+        if (!ctx->stepBegun && (rc = pb_step_begin(ctx))) return rc;
+        if ((rc = stepNarrow(ctx))) return rc;
+    }
+    ctx->stepBegun = false; ctx->mainMarked = false; ctx->stepNarrowed = false;
     if ((rc = pb_wait_velocities(ctx))) return rc;      // first readers of the velocities: contact build, then the solver
     chooseIslands(ctx);
     if ((rc = pb_joint_begin_step(ctx))) return rc;      // solver body indices of the joints: the island search hooks through them
@@ -813,30 +847,72 @@ int pb_get_state_begin(pb_ctx* ctx, float* pos3, float* quat4, float* vel3, floa
     if (nChunks < 1) nChunks = 1;
     if (nChunks > PB_MAX_READ_CHUNKS) nChunks = PB_MAX_READ_CHUNKS;
     const int nDyn = ctx->nDyn;
+    const int before = ctx->readChunks;
     ctx->readChunks = 0;
     if (!nDyn) return PB_OK;
     const size_t n = (size_t)nDyn;
-    int rc = ensureStage(ctx, sizeof(float) * 13 * n); if (rc) return rc;
-    float* s = ctx->stage;
+    if (ctx->stageReadBytes < sizeof(float) * 13 * n) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->readStream));
+        if (ctx->stageRead) cudaFree(ctx->stageRead);
+        ctx->stageRead = nullptr; ctx->stageReadBytes = 0;
+        PB_CUDA(ctx, cudaMalloc((void**)&ctx->stageRead, sizeof(float) * 13 * n));
+        ctx->stageReadBytes = sizeof(float) * 13 * n;
+    } else if (before > 0) {
+        // the copies of the previous read-back leave the staging buffer before it is packed again
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evRead[before - 1], 0));
+    }
+    // The state is PACKED on the main stream (a snapshot in device memory: microseconds) and COPIED OUT on the read stream: whatever
+    // the main stream is given next -- the upload and the kernels of the following step -- runs beside the PCIe transfer, and only
+    // pb_get_state_wait waits for it.  A caller that reads step k's result after enqueueing step k + 1 hides the read-back entirely.
+    float* s = ctx->stageRead;
     const int g = pb_grid(nDyn, 256);
     if (pos3) ++ctx->launches, k_pack3<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->pos, s);
     if (quat4) ++ctx->launches, k_pack4<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->quat, s + 3 * n);
     if (vel3 || angvel3)
         ++ctx->launches, k_pack_vel<<<g, 256, 0, ctx->stream>>>(nDyn, ctx->vel, vel3 ? s + 7 * n : nullptr, angvel3 ? s + 10 * n : nullptr);
+    PB_CUDA(ctx, cudaEventRecord(ctx->evPacked, ctx->stream));
+    cudaStream_t rs = ctx->readStream;
+    PB_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evPacked, 0));
+    int rc = PB_OK;
+    // chunk by chunk (poses, then velocities of the chunk), or -- pb_set_readback_order -- the poses of every chunk first: whoever
+    // sends the result back up for the next step needs the poses first (narrowphase) and the velocities a stage later (contact build)
     const int per = (nDyn + nChunks - 1) / nChunks;
-    for (int c = 0; c < nChunks; ++c) {
-        const size_t f = (size_t)c * per;
-        if (f >= n) break;
-        const size_t m = std::min(n - f, (size_t)per);
-        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3 + 3 * f, s + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
-        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4 + 4 * f, s + 3 * n + 4 * f, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
-        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3 + 3 * f, s + 7 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
-        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(angvel3 + 3 * f, s + 10 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
-        if (!ctx->evRead[c]) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evRead[c], cudaEventDisableTiming));
-        PB_CUDA(ctx, cudaEventRecord(ctx->evRead[c], ctx->stream));
+    auto copyPoses = [&](int c, size_t f, size_t m) -> int {
+        if (pos3) PB_CUDA(ctx, cudaMemcpyAsync(pos3 + 3 * f, s + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, rs));
+        if (quat4) PB_CUDA(ctx, cudaMemcpyAsync(quat4 + 4 * f, s + 3 * n + 4 * f, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost, rs));
+        if (!ctx->evReadPose[c]) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evReadPose[c], cudaEventDisableTiming));
+        PB_CUDA(ctx, cudaEventRecord(ctx->evReadPose[c], rs));
         ctx->readFirst[c] = (int)f; ctx->readCount[c] = (int)m;
         ctx->readChunks = c + 1;
+        return PB_OK;
+    };
+    auto copyVels = [&](int c, size_t f, size_t m) -> int {
+        if (vel3) PB_CUDA(ctx, cudaMemcpyAsync(vel3 + 3 * f, s + 7 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, rs));
+        if (angvel3) PB_CUDA(ctx, cudaMemcpyAsync(angvel3 + 3 * f, s + 10 * n + 3 * f, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, rs));
+        if (!ctx->evRead[c]) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evRead[c], cudaEventDisableTiming));
+        PB_CUDA(ctx, cudaEventRecord(ctx->evRead[c], rs));
+        return PB_OK;
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < nChunks; ++c) {
+            const size_t f = (size_t)c * per;
+            if (f >= n) break;
+            const size_t m = std::min(n - f, (size_t)per);
+            if (ctx->readPosesFirst) { if ((rc = pass == 0 ? copyPoses(c, f, m) : copyVels(c, f, m))) return rc; }
+            else if (pass == 0) { if ((rc = copyPoses(c, f, m)) || (rc = copyVels(c, f, m))) return rc; }
+        }
     }
+    return PB_OK;
+}
+
+int pb_set_readback_order(pb_ctx* ctx, int poses_first) { ctx->readPosesFirst = poses_first ? 1 : 0; return PB_OK; }
+
+int pb_get_state_wait_poses(pb_ctx* ctx, int chunk, int* first, int* count) {
+    cudaSetDevice(ctx->device);
+    if (chunk < 0 || chunk >= ctx->readChunks) { if (first) *first = 0; if (count) *count = 0; return chunk < 0 ? PB_EINVAL : PB_OK; }
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->evReadPose[chunk]));
+    if (first) *first = ctx->readFirst[chunk];
+    if (count) *count = ctx->readCount[chunk];
     return PB_OK;
 }
 
@@ -870,7 +946,7 @@ int pb_set_static_poses(pb_ctx* ctx, int nStatic, const float* pos3, const float
 int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     if (n <= 0) return PB_OK;
     for (int i = 0; i < n; ++i) if (cols[i] < 0 || cols[i] >= ctx->nCol) return pb_fail(ctx, PB_EINVAL, "pb_set_bounds: collider out of range");
     int rc = ensureStage(ctx, sizeof(float) * 7 * (size_t)n); if (rc) return rc;
@@ -885,7 +961,7 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
 int pb_set_kinematic(pb_ctx* ctx, int nDyn, const int* kinematic) {
     cudaSetDevice(ctx->device);
     { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
-    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;     // a broadphase already enqueued by pb_step_begin is stale now
+    PB_STALE_BROADPHASE(ctx);
     if (nDyn != ctx->nDyn) return pb_fail(ctx, PB_EINVAL, "pb_set_kinematic: n_dynamic mismatch");
     if (!nDyn) return PB_OK;
     ctx->hKinematic.assign(kinematic, kinematic + nDyn);

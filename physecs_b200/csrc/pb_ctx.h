@@ -99,6 +99,9 @@ struct pb_ctx {
     // refreshed at the end of the previous step, like the reference: Physecs.cpp:556-559) nor velocities, the narrowphase needs the
     // poses, the contact build the velocities: the step waits for evPoseReady after the broadphase and for evVelReady before the
     // build, so the whole H2D copy hides behind the broadphase.  Every other entry point waits for both (pb_wait_velocities).
+    // read-back of pb_get_state_begin: packed on the main stream into its own staging buffer, copied out on the READ stream, so the copies
+    // of step k run beside the upload and the kernels of step k + 1 (pb_get_state_wait is the only thing that waits for them)
+    cudaStream_t readStream = nullptr; cudaEvent_t evPacked = nullptr; float* stageRead = nullptr; size_t stageReadBytes = 0;
     cudaStream_t copyStream = nullptr; cudaEvent_t evMainAtSet = nullptr, evVelReady = nullptr, evPoseReady = nullptr; bool velPending = false, posePending = false;
     float* stageVel = nullptr; size_t stageVelBytes = 0;   // staging of the copy stream: 13 floats per body (pos 3, quat 4, vel 3, angvel 3)
 
@@ -226,8 +229,11 @@ struct pb_ctx {
     // the scene untouched) and the host COLLECTS the outcome -- counters snapshot, status -- at the next call that synchronises with the
     // step (capi.cu collectStep).  stepPending: a step's outcome has not been collected yet; undo*: host bookkeeping to roll back then.
     cudaEvent_t evCounters = nullptr; bool stepPending = false; bool statsCopied = false;   // statsCopied: the island statistics rode along with the counters
+    bool stepNarrowed = false;       // pb_step_narrowphase ran: the next pb_step continues behind the narrowphase
     bool stepBegun = false;          // pb_step_begin ran: the next pb_step continues behind its broadphase
     bool mainMarked = false;         // evMainAtSet already holds "the main stream before this step's broadphase": uploads wait for that
+    int readPosesFirst = 0;          // pb_set_readback_order: 1 = the poses of every chunk go out before any velocity
+    cudaEvent_t evReadPose[PB_MAX_READ_CHUNKS] = {nullptr};      // ... the chunk's poses have arrived (they are copied out first)
     cudaEvent_t evRead[PB_MAX_READ_CHUNKS] = {nullptr}; int readFirst[PB_MAX_READ_CHUNKS] = {0}, readCount[PB_MAX_READ_CHUNKS] = {0}, readChunks = 0;   // pb_get_state_begin / _wait
     int rawHint = -1;                // raw manifold count of the last collected step (-1: none yet): shapes grids only
     bool undoCacheValid = false, undoCacheBuilt = false; int undoVelSwaps = 0;

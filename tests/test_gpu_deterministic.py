@@ -52,3 +52,65 @@ def test_gates_in_deterministic_mode(maker, monkeypatch):
     monkeypatch.setenv("PB_DETERMINISTIC", "1")
     s = parity.run_gates(maker(), steps=8)
     assert s["steps"] == 8 and s["worst_manifold"] <= parity.TOL
+
+
+def test_chunked_round_trip_beside_the_step_equals_plain_steps():
+    """The host-authoritative loop with the transfers beside the device's work -- pb_get_state_begin (chunks, read stream), pb_step_begin
+    (the next broadphase at once), every chunk uploaded again as it arrives (pb_set_state_rows), pb_step -- against plain pb_step calls
+    on a second context: bit-identical states (deterministic colours), i.e. the overlap changes nothing the step sees."""
+    import ctypes as C
+    import torch
+    from physecs_b200.capi import Context
+    d = S.mixed_bin(20_000)
+    a = Context(d, max_pairs=32 * d.n + 4096, max_manifolds=12 * d.n + 4096)
+    b = Context(d, max_pairs=32 * d.n + 4096, max_manifolds=12 * d.n + 4096)
+    try:
+        for c in (a, b):
+            c.set_deterministic(True)
+        n = a.n_dyn
+        pin = lambda w: torch.empty((n, w), dtype=torch.float32).pin_memory()
+        tp, tq, tv, tw = pin(3), pin(4), pin(3), pin(3)
+        pos, quat, vel, ang = tp.numpy(), tq.numpy(), tv.numpy(), tw.numpy()
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        lib, h = b.lib, b.ctx
+        assert lib.pb_get_state(h, fp(pos), fp(quat), fp(vel), fp(ang)) == 0
+        CH, steps = 5, 70
+        first, count = C.c_int(), C.c_int()
+        NULLF = C.POINTER(C.c_float)()
+        assert lib.pb_set_readback_order(h, 1) == 0
+        assert lib.pb_step_begin(h) == 0
+        for k in range(steps):
+            a.step()
+            for half in (0, 1):
+                for c in range(CH if k > 0 else 1):
+                    if k > 0:
+                        assert (lib.pb_get_state_wait if half else lib.pb_get_state_wait_poses)(h, c, C.byref(first), C.byref(count)) == 0
+                        f0, cnt = first.value, count.value
+                    else:
+                        f0, cnt = 0, n
+                    if cnt:
+                        off = lambda x, w: C.cast(C.c_void_p(x.ctypes.data + 4 * w * f0), C.POINTER(C.c_float))
+                        if half == 0:
+                            assert lib.pb_set_state_rows(h, f0, cnt, off(pos, 3), off(quat, 4), NULLF, NULLF) == 0
+                        else:
+                            assert lib.pb_set_state_rows(h, f0, cnt, NULLF, NULLF, off(vel, 3), off(ang, 3)) == 0
+                if half == 0:
+                    assert lib.pb_step_narrowphase(h) == 0
+            assert lib.pb_step(h, C.c_float(d.dt), d.substeps, d.iterations, C.c_float(d.gravity)) == 0, lib.pb_last_error(h)
+            assert lib.pb_get_state_begin(h, fp(pos), fp(quat), fp(vel), fp(ang), CH) == 0
+            if k + 1 < steps:
+                assert lib.pb_step_begin(h) == 0
+        seen = 0
+        for c in range(CH):
+            assert lib.pb_get_state_wait(h, c, C.byref(first), C.byref(count)) == 0
+            seen += count.value
+        assert seen == n
+        A = a.get_state()
+        for x, y, what in zip(A, (pos, quat, vel, ang), ("pos", "quat", "vel", "angvel")):
+            assert np.array_equal(x.view(np.int32), y.view(np.int32)), what
+        B = b.get_state()            # ... and the device holds what was read
+        for x, y in zip(A, B):
+            assert np.array_equal(x.view(np.int32), y.view(np.int32))
+        assert a.counts().n_manifolds > 10000
+    finally:
+        a.close(); b.close()
