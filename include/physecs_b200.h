@@ -187,8 +187,8 @@ int pb_step(pb_ctx* ctx, float dt, int substeps, int iterations, float gravity);
 int pb_step_begin(pb_ctx* ctx);
 /* Optional middle of a step: world poses + narrowphase (behind pb_step_begin's broadphase; calls it if it was not).  They read the
  * new poses but no velocity, so a caller uploads the poses, calls this, uploads the velocities while the narrowphase runs, and then
- * calls pb_step, which continues with the contact build.  Between this call and pb_step only velocity uploads (pb_set_state /
- * pb_set_state_rows with null pose pointers) and read-back calls are allowed: scene edits return PB_EINVAL. */
+ * calls pb_step, which continues with the contact build.  Poses uploaded after this call are not seen by the narrowphase already
+ * enqueued; a scene edit in between (colliders, kinematic flags, moved rows, bounds) makes pb_step start the step over. */
 int pb_step_narrowphase(pb_ctx* ctx);
 /* waits for the narrowphase of the last pb_step (not for the whole step) and returns its status; PB_OK when nothing is pending */
 int pb_collect_step(pb_ctx* ctx);

@@ -86,11 +86,19 @@ __global__ void k_col_dynamic_flag(int n, const int* __restrict__ colRow, int nD
     colFlags[i] = (colFlags[i] & 3) | (dyn ? 4 : 0);
 }
 
-// a call that changes bounds / colliders: a broadphase already enqueued by pb_step_begin is stale now (and a narrowphase enqueued by
-// pb_step_narrowphase cannot be taken back: such calls belong before it or after pb_step)
-#define PB_STALE_BROADPHASE(ctx) do { \
-    if ((ctx)->stepNarrowed) return pb_fail((ctx), PB_EINVAL, "the scene cannot be edited between pb_step_narrowphase and pb_step"); \
-    (ctx)->queryTreeValid = false; (ctx)->stepBegun = false; (ctx)->mainMarked = false; } while (0)
+// A call that changes bounds / colliders / body kinds: a broadphase already enqueued by pb_step_begin is stale now.  If the narrowphase
+// went out as well (pb_step_narrowphase), its host-side bookkeeping is taken back -- the device's results are scratch that the next
+// pb_step_begin resets -- and pb_step starts the step over.
+static void staleBroadphase(pb_ctx* ctx) {
+    if (ctx->stepNarrowed) {
+        ctx->stepNarrowed = false;
+        ctx->stepPending = false;        // nobody collects the abandoned narrowphase
+        ctx->curBuf ^= 1;
+        ctx->cacheValid = ctx->undoCacheValid; ctx->cacheBuilt = ctx->undoCacheBuilt;
+    }
+    ctx->queryTreeValid = false; ctx->stepBegun = false; ctx->mainMarked = false;
+}
+#define PB_STALE_BROADPHASE(ctx) staleBroadphase(ctx)
 
 static int ensureStage(pb_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->stageBytes) return PB_OK;

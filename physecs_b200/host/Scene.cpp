@@ -820,13 +820,18 @@ void Scene::simulate(float timeStep) {
         return packedAt<TransformComponent>(trStore, idx);
     };
     const bool full = S.syncMode == SYNC_FULL;
-    auto gatherDyn = [&](size_t b, size_t e) {
+    // what: 1 = poses (TransformComponent), 2 = velocities + the fields the reference reads live (RigidBodyDynamicComponent), 3 = both
+    auto gatherDyn = [&](size_t b, size_t e, int what) {
         for (size_t r = b; r < e; ++r) {
-            const TransformComponent& t = transformOf((int)r);
+            if (what & 1) {
+                const TransformComponent& t = transformOf((int)r);
+                float* p = S.hPos.p + 3 * r; float* q = S.hQuat.p + 4 * r;
+                p[0] = t.position.x; p[1] = t.position.y; p[2] = t.position.z;
+                q[0] = t.orientation.x; q[1] = t.orientation.y; q[2] = t.orientation.z; q[3] = t.orientation.w;
+            }
+            if (!(what & 2)) continue;
             const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
-            float* p = S.hPos.p + 3 * r; float* q = S.hQuat.p + 4 * r; float* v = S.hVel.p + 3 * r; float* w = S.hAng.p + 3 * r;
-            p[0] = t.position.x; p[1] = t.position.y; p[2] = t.position.z;
-            q[0] = t.orientation.x; q[1] = t.orientation.y; q[2] = t.orientation.z; q[3] = t.orientation.w;
+            float* v = S.hVel.p + 3 * r; float* w = S.hAng.p + 3 * r;
             v[0] = d.velocity.x; v[1] = d.velocity.y; v[2] = d.velocity.z;
             w[0] = d.angularVelocity.x; w[1] = d.angularVelocity.y; w[2] = d.angularVelocity.z;
             // fields the reference reads live every step (Physecs.cpp:219-226, :446-467): detect direct writes
@@ -843,16 +848,24 @@ void Scene::simulate(float timeStep) {
     // The step's head goes to the device first: counters reset + broadphase, which run on the bounds the previous step left (as the
     // reference's sweep does, Physecs.cpp:119-173) and need nothing from the registry.  The gather below overlaps it.
     S.check(pb_step_begin(S.ctx), "pb_step_begin");
-    // dynamic rows in chunks: each chunk's upload (copy stream) starts as soon as the worker threads have gathered it
+    // Dynamic rows in chunks: each chunk's upload (copy stream) starts as soon as the worker threads have gathered it.  Poses go
+    // first, for every chunk; the narrowphase, which needs nothing else, is enqueued behind them (pb_step_narrowphase), and the
+    // velocities are gathered and uploaded while it runs -- only the contact build waits for them.
     const int nChunks = nDyn >= 65536 ? 8 : 1;
     const size_t perChunk = ((size_t)nDyn + nChunks - 1) / nChunks;
     auto gatherAndUpload = [&]() {
-        for (int c = 0; c < nChunks; ++c) {
-            const size_t first = (size_t)c * perChunk;
-            if (first >= (size_t)nDyn) break;
-            const size_t count = std::min(perChunk, (size_t)nDyn - first);
-            S.workers.parallelFor(count, [&](size_t b, size_t e) { gatherDyn(first + b, first + e); });
-            S.check(pb_set_state_rows(S.ctx, (int)first, (int)count, S.hPos.p + 3 * first, S.hQuat.p + 4 * first, S.hVel.p + 3 * first, S.hAng.p + 3 * first), "pb_set_state_rows");
+        const bool split = nDyn >= 65536;
+        for (int pass = 0; pass < (split ? 2 : 1); ++pass) {
+            const int what = split ? (pass == 0 ? 1 : 2) : 3;
+            for (int c = 0; c < nChunks; ++c) {
+                const size_t first = (size_t)c * perChunk;
+                if (first >= (size_t)nDyn) break;
+                const size_t count = std::min(perChunk, (size_t)nDyn - first);
+                S.workers.parallelFor(count, [&](size_t b, size_t e) { gatherDyn(first + b, first + e, what); });
+                S.check(pb_set_state_rows(S.ctx, (int)first, (int)count, (what & 1) ? S.hPos.p + 3 * first : nullptr, (what & 1) ? S.hQuat.p + 4 * first : nullptr,
+                                          (what & 2) ? S.hVel.p + 3 * first : nullptr, (what & 2) ? S.hAng.p + 3 * first : nullptr), "pb_set_state_rows");
+            }
+            if (split && pass == 0) S.check(pb_step_narrowphase(S.ctx), "pb_step_narrowphase");
         }
     };
     if (full) {
@@ -872,7 +885,7 @@ void Scene::simulate(float timeStep) {
         // device-authoritative: the staging buffers still hold the previous step's result; refresh only announced rows
         if (!S.stagingValid) gatherAndUpload();
         else {
-            for (unsigned r : S.touched) if ((int)r < nDyn) gatherDyn(r, r + 1);
+            for (unsigned r : S.touched) if ((int)r < nDyn) gatherDyn(r, r + 1, 3);
             S.check(pb_set_state(S.ctx, nDyn, S.hPos.p, S.hQuat.p, S.hVel.p, S.hAng.p), "pb_set_state");
         }
     }
