@@ -114,3 +114,32 @@ def test_chunked_round_trip_beside_the_step_equals_plain_steps():
         assert a.counts().n_manifolds > 10000
     finally:
         a.close(); b.close()
+
+
+def test_scene_edit_between_narrowphase_and_step_restarts_the_step():
+    """pb_step_narrowphase enqueues half a step; a scene edit behind it (rows moved: bounds change) makes pb_step start over.  Same result
+    as the edit followed by a plain pb_step, over several steps (the abandoned narrowphase leaves nothing behind)."""
+    from physecs_b200.capi import Context
+    d = S.mixed_bin(3000, spacing=0.8)
+    a, b = Context(d), Context(d)
+    try:
+        dyn = d.dynamic_entities()
+        for c in (a, b):
+            c.set_deterministic(True)
+            for _ in range(40):
+                c.step()
+        for k in range(6):
+            P, Q, _, _ = a.get_state_entities()
+            ents = dyn[k::7][:50]
+            newP = P[ents] + np.float32([0.0, 0.5, 0.0]); newQ = Q[ents]
+            a.move_rows(ents, newP, newQ)
+            a.step()
+            assert b.lib.pb_step_narrowphase(b.ctx) == 0
+            b.move_rows(ents, newP, newQ)
+            b.step()
+            b.step(); a.step()
+            for x, y, what in zip(a.get_state(), b.get_state(), ("pos", "quat", "vel", "angvel")):
+                assert np.array_equal(x.view(np.int32), y.view(np.int32)), (k, what)
+        assert a.counts().n_manifolds == b.counts().n_manifolds and a.counts().n_manifolds > 1000
+    finally:
+        a.close(); b.close()
