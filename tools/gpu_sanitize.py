@@ -30,4 +30,37 @@ run("big shapes on a fine mesh (mesh spill kernel)", S.big_on_fine_mesh(cells=40
 run("degenerate convex pairs (GJK / EPA spill kernel)", S.degenerate_convex(), 3)
 run("convex pile, deterministic colouring", S.convex_pile(300, mix_prims=True), 30, PB_DETERMINISTIC=1)
 run("joint zoo + overflow bucket", S.joint_star(12), 10)
+run("pyramid as one thread-block cluster (hardware cluster barrier)", S.pyramid(60), 4, PB_ISLANDS=0, PB_FUSED=1)
+run("mixed bin, small and big islands in one step (per-CTA sweeps + device-wide colours)", S.mixed_bin(2500, spacing=0.8), 30, PB_ISLAND_LOCAL_MAX=40, PB_FUSED=0, PB_ISLANDS=1)
+
+
+def round_trip():
+    # read-back on the read stream beside the next step's broadphase / narrowphase, uploads on the copy stream (bench.py e2e loop)
+    import ctypes as C
+    import numpy as np
+    d = S.mixed_bin(1500, spacing=0.8)
+    ctx = Context(d)
+    n = ctx.n_dyn
+    pos, quat, vel, ang = (np.zeros((n, w), np.float32) for w in (3, 4, 3, 3))
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    lib, h = ctx.lib, ctx.ctx
+    NULLF = C.POINTER(C.c_float)()
+    first, count = C.c_int(), C.c_int()
+    lib.pb_get_state(h, fp(pos), fp(quat), fp(vel), fp(ang)); lib.pb_set_readback_order(h, 1); lib.pb_step_begin(h)
+    for k in range(12):
+        if k:
+            lib.pb_get_state_wait_poses(h, 0, C.byref(first), C.byref(count))
+        lib.pb_set_state_rows(h, 0, n, fp(pos), fp(quat), NULLF, NULLF); lib.pb_step_narrowphase(h)
+        if k:
+            lib.pb_get_state_wait(h, 0, C.byref(first), C.byref(count))
+        lib.pb_set_state_rows(h, 0, n, NULLF, NULLF, fp(vel), fp(ang))
+        assert lib.pb_step(h, C.c_float(d.dt), d.substeps, d.iterations, C.c_float(d.gravity)) == 0
+        assert lib.pb_get_state_begin(h, fp(pos), fp(quat), fp(vel), fp(ang), 1) == 0
+        lib.pb_step_begin(h)
+    lib.pb_get_state_wait(h, 0, C.byref(first), C.byref(count))
+    print(f"round trip beside the step: manifolds {ctx.counts().n_manifolds} rows read {count.value}", flush=True)
+    ctx.close()
+
+
+round_trip()
 print("sanitize scenes done")
