@@ -305,6 +305,11 @@ class Context:
         self._check(self.lib.pb_get_island_stats(self.ctx, out))
         return dict(on=bool(out[0]), local=out[1], total=out[2])
 
+    def broadphase_info(self):
+        out = (C.c_int * 3)()
+        self._check(self.lib.pb_get_broadphase_info(self.ctx, out))
+        return dict(all_pairs=bool(out[0]), tile_hits=out[1], tiles=out[2])
+
     def launches(self):
         return int(self.lib.pb_get_launches(self.ctx))
 

@@ -489,63 +489,100 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
     __syncthreads();
     for (int k = 0; k < BF_TILE / 32; ++k) { qmn = vmin(qmn, mk3(qred[k][0], qred[k][1], qred[k][2])); qmx = vmax(qmx, mk3(qred[k][3], qred[k][4], qred[k][5])); }
     if (qmn.x > qmx.x) return;                 // no querying collider in this CTA (uniform)
+    // Tiles in reach of this CTA's queries: 128 tile boxes are tested at a time, one per thread (the boxes of a batch of thousands of
+    // scenes -- hundreds of tiles -- cost a few coalesced loads instead of one dependent round trip per tile), then the CTA walks the
+    // hits in tile order.
+    __shared__ unsigned int sHit[BF_TILE / 32];
     const int firstTile = blockIdx.y * tilesPerSlice;
-    for (int t = firstTile; t < firstTile + tilesPerSlice; ++t) {
-        const int base = t * BF_TILE;
-        if (base >= n) break;                 // uniform across the CTA
-        const float4 tmn = tileMin[t], tmx = tileMax[t];
-        if (!overlaps(qmn, qmx, tmn, tmx)) continue;      // uniform across the CTA: the whole tile is out of reach
-        const int b0 = base + threadIdx.x;
-        if (b0 < n) { smn[threadIdx.x] = aabbMin[b0]; smx[threadIdx.x] = aabbMax[b0]; sflag[threadIdx.x] = colFlags[b0]; srow[threadIdx.x] = colRow[b0]; }
-        else sflag[threadIdx.x] = 0;
+    const int nTiles = (n + BF_TILE - 1) / BF_TILE;
+    const int lastTile = min(firstTile + tilesPerSlice, nTiles);
+    int met = 0;
+    for (int chunk = firstTile; chunk < lastTile; chunk += BF_TILE) {
+        const int tt = chunk + threadIdx.x;
+        const bool reach = tt < lastTile && overlaps(qmn, qmx, tileMin[tt], tileMax[tt]);
+        const unsigned int bal = __ballot_sync(0xffffffffu, reach);
+        if ((threadIdx.x & 31) == 0) sHit[threadIdx.x >> 5] = bal;
         __syncthreads();
-        // hits of this thread in this tile as a 128-bit mask; the pairs are appended afterwards with ONE atomic per warp and tile (a
-        // batch of 512 little scenes emits ~10 k pairs per step: one atomic per pair on the one counter was most of this kernel's time)
-        unsigned int hit[BF_TILE / 32] = {0, 0, 0, 0};
-        if (active && overlaps(amn, amx, tmn, tmx)) {
-            const int cnt = min(BF_TILE, n - base);
-            for (int j = 0; j < cnt; ++j) {
-                const int fb = sflag[j];
-                if (!(fb & COLF_ENABLE)) continue;
-                const int b = base + j;
-                if ((fb & COLF_DYNAMIC) && b <= a) continue;      // a pair of two querying colliders is emitted by the lower index
-                if (srow[j] == rowA) continue;                    // same entity (Physecs.cpp:145)
-                if (!overlaps(amn, amx, smn[j], smx[j])) continue;
-                hit[j >> 5] |= 1u << (j & 31);
-            }
-        }
-        {
-            const int mine = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
-            const int lane = threadIdx.x & 31;
-            int inc = mine;
+        unsigned int masks[BF_TILE / 32];
+        for (int w = 0; w < BF_TILE / 32; ++w) masks[w] = sHit[w];
+        __syncthreads();
+        for (int w = 0; w < BF_TILE / 32; ++w) {
+            unsigned int tm = masks[w];
+            while (tm) {                            // uniform across the CTA
+                const int t = chunk + 32 * w + __ffs(tm) - 1;
+                tm &= tm - 1;
+                ++met;
+                const int base = t * BF_TILE;
+                const float4 tmn = tileMin[t], tmx = tileMax[t];
+                const int b0 = base + threadIdx.x;
+                if (b0 < n) { smn[threadIdx.x] = aabbMin[b0]; smx[threadIdx.x] = aabbMax[b0]; sflag[threadIdx.x] = colFlags[b0]; srow[threadIdx.x] = colRow[b0]; }
+                else sflag[threadIdx.x] = 0;
+                __syncthreads();
+                // hits of this thread in this tile as a 128-bit mask; the pairs are appended afterwards with ONE atomic per warp and tile (a
+                // batch of 512 little scenes emits ~10 k pairs per step: one atomic per pair on the one counter was most of this kernel's time)
+                unsigned int hit[BF_TILE / 32] = {0, 0, 0, 0};
+                if (active && overlaps(amn, amx, tmn, tmx)) {
+                    const int cnt = min(BF_TILE, n - base);
+                    for (int j = 0; j < cnt; ++j) {
+                        const int fb = sflag[j];
+                        if (!(fb & COLF_ENABLE)) continue;
+                        const int b = base + j;
+                        if ((fb & COLF_DYNAMIC) && b <= a) continue;      // a pair of two querying colliders is emitted by the lower index
+                        if (srow[j] == rowA) continue;                    // same entity (Physecs.cpp:145)
+                        if (!overlaps(amn, amx, smn[j], smx[j])) continue;
+                        hit[j >> 5] |= 1u << (j & 31);
+                    }
+                }
+                {
+                    const int mine = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
+                    const int lane = threadIdx.x & 31;
+                    int inc = mine;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (total) {                                          // warp-uniform
-                int wbase = 0;
-                if (lane == 31) wbase = atomicAdd(&counters[CNT_PAIRS], total);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                int slot = wbase + inc - mine;
-                if (mine) {
-                    const unsigned int ea = (unsigned int)rowEntity[rowA];
-                    for (int w = 0; w < BF_TILE / 32; ++w) {
-                        unsigned int m = hit[w];
-                        while (m) {
-                            const int j = 32 * w + __ffs(m) - 1;
-                            m &= m - 1;
-                            const int b = base + j;
-                            if (slot < maxPairs) {
-                                const unsigned int eb = (unsigned int)rowEntity[srow[j]];
-                                pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
-                            } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
-                            ++slot;
+                    for (int d = 1; d < 32; d <<= 1) { int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+                    const int total = __shfl_sync(0xffffffffu, inc, 31);
+                    if (total) {                                          // warp-uniform
+                        int wbase = 0;
+                        if (lane == 31) wbase = atomicAdd(&counters[CNT_PAIRS], total);
+                        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                        int slot = wbase + inc - mine;
+                        if (mine) {
+                            const unsigned int ea = (unsigned int)rowEntity[rowA];
+                            for (int hw = 0; hw < BF_TILE / 32; ++hw) {
+                                unsigned int m = hit[hw];
+                                while (m) {
+                                    const int j = 32 * hw + __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const int b = base + j;
+                                    if (slot < maxPairs) {
+                                        const unsigned int eb = (unsigned int)rowEntity[srow[j]];
+                                        pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
+                                    } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
+                                    ++slot;
+                                }
+                            }
                         }
                     }
                 }
+                __syncthreads();
             }
         }
-        __syncthreads();
     }
+    if (threadIdx.x == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], met);
+}
+
+// How many (query tile, collider tile) pairs meet: what the all-pairs kernel would have to walk.  Run beside the tree broadphase
+// for mid-sized scenes, so the host can tell (one step late) a batch of scenes laid out side by side -- a handful of tiles in
+// reach of every tile: all-pairs wins -- from a pile, where every tile meets most others.
+__global__ void __launch_bounds__(BF_TILE) k_tile_probe(int nTiles, const float4* __restrict__ tileMin, const float4* __restrict__ tileMax, int* __restrict__ counters) {
+    const int q = blockIdx.x;
+    const float4 qmn = tileMin[q], qmx = tileMax[q];
+    int met = 0;
+    for (int t = threadIdx.x; t < nTiles; t += blockDim.x) {
+        const float4 a = tileMin[t], b = tileMax[t];
+        if (!(qmx.x < a.x || qmn.x > b.x) && !(qmx.y < a.y || qmn.y > b.y) && !(qmx.z < a.z || qmn.z > b.z)) ++met;
+    }
+    for (int d = 16; d > 0; d >>= 1) met += __shfl_xor_sync(0xffffffffu, met, d);
+    if ((threadIdx.x & 31) == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], met);
 }
 
 // Morton sort + LBVH build + refit over the current collider bounds (n >= 2).  Shared by the step's pair search and the
@@ -576,19 +613,35 @@ int pb_build_tree(pb_ctx* ctx, bool forStep) {
 // n == 2..: general path.  n < 2: no pairs.
 int pb_broadphase(pb_ctx* ctx) {
     int n = ctx->nCol;
+    ctx->stepBrute = false; ctx->pendingTiles = 0;
     if (n < 2) return PB_OK;
-    if (n <= ctx->bruteForceMax) {
-        const int tiles = (n + BF_TILE - 1) / BF_TILE;
+    const int tiles = (n + BF_TILE - 1) / BF_TILE;
+    // Mid-sized scenes: all pairs when creation order is spatially coherent -- a tile meets a handful of tiles (a batch of scenes side
+    // by side; the statistics are the previous step's) --, the tree otherwise.  The tree's ~25 dependent launches cost ~0.2 ms however
+    // small the scene; the all-pairs kernel of 4096 ragdoll scenes walks ~3 tiles per tile.
+    const bool midSized = n > ctx->bruteForceMax && n <= ctx->bruteForceBigMax;
+    const bool coherent = midSized && ctx->lastTileHits >= 0 && ctx->lastTiles == tiles && (long long)ctx->lastTileHits <= 12ll * tiles;
+    if (n <= ctx->bruteForceMax || coherent) {
         int slices = (4 * ctx->numSMs + tiles - 1) / tiles;        // enough CTAs to fill the device a few times over
         if (slices > tiles) slices = tiles;
         if (slices < 1) slices = 1;
         const int tilesPerSlice = (tiles + slices - 1) / slices;
-        // tile boxes live in the (otherwise idle) tree node arrays: tiles <= 64 entries of nodeMin / nodeMax
+        // tile boxes live in the (otherwise idle) tree node arrays: one entry of nodeMin / nodeMax per tile
         ++ctx->launches, k_tile_bounds<<<tiles, BF_TILE, 0, ctx->stream>>>(n, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
         ++ctx->launches, k_pairs_bruteforce<<<dim3(tiles, slices), BF_TILE, 0, ctx->stream>>>(n, tilesPerSlice, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                                                           ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
+        ctx->stepBrute = true; ctx->pendingTiles = tiles;
         PB_CUDA(ctx, cudaGetLastError());
         return PB_OK;
+    }
+    if (midSized) {
+        // the tile statistics for the next step's choice (tile boxes in the tail of the pair arena: the tree owns the node arrays)
+        float4* tb = (float4*)ctx->pairs;
+        if ((size_t)ctx->caps.max_pairs * sizeof(int2) >= 2 * (size_t)tiles * sizeof(float4)) {
+            ++ctx->launches, k_tile_bounds<<<tiles, BF_TILE, 0, ctx->stream>>>(n, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, tb, tb + tiles);
+            ++ctx->launches, k_tile_probe<<<tiles, BF_TILE, 0, ctx->stream>>>(tiles, tb, tb + tiles, ctx->counters);
+            ctx->pendingTiles = tiles;
+        }
     }
     int rc = pb_build_tree(ctx, true);
     if (rc) return rc;

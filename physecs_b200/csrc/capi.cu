@@ -190,6 +190,10 @@ int pb_get_island_stats(pb_ctx* ctx, int* out3) {
     out3[0] = ctx->islandsOn ? 1 : 0; out3[1] = ctx->lastIslandLocal; out3[2] = ctx->lastIslandTotal;
     return PB_OK;
 }
+int pb_get_broadphase_info(pb_ctx* ctx, int* out3) {
+    out3[0] = ctx->stepBrute ? 1 : 0; out3[1] = ctx->lastTileHits; out3[2] = ctx->lastTiles;
+    return PB_OK;
+}
 int pb_set_deterministic(pb_ctx* ctx, int on) { ctx->deterministic = on != 0; return PB_OK; }
 unsigned long long pb_get_launches(pb_ctx* ctx) { return ctx->launches; }
 void pb_profiler_range(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
@@ -253,6 +257,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (!rc && cudaMallocHost((void**)&ctx->hCounters, sizeof(int) * (CNT_TOTAL + 4)) != cudaSuccess) rc = PB_ECUDA;
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
+    if (const char* e = getenv("PB_BRUTE_FORCE_BIG_MAX")) ctx->bruteForceBigMax = atoi(e);
     if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
     if (const char* e = getenv("PB_SORT_COOP")) ctx->sortCoopMode = atoi(e);
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
@@ -721,6 +726,7 @@ int pb_collect_step(pb_ctx* ctx) {
     ctx->lastCounts.n_triggers = h[CNT_TRIGGERS];
     ctx->lastCounts.cause = cause;
     ctx->lastCounts.n_spilled = h[CNT_SPILLED];
+    if (ctx->pendingTiles) { ctx->lastTileHits = h[CNT_TILE_HITS]; ctx->lastTiles = ctx->pendingTiles; }      // tile statistics: the next step's broadphase choice
     ctx->pairsHint = std::min(nPairs, ctx->caps.max_pairs);
     ctx->rawHint = std::min(nRaw, ctx->caps.max_manifolds);
     const bool overflow = nPairs > ctx->caps.max_pairs || nRaw > ctx->caps.max_manifolds || (status & PB_ECAPACITY);

@@ -65,6 +65,7 @@ enum {
     CNT_BINSTART = 32,                  // PB_NUM_BINS+1 bin starts
     CNT_COLORSTART = 64,                // PB_MAX_COLORS+1 manifold start per colour
     CNT_MULTISTART = 130,               // PB_MAX_COLORS: where the multi-point manifolds of each colour start (singles come first)
+    CNT_TILE_HITS = 202,                // (query tile, collider tile) pairs whose union boxes meet, from k_pairs_bruteforce / k_tile_probe: how coherent creation order is
     CNT_TOTAL = 256
 };
 
@@ -142,6 +143,11 @@ struct pb_ctx {
     int pairsHint = -1;                 // candidate pairs of the previous step (-1: none yet): bounds the bin kernels' grids on small scenes
     int npFuseSmall = 1;                // small scenes: the six analytic bins in one launch (env PB_NP_FUSE=0: one launch per bin)
     int npWaves = 4;                    // narrowphase bin kernels: grid = SMs x co-resident CTAs x npWaves (env PB_NP_WAVES; 0 = the former numSMs * 8)
+    int bruteForceBigMax = 131072;      // ... and up to this many when creation order is spatially coherent (a batch of scenes side by side): decided from the
+                                        // previous step's tile statistics (env PB_BRUTE_FORCE_BIG_MAX; 0 = off)
+    int lastTileHits = -1, lastTiles = 0;   // tile pairs that met / tiles, last step that looked (-1: never)
+    int pendingTiles = 0;               // tiles of the step in flight if it produces tile statistics (0: it does not)
+    bool stepBrute = false;             // this step's broadphase was the all-pairs kernel
     int bruteForceMax = 8192;           // colliders up to which the step tests all pairs directly instead of building the tree (env PB_BRUTE_FORCE_MAX)
     bool queryTreeValid = false;        // tree + world poses match the current bounds / poses (scene queries)
     int* queryOut = nullptr; int queryCap = 0;   // device result buffer of the scene queries (queries.cu)

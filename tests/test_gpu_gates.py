@@ -185,3 +185,34 @@ def test_free_run_bodies_stay_in_the_bin(maker):
             P = ctx.get_state()[0]
             assert np.isfinite(P).all() and P[:, 1].min() > -0.25, (k, float(P[:, 1].min()))
     ctx.close()
+
+
+def test_three_gates_all_pairs_broadphase_on_a_big_batch():
+    """1500 ragdoll scenes side by side (18 k colliders, past the 8192 up to which the step always tests all pairs): the tile statistics of
+    the first step (tree + probe) show that every tile of 128 consecutive colliders meets a handful of tiles, and from the second step on the
+    all-pairs kernel replaces Morton sort + tree.  Same pair sets, manifolds and solves as the oracle throughout."""
+    from physecs_b200.capi import Context
+    d = S.ragdolls(1500)
+    s = parity.run_gates(d, steps=8, bulk=True)
+    assert s["steps"] == 8 and s["worst_manifold"] <= parity.TOL
+    ctx = Context(d)
+    kinds = []
+    for _ in range(4):
+        ctx.step(); ctx.sync()
+        kinds.append(ctx.broadphase_info())
+    ctx.close()
+    assert not kinds[0]["all_pairs"] and kinds[0]["tiles"] > 64 and 0 < kinds[0]["tile_hits"] <= 12 * kinds[0]["tiles"], kinds
+    assert all(k["all_pairs"] for k in kinds[1:]), kinds
+
+
+def test_a_pile_keeps_the_tree():
+    """20 000 bodies in one bin: consecutive colliders are NOT neighbours for long (the bodies mix), every tile meets most tiles, the tree stays"""
+    from physecs_b200.capi import Context
+    d = S.mixed_bin(20000)
+    ctx = Context(d, max_pairs=64 * d.n + 4096, max_manifolds=16 * d.n + 4096)
+    for _ in range(90):
+        ctx.step()
+    ctx.sync()
+    info = ctx.broadphase_info()
+    ctx.close()
+    assert not info["all_pairs"] and info["tile_hits"] > 12 * info["tiles"], info

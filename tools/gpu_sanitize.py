@@ -30,6 +30,7 @@ run("big shapes on a fine mesh (mesh spill kernel)", S.big_on_fine_mesh(cells=40
 run("degenerate convex pairs (GJK / EPA spill kernel)", S.degenerate_convex(), 3)
 run("convex pile, deterministic colouring", S.convex_pile(300, mix_prims=True), 30, PB_DETERMINISTIC=1)
 run("joint zoo + overflow bucket", S.joint_star(12), 10)
+run("800 ragdoll scenes: tree + tile probe on the first step, all-pairs kernel with tile culling from the second", S.ragdolls(800), 4)
 run("pyramid as one thread-block cluster (hardware cluster barrier)", S.pyramid(60), 4, PB_ISLANDS=0, PB_FUSED=1)
 run("mixed bin, small and big islands in one step (per-CTA sweeps + device-wide colours)", S.mixed_bin(2500, spacing=0.8), 30, PB_ISLAND_LOCAL_MAX=40, PB_FUSED=0, PB_ISLANDS=1)
 
