@@ -263,8 +263,8 @@ int pb_collider_ids(pb_ctx* ctx, int n, const int* cols, int* out_entity, int* o
  * the mode.  0 = off, 1 = on, 2 = auto (default: on while at least half of the constraints sit in small islands).
  * pb_get_island_stats: {on in the last step, constraints in small islands, constraints in all islands} of the last step that looked. */
 int pb_set_islands(pb_ctx* ctx, int mode);
-/* Which broadphase the last enqueued step took: out3 = {1 = all pairs through shared-memory tiles / 0 = tree, tile pairs that met in
- * the last step that looked (-1: none yet), tiles}.  Up to 8192 colliders the step always tests all pairs; up to 131 072 it does when
+/* Which broadphase the last enqueued step took: out3 = {1 = all pairs through shared-memory tiles / 0 = tree, (group of 32
+ * consecutive colliders, tile of 128) pairs whose boxes met in the last step that looked (-1: none yet), tiles}.  Up to 8192 colliders the step always tests all pairs; up to 131 072 it does when
  * colliders that were created together lie together (a batch of scenes side by side: every tile of 128 consecutive colliders meets a
  * handful of tiles), judged from the previous step's tile statistics; otherwise the LBVH.  Same pair set either way. */
 int pb_get_broadphase_info(pb_ctx* ctx, int* out3);

@@ -464,14 +464,19 @@ __global__ void __launch_bounds__(BF_TILE) k_tile_bounds(int n, const int* __res
     }
 }
 
+// 32 queries per CTA, four threads per query: thread (q = lane, part = warp) tests query q against candidates [32 part, 32 part + 32) of
+// every staged tile.  (128 queries per CTA with one thread walking all 128 candidates left each warp a stream of thousands of dependent
+// instructions at ~20 cycles apiece and ~11 warps per SM: ncu showed the kernel bound by exactly that, whatever the culling did.)
+#define BF_QUERIES 32
 __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPerSlice, const int* __restrict__ colFlags, const int* __restrict__ colRow,
                                                              const int* __restrict__ rowEntity, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
                                                              const float4* __restrict__ tileMin, const float4* __restrict__ tileMax,
                                                              int2* __restrict__ pairs, int* __restrict__ counters, int maxPairs) {
     __shared__ float4 smn[BF_TILE], smx[BF_TILE];
     __shared__ int sflag[BF_TILE], srow[BF_TILE];
-    __shared__ float qred[BF_TILE / 32][6];
-    const int a = blockIdx.x * BF_TILE + threadIdx.x;
+    __shared__ unsigned int sHit[BF_TILE / 32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int a = blockIdx.x * BF_QUERIES + lane;
     bool active = false;
     V3 amn = mk3(FLT_MAX), amx = mk3(-FLT_MAX);       // empty box: meets nothing
     int rowA = -1;
@@ -479,20 +484,16 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
         active = (colFlags[a] & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC);
         if (active) { amn = mk3(aabbMin[a]); amx = mk3(aabbMax[a]); rowA = colRow[a]; }
     }
-    // union box of this CTA's queries
+    // union box of the CTA's 32 queries (every warp holds the same 32: a warp reduction is the CTA's)
     V3 qmn = amn, qmx = amx;
     for (int d = 16; d > 0; d >>= 1) {
         qmn.x = fminf(qmn.x, __shfl_xor_sync(0xffffffffu, qmn.x, d)); qmn.y = fminf(qmn.y, __shfl_xor_sync(0xffffffffu, qmn.y, d)); qmn.z = fminf(qmn.z, __shfl_xor_sync(0xffffffffu, qmn.z, d));
         qmx.x = fmaxf(qmx.x, __shfl_xor_sync(0xffffffffu, qmx.x, d)); qmx.y = fmaxf(qmx.y, __shfl_xor_sync(0xffffffffu, qmx.y, d)); qmx.z = fmaxf(qmx.z, __shfl_xor_sync(0xffffffffu, qmx.z, d));
     }
-    if ((threadIdx.x & 31) == 0) { float* r = qred[threadIdx.x >> 5]; r[0] = qmn.x; r[1] = qmn.y; r[2] = qmn.z; r[3] = qmx.x; r[4] = qmx.y; r[5] = qmx.z; }
-    __syncthreads();
-    for (int k = 0; k < BF_TILE / 32; ++k) { qmn = vmin(qmn, mk3(qred[k][0], qred[k][1], qred[k][2])); qmx = vmax(qmx, mk3(qred[k][3], qred[k][4], qred[k][5])); }
     if (qmn.x > qmx.x) return;                 // no querying collider in this CTA (uniform)
-    // Tiles in reach of this CTA's queries: 128 tile boxes are tested at a time, one per thread (the boxes of a batch of thousands of
-    // scenes -- hundreds of tiles -- cost a few coalesced loads instead of one dependent round trip per tile), then the CTA walks the
-    // hits in tile order.
-    __shared__ unsigned int sHit[BF_TILE / 32];
+    // Tiles (128 consecutive colliders) in reach: 128 tile boxes at a time, one per thread, against the union box -- the boxes of a
+    // batch of thousands of scenes cost a few coalesced loads instead of one dependent round trip per tile; the CTA then walks the hits
+    // in tile order, and a query skips a tile its own box misses.
     const int firstTile = blockIdx.y * tilesPerSlice;
     const int nTiles = (n + BF_TILE - 1) / BF_TILE;
     const int lastTile = min(firstTile + tilesPerSlice, nTiles);
@@ -501,11 +502,12 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
         const int tt = chunk + threadIdx.x;
         const bool reach = tt < lastTile && overlaps(qmn, qmx, tileMin[tt], tileMax[tt]);
         const unsigned int bal = __ballot_sync(0xffffffffu, reach);
-        if ((threadIdx.x & 31) == 0) sHit[threadIdx.x >> 5] = bal;
+        if (lane == 0) sHit[part] = bal;
         __syncthreads();
         unsigned int masks[BF_TILE / 32];
         for (int w = 0; w < BF_TILE / 32; ++w) masks[w] = sHit[w];
         __syncthreads();
+#pragma unroll
         for (int w = 0; w < BF_TILE / 32; ++w) {
             unsigned int tm = masks[w];
             while (tm) {                            // uniform across the CTA
@@ -518,24 +520,21 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
                 if (b0 < n) { smn[threadIdx.x] = aabbMin[b0]; smx[threadIdx.x] = aabbMax[b0]; sflag[threadIdx.x] = colFlags[b0]; srow[threadIdx.x] = colRow[b0]; }
                 else sflag[threadIdx.x] = 0;
                 __syncthreads();
-                // hits of this thread in this tile as a 128-bit mask; the pairs are appended afterwards with ONE atomic per warp and tile (a
-                // batch of 512 little scenes emits ~10 k pairs per step: one atomic per pair on the one counter was most of this kernel's time)
-                unsigned int hit[BF_TILE / 32] = {0, 0, 0, 0};
+                // this thread's hits among its 32 candidates of the tile (branch-free, unrolled: the shared-memory loads of a run of
+                // iterations go out together); the pairs are appended afterwards with ONE atomic per warp and tile
+                unsigned int hit = 0;
                 if (active && overlaps(amn, amx, tmn, tmx)) {
-                    const int cnt = min(BF_TILE, n - base);
-                    for (int j = 0; j < cnt; ++j) {
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) {
+                        const int j = 32 * part + k;
                         const int fb = sflag[j];
-                        if (!(fb & COLF_ENABLE)) continue;
-                        const int b = base + j;
-                        if ((fb & COLF_DYNAMIC) && b <= a) continue;      // a pair of two querying colliders is emitted by the lower index
-                        if (srow[j] == rowA) continue;                    // same entity (Physecs.cpp:145)
-                        if (!overlaps(amn, amx, smn[j], smx[j])) continue;
-                        hit[j >> 5] |= 1u << (j & 31);
+                        // enabled; a pair of two querying colliders is emitted by the lower index; not the same entity (Physecs.cpp:145)
+                        const bool ok = (fb & COLF_ENABLE) && !((fb & COLF_DYNAMIC) && base + j <= a) && srow[j] != rowA && overlaps(amn, amx, smn[j], smx[j]);
+                        hit |= (ok ? 1u : 0u) << k;
                     }
                 }
                 {
-                    const int mine = __popc(hit[0]) + __popc(hit[1]) + __popc(hit[2]) + __popc(hit[3]);
-                    const int lane = threadIdx.x & 31;
+                    const int mine = __popc(hit);
                     int inc = mine;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
@@ -547,18 +546,16 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
                         int slot = wbase + inc - mine;
                         if (mine) {
                             const unsigned int ea = (unsigned int)rowEntity[rowA];
-                            for (int hw = 0; hw < BF_TILE / 32; ++hw) {
-                                unsigned int m = hit[hw];
-                                while (m) {
-                                    const int j = 32 * hw + __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const int b = base + j;
-                                    if (slot < maxPairs) {
-                                        const unsigned int eb = (unsigned int)rowEntity[srow[j]];
-                                        pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
-                                    } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
-                                    ++slot;
-                                }
+                            unsigned int m = hit;
+                            while (m) {
+                                const int j = 32 * part + __ffs(m) - 1;
+                                m &= m - 1;
+                                const int b = base + j;
+                                if (slot < maxPairs) {
+                                    const unsigned int eb = (unsigned int)rowEntity[srow[j]];
+                                    pairs[slot] = (ea < eb) ? make_int2(a, b) : make_int2(b, a);   // lower entity id first (Physecs.cpp:158-168)
+                                } else { atomicOr(&counters[CNT_STATUS], PB_ECAPACITY); atomicOr(&counters[CNT_CAUSE], PB_CAUSE_PAIRS); }
+                                ++slot;
                             }
                         }
                     }
@@ -582,7 +579,7 @@ __global__ void __launch_bounds__(BF_TILE) k_tile_probe(int nTiles, const float4
         if (!(qmx.x < a.x || qmn.x > b.x) && !(qmx.y < a.y || qmn.y > b.y) && !(qmx.z < a.z || qmn.z > b.z)) ++met;
     }
     for (int d = 16; d > 0; d >>= 1) met += __shfl_xor_sync(0xffffffffu, met, d);
-    if ((threadIdx.x & 31) == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], met);
+    if ((threadIdx.x & 31) == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], 4 * met);      // in the all-pairs kernel's unit: (group of 32 queries, tile) pairs
 }
 
 // Morton sort + LBVH build + refit over the current collider bounds (n >= 2).  Shared by the step's pair search and the
@@ -616,19 +613,20 @@ int pb_broadphase(pb_ctx* ctx) {
     ctx->stepBrute = false; ctx->pendingTiles = 0;
     if (n < 2) return PB_OK;
     const int tiles = (n + BF_TILE - 1) / BF_TILE;
-    // Mid-sized scenes: all pairs when creation order is spatially coherent -- a tile meets a handful of tiles (a batch of scenes side
-    // by side; the statistics are the previous step's) --, the tree otherwise.  The tree's ~25 dependent launches cost ~0.2 ms however
+    // Mid-sized scenes: all pairs when creation order is spatially coherent -- a group of 32 consecutive colliders meets a handful of
+    // tiles (a batch of scenes side by side; the statistics are the previous step's) --, the tree otherwise.  The tree's ~25 dependent launches cost ~0.2 ms however
     // small the scene; the all-pairs kernel of 4096 ragdoll scenes walks ~3 tiles per tile.
     const bool midSized = n > ctx->bruteForceMax && n <= ctx->bruteForceBigMax;
-    const bool coherent = midSized && ctx->lastTileHits >= 0 && ctx->lastTiles == tiles && (long long)ctx->lastTileHits <= 12ll * tiles;
+    const bool coherent = midSized && ctx->lastTileHits >= 0 && ctx->lastTiles == tiles && (long long)ctx->lastTileHits <= 24ll * tiles;     // <= 6 tiles in reach of a group of 32 queries, on average
     if (n <= ctx->bruteForceMax || coherent) {
-        int slices = (4 * ctx->numSMs + tiles - 1) / tiles;        // enough CTAs to fill the device a few times over
+        const int groups = (n + BF_QUERIES - 1) / BF_QUERIES;     // CTAs of 32 queries
+        int slices = (4 * ctx->numSMs + groups - 1) / groups;      // enough CTAs to fill the device a few times over
         if (slices > tiles) slices = tiles;
         if (slices < 1) slices = 1;
         const int tilesPerSlice = (tiles + slices - 1) / slices;
         // tile boxes live in the (otherwise idle) tree node arrays: one entry of nodeMin / nodeMax per tile
         ++ctx->launches, k_tile_bounds<<<tiles, BF_TILE, 0, ctx->stream>>>(n, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, ctx->nodeMin, ctx->nodeMax);
-        ++ctx->launches, k_pairs_bruteforce<<<dim3(tiles, slices), BF_TILE, 0, ctx->stream>>>(n, tilesPerSlice, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
+        ++ctx->launches, k_pairs_bruteforce<<<dim3(groups, slices), BF_TILE, 0, ctx->stream>>>(n, tilesPerSlice, ctx->colFlags, ctx->colRow, ctx->rowEntity, ctx->aabbMin, ctx->aabbMax,
                                                                                           ctx->nodeMin, ctx->nodeMax, (int2*)ctx->pairs, ctx->counters, ctx->caps.max_pairs);
         ctx->stepBrute = true; ctx->pendingTiles = tiles;
         PB_CUDA(ctx, cudaGetLastError());
