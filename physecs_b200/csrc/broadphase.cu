@@ -567,19 +567,25 @@ __global__ void __launch_bounds__(BF_TILE) k_pairs_bruteforce(int n, int tilesPe
     if (threadIdx.x == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], met);
 }
 
-// How many (query tile, collider tile) pairs meet: what the all-pairs kernel would have to walk.  Run beside the tree broadphase
-// for mid-sized scenes, so the host can tell (one step late) a batch of scenes laid out side by side -- a handful of tiles in
-// reach of every tile: all-pairs wins -- from a pile, where every tile meets most others.
-__global__ void __launch_bounds__(BF_TILE) k_tile_probe(int nTiles, const float4* __restrict__ tileMin, const float4* __restrict__ tileMax, int* __restrict__ counters) {
-    const int q = blockIdx.x;
-    const float4 qmn = tileMin[q], qmx = tileMax[q];
-    int met = 0;
-    for (int t = threadIdx.x; t < nTiles; t += blockDim.x) {
-        const float4 a = tileMin[t], b = tileMax[t];
-        if (!(qmx.x < a.x || qmn.x > b.x) && !(qmx.y < a.y || qmn.y > b.y) && !(qmx.z < a.z || qmn.z > b.z)) ++met;
+// How many (group of 32 queries, tile) pairs meet -- what the all-pairs kernel would have to walk, counted the way it counts: the union
+// box of a group's querying colliders against every tile box.  Run beside the tree broadphase for mid-sized scenes, so the host can
+// tell (one step late) a batch of scenes laid out side by side -- a handful of tiles in reach of every group: all-pairs wins -- from a
+// pile, where every group meets most tiles.
+__global__ void __launch_bounds__(BF_TILE) k_tile_probe(int n, int nTiles, const int* __restrict__ colFlags, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                                                       const float4* __restrict__ tileMin, const float4* __restrict__ tileMax, int* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * BF_TILE + threadIdx.x;
+    V3 qmn = mk3(FLT_MAX), qmx = mk3(-FLT_MAX);
+    if (a < n && (colFlags[a] & (COLF_ENABLE | COLF_DYNAMIC)) == (COLF_ENABLE | COLF_DYNAMIC)) { qmn = mk3(aabbMin[a]); qmx = mk3(aabbMax[a]); }
+    for (int d = 16; d > 0; d >>= 1) {
+        qmn.x = fminf(qmn.x, __shfl_xor_sync(0xffffffffu, qmn.x, d)); qmn.y = fminf(qmn.y, __shfl_xor_sync(0xffffffffu, qmn.y, d)); qmn.z = fminf(qmn.z, __shfl_xor_sync(0xffffffffu, qmn.z, d));
+        qmx.x = fmaxf(qmx.x, __shfl_xor_sync(0xffffffffu, qmx.x, d)); qmx.y = fmaxf(qmx.y, __shfl_xor_sync(0xffffffffu, qmx.y, d)); qmx.z = fmaxf(qmx.z, __shfl_xor_sync(0xffffffffu, qmx.z, d));
     }
+    if (qmn.x > qmx.x) return;                 // no querying collider in this group (warp-uniform)
+    int met = 0;
+    for (int t = lane; t < nTiles; t += 32) if (overlaps(qmn, qmx, tileMin[t], tileMax[t])) ++met;
     for (int d = 16; d > 0; d >>= 1) met += __shfl_xor_sync(0xffffffffu, met, d);
-    if ((threadIdx.x & 31) == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], 4 * met);      // in the all-pairs kernel's unit: (group of 32 queries, tile) pairs
+    if (lane == 0 && met) atomicAdd(&counters[CNT_TILE_HITS], met);
 }
 
 // Morton sort + LBVH build + refit over the current collider bounds (n >= 2).  Shared by the step's pair search and the
@@ -637,7 +643,7 @@ int pb_broadphase(pb_ctx* ctx) {
         float4* tb = (float4*)ctx->pairs;
         if ((size_t)ctx->caps.max_pairs * sizeof(int2) >= 2 * (size_t)tiles * sizeof(float4)) {
             ++ctx->launches, k_tile_bounds<<<tiles, BF_TILE, 0, ctx->stream>>>(n, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, tb, tb + tiles);
-            ++ctx->launches, k_tile_probe<<<tiles, BF_TILE, 0, ctx->stream>>>(tiles, tb, tb + tiles, ctx->counters);
+            ++ctx->launches, k_tile_probe<<<tiles, BF_TILE, 0, ctx->stream>>>(n, tiles, ctx->colFlags, ctx->aabbMin, ctx->aabbMax, tb, tb + tiles, ctx->counters);
             ctx->pendingTiles = tiles;
         }
     }
