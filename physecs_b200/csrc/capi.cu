@@ -217,6 +217,8 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->readStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB_ECUDA; }
+    for (cudaEvent_t* e : { &ctx->evFork, &ctx->evColour, &ctx->evGroups, &ctx->evJoints }) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evPacked, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evMainAtSet, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evVelReady, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evPoseReady, cudaEventDisableTiming);
@@ -258,6 +260,7 @@ int pb_ctx_create(int device, const pb_caps* caps, pb_ctx** out) {
     if (const char* e = getenv("PB_ISLANDS")) ctx->islandsMode = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_MAX")) ctx->bruteForceMax = atoi(e);
     if (const char* e = getenv("PB_BRUTE_FORCE_BIG_MAX")) ctx->bruteForceBigMax = atoi(e);
+    if (const char* e = getenv("PB_BUILD_FORK")) ctx->buildFork = atoi(e);
     if (const char* e = getenv("PB_FUSED")) ctx->fusedMode = atoi(e);
     if (const char* e = getenv("PB_SORT_COOP")) ctx->sortCoopMode = atoi(e);
     if (const char* e = getenv("PB_BIG_LIST")) ctx->bigListMode = atoi(e);
@@ -338,6 +341,8 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->readStream) { cudaStreamSynchronize(ctx->readStream); cudaStreamDestroy(ctx->readStream); }
+    if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
+    for (cudaEvent_t e : { ctx->evFork, ctx->evColour, ctx->evGroups, ctx->evJoints }) if (e) cudaEventDestroy(e);
     if (ctx->evPacked) cudaEventDestroy(ctx->evPacked);
     if (ctx->stageRead) cudaFree(ctx->stageRead);
     pb_joints_free(ctx);

@@ -441,6 +441,18 @@ int pb_contact_build(pb_ctx* ctx) {
         for (int i = 0; i < k; ++i) most = std::max(most, (size_t)L.n[i]);
         ++ctx->launches, k_build_clear<<<std::max(1, std::min(ctx->numSMs * 4, (int)((most + 1023) / 1024))), 256, 0, ctx->stream>>>(L);
     }
+    // Two independent strands meet in the manifold order: the COLOURS (k_color) and the GROUPS (island search).  With islands on they run
+    // side by side -- the colouring on a second stream behind the clear kernel -- and so do, further down, the joint lists (they need the
+    // groups only) and the ordering of the manifolds.  A step of a small scene is a chain of few-microsecond kernels: what runs beside
+    // another is off that chain (512 ragdoll scenes: ~30 us of 420).
+    struct StreamSwap {        // launches of the enclosed calls go to the side stream (everything here launches on ctx->stream)
+        pb_ctx* c; cudaStream_t keep;
+        StreamSwap(pb_ctx* c_, cudaStream_t s) : c(c_), keep(c_->stream) { c->stream = s; }
+        ~StreamSwap() { c->stream = keep; }
+    };
+    const bool fork = ctx->islandsOn && !ctx->deterministic && ctx->buildFork && ctx->sideStream && G <= 4000;      // (G: the joint lists' scan stays a one-CTA scan without scratch)
+    cudaStream_t mainStream = ctx->stream;
+    if (fork) { PB_CUDA(ctx, cudaEventRecord(ctx->evFork, mainStream)); PB_CUDA(ctx, cudaStreamWaitEvent(ctx->sideStream, ctx->evFork, 0)); }
     if (ctx->deterministic) {
         if (!ctx->jpBest) {
             if ((rc = pb_alloc(ctx, &ctx->jpBest, (size_t)ctx->caps.max_bodies)) || (rc = pb_alloc(ctx, &ctx->jpScratch, 64))) return rc;
@@ -455,13 +467,24 @@ int pb_contact_build(pb_ctx* ctx) {
         void* args[] = { &mKey, &counters, &maxM, &colRow, &nDyn, &kin, &mask, &best, &sk, &bar, &rem };
         ++ctx->launches;
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_color_jp, dim3(ctx->jpGrid), dim3(256), args, 0, ctx->stream));
-    } else
-    ++ctx->launches, k_color<<<blocks, 256, 0, ctx->stream>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask,
-                                             ctx->mSortKeyA);
-    ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->islandsOn ? nullptr : ctx->keyStart + (size_t)G * PB_KEY_COLORS);
+        ++ctx->launches, k_color_starts<<<1, 32, 0, ctx->stream>>>(ctx->counters, ctx->islandsOn ? nullptr : ctx->keyStart + (size_t)G * PB_KEY_COLORS);
+    } else {
+        cudaStream_t cs = fork ? ctx->sideStream : mainStream;
+        ++ctx->launches, k_color<<<blocks, 256, 0, cs>>>(ctx->mKey, ctx->counters, maxM, ctx->colRow, ctx->nDyn, ctx->kinematic, ctx->colorMask, ctx->mSortKeyA);
+        ++ctx->launches, k_color_starts<<<1, 32, 0, cs>>>(ctx->counters, ctx->islandsOn ? nullptr : ctx->keyStart + (size_t)G * PB_KEY_COLORS);
+        if (fork) PB_CUDA(ctx, cudaEventRecord(ctx->evColour, cs));
+    }
     if (ctx->islandsOn) {
         if ((rc = pb_islands_build(ctx))) return rc;
-        if ((rc = pb_joint_lists(ctx))) return rc;
+        if (fork && ctx->nJoints) {
+            // the joint lists need the groups and nothing else: side stream, joined in front of the solver (end of this function)
+            PB_CUDA(ctx, cudaEventRecord(ctx->evGroups, mainStream));
+            PB_CUDA(ctx, cudaStreamWaitEvent(ctx->sideStream, ctx->evGroups, 0));
+            { StreamSwap sw(ctx, ctx->sideStream); rc = pb_joint_lists(ctx); }
+            if (rc) return rc;
+            PB_CUDA(ctx, cudaEventRecord(ctx->evJoints, ctx->sideStream));
+        } else if ((rc = pb_joint_lists(ctx))) return rc;
+        if (fork) PB_CUDA(ctx, cudaStreamWaitEvent(mainStream, ctx->evColour, 0));      // the manifold keys below need the colours
     }
     // Solve order = a counting sort by (group, colour, single | multi): the run table holds the first slot of every key (scanned key
     // histogram), so one scatter pass places every manifold (slot = run start + arrival rank, one atomic per distinct key per warp).
@@ -497,6 +520,7 @@ int pb_contact_build(pb_ctx* ctx) {
         ctx->cHead, ctx->cBodies, ctx->cRowsT, ctx->cNormal, ctx->cSoft, ctx->cNpBuf[cur], ctx->pR0T[cur], ctx->pR1,
         (ctx->cacheValid && ctx->anyRestitution) ? ctx->cacheTag[prev] : nullptr, ctx->cacheVal[prev], ctx->cPointOfsBuf[prev], ctx->cNpBuf[prev], ctx->pR0T[prev],
         ctx->cacheTag[cur], ctx->cacheVal[cur], ctx->cacheSize - 1);
+    if (fork && ctx->nJoints) PB_CUDA(ctx, cudaStreamWaitEvent(mainStream, ctx->evJoints, 0));
     PB_CUDA(ctx, cudaGetLastError());
     return PB_OK;
 }

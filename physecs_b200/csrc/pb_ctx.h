@@ -103,6 +103,8 @@ struct pb_ctx {
     // read-back of pb_get_state_begin: packed on the main stream into its own staging buffer, copied out on the READ stream, so the copies
     // of step k run beside the upload and the kernels of step k + 1 (pb_get_state_wait is the only thing that waits for them)
     cudaStream_t readStream = nullptr; cudaEvent_t evPacked = nullptr; float* stageRead = nullptr; size_t stageReadBytes = 0;
+    // build stage: the colouring runs beside the island search, the joint lists beside the manifold ordering (contacts.cu pb_contact_build)
+    cudaStream_t sideStream = nullptr; cudaEvent_t evFork = nullptr, evColour = nullptr, evGroups = nullptr, evJoints = nullptr; int buildFork = 1;   // env PB_BUILD_FORK=0: one stream
     cudaStream_t copyStream = nullptr; cudaEvent_t evMainAtSet = nullptr, evVelReady = nullptr, evPoseReady = nullptr; bool velPending = false, posePending = false;
     float* stageVel = nullptr; size_t stageVelBytes = 0;   // staging of the copy stream: 13 floats per body (pos 3, quat 4, vel 3, angvel 3)
 
