@@ -10,8 +10,11 @@
 // <= 256 faces, <= 64 horizon edges, clip polygons of <= 24 points: `LimFast`).  The reference's containers are unbounded
 // (std::vector polytope, EPA.h:22-124; 128-point clip buffers, Clipping.cpp:6): a pair that outgrows the fast limits reports the
 // cause through `ovf` (no result is stored) and is redone by a spill kernel with `LimSpill`: the polytope in global-memory scratch
-// (8192 faces, 8192 horizon edges: EPA stops after 100 insertions, EPA.h:178, and a polytope that degenerates -- inconsistent
-// visibility, unmatched horizon edges -- has been seen past 2048 faces in a 250 k-body soak), 128-point polygons.  Same routines, same arithmetic -- only the container bounds differ.
+// (2048 faces, 1024 horizon edges), 128-point polygons.  EPA stops after 100 insertions (EPA.h:178); a polytope that DEGENERATES --
+// inconsistent visibility, unmatched horizon edges: seen once in a 250 k-body soak -- can pass even that.  The bound stays: the
+// insertion is O(faces x horizon edges) on one thread, and with 8192 / 8192 one such pair held a step for 1.9 s (the reference grinds
+// through the same work on a CPU core).  Past the bound the pair keeps the manifold of the truncated polytope for that step and
+// PB_CAUSE_SPILL_SCRATCH is set.  Same routines, same arithmetic -- only the container bounds differ.
 #pragma once
 #include "np_clip.cuh"
 #include "pb_ctx.h"
@@ -173,7 +176,7 @@ struct EpaT {
 };
 // container bounds of the per-pair routines: the per-thread fast path and the spill kernels' global-memory scratch
 struct LimFast  { typedef EpaT<256, 64> Epa;    static constexpr int POLY = 24; };
-struct LimSpill { typedef EpaT<8192, 8192> Epa; static constexpr int POLY = 128; };   // POLY == the reference's own bound (Clipping.cpp:6)
+struct LimSpill { typedef EpaT<2048, 1024> Epa; static constexpr int POLY = 128; };   // POLY == the reference's own bound (Clipping.cpp:6)
 typedef LimFast::Epa Epa;
 
 template <class E>

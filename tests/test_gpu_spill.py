@@ -97,7 +97,7 @@ def test_soak(name, maker, steps, seed):
         assert np.isfinite(P).all() and np.isfinite(V).all() and np.isfinite(Q).all() and np.isfinite(W).all()
     finally:
         ctx.close()
-    # (PB_CAUSE_SPILL_SCRATCH -- a degenerate EPA polytope past even the spill kernel's 8192 faces -- is reported, not fatal: the pair's
+    # (PB_CAUSE_SPILL_SCRATCH -- a degenerate EPA polytope past even the spill kernel's 2048 faces -- is reported, not fatal: the pair's
     # manifold comes from the truncated polytope for that step; every other bound is)
     assert not cause & (FATAL_CAUSES & ~capi.PB_CAUSE_SPILL_SCRATCH), hex(cause)
     print(name, hex(seed), "cause", hex(cause), "max spilled pairs per step", spilled)
