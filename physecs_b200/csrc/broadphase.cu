@@ -616,6 +616,7 @@ int pb_build_tree(pb_ctx* ctx, bool forStep) {
 // n == 2..: general path.  n < 2: no pairs.
 int pb_broadphase(pb_ctx* ctx) {
     int n = ctx->nCol;
+    const bool wasBrute = ctx->stepBrute;
     ctx->stepBrute = false; ctx->pendingTiles = 0;
     if (n < 2) return PB_OK;
     const int tiles = (n + BF_TILE - 1) / BF_TILE;
@@ -623,7 +624,7 @@ int pb_broadphase(pb_ctx* ctx) {
     // tiles (a batch of scenes side by side; the statistics are the previous step's) --, the tree otherwise.  The tree's ~25 dependent launches cost ~0.2 ms however
     // small the scene; the all-pairs kernel of 4096 ragdoll scenes walks ~3 tiles per tile.
     const bool midSized = n > ctx->bruteForceMax && n <= ctx->bruteForceBigMax;
-    const bool coherent = midSized && ctx->lastTileHits >= 0 && ctx->lastTiles == tiles && (long long)ctx->lastTileHits <= 24ll * tiles;     // <= 6 tiles in reach of a group of 32 queries, on average
+    const bool coherent = midSized && ctx->lastTileHits >= 0 && ctx->lastTiles == tiles && (long long)ctx->lastTileHits <= (wasBrute ? 32ll : 24ll) * tiles;     // <= 6 tiles in reach of a group of 32 queries, on average (8 to stay: no flapping at the threshold)
     if (n <= ctx->bruteForceMax || coherent) {
         const int groups = (n + BF_QUERIES - 1) / BF_QUERIES;     // CTAs of 32 queries
         int slices = (4 * ctx->numSMs + groups - 1) / groups;      // enough CTAs to fill the device a few times over
