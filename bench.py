@@ -660,6 +660,28 @@ def main():
                 walls.append(time.perf_counter() - tt)
             out["e2e_scene"]["device_authoritative"] = {"ms_per_step": float(np.mean(walls)) * 1e3, "p95_ms_per_step": float(np.percentile(walls, 95) * 1e3),
                                                         "value": sd.n_dynamic / float(np.mean(walls)), "unit": UNIT}
+            # a structural edit of the live registry: ONE body spawned, then destroyed again -- the cost of the simulate() call that
+            # follows (the device scene description is brought up to date inside it: `prepare_ms`, Scene::getLastStepStats)
+            try:
+                hs.set_sync_mode(False)
+                hs.simulate()
+                one = S.dynamic_only(S.mixed_bin(1, spacing=0.8, seed=0x99), lift=(0.0, 60.0, 0.0))
+                edit = {}
+                for rep in range(2):
+                    tt = time.perf_counter()
+                    first_new = hs.add_entities(one)
+                    hs.simulate()
+                    edit.setdefault("spawn_step_ms", []).append((time.perf_counter() - tt) * 1e3)
+                    edit.setdefault("spawn_prepare_ms", []).append(hs.stats()["prepare_ms"])
+                    tt = time.perf_counter()
+                    hs.destroy_entity(first_new)
+                    hs.simulate()
+                    edit.setdefault("destroy_step_ms", []).append((time.perf_counter() - tt) * 1e3)
+                    edit.setdefault("destroy_prepare_ms", []).append(hs.stats()["prepare_ms"])
+                out["e2e_scene"]["structural_edit"] = dict({k: float(min(v)) for k, v in edit.items()},
+                                                           note="one body spawned into / destroyed in the live 1 M-entity registry; the step that follows, best of 2")
+            except Exception as e:
+                out["e2e_scene"]["structural_edit"] = {"unavailable": str(e)[:200]}
             hs.close()
         except Exception as e:
             out["e2e_scene"] = {"unavailable": str(e)[:200]}

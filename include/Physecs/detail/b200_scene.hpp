@@ -129,7 +129,7 @@ public:
     // to the registry before the step has succeeded).
     void setArenaCapacity(int maxPairs, int maxManifolds);
     pb_ctx* nativeContext();                 // the C-ABI context (parity taps: pb_get_pairs / pb_get_manifolds / pb_get_bounds ...)
-    struct StepStats { int pairs, manifolds, points, colors, triggers; float deviceMs; double gatherMs, scatterMs, totalMs; };
+    struct StepStats { int pairs, manifolds, points, colors, triggers; float deviceMs; double gatherMs, scatterMs, totalMs, prepareMs; };   // prepareMs: bringing the device scene description up to date (structural edits, joints, filters) -- part of totalMs
     StepStats getLastStepStats() const;
 };
 

@@ -164,6 +164,15 @@ class RefScene:
     def destroy_entity(self, e):
         self.lib.ph_destroy_entity(self.h, int(e))
 
+    def add_collider(self, e, lpos, lquat, ctype, params, mesh=-1, material=(0.4, 0.2, 0.0), flags=2, data=0):
+        """Scene::addCollider on a live entity (Physecs.cpp:738-751; flags: bit 0 trigger, bit 1 enableSimulation)."""
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        self.lib.ph_add_collider(self.h, int(e), _p(_f(lpos)), _p(_f(lquat)), int(ctype), _p(prm), int(mesh), _p(_f(material)), int(flags), int(data))
+
+    def clear_colliders(self, e):
+        """Scene::clearColliders (Physecs.cpp:725-736)."""
+        self.lib.ph_clear_colliders(self.h, int(e))
+
     def add_joint(self, t, e0, a0p, a0q, e1, a1p, a1q, prm):
         return self.lib.ph_add_joint(self.h, int(t), int(e0), _p(_f(a0p)), _p(_f(a0q)), int(e1), _p(_f(a1p)), _p(_f(a1q)), _p(_f(prm)))
 

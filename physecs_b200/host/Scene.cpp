@@ -524,22 +524,30 @@ void Scene::prepareDevice() {
 
     // ---- (re)build the device scene description after structural changes -----------------------------------------------------
     auto rebuild = [&](bool growCaps) {
-        // bounds history of colliders that survive the re-upload (creation bounds have no margin, refreshed ones do: quirk Q6)
-        std::unordered_map<unsigned long long, std::array<float, 6>> keep;
-        if (S.ctx && !S.ctxFresh && !S.cols.empty()) {
-            std::vector<float> b((size_t)6 * S.cols.size());
-            S.check(pb_get_bounds(S.ctx, b.data()), "pb_get_bounds");
-            keep.reserve(S.cols.size() * 2);
-            for (size_t i = 0; i < S.cols.size(); ++i) {
-                unsigned long long k = colKey(S.cols[i].e, S.cols[i].idx);
-                if (S.freshCols.count(k)) continue;
-                std::array<float, 6> a;
-                std::memcpy(a.data(), &b[6 * i], sizeof(float) * 6);
-                keep.emplace(k, a);
-            }
-        }
+        // What the device holds now.  Colliders that survive the re-upload keep their bounds history (creation bounds have no margin,
+        // refreshed ones do: quirk Q6) and their contact-cache entries.  The colliders of an entity are contiguous in device order, so
+        // "where was (entity, index) before" is one flat table over entity indices (entity versions are compared through oldCols) --
+        // at 1 M colliders a hash map per lookup was most of a structural edit's cost.
         std::vector<Impl::ColRef> oldCols;
-        if (S.ctx && !S.ctxFresh) oldCols = S.cols;
+        std::vector<float> oldBounds;
+        std::vector<int> oldFirst;                  // entt::to_entity(e) -> first collider of e in oldCols, -1 = none
+        if (S.ctx && !S.ctxFresh && !S.cols.empty()) {
+            oldCols.swap(S.cols);
+            oldBounds.resize((size_t)6 * oldCols.size());
+            S.check(pb_get_bounds(S.ctx, oldBounds.data()), "pb_get_bounds");
+            size_t top = 0;
+            for (auto& c : oldCols) top = std::max(top, (size_t)entt::to_entity(c.e));
+            oldFirst.assign(top + 1, -1);
+            for (size_t i = oldCols.size(); i-- > 0;) oldFirst[(size_t)entt::to_entity(oldCols[i].e)] = (int)i;
+        }
+        auto oldIndexOf = [&](entt::entity e, int idx) -> int {
+            const size_t k = (size_t)entt::to_entity(e);
+            if (k >= oldFirst.size() || oldFirst[k] < 0) return -1;
+            const size_t i = (size_t)oldFirst[k] + (size_t)idx;
+            if (i >= oldCols.size() || oldCols[i].e != e || oldCols[i].idx != idx) return -1;
+            return (int)i;
+        };
+        bool carryCache = !oldCols.empty();
         const size_t nDyn = dynStore.size();
         S.rowEntity.clear();
         S.rowEntity.reserve(nDyn + colStore.size());
@@ -586,7 +594,7 @@ void Scene::prepareDevice() {
             S.caps = c;
             S.jointsDirty = S.pairsDirty = S.filterDirty = true;
             S.uploadedJoints.clear();
-            oldCols.clear();         // a new context starts with an empty contact cache
+            carryCache = false;      // a new context starts with an empty contact cache (the bounds history is carried over)
         }
 
         // meshes referenced by colliders
@@ -620,74 +628,70 @@ void Scene::prepareDevice() {
         std::vector<int> ent(rows);
         std::vector<float> pos((size_t)3 * rows), quat((size_t)4 * rows), vel((size_t)3 * nDyn), ang((size_t)3 * nDyn);
         S.kin.assign(nDyn, 0); S.invMass.assign(nDyn, 0.f); S.com.assign(3 * nDyn, 0.f); S.invI.assign(9 * nDyn, 0.f);
-        for (int r = 0; r < rows; ++r) {
-            auto e = S.rowEntity[r];
-            ent[r] = (int)entt::to_integral(e);
-            const TransformComponent& t = packedAt<TransformComponent>(trStore, S.rowTransformIdx[r]);
-            std::memcpy(&pos[3 * (size_t)r], &t.position, sizeof(float) * 3);
-            quat[4 * (size_t)r] = t.orientation.x; quat[4 * (size_t)r + 1] = t.orientation.y; quat[4 * (size_t)r + 2] = t.orientation.z; quat[4 * (size_t)r + 3] = t.orientation.w;
-            if (r < (int)nDyn) {
-                const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, (size_t)r);
-                S.kin[r] = d.isKinematic ? 1 : 0;
-                std::memcpy(&vel[3 * (size_t)r], &d.velocity, sizeof(float) * 3);
-                std::memcpy(&ang[3 * (size_t)r], &d.angularVelocity, sizeof(float) * 3);
-                S.invMass[r] = d.invMass;
-                std::memcpy(&S.com[3 * (size_t)r], &d.com, sizeof(float) * 3);
-                std::memcpy(&S.invI[9 * (size_t)r], &d.invInertiaTensor, sizeof(float) * 9);
+        S.workers.parallelFor((size_t)rows, [&](size_t rb, size_t re) {
+            for (size_t r = rb; r < re; ++r) {
+                auto e = S.rowEntity[r];
+                ent[r] = (int)entt::to_integral(e);
+                const TransformComponent& t = packedAt<TransformComponent>(trStore, S.rowTransformIdx[r]);
+                std::memcpy(&pos[3 * (size_t)r], &t.position, sizeof(float) * 3);
+                quat[4 * (size_t)r] = t.orientation.x; quat[4 * (size_t)r + 1] = t.orientation.y; quat[4 * (size_t)r + 2] = t.orientation.z; quat[4 * (size_t)r + 3] = t.orientation.w;
+                if (r < nDyn) {
+                    const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
+                    S.kin[r] = d.isKinematic ? 1 : 0;
+                    std::memcpy(&vel[3 * (size_t)r], &d.velocity, sizeof(float) * 3);
+                    std::memcpy(&ang[3 * (size_t)r], &d.angularVelocity, sizeof(float) * 3);
+                    S.invMass[r] = d.invMass;
+                    std::memcpy(&S.com[3 * (size_t)r], &d.com, sizeof(float) * 3);
+                    std::memcpy(&S.invI[9 * (size_t)r], &d.invInertiaTensor, sizeof(float) * 9);
+                }
             }
-        }
+        });
         S.check(pb_upload_bodies(S.ctx, (int)nDyn, S.nStatic, ent.data(), pos.data(), quat.data(), S.kin.data(), vel.data(), ang.data(),
                                  S.invMass.data(), S.com.data(), S.invI.data()), "pb_upload_bodies");
 
         // colliders
         std::vector<int> cRow(nCol), cIdx(nCol), cType(nCol), cMesh(nCol), cFlags(nCol), cData(nCol);
         std::vector<float> lp((size_t)3 * nCol), lq((size_t)4 * nCol), prm((size_t)4 * nCol, 0.f), mat((size_t)3 * nCol);
-        for (int i = 0; i < nCol; ++i) {
-            const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
-            cRow[i] = S.entityRow[(size_t)entt::to_entity(S.cols[i].e)];
-            cIdx[i] = S.cols[i].idx;
-            cType[i] = (int)c.geometry.type;
-            cMesh[i] = -1;
-            std::memcpy(&lp[3 * (size_t)i], &c.position, sizeof(float) * 3);
-            lq[4 * (size_t)i] = c.orientation.x; lq[4 * (size_t)i + 1] = c.orientation.y; lq[4 * (size_t)i + 2] = c.orientation.z; lq[4 * (size_t)i + 3] = c.orientation.w;
-            float* p = &prm[4 * (size_t)i];
-            switch (c.geometry.type) {
-                case SPHERE: p[0] = c.geometry.sphere.radius; break;
-                case CAPSULE: p[0] = c.geometry.capsule.halfHeight; p[1] = c.geometry.capsule.radius; break;
-                case BOX: std::memcpy(p, &c.geometry.box.halfExtents, sizeof(float) * 3); break;
-                case CONVEX_MESH: std::memcpy(p, &c.geometry.convex.scale, sizeof(float) * 3); cMesh[i] = S.convexHandle[c.geometry.convex.mesh]; break;
-                case TRIANGLE_MESH: cMesh[i] = S.trimeshHandle[c.geometry.triangleMesh.mesh]; break;
+        S.workers.parallelFor((size_t)nCol, [&](size_t cb, size_t ce) {
+            for (size_t i = cb; i < ce; ++i) {
+                const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
+                cRow[i] = S.entityRow[(size_t)entt::to_entity(S.cols[i].e)];
+                cIdx[i] = S.cols[i].idx;
+                cType[i] = (int)c.geometry.type;
+                cMesh[i] = -1;
+                std::memcpy(&lp[3 * (size_t)i], &c.position, sizeof(float) * 3);
+                lq[4 * (size_t)i] = c.orientation.x; lq[4 * (size_t)i + 1] = c.orientation.y; lq[4 * (size_t)i + 2] = c.orientation.z; lq[4 * (size_t)i + 3] = c.orientation.w;
+                float* p = &prm[4 * (size_t)i];
+                switch (c.geometry.type) {
+                    case SPHERE: p[0] = c.geometry.sphere.radius; break;
+                    case CAPSULE: p[0] = c.geometry.capsule.halfHeight; p[1] = c.geometry.capsule.radius; break;
+                    case BOX: std::memcpy(p, &c.geometry.box.halfExtents, sizeof(float) * 3); break;
+                    case CONVEX_MESH: std::memcpy(p, &c.geometry.convex.scale, sizeof(float) * 3); cMesh[i] = S.convexHandle.at(c.geometry.convex.mesh); break;
+                    case TRIANGLE_MESH: cMesh[i] = S.trimeshHandle.at(c.geometry.triangleMesh.mesh); break;
+                }
+                mat[3 * (size_t)i] = c.material.friction; mat[3 * (size_t)i + 1] = c.material.restitution; mat[3 * (size_t)i + 2] = c.material.damping;
+                cFlags[i] = (c.isTrigger ? PB_COL_TRIGGER : 0) | (c.enableSimulation ? PB_COL_ENABLE_SIM : 0);
+                cData[i] = c.data;
             }
-            mat[3 * (size_t)i] = c.material.friction; mat[3 * (size_t)i + 1] = c.material.restitution; mat[3 * (size_t)i + 2] = c.material.damping;
-            cFlags[i] = (c.isTrigger ? PB_COL_TRIGGER : 0) | (c.enableSimulation ? PB_COL_ENABLE_SIM : 0);
-            cData[i] = c.data;
-        }
+        });
         S.check(pb_upload_colliders(S.ctx, nCol, cRow.data(), cIdx.data(), lp.data(), lq.data(), cType.data(), prm.data(), cMesh.data(), mat.data(),
                                     cFlags.data(), cData.data()), "pb_upload_colliders");
-        if (!keep.empty()) {
-            std::vector<int> which; std::vector<float> b;
-            for (int i = 0; i < nCol; ++i) {
-                auto it = keep.find(colKey(S.cols[i].e, S.cols[i].idx));
-                if (it == keep.end()) continue;
-                which.push_back(i);
-                b.insert(b.end(), it->second.begin(), it->second.end());
-            }
-            if (!which.empty()) S.check(pb_set_bounds(S.ctx, (int)which.size(), which.data(), b.data()), "pb_set_bounds");
-        }
         if (!oldCols.empty()) {
             // persisting contacts keep their cached restitution targets across the re-upload (reference contactCache is keyed
             // by (entity, collider) pairs, Physecs.cpp:237; the device table is keyed by collider rows, so re-key it)
-            std::unordered_map<unsigned long long, int> now;
-            now.reserve((size_t)nCol * 2);
-            for (int i = 0; i < nCol; ++i) now.emplace(colKey(S.cols[i].e, S.cols[i].idx), i);
-            std::vector<int> oldToNew(oldCols.size(), -1);
-            for (size_t i = 0; i < oldCols.size(); ++i) {
-                unsigned long long k = colKey(oldCols[i].e, oldCols[i].idx);
-                if (S.freshCols.count(k)) continue;
-                auto it = now.find(k);
-                if (it != now.end()) oldToNew[i] = it->second;
+            std::vector<int> which, oldToNew(oldCols.size(), -1);
+            std::vector<float> b;
+            which.reserve((size_t)nCol); b.reserve((size_t)6 * nCol);
+            for (int i = 0; i < nCol; ++i) {
+                const int o = oldIndexOf(S.cols[i].e, S.cols[i].idx);
+                if (o < 0) continue;
+                oldToNew[o] = i;         // the reference's contact cache goes by name (entity, collider index): a collider cleared and added again finds its entries
+                if (!S.freshCols.empty() && S.freshCols.count(colKey(S.cols[i].e, S.cols[i].idx))) continue;    // ... but it starts from creation bounds (Physecs.cpp:739-748)
+                which.push_back(i);
+                b.insert(b.end(), &oldBounds[(size_t)6 * o], &oldBounds[(size_t)6 * o] + 6);
             }
-            S.check(pb_keep_contact_cache(S.ctx, (int)oldToNew.size(), oldToNew.data()), "pb_keep_contact_cache");
+            if (!which.empty()) S.check(pb_set_bounds(S.ctx, (int)which.size(), which.data(), b.data()), "pb_set_bounds");
+            if (carryCache) S.check(pb_keep_contact_cache(S.ctx, (int)oldToNew.size(), oldToNew.data()), "pb_keep_contact_cache");
         }
         S.freshCols.clear();
         S.touched.clear();
@@ -800,6 +804,7 @@ void Scene::simulate(float timeStep) {
     Impl& S = *impl;
     auto tStart = Clock::now();
     prepareDevice();
+    const double prepareMs = msSince(tStart);
     auto& dynStore = registry.storage<RigidBodyDynamicComponent>();
     auto& trStore = registry.storage<TransformComponent>();
     const int nDyn = S.nDyn, nStatic = S.nStatic;
@@ -964,7 +969,7 @@ void Scene::simulate(float timeStep) {
 
     pb_timings tm{};
     pb_get_timings(S.ctx, &tm);
-    S.stats = { counts.n_pairs, counts.n_manifolds, counts.n_points, counts.n_colors, counts.n_triggers, tm.total, gatherMs, scatterMs, msSince(tStart) };
+    S.stats = { counts.n_pairs, counts.n_manifolds, counts.n_points, counts.n_colors, counts.n_triggers, tm.total, gatherMs, scatterMs, msSince(tStart), prepareMs };
 }
 
 } // namespace physecs

@@ -342,10 +342,10 @@ int psh_bvh_leaves(void* hp, int cap, int* ids2, float* bounds6) {
 
 // the Scene's C-ABI context (pb_ctx*) for the parity taps, and the statistics of the last step
 void* psh_native_context(void* hp) { return ((Harness*)hp)->scene->nativeContext(); }
-void psh_get_stats(void* hp, double* out9) {
+void psh_get_stats(void* hp, double* out10) {
     auto s = ((Harness*)hp)->scene->getLastStepStats();
-    out9[0] = s.pairs; out9[1] = s.manifolds; out9[2] = s.points; out9[3] = s.colors; out9[4] = s.triggers;
-    out9[5] = s.deviceMs; out9[6] = s.gatherMs; out9[7] = s.scatterMs; out9[8] = s.totalMs;
+    out10[0] = s.pairs; out10[1] = s.manifolds; out10[2] = s.points; out10[3] = s.colors; out10[4] = s.triggers;
+    out10[5] = s.deviceMs; out10[6] = s.gatherMs; out10[7] = s.scatterMs; out10[8] = s.totalMs; out10[9] = s.prepareMs;
 }
 
 // physecs::computeCOMAndInvInertiaTensor on entity e's colliders (MassUtil parity check)

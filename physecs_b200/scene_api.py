@@ -15,7 +15,7 @@ import numpy as np
 from . import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libphysecs_b200_scene.so")
+LIB_PATH = os.environ.get("PHYSECS_SCENE_LIB") or os.path.join(_HERE, "lib", "libphysecs_b200_scene.so")   # the override serves A/B runs of two builds of the host layer
 
 EXPORTS = [
     "psh_create", "psh_destroy", "psh_last_error", "psh_add_convex", "psh_add_trimesh", "psh_add_entities", "psh_destroy_entity",
@@ -162,6 +162,14 @@ class HostScene:
     def destroy_entity(self, e):
         self.lib.psh_destroy_entity(self.h, int(e))
 
+    def add_collider(self, e, lpos, lquat, ctype, params, mesh=-1, material=(0.4, 0.2, 0.0), flags=2, data=0):
+        """Scene::addCollider on a live entity (flags: bit 0 trigger, bit 1 enableSimulation)."""
+        prm = _f(list(params) + [0.0] * (4 - len(params)))
+        self.lib.psh_add_collider(self.h, int(e), _p(_f(lpos)), _p(_f(lquat)), int(ctype), _p(prm), int(mesh), _p(_f(material)), int(flags), int(data))
+
+    def clear_colliders(self, e):
+        self.lib.psh_clear_colliders(self.h, int(e))
+
     def add_joint(self, t, e0, a0p, a0q, e1, a1p, a1q, prm):
         return self.lib.psh_add_joint(self.h, int(t), int(e0), _p(_f(a0p)), _p(_f(a0q)), int(e1), _p(_f(a1p)), _p(_f(a1q)), _p(_f(prm)))
 
@@ -209,9 +217,9 @@ class HostScene:
         return ids[:n], b[:n]
 
     def stats(self):
-        out = (C.c_double * 9)()
+        out = (C.c_double * 10)()
         self.lib.psh_get_stats(self.h, out)
-        names = ["pairs", "manifolds", "points", "colors", "triggers", "device_ms", "gather_ms", "scatter_ms", "total_ms"]
+        names = ["pairs", "manifolds", "points", "colors", "triggers", "device_ms", "gather_ms", "scatter_ms", "total_ms", "prepare_ms"]
         return {k: out[i] for i, k in enumerate(names)}
 
     def mass_props(self, e, mass):

@@ -84,6 +84,19 @@ class SceneDesc:
         return np.nonzero((self.flags & F_DYNAMIC) == 0)[0].astype(np.int32)
 
 
+def dynamic_only(desc, lift=(0.0, 0.0, 0.0)) -> SceneDesc:
+    """The dynamic bodies of a description whose bodies hold one collider each (mixed_bin, terrain, ...), moved by `lift`: what a
+    running application spawns into a live registry (HostScene.add_entities)."""
+    assert np.array_equal(desc.col_offsets, np.arange(desc.n + 1)), "one collider per body expected"
+    sel = desc.dynamic_entities()
+    cut = lambda a: np.ascontiguousarray(a[sel])
+    return dataclasses.replace(desc, pos=cut(desc.pos) + np.asarray(lift, np.float32), quat=cut(desc.quat), flags=cut(desc.flags), vel=cut(desc.vel),
+                               angvel=cut(desc.angvel), inv_mass=cut(desc.inv_mass), com=cut(desc.com), inv_inertia=cut(desc.inv_inertia),
+                               col_offsets=np.arange(len(sel) + 1, dtype=np.int32), col_lpos=cut(desc.col_lpos), col_lquat=cut(desc.col_lquat),
+                               col_type=cut(desc.col_type), col_params=cut(desc.col_params), col_mesh=cut(desc.col_mesh),
+                               col_material=cut(desc.col_material), col_flags=cut(desc.col_flags), col_data=cut(desc.col_data))
+
+
 class SceneBuilder:
     def __init__(self, name=""):
         self.name = name

@@ -115,6 +115,42 @@ def test_scene_structural_edits():
     assert r["worst"] == 0.0 and r["manifolds"] > 100
 
 
+def test_scene_collider_edits():
+    """Scene::addCollider / clearColliders on live entities (Physecs.cpp:725-751): a second collider on dynamic bodies and on a
+    static wall, bodies left without colliders -- the device collider table is re-uploaded, everything that persists keeps its
+    bounds history and contact cache, the new colliders start from creation bounds."""
+    d = S.mixed_bin(400, spacing=0.8)
+    dyn = d.dynamic_entities()
+    floor = int(d.static_entities()[0])
+    idq = [0, 0, 0, 1]
+    bouncy = (0.4, 0.3, 0.0)
+    ops = {
+        8: lambda s: [s.add_collider(int(e), [0.45, 0.0, 0.0], idq, S.SPHERE, [0.25], material=bouncy) for e in dyn[[7, 8, 150]]],
+        14: lambda s: s.add_collider(floor, [0.0, 1.3, 0.0], idq, S.BOX, [1.5, 0.3, 1.5], material=bouncy),
+        20: lambda s: [s.clear_colliders(int(e)) for e in dyn[[30, 31]]],
+        26: lambda s: s.add_collider(int(dyn[30]), [0.0, 0.0, 0.0], idq, S.CAPSULE, [0.3, 0.2]),
+        34: lambda s: s.add_collider(int(dyn[9]), [0.0, 0.4, 0.0], [0.0, 0.0, 0.38268343, 0.92387953], S.BOX, [0.3, 0.1, 0.2], material=bouncy),
+    }
+    r = run_scene(d, 50, ops=ops)
+    assert r["worst"] == 0.0 and r["manifolds"] > 100
+
+
+def test_scene_collider_cleared_and_added_again():
+    """A collider cleared and added again under the same (entity, index) between two steps: new broadphase entry from creation
+    bounds, but the reference's contact cache goes by name and still finds the pair's entries (Physecs.cpp:237)."""
+    d = S.mixed_bin(300, spacing=0.8)
+    d.col_material[:, 1] = 0.3            # restitution: the cache's target velocities matter
+    dyn = d.dynamic_entities()
+    idq = [0, 0, 0, 1]
+
+    def again(s, e):
+        s.clear_colliders(e)
+        s.add_collider(e, d.col_lpos[e], d.col_lquat[e], int(d.col_type[e]), list(d.col_params[e]), material=tuple(d.col_material[e]))
+    ops = {k: (lambda s, k=k: [again(s, int(e)) for e in dyn[[k, k + 50, k + 100]]]) for k in (22, 23, 24, 25, 26, 30, 34)}
+    r = run_scene(d, 45, ops=ops)
+    assert r["worst"] == 0.0 and r["manifolds"] > 100
+
+
 def test_scene_joint_edits():
     d = S.ragdolls(4)
     j0 = d.joints[3]
