@@ -155,6 +155,11 @@ int pb_set_mass(pb_ctx* ctx, int n_dynamic, const float* inv_mass, const float* 
 /* overwrite persistent collider bounds (BroadPhaseEntry::bounds): lets the host carry bounds across a re-upload so the
  * creation-without-margin / margin-after-update history of surviving colliders is kept (quirk Q6) */
 int pb_set_bounds(pb_ctx* ctx, int n, const int* colliders, const float* bounds6);
+/* the same carry-over on the device: pb_keep_bounds_begin BEFORE pb_upload_colliders keeps a copy of the current bounds,
+ * pb_keep_bounds AFTER it gives collider old_to_new[i] the bounds collider i had (-1 = none: removed, or a collider the
+ * reference would have created anew, Physecs.cpp:20-33, :738-751); n_old = the collider count at pb_keep_bounds_begin */
+int pb_keep_bounds_begin(pb_ctx* ctx);
+int pb_keep_bounds(pb_ctx* ctx, int n_old, const int* old_to_new);
 
 /* ---- per-step state exchange ---------------------------------------------------------------------- */
 /* push registry state of the dynamic rows (what the reference reads through registry.get each step) */

@@ -29,7 +29,7 @@ EXPORTS = [
     "pb_set_noncolliding_pairs", "pb_set_state", "pb_move_rows", "pb_refresh_bounds", "pb_step", "pb_get_state", "pb_sync",
     "pb_get_counts", "pb_get_timings", "pb_get_pairs", "pb_get_bounds", "pb_get_manifolds", "pb_build_trimesh",
     "pb_set_profile", "pb_get_profile", "pb_get_launches", "pb_profiler_range",
-    "pb_update_joint_params", "pb_set_contact_filter", "pb_set_kinematic", "pb_set_mass", "pb_set_bounds",
+    "pb_update_joint_params", "pb_set_contact_filter", "pb_set_kinematic", "pb_set_mass", "pb_set_bounds", "pb_keep_bounds_begin", "pb_keep_bounds",
     "pb_set_static_poses", "pb_get_triggers", "pb_keep_contact_cache", "pb_keep_joint_state", "pb_grow_arenas", "pb_query_raycast", "pb_query_overlap",
     "pb_debug_sort_pairs",
 ]

@@ -77,6 +77,16 @@ __global__ void k_scatter_bounds(int n, const int* __restrict__ cols, const floa
     mn[c] = make_float4(b6[6 * i], b6[6 * i + 1], b6[6 * i + 2], 0.f);
     mx[c] = make_float4(b6[6 * i + 3], b6[6 * i + 4], b6[6 * i + 5], 0.f);
 }
+// bounds kept across a collider re-upload: old collider o lives on as collider oldToNew[o] (-1 = gone, or it starts from creation bounds)
+__global__ void k_restore_bounds(int nOld, const int* __restrict__ oldToNew, int nNew, const float4* __restrict__ keptMin, const float4* __restrict__ keptMax,
+                                 float4* __restrict__ mn, float4* __restrict__ mx) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nOld) return;
+    int c = oldToNew[o];
+    if (c < 0 || c >= nNew) return;
+    mn[c] = keptMin[o];
+    mx[c] = keptMax[o];
+}
 // BroadPhaseEntry::isDynamic (Physecs.cpp:56-77, :753-770): bit2 of the device collider flags
 __global__ void k_col_dynamic_flag(int n, const int* __restrict__ colRow, int nDyn, const int* __restrict__ kinematic, int* __restrict__ colFlags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +369,7 @@ void pb_ctx_destroy(pb_ctx* ctx) {
     F(rowEntity); F(pos); F(quat); F(velBuf[0]); F(velBuf[1]); F(bodyRec); F(comInvMass); F(invIL);
     F(kinematic); F(pseudoLin); F(pseudoAng); F(colorMask); F(rowMark); F(stage);
     F(colRow); F(colIndex); F(colType); F(colFlags); F(colInfo); F(colData); F(colMesh); F(colLPos); F(colLQuat); F(colParams); F(colMat); F(colWPos);
-    F(colWQuat); F(aabbMin); F(aabbMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
+    F(colWQuat); F(aabbMin); F(aabbMax); F(keptMin); F(keptMax); F(mortonA); F(mortonB); F(leafIdA); F(leafIdB); F(radixHist); F(sceneBounds); F(bigList); F(sortBarrier);
     F(nodeLeft); F(nodeRight); F(nodeParent); F(leafParent); F(nodeFlag); F(nodeRange); F(nodeMin); F(nodeMax); F(pairs); F(pairOrder);
     F(mKey); F(mNormal); F(mPts); F(mSortKeyA); F(mSortKeyB); F(mSortValB); F(cHead); F(cBodies); F(cRowsT); F(cNormal); F(cSoft);
     F(pR0T[0]); F(pR0T[1]); F(cPointOfsBuf[0]); F(cPointOfsBuf[1]); F(cNpBuf[0]); F(cNpBuf[1]); F(pR1);
@@ -973,6 +983,39 @@ int pb_set_bounds(pb_ctx* ctx, int n, const int* cols, const float* bounds6) {
     PB_CUDA(ctx, cudaMemcpyAsync(s, cols, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
     PB_CUDA(ctx, cudaMemcpyAsync(s + n, bounds6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     ++ctx->launches, k_scatter_bounds<<<pb_grid(n, 256), 256, 0, ctx->stream>>>(n, (const int*)s, s + n, ctx->aabbMin, ctx->aabbMax);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+// The same carry-over without the round trip through the host (pb_get_bounds + pb_set_bounds move 52 B per collider over PCIe and
+// through two host loops): a device copy before the re-upload, one scatter after it.
+int pb_keep_bounds_begin(pb_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    ctx->keptN = 0;
+    if (ctx->nCol <= 0) return PB_OK;
+    if (ctx->keptCap < ctx->nCol) {
+        const int cap = ctx->nCol + ctx->nCol / 4 + 256;
+        ctx->keptCap = 0;
+        int rc = pb_alloc(ctx, &ctx->keptMin, (size_t)cap); if (rc) return rc;
+        rc = pb_alloc(ctx, &ctx->keptMax, (size_t)cap); if (rc) return rc;
+        ctx->keptCap = cap;
+    }
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->keptMin, ctx->aabbMin, sizeof(float4) * (size_t)ctx->nCol, cudaMemcpyDeviceToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->keptMax, ctx->aabbMax, sizeof(float4) * (size_t)ctx->nCol, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->keptN = ctx->nCol;
+    return PB_OK;
+}
+
+int pb_keep_bounds(pb_ctx* ctx, int nOld, const int* oldToNew) {
+    cudaSetDevice(ctx->device);
+    { int rcw = pb_wait_velocities(ctx); if (rcw) return rcw; }
+    PB_STALE_BROADPHASE(ctx);
+    if (nOld != ctx->keptN) return pb_fail(ctx, PB_EINVAL, "pb_keep_bounds: n_old is not the collider count pb_keep_bounds_begin saw");
+    ctx->keptN = 0;
+    if (nOld <= 0) return PB_OK;
+    int rc = ensureStage(ctx, sizeof(int) * (size_t)nOld); if (rc) return rc;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, oldToNew, sizeof(int) * (size_t)nOld, cudaMemcpyHostToDevice, ctx->stream));
+    ++ctx->launches, k_restore_bounds<<<pb_grid(nOld, 256), 256, 0, ctx->stream>>>(nOld, (const int*)ctx->stage, ctx->nCol, ctx->keptMin, ctx->keptMax, ctx->aabbMin, ctx->aabbMax);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB_OK;
 }

@@ -115,6 +115,7 @@ struct pb_ctx {
     float4* colLPos = nullptr; float4* colLQuat = nullptr; float4* colParams = nullptr; float4* colMat = nullptr;
     float4* colWPos = nullptr; float4* colWQuat = nullptr;   // world pose, refreshed each step
     float4* aabbMin = nullptr; float4* aabbMax = nullptr;     // persistent bounds (BroadPhaseEntry::bounds)
+    float4* keptMin = nullptr; float4* keptMax = nullptr; int keptCap = 0, keptN = 0;   // pb_keep_bounds_begin's copy of the bounds (carried across a collider re-upload)
     std::vector<int> hColType, hColMesh, hColRow, hColIndex, hRowEntity;   // host mirrors (trimesh colliders are found on the host)
     int* rowMark = nullptr;          // [rows] scratch marks for pb_move_rows
 

@@ -14,6 +14,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <set>
@@ -100,6 +102,10 @@ template <class T> struct Pinned {
         p = (T*)q; cap = want;
     }
     ~Pinned() { if (p) pb_host_free(p); }
+    // enough of std::vector's face for the host mirrors (contents are NOT kept when the buffer grows: every user refills it)
+    void resize(size_t n) { reserve(n); }
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
 };
 
 inline unsigned long long colKey(entt::entity e, int idx) { return ((unsigned long long)entt::to_integral(e) << 20) ^ (unsigned long long)(unsigned)idx; }
@@ -141,9 +147,10 @@ struct Scene::Impl {
 
     // pinned staging
     Pinned<float> hPos, hQuat, hVel, hAng, hSPos, hSQuat;
+    Pinned<int> upI; Pinned<float> upF;         // tables of a scene re-upload (prepareDevice)
     // host mirrors for change detection of fields the reference reads live every step
-    std::vector<int> kin;
-    std::vector<float> invMass, com, invI;
+    Pinned<int> kin;                            // (pinned: they are upload sources of every re-upload)
+    Pinned<float> invMass, com, invI;
 
     // joints
     std::vector<Joint*> joints;                 // creation order
@@ -524,17 +531,23 @@ void Scene::prepareDevice() {
 
     // ---- (re)build the device scene description after structural changes -----------------------------------------------------
     auto rebuild = [&](bool growCaps) {
+        // PB_TRACE_EDIT=1: where a re-upload spends its time, one line on stderr
+        static const bool trace = std::getenv("PB_TRACE_EDIT") != nullptr;
+        auto tPhase = Clock::now();
+        std::string traceLine;
+        auto phase = [&](const char* name) {
+            if (!trace) return;
+            char buf[64]; std::snprintf(buf, sizeof buf, " %s %.1f", name, msSince(tPhase));
+            traceLine += buf; tPhase = Clock::now();
+        };
         // What the device holds now.  Colliders that survive the re-upload keep their bounds history (creation bounds have no margin,
         // refreshed ones do: quirk Q6) and their contact-cache entries.  The colliders of an entity are contiguous in device order, so
         // "where was (entity, index) before" is one flat table over entity indices (entity versions are compared through oldCols) --
         // at 1 M colliders a hash map per lookup was most of a structural edit's cost.
         std::vector<Impl::ColRef> oldCols;
-        std::vector<float> oldBounds;
         std::vector<int> oldFirst;                  // entt::to_entity(e) -> first collider of e in oldCols, -1 = none
         if (S.ctx && !S.ctxFresh && !S.cols.empty()) {
             oldCols.swap(S.cols);
-            oldBounds.resize((size_t)6 * oldCols.size());
-            S.check(pb_get_bounds(S.ctx, oldBounds.data()), "pb_get_bounds");
             size_t top = 0;
             for (auto& c : oldCols) top = std::max(top, (size_t)entt::to_entity(c.e));
             oldFirst.assign(top + 1, -1);
@@ -548,11 +561,14 @@ void Scene::prepareDevice() {
             return (int)i;
         };
         bool carryCache = !oldCols.empty();
+        phase("old-table");
+
+        // ---- rows -----------------------------------------------------------------------------------------------------------------
         const size_t nDyn = dynStore.size();
         S.rowEntity.clear();
         S.rowEntity.reserve(nDyn + colStore.size());
         const entt::entity* dynEnts = dynStore.data();
-        for (size_t i = 0; i < nDyn; ++i) S.rowEntity.push_back(dynEnts[i]);
+        S.rowEntity.insert(S.rowEntity.end(), dynEnts, dynEnts + nDyn);
         const entt::entity* colEnts = colStore.data();
         for (size_t i = 0; i < colStore.size(); ++i)
             if (!dynStore.contains(colEnts[i])) S.rowEntity.push_back(colEnts[i]);
@@ -562,25 +578,58 @@ void Scene::prepareDevice() {
         size_t maxIdx = 0;
         for (auto e : S.rowEntity) maxIdx = std::max(maxIdx, (size_t)entt::to_entity(e));
         S.entityRow.assign(rows ? maxIdx + 1 : 0, -1);
-        S.rowTransformIdx.assign(rows, 0u);
-        for (int r = 0; r < rows; ++r) {
-            S.entityRow[(size_t)entt::to_entity(S.rowEntity[r])] = r;
-            S.rowTransformIdx[r] = (unsigned)trStore.index(S.rowEntity[r]);
-        }
-        // colliders, row-major
-        S.cols.clear();
-        for (int r = 0; r < rows; ++r) {
-            auto e = S.rowEntity[r];
-            if (!colStore.contains(e)) continue;
-            auto& cc = colStore.get(e);
-            for (int i = 0; i < (int)cc.colliders.size(); ++i) S.cols.push_back({ e, i });
-        }
-        const int nCol = (int)S.cols.size();
+        S.rowTransformIdx.resize(rows);
+        phase("rows");
+        // ---- colliders, row-major: a count per row, offsets, then the list -- on the worker threads, like every other walk over the
+        // registry here; the meshes the colliders reference are noted on the way (with the row that named them first)
+        std::vector<int> colStart((size_t)rows + 1, 0);
+        std::vector<std::pair<size_t, const ConvexMesh*>> convexSeen;
+        std::vector<std::pair<size_t, const TriangleMesh*>> trimeshSeen;
+        std::mutex seenLock;
+        S.workers.parallelFor((size_t)rows, [&](size_t rb, size_t re) {
+            std::vector<std::pair<size_t, const ConvexMesh*>> cv;
+            std::vector<std::pair<size_t, const TriangleMesh*>> tm;
+            for (size_t r = rb; r < re; ++r) {
+                const auto e = S.rowEntity[r];
+                S.entityRow[(size_t)entt::to_entity(e)] = (int)r;
+                S.rowTransformIdx[r] = (unsigned)trStore.index(e);
+                if (r < nDyn && !colStore.contains(e)) continue;
+                const auto& cc = colStore.get(e).colliders;
+                colStart[r + 1] = (int)cc.size();
+                for (const Collider& c : cc) {
+                    if (c.geometry.type == CONVEX_MESH) {
+                        const ConvexMesh* m = c.geometry.convex.mesh;
+                        if (std::find_if(cv.begin(), cv.end(), [m](auto& s) { return s.second == m; }) == cv.end()) cv.emplace_back(r, m);
+                    } else if (c.geometry.type == TRIANGLE_MESH) {
+                        const TriangleMesh* m = c.geometry.triangleMesh.mesh;
+                        if (std::find_if(tm.begin(), tm.end(), [m](auto& s) { return s.second == m; }) == tm.end()) tm.emplace_back(r, m);
+                    }
+                }
+            }
+            if (cv.empty() && tm.empty()) return;
+            std::lock_guard<std::mutex> lk(seenLock);
+            convexSeen.insert(convexSeen.end(), cv.begin(), cv.end());
+            trimeshSeen.insert(trimeshSeen.end(), tm.begin(), tm.end());
+        });
+        for (int r = 0; r < rows; ++r) colStart[r + 1] += colStart[r];
+        const int nCol = colStart[rows];
+        S.cols.resize((size_t)nCol);
+        S.workers.parallelFor((size_t)rows, [&](size_t rb, size_t re) {
+            for (size_t r = rb; r < re; ++r)
+                for (int i = 0, n = colStart[r + 1] - colStart[r]; i < n; ++i) S.cols[(size_t)colStart[r] + i] = { S.rowEntity[r], i };
+        });
 
-        // capacities: context is sized with headroom and re-created when the scene outgrows it
+        phase("collider-list");
+        // capacities: context is sized with headroom and re-created when the scene outgrows it.  The bounds history travels on the
+        // device while the context lives (pb_keep_bounds_begin / pb_keep_bounds) and through the host when it is replaced.
         auto roomy = [](int n) { return std::max(1024, n + n / 2); };
         bool need = !S.ctx || rows > S.caps.max_bodies || nCol > S.caps.max_colliders || (int)S.joints.size() > S.caps.max_joints || growCaps;
+        std::vector<float> oldBounds;
         if (need) {
+            if (!oldCols.empty()) {
+                oldBounds.resize((size_t)6 * oldCols.size());
+                S.check(pb_get_bounds(S.ctx, oldBounds.data()), "pb_get_bounds");
+            }
             pb_caps c{};
             c.max_bodies = roomy(rows);
             c.max_colliders = roomy(nCol);
@@ -594,105 +643,135 @@ void Scene::prepareDevice() {
             S.caps = c;
             S.jointsDirty = S.pairsDirty = S.filterDirty = true;
             S.uploadedJoints.clear();
-            carryCache = false;      // a new context starts with an empty contact cache (the bounds history is carried over)
+            carryCache = false;      // a new context starts with an empty contact cache
+        } else if (!oldCols.empty()) {
+            S.check(pb_keep_bounds_begin(S.ctx), "pb_keep_bounds_begin");
         }
 
-        // meshes referenced by colliders
-        for (auto& cr : S.cols) {
-            const Collider& c = colStore.get(cr.e).colliders[cr.idx];
-            if (c.geometry.type == CONVEX_MESH && !S.convexHandle.count(c.geometry.convex.mesh)) {
-                const ConvexMesh* m = c.geometry.convex.mesh;
-                std::vector<float> v((size_t)3 * m->vertices.size()), fn((size_t)3 * m->faces.size()), fc((size_t)3 * m->faces.size());
-                for (int i = 0; i < m->vertices.size(); ++i) std::memcpy(&v[3 * i], &m->vertices[i], sizeof(float) * 3);
-                std::vector<int> off(m->faces.size() + 1, 0), idx;
-                for (size_t f = 0; f < m->faces.size(); ++f) {
-                    idx.insert(idx.end(), m->faces[f].indices.begin(), m->faces[f].indices.end());
-                    off[f + 1] = (int)idx.size();
-                    std::memcpy(&fn[3 * f], &m->faces[f].normal, sizeof(float) * 3);
-                    std::memcpy(&fc[3 * f], &m->faces[f].centroid, sizeof(float) * 3);
-                }
-                int h = -1;
-                S.check(pb_register_convex(S.ctx, v.data(), m->vertices.size(), off.data(), idx.data(), (int)m->faces.size(), fn.data(), fc.data(), &h), "pb_register_convex");
-                S.convexHandle[m] = h;
+        phase("context");
+        // meshes referenced by colliders, registered in the order the colliders name them
+        std::sort(convexSeen.begin(), convexSeen.end());
+        std::sort(trimeshSeen.begin(), trimeshSeen.end());
+        for (auto& seen : convexSeen) {
+            const ConvexMesh* m = seen.second;
+            if (S.convexHandle.count(m)) continue;
+            std::vector<float> v((size_t)3 * m->vertices.size()), fn((size_t)3 * m->faces.size()), fc((size_t)3 * m->faces.size());
+            for (int i = 0; i < m->vertices.size(); ++i) std::memcpy(&v[3 * i], &m->vertices[i], sizeof(float) * 3);
+            std::vector<int> off(m->faces.size() + 1, 0), idx;
+            for (size_t f = 0; f < m->faces.size(); ++f) {
+                idx.insert(idx.end(), m->faces[f].indices.begin(), m->faces[f].indices.end());
+                off[f + 1] = (int)idx.size();
+                std::memcpy(&fn[3 * f], &m->faces[f].normal, sizeof(float) * 3);
+                std::memcpy(&fc[3 * f], &m->faces[f].centroid, sizeof(float) * 3);
             }
-            if (c.geometry.type == TRIANGLE_MESH && !S.trimeshHandle.count(c.geometry.triangleMesh.mesh)) {
-                const TriangleMesh* m = c.geometry.triangleMesh.mesh;
-                int h = -1;
-                S.check(pb_register_trimesh(S.ctx, (const float*)m->vertices.data(), (int)m->vertices.size(), m->getSourceIndices().data(),
-                                            (int)m->getSourceIndices().size(), &h, nullptr), "pb_register_trimesh");
-                S.trimeshHandle[m] = h;
-            }
+            int h = -1;
+            S.check(pb_register_convex(S.ctx, v.data(), m->vertices.size(), off.data(), idx.data(), (int)m->faces.size(), fn.data(), fc.data(), &h), "pb_register_convex");
+            S.convexHandle[m] = h;
         }
+        for (auto& seen : trimeshSeen) {
+            const TriangleMesh* m = seen.second;
+            if (S.trimeshHandle.count(m)) continue;
+            int h = -1;
+            S.check(pb_register_trimesh(S.ctx, (const float*)m->vertices.data(), (int)m->vertices.size(), m->getSourceIndices().data(),
+                                        (int)m->getSourceIndices().size(), &h, nullptr), "pb_register_trimesh");
+            S.trimeshHandle[m] = h;
+        }
+
+        phase("meshes");
+        // The body and collider tables are written into pinned memory that stays allocated between edits (fresh pageable vectors cost a
+        // page fault per 4 KB and a staged copy: at 1 M bodies that was a third of an edit); each upload call returns after its copy, so
+        // the two tables share the buffers.
+        S.upI.reserve(std::max((size_t)rows, (size_t)6 * nCol));
+        S.upF.reserve(std::max((size_t)7 * rows + 6 * nDyn, (size_t)14 * nCol));
 
         // bodies
-        std::vector<int> ent(rows);
-        std::vector<float> pos((size_t)3 * rows), quat((size_t)4 * rows), vel((size_t)3 * nDyn), ang((size_t)3 * nDyn);
-        S.kin.assign(nDyn, 0); S.invMass.assign(nDyn, 0.f); S.com.assign(3 * nDyn, 0.f); S.invI.assign(9 * nDyn, 0.f);
-        S.workers.parallelFor((size_t)rows, [&](size_t rb, size_t re) {
-            for (size_t r = rb; r < re; ++r) {
-                auto e = S.rowEntity[r];
-                ent[r] = (int)entt::to_integral(e);
-                const TransformComponent& t = packedAt<TransformComponent>(trStore, S.rowTransformIdx[r]);
-                std::memcpy(&pos[3 * (size_t)r], &t.position, sizeof(float) * 3);
-                quat[4 * (size_t)r] = t.orientation.x; quat[4 * (size_t)r + 1] = t.orientation.y; quat[4 * (size_t)r + 2] = t.orientation.z; quat[4 * (size_t)r + 3] = t.orientation.w;
-                if (r < nDyn) {
-                    const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
-                    S.kin[r] = d.isKinematic ? 1 : 0;
-                    std::memcpy(&vel[3 * (size_t)r], &d.velocity, sizeof(float) * 3);
-                    std::memcpy(&ang[3 * (size_t)r], &d.angularVelocity, sizeof(float) * 3);
-                    S.invMass[r] = d.invMass;
-                    std::memcpy(&S.com[3 * (size_t)r], &d.com, sizeof(float) * 3);
-                    std::memcpy(&S.invI[9 * (size_t)r], &d.invInertiaTensor, sizeof(float) * 9);
+        {
+            int* ent = S.upI.p;
+            float* pos = S.upF.p; float* quat = pos + (size_t)3 * rows; float* vel = quat + (size_t)4 * rows; float* ang = vel + 3 * nDyn;
+            S.kin.resize(nDyn); S.invMass.resize(nDyn); S.com.resize(3 * nDyn); S.invI.resize(9 * nDyn);
+            S.workers.parallelFor((size_t)rows, [&](size_t rb, size_t re) {
+                for (size_t r = rb; r < re; ++r) {
+                    ent[r] = (int)entt::to_integral(S.rowEntity[r]);
+                    const TransformComponent& t = packedAt<TransformComponent>(trStore, S.rowTransformIdx[r]);
+                    std::memcpy(&pos[3 * r], &t.position, sizeof(float) * 3);
+                    quat[4 * r] = t.orientation.x; quat[4 * r + 1] = t.orientation.y; quat[4 * r + 2] = t.orientation.z; quat[4 * r + 3] = t.orientation.w;
+                    if (r < nDyn) {
+                        const RigidBodyDynamicComponent& d = packedAt<RigidBodyDynamicComponent>(dynStore, r);
+                        S.kin[r] = d.isKinematic ? 1 : 0;
+                        std::memcpy(&vel[3 * r], &d.velocity, sizeof(float) * 3);
+                        std::memcpy(&ang[3 * r], &d.angularVelocity, sizeof(float) * 3);
+                        S.invMass[r] = d.invMass;
+                        std::memcpy(&S.com[3 * r], &d.com, sizeof(float) * 3);
+                        std::memcpy(&S.invI[9 * r], &d.invInertiaTensor, sizeof(float) * 9);
+                    }
                 }
-            }
-        });
-        S.check(pb_upload_bodies(S.ctx, (int)nDyn, S.nStatic, ent.data(), pos.data(), quat.data(), S.kin.data(), vel.data(), ang.data(),
-                                 S.invMass.data(), S.com.data(), S.invI.data()), "pb_upload_bodies");
+            });
+            phase("body-table");
+            S.check(pb_upload_bodies(S.ctx, (int)nDyn, S.nStatic, ent, pos, quat, S.kin.data(), vel, ang, S.invMass.data(), S.com.data(), S.invI.data()), "pb_upload_bodies");
+            phase("pb_upload_bodies");
+        }
 
         // colliders
-        std::vector<int> cRow(nCol), cIdx(nCol), cType(nCol), cMesh(nCol), cFlags(nCol), cData(nCol);
-        std::vector<float> lp((size_t)3 * nCol), lq((size_t)4 * nCol), prm((size_t)4 * nCol, 0.f), mat((size_t)3 * nCol);
-        S.workers.parallelFor((size_t)nCol, [&](size_t cb, size_t ce) {
-            for (size_t i = cb; i < ce; ++i) {
-                const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
-                cRow[i] = S.entityRow[(size_t)entt::to_entity(S.cols[i].e)];
-                cIdx[i] = S.cols[i].idx;
-                cType[i] = (int)c.geometry.type;
-                cMesh[i] = -1;
-                std::memcpy(&lp[3 * (size_t)i], &c.position, sizeof(float) * 3);
-                lq[4 * (size_t)i] = c.orientation.x; lq[4 * (size_t)i + 1] = c.orientation.y; lq[4 * (size_t)i + 2] = c.orientation.z; lq[4 * (size_t)i + 3] = c.orientation.w;
-                float* p = &prm[4 * (size_t)i];
-                switch (c.geometry.type) {
-                    case SPHERE: p[0] = c.geometry.sphere.radius; break;
-                    case CAPSULE: p[0] = c.geometry.capsule.halfHeight; p[1] = c.geometry.capsule.radius; break;
-                    case BOX: std::memcpy(p, &c.geometry.box.halfExtents, sizeof(float) * 3); break;
-                    case CONVEX_MESH: std::memcpy(p, &c.geometry.convex.scale, sizeof(float) * 3); cMesh[i] = S.convexHandle.at(c.geometry.convex.mesh); break;
-                    case TRIANGLE_MESH: cMesh[i] = S.trimeshHandle.at(c.geometry.triangleMesh.mesh); break;
+        {
+            const size_t C = (size_t)nCol;
+            int* cRow = S.upI.p; int* cIdx = cRow + C; int* cType = cIdx + C; int* cMesh = cType + C; int* cFlags = cMesh + C; int* cData = cFlags + C;
+            float* lp = S.upF.p; float* lq = lp + 3 * C; float* prm = lq + 4 * C; float* mat = prm + 4 * C;
+            S.workers.parallelFor(C, [&](size_t cb, size_t ce) {
+                for (size_t i = cb; i < ce; ++i) {
+                    const Collider& c = colStore.get(S.cols[i].e).colliders[S.cols[i].idx];
+                    cRow[i] = S.entityRow[(size_t)entt::to_entity(S.cols[i].e)];
+                    cIdx[i] = S.cols[i].idx;
+                    cType[i] = (int)c.geometry.type;
+                    cMesh[i] = -1;
+                    std::memcpy(&lp[3 * i], &c.position, sizeof(float) * 3);
+                    lq[4 * i] = c.orientation.x; lq[4 * i + 1] = c.orientation.y; lq[4 * i + 2] = c.orientation.z; lq[4 * i + 3] = c.orientation.w;
+                    float* p = &prm[4 * i];
+                    p[0] = p[1] = p[2] = p[3] = 0.f;
+                    switch (c.geometry.type) {
+                        case SPHERE: p[0] = c.geometry.sphere.radius; break;
+                        case CAPSULE: p[0] = c.geometry.capsule.halfHeight; p[1] = c.geometry.capsule.radius; break;
+                        case BOX: std::memcpy(p, &c.geometry.box.halfExtents, sizeof(float) * 3); break;
+                        case CONVEX_MESH: std::memcpy(p, &c.geometry.convex.scale, sizeof(float) * 3); cMesh[i] = S.convexHandle.at(c.geometry.convex.mesh); break;
+                        case TRIANGLE_MESH: cMesh[i] = S.trimeshHandle.at(c.geometry.triangleMesh.mesh); break;
+                    }
+                    mat[3 * i] = c.material.friction; mat[3 * i + 1] = c.material.restitution; mat[3 * i + 2] = c.material.damping;
+                    cFlags[i] = (c.isTrigger ? PB_COL_TRIGGER : 0) | (c.enableSimulation ? PB_COL_ENABLE_SIM : 0);
+                    cData[i] = c.data;
                 }
-                mat[3 * (size_t)i] = c.material.friction; mat[3 * (size_t)i + 1] = c.material.restitution; mat[3 * (size_t)i + 2] = c.material.damping;
-                cFlags[i] = (c.isTrigger ? PB_COL_TRIGGER : 0) | (c.enableSimulation ? PB_COL_ENABLE_SIM : 0);
-                cData[i] = c.data;
-            }
-        });
-        S.check(pb_upload_colliders(S.ctx, nCol, cRow.data(), cIdx.data(), lp.data(), lq.data(), cType.data(), prm.data(), cMesh.data(), mat.data(),
-                                    cFlags.data(), cData.data()), "pb_upload_colliders");
-        if (!oldCols.empty()) {
-            // persisting contacts keep their cached restitution targets across the re-upload (reference contactCache is keyed
-            // by (entity, collider) pairs, Physecs.cpp:237; the device table is keyed by collider rows, so re-key it)
-            std::vector<int> which, oldToNew(oldCols.size(), -1);
-            std::vector<float> b;
-            which.reserve((size_t)nCol); b.reserve((size_t)6 * nCol);
-            for (int i = 0; i < nCol; ++i) {
-                const int o = oldIndexOf(S.cols[i].e, S.cols[i].idx);
-                if (o < 0) continue;
-                oldToNew[o] = i;         // the reference's contact cache goes by name (entity, collider index): a collider cleared and added again finds its entries
-                if (!S.freshCols.empty() && S.freshCols.count(colKey(S.cols[i].e, S.cols[i].idx))) continue;    // ... but it starts from creation bounds (Physecs.cpp:739-748)
-                which.push_back(i);
-                b.insert(b.end(), &oldBounds[(size_t)6 * o], &oldBounds[(size_t)6 * o] + 6);
-            }
-            if (!which.empty()) S.check(pb_set_bounds(S.ctx, (int)which.size(), which.data(), b.data()), "pb_set_bounds");
-            if (carryCache) S.check(pb_keep_contact_cache(S.ctx, (int)oldToNew.size(), oldToNew.data()), "pb_keep_contact_cache");
+            });
+            phase("collider-table");
+            S.check(pb_upload_colliders(S.ctx, nCol, cRow, cIdx, lp, lq, cType, prm, cMesh, mat, cFlags, cData), "pb_upload_colliders");
+            phase("pb_upload_colliders");
         }
+
+        if (!oldCols.empty()) {
+            // boundsMap / cacheMap[o] = where old collider o is now (-1 = gone).  Persisting contacts keep their cached restitution targets
+            // across the re-upload: the reference's contactCache is keyed by (entity, collider index) pairs (Physecs.cpp:237), the device
+            // table by collider rows, so it is re-keyed -- by NAME, so a collider cleared and added again finds its entries, while its
+            // bounds start over from creation bounds like the reference's new BroadPhaseEntry (Physecs.cpp:739-748).
+            std::vector<int> boundsMap(oldCols.size(), -1), cacheMap(oldCols.size(), -1);
+            S.workers.parallelFor((size_t)nCol, [&](size_t cb, size_t ce) {
+                for (size_t i = cb; i < ce; ++i) {
+                    const int o = oldIndexOf(S.cols[i].e, S.cols[i].idx);
+                    if (o < 0) continue;
+                    cacheMap[o] = (int)i;
+                    if (S.freshCols.empty() || !S.freshCols.count(colKey(S.cols[i].e, S.cols[i].idx))) boundsMap[o] = (int)i;
+                }
+            });
+            if (!need) S.check(pb_keep_bounds(S.ctx, (int)boundsMap.size(), boundsMap.data()), "pb_keep_bounds");
+            else {
+                std::vector<int> which; std::vector<float> b;
+                for (size_t o = 0; o < boundsMap.size(); ++o) {
+                    if (boundsMap[o] < 0) continue;
+                    which.push_back(boundsMap[o]);
+                    b.insert(b.end(), &oldBounds[6 * o], &oldBounds[6 * o] + 6);
+                }
+                if (!which.empty()) S.check(pb_set_bounds(S.ctx, (int)which.size(), which.data(), b.data()), "pb_set_bounds");
+            }
+            if (carryCache) S.check(pb_keep_contact_cache(S.ctx, (int)cacheMap.size(), cacheMap.data()), "pb_keep_contact_cache");
+        }
+        phase("carry-over");
+        if (trace) std::fprintf(stderr, "physecs_b200 re-upload (%d rows, %d colliders), ms:%s\n", rows, nCol, traceLine.c_str());
         S.freshCols.clear();
         S.touched.clear();
         S.stagingValid = false;
