@@ -529,6 +529,20 @@ void Scene::prepareDevice() {
     auto& colStore = registry.storage<RigidBodyCollisionComponent>();
     auto& trStore = registry.storage<TransformComponent>();
 
+    // The body rows follow the packed order of the dynamic-body pool (the reference indexes bodies by their position in it, Physecs.cpp:116-117).
+    // No signal tells of a registry.sort on it: compare the pool's entity list with the rows' (4 B per body, on the workers).
+    if (!S.topologyDirty && S.ctx) {
+        if (dynStore.size() != (size_t)S.nDyn) S.topologyDirty = true;
+        else {
+            std::atomic<int> differs{0};
+            const entt::entity* pool = dynStore.data();
+            S.workers.parallelFor((size_t)S.nDyn, [&](size_t b, size_t e) {
+                if (std::memcmp(pool + b, S.rowEntity.data() + b, sizeof(entt::entity) * (e - b))) differs.store(1, std::memory_order_relaxed);
+            });
+            if (differs.load()) S.topologyDirty = true;
+        }
+    }
+
     // ---- (re)build the device scene description after structural changes -----------------------------------------------------
     auto rebuild = [&](bool growCaps) {
         // PB_TRACE_EDIT=1: where a re-upload spends its time, one line on stderr

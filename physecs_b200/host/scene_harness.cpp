@@ -146,6 +146,13 @@ int psh_destroy_entity(void* hp, int e) {
     return 0;
 }
 
+// registry.sort on the dynamic-body pool: the Scene has to notice that its rows no longer follow the pool
+void psh_sort_dynamic(void* hp, int descending) {
+    auto* h = (Harness*)hp;
+    if (descending) h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a > b; });
+    else h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a < b; });
+}
+
 int psh_add_collider(void* hp, int e, const float* lpos, const float* lquat, int type, const float* params, int mesh, const float* material, int flags, int data) {
     auto* h = (Harness*)hp;
     h->scene->addCollider(h->entities[e], makeCollider(h, lpos, lquat, type, params, mesh, material, flags, data));

@@ -22,7 +22,7 @@ EXPORTS = [
     "psh_add_collider", "psh_clear_colliders", "psh_add_joint", "psh_set_revolute_drive", "psh_destroy_joint", "psh_set_params",
     "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter", "psh_record_trigger_events",
     "psh_take_trigger_events", "psh_set_state", "psh_simulate", "psh_num_entities", "psh_get_state", "psh_native_context",
-    "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity", "psh_raycast", "psh_overlap",
+    "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity", "psh_raycast", "psh_overlap", "psh_sort_dynamic",
 ]
 
 _lib = None
@@ -46,7 +46,7 @@ def load_library():
     lib.psh_simulate.restype = C.c_double
     lib.psh_native_context.restype = C.c_void_p
     for f in ("psh_set_params", "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter",
-              "psh_record_trigger_events", "psh_set_state", "psh_get_state", "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity"):
+              "psh_record_trigger_events", "psh_set_state", "psh_get_state", "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity", "psh_sort_dynamic"):
         getattr(lib, f).restype = None
     _lib = lib
     return lib
@@ -161,6 +161,10 @@ class HostScene:
 
     def destroy_entity(self, e):
         self.lib.psh_destroy_entity(self.h, int(e))
+
+    def sort_dynamic(self, descending=True):
+        """registry.sort<RigidBodyDynamicComponent> by entity id: the pool the body rows follow is reordered behind the Scene's back."""
+        self.lib.psh_sort_dynamic(self.h, int(descending))
 
     def add_collider(self, e, lpos, lquat, ctype, params, mesh=-1, material=(0.4, 0.2, 0.0), flags=2, data=0):
         """Scene::addCollider on a live entity (flags: bit 0 trigger, bit 1 enableSimulation)."""
