@@ -164,9 +164,9 @@ class RefScene:
     def destroy_entity(self, e):
         self.lib.ph_destroy_entity(self.h, int(e))
 
-    def sort_dynamic(self, descending=True):
-        """registry.sort<RigidBodyDynamicComponent> by entity id."""
-        self.lib.ph_sort_dynamic(self.h, int(descending))
+    def sort_dynamic(self, greater_first=True):
+        """registry.sort<RigidBodyDynamicComponent> by entity id, comparator a > b (True) / a < b (False); see scene_api.HostScene.sort_dynamic."""
+        self.lib.ph_sort_dynamic(self.h, int(greater_first))
 
     def add_collider(self, e, lpos, lquat, ctype, params, mesh=-1, material=(0.4, 0.2, 0.0), flags=2, data=0):
         """Scene::addCollider on a live entity (Physecs.cpp:738-751; flags: bit 0 trigger, bit 1 enableSimulation)."""

@@ -459,9 +459,9 @@ void ph_set_contact_filter(void* hp, int mode) {
 void ph_destroy_entity(void* hp, int e) { auto* h = (Harness*)hp; h->registry.destroy(h->entities[e]); }
 // the application reorders the dynamic-body pool (registry.sort): the reference indexes bodies by their CURRENT position in it every
 // step (Physecs.cpp:116-117), so nothing else has to follow
-void ph_sort_dynamic(void* hp, int descending) {
+void ph_sort_dynamic(void* hp, int greaterFirst) {     // EnTT iterates a pool back to front: a > b keeps a creation-ordered pool's packed order, a < b reverses it
     auto* h = (Harness*)hp;
-    if (descending) h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a > b; });
+    if (greaterFirst) h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a > b; });
     else h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a < b; });
 }
 void ph_destroy_joint(void* hp, int j) { auto* h = (Harness*)hp; h->scene->destroyJoint(h->joints[j]); h->joints[j] = nullptr; }

@@ -147,9 +147,9 @@ int psh_destroy_entity(void* hp, int e) {
 }
 
 // registry.sort on the dynamic-body pool: the Scene has to notice that its rows no longer follow the pool
-void psh_sort_dynamic(void* hp, int descending) {
+void psh_sort_dynamic(void* hp, int greaterFirst) {     // EnTT iterates a pool back to front: a > b keeps a creation-ordered pool's packed order, a < b reverses it
     auto* h = (Harness*)hp;
-    if (descending) h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a > b; });
+    if (greaterFirst) h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a > b; });
     else h->registry.sort<physecs::RigidBodyDynamicComponent>([](const entt::entity a, const entt::entity b) { return a < b; });
 }
 

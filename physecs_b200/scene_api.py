@@ -32,14 +32,7 @@ def available():
     return os.path.exists(LIB_PATH)
 
 
-def load_library():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: build it with `python build.py` where EnTT and GLM headers are available")
-    capi.load_library()   # libphysecs_b200.so first (the scene library links against it)
-    lib = C.CDLL(LIB_PATH)
+def _declare(lib):
     lib.psh_create.restype = C.c_void_p
     lib.psh_destroy.restype = None
     lib.psh_last_error.restype = C.c_char_p
@@ -48,8 +41,24 @@ def load_library():
     for f in ("psh_set_params", "psh_set_can_collide", "psh_set_kinematic", "psh_set_sync_mode", "psh_set_contact_filter",
               "psh_record_trigger_events", "psh_set_state", "psh_get_state", "psh_get_stats", "psh_mass_props", "psh_set_arena_capacity", "psh_sort_dynamic"):
         getattr(lib, f).restype = None
-    _lib = lib
     return lib
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python build.py` where EnTT and GLM headers are available")
+    capi.load_library()   # libphysecs_b200.so first (the scene library links against it)
+    _lib = _declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def load_other_build(path):
+    """The same harness entry points from another build of the host layer (tests/abi_recorder: the host layer linked against a recording
+    double of the C ABI, for the CPU tests of the host's bookkeeping).  Never used by the product path."""
+    return _declare(C.CDLL(path))
 
 
 def _p(a, ct=C.c_float):
@@ -71,8 +80,8 @@ class SceneError(RuntimeError):
 class HostScene:
     """physecs::Scene (this repo's) over a registry filled from a SceneDesc, entity id == description index."""
 
-    def __init__(self, desc, num_threads=0, device=0):
-        self.lib = load_library()
+    def __init__(self, desc, num_threads=0, device=0, lib=None):
+        self.lib = lib if lib is not None else load_library()
         self.desc = desc
         self.h = C.c_void_p(self.lib.psh_create(int(num_threads), int(device)))
         d = desc
@@ -162,9 +171,11 @@ class HostScene:
     def destroy_entity(self, e):
         self.lib.psh_destroy_entity(self.h, int(e))
 
-    def sort_dynamic(self, descending=True):
-        """registry.sort<RigidBodyDynamicComponent> by entity id: the pool the body rows follow is reordered behind the Scene's back."""
-        self.lib.psh_sort_dynamic(self.h, int(descending))
+    def sort_dynamic(self, greater_first=True):
+        """registry.sort<RigidBodyDynamicComponent> by entity id with the comparator a > b (True) or a < b (False).  EnTT iterates a pool back
+        to front: a > b leaves a pool filled in creation order as it is, a < b REVERSES its packed order -- the order the body rows follow --
+        behind the Scene's back (no signal fires)."""
+        self.lib.psh_sort_dynamic(self.h, int(greater_first))
 
     def add_collider(self, e, lpos, lquat, ctype, params, mesh=-1, material=(0.4, 0.2, 0.0), flags=2, data=0):
         """Scene::addCollider on a live entity (flags: bit 0 trigger, bit 1 enableSimulation)."""

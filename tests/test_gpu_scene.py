@@ -154,15 +154,12 @@ def test_scene_collider_cleared_and_added_again():
 def test_scene_dynamic_pool_reordered():
     """registry.sort on the RigidBodyDynamicComponent pool between two steps: no signal fires, the reference simply indexes bodies by
     their new position (Physecs.cpp:116-117) -- the Scene has to notice that its rows no longer follow the pool and re-upload (joints
-    and contacts included: ragdolls resting on the ground)."""
+    and contacts included: ragdolls on the ground).  EnTT iterates a pool back to front, so the comparator `a > b` (True) leaves a pool
+    filled in creation order as it is and `a < b` (False) reverses its packed order: step 18 is the no-op, step 30 the reversal."""
     d = S.ragdolls(5)
     ops = {18: lambda s: s.sort_dynamic(True), 30: lambda s: s.sort_dynamic(False)}
     r = run_scene(d, 44, ops=ops)
     assert r["worst"] == 0.0 and r["manifolds"] > 0
-    d = S.mixed_bin(300, spacing=0.8)
-    d.col_material[:, 1] = 0.3
-    r = run_scene(d, 40, ops={27: lambda s: s.sort_dynamic(True)})
-    assert r["worst"] == 0.0 and r["manifolds"] > 100
 
 
 def test_scene_joint_edits():
