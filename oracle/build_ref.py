@@ -149,6 +149,22 @@ def patch_tree(root, hashfix):
     wr(p, s)
 
 
+def stage_tree(hashfix=False):
+    """Copy of the reference's src/ + include/ under the scratch dir with the portability patch applied (no compile); returns its root.
+    Also used by tests/test_cpu_dropin.py to build examples/dropin_app.cpp against the reference's own headers."""
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, "shim.h"), "w") as f:
+        f.write(SHIM)
+    root = os.path.join(BUILD, "ref" + ("_hashfix" if hashfix else ""))
+    if os.path.isdir(root):
+        shutil.rmtree(root)
+    os.makedirs(root)
+    shutil.copytree(os.path.join(REF, "src"), os.path.join(root, "src"))
+    shutil.copytree(os.path.join(REF, "include"), os.path.join(root, "include"))
+    patch_tree(root, hashfix)
+    return root
+
+
 def build(verbose=True):
     if not os.path.isdir(REF):
         raise RuntimeError(f"reference tree not found at {REF}")
@@ -161,13 +177,7 @@ def build(verbose=True):
     harness = os.path.join(HERE, "ref_harness.cpp")
     jobs = []
     for variant, hashfix in (("", False), ("_hashfix", True)):
-        root = os.path.join(BUILD, "ref" + variant)
-        if os.path.isdir(root):
-            shutil.rmtree(root)
-        os.makedirs(root)
-        shutil.copytree(os.path.join(REF, "src"), os.path.join(root, "src"))
-        shutil.copytree(os.path.join(REF, "include"), os.path.join(root, "include"))
-        patch_tree(root, hashfix)
+        root = stage_tree(hashfix)
         srcs = []
         for dp, _, fns in os.walk(os.path.join(root, "src")):
             for fn in fns:
