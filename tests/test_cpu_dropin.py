@@ -11,10 +11,11 @@ import subprocess
 
 import pytest
 
-import build as product_build
 from oracle import build_ref
 from oracle import ref as R
 from tests.abi_recorder import build as recorder_build
+
+product_build = recorder_build.product_build      # the repo's build.py (include paths of EnTT / GLM)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 APP = os.path.join(ROOT, "examples", "dropin_app.cpp")
