@@ -29,6 +29,7 @@ struct pb_ctx {
     int nConvex = 0, nTrimesh = 0, nFilterClasses = 0;
     float *outPos = nullptr, *outQuat = nullptr, *outVel = nullptr, *outAng = nullptr;
     int chunks = 1;
+    int failSteps = 0; bool failed = false; int needPairs = 0, needManifolds = 0;     // pbr_fail_next_steps: steps that overflow an arena
 };
 
 static int fail(pb_ctx* c, int code, const char* msg) { c->error = msg; return code; }
@@ -136,11 +137,16 @@ int pb_set_static_poses(pb_ctx* c, int nStatic, const float* p, const float* q) 
 int pb_step_begin(pb_ctx*) { return PB_OK; }
 int pb_step_narrowphase(pb_ctx*) { return PB_OK; }
 int pb_step(pb_ctx* c, float, int, int, float) {
+    // an arena overflow as the device reports it: the step leaves the scene as it was, the status arrives with the next call that
+    // synchronises with it (the read-back), the counters say how much room the step needs (needPairs < 0: a failure no arena explains)
+    c->failed = false;
+    if (c->failSteps > 0 && (c->needPairs < 0 || c->caps.max_pairs < c->needPairs || c->caps.max_manifolds < c->needManifolds)) { --c->failSteps; c->failed = true; return PB_OK; }
     for (int r = 0; r < c->nDyn; ++r) if (!c->kinematic[r]) c->pos[3 * (size_t)r] += 1.f;       // the visible trace of a "step"
     ++c->steps;
     return PB_OK;
 }
 int pb_get_state_begin(pb_ctx* c, float* p, float* q, float* v, float* w, int chunks) {
+    if (c->failed) return fail(c, PB_ECAPACITY, "per-step arena overflow (recorded)");
     std::copy(c->pos.begin(), c->pos.begin() + 3 * (size_t)c->nDyn, p); std::copy(c->quat.begin(), c->quat.begin() + 4 * (size_t)c->nDyn, q);
     std::copy(c->vel.begin(), c->vel.end(), v); std::copy(c->ang.begin(), c->ang.end(), w);
     c->chunks = std::max(1, std::min(chunks, 32));
@@ -153,7 +159,11 @@ int pb_get_state_wait(pb_ctx* c, int chunk, int* first, int* count) {
     *first = f; *count = std::min(per, c->nDyn - f);
     return PB_OK;
 }
-int pb_get_counts(pb_ctx*, pb_counts* out) { std::memset(out, 0, sizeof *out); return PB_OK; }
+int pb_get_counts(pb_ctx* c, pb_counts* out) {
+    std::memset(out, 0, sizeof *out);
+    if (c->failed) { out->n_pairs = std::max(c->needPairs, 0); out->n_manifolds = std::max(c->needManifolds, 0); out->status = PB_ECAPACITY; }
+    return PB_OK;
+}
 int pb_get_timings(pb_ctx*, pb_timings* out) { std::memset(out, 0, sizeof *out); return PB_OK; }
 int pb_get_manifolds(pb_ctx*, int, int*, int*, float*, float*, int*, int* n) { *n = 0; return PB_OK; }
 int pb_get_triggers(pb_ctx*, int*, int, int* n) { *n = 0; return PB_OK; }
@@ -172,6 +182,8 @@ int pbr_counts(pb_ctx* c, int* out8) {
     out8[6] = (int)c->noCollide.size() / 2; out8[7] = c->nFilterClasses;
     return PB_OK;
 }
+void pbr_fail_next_steps(pb_ctx* c, int n, int needPairs, int needManifolds) { c->failSteps = n; c->needPairs = needPairs; c->needManifolds = needManifolds; }
+void pbr_caps(pb_ctx* c, int* out5) { out5[0] = c->caps.max_bodies; out5[1] = c->caps.max_colliders; out5[2] = c->caps.max_pairs; out5[3] = c->caps.max_manifolds; out5[4] = c->caps.max_joints; }
 void pbr_rows(pb_ctx* c, int* entity) { std::copy(c->entity.begin(), c->entity.end(), entity); }
 void pbr_colliders(pb_ctx* c, int* row, int* idx, int* type, float* tag2) {
     for (int i = 0; i < c->nCol; ++i) { row[i] = c->colRow[i]; idx[i] = c->colIdx[i]; type[i] = c->colType[i]; tag2[2 * i] = c->bounds[6 * (size_t)i]; tag2[2 * i + 1] = c->bounds[6 * (size_t)i + 1]; }

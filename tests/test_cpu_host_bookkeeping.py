@@ -227,3 +227,59 @@ def test_kinematic_body_is_not_written_back():
     others = np.array([x for x in d.dynamic_entities() if x != e])
     assert _moved(p[others], d.pos[others], 2)
     r.close()
+
+
+def test_arena_overflow_grows_the_arenas_and_runs_the_step_again():
+    """pb_step only enqueues; an overflowing arena is reported by the read-back (PB_ECAPACITY) with the counters saying what the step needs.
+    Scene::simulate enlarges the arenas in place and runs the step again -- once, not once per missing entry."""
+    d = S.mixed_bin(50, spacing=0.8)
+    r = Recorded(d)
+    caps = (C.c_int * 5)()
+    r.rec.pbr_caps(r.ctx, caps)
+    pairs0, man0 = caps[2], caps[3]
+    r.rec.pbr_fail_next_steps(r.ctx, 5, pairs0 * 3, man0 + 10)
+    r.hs.simulate()
+    r.rec.pbr_caps(r.ctx, caps)
+    assert caps[2] >= pairs0 * 3 and caps[3] >= man0 + 10
+    c = r.counts()
+    assert c["steps"] == 2 and c["uploads"] == 1            # the first step and the repeated one; the scene was not re-uploaded
+    p = r.hs.get_state()[0]
+    dyn = d.dynamic_entities()
+    assert _moved(p[dyn], d.pos[dyn], 2)                    # the failed attempt moved nothing
+    r.close()
+
+
+def test_a_failure_no_arena_explains_is_reported_not_retried():
+    d = S.mixed_bin(20, spacing=0.8)
+    r = Recorded(d)
+    r.rec.pbr_fail_next_steps(r.ctx, 100, -1, -1)           # PB_ECAPACITY with the counters inside the arenas: nothing to grow
+    with pytest.raises(scene_api.SceneError, match="recorded"):
+        r.hs.simulate()
+    assert r.counts()["steps"] == 1                         # one attempt, no blind retries
+    r.rec.pbr_fail_next_steps(r.ctx, 0, 0, 0)
+    r.hs.simulate()                                         # ... and the Scene is usable afterwards
+    assert r.counts()["steps"] == 2
+    r.close()
+
+
+def test_contact_filter_table_and_noncolliding_pairs():
+    d = S.trigger_zoo(60)
+    r = Recorded(d)
+    assert r.counts()["filter_classes"] == 0                # defaultContactFilter: no table
+    r.hs.set_contact_filter(1)
+    r.hs.simulate()
+    classes = {(int(f) & 1, int(x)) for f, x in zip(d.col_flags, d.col_data)}
+    assert r.counts()["filter_classes"] == len(classes)     # one class per (isTrigger, data) present in the scene
+    n0 = r.counts()["no_collide"]
+    dyn = d.dynamic_entities()
+    r.hs.set_can_collide(int(dyn[0]), int(dyn[1]), False)
+    r.hs.set_can_collide(int(dyn[1]), int(dyn[0]), False)   # the same pair the other way round
+    r.hs.simulate()
+    assert r.counts()["no_collide"] == n0 + 1
+    r.hs.set_can_collide(int(dyn[0]), int(dyn[1]), True)
+    # a spawn re-uploads the colliders: the per-collider class table has to follow
+    r.hs.add_entities(S.dynamic_only(S.mixed_bin(3, spacing=0.8, seed=0x99), lift=(0.0, 6.0, 0.0)))
+    r.hs.simulate()
+    c = r.counts()
+    assert c["no_collide"] == n0 and c["filter_classes"] >= len(classes) and c["uploads"] == 2
+    r.close()
