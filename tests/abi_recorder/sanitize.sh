@@ -1,6 +1,6 @@
 #!/bin/bash
 # ThreadSanitizer and Address/UB-Sanitizer runs of the host layer's structural-edit path over the recording double (no device needed).
-#   bash tests/abi_recorder/sanitize.sh          (needs the EnTT / GLM headers: PHYSECS_ENTT_INCLUDE / PHYSECS_GLM_INCLUDE or /root/reference)
+#   bash tests/abi_recorder/sanitize.sh [bodies]  (needs the EnTT / GLM headers: PHYSECS_ENTT_INCLUDE / PHYSECS_GLM_INCLUDE or /root/reference)
 set -e
 cd "$(dirname "$0")/../.."
 REF=${PHYSECS_REFERENCE:-/root/reference}
@@ -13,5 +13,5 @@ for SAN in thread address,undefined; do
     g++ -std=c++17 -O1 -g -fsanitize=$SAN -fno-omit-frame-pointer -Wno-comment -ffp-contract=off -DGLM_FORCE_INLINE -I include/Physecs -I include/Physecs/Joints -I include \
         -I "$GLM" -I "$ENTT" physecs_b200/host/{Scene,Meshes,MassUtil,scene_harness}.cpp tests/abi_recorder/pb_recorder.cpp tests/abi_recorder/sanitize_driver.cpp -o $BIN -lpthread
     echo "== -fsanitize=$SAN"
-    TSAN_OPTIONS=halt_on_error=1 ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1 $BIN
+    TSAN_OPTIONS=halt_on_error=1 ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1 $BIN ${1:-30000}
 done

@@ -40,9 +40,9 @@ static void step(void* h, const char* what) {
     if (psh_simulate(h, 1.f / 60.f) < 0) { std::fprintf(stderr, "simulate failed after %s: %s\n", what, psh_last_error(h)); std::exit(1); }
 }
 
-int main() {
+int main(int argc, char** argv) {
     void* h = psh_create(6, 0);
-    const int N = 30000;
+    const int N = argc > 1 ? std::atoi(argv[1]) : 30000;      // from 65 536 bodies the gather / upload / read-back runs in 8 chunks, poses before velocities
     add(h, 50, 0, -1000.f);             // statics
     int first = add(h, N, 2, 0.f);      // dynamics
     step(h, "build");
