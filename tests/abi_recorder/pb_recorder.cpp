@@ -159,6 +159,15 @@ int pb_get_state_wait(pb_ctx* c, int chunk, int* first, int* count) {
     *first = f; *count = std::min(per, c->nDyn - f);
     return PB_OK;
 }
+int pb_sync(pb_ctx*) { return PB_OK; }
+int pb_get_state(pb_ctx* c, float* p, float* q, float* v, float* w) {
+    if (c->failed) return fail(c, PB_ECAPACITY, "per-step arena overflow (recorded)");
+    if (p) std::copy(c->pos.begin(), c->pos.begin() + 3 * (size_t)c->nDyn, p);
+    if (q) std::copy(c->quat.begin(), c->quat.begin() + 4 * (size_t)c->nDyn, q);
+    if (v) std::copy(c->vel.begin(), c->vel.end(), v);
+    if (w) std::copy(c->ang.begin(), c->ang.end(), w);
+    return PB_OK;
+}
 int pb_get_counts(pb_ctx* c, pb_counts* out) {
     std::memset(out, 0, sizeof *out);
     if (c->failed) { out->n_pairs = std::max(c->needPairs, 0); out->n_manifolds = std::max(c->needManifolds, 0); out->status = PB_ECAPACITY; }
