@@ -9,6 +9,8 @@
 #include <Physecs/Joints/RevoluteJoint.h>
 #include <Physecs/Joints/SphericalJoint.h>
 #include <Physecs/Joints/FixedJoint.h>
+#include <Physecs/ConvexMesh.h>
+#include <Physecs/TriangleMesh.h>
 #include <Transform.h>
 #ifdef DROPIN_WITH_CHARACTER_CONTROLLER
 #include <CharacterController.h>       // the reference's own file, unchanged
@@ -44,6 +46,39 @@ entt::entity spawn(entt::registry& registry, glm::vec3 position, physecs::Geomet
     return e;
 }
 
+// a unit cube as a convex mesh: vertices + faces (indices, outward normal, centroid), as the reference's ConvexMesh wants them
+physecs::ConvexMesh makeCubeHull() {
+    std::vector<glm::vec3> v;
+    for (int i = 0; i < 8; ++i) v.emplace_back((i & 1) ? 0.5f : -0.5f, (i & 2) ? 0.5f : -0.5f, (i & 4) ? 0.5f : -0.5f);
+    const int quads[6][4] = { { 0, 4, 6, 2 }, { 1, 3, 7, 5 }, { 0, 1, 5, 4 }, { 2, 6, 7, 3 }, { 0, 2, 3, 1 }, { 4, 5, 7, 6 } };
+    const glm::vec3 normals[6] = { { -1, 0, 0 }, { 1, 0, 0 }, { 0, -1, 0 }, { 0, 1, 0 }, { 0, 0, -1 }, { 0, 0, 1 } };
+    std::vector<physecs::ConvexMeshFace> faces;
+    for (int f = 0; f < 6; ++f) {
+        physecs::ConvexMeshFace face;
+        glm::vec3 c(0);
+        for (int k = 0; k < 4; ++k) { face.indices.push_back(quads[f][k]); c += v[quads[f][k]]; }
+        face.normal = normals[f];
+        face.centroid = c / 4.f;
+        faces.push_back(face);
+    }
+    return physecs::ConvexMesh(std::move(v), std::move(faces));
+}
+
+// a bumpy 12 x 12 patch of triangles
+physecs::TriangleMesh makePatch(glm::vec3 origin) {
+    const int n = 12;
+    std::vector<glm::vec3> v;
+    std::vector<unsigned int> idx;
+    for (int z = 0; z <= n; ++z)
+        for (int x = 0; x <= n; ++x) v.push_back(origin + glm::vec3(x * 0.5f, 0.1f * ((x * 7 + z * 3) % 5), z * 0.5f));
+    for (int z = 0; z < n; ++z)
+        for (int x = 0; x < n; ++x) {
+            unsigned a = z * (n + 1) + x, b = a + 1, c = a + n + 1, d = c + 1;
+            idx.insert(idx.end(), { a, c, b, b, c, d });
+        }
+    return physecs::TriangleMesh(v, idx);
+}
+
 } // namespace
 
 int main() {
@@ -63,6 +98,21 @@ int main() {
     for (int i = 0; i < 24; ++i)
         bodies.push_back(spawn(registry, glm::vec3((i % 6) * 1.5f - 4.f, 0.6f + (i / 6) * 1.2f, (i % 3) * 0.1f), i % 3 == 0 ? box : i % 3 == 1 ? ball : pill, true));
     auto sensor = spawn(registry, glm::vec3(0, 0.5f, 0), box, false, true, 1);
+
+    // user-owned meshes (Colliders.h:24-31: raw pointers that must outlive the Scene): hulls dropped onto a triangle-mesh patch
+    physecs::ConvexMesh cube = makeCubeHull();
+    physecs::TriangleMesh patch = makePatch(glm::vec3(30, 0, 30));
+    physecs::Geometry hull = { physecs::CONVEX_MESH };       hull.convex = { &cube, glm::vec3(0.8f, 0.6f, 0.8f) };
+    physecs::Geometry terrain = { physecs::TRIANGLE_MESH };  terrain.triangleMesh = { &patch };
+    spawn(registry, glm::vec3(0, 0, 0), terrain, false);
+    std::vector<entt::entity> onPatch;
+    for (int i = 0; i < 6; ++i) onPatch.push_back(spawn(registry, glm::vec3(31.f + i * 0.9f, 1.2f, 32.f + (i % 2)), i % 2 ? hull : ball, true));
+    // the triangle mesh as the application sees it: post-build triangle order and BVH (TriangleMesh.h: public members)
+    unsigned long long meshPrint = 1469598103934665603ull;
+    for (auto& t : patch.triangles) for (unsigned k : t.indices) { meshPrint ^= k; meshPrint *= 1099511628211ull; }
+    for (auto& nd : patch.bvh) { meshPrint ^= (unsigned)nd.triCount * 977u + (unsigned)nd.index; meshPrint *= 1099511628211ull; }
+    std::printf("mesh: %zu triangles %zu nodes order %016llx, %zu hit by a query box\n", patch.triangles.size(), patch.bvh.size(), meshPrint,
+                patch.overlapBvh({ glm::vec3(31, -1, 31), glm::vec3(32.2f, 1, 32.2f) }).size());
 
     Events events;
     scene.addOnTriggerEnterCallback(&events);
@@ -108,6 +158,9 @@ int main() {
     scene.removeOnTriggerEnterCallback(&events);
     scene.removeOnTriggerExitCallback(&events);
 
+    float patchLowest = 1e9f;
+    for (auto e : onPatch) patchLowest = std::min(patchLowest, registry.get<TransformComponent>(e).position.y);
+    std::printf("on the patch: lowest y %.3f\n", patchLowest);
     float lowest = 1e9f;
     for (auto e : bodies) if (e != entt::null) lowest = std::min(lowest, registry.get<TransformComponent>(e).position.y);
     std::printf("bodies %zu lowest y %.3f ray hit %d (y %.3f) filtered ray hit %d overlaps %zu mtd rows %zu trigger enter %d exit %d contacts %zu\n",

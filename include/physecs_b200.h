@@ -37,7 +37,7 @@ enum {
 
 /* geometry types == physecs::GeometryType (reference include/Physecs/Colliders.h:9) */
 enum { PB_SPHERE = 0, PB_CAPSULE = 1, PB_BOX = 2, PB_CONVEX_MESH = 3, PB_TRIANGLE_MESH = 4 };
-/* joint types (reference include/Physecs/Joints/*.h) */
+/* joint types (reference include/Physecs/Joints/<Type>Joint.h) */
 enum { PB_JOINT_FIXED = 0, PB_JOINT_REVOLUTE = 1, PB_JOINT_SPHERICAL = 2, PB_JOINT_UNIVERSAL = 3,
        PB_JOINT_PRISMATIC = 4, PB_JOINT_GEAR = 5, PB_JOINT_SERVO = 6 };
 /* collider flag bits */
@@ -129,7 +129,7 @@ int pb_build_trimesh(const float* verts3, int n_verts, const unsigned* indices, 
 int pb_upload_joints(pb_ctx* ctx, int n, const int* type, const int* body_row0, const int* body_row1,
                      const float* anchor0_pos3, const float* anchor0_quat4, const float* anchor1_pos3,
                      const float* anchor1_quat4, const float* params8, const int* color);
-/* new parameters of the uploaded joints after a setter call on a live joint (reference Joints/*.cpp setters); same
+/* new parameters of the uploaded joints after a setter call on a live joint (reference Joints/<Type>Joint.cpp setters); same
  * layout and joint order as pb_upload_joints; accumulated impulses and gear angle state are kept */
 int pb_update_joint_params(pb_ctx* ctx, int n, const float* params8);
 /* after a re-upload: old_index[j] = position joint j had in the previous pb_upload_joints call (-1 = new joint);

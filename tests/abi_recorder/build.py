@@ -30,11 +30,12 @@ def build():
     inc = os.path.join(ROOT, "include")
     srcs = [os.path.join(host, f) for f in product_build.HOST_SRC]
     rec_src = os.path.join(HERE, "pb_recorder.cpp")
-    deps = srcs + [rec_src, os.path.abspath(__file__), os.path.join(inc, "physecs_b200.h")] + \
+    tri_src = os.path.join(ROOT, "physecs_b200", "csrc", "trimesh_build.cpp")      # setup-time host code of the product: the triangle-mesh BVH build
+    deps = srcs + [rec_src, tri_src, os.path.abspath(__file__), os.path.join(inc, "physecs_b200.h")] + \
            [os.path.join(dp, f) for dp, _, fns in os.walk(os.path.join(inc, "Physecs")) for f in fns]
     if os.path.exists(RECORDER) and os.path.exists(SCENE) and all(os.path.getmtime(d) <= min(os.path.getmtime(RECORDER), os.path.getmtime(SCENE)) for d in deps):
         return RECORDER, SCENE
-    _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-comment", rec_src, "-o", RECORDER])
+    _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", rec_src, tri_src, "-o", RECORDER])
     _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DGLM_FORCE_INLINE", "-I", os.path.join(inc, "Physecs"),
           "-I", os.path.join(inc, "Physecs", "Joints"), "-I", inc, "-I", glm, "-I", entt] + srcs +
          ["-o", SCENE, "-L", OUT, "-lpb_recorder", "-Wl,-rpath,$ORIGIN", "-lpthread"])

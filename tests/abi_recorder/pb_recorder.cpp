@@ -7,6 +7,7 @@
 // collider i the tag (k, i); pb_move_rows re-tags with k = -1.  Only tests/ builds or loads this file (tests/abi_recorder/build.py);
 // the product libraries never see it.
 #include "../../include/physecs_b200.h"
+#include "../../physecs_b200/csrc/trimesh_build.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -72,7 +73,17 @@ int pb_upload_colliders(pb_ctx* c, int n, const int* row, const int* idx, const 
 }
 int pb_register_convex(pb_ctx* c, const float*, int, const int*, const int*, int, const float*, const float*, int* h) { *h = c->nConvex++; return PB_OK; }
 int pb_register_trimesh(pb_ctx* c, const float*, int, const unsigned*, int, int* h, int*) { *h = c->nTrimesh++; return PB_OK; }
-int pb_build_trimesh(const float*, int, const unsigned*, int, unsigned*, int*, float*, int*, int*) { return PB_EUNSUPPORTED; }
+// setup-time HOST code of the product (csrc/trimesh_build.cpp, no device involved): the double forwards to it like capi.cu does
+int pb_build_trimesh(const float* verts3, int nVerts, const unsigned* indices, int nIndices, unsigned* triIdx, int* triOrig, float* nodeBounds6, int* nodeCountIndex2, int* nNodes) {
+    PbHostTriMesh h;
+    pb_build_trimesh_host(verts3, nVerts, indices, nIndices, h);
+    if (triIdx) std::memcpy(triIdx, h.triIdx.data(), sizeof(unsigned) * h.triIdx.size());
+    if (triOrig) std::memcpy(triOrig, h.triOrig.data(), sizeof(int) * h.triOrig.size());
+    if (nodeBounds6) std::memcpy(nodeBounds6, h.nodeBounds.data(), sizeof(float) * h.nodeBounds.size());
+    if (nodeCountIndex2) std::memcpy(nodeCountIndex2, h.nodeCountIndex.data(), sizeof(int) * h.nodeCountIndex.size());
+    if (nNodes) *nNodes = h.nNodes;
+    return PB_OK;
+}
 int pb_upload_joints(pb_ctx* c, int n, const int* type, const int* r0, const int* r1, const float*, const float*, const float*, const float*, const float*, const int* color) {
     if (n > c->caps.max_joints) return fail(c, PB_ECAPACITY, "max_joints");
     c->jointType.assign(type, type + n); c->jointRow0.assign(r0, r0 + n); c->jointRow1.assign(r1, r1 + n); c->jointColor.assign(color, color + n);

@@ -85,8 +85,9 @@ def test_batch_driver_under_thread_sanitizer(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     rec = os.path.join(root, "tests", "abi_recorder")
     exe = str(tmp_path / "batch_tsan")
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-Wno-comment", "-I", os.path.join(rec, "stub"),
-           os.path.join(root, "physecs_b200", "csrc", "batch.cpp"), os.path.join(rec, "pb_recorder.cpp"), os.path.join(rec, "sanitize_batch_driver.cpp"),
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-I", os.path.join(rec, "stub"),
+           os.path.join(root, "physecs_b200", "csrc", "batch.cpp"), os.path.join(rec, "pb_recorder.cpp"), os.path.join(root, "physecs_b200", "csrc", "trimesh_build.cpp"),
+           os.path.join(rec, "sanitize_batch_driver.cpp"),
            "-o", exe, "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode and b"tsan" in r.stdout.lower():

@@ -37,8 +37,10 @@ def _summary(out):
             "enter": int(line[line.index("enter") + 1]), "exit": int(line[line.index("exit") + 1])}
 
 
-@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
-def test_app_builds_and_runs_against_the_reference():
+@pytest.fixture(scope="module")
+def reference_run():
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
     entt, glm = product_build.find_ecs_includes()
     root = build_ref.stage_tree(False)
     os.makedirs(SCRATCH, exist_ok=True)
@@ -48,12 +50,11 @@ def test_app_builds_and_runs_against_the_reference():
           "-include", os.path.join(build_ref.BUILD, "shim.h"), "-I", os.path.join(root, "include"), "-I", os.path.join(root, "include", "Physecs"),
           "-I", os.path.join(root, "include", "Physecs", "Joints"), "-I", os.path.join(root, "src"), "-I", glm, "-I", entt, APP, "-o", exe,
           "-L", lib_dir, "-lphysecs_ref", "-Wl,-rpath," + lib_dir, "-lpthread"])
-    s = _summary(_run([exe]))
-    # the reference simulates: the bodies have come down onto the ground, the trigger volume has seen them
-    assert s["bodies"] == 25 and 0.0 < s["lowest_y"] < 0.6 and s["enter"] > 0 and s["overlaps"] > 0
+    return _run([exe])
 
 
-def test_app_and_reference_character_controller_build_against_the_drop_in_headers():
+@pytest.fixture(scope="module")
+def drop_in_run():
     built = recorder_build.build()
     assert built is not None
     entt, glm = product_build.find_ecs_includes()
@@ -63,19 +64,33 @@ def test_app_and_reference_character_controller_build_against_the_drop_in_header
     exe = os.path.join(SCRATCH, "dropin_b200")
     inc = os.path.join(ROOT, "include")
     out_dir = os.path.dirname(built[0])
-    _run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-Wno-comment", "-DGLM_FORCE_INLINE", "-DDROPIN_WITH_CHARACTER_CONTROLLER", "-I", inc,
+    _run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-DGLM_FORCE_INLINE", "-DDROPIN_WITH_CHARACTER_CONTROLLER", "-I", inc,
           "-I", os.path.join(inc, "Physecs"), "-I", os.path.join(inc, "Physecs", "Joints"), "-I", SCRATCH, "-I", glm, "-I", entt, APP,
           os.path.join(SCRATCH, "CharacterController.cpp"), "-o", exe, "-L", out_dir, "-lphysecs_b200_scene_recorder", "-lpb_recorder",
           "-Wl,-rpath," + out_dir, "-lpthread"])
-    s = _summary(_run([exe]))
+    return exe, _run([exe])
+
+
+def test_app_builds_and_runs_against_the_reference(reference_run):
+    s = _summary(reference_run)
+    # the reference simulates: the bodies have come down onto the ground, the trigger volume has seen them
+    assert s["bodies"] == 25 and 0.0 < s["lowest_y"] < 0.6 and s["enter"] > 0 and s["overlaps"] > 0
+
+
+def test_app_and_reference_character_controller_build_against_the_drop_in_headers(drop_in_run):
+    s = _summary(drop_in_run[1])
     # over the recording double nothing falls (its "step" only shifts x): the run proves the API surface, not the physics
     assert s["bodies"] == 25 and abs(s["lowest_y"] - 0.6) < 1e-6
 
 
-def test_without_a_device_the_application_gets_an_exception_not_a_cpu_path():
+def test_triangle_mesh_object_is_the_references(reference_run, drop_in_run):
+    """physecs::TriangleMesh as the application sees it (public members `triangles`, `bvh`, `overlapBvh`): post-build triangle order, node
+    table and query result of this repo's host object (csrc/trimesh_build.cpp) equal the reference's (TriangleMesh.cpp:99-192)."""
+    mesh = lambda out: [l for l in out.splitlines() if l.startswith("mesh: ")]
+    assert mesh(reference_run) and mesh(reference_run) == mesh(drop_in_run[1])
+
+
+def test_without_a_device_the_application_gets_an_exception_not_a_cpu_path(drop_in_run):
     """The real failure mode of way A without a GPU: Scene::simulate throws (pb_ctx_create fails); the double can play that too."""
-    exe = os.path.join(SCRATCH, "dropin_b200")
-    if not os.path.exists(exe):
-        pytest.skip("built by the test above")
-    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=dict(os.environ, PB_RECORDER_NO_DEVICE="1"))
+    r = subprocess.run([drop_in_run[0]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=dict(os.environ, PB_RECORDER_NO_DEVICE="1"))
     assert r.returncode != 0 and b"no CPU fallback" in r.stdout
