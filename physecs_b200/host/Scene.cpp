@@ -206,6 +206,7 @@ Scene::~Scene() {
 
 void Scene::onRigidBodyCreate(entt::registry& reg, entt::entity e) {
     impl->topologyDirty = true;
+    if (impl->ctxFresh) return;      // nothing is on the device yet: no history a new collider could inherit (a 1 M-entity initial fill skips 1 M set inserts)
     auto& c = reg.get<RigidBodyCollisionComponent>(e);
     for (int i = 0; i < (int)c.colliders.size(); ++i) impl->freshCols.insert(colKey(e, i));
 }
@@ -281,7 +282,7 @@ void Scene::clearColliders(entt::entity entity) {
 
 void Scene::addCollider(entt::entity entity, const Collider& collider) {
     auto& col = registry.get<RigidBodyCollisionComponent>(entity);
-    impl->freshCols.insert(colKey(entity, (int)col.colliders.size()));
+    if (!impl->ctxFresh) impl->freshCols.insert(colKey(entity, (int)col.colliders.size()));
     col.colliders.push_back(collider);
     impl->topologyDirty = true;
 }
