@@ -149,7 +149,7 @@ def test_no_device_means_failure_not_fallback():
 
 
 def test_product_does_not_import_oracle():
-    """The product package never references oracle/ (checker isolation)."""
+    """The product package never references oracle/ (checker isolation), nor the recording double of the C ABI under tests/."""
     import ast
     pkg = os.path.join(ROOT, "physecs_b200")
     for dp, _, fns in os.walk(pkg):
@@ -164,13 +164,16 @@ def test_product_does_not_import_oracle():
                     elif isinstance(node, ast.ImportFrom):
                         names = [node.module or ""]
                     assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{path} imports the oracle"
+                    assert not any(n == "tests" or n.startswith("tests.") for n in names), f"{path} imports test infrastructure"
                     if isinstance(node, ast.Constant) and isinstance(node.value, str) and node is not getattr(tree.body[0], "value", None):
                         assert "_ref/" not in node.value and "libphysecs_ref" not in node.value, f"{path} names an oracle artefact"
+                        assert "pb_recorder" not in node.value and "libphysecs_b200_scene_recorder" not in node.value, f"{path} names the test double of the C ABI"
             elif fn.endswith((".cu", ".cuh", ".h", ".cpp")):
                 for line in open(path, errors="replace"):
                     code = line.split("//")[0]
                     assert not ("#include" in code and "oracle" in code), f"{path} includes oracle code"
                     assert "libphysecs_ref" not in code, f"{path} names an oracle artefact"
+                    assert "pb_recorder" not in code and "abi_recorder" not in code, f"{path} names the test double of the C ABI"
 
 
 def test_scene_generators_are_deterministic():
