@@ -283,3 +283,39 @@ def test_contact_filter_table_and_noncolliding_pairs():
     c = r.counts()
     assert c["no_collide"] == n0 and c["filter_classes"] >= len(classes) and c["uploads"] == 2
     r.close()
+
+
+def test_outgrown_context_is_replaced_and_the_bounds_history_travels_through_the_host():
+    """A scene that outgrows max_bodies / max_colliders gets a new device context (capacities carry 50 % headroom): poses, velocities and
+    the bounds history are carried over (pb_get_bounds before, pb_set_bounds after), the contact cache starts empty (documented)."""
+    d = S.mixed_bin(300, spacing=0.8)
+    r = Recorded(d)
+    old_ctx = r.ctx.value
+    before = r.named_tags()
+    row0, idx0, _, _ = r.colliders()
+    dyn = d.dynamic_entities()
+    gone = [int(e) for e in dyn[[0, 1, 2]]]
+    for e in gone:
+        r.hs.destroy_entity(e)
+    extra = S.dynamic_only(S.mixed_bin(1500, spacing=0.8, seed=0x99), lift=(0.0, 30.0, 0.0))
+    first = r.hs.add_entities(extra)
+    r.hs.sort_dynamic(False)                                 # ... all of them: the pool is reversed as well
+    r.hs.simulate()
+    assert r.ctx.value != old_ctx or r.counts()["uploads"] == 1, "the context was expected to be replaced"
+    c = r.counts()
+    assert c["uploads"] == 1 and c["n_dyn"] == d.n_dynamic - 3 + 1500
+    now = r.named_tags()
+    survivors = {k for k in before if k[0] not in gone}
+    assert survivors <= set(now)
+    assert all(now[k] == before[k] for k in survivors), "a surviving collider lost its bounds history across the context change"
+    ent = r.rows()
+    row, idx, _, tag = r.colliders()
+    moved = [i for i in range(len(row)) if (int(ent[row[i]]), int(idx[i])) in survivors and int(tag[i][1]) != i]
+    assert len(moved) > 100, "the check above only means something where collider positions changed"
+    fresh = [i for i in range(len(row)) if (int(ent[row[i]]), int(idx[i])) not in survivors]
+    assert len(fresh) == 1500 and all(int(tag[i][0]) == 1 and int(tag[i][1]) == i for i in fresh)
+    assert len(r.carry_map(1)) == 0                          # no contact cache to re-key on a new context
+    p = r.hs.get_state()[0]
+    keep = np.array([e for e in dyn if int(e) not in gone])
+    assert _moved(p[keep], d.pos[keep], 2) and _moved(p[first:first + 1500], extra.pos, 1)
+    r.close()
